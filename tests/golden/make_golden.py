@@ -1,0 +1,594 @@
+"""Generate the golden fixtures in tests/golden/*.npz from the UNMODIFIED reference.
+
+Run in the build container (where /root/reference is mounted):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests and no golden vectors of its own, so the
+fixtures are outputs of the reference itself, run on CPU through oracle/refshim.py.
+The reference draws its own random numbers; every tensor it draws
+(`torch.distributions` standard-normal draws and `params_dist.sample`) is RECORDED and
+stored next to the outputs, so the oracle and the CUDA path are fed the identical noise.
+
+Fixtures that pass through the gpytorch / KDEpy stand-ins are tagged "shim-dependent"
+in MANIFEST.json (the stand-ins restate documented third-party behaviour).
+"""
+import hashlib
+import json
+import os
+import sys
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.distributions as dist
+import yaml
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle.refshim import REFERENCE_ROOT, ref_import  # noqa: E402
+
+disco = ref_import("controllers.disco")
+likelihoods = ref_import("inference.likelihoods")
+svgd_mod = ref_import("inference.svgd")
+svmpc_mod = ref_import("inference.svmpc")
+mpf_mod = ref_import("inference.mpf")
+base_kernels = ref_import("kernels.base_kernels")
+composite_kernels = ref_import("kernels.composite_kernels")
+pendulum_mod = ref_import("models.pendulum")
+particle_mod = ref_import("models.particle")
+from gpytorch.kernels import RBFKernel  # noqa: E402  (the shim's stand-in)
+
+torch.set_num_threads(1)
+MANIFEST = {}
+
+
+# ----------------------------------------------------------------------------------
+# noise recording
+# ----------------------------------------------------------------------------------
+class NoiseRecorder:
+    """Wraps torch.distributions' `_standard_normal` so every draw is kept."""
+
+    def __init__(self):
+        self.draws = []
+        self._mods = [torch.distributions.multivariate_normal, torch.distributions.normal]
+        self._orig = [m._standard_normal for m in self._mods]
+
+    def __enter__(self):
+        def wrapped(shape, dtype, device, _o=self._orig[0]):
+            x = _o(shape, dtype, device)
+            self.draws.append(x.detach().clone())
+            return x
+
+        for m in self._mods:
+            m._standard_normal = wrapped
+        return self
+
+    def __exit__(self, *exc):
+        for m, o in zip(self._mods, self._orig):
+            m._standard_normal = o
+
+
+class RecordingDist:
+    """A params_dist that remembers what it sampled (disco.py:168-174 contract)."""
+
+    def __init__(self, d):
+        self.d = d
+        self.samples = []
+
+    @property
+    def event_shape(self):
+        return self.d.event_shape
+
+    @property
+    def mean(self):
+        return self.d.mean
+
+    def sample(self, shape=torch.Size()):
+        x = self.d.sample(shape)
+        self.samples.append(x.detach().clone())
+        return x
+
+    def log_prob(self, x):
+        return self.d.log_prob(x)
+
+
+def save(name, tags=(), **arrays):
+    out = {}
+    for k, v in arrays.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **out)
+    MANIFEST[name] = {
+        "tags": list(tags),
+        "keys": {k: [str(v.dtype), list(v.shape)] for k, v in out.items()},
+        "bytes": os.path.getsize(path),
+    }
+    print(f"  wrote {name}.npz  {os.path.getsize(path)/1024:.1f} KiB")
+
+
+# ----------------------------------------------------------------------------------
+# configs (the reference's own yaml files, unchanged)
+# ----------------------------------------------------------------------------------
+with open(os.path.join(REFERENCE_ROOT, "demo", "pendulum_config.yaml")) as f:
+    PEND = yaml.load(f, yaml.FullLoader)
+with open(os.path.join(REFERENCE_ROOT, "demo", "particle_config.yaml")) as f:
+    PART = yaml.load(f, yaml.FullLoader)
+
+
+def pend_inst_cost(states, controls=None, n_pol=1, debug=None):
+    # the demo's cost (pendulum_example.py:21-28); lives in the demo script, not the package
+    theta, theta_d = states.chunk(2, dim=1)
+    return 50.0 * (theta.cos() - 1) ** 2 + 1.0 * theta_d ** 2
+
+
+def pend_term_cost(states, n_pol=1, debug=None):
+    return pend_inst_cost(states).squeeze()
+
+
+def make_pendulum(seed, kernel="rbf", params_sampling=True, n_pol=None, S=None, H=None, P=None,
+                  log_space=False):
+    ep = PEND["exp_params"]
+    torch.manual_seed(seed)
+    H = H or ep["horizon"]
+    N = n_pol or ep["n_particles"]
+    S = S or ep["action_samples"]
+    P = P or ep["params_samples"]
+    A = ep["ctrl_dim"]
+    model = pendulum_mod.PendulumModel(uncertain_params=("length", "mass"))
+    prior = svgd_mod.get_gmm(
+        torch.randn(N, H, A), torch.ones(N), ep["prior_sigma"] ** 2 * torch.eye(A)
+    )
+    theta0 = prior.sample([N])
+    dyn = dist.Independent(dist.Uniform(torch.tensor([0.6, 0.6]), torch.tensor([1.3, 1.3])), 1)
+    ctrl = disco.MultiDISCO(
+        observation_space=model.observation_space,
+        action_space=model.action_space,
+        hz_len=H,
+        n_policies=N,
+        action_samples=S,
+        params_samples=P,
+        temperature=1 / ep["alpha"],
+        a_cov=ep["ctrl_sigma"] ** 2 * torch.eye(A),
+        inst_cost_fn=pend_inst_cost,
+        term_cost_fn=pend_term_cost,
+        params_sampling=params_sampling,
+        params_log_space=log_space,
+    )
+    if kernel == "rbf":
+        k = RBFKernel()
+    else:
+        k = composite_kernels.iid_mp(
+            base_kernel=base_kernels.RBF(bandwidth=-1), ctrl_dim=A, indep_controls=True
+        )
+    lik = likelihoods.ExponentiatedUtility(ep["alpha"], n_samples=S, controller=ctrl, model=model)
+    sv = svmpc_mod.SVMPC(
+        init_particles=theta0.clone(),
+        prior=prior,
+        likelihood=lik,
+        kernel=k,
+        n_particles=N,
+        bw_scale=ep["bandwidth_scaling"],
+        n_steps=1,
+        optimizer_class=torch.optim.SGD,
+        lr=ep["learning_rate"],
+        weighted_prior=ep["weighted_prior"],
+    )
+    state = torch.as_tensor(ep["init_state"]).clone()
+    return dict(model=model, ctrl=ctrl, svmpc=sv, dyn=dyn, state=state, prior=prior, cfg=ep)
+
+
+def make_particle(seed, kernel="rbf", n_pol=None, S=None, H=None, P=None):
+    ep, env = PART["exp_params"], PART["env_params"]
+    torch.manual_seed(seed)
+    H = H or ep["horizon"]
+    N = n_pol or ep["n_particles"]
+    S = S or ep["action_samples"]
+    P = P or ep["params_samples"]
+    A = ep["ctrl_dim"]
+    prior = svgd_mod.get_gmm(
+        torch.randn(N, H, A), torch.ones(N), ep["prior_sigma"] ** 2 * torch.eye(A)
+    )
+    theta0 = prior.sample([N])
+    dyn_prior = dist.Normal(ep["dyn_prior_arg1"], ep["dyn_prior_arg2"])
+    sysk = {"uncertain_params": ["mass"], "mass": dyn_prior.mean}
+    model = particle_mod.Particle(**env, **sysk)
+    ctrl = disco.MultiDISCO(
+        model.observation_space,
+        model.action_space,
+        H,
+        N,
+        S,
+        temperature=1 / ep["alpha"],
+        a_cov=ep["ctrl_sigma"] ** 2 * torch.eye(A),
+        params_sampling=ep["sampling"],
+        params_samples=P,
+        params_log_space=ep["mpf_log_space"],
+        inst_cost_fn=model.default_inst_cost,
+        term_cost_fn=model.default_term_cost,
+    )
+    if kernel == "rbf":
+        k = RBFKernel()
+    else:
+        k = composite_kernels.iid_mp(
+            base_kernel=base_kernels.RBF(bandwidth=-1), ctrl_dim=A, indep_controls=True
+        )
+    lik = likelihoods.ExponentiatedUtility(ep["alpha"], controller=ctrl, model=model, n_samples=S)
+    sv = svmpc_mod.SVMPC(
+        init_particles=theta0.clone(),
+        prior=prior,
+        likelihood=lik,
+        kernel=k,
+        n_particles=N,
+        bw_scale=ep["bandwidth_scaling"],
+        n_steps=1,
+        optimizer_class=torch.optim.SGD,
+        lr=ep["learning_rate"],
+        weighted_prior=ep["weighted_prior"],
+    )
+    state = torch.as_tensor(env["init_state"], dtype=torch.float).clone()
+    return dict(model=model, ctrl=ctrl, svmpc=sv, dyn=dyn_prior, state=state, prior=prior,
+                cfg=ep, env=env)
+
+
+def prior_mu(prior):
+    return prior.component_distribution.base_dist.loc.detach().clone()
+
+
+def prior_mix(prior):
+    return prior.mixture_distribution.probs.detach().clone()
+
+
+# ----------------------------------------------------------------------------------
+# G0: obstacle map
+# ----------------------------------------------------------------------------------
+def gen_map():
+    print("G0 obstacle map")
+    w = make_particle(0)
+    m = w["model"].obst_map.map.astype(np.uint8)
+    sha = hashlib.sha1(m.tobytes()).hexdigest()
+    save(
+        "map_grid4x4",
+        packed=np.packbits(m.reshape(-1)),
+        shape=np.array(m.shape),
+        occupied=np.array(int(m.sum())),
+        c_offset=w["model"].obst_map.c_offset.numpy(),
+        cell_size=np.array(w["model"].obst_map.cell_size),
+    )
+    MANIFEST["map_grid4x4"]["sha1_uint8"] = sha
+    # a couple of other presets, to pin the generator (obstacle_map.py:101-224)
+    for preset, width in [("staggered_3-2-3", 2.0), ("grid_3x3", 1.5), ("single_centred", 3.0),
+                          ("staggered_4-3-4-3-4", 1.0), ("grid_6x6", 1.3)]:
+        om = ref_import("utils.obstacle_map")
+        params = om.get_obst_preset(preset, width)
+        mm = om.generate_obstacle_map([22, 22], params, 0.1, map_type="direct")
+        arr = mm.map.astype(np.uint8)
+        save(f"map_{preset}", packed=np.packbits(arr.reshape(-1)), shape=np.array(arr.shape),
+             occupied=np.array(int(arr.sum())), width=np.array(width))
+    # collision lookups at awkward coordinates (obstacle_map.py:64-93)
+    torch.manual_seed(5)
+    X = torch.cat([
+        (torch.rand(4000, 2) - 0.5) * 26.0,                     # includes out-of-map points
+        torch.tensor([[-11.0, -11.0], [10.99, 10.99], [11.0, 11.0], [0.0, 0.0], [-0.05, 0.05],
+                      [4.95, 4.95], [4.949999, 7.05], [7.05, 7.0500001], [-1e9, 1e9]]),
+        (torch.randint(-115, 115, (2000, 2)).float() / 10.0),   # exactly on cell boundaries
+    ])
+    c = w["model"].obst_map.get_collisions(X)
+    save("map_collisions", X=X, coll=c)
+
+
+# ----------------------------------------------------------------------------------
+# G1/G2: MultiDISCO.forward (+ step) on recorded noise
+# ----------------------------------------------------------------------------------
+def gen_forward(kind, seed, sub_s=8, **kw):
+    w = make_pendulum(seed, **kw) if kind == "pendulum" else make_particle(seed, **kw)
+    ctrl, model = w["ctrl"], w["model"]
+    theta = w["svmpc"].theta.detach().clone()
+    # a state away from the initial one so clamps / obstacles are exercised
+    torch.manual_seed(1000 + seed)
+    if kind == "pendulum":
+        state = torch.tensor([3.0, 0.0]) + torch.randn(2) * torch.tensor([0.5, 2.0])
+    else:
+        state = torch.tensor([-9.0, -9.0, 0.0, 0.0]) + torch.rand(4) * torch.tensor([9.0, 9.0, 2.0, 2.0])
+    S, N, H, A = ctrl.n_actions, ctrl.n_pol, ctrl.hz_len, ctrl.dim_a
+    sigma = ctrl.a_dist.covariance_matrix.diag().sqrt()
+    eps = torch.randn(S, N, H, A)
+    actions = theta + sigma * eps
+    if kind == "pendulum":
+        pd = RecordingDist(w["dyn"])
+    else:
+        # the particle demo samples masses from the MPF prior (log-space GMM over 50 particles)
+        x = dist.Normal(2.0, 0.1).sample([50, 1]).clamp(min=1e-6).log()
+        mix = dist.Categorical(torch.ones(50))
+        comp = dist.Independent(dist.MultivariateNormal(loc=x, covariance_matrix=0.04 * torch.eye(1)), 0)
+        pd = RecordingDist(dist.MixtureSameFamily(mix, comp))
+    c = deepcopy(ctrl)
+    a_mat0 = torch.randn(N, H, A)
+    c.a_mat = a_mat0.clone()
+    costs, states, acts, weights, plogp = c.forward(state, model, pd, actions)
+    out = dict(
+        state=state, theta=theta, eps=eps, sigma=sigma, actions=actions,
+        params=pd.samples[0] if pd.samples else np.zeros((0,)),
+        costs=costs, weights=weights, states_sub=states[:, :sub_s],
+        states_last=states[..., -1, :],
+        a_mat0=a_mat0, a_mat1=c.a_mat, a_mix1=c.a_mix,
+        params_log_p=plogp if plogp is not None else np.zeros((0,)),
+        temp=np.array(c.temp), H=np.array(H), N=np.array(N), S=np.array(S), A=np.array(A),
+        P=np.array(c.n_params), log_space=np.array(bool(c._params_log_space)),
+    )
+    # stand-alone controller step (disco.py:396-417)
+    for strat in ("argmax", "average"):
+        c2 = deepcopy(c)
+        nxt = c2.step(strategy=strat, steps=1)
+        out[f"step_{strat}_action"] = nxt.clone()
+        out[f"step_{strat}_a_seq"] = c2.a_seq
+        out[f"step_{strat}_a_mat"] = c2.a_mat
+    return out
+
+
+def gen_forward_all():
+    print("G1/G2 MultiDISCO.forward")
+    for seed in (0, 1, 2):
+        save(f"fwd_pendulum_s{seed}", **gen_forward("pendulum", seed))
+        save(f"fwd_particle_s{seed}", **gen_forward("particle", seed))
+    # P=1 / no parameter sampling (batched-pendulum shape: N=8,S=256,H=20)
+    save("fwd_pendulum_nops", **gen_forward("pendulum", 3, params_sampling=None, n_pol=8, S=256, H=20))
+    # internal action sampling (ext_actions=None, disco.py:157-160)
+    w = make_pendulum(7)
+    c = deepcopy(w["ctrl"])
+    c.a_mat = torch.randn(c.n_pol, c.hz_len, c.dim_a)
+    a_mat0 = c.a_mat.clone()
+    pd = RecordingDist(w["dyn"])
+    with NoiseRecorder() as rec:
+        costs, states, acts, weights, plogp = c.forward(w["state"], w["model"], pd)
+    save("fwd_pendulum_internal", state=w["state"], eps=rec.draws[0], a_mat0=a_mat0,
+         params=pd.samples[0], costs=costs, weights=weights, a_mat1=c.a_mat, a_mix1=c.a_mix,
+         sigma=c.a_dist.covariance_matrix.diag().sqrt())
+
+
+# ----------------------------------------------------------------------------------
+# G3: SVMPC.optimize + SVMPC.forward, one control step, teacher-forced sequence
+# ----------------------------------------------------------------------------------
+def run_svmpc_steps(w, n_steps, plant_params=None, with_mpf=None, tag_kernel="rbf"):
+    """Runs the reference closed loop and records, per step, inputs and outputs."""
+    sv, model = w["svmpc"], w["model"]
+    state = w["state"].clone()
+    rec_steps = []
+    mpf = with_mpf
+    dyn = RecordingDist(mpf.prior if mpf is not None else w["dyn"])
+    for step in range(n_steps):
+        pre = dict(
+            state=state.clone(), theta0=sv.theta.detach().clone(), mu0=prior_mu(sv.prior),
+            mix0=prior_mix(sv.prior),
+        )
+        if mpf is not None:
+            dyn.d = mpf.prior  # particle_example.py:171 captures once; the object tracks mpf.x by view
+            pre["mpf_x0"] = mpf.x.detach().clone()
+        dyn.samples.clear()
+        with NoiseRecorder() as rec:
+            sv.optimize(state, dyn)
+        eps = [d for d in rec.draws if d.ndim == 4][0]
+        pre["eps"] = eps
+        pre["params"] = dyn.samples[0].clone() if dyn.samples else torch.zeros(0)
+        post = dict(
+            costs=sv.likelihood.last_costs.detach().clone(),
+            log_l=sv.likelihood.log_prob(sv.likelihood.last_costs).detach().clone(),
+            theta1=sv.theta.detach().clone(),
+            phi=-sv.theta.grad.detach().clone(),
+        )
+        a_seq, p_w = sv.forward(state, dyn)
+        post.update(
+            a_seq=a_seq.clone(), p_weights=p_w.clone(), i_star=np.array(int(p_w.argmax())),
+            theta2=sv.theta.detach().clone(), mu2=prior_mu(sv.prior), mix2=prior_mix(sv.prior),
+        )
+        action = a_seq[0]
+        # plant = the model's own step with "true" parameters (gym is absent)
+        if plant_params is None:
+            nxt = model.step(state.view(1, -1), action.view(1, -1)).view(-1)
+        else:
+            nxt = model.step(state.view(1, -1), action.view(1, -1), plant_params).view(-1)
+        post["next_state"] = nxt.clone()
+        if mpf is not None:
+            bw_arg = w.get("mpf_bw")
+            gn, bw = mpf.optimize(action.squeeze(), nxt.clone(), bw=bw_arg, n_steps=w["mpf_steps"])
+            post["mpf_x1"] = mpf.x.detach().clone()
+            post["mpf_grad_norms"] = gn.clone()
+            post["mpf_bw"] = np.array(float(bw))
+        state = nxt
+        rec_steps.append((pre, post))
+    return rec_steps
+
+
+def flatten_steps(rec_steps):
+    out = {}
+    for i, (pre, post) in enumerate(rec_steps):
+        for k, v in pre.items():
+            out[f"t{i}_in_{k}"] = v
+        for k, v in post.items():
+            out[f"t{i}_out_{k}"] = v
+    out["n_steps"] = np.array(len(rec_steps))
+    return out
+
+
+def gen_svmpc():
+    print("G3 SVMPC step sequences")
+    # pendulum, shipped kernel (gpytorch RBFKernel stand-in) -> shim-dependent
+    w = make_pendulum(0, kernel="rbf")
+    pp = {"length": torch.tensor([[1.1]]), "mass": torch.tensor([[0.8]])}
+    save("svmpc_pendulum_rbf", tags=["shim-dependent:gpytorch", "shim-dependent:KDEpy(dead value)"],
+         sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(),
+         **flatten_steps(run_svmpc_steps(w, 6, plant_params=pp)))
+    # pendulum, the reference's own kernels (message passing)
+    w = make_pendulum(1, kernel="mp")
+    save("svmpc_pendulum_mp", tags=["shim-dependent:KDEpy(dead value)"],
+         sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(),
+         **flatten_steps(run_svmpc_steps(w, 4, plant_params=pp)))
+    w = make_particle(0, kernel="rbf")
+    save("svmpc_particle_rbf", tags=["shim-dependent:gpytorch", "shim-dependent:KDEpy(dead value)"],
+         sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(),
+         **flatten_steps(run_svmpc_steps(w, 4)))
+    w = make_particle(1, kernel="mp")
+    save("svmpc_particle_mp", tags=["shim-dependent:KDEpy(dead value)"],
+         sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(),
+         **flatten_steps(run_svmpc_steps(w, 3)))
+
+
+# ----------------------------------------------------------------------------------
+# G4: full dual loop (SVMPC + MPF), as the demos run it
+# ----------------------------------------------------------------------------------
+def gen_dual():
+    print("G4 dual DuSt-MPC loops")
+    # pendulum: linear space, explicit bandwidth (avoids the KDEpy stand-in) and Silverman
+    for name, bw, tags in (("dual_pendulum_bw", 0.1, ["shim-dependent:gpytorch"]),
+                           ("dual_pendulum_silverman", None,
+                            ["shim-dependent:gpytorch", "shim-dependent:KDEpy"])):
+        w = make_pendulum(2, kernel="rbf")
+        ep = w["cfg"]
+        torch.manual_seed(42)
+        x0 = w["dyn"].sample([ep["mpf_n_particles"]])
+        lik = likelihoods.GaussianLikelihood(
+            initial_obs=w["state"].clone(), obs_std=ep["mpf_obs_std"],
+            model=pendulum_mod.PendulumModel(uncertain_params=("length", "mass")), log_space=False)
+        mpf = mpf_mod.MPF(init_particles=x0, likelihood=lik, optimizer_class=torch.optim.SGD,
+                          lr=ep["mpf_learning_rate"], bw=bw, bw_scale=ep["mpf_bandwidth_scaling"])
+        w["mpf_bw"], w["mpf_steps"] = bw, ep["mpf_steps"]
+        prior_bw = float(mpf.prior.component_distribution.base_dist.covariance_matrix[0, 0, 0].sqrt())
+        pp = {"length": torch.tensor([[1.1]]), "mass": torch.tensor([[0.8]])}
+        save(name, tags=tags, sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(),
+             mpf_prior_bw0=np.array(prior_bw), obs_std=np.array(ep["mpf_obs_std"]),
+             mpf_lr=np.array(ep["mpf_learning_rate"]),
+             **flatten_steps(run_svmpc_steps(w, 4, plant_params=pp, with_mpf=mpf)))
+    # particle: log space, bw = 0.5 (particle_config.yaml:31-35)
+    w = make_particle(2, kernel="rbf")
+    ep = w["cfg"]
+    torch.manual_seed(43)
+    x0 = w["dyn"].sample([ep["mpf_n_particles"], 1]).clamp(min=1e-6).log()
+    lik = likelihoods.GaussianLikelihood(initial_obs=w["state"].clone(), obs_std=ep["mpf_obs_std"],
+                                         model=w["model"], log_space=True)
+    init_bw = (2 * ep["dyn_prior_arg2"]) ** 1 / 2  # particle_example.py:145 (precedence quirk: = 0.1)
+    mpf = mpf_mod.MPF(init_particles=x0, likelihood=lik, optimizer_class=torch.optim.SGD,
+                      lr=ep["mpf_learning_rate"], bw=init_bw, bw_scale=ep["mpf_bandwidth_scaling"])
+    w["mpf_bw"], w["mpf_steps"] = ep["mpf_bandwidth"], ep["mpf_steps"]
+    pp = {"mass": torch.tensor([[3.0]])}
+    save("dual_particle", tags=["shim-dependent:gpytorch"],
+         sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(),
+         mpf_prior_bw0=np.array(init_bw), obs_std=np.array(ep["mpf_obs_std"]),
+         mpf_lr=np.array(ep["mpf_learning_rate"]),
+         **flatten_steps(run_svmpc_steps(w, 4, plant_params=pp, with_mpf=mpf)))
+
+
+# ----------------------------------------------------------------------------------
+# G5: MPF.optimize stand-alone (one-step likelihood gradient by autograd, mpf.py:40-62)
+# ----------------------------------------------------------------------------------
+def gen_mpf():
+    print("G5 MPF.optimize")
+    torch.manual_seed(11)
+    # pendulum, linear space, two parameters (length, mass)
+    model = pendulum_mod.PendulumModel(uncertain_params=("length", "mass"))
+    x0 = dist.Uniform(torch.tensor([0.6, 0.6]), torch.tensor([1.3, 1.3])).sample([50])
+    obs0 = torch.tensor([2.5, -1.0])
+    lik = likelihoods.GaussianLikelihood(initial_obs=obs0, obs_std=0.1, model=model, log_space=False)
+    mpf = mpf_mod.MPF(init_particles=x0.clone(), likelihood=lik, optimizer_class=torch.optim.SGD,
+                      lr=1e-3, bw=0.1, bw_scale=1.0)
+    action = torch.tensor(1.3)
+    true = {"length": torch.tensor([[0.9]]), "mass": torch.tensor([[1.2]])}
+    obs1 = model.step(obs0.view(1, -1), action.view(1, -1), true).view(-1)
+    # one phi evaluation (for the unit-level check), then the 20-step optimise
+    lik.condition(action, obs1)
+    phi0 = mpf.phi(0.1)
+    lik.loc = obs0  # undo so that optimise() conditions again from the same past
+    del lik.past_obs
+    lik.condition(action=None, new_obs=obs0)
+    gn, bw = mpf.optimize(action, obs1, bw=0.1, n_steps=20)
+    save("mpf_pendulum", x0=x0, obs0=obs0, obs1=obs1, action=action, phi0=phi0, x1=mpf.x,
+         grad_norms=gn, bw=np.array(bw), prior_bw=np.array(0.1), obs_std=np.array(0.1),
+         lr=np.array(1e-3), mu1=mpf.prior.component_distribution.base_dist.loc)
+    # particle, log space, one parameter (mass)
+    w = make_particle(3)
+    model = w["model"]
+    x0 = dist.Normal(2.0, 0.1).sample([50, 1]).clamp(min=1e-6).log()
+    obs0 = torch.tensor([-8.0, -7.5, 1.0, 2.0])
+    lik = likelihoods.GaussianLikelihood(initial_obs=obs0, obs_std=0.1, model=model, log_space=True)
+    mpf = mpf_mod.MPF(init_particles=x0.clone(), likelihood=lik, optimizer_class=torch.optim.SGD,
+                      lr=0.01, bw=0.1, bw_scale=1.0)
+    action = torch.tensor([6.0, -3.0])
+    obs1 = model.step(obs0.view(1, -1), action.view(1, -1), {"mass": torch.tensor([[3.0]])}).view(-1)
+    gn, bw = mpf.optimize(action, obs1, bw=0.5, n_steps=20)
+    save("mpf_particle", x0=x0, obs0=obs0, obs1=obs1, action=action, x1=mpf.x, grad_norms=gn,
+         bw=np.array(bw), prior_bw=np.array(0.1), obs_std=np.array(0.1), lr=np.array(0.01))
+
+
+# ----------------------------------------------------------------------------------
+# G6: generic SVGD.phi + bw_median; RBF.eval; iid_mp.eval
+# ----------------------------------------------------------------------------------
+def gen_phi():
+    print("G6 SVGD.phi / kernels")
+    s = svgd_mod.SVGD()
+    for N in (64, 257, 1024):
+        torch.manual_seed(N)
+        d = 40
+        scale = torch.arange(1, d + 1).float() / 10.0 if N == 257 else torch.ones(d)
+        X = (torch.randn(N, d) * scale).requires_grad_(True)
+        log_p = lambda x: -0.5 * (x ** 2).sum(-1)  # noqa: E731  standard-normal target
+        bw = svgd_mod.bw_median(X, X)
+        phi = s.phi(X, log_p, bw)
+        d2 = svgd_mod.squared_distance(X.detach(), X.detach())
+        med = torch.median(d2)
+        save(f"phi_svgd_N{N}", X=X.detach(), score=-X.detach(), bw=bw.detach(), phi=phi.detach(),
+             median_d2=med)
+    # the reference's own kernels on a tiny set
+    torch.manual_seed(3)
+    X = torch.randn(6, 80) * 3
+    k = base_kernels.RBF(bandwidth=-1)
+    K, dK = k.eval(X, X.clone())
+    h, d2 = k.compute_bandwidth(X, X.clone())
+    mp = composite_kernels.iid_mp(base_kernel=base_kernels.RBF(bandwidth=-1), ctrl_dim=2)
+    Kmp, dKmp = mp.eval(X, X.clone())
+    save("kernels_small", X=X, K=K, dK=dK, h=np.array(float(h)), d2=d2, Kmp=Kmp, dKmp=dKmp)
+
+
+# ----------------------------------------------------------------------------------
+# G7: pathwise gradient (svmpc.py:58-60 alternative), autograd through the reference rollout
+# ----------------------------------------------------------------------------------
+def gen_pathwise():
+    print("G7 pathwise (autograd) likelihood gradient")
+    for kind, seed in (("pendulum", 4), ("particle", 4), ("particle", 5)):
+        w = make_pendulum(seed) if kind == "pendulum" else make_particle(seed)
+        sv = w["svmpc"]
+        torch.manual_seed(2000 + seed)
+        if kind == "pendulum":
+            state = torch.tensor([2.0, 1.0])
+        elif seed == 4:
+            state = torch.tensor([-9.0, -9.0, 0.0, 0.0])  # free space (demo start)
+        else:
+            state = torch.tensor([-7.6, -6.0, 1.0, 0.5])  # drifting towards an obstacle face
+        pd = RecordingDist(w["dyn"]) if kind == "pendulum" else RecordingDist(dist.Normal(0.7, 0.1))
+        # NB: for the particle the controller is in log space: masses = exp(N(0.7,0.1))
+        x = sv.theta.detach().clone().requires_grad_(True)
+        with NoiseRecorder() as rec:
+            costs, actions = sv.likelihood.sample(x, state, pd)
+        log_l = sv.likelihood.log_prob(costs)
+        g = torch.autograd.grad(log_l.sum(), x)[0]
+        eps = [d for d in rec.draws if d.ndim == 4][0]
+        save(f"pathwise_{kind}_s{seed}", state=state, theta=x.detach(), eps=eps,
+             params=pd.samples[0], costs=costs.detach(), log_l=log_l.detach(), grad=g,
+             sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt())
+
+
+if __name__ == "__main__":
+    gen_map()
+    gen_forward_all()
+    gen_svmpc()
+    gen_dual()
+    gen_mpf()
+    gen_phi()
+    gen_pathwise()
+    with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
+        json.dump({"generator": "tests/golden/make_golden.py", "torch": torch.__version__,
+                   "fixtures": MANIFEST}, f, indent=1, sort_keys=True)
+    total = sum(v["bytes"] for v in MANIFEST.values())
+    print(f"total {total/1e6:.2f} MB in {len(MANIFEST)} fixtures")
