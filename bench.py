@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- DuSt-MPC control steps/s on B200 (BASELINE.json metric).
+
+Workload (configs[2], the configuration the 1/2/4/8-GPU metric is quoted on): batched pendulum
+SVMPC, 4096 independent MPC instances PER GPU x 8 policies x 256 action samples x horizon 20,
+no parameter sampling (P = 1).  One "step" = SVMPC.optimize (n_steps = 1) + SVMPC.forward for
+every instance: GMM prior score -> rollout + cost + soft-min likelihood gradient -> fused
+SVGD phi + SGD update -> weights / argmax / shift / prior refresh.
+
+  python bench.py --gpus N --steps K --warmup W            (one rank per GPU under torchrun)
+  python bench.py --impl reference ...                      (CPU arm: the oracle port of the
+                                                             reference's eager-torch path)
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CFG = dict(N=8, S=256, H=20, A=1, ds=2, P=1, ctrl_sigma=2.0, prior_sigma=2.0, alpha=1.0, lr=2.0)
+METRIC, UNIT = "svmpc_control_steps_per_sec", "instance-steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--instances", type=int, default=4096, help="MPC instances per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=48, help="instances in the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    c = CFG
+    return {
+        "workload": "batched pendulum SVMPC (BASELINE.json configs[2])",
+        "instances_per_gpu": args.instances, "policies": c["N"], "action_samples": c["S"], "horizon": c["H"],
+        "params_samples": c["P"], "model": None, "kernel": "rbf (gpytorch default lengthscale)",
+        "likelihood": "ExponentiatedUtility", "sharding": f"instances x{n_gpus}, no data-path collective",
+        "rollouts_per_step": args.instances * n_gpus * c["N"] * c["S"] * c["P"],
+        "l2_policy": "noise input (671 MB/GPU/step) is larger than the 126 MB L2",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's path, one instance at a time (the reference has no
+# batch dimension: B instances are B sequential SVMPC.optimize + SVMPC.forward calls)
+# ---------------------------------------------------------------------------------------------
+def cpu_instance_steps(n_instances, n_steps, threads, seed=0):
+    from oracle import dust_oracle as O
+
+    c = CFG
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    model = O.Model("pendulum")
+    sigma = torch.tensor([c["ctrl_sigma"]])
+    insts = []
+    for _ in range(n_instances):
+        mu = torch.randn(c["N"], c["H"], c["A"], generator=g)
+        theta = mu + c["prior_sigma"] * torch.randn(c["N"], c["H"], c["A"], generator=g)
+        st = O.SvmpcState(theta, mu, torch.ones(c["N"]), c["prior_sigma"] ** 2)
+        state = (torch.rand(2, generator=g) * 2 - 1) * torch.tensor([3.14159, 1.0])
+        insts.append((st, state))
+    t0 = time.perf_counter()
+    for _ in range(n_steps):
+        for st, state in insts:
+            eps = torch.randn(c["S"], c["N"], c["H"], c["A"], generator=g)  # reference draws by rsample
+            out = O.svmpc_optimize(model, st, state, eps, sigma, None, False, c["alpha"], c["lr"], kernel="rbf")
+            O.svmpc_forward(st, out["costs"], c["alpha"], False)
+    dt = time.perf_counter() - t0
+    return n_instances * n_steps / dt, dt
+
+
+def best_cpu(n_instances, n_steps):
+    ncpu = os.cpu_count() or 1
+    best = None
+    for th in sorted({1, min(4, ncpu), min(16, ncpu)}):
+        cpu_instance_steps(2, 1, th)  # warm-up
+        v, dt = cpu_instance_steps(max(2, n_instances // 4), 1, th)
+        if best is None or v > best[0]:
+            best = (v, th)
+    v, dt = cpu_instance_steps(n_instances, n_steps, best[1])
+    return v, best[1], dt
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    ncpu = os.cpu_count() or 1
+    n = args.cpu_sample
+    # thread sweep on a small probe, then K timed "steps", each a bounded sample of n instances
+    probe = {}
+    for th in sorted({1, min(4, ncpu), min(16, ncpu)}):
+        cpu_instance_steps(2, 1, th)
+        probe[th] = cpu_instance_steps(8, 1, th)[0]
+    th = max(probe, key=probe.get)
+    for _ in range(args.warmup):
+        cpu_instance_steps(max(2, n // 8), 1, th)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_instance_steps(n, 1, th, seed=k)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} of {args.instances * args.gpus} instances per step, one at a time (the reference has no batch dim)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": th, "kind": "port", "sample": sample,
+                         "host_cpus": ncpu, "thread_probe": {str(k): v for k, v in probe.items()}},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        except Exception:
+            pass
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from dust_b200 import _lib as L
+    from dust_b200.batched import BatchedSVMPC
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    L.require_cuda()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    c = CFG
+    B = args.instances
+    ctl = BatchedSVMPC(PendulumModel(), B, c["N"], c["S"], c["H"], c["ctrl_sigma"], c["prior_sigma"], alpha=c["alpha"],
+                       learning_rate=c["lr"], kernel="gpytorch", inst_cost_fn=inst_cost, term_cost_fn=term_cost,
+                       device=dev, seed=1234 + rank)
+    g = ctl.gen
+    state = (torch.rand(B, 2, device=dev, generator=g) * 2 - 1) * torch.tensor([3.14159, 1.0], device=dev)
+    eps = ctl.draw_noise()  # resident in HBM for the `value` measurement
+    lib = L.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        ctl.optimize(state, eps)
+        ctl.forward()
+
+    for _ in range(args.warmup):
+        step_resident()
+    # ---- value: K steps, inputs resident in HBM ------------------------------------------------
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.15)
+    n0 = lib.dust_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    launches = int(lib.dust_launch_count() - n0)
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms[0])
+    clocks = sampler.stop() if sampler else None
+
+    # ---- per-kernel breakdown with the library's event timer (same steps, second pass) -------
+    lib.dust_profiler_reset()
+    lib.dust_profiler_enable(1)
+    for _ in range(args.steps):
+        step_resident()
+    prof = L.profiler_report()
+    lib.dust_profiler_enable(0)
+
+    # ---- e2e: host state in, action out, noise drawn on the device by the public API ----------
+    h_state = state.cpu().pin_memory()
+    h_action = torch.empty(B, c["A"]).pin_memory()
+    d_state = torch.empty_like(state)
+    for _ in range(max(3, args.warmup // 2)):
+        d_state.copy_(h_state, non_blocking=True)
+        h_action.copy_(ctl.control_step(d_state), non_blocking=True)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        d_state.copy_(h_state, non_blocking=True)
+        h_action.copy_(ctl.control_step(d_state), non_blocking=True)
+    f1.record()
+    barrier()
+    ms2 = torch.tensor([f0.elapsed_time(f1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
+    e2e_ms_total = float(ms2[0])
+
+    if rank != 0:
+        return
+    K = args.steps
+    total_inst = B * world
+    value = total_inst * K / (ms_total * 1e-3)
+    e2e_value = total_inst * K / (e2e_ms_total * 1e-3)
+    # roofline of the dominant kernel (rollout + cost): algorithmic bytes per launch =
+    # 4 * B * (S*N*H*A noise read + S*N costs written + N*H*A theta read + ds state read)
+    algo_bytes = 4.0 * B * (c["S"] * c["N"] * c["H"] * c["A"] + c["S"] * c["N"] + c["N"] * c["H"] * c["A"] + c["ds"])
+    peak, peak_src = measured_peak()
+    n_roll, ms_roll = prof.get("rollout_cost_kernel", (0, 0.0))
+    roof = None
+    if n_roll:
+        per = ms_roll / n_roll
+        ach = algo_bytes / (per * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "rollout_traffic.json")
+        if os.path.isfile(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"kernel": "rollout_cost_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                "ms_per_launch": per, "peak_source": peak_src,
+                "note": "kernel is FP32-issue/SFU bound (sinf+cosf per model step), see DESIGN.md"}
+    step_kernel_ms = {k: v[1] / K for k, v in prof.items()}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        v, th, dt = best_cpu(args.cpu_sample, 1)
+        cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port", "host_cpus": os.cpu_count(),
+               "sample": f"{args.cpu_sample} of {B} instances, 1 step each, one instance at a time ({dt:.1f} s)"}
+    cfg = workload_config(args, world)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": cfg, "rollouts_per_sec": value * c["N"] * c["S"] * c["P"],
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / K,
+                "h2d_bytes_per_step": B * c["ds"] * 4, "d2h_bytes_per_step": B * c["A"] * 4,
+                "note": "state in (pinned host) -> action out (pinned host); noise drawn on the device inside the call"},
+        "gpu_launches": launches, "kernel_ms_per_step": step_kernel_ms, "roofline": roof, "cpu_baseline": cpu,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,197 @@
+"""ctypes binding of libdust_b200.so (the C ABI declared in include/dust_b200.h).
+
+There is NO CPU fallback: if the shared library is missing, or a call is made without a
+CUDA device, the import / call raises.  torch is used only for device memory and streams.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdust_b200.so")
+
+OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
+MODEL_PENDULUM, MODEL_PARTICLE = 0, 1
+PARAMS_BLOCKED, PARAMS_INTERLEAVED = 0, 1
+LIK_EXP_UTILITY, LIK_EXPECTED_COST = 0, 1
+ROLL_REPEAT, ROLL_MEAN = 0, 1
+SELECT_ARGMAX, SELECT_AVERAGE = 0, 1
+
+_f, _i, _p, _sz = C.c_float, C.c_int32, C.c_void_p, C.c_size_t
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [
+        ("kind", _i), ("dt", _f), ("g", _f), ("max_torque", _f), ("max_speed_pend", _f),
+        ("w_angle", _f), ("w_speed", _f), ("default_length", _f), ("default_mass", _f),
+        ("max_accel", _f), ("max_speed", _f), ("target", _f * 4), ("w_state", _f * 4),
+        ("w_term", _f * 4), ("w_ctrl", _f * 2), ("w_obs", _f), ("inv_cell", _f),
+        ("c_offset", _f * 2), ("grid_nx", _i), ("grid_ny", _i), ("can_crash", _i),
+        ("with_obstacle", _i), ("grid_bits", _p),
+    ]
+
+
+class RolloutArgs(C.Structure):
+    _fields_ = [
+        ("model", C.POINTER(ModelDesc)), ("B", _i), ("N", _i), ("S", _i), ("P", _i), ("H", _i),
+        ("param_tiling", _i), ("likelihood", _i),
+        ("state0", _p), ("theta", _p), ("noise", _p), ("sigma", _p), ("params", _p), ("a_seq", _p),
+        ("pert", _p), ("alpha", _f), ("temperature", _f),
+        ("costs", _p), ("log_lik", _p), ("lik_weights", _p), ("grad_lik", _p), ("mppi_weights", _p),
+        ("mppi_delta", _p), ("mix", _p), ("states", _p),
+        ("workspace", _p), ("workspace_bytes", _sz),
+    ]
+
+
+class AdjointArgs(C.Structure):
+    _fields_ = [
+        ("model", C.POINTER(ModelDesc)), ("B", _i), ("N", _i), ("S", _i), ("P", _i), ("H", _i),
+        ("param_tiling", _i), ("likelihood", _i),
+        ("state0", _p), ("theta", _p), ("noise", _p), ("sigma", _p), ("params", _p), ("lik_weights", _p),
+        ("alpha", _f), ("grad_theta", _p), ("grad_params", _p),
+        ("workspace", _p), ("workspace_bytes", _sz),
+    ]
+
+
+class GmmArgs(C.Structure):
+    _fields_ = [
+        ("B", _i), ("M", _i), ("K", _i), ("D", _i), ("x", _p), ("mu", _p), ("mix", _p),
+        ("inv_var", _p), ("log_norm", _f), ("log_prob", _p), ("score", _p),
+    ]
+
+
+class MedianArgs(C.Structure):
+    _fields_ = [
+        ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("x", _p), ("hist", _p),
+        ("selected", _p), ("row_norms", _p),
+    ]
+
+
+class PhiArgs(C.Structure):
+    _fields_ = [
+        ("B", _i), ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("per_dim", _i),
+        ("x", _p), ("score", _p), ("gamma", _f), ("c1", _f), ("c2", _f), ("gamma_dev", _p),
+        ("bw_scale", _f), ("lr", _f), ("phi", _p), ("x_out", _p), ("bandwidths", _p),
+        ("workspace", _p), ("workspace_bytes", _sz),
+    ]
+
+
+class SvmpcForwardArgs(C.Structure):
+    _fields_ = [
+        ("B", _i), ("N", _i), ("H", _i), ("A", _i), ("roll_strategy", _i), ("weighted_prior", _i),
+        ("log_lik", _p), ("theta", _p), ("mu", _p), ("mix", _p), ("inv_var", _p), ("log_norm", _f),
+        ("p_weights", _p), ("i_star", _p), ("a_seq", _p), ("theta_next", _p), ("mix_next", _p),
+    ]
+
+
+class DiscoStepArgs(C.Structure):
+    _fields_ = [
+        ("B", _i), ("N", _i), ("H", _i), ("A", _i), ("strategy", _i), ("steps", _i),
+        ("a_low", _p), ("a_high", _p), ("a_mat", _p), ("a_mix", _p), ("a_seq", _p),
+        ("next_actions", _p),
+    ]
+
+
+class MpfArgs(C.Structure):
+    _fields_ = [
+        ("model", C.POINTER(ModelDesc)), ("B", _i), ("Np", _i), ("n_steps", _i), ("log_space", _i),
+        ("x", _p), ("obs0", _p), ("action", _p), ("obs1", _p), ("prior_inv_var", _p),
+        ("obs_std", _f), ("bw", _f), ("lr", _f), ("grad_norms", _p),
+    ]
+
+
+# every symbol include/dust_b200.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "dust_rollout_workspace_bytes": (_sz, [C.POINTER(RolloutArgs)]),
+    "dust_rollout_cost": (C.c_int, [C.POINTER(RolloutArgs), _p]),
+    "dust_adjoint_workspace_bytes": (_sz, [C.POINTER(AdjointArgs)]),
+    "dust_rollout_adjoint": (C.c_int, [C.POINTER(AdjointArgs), _p]),
+    "dust_gmm_score": (C.c_int, [C.POINTER(GmmArgs), _p]),
+    "dust_median_hist_pass": (C.c_int, [C.POINTER(MedianArgs), _i, _p]),
+    "dust_median_select": (C.c_int, [C.POINTER(MedianArgs), _i, _p, _p]),
+    "dust_phi_workspace_bytes": (_sz, [C.POINTER(PhiArgs)]),
+    "dust_svgd_phi": (C.c_int, [C.POINTER(PhiArgs), _p]),
+    "dust_bandwidth_from_median": (C.c_int, [_p, _i, _f, _i, _p, _p]),
+    "dust_svmpc_forward": (C.c_int, [C.POINTER(SvmpcForwardArgs), _p]),
+    "dust_disco_step": (C.c_int, [C.POINTER(DiscoStepArgs), _p]),
+    "dust_mpf_optimize": (C.c_int, [C.POINTER(MpfArgs), _p]),
+    "dust_model_step": (C.c_int, [C.POINTER(ModelDesc), _i, _p, _p, _p, _p, _p]),
+    "dust_model_cost": (C.c_int, [C.POINTER(ModelDesc), _i, _i, _p, _p, _p, _p]),
+    "dust_profiler_enable": (None, [C.c_int]),
+    "dust_profiler_reset": (None, []),
+    "dust_profiler_report": (C.c_int, [C.c_char_p, _sz]),
+    "dust_launch_count": (C.c_ulonglong, []),
+    "dust_abi_version": (C.c_int, []),
+    "dust_last_error": (C.c_char_p, []),
+    "dust_build_info": (C.c_char_p, []),
+}
+
+_lib = None
+launch_count = 0  # kernels-launching ABI calls made through this module (bench.py reads it)
+
+
+def load():
+    """dlopen libdust_b200.so (once) and declare the prototypes.  Raises if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C dust_b200/csrc`).  dust_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    if lib.dust_abi_version() != 1:
+        raise ImportError("libdust_b200.so ABI version mismatch: rebuild the library")
+    _lib = lib
+    return lib
+
+
+_EXC = {ERR_INVALID_ARG: ValueError, ERR_UNSUPPORTED: NotImplementedError,
+        ERR_WORKSPACE: RuntimeError, ERR_CUDA: RuntimeError}
+
+
+def check(rc):
+    if rc != OK:
+        msg = load().dust_last_error().decode("utf-8", "replace")
+        raise _EXC.get(rc, RuntimeError)(msg)
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("dust_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def ptr(t):
+    """device pointer of a contiguous float32/int32 CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise ValueError("dust_b200: tensor must live on a CUDA device")
+    if not t.is_contiguous():
+        raise ValueError("dust_b200: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def profiler_report():
+    """{kernel name: (launches, total_ms)} accumulated since dust_profiler_reset (synchronises)."""
+    buf = C.create_string_buffer(1 << 16)
+    check(load().dust_profiler_report(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.rsplit(" ", 2)
+        out[name] = (int(n), float(ms))
+    return out
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args, launches=1):
+    global launch_count
+    launch_count += launches
+    check(getattr(load(), name)(*args))

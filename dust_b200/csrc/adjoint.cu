@@ -1,0 +1,270 @@
+// K2: pathwise likelihood gradient by hand-derived reverse-time adjoints of the two shipped
+// models (in place of torch.autograd through rsample -> rollout -> cost,
+// dust/inference/svmpc.py:58-60).  Forward sweep stores the trajectory in per-thread local
+// memory, the reverse sweep propagates the cost cotangent; clamp sub-gradients are inclusive
+// and floor / occupancy terms carry none (torch semantics).
+// Compiled with -fmad=false so the forward sweep reproduces K1's trajectories exactly.
+#include "models.cuh"
+
+namespace dust {
+
+constexpr int kAdjTile = 128;
+
+__host__ __device__ inline int adj_stride(int HA) {
+  int s4 = (HA + 3) / 4;
+  if ((s4 & 1) == 0) s4 += 1;
+  return s4 * 4;
+}
+
+struct AdjKParams {
+  ModelParams m;
+  int B, N, S, P, H, A, SN, HA, PC, Pchunk, interleaved, likelihood, tiles;
+  const float *state0, *theta, *noise, *sigma, *params, *lik_w;
+  float alpha;
+  float* partial;  // [B, tiles, PC, N*HA]
+};
+
+template <int MODEL, int MAXH>
+__global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKParams k) {
+  constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
+  constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
+  extern __shared__ __align__(16) float smem[];
+  const int stride = adj_stride(k.HA);
+  float* tile = smem;                        // actions  [kAdjTile][stride]
+  float* gacc = smem + kAdjTile * stride;    // gradient [kAdjTile][stride]
+  uint32_t* grid_s = reinterpret_cast<uint32_t*>(gacc + kAdjTile * stride);
+
+  const long long inst = blockIdx.x / k.tiles;
+  const int tile_idx = blockIdx.x - (int)inst * k.tiles;
+  const int j0 = tile_idx * kAdjTile;
+  const int rows = min(kAdjTile, k.SN - j0);
+  const int pc = blockIdx.y;
+  const int HA = k.HA;
+
+  {  // stage actions = theta + sigma*eps
+    const float* __restrict__ src = k.noise + (inst * k.SN + j0) * (long long)HA;
+    const float* __restrict__ th = k.theta ? k.theta + inst * (long long)k.N * HA : nullptr;
+    const int NHA = k.N * HA;
+    const int wrap0 = (int)(((long long)j0 * HA) % NHA);
+    for (int e = threadIdx.x; e < rows * HA; e += kAdjTile) {
+      const int row = e / HA, c = e - row * HA;
+      float v = __ldg(src + e);
+      if (th) v = __ldg(th + (wrap0 + e) % NHA) + k.sigma[c % A] * v;
+      tile[row * stride + c] = v;
+    }
+    for (int e = threadIdx.x; e < kAdjTile * stride; e += kAdjTile) gacc[e] = 0.f;
+    if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
+      const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
+      for (int w = threadIdx.x; w < words; w += kAdjTile) grid_s[w] = __ldg(k.m.grid_bits + w);
+    }
+  }
+  __syncthreads();
+
+  const int row = threadIdx.x;
+  if (row < rows) {
+    const int j = j0 + row;
+    const float* __restrict__ arow = tile + row * stride;
+    float* __restrict__ grow = gacc + row * stride;
+    const float* __restrict__ x0 = k.state0 + inst * DS;
+    const int p_begin = pc * k.Pchunk, p_end = min(k.P, p_begin + k.Pchunk);
+    float coef;
+    if (k.likelihood == DUST_LIK_EXP_UTILITY)
+      coef = -k.alpha * __ldg(k.lik_w + inst * k.SN + j) / (float)k.P;
+    else
+      coef = -k.alpha / ((float)k.S * (float)k.P);
+
+    for (int p = p_begin; p < p_end; ++p) {
+      const float* prm = nullptr;
+      if (k.params) {
+        const int pi = k.interleaved ? (int)(((long long)p * k.SN + j) % k.P) : p;
+        prm = k.params + (inst * k.P + pi) * DP;
+      }
+      if (MODEL == DUST_MODEL_PENDULUM) {
+        const PendulumCoef cf = prm ? pendulum_coef_sampled(k.m, __ldg(prm), __ldg(prm + 1)) : pendulum_coef_default(k.m);
+        float ths[MAXH + 1], oms[MAXH + 1];
+        uint32_t m8[(MAXH + 31) / 32];
+#pragma unroll
+        for (int w = 0; w < (MAXH + 31) / 32; ++w) m8[w] = 0u;
+        float th = __ldg(x0), om = __ldg(x0 + 1);
+        ths[0] = th; oms[0] = om;
+        for (int t = 0; t < k.H; ++t) {
+          float pre;
+          pendulum_step(k.m, cf, th, om, arow[t], &pre);
+          if (pre >= -k.m.max_speed_pend && pre <= k.m.max_speed_pend) m8[t >> 5] |= 1u << (t & 31);
+          ths[t + 1] = th; oms[t + 1] = om;
+        }
+        float sH, cH;
+        sincosf(ths[k.H], &sH, &cH);
+        float lam_th = -2.0f * k.m.w_angle * (cH - 1.0f) * sH;
+        float lam_om = 2.0f * k.m.w_speed * oms[k.H];
+        for (int t = k.H - 1; t >= 0; --t) {
+          const float a = arow[t];
+          const float tht = ths[t], omt = oms[t];
+          const bool in8 = (m8[t >> 5] >> (t & 31)) & 1u;
+          const bool in2 = (a >= -k.m.max_torque) && (a <= k.m.max_torque);
+          const float gom = lam_om + k.m.dt * lam_th;
+          const float g = in8 ? gom : 0.f;
+          const float ga = in2 ? g * k.m.dt * cf.c2 : 0.f;
+          grow[t] += coef * ga;
+          float st, ct;
+          sincosf(tht, &st, &ct);
+          const float cpi = cosf(tht + kPiF);
+          lam_th = lam_th + g * k.m.dt * cf.c1 * cpi - 2.0f * k.m.w_angle * (ct - 1.0f) * st;
+          lam_om = g + 2.0f * k.m.w_speed * omt;
+        }
+      } else {
+        const float mass = prm ? __ldg(prm) : k.m.default_mass;
+        float xs[MAXH + 1][4];
+        uint32_t cbit[(MAXH + 31) / 32], mvx[(MAXH + 31) / 32], mvy[(MAXH + 31) / 32];
+#pragma unroll
+        for (int w = 0; w < (MAXH + 31) / 32; ++w) { cbit[w] = 0u; mvx[w] = 0u; mvy[w] = 0u; }
+        ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
+        const bool has_grid = k.m.grid_bits != nullptr;
+        for (int t = 0; t < k.H; ++t) {
+          xs[t][0] = s.x; xs[t][1] = s.y; xs[t][2] = s.vx; xs[t][3] = s.vy;
+          const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
+          float vpre[2];
+          particle_step(k.m, s, arow[2 * t], arow[2 * t + 1], mass, c, vpre);
+          if (c != 0.f) cbit[t >> 5] |= 1u << (t & 31);
+          if (vpre[0] >= -k.m.max_speed && vpre[0] <= k.m.max_speed) mvx[t >> 5] |= 1u << (t & 31);
+          if (vpre[1] >= -k.m.max_speed && vpre[1] <= k.m.max_speed) mvy[t >> 5] |= 1u << (t & 31);
+        }
+        float lam[4];
+        lam[0] = 2.0f * k.m.w_term[0] * (s.x - k.m.target[0]);
+        lam[1] = 2.0f * k.m.w_term[1] * (s.y - k.m.target[1]);
+        lam[2] = 2.0f * k.m.w_term[2] * (s.vx - k.m.target[2]);
+        lam[3] = 2.0f * k.m.w_term[3] * (s.vy - k.m.target[3]);
+        for (int t = k.H - 1; t >= 0; --t) {
+          const float ax = arow[2 * t], ay = arow[2 * t + 1];
+          const float amx = ax / mass, amy = ay / mass;
+          const bool max_ = (amx >= -k.m.max_accel) && (amx <= k.m.max_accel);
+          const bool may_ = (amy >= -k.m.max_accel) && (amy <= k.m.max_accel);
+          const bool crashed = (cbit[t >> 5] >> (t & 31)) & 1u;
+          const float kk = (k.m.can_crash && crashed) ? 0.f : k.m.dt;
+          const float gvx = ((mvx[t >> 5] >> (t & 31)) & 1u) ? lam[2] : 0.f;
+          const float gvy = ((mvy[t >> 5] >> (t & 31)) & 1u) ? lam[3] : 0.f;
+          const float gax = (max_ ? kk * gvx / mass : 0.f) + 2.0f * k.m.w_ctrl[0] * ax;
+          const float gay = (may_ ? kk * gvy / mass : 0.f) + 2.0f * k.m.w_ctrl[1] * ay;
+          grow[2 * t] += coef * gax;
+          grow[2 * t + 1] += coef * gay;
+          const float l0 = lam[0] + 2.0f * k.m.w_state[0] * (xs[t][0] - k.m.target[0]);
+          const float l1 = lam[1] + 2.0f * k.m.w_state[1] * (xs[t][1] - k.m.target[1]);
+          const float l2 = gvx + kk * lam[0] + 2.0f * k.m.w_state[2] * (xs[t][2] - k.m.target[2]);
+          const float l3 = gvy + kk * lam[1] + 2.0f * k.m.w_state[3] * (xs[t][3] - k.m.target[3]);
+          lam[0] = l0; lam[1] = l1; lam[2] = l2; lam[3] = l3;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // column sums over the rows of this tile that belong to the same policy n
+  float* out = k.partial + ((inst * k.tiles + tile_idx) * (long long)k.PC + pc) * (long long)(k.N * HA);
+  for (int col = threadIdx.x; col < k.N * HA; col += kAdjTile) {
+    const int n = col / HA, c = col - n * HA;
+    int r0 = (n - (j0 % k.N)) % k.N;
+    if (r0 < 0) r0 += k.N;
+    float acc = 0.f;
+    for (int r = r0; r < rows; r += k.N) acc += gacc[r * stride + c];
+    out[col] = acc;
+  }
+}
+
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int W, int parts) {
+  const long long inst = blockIdx.y;
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= W) return;
+  const float* p = partial + inst * (long long)parts * W + col;
+  float acc = 0.f;
+  for (int q = 0; q < parts; ++q) acc += p[(long long)q * W];
+  out[inst * W + col] = acc;
+}
+
+struct AdjPlan {
+  int PC, Pchunk, tiles;
+  size_t total;
+};
+
+static AdjPlan plan_adjoint(const dust_adjoint_args* a) {
+  AdjPlan pl{};
+  const long long SN = (long long)a->S * a->N;
+  const int P = a->params ? a->P : 1;
+  const long long target_threads = (long long)kNumSMs * 2048 * 2;
+  long long pc = 1;
+  if (P > 1 && a->B * SN < target_threads) pc = (target_threads + a->B * SN - 1) / (a->B * SN);
+  if (pc > P) pc = P;
+  const int chunk = (int)((P + pc - 1) / pc);
+  pl.PC = (P + chunk - 1) / chunk;
+  pl.Pchunk = chunk;
+  pl.tiles = ceil_div(SN, kAdjTile);
+  const int A = model_da(a->model->kind);
+  pl.total = sizeof(float) * (size_t)a->B * pl.tiles * pl.PC * a->N * a->H * A;
+  return pl;
+}
+
+template <int MODEL, int MAXH>
+static int launch_adjoint(const AdjKParams& k, dim3 grid, size_t smem, cudaStream_t stream) {
+  if (smem > 48 * 1024)
+    DUST_CUDA_OK(cudaFuncSetAttribute(rollout_adjoint_kernel<MODEL, MAXH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  { DUST_TIMED("rollout_adjoint_kernel", stream); rollout_adjoint_kernel<MODEL, MAXH><<<grid, kAdjTile, smem, stream>>>(k); }
+  DUST_LAUNCH_OK("rollout_adjoint_kernel");
+  return DUST_OK;
+}
+
+}  // namespace dust
+
+using namespace dust;
+
+extern "C" size_t dust_adjoint_workspace_bytes(const dust_adjoint_args* a) {
+  if (!a || !a->model || a->B <= 0 || a->N <= 0 || a->S <= 0 || a->H <= 0) return 0;
+  return plan_adjoint(a).total;
+}
+
+extern "C" int dust_rollout_adjoint(const dust_adjoint_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_rollout_adjoint: args is NULL");
+  int rc = validate_model(a->model);
+  if (rc) return rc;
+  DUST_REQUIRE(a->B > 0 && a->N > 0 && a->S > 0 && a->H > 0, DUST_ERR_INVALID_ARG, "dust_rollout_adjoint: sizes must be positive");
+  DUST_REQUIRE(a->state0 && a->noise && a->grad_theta, DUST_ERR_INVALID_ARG,
+               "dust_rollout_adjoint: state0, noise and grad_theta are required");
+  DUST_REQUIRE(!a->theta || a->sigma, DUST_ERR_INVALID_ARG, "dust_rollout_adjoint: sigma is required with theta");
+  DUST_REQUIRE(a->likelihood != DUST_LIK_EXP_UTILITY || a->lik_weights, DUST_ERR_INVALID_ARG,
+               "dust_rollout_adjoint: lik_weights (from dust_rollout_cost) are required for the exponentiated utility");
+  DUST_REQUIRE(a->grad_params == nullptr, DUST_ERR_UNSUPPORTED,
+               "dust_rollout_adjoint: grad_params is not implemented in this build");
+  DUST_REQUIRE(a->H <= 128, DUST_ERR_UNSUPPORTED, "dust_rollout_adjoint: H=%d > 128", a->H);
+  DUST_REQUIRE(a->B <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_adjoint: B > 65535");
+  const AdjPlan pl = plan_adjoint(a);
+  DUST_REQUIRE(a->workspace && a->workspace_bytes >= pl.total, DUST_ERR_WORKSPACE,
+               "dust_rollout_adjoint: workspace needs %zu bytes, got %zu", pl.total, a->workspace_bytes);
+  const int kind = a->model->kind, A = model_da(kind);
+  AdjKParams k;
+  k.m = to_params(*a->model);
+  k.B = a->B; k.N = a->N; k.S = a->S; k.P = a->params ? a->P : 1; k.H = a->H; k.A = A;
+  k.SN = a->S * a->N; k.HA = a->H * A; k.PC = pl.PC; k.Pchunk = pl.Pchunk;
+  k.interleaved = a->param_tiling == DUST_PARAMS_INTERLEAVED; k.likelihood = a->likelihood; k.tiles = pl.tiles;
+  k.state0 = a->state0; k.theta = a->theta; k.noise = a->noise; k.sigma = a->sigma; k.params = a->params;
+  k.lik_w = a->lik_weights; k.alpha = a->alpha; k.partial = (float*)a->workspace;
+  size_t smem = sizeof(float) * 2 * kAdjTile * adj_stride(k.HA);
+  if (kind == DUST_MODEL_PARTICLE && a->model->grid_bits) smem += sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32);
+  DUST_REQUIRE(smem <= 227 * 1024, DUST_ERR_UNSUPPORTED, "dust_rollout_adjoint: H*A=%d needs %zu B of shared memory", k.HA, smem);
+  const long long gx = (long long)a->B * pl.tiles;
+  DUST_REQUIRE(gx < (1ll << 31), DUST_ERR_UNSUPPORTED, "dust_rollout_adjoint: grid too large");
+  dim3 grid((unsigned)gx, (unsigned)pl.PC, 1);
+  if (kind == DUST_MODEL_PENDULUM) {
+    if (a->H <= 32) rc = launch_adjoint<DUST_MODEL_PENDULUM, 32>(k, grid, smem, stream);
+    else if (a->H <= 64) rc = launch_adjoint<DUST_MODEL_PENDULUM, 64>(k, grid, smem, stream);
+    else rc = launch_adjoint<DUST_MODEL_PENDULUM, 128>(k, grid, smem, stream);
+  } else {
+    if (a->H <= 32) rc = launch_adjoint<DUST_MODEL_PARTICLE, 32>(k, grid, smem, stream);
+    else if (a->H <= 64) rc = launch_adjoint<DUST_MODEL_PARTICLE, 64>(k, grid, smem, stream);
+    else rc = launch_adjoint<DUST_MODEL_PARTICLE, 128>(k, grid, smem, stream);
+  }
+  if (rc) return rc;
+  const int W = a->N * k.HA;
+  { DUST_TIMED("reduce_partials_kernel", stream); reduce_partials_kernel<<<dim3((unsigned)ceil_div(W, 256), (unsigned)a->B, 1), 256, 0, stream>>>(
+      k.partial, a->grad_theta, W, pl.tiles * pl.PC); }
+  DUST_LAUNCH_OK("reduce_partials_kernel");
+  return DUST_OK;
+}

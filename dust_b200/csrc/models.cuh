@@ -1,0 +1,120 @@
+// Device-side forward models and costs.  Every translation unit that includes this file is
+// compiled with -fmad=false: the expressions below follow the reference's float32 op order
+// one rounding at a time, so the particle trajectories are bit-identical
+// to the CPU reference and the pendulum ones differ only by sinf/cosf ulps.
+#pragma once
+#include "common.cuh"
+
+namespace dust {
+
+constexpr float kPiF = 3.14159274101257324f;  // (float)math.pi  (pendulum.py:95)
+
+// ---------------------------------------------------------------------------------------
+// inverted pendulum  (dust/models/pendulum.py:84-100)
+// ---------------------------------------------------------------------------------------
+struct PendulumCoef {
+  float c1, c2;  // c1 = (-3 g)/(2 l),  c2 = 3/(m l^2)
+};
+
+// With sampled (tensor) parameters torch evaluates `scalar / tensor` as reciprocal(tensor) * scalar
+// (Tensor.__rtruediv__); with the python-float defaults the quotient is formed in double first.
+__device__ __forceinline__ PendulumCoef pendulum_coef_sampled(const ModelParams& m, float length, float mass) {
+  PendulumCoef c;
+  const float neg3g = (float)(-3.0 * (double)m.g);
+  c.c1 = __fmul_rn(__frcp_rn(__fmul_rn(2.0f, length)), neg3g);
+  c.c2 = __fmul_rn(__frcp_rn(__fmul_rn(mass, __fmul_rn(length, length))), 3.0f);
+  return c;
+}
+__device__ __forceinline__ PendulumCoef pendulum_coef_default(const ModelParams& m) {
+  PendulumCoef c;
+  const double l = (double)m.default_length, ms = (double)m.default_mass;
+  c.c1 = (float)(-3.0 * (double)m.g / (2.0 * l));
+  c.c2 = (float)(3.0 / (ms * l * l));
+  return c;
+}
+
+// one step; returns the pre-clamp angular speed through *pre (the adjoint needs the mask)
+__device__ __forceinline__ void pendulum_step(const ModelParams& m, const PendulumCoef& c, float& th, float& om,
+                                              float a, float* pre_out = nullptr) {
+  const float u = fminf(fmaxf(a, -m.max_torque), m.max_torque);
+  const float s = sinf(th + kPiF);
+  const float acc = c.c1 * s + c.c2 * u;
+  float pre = om + m.dt * acc;
+  if (pre_out) *pre_out = pre;
+  om = fminf(fmaxf(pre, -m.max_speed_pend), m.max_speed_pend);
+  th = th + om * m.dt;
+}
+
+// demo/pendulum_example.py:21-28
+__device__ __forceinline__ float pendulum_cost(const ModelParams& m, float th, float om) {
+  float t = cosf(th) - 1.0f;
+  t = t * t;
+  return m.w_angle * t + m.w_speed * (om * om);
+}
+
+// ---------------------------------------------------------------------------------------
+// 2-D point mass among obstacles  (dust/models/particle.py:136-225, dust/utils/obstacle_map.py:64-93)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ float grid_lookup(const ModelParams& m, const uint32_t* __restrict__ bits, float x, float y) {
+  float fx = floorf(x * m.inv_cell + m.c_offset[0]);
+  float fy = floorf(y * m.inv_cell + m.c_offset[1]);
+  fx = fminf(fmaxf(fx, 0.0f), (float)(m.grid_nx - 1));
+  fy = fminf(fmaxf(fy, 0.0f), (float)(m.grid_ny - 1));
+  const int cell = (int)fx * m.grid_ny + (int)fy;
+  return (float)((bits[cell >> 5] >> (cell & 31)) & 1u);
+}
+
+struct ParticleState {
+  float x, y, vx, vy;
+};
+
+// c: occupancy (0/1) of the CURRENT cell (shared by the step and the instantaneous cost)
+__device__ __forceinline__ void particle_step(const ModelParams& m, ParticleState& s, float ax, float ay, float mass,
+                                              float c, float* vpre = nullptr) {
+  const float ux = fminf(fmaxf(ax / mass, -m.max_accel), m.max_accel);
+  const float uy = fminf(fmaxf(ay / mass, -m.max_accel), m.max_accel);
+  float nx, ny, nvx, nvy;
+  if (m.can_crash) {
+    const float k = 1.0f - c;
+    nx = s.x + (s.vx * m.dt) * k;
+    ny = s.y + (s.vy * m.dt) * k;
+    nvx = s.vx + (ux * m.dt) * k;
+    nvy = s.vy + (uy * m.dt) * k;
+  } else {
+    nx = s.x + s.vx * m.dt;
+    ny = s.y + s.vy * m.dt;
+    nvx = s.vx + ux * m.dt;
+    nvy = s.vy + uy * m.dt;
+  }
+  if (vpre) { vpre[0] = nvx; vpre[1] = nvy; }
+  s.x = nx;
+  s.y = ny;
+  s.vx = fminf(fmaxf(nvx, -m.max_speed), m.max_speed);
+  s.vy = fminf(fmaxf(nvy, -m.max_speed), m.max_speed);
+}
+
+__device__ __forceinline__ float particle_quad(const ParticleState& s, const float* tgt, const float* w) {
+  const float d0 = s.x - tgt[0], d1 = s.y - tgt[1], d2 = s.vx - tgt[2], d3 = s.vy - tgt[3];
+  float acc = (d0 * d0) * w[0];
+  acc = acc + (d1 * d1) * w[1];
+  acc = acc + (d2 * d2) * w[2];
+  acc = acc + (d3 * d3) * w[3];
+  return acc;
+}
+
+// particle.py:170-198 (raw actions in the control term); c = occupancy of the current cell
+__device__ __forceinline__ float particle_inst_cost(const ModelParams& m, const ParticleState& s, float ax, float ay, float c) {
+  const float sc = particle_quad(s, m.target, m.w_state);
+  const float cc = (ax * ax) * m.w_ctrl[0] + (ay * ay) * m.w_ctrl[1];
+  float cost = sc + cc;
+  if (m.with_obstacle) cost = cost + m.w_obs * c;
+  return cost;
+}
+// particle.py:202-225
+__device__ __forceinline__ float particle_term_cost(const ModelParams& m, const ParticleState& s, float c) {
+  float cost = particle_quad(s, m.target, m.w_term);
+  if (m.with_obstacle) cost = cost + m.w_obs * c;
+  return cost;
+}
+
+}  // namespace dust

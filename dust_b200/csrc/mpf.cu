@@ -1,0 +1,252 @@
+// MPF: SVGD over dynamics-parameter particles, every optimisation step inside one launch
+// (one CTA per MPC instance; particles, scores and the pairwise work live in shared memory).
+// Also the stand-alone model step / cost entry points used by the host-side drivers.
+//
+// Reference: dust/inference/mpf.py:40-86, dust/inference/likelihoods.py:30-49 (one model step
+// per parameter particle; the autograd call of mpf.py:50 is replaced by the closed-form
+// Jacobian of each shipped model, SURVEY.md §9 "MPF one-step").
+// Compiled with -fmad=false (models.cuh).
+#include "models.cuh"
+
+namespace dust {
+
+constexpr int kMpfThreads = 256;
+constexpr int kMaxDp = 2;
+
+struct MpfKParams {
+  ModelParams m;
+  int B, Np, dp, n_steps, log_space;
+  float* x;
+  const float *obs0, *action, *obs1, *prior_inv_var;
+  float inv_obs_var, bw, lr;
+  float* grad_norms;
+};
+
+// d log N(obs1; f(obs0, a; p), obs_std^2 I) / d x  for one particle (x = p or log p)
+template <int MODEL>
+__device__ __forceinline__ void mpf_lik_grad(const ModelParams& m, const float* xp, int log_space, const float* o0,
+                                             const float* act, const float* o1, float inv_obs_var, float c_cell,
+                                             float* g) {
+  if (MODEL == DUST_MODEL_PENDULUM) {
+    const float l = log_space ? expf(xp[0]) : xp[0];
+    const float ms = log_space ? expf(xp[1]) : xp[1];
+    const PendulumCoef cf = pendulum_coef_sampled(m, l, ms);
+    float th = o0[0], om = o0[1], pre;
+    const float a = act[0];
+    const float u = fminf(fmaxf(a, -m.max_torque), m.max_torque);
+    const float sn = sinf(th + kPiF);
+    pendulum_step(m, cf, th, om, a, &pre);
+    const float r_th = (o1[0] - th) * inv_obs_var, r_om = (o1[1] - om) * inv_obs_var;
+    const bool in8 = pre >= -m.max_speed_pend && pre <= m.max_speed_pend;
+    // d om'/d l = dt (3g/(2 l^2) sin(th+pi) - 6u/(m l^3)),  d om'/d m = -dt 3u/(m^2 l^2);  th' = th + dt om'
+    const float dom_dl = in8 ? m.dt * (3.0f * m.g / (2.0f * l * l) * sn - 6.0f * u / (ms * l * l * l)) : 0.f;
+    const float dom_dm = in8 ? m.dt * (-3.0f * u / (ms * ms * l * l)) : 0.f;
+    const float w = r_th * m.dt + r_om;
+    g[0] = w * dom_dl * (log_space ? l : 1.0f);
+    g[1] = w * dom_dm * (log_space ? ms : 1.0f);
+  } else {
+    const float ms = log_space ? expf(xp[0]) : xp[0];
+    ParticleState s{o0[0], o0[1], o0[2], o0[3]};
+    float vpre[2];
+    const float ax = act[0], ay = act[1];
+    particle_step(m, s, ax, ay, ms, c_cell, vpre);
+    const float kk = m.can_crash ? m.dt * (1.0f - c_cell) : m.dt;
+    const float amx = ax / ms, amy = ay / ms;
+    const bool max_ = amx >= -m.max_accel && amx <= m.max_accel, may_ = amy >= -m.max_accel && amy <= m.max_accel;
+    const bool mvx = vpre[0] >= -m.max_speed && vpre[0] <= m.max_speed, mvy = vpre[1] >= -m.max_speed && vpre[1] <= m.max_speed;
+    const float r_vx = (o1[2] - s.vx) * inv_obs_var, r_vy = (o1[3] - s.vy) * inv_obs_var;
+    float gm = 0.f;
+    if (max_ && mvx) gm += r_vx * kk * (-ax / (ms * ms));
+    if (may_ && mvy) gm += r_vy * kk * (-ay / (ms * ms));
+    g[0] = gm * (log_space ? ms : 1.0f);
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kMpfThreads) mpf_kernel(const MpfKParams k) {
+  constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
+  constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
+  constexpr int DA = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  extern __shared__ float sm[];
+  float* xs = sm;                       // [Np][DP]
+  float* sc = sm + k.Np * DP;           // [Np][DP] score
+  float* ph = sc + k.Np * DP;           // [Np][DP] phi
+  __shared__ float red[kMpfThreads / 32];
+  __shared__ float s_cell;
+  const long long inst = blockIdx.x;
+  float* xg = k.x + inst * (long long)k.Np * DP;
+  float o0[DS], o1[DS], act[DA], piv[DP];
+#pragma unroll
+  for (int i = 0; i < DS; ++i) { o0[i] = k.obs0[inst * DS + i]; o1[i] = k.obs1[inst * DS + i]; }
+#pragma unroll
+  for (int i = 0; i < DA; ++i) act[i] = k.action[inst * DA + i];
+#pragma unroll
+  for (int i = 0; i < DP; ++i) piv[i] = k.prior_inv_var[i];
+  for (int e = threadIdx.x; e < k.Np * DP; e += kMpfThreads) xs[e] = xg[e];
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+    if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits) c = grid_lookup(k.m, k.m.grid_bits, o0[0], o0[1]);
+    s_cell = c;
+  }
+  __syncthreads();
+  const float c_cell = s_cell;
+  const float inv_bw2 = 1.0f / (k.bw * k.bw);
+  const float inv_np = 1.0f / (float)k.Np;
+
+  for (int step = 0; step < k.n_steps; ++step) {
+    // score_i = grad log-likelihood + grad log GMM(x_i; centres = current particles)
+    for (int i = threadIdx.x; i < k.Np; i += kMpfThreads) {
+      float xi[DP], g[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) xi[d] = xs[i * DP + d];
+      mpf_lik_grad<MODEL>(k.m, xi, k.log_space, o0, act, o1, k.inv_obs_var, c_cell, g);
+      float mx = -INFINITY;
+      for (int j = 0; j < k.Np; ++j) {
+        float q = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { const float df = xi[d] - xs[j * DP + d]; q += df * df * piv[d]; }
+        mx = fmaxf(mx, -0.5f * q);
+      }
+      float z = 0.f, acc[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) acc[d] = 0.f;
+      for (int j = 0; j < k.Np; ++j) {
+        float q = 0.f;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { const float df = xi[d] - xs[j * DP + d]; q += df * df * piv[d]; }
+        const float e = expf(-0.5f * q - mx);
+        z += e;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) acc[d] += e * (xs[j * DP + d] - xi[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < DP; ++d) sc[i * DP + d] = g[d] + acc[d] / z * piv[d];
+    }
+    __syncthreads();
+    // phi_i = (1/Np) sum_j K_ij s_j - (1/bw^2) sum_j K_ij (x_i - x_j)     (mpf.py:53-56)
+    float nrm = 0.f;
+    for (int i = threadIdx.x; i < k.Np; i += kMpfThreads) {
+      float xi[DP], acc[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) { xi[d] = xs[i * DP + d]; acc[d] = 0.f; }
+      for (int j = 0; j < k.Np; ++j) {
+        float d2 = 0.f, df[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { df[d] = xi[d] - xs[j * DP + d]; d2 += df[d] * df[d]; }
+        const float kij = expf(-d2 * inv_bw2 * 0.5f);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) acc[d] += kij * (inv_np * sc[j * DP + d] - inv_bw2 * df[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < DP; ++d) { ph[i * DP + d] = acc[d]; nrm += acc[d] * acc[d]; }
+    }
+    nrm = warp_sum(nrm);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+    __syncthreads();
+    if (threadIdx.x == 0 && k.grad_norms) {
+      float t = 0.f;
+      for (int w = 0; w < kMpfThreads / 32; ++w) t += red[w];
+      k.grad_norms[inst * k.n_steps + step] = sqrtf(t);
+    }
+    for (int e = threadIdx.x; e < k.Np * DP; e += kMpfThreads) xs[e] = xs[e] + k.lr * ph[e];  // SGD (mpf.py:59-62)
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < k.Np * DP; e += kMpfThreads) xg[e] = xs[e];
+}
+
+template <int MODEL>
+__global__ void model_step_kernel(const ModelParams m, int M, const float* __restrict__ states,
+                                  const float* __restrict__ actions, const float* __restrict__ params,
+                                  float* __restrict__ next) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  if (MODEL == DUST_MODEL_PENDULUM) {
+    const PendulumCoef cf = params ? pendulum_coef_sampled(m, params[2 * i], params[2 * i + 1]) : pendulum_coef_default(m);
+    float th = states[2 * i], om = states[2 * i + 1];
+    pendulum_step(m, cf, th, om, actions[i]);
+    next[2 * i] = th;
+    next[2 * i + 1] = om;
+  } else {
+    ParticleState s{states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+    const float c = m.grid_bits ? grid_lookup(m, m.grid_bits, s.x, s.y) : 0.f;
+    particle_step(m, s, actions[2 * i], actions[2 * i + 1], params ? params[i] : m.default_mass, c);
+    next[4 * i] = s.x; next[4 * i + 1] = s.y; next[4 * i + 2] = s.vx; next[4 * i + 3] = s.vy;
+  }
+}
+
+template <int MODEL>
+__global__ void model_cost_kernel(const ModelParams m, int M, int terminal, const float* __restrict__ states,
+                                  const float* __restrict__ actions, float* __restrict__ costs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  if (MODEL == DUST_MODEL_PENDULUM) {
+    costs[i] = pendulum_cost(m, states[2 * i], states[2 * i + 1]);
+  } else {
+    ParticleState s{states[4 * i], states[4 * i + 1], states[4 * i + 2], states[4 * i + 3]};
+    const float c = m.grid_bits ? grid_lookup(m, m.grid_bits, s.x, s.y) : 0.f;
+    if (terminal) costs[i] = particle_term_cost(m, s, c);
+    else costs[i] = particle_inst_cost(m, s, actions ? actions[2 * i] : 0.f, actions ? actions[2 * i + 1] : 0.f, c);
+  }
+}
+
+}  // namespace dust
+
+using namespace dust;
+
+extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
+  DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_mpf_optimize: args is NULL");
+  int rc = validate_model(a->model);
+  if (rc) return rc;
+  DUST_REQUIRE(a->B > 0 && a->Np > 0 && a->n_steps >= 0, DUST_ERR_INVALID_ARG, "dust_mpf_optimize: sizes must be positive");
+  DUST_REQUIRE(a->x && a->obs0 && a->action && a->obs1 && a->prior_inv_var, DUST_ERR_INVALID_ARG,
+               "dust_mpf_optimize: x, obs0, action, obs1, prior_inv_var are required");
+  DUST_REQUIRE(a->obs_std > 0.f && a->bw > 0.f, DUST_ERR_INVALID_ARG, "dust_mpf_optimize: obs_std and bw must be positive");
+  const int kind = a->model->kind, dp = model_dp(kind);
+  const size_t smem = sizeof(float) * 3 * (size_t)a->Np * dp;
+  DUST_REQUIRE(smem <= 200 * 1024, DUST_ERR_UNSUPPORTED, "dust_mpf_optimize: Np=%d too large for one CTA", a->Np);
+  MpfKParams k;
+  k.m = to_params(*a->model);
+  k.B = a->B; k.Np = a->Np; k.dp = dp; k.n_steps = a->n_steps; k.log_space = a->log_space;
+  k.x = a->x; k.obs0 = a->obs0; k.action = a->action; k.obs1 = a->obs1; k.prior_inv_var = a->prior_inv_var;
+  k.inv_obs_var = 1.0f / (a->obs_std * a->obs_std); k.bw = a->bw; k.lr = a->lr; k.grad_norms = a->grad_norms;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (kind == DUST_MODEL_PENDULUM) {
+    if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(mpf_kernel<DUST_MODEL_PENDULUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { DUST_TIMED("mpf_kernel", stream); mpf_kernel<DUST_MODEL_PENDULUM><<<a->B, kMpfThreads, smem, stream>>>(k); }
+  } else {
+    if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(mpf_kernel<DUST_MODEL_PARTICLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { DUST_TIMED("mpf_kernel", stream); mpf_kernel<DUST_MODEL_PARTICLE><<<a->B, kMpfThreads, smem, stream>>>(k); }
+  }
+  DUST_LAUNCH_OK("mpf_kernel");
+  return DUST_OK;
+}
+
+extern "C" int dust_model_step(const dust_model_desc* model, int32_t M, const float* states, const float* actions,
+                               const float* params, float* next_states, void* stream_) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  DUST_REQUIRE(M > 0 && states && actions && next_states, DUST_ERR_INVALID_ARG, "dust_model_step: bad arguments");
+  const ModelParams m = to_params(*model);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (model->kind == DUST_MODEL_PENDULUM)
+    { DUST_TIMED("model_step_kernel", stream); model_step_kernel<DUST_MODEL_PENDULUM><<<ceil_div(M, 128), 128, 0, stream>>>(m, M, states, actions, params, next_states); }
+  else
+    { DUST_TIMED("model_step_kernel", stream); model_step_kernel<DUST_MODEL_PARTICLE><<<ceil_div(M, 128), 128, 0, stream>>>(m, M, states, actions, params, next_states); }
+  DUST_LAUNCH_OK("model_step_kernel");
+  return DUST_OK;
+}
+
+extern "C" int dust_model_cost(const dust_model_desc* model, int32_t M, int32_t terminal, const float* states,
+                               const float* actions, float* costs, void* stream_) {
+  int rc = validate_model(model);
+  if (rc) return rc;
+  DUST_REQUIRE(M > 0 && states && costs, DUST_ERR_INVALID_ARG, "dust_model_cost: bad arguments");
+  const ModelParams m = to_params(*model);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (model->kind == DUST_MODEL_PENDULUM)
+    { DUST_TIMED("model_cost_kernel", stream); model_cost_kernel<DUST_MODEL_PENDULUM><<<ceil_div(M, 128), 128, 0, stream>>>(m, M, terminal, states, actions, costs); }
+  else
+    { DUST_TIMED("model_cost_kernel", stream); model_cost_kernel<DUST_MODEL_PARTICLE><<<ceil_div(M, 128), 128, 0, stream>>>(m, M, terminal, states, actions, costs); }
+  DUST_LAUNCH_OK("model_cost_kernel");
+  return DUST_OK;
+}

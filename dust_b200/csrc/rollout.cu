@@ -1,0 +1,443 @@
+// K1: batched rollout + trajectory cost, then the per-policy soft-min / likelihood reductions.
+// One thread per trajectory (sample s, policy n) of one MPC instance; the state lives in
+// registers, the action tile is staged through shared memory, parameter samples are looped
+// inside the thread so the mean over P needs no communication.
+//
+// Reference: dust/controllers/disco.py:139-209 (rollout), :294-346 (cost), :380-393 (soft-min),
+// dust/inference/likelihoods.py:81-135, dust/inference/svmpc.py:46-54.
+// Compiled with -fmad=false (see models.cuh).
+#include "models.cuh"
+
+namespace dust {
+
+constexpr int kTile = 128;  // trajectories (threads) per CTA
+
+__host__ __device__ inline int padded_stride(int HA) {
+  // row stride (floats) of the action tile in shared memory: a multiple of 4 whose quarter is
+  // odd, so that 16-byte row reads by consecutive threads hit distinct bank groups.
+  int s4 = (HA + 3) / 4;
+  if ((s4 & 1) == 0) s4 += 1;
+  return s4 * 4;
+}
+
+struct RolloutKParams {
+  ModelParams m;
+  int B, N, S, P, H, A;
+  int SN;          // S*N trajectories per instance
+  int HA;          // H*A
+  int PC;          // number of parameter chunks (grid.y)
+  int Pchunk;      // parameters per chunk
+  int interleaved;
+  const float* state0;
+  const float* theta;
+  const float* noise;
+  const float* sigma;
+  const float* params;
+  float* cost_out;     // PC==1: costs [B,S,N] (already divided by P); else partial sums [B,PC,SN]
+  float* states;       // optional [B,P,S,N,H+1,ds]
+};
+
+// cooperative load of a [rows, HA] tile of the noise tensor into padded shared memory, fused
+// with actions = theta + sigma * eps (likelihoods.py:85-90; exact: one product, one sum).
+template <int A>
+__device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float* tile, int stride, long long inst,
+                                                 int j0, int rows) {
+  const int HA = k.HA;
+  const float* __restrict__ src = k.noise + (inst * k.SN + j0) * (long long)HA;
+  const float* __restrict__ th = k.theta ? k.theta + inst * (long long)k.N * HA : nullptr;
+  const int NHA = k.N * HA;
+  const bool vec = ((HA & 3) == 0) && ((((uintptr_t)src) & 15) == 0) && (!th || ((((uintptr_t)th) & 15) == 0));
+  if (vec) {
+    const int HA4 = HA >> 2;
+    const int total4 = rows * HA4;
+    float sg[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sg[q] = th ? k.sigma[q % A] : 0.f;
+    for (int e = threadIdx.x; e < total4; e += kTile) {
+      const int row = e / HA4, c4 = e - row * HA4;
+      float4 v = __ldg(reinterpret_cast<const float4*>(src) + e);
+      if (th) {
+        // theta offset of this float4: ((j0+row) % N) * HA + 4*c4
+        const int n = (j0 + row) % k.N;
+        const float4 t = __ldg(reinterpret_cast<const float4*>(th + n * HA) + c4);
+        v.x = t.x + sg[0] * v.x;
+        v.y = t.y + sg[1] * v.y;
+        v.z = t.z + sg[2] * v.z;
+        v.w = t.w + sg[3] * v.w;
+      }
+      *reinterpret_cast<float4*>(tile + row * stride + 4 * c4) = v;
+    }
+  } else {
+    const int total = rows * HA;
+    const int wrap0 = (int)(((long long)j0 * HA) % NHA);
+    for (int e = threadIdx.x; e < total; e += kTile) {
+      const int row = e / HA, c = e - row * HA;
+      float v = __ldg(src + e);
+      if (th) {
+        const int to = (wrap0 + e) % NHA;
+        v = __ldg(th + to) + k.sigma[c % A] * v;
+      }
+      tile[row * stride + c] = v;
+    }
+  }
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParams k) {
+  constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
+  constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
+  extern __shared__ __align__(16) float smem[];
+  const int stride = padded_stride(k.HA);
+  float* tile = smem;  // [kTile][stride]
+  uint32_t* grid_s = reinterpret_cast<uint32_t*>(smem + kTile * stride);
+
+  const int tiles_per_inst = (k.SN + kTile - 1) / kTile;
+  const long long inst = blockIdx.x / tiles_per_inst;
+  const int j0 = (blockIdx.x - (int)inst * tiles_per_inst) * kTile;
+  const int rows = min(kTile, k.SN - j0);
+  const int pc = blockIdx.y;
+
+  load_action_tile<A>(k, tile, stride, inst, j0, rows);
+  if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
+    const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += kTile) grid_s[w] = __ldg(k.m.grid_bits + w);
+  }
+  __syncthreads();
+
+  const int row = threadIdx.x;
+  if (row >= rows) return;
+  const int j = j0 + row;
+  const float* __restrict__ arow = tile + row * stride;
+  const float* __restrict__ x0 = k.state0 + inst * DS;
+  const int p_begin = pc * k.Pchunk;
+  const int p_end = min(k.P, p_begin + k.Pchunk);
+
+  float csum = 0.f;
+  for (int p = p_begin; p < p_end; ++p) {
+    const float* prm = nullptr;
+    if (k.params) {
+      const int pi = k.interleaved ? (int)(((long long)p * k.SN + j) % k.P) : p;
+      prm = k.params + (inst * k.P + pi) * DP;
+    }
+    float* st_out = nullptr;
+    if (k.states) st_out = k.states + (((inst * k.P + p) * k.SN + j) * (long long)(k.H + 1)) * DS;
+    float cost = 0.f;
+    if (MODEL == DUST_MODEL_PENDULUM) {
+      const PendulumCoef cf = prm ? pendulum_coef_sampled(k.m, __ldg(prm), __ldg(prm + 1)) : pendulum_coef_default(k.m);
+      float th = __ldg(x0), om = __ldg(x0 + 1);
+      if (st_out) { st_out[0] = th; st_out[1] = om; }
+#pragma unroll 4
+      for (int t = 0; t < k.H; ++t) {
+        cost = cost + pendulum_cost(k.m, th, om);
+        pendulum_step(k.m, cf, th, om, arow[t]);
+        if (st_out) { st_out[(t + 1) * 2] = th; st_out[(t + 1) * 2 + 1] = om; }
+      }
+      cost = cost + pendulum_cost(k.m, th, om);
+    } else {
+      const float mass = prm ? __ldg(prm) : k.m.default_mass;
+      ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
+      if (st_out) { st_out[0] = s.x; st_out[1] = s.y; st_out[2] = s.vx; st_out[3] = s.vy; }
+      const bool has_grid = k.m.grid_bits != nullptr;
+#pragma unroll 2
+      for (int t = 0; t < k.H; ++t) {
+        const float ax = arow[2 * t], ay = arow[2 * t + 1];
+        const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
+        cost = cost + particle_inst_cost(k.m, s, ax, ay, c);
+        particle_step(k.m, s, ax, ay, mass, c);
+        if (st_out) {
+          float* o = st_out + (t + 1) * 4;
+          o[0] = s.x; o[1] = s.y; o[2] = s.vx; o[3] = s.vy;
+        }
+      }
+      const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
+      cost = cost + particle_term_cost(k.m, s, c);
+    }
+    csum = csum + cost;
+  }
+  if (k.PC == 1) {
+    k.cost_out[inst * k.SN + j] = csum / (float)k.P;  // mean over parameter samples (disco.py:330)
+  } else {
+    k.cost_out[(inst * k.PC + pc) * (long long)k.SN + j] = csum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// per-policy statistics: combine parameter chunks, log-likelihood, soft-min weights, mixture
+// one CTA per instance; warp w handles policies w, w+nwarps, ...
+// ---------------------------------------------------------------------------------------
+struct SoftminKParams {
+  int B, N, S, P, PC, SN;
+  int likelihood;
+  float alpha, inv_temp;
+  const float* cost_part;  // [B,PC,SN] when PC>1 (else costs already final)
+  float* costs;            // [B,S,N]
+  float* log_lik;          // [B,N] or null
+  float* lik_w;            // [B,S,N] or null
+  float* mppi_w;           // [B,S,N] or null
+  float* mix;              // [B,N] or null
+};
+
+constexpr int kSoftminThreads = 256;
+
+__global__ void __launch_bounds__(kSoftminThreads) policy_softmin_kernel(const SoftminKParams k) {
+  extern __shared__ float sm_eta[];  // [N] eta_n
+  const long long inst = blockIdx.x;
+  float* costs = k.costs + inst * k.SN;
+  if (k.PC > 1) {
+    const float* part = k.cost_part + inst * (long long)k.PC * k.SN;
+    for (int j = threadIdx.x; j < k.SN; j += blockDim.x) {
+      float acc = 0.f;
+      for (int c = 0; c < k.PC; ++c) acc = acc + part[(long long)c * k.SN + j];
+      costs[j] = acc / (float)k.P;
+    }
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const bool need_mppi = (k.mppi_w != nullptr) || (k.mix != nullptr);
+  for (int n = warp; n < k.N; n += nwarps) {
+    float cmin = INFINITY, csum = 0.f;
+    for (int s = lane; s < k.S; s += 32) {
+      const float c = costs[s * k.N + n];
+      cmin = fminf(cmin, c);
+      csum += c;
+    }
+    cmin = warp_min(cmin);
+    csum = warp_sum(csum);
+    float za = 0.f, zt = 0.f;
+    for (int s = lane; s < k.S; s += 32) {
+      const float c = costs[s * k.N + n];
+      za += expf(-k.alpha * (c - cmin));
+      if (need_mppi) zt += expf(-(c - cmin) * k.inv_temp);
+    }
+    za = warp_sum(za);
+    zt = warp_sum(zt);
+    if (k.log_lik && lane == 0) {
+      float ll;
+      if (k.likelihood == DUST_LIK_EXP_UTILITY)
+        ll = (-k.alpha * cmin + logf(za)) - logf((float)k.S);  // likelihoods.py:133-135
+      else
+        ll = -k.alpha * (csum / (float)k.S);                   // likelihoods.py:119
+      k.log_lik[inst * k.N + n] = ll;
+    }
+    const float inv_za = 1.f / za, inv_zt = need_mppi ? 1.f / zt : 0.f;
+    for (int s = lane; s < k.S; s += 32) {
+      const float c = costs[s * k.N + n];
+      if (k.lik_w) k.lik_w[inst * k.SN + s * k.N + n] = expf(-k.alpha * (c - cmin)) * inv_za;
+      if (k.mppi_w) k.mppi_w[inst * k.SN + s * k.N + n] = expf(-(c - cmin) * k.inv_temp) * inv_zt;
+    }
+    if (need_mppi && lane == 0) sm_eta[n] = -cmin * k.inv_temp + logf(zt);  // eta_n + beta/temp
+  }
+  if (k.mix) {
+    __syncthreads();
+    // a_mix = softmax_n(eta) (disco.py:393); the global shift beta cancels
+    if (warp == 0) {
+      float mx = -INFINITY;
+      for (int n = lane; n < k.N; n += 32) mx = fmaxf(mx, sm_eta[n]);
+      mx = warp_max(mx);
+      float z = 0.f;
+      for (int n = lane; n < k.N; n += 32) z += expf(sm_eta[n] - mx);
+      z = warp_sum(z);
+      for (int n = lane; n < k.N; n += 32) k.mix[inst * k.N + n] = expf(sm_eta[n] - mx) / z;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// weighted column sums over the [S, N*H*A] noise block of one instance:
+//   grad_lik[n,c]   = sum_s lik_w[s,n]  * ((theta + sigma*eps) - theta) / sigma^2     (svmpc.py:52-54)
+//   mppi_delta[n,c] = sum_s mppi_w[s,n] * pert[s,n,c]                                 (disco.py:387-392)
+// grid = (column chunks, B); thread <-> one column (n, c), rows strided over row groups.
+// ---------------------------------------------------------------------------------------
+struct ColsumKParams {
+  int B, N, S, HA, A, W;  // W = N*HA
+  const float* theta;     // [B,N,HA] or null
+  const float* noise;     // [B,S,W]
+  const float* sigma;     // [A]
+  const float* a_seq;     // [B,HA] or null
+  const float* pert;      // [B,S,W] or null
+  const float* lik_w;     // [B,S,N]
+  const float* mppi_w;    // [B,S,N]
+  float* grad_lik;        // [B,W] or null
+  float* mppi_delta;      // [B,W] or null
+};
+
+constexpr int kColsumThreads = 256;
+
+__global__ void __launch_bounds__(kColsumThreads) weighted_colsum_kernel(const ColsumKParams k) {
+  __shared__ float red_g[kColsumThreads], red_d[kColsumThreads];
+  const long long inst = blockIdx.y;
+  const int W = k.W;
+  // columns handled by this CTA: [col0, col0 + cols)
+  const int cols_per_cta = min(W, kColsumThreads);
+  const int col0 = blockIdx.x * cols_per_cta;
+  const int cols = min(cols_per_cta, W - col0);
+  const int groups = kColsumThreads / cols_per_cta;  // row groups when W < threads
+  const int g = threadIdx.x / cols_per_cta;
+  const int cl = threadIdx.x - g * cols_per_cta;
+  float accg = 0.f, accd = 0.f;
+  const bool active = (g < groups) && (cl < cols);
+  if (active) {
+    const int col = col0 + cl;
+    const int n = col / k.HA, c = col - n * k.HA;
+    const float sg = k.sigma ? k.sigma[c % k.A] : 1.f;
+    const float sg2 = sg * sg;
+    const float th = k.theta ? k.theta[inst * W + col] : 0.f;
+    const float aseq = k.a_seq ? k.a_seq[inst * k.HA + c] : 0.f;
+    const float* __restrict__ nz = k.noise + inst * (long long)k.S * W + col;
+    const float* __restrict__ pt = k.pert ? k.pert + inst * (long long)k.S * W + col : nullptr;
+    const float* __restrict__ lw = k.lik_w ? k.lik_w + inst * (long long)k.S * k.N + n : nullptr;
+    const float* __restrict__ mw = k.mppi_w ? k.mppi_w + inst * (long long)k.S * k.N + n : nullptr;
+    for (int s = g; s < k.S; s += groups) {
+      const float e = __ldg(nz + (long long)s * W);
+      const float a = k.theta ? (th + sg * e) : e;
+      if (k.grad_lik) accg += __ldg(lw + s * k.N) * ((a - th) / sg2);
+      if (k.mppi_delta) {
+        const float pv = pt ? __ldg(pt + (long long)s * W) : (a - aseq);
+        accd += __ldg(mw + s * k.N) * pv;
+      }
+    }
+  }
+  if (groups > 1) {
+    red_g[threadIdx.x] = accg;
+    red_d[threadIdx.x] = accd;
+    __syncthreads();
+    if (g == 0 && cl < cols) {
+      for (int q = 1; q < groups; ++q) {
+        accg += red_g[q * cols_per_cta + cl];
+        accd += red_d[q * cols_per_cta + cl];
+      }
+    }
+  }
+  if (g == 0 && cl < cols) {
+    if (k.grad_lik) k.grad_lik[inst * W + col0 + cl] = accg;
+    if (k.mppi_delta) k.mppi_delta[inst * W + col0 + cl] = accd;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+static int choose_param_chunks(long long BSN, int P) {
+  const long long target_threads = (long long)kNumSMs * 2048 * 2;
+  if (P <= 1 || BSN >= target_threads) return 1;
+  long long pc = (target_threads + BSN - 1) / BSN;
+  if (pc > P) pc = P;
+  return (int)pc;
+}
+
+struct RolloutPlan {
+  int PC, Pchunk;
+  size_t off_part, off_likw, off_mppiw, off_costs, total;
+};
+
+static RolloutPlan plan_rollout(const dust_rollout_args* a) {
+  RolloutPlan pl{};
+  const long long SN = (long long)a->S * a->N;
+  const int P = a->params ? a->P : 1;
+  int pc = choose_param_chunks((long long)a->B * SN, P);
+  const int chunk = (P + pc - 1) / pc;
+  pc = (P + chunk - 1) / chunk;
+  pl.PC = pc;
+  pl.Pchunk = chunk;
+  size_t off = 0;
+  auto take = [&](bool needed, size_t bytes) {
+    const size_t o = off;
+    if (needed) off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t per_traj = sizeof(float) * (size_t)a->B * (size_t)SN;
+  pl.off_part = take(pc > 1, per_traj * pc);
+  pl.off_likw = take(a->grad_lik && !a->lik_weights, per_traj);
+  pl.off_mppiw = take(a->mppi_delta && !a->mppi_weights, per_traj);
+  pl.off_costs = take(!a->costs, per_traj);
+  pl.total = off;
+  return pl;
+}
+
+}  // namespace dust
+
+using namespace dust;
+
+extern "C" size_t dust_rollout_workspace_bytes(const dust_rollout_args* a) {
+  if (!a || a->B <= 0 || a->N <= 0 || a->S <= 0) return 0;
+  return plan_rollout(a).total;
+}
+
+extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_rollout_cost: args is NULL");
+  int rc = validate_model(a->model);
+  if (rc) return rc;
+  DUST_REQUIRE(a->B > 0 && a->N > 0 && a->S > 0 && a->H > 0, DUST_ERR_INVALID_ARG,
+               "dust_rollout_cost: B,N,S,H must be positive (got %d,%d,%d,%d)", a->B, a->N, a->S, a->H);
+  DUST_REQUIRE(a->state0 && a->noise, DUST_ERR_INVALID_ARG, "dust_rollout_cost: state0 and noise are required");
+  DUST_REQUIRE(!a->theta || a->sigma, DUST_ERR_INVALID_ARG, "dust_rollout_cost: sigma is required with theta");
+  DUST_REQUIRE(!a->params || a->P > 0, DUST_ERR_INVALID_ARG, "dust_rollout_cost: P must be positive with params");
+  DUST_REQUIRE(!a->grad_lik || a->theta, DUST_ERR_INVALID_ARG,
+               "dust_rollout_cost: grad_lik needs theta (analytic score of N(theta, sigma^2))");
+  DUST_REQUIRE(a->alpha > 0.f && a->temperature > 0.f, DUST_ERR_INVALID_ARG,
+               "dust_rollout_cost: alpha and temperature must be positive");
+  const int kind = a->model->kind;
+  const int A = model_da(kind);
+  const int P = a->params ? a->P : 1;
+  const long long SN = (long long)a->S * a->N;
+  DUST_REQUIRE(SN < (1ll << 30), DUST_ERR_UNSUPPORTED, "dust_rollout_cost: S*N too large");
+
+  const RolloutPlan pl = plan_rollout(a);
+  DUST_REQUIRE(pl.total == 0 || (a->workspace && a->workspace_bytes >= pl.total), DUST_ERR_WORKSPACE,
+               "dust_rollout_cost: workspace needs %zu bytes, got %zu", pl.total, a->workspace_bytes);
+  char* ws = (char*)a->workspace;
+  float* costs = a->costs ? a->costs : (float*)(ws + pl.off_costs);
+  float* part = pl.PC > 1 ? (float*)(ws + pl.off_part) : nullptr;
+  float* likw = a->lik_weights ? a->lik_weights : ((a->grad_lik) ? (float*)(ws + pl.off_likw) : nullptr);
+  float* mppiw = a->mppi_weights ? a->mppi_weights : ((a->mppi_delta) ? (float*)(ws + pl.off_mppiw) : nullptr);
+
+  RolloutKParams k;
+  k.m = to_params(*a->model);
+  k.B = a->B; k.N = a->N; k.S = a->S; k.P = P; k.H = a->H; k.A = A;
+  k.SN = (int)SN; k.HA = a->H * A; k.PC = pl.PC; k.Pchunk = pl.Pchunk;
+  k.interleaved = a->param_tiling == DUST_PARAMS_INTERLEAVED;
+  k.state0 = a->state0; k.theta = a->theta; k.noise = a->noise; k.sigma = a->sigma; k.params = a->params;
+  k.cost_out = pl.PC > 1 ? part : costs;
+  k.states = a->states;
+
+  const int stride = padded_stride(k.HA);
+  size_t smem = sizeof(float) * kTile * stride;
+  if (kind == DUST_MODEL_PARTICLE && a->model->grid_bits) smem += sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32);
+  DUST_REQUIRE(smem <= 227 * 1024, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: H*A=%d needs %zu B of shared memory", k.HA, smem);
+  const int tiles = ceil_div(SN, kTile);
+  const long long gx = (long long)a->B * tiles;
+  DUST_REQUIRE(gx < (1ll << 31) && pl.PC <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: grid too large");
+  dim3 grid((unsigned)gx, (unsigned)pl.PC, 1);
+  if (kind == DUST_MODEL_PENDULUM) {
+    if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<DUST_MODEL_PENDULUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<DUST_MODEL_PENDULUM><<<grid, kTile, smem, stream>>>(k); }
+  } else {
+    if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<DUST_MODEL_PARTICLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<DUST_MODEL_PARTICLE><<<grid, kTile, smem, stream>>>(k); }
+  }
+  DUST_LAUNCH_OK("rollout_cost_kernel");
+
+  const bool need_stats = pl.PC > 1 || a->log_lik || likw || mppiw || a->mix;
+  if (need_stats) {
+    SoftminKParams s;
+    s.B = a->B; s.N = a->N; s.S = a->S; s.P = P; s.PC = pl.PC; s.SN = (int)SN;
+    s.likelihood = a->likelihood; s.alpha = a->alpha; s.inv_temp = 1.0f / a->temperature;
+    s.cost_part = part; s.costs = costs; s.log_lik = a->log_lik; s.lik_w = likw; s.mppi_w = mppiw; s.mix = a->mix;
+    { DUST_TIMED("policy_softmin_kernel", stream); policy_softmin_kernel<<<a->B, kSoftminThreads, sizeof(float) * a->N, stream>>>(s); }
+    DUST_LAUNCH_OK("policy_softmin_kernel");
+  }
+  if (a->grad_lik || a->mppi_delta) {
+    ColsumKParams c;
+    c.B = a->B; c.N = a->N; c.S = a->S; c.HA = k.HA; c.A = A; c.W = a->N * k.HA;
+    c.theta = a->theta; c.noise = a->noise; c.sigma = a->theta ? a->sigma : nullptr; c.a_seq = a->a_seq; c.pert = a->pert;
+    c.lik_w = likw; c.mppi_w = mppiw; c.grad_lik = a->grad_lik; c.mppi_delta = a->mppi_delta;
+    const int cols_per_cta = c.W < kColsumThreads ? c.W : kColsumThreads;
+    dim3 g2((unsigned)ceil_div(c.W, cols_per_cta), (unsigned)a->B, 1);
+    DUST_REQUIRE(a->B <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: B > 65535 with gradient outputs");
+    { DUST_TIMED("weighted_colsum_kernel", stream); weighted_colsum_kernel<<<g2, kColsumThreads, 0, stream>>>(c); }
+    DUST_LAUNCH_OK("weighted_colsum_kernel");
+  }
+  return DUST_OK;
+}

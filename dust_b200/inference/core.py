@@ -1,0 +1,106 @@
+"""Batched engine behind SVMPC: B independent MPC instances advance together, one kernel
+launch per stage.  The drop-in `SVMPC` class is this engine with B = 1.
+
+Stage order per control step (dust/inference/svmpc.py:87-126, 172-200):
+  K3 prior score -> K1 rollout/cost/likelihood/analytic gradient [-> K2 adjoint] ->
+  K5 phi + SGD update -> K7 weights / argmax / shift / prior refresh.
+"""
+import math
+
+import torch
+
+from .. import _lib as L
+from .. import ops
+
+GPYTORCH_DEFAULT_LENGTHSCALE = math.log(2.0)
+
+
+class SvmpcCore:
+    def __init__(self, spec, theta, mu, mix, prior_var, sigma, alpha=1.0, temperature=1.0, lr=1.0,
+                 kernel="gpytorch", lengthscale=GPYTORCH_DEFAULT_LENGTHSCALE, bw_scale=1.0,
+                 likelihood=L.LIK_EXP_UTILITY, grad="analytic", roll_strategy="repeat", weighted_prior=False,
+                 aliased=False):
+        """theta, mu [B,N,H,A]; mix [B,N]; prior_var [A] (diagonal, shared by all components);
+        sigma [A]."""
+        self.spec = spec
+        self.theta, self.mu, self.mix = theta.contiguous(), mu.contiguous(), mix.contiguous()
+        self.B, self.N, self.H, self.A = theta.shape
+        self.D = self.H * self.A
+        dev = theta.device
+        self.sigma = torch.as_tensor(sigma, dtype=torch.float32).to(dev).contiguous()
+        self.set_prior_var(prior_var)
+        self.alpha, self.temperature, self.lr = float(alpha), float(temperature), float(lr)
+        if kernel not in ("gpytorch", "mp"):
+            raise NotImplementedError(f"kernel mode {kernel!r}")
+        self.kernel, self.lengthscale, self.bw_scale = kernel, float(lengthscale), float(bw_scale)
+        self.likelihood = likelihood
+        if grad not in ("analytic", "pathwise"):
+            raise ValueError(grad)
+        self.grad = grad
+        if roll_strategy not in ("repeat", "mean"):
+            if roll_strategy == "resample":
+                raise NotImplementedError("roll_strategy='resample' (device RNG) is not available yet")
+            raise ValueError("{} is an invalid roll strategy.".format(roll_strategy))
+        self.roll_strategy = L.ROLL_REPEAT if roll_strategy == "repeat" else L.ROLL_MEAN
+        self.weighted_prior = bool(weighted_prior)
+        self.aliased = bool(aliased)
+        self.last = {}
+
+    def set_prior_var(self, prior_var):
+        dev = self.theta.device
+        pv = torch.as_tensor(prior_var, dtype=torch.float32).reshape(-1).cpu()
+        if pv.numel() == 1:
+            pv = pv.expand(self.A)
+        self.prior_var = pv.clone()
+        full = pv.repeat(self.H)
+        self.inv_var = (1.0 / full).to(dev).contiguous()
+        self.log_norm = ops.gmm_log_norm(full)
+
+    def _flat(self, t):
+        return t.reshape(self.B, self.N, self.D)
+
+    def optimize_step(self, state0, eps, params=None, tiling=L.PARAMS_BLOCKED, want_states=False):
+        """One SVGD step on the policy particles.  state0 [B,ds], eps [B,S,N,H,A] standard normal,
+        params [B,P,dp] | None.  Updates theta in place of the old tensor (new storage)."""
+        mu = self.theta if self.aliased else self.mu
+        _, grad_pri = ops.gmm(self._flat(self.theta), self._flat(mu), self.mix, self.inv_var, self.log_norm,
+                              want_log_prob=False)
+        want = ["costs", "log_lik", "lik_weights"]
+        if self.grad == "analytic":
+            want.append("grad_lik")
+        if want_states:
+            want.append("states")
+        out = ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
+                               param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
+                               temperature=self.temperature, want=tuple(want))
+        if self.grad == "analytic":
+            grad_lik = out["grad_lik"]
+        else:
+            grad_lik = ops.rollout_adjoint(self.spec, state0, eps, out["lik_weights"], theta=self.theta,
+                                           sigma=self.sigma, params=params, param_tiling=tiling,
+                                           likelihood=self.likelihood, alpha=self.alpha)
+        score = grad_lik.reshape(self.B, self.N, self.D) + grad_pri
+        x = self._flat(self.theta)
+        if self.kernel == "gpytorch":
+            ell2 = self.lengthscale ** 2
+            res = ops.svgd_phi(x, score, gamma=1.0 / (2.0 * ell2), c1=1.0 / self.N, c2=-1.0 / ell2, lr=self.lr,
+                               want_update=True)
+        else:
+            res = ops.svgd_phi(x, score, per_dim=True, bw_scale=self.bw_scale, lr=self.lr, want_update=True)
+        self.theta = res["x_out"].reshape(self.B, self.N, self.H, self.A)
+        self.last = dict(costs=out["costs"], log_lik=out["log_lik"], grad_lik=grad_lik, grad_pri=grad_pri,
+                         phi=res["phi"].reshape(self.B, self.N, self.H, self.A), states=out.get("states"),
+                         lik_weights=out["lik_weights"])
+        return self.last
+
+    def forward_step(self, log_lik=None):
+        """Weights, best particle, shift, prior refresh.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])."""
+        log_lik = self.last["log_lik"] if log_lik is None else log_lik
+        mu = self.theta if self.aliased else self.mu
+        out = ops.svmpc_forward(log_lik, self.theta, mu, self.mix, self.inv_var, self.log_norm,
+                                roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior)
+        self.theta = out["theta_next"]
+        self.mu = self.theta
+        self.mix = out["mix_next"]
+        self.aliased = True
+        return out["a_seq"], out["p_weights"], out["i_star"]

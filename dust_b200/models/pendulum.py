@@ -1,0 +1,117 @@
+"""Inverted pendulum (dust/models/pendulum.py:61-100) and the swing-up cost of the pendulum
+demo (demo/pendulum_example.py:21-28), both evaluated by CUDA kernels."""
+import math
+
+import torch
+
+from .. import _lib as L
+from .. import ops
+from ..utils.spaces import Box
+from .base import BaseModel, DeviceModelSpec
+
+
+class SwingUpCost:
+    """cost = w_angle (cos th - 1)^2 + w_speed thd^2; callable with the reference's cost-function
+    signature (`inst(states, controls=None, n_pol=1, debug=None)`)."""
+
+    def __init__(self, w_angle=50.0, w_speed=1.0, terminal=False):
+        self.w_angle, self.w_speed, self.terminal = float(w_angle), float(w_speed), terminal
+
+    def __call__(self, states, controls=None, n_pol=1, debug=None):
+        theta, theta_d = states.chunk(2, dim=1)
+        c = self.w_angle * (theta.cos() - 1) ** 2 + self.w_speed * theta_d ** 2
+        return c.squeeze() if self.terminal else c
+
+
+inst_cost = SwingUpCost()
+term_cost = SwingUpCost(terminal=True)
+
+
+def _match_swingup(fn):
+    """Recognise a python cost callable of the swing-up family by probing it on a few states
+    (lets demo/pendulum_example.py's own `inst_cost` run unchanged).  Returns (w_angle, w_speed)
+    or None."""
+    if isinstance(fn, SwingUpCost):
+        return fn.w_angle, fn.w_speed
+    try:
+        probe = torch.tensor([[0.0, 0.0], [math.pi, 0.0], [0.0, 1.0], [1.0, 2.0], [-2.5, -3.0], [4.0, 0.5]])
+        with torch.no_grad():
+            vals = torch.as_tensor(fn(probe)).reshape(-1).double()
+        if vals.numel() != probe.shape[0] or abs(float(vals[0])) > 1e-9:
+            return None
+        w_angle = float(vals[1]) / 4.0
+        w_speed = float(vals[2])
+        th, om = probe[:, 0].double(), probe[:, 1].double()
+        fit = w_angle * (th.cos() - 1) ** 2 + w_speed * om ** 2
+        if float((fit - vals).abs().max()) <= 1e-4 * (1.0 + float(vals.abs().max())):
+            return w_angle, w_speed
+    except Exception:
+        return None
+    return None
+
+
+class PendulumModel(BaseModel):
+    device_param_order = ("length", "mass")
+
+    def __init__(self, g=9.8, mass=1.0, length=1.0, **kwargs):
+        super().__init__(params_dict={"g": g, "mass": mass, "length": length}, **kwargs)
+        self._max_speed, self._max_torque = 8.0, 2.0
+        bounds = torch.tensor([float("inf"), self._max_speed])
+        self._observation_space = Box(dim=2, low=-bounds, high=bounds, dtype=torch.float)
+        self._action_space = Box(dim=1, low=-self._max_torque, high=self._max_torque, dtype=torch.float)
+
+    @property
+    def observation_space(self):
+        return self._observation_space
+
+    @property
+    def action_space(self):
+        return self._action_space
+
+    def defaults_are_tensors(self):
+        """With tensor-valued defaults torch evaluates the dynamics coefficients through
+        reciprocal()*scalar in float32 (as for sampled parameters) instead of in double."""
+        return any(torch.is_tensor(self.params_dict[k]) for k in ("mass", "length"))
+
+    def device_spec(self, inst_cost_fn=None, term_cost_fn=None, device="cuda"):
+        w = (50.0, 1.0)
+        for fn in (inst_cost_fn, term_cost_fn):
+            if fn is None:
+                continue
+            m = _match_swingup(fn)
+            if m is None:
+                raise NotImplementedError(
+                    "PendulumModel: only costs of the swing-up family w_angle*(cos(th)-1)^2 + w_speed*thd^2 "
+                    "have a device kernel (dust_b200.models.pendulum.SwingUpCost); got %r" % (fn,))
+            w = m
+        if inst_cost_fn is not None and term_cost_fn is not None:
+            if _match_swingup(inst_cost_fn) != _match_swingup(term_cost_fn):
+                raise NotImplementedError("PendulumModel: instantaneous and terminal cost weights must agree")
+        d = L.ModelDesc()
+        d.kind, d.dt = L.MODEL_PENDULUM, float(self.dt)
+        d.g = float(self.params_dict["g"])
+        d.max_torque, d.max_speed_pend = self._max_torque, self._max_speed
+        d.w_angle, d.w_speed = w
+        d.default_length, d.default_mass = float(self.params_dict["length"]), float(self.params_dict["mass"])
+        return DeviceModelSpec(d, L.MODEL_PENDULUM)
+
+    def step(self, states, actions, params_dict=None):
+        """One transition for a batch of (state, action[, params]) rows, on the GPU."""
+        L.require_cuda()
+        dev = torch.device("cuda")
+        st = torch.as_tensor(states, dtype=torch.float32).reshape(-1, 2).to(dev).contiguous()
+        M = st.shape[0]
+        ac = torch.as_tensor(actions, dtype=torch.float32).reshape(-1, 1).to(dev).expand(M, 1).contiguous()
+        if params_dict is None and self.defaults_are_tensors():
+            params_dict = {}
+        prm = self._dict_to_device_params(params_dict, M, dev)
+        out = ops.model_step(self.device_spec(), st, ac, prm)
+        return out.reshape(torch.as_tensor(states).shape)
+
+    @staticmethod
+    def get_obs(state):
+        try:
+            theta, theta_d = state.chunk(2, dim=1)
+        except ValueError:
+            raise ValueError("Dimension 1 of state tensor must be exactly 2.")
+        return torch.cat([torch.cos(theta), torch.sin(theta), theta_d], dim=1)

@@ -1,0 +1,230 @@
+"""Functional wrappers over the C ABI: allocate outputs / scratch as torch CUDA tensors,
+fill the argument struct, enqueue on the current stream.  All tensors carry a leading
+instance dimension B."""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+
+def _f32(t, device):
+    """float32, contiguous, on `device` (host tensors are copied over)."""
+    if t is None:
+        return None
+    t = torch.as_tensor(t)
+    if t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+        t = t.to(device=device, dtype=torch.float32).contiguous()
+    return t
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=device)
+
+
+def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param_tiling=L.PARAMS_BLOCKED,
+                 likelihood=L.LIK_EXP_UTILITY, a_seq=None, pert=None, alpha=1.0, temperature=1.0,
+                 want=("costs", "log_lik"), out=None):
+    """K1.  noise [B,S,N,H,A]; theta [B,N,H,A] or None (noise = actions); params [B,P,dp] or None.
+    `want` subset of {costs, log_lik, lik_weights, grad_lik, mppi_weights, mppi_delta, mix, states}.
+    Returns a dict of CUDA tensors."""
+    L.require_cuda()
+    dev = noise.device
+    B, S, N, H, A = noise.shape
+    assert A == spec.da, f"action dim {A} != model's {spec.da}"
+    P = 1 if params is None else params.shape[1]
+    out = {} if out is None else out
+    shapes = {
+        "costs": (B, S, N), "log_lik": (B, N), "lik_weights": (B, S, N), "grad_lik": (B, N, H, A),
+        "mppi_weights": (B, S, N), "mppi_delta": (B, N, H, A), "mix": (B, N),
+        "states": (B, P, S, N, H + 1, spec.ds),
+    }
+    for k in want:
+        if k not in out:
+            out[k] = torch.empty(shapes[k], dtype=torch.float32, device=dev)
+    a = L.RolloutArgs()
+    a.model = C.pointer(spec.desc)
+    a.B, a.N, a.S, a.P, a.H = B, N, S, P, H
+    a.param_tiling, a.likelihood = param_tiling, likelihood
+    a.state0, a.theta, a.noise = L.ptr(state0), L.ptr(theta), L.ptr(noise)
+    a.sigma, a.params, a.a_seq, a.pert = L.ptr(sigma), L.ptr(params), L.ptr(a_seq), L.ptr(pert)
+    a.alpha, a.temperature = float(alpha), float(temperature)
+    for k in shapes:
+        setattr(a, k, L.ptr(out.get(k)) if k in want else None)
+    nbytes = L.load().dust_rollout_workspace_bytes(C.byref(a))
+    ws = _ws(nbytes, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    L.call("dust_rollout_cost", C.byref(a), L.stream(), launches=3)
+    return out
+
+
+def rollout_adjoint(spec, state0, noise, lik_weights, theta=None, sigma=None, params=None,
+                    param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0):
+    """K2.  Returns grad_theta [B,N,H,A] = d sum_n log_l_n / d theta (pathwise)."""
+    L.require_cuda()
+    dev = noise.device
+    B, S, N, H, A = noise.shape
+    P = 1 if params is None else params.shape[1]
+    g = torch.empty((B, N, H, A), dtype=torch.float32, device=dev)
+    a = L.AdjointArgs()
+    a.model = C.pointer(spec.desc)
+    a.B, a.N, a.S, a.P, a.H = B, N, S, P, H
+    a.param_tiling, a.likelihood = param_tiling, likelihood
+    a.state0, a.theta, a.noise, a.sigma = L.ptr(state0), L.ptr(theta), L.ptr(noise), L.ptr(sigma)
+    a.params, a.lik_weights, a.alpha = L.ptr(params), L.ptr(lik_weights), float(alpha)
+    a.grad_theta, a.grad_params = L.ptr(g), None
+    nbytes = L.load().dust_adjoint_workspace_bytes(C.byref(a))
+    ws = _ws(nbytes, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    L.call("dust_rollout_adjoint", C.byref(a), L.stream(), launches=2)
+    return g
+
+
+def gmm(x, mu, mix, inv_var, log_norm, want_log_prob=True, want_score=True):
+    """K3.  x [B,M,D], mu [B,K,D], mix [B,K] | None, inv_var [D].  -> (log_prob [B,M], score [B,M,D])."""
+    L.require_cuda()
+    B, M, D = x.shape
+    K = mu.shape[1]
+    lp = torch.empty((B, M), dtype=torch.float32, device=x.device) if want_log_prob else None
+    sc = torch.empty((B, M, D), dtype=torch.float32, device=x.device) if want_score else None
+    a = L.GmmArgs(B, M, K, D, L.ptr(x), L.ptr(mu), L.ptr(mix), L.ptr(inv_var), float(log_norm),
+                  L.ptr(lp), L.ptr(sc))
+    L.call("dust_gmm_score", C.byref(a), L.stream())
+    return lp, sc
+
+
+def gmm_log_norm(var_full):
+    """-0.5 (D log 2pi + sum log var) for a diagonal covariance given as a [D] tensor."""
+    var_full = torch.as_tensor(var_full, dtype=torch.float64)
+    return float(-0.5 * (var_full.numel() * math.log(2 * math.pi) + var_full.log().sum()))
+
+
+def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, gamma_dev=None, per_dim=False, bw_scale=1.0, lr=0.0,
+             want_phi=True, want_update=False, rows=None, want_bandwidths=False):
+    """K5.  x, score [B,N,D].  Returns dict(phi=, x_out=, bandwidths=)."""
+    L.require_cuda()
+    B, N, D = x.shape
+    dev = x.device
+    phi = torch.empty_like(x) if want_phi else None
+    xo = torch.empty_like(x) if want_update else None
+    bws = torch.empty((B, D), dtype=torch.float32, device=dev) if (per_dim and want_bandwidths) else None
+    a = L.PhiArgs()
+    a.B, a.N, a.D = B, N, D
+    a.row_begin, a.row_end = (0, N) if rows is None else rows
+    a.per_dim = int(per_dim)
+    a.x, a.score = L.ptr(x), L.ptr(score)
+    a.gamma, a.c1, a.c2, a.gamma_dev = float(gamma), float(c1), float(c2), L.ptr(gamma_dev)
+    a.bw_scale, a.lr = float(bw_scale), float(lr)
+    a.phi, a.x_out, a.bandwidths = L.ptr(phi), L.ptr(xo), L.ptr(bws)
+    nbytes = L.load().dust_phi_workspace_bytes(C.byref(a))
+    ws = _ws(nbytes, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    L.call("dust_svgd_phi", C.byref(a), L.stream(), launches=2 if per_dim or N > 512 else 1)
+    return dict(phi=phi, x_out=xo, bandwidths=bws)
+
+
+class MedianWorkspace:
+    """Device scratch for the radix select: 65536 u64 bins, 4 u32 of state, N row norms."""
+
+    def __init__(self, N, device):
+        self.hist = torch.zeros(65536, dtype=torch.int64, device=device)
+        self.selected = torch.zeros(4, dtype=torch.int32, device=device)
+        self.row_norms = torch.empty(N, dtype=torch.float32, device=device)
+        self.median = torch.zeros(1, dtype=torch.float32, device=device)
+
+
+def median_sq_dist(x, ws=None, rows=None, all_reduce=None):
+    """K4.  Exact lower median of the N^2 clamped squared distances of x [N,D] (device scalar).
+    `rows` restricts the histogrammed row block; `all_reduce(hist)` (e.g. an NCCL sum) is called
+    between the histogram and the select of each pass when the rows are sharded over ranks."""
+    L.require_cuda()
+    N, D = x.shape
+    ws = ws or MedianWorkspace(N, x.device)
+    a = L.MedianArgs()
+    a.N, a.D = N, D
+    a.row_begin, a.row_end = (0, N) if rows is None else rows
+    a.x, a.hist, a.selected, a.row_norms = L.ptr(x), ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
+    ws.hist.zero_()
+    for p in (0, 1):
+        L.call("dust_median_hist_pass", C.byref(a), p, L.stream(), launches=2 if p == 0 else 1)
+        if all_reduce is not None:
+            all_reduce(ws.hist)
+        L.call("dust_median_select", C.byref(a), p, ws.median.data_ptr(), L.stream())
+    return ws.median
+
+
+def bandwidth_from_median(median, N, scale=1.0, mode=0):
+    """-> device tensor {gamma, c1, c2, bw|h}."""
+    out = torch.empty(4, dtype=torch.float32, device=median.device)
+    L.call("dust_bandwidth_from_median", median.data_ptr(), int(N), float(scale), int(mode), out.data_ptr(),
+           L.stream())
+    return out
+
+
+def svmpc_forward(log_lik, theta, mu, mix, inv_var, log_norm, roll_strategy=L.ROLL_REPEAT, weighted_prior=False):
+    """K7.  theta, mu [B,N,H,A].  Returns dict(p_weights, i_star, a_seq, theta_next, mix_next)."""
+    L.require_cuda()
+    B, N, H, A = theta.shape
+    dev = theta.device
+    out = dict(
+        p_weights=torch.empty((B, N), dtype=torch.float32, device=dev),
+        i_star=torch.empty((B,), dtype=torch.int32, device=dev),
+        a_seq=torch.empty((B, H, A), dtype=torch.float32, device=dev),
+        theta_next=torch.empty_like(theta),
+        mix_next=torch.empty((B, N), dtype=torch.float32, device=dev),
+    )
+    a = L.SvmpcForwardArgs(B, N, H, A, int(roll_strategy), int(bool(weighted_prior)), L.ptr(log_lik), L.ptr(theta),
+                           L.ptr(mu), L.ptr(mix), L.ptr(inv_var), float(log_norm), L.ptr(out["p_weights"]),
+                           L.ptr(out["i_star"]), L.ptr(out["a_seq"]), L.ptr(out["theta_next"]), L.ptr(out["mix_next"]))
+    L.call("dust_svmpc_forward", C.byref(a), L.stream())
+    return out
+
+
+def disco_step(a_mat, a_mix, a_low, a_high, strategy=L.SELECT_ARGMAX, steps=1):
+    """MultiDISCO.step.  a_mat [B,N,H,A] is updated IN PLACE.  -> (next_actions [B,steps,A], a_seq [B,H,A])."""
+    L.require_cuda()
+    B, N, H, A = a_mat.shape
+    dev = a_mat.device
+    a_seq = torch.empty((B, H, A), dtype=torch.float32, device=dev)
+    nxt = torch.empty((B, steps, A), dtype=torch.float32, device=dev)
+    a = L.DiscoStepArgs(B, N, H, A, int(strategy), int(steps), L.ptr(a_low), L.ptr(a_high), L.ptr(a_mat), L.ptr(a_mix),
+                        L.ptr(a_seq), L.ptr(nxt))
+    L.call("dust_disco_step", C.byref(a), L.stream())
+    return nxt, a_seq
+
+
+def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space):
+    """x [B,Np,dp] is updated IN PLACE.  -> grad_norms [B,n_steps]."""
+    L.require_cuda()
+    B, Np, dp = x.shape
+    assert dp == spec.dp, f"parameter dim {dp} != model's {spec.dp}"
+    gn = torch.empty((B, n_steps), dtype=torch.float32, device=x.device)
+    a = L.MpfArgs()
+    a.model = C.pointer(spec.desc)
+    a.B, a.Np, a.n_steps, a.log_space = B, Np, int(n_steps), int(bool(log_space))
+    a.x, a.obs0, a.action, a.obs1 = L.ptr(x), L.ptr(obs0), L.ptr(action), L.ptr(obs1)
+    a.prior_inv_var = L.ptr(prior_inv_var)
+    a.obs_std, a.bw, a.lr = float(obs_std), float(bw), float(lr)
+    a.grad_norms = L.ptr(gn)
+    L.call("dust_mpf_optimize", C.byref(a), L.stream())
+    return gn
+
+
+def model_step(spec, states, actions, params=None):
+    """states [M,ds], actions [M,A], params [M,dp] | None -> next states [M,ds]."""
+    L.require_cuda()
+    M = states.shape[0]
+    nxt = torch.empty_like(states)
+    L.call("dust_model_step", C.byref(spec.desc), M, L.ptr(states), L.ptr(actions), L.ptr(params), L.ptr(nxt),
+           L.stream())
+    return nxt
+
+
+def model_cost(spec, states, actions=None, terminal=False):
+    L.require_cuda()
+    M = states.shape[0]
+    c = torch.empty((M,), dtype=torch.float32, device=states.device)
+    L.call("dust_model_cost", C.byref(spec.desc), M, int(bool(terminal)), L.ptr(states), L.ptr(actions), L.ptr(c),
+           L.stream())
+    return c

@@ -1,0 +1,432 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors
+generated from the unmodified reference.  Tolerances are BASELINE.json's: costs / rollouts
+<= 1e-5 relative (float32), phi and updated particles <= 1e-4 relative, indices exact."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dust_oracle as O
+from tests.util import RTOL_COST, RTOL_PHI, assert_close_to_reference, golden_grid, load, rel_elem, rel_max
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def env():
+    from dust_b200 import _lib as L
+    from dust_b200.models.particle import Particle
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    env_params = dict(dt=0.015, control_type="acceleration", noise_std=[0.1, 0.1], init_state=[-9.0, -9.0, 0, 0],
+                      target_state=[9.0, 9.0, 0, 0], can_crash=True, with_obstacle=True, deterministic=True,
+                      cost_params=dict(w_qpos=0.5, w_qvel=0.25, w_ctrl=0.2, w_obs=1.0e6, w_qpos_T=1.0e3, w_qvel_T=0.1),
+                      obst_preset="grid_4x4", obst_width=2.1, max_speed=5, max_accel=10, map_cell_size=0.1,
+                      map_size=[22, 22], map_type="direct")
+    part = Particle(**env_params, uncertain_params=["mass"], mass=2.0)
+    pend = PendulumModel(uncertain_params=("length", "mass"))
+    return dict(
+        L=L, part=part, pend=pend,
+        spec=dict(particle=part.device_spec(part.default_inst_cost, part.default_term_cost, DEV),
+                  pendulum=pend.device_spec(inst_cost, term_cost, DEV)),
+        cfg=O.ParticleCfg(golden_grid()),
+    )
+
+
+def cu(t):
+    return None if t is None else torch.as_tensor(t, dtype=torch.float32).to(DEV).contiguous()
+
+
+def dev_params(kind, params, log_space):
+    """sampled params (golden layout) -> (kernel params [1,P,dp], tiling)."""
+    if params is None or params.numel() == 0:
+        return None, 0
+    p = params.exp() if log_space else params
+    tiling = 1 if p.ndim == 1 else 0
+    p = p.reshape(p.shape[0], -1)
+    return cu(p).unsqueeze(0), tiling
+
+
+# ---------------------------------------------------------------------------------------------
+# K1: rollout + cost + soft-min
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["pendulum", "particle"])
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_rollout_cost_vs_reference(env, kind, seed):
+    from dust_b200 import ops
+
+    d = load(f"fwd_{kind}_s{seed}")
+    params, tiling = dev_params(kind, d["params"], bool(d["log_space"]))
+    out = ops.rollout_cost(env["spec"][kind], cu(d["state"]).reshape(1, -1), cu(d["actions"]).unsqueeze(0),
+                           params=params, param_tiling=tiling, temperature=float(d["temp"]),
+                           want=("costs", "mppi_weights", "mppi_delta", "mix", "states"))
+    costs = out["costs"][0].cpu()
+    assert rel_elem(costs, d["costs"]) <= RTOL_COST
+    states = out["states"][0].cpu()
+    if kind == "particle":
+        # +, *, /, floor, clamp only: trajectories are bit-identical to the CPU reference
+        assert torch.equal(states[:, :8], d["states_sub"])
+        assert torch.equal(states[..., -1, :], d["states_last"])
+    else:
+        assert rel_max(states[:, :8], d["states_sub"]) <= RTOL_COST
+        assert rel_max(states[..., -1, :], d["states_last"]) <= RTOL_COST
+    assert float((out["mppi_weights"][0].cpu() - d["weights"]).abs().max()) <= 2e-5
+    assert rel_max(d["a_mat0"] + out["mppi_delta"][0].cpu(), d["a_mat1"]) <= 1e-4
+    assert float((out["mix"][0].cpu() - d["a_mix1"]).abs().max()) <= 2e-5
+
+
+def test_rollout_default_params_and_internal_sampling(env):
+    from dust_b200 import ops
+
+    d = load("fwd_pendulum_nops")  # N=8, S=256, H=20, P=1 (the batched-pendulum shape)
+    out = ops.rollout_cost(env["spec"]["pendulum"], cu(d["state"]).reshape(1, -1), cu(d["actions"]).unsqueeze(0),
+                           want=("costs",))
+    assert rel_elem(out["costs"][0].cpu(), d["costs"]) <= RTOL_COST
+    d = load("fwd_pendulum_internal")
+    eps = d["eps"] * d["sigma"]
+    out = ops.rollout_cost(env["spec"]["pendulum"], cu(d["state"]).reshape(1, -1), cu(eps + d["a_mat0"]).unsqueeze(0),
+                           params=cu(d["params"]).unsqueeze(0), pert=cu(eps).unsqueeze(0),
+                           want=("costs", "mppi_delta", "mix"))
+    assert rel_elem(out["costs"][0].cpu(), d["costs"]) <= RTOL_COST
+    assert rel_max(d["a_mat0"] + out["mppi_delta"][0].cpu(), d["a_mat1"]) <= 1e-4
+
+
+@pytest.mark.parametrize("name,kind,log", [("svmpc_pendulum_rbf", "pendulum", False), ("svmpc_particle_rbf", "particle", True),
+                                           ("dual_particle", "particle", True)])
+def test_fused_actions_likelihood_and_analytic_gradient(env, name, kind, log):
+    """theta + sigma*eps formed in-kernel; log-likelihood; svmpc.py:46-54 gradient."""
+    from dust_b200 import ops
+
+    d = load(name)
+    for t in range(int(d["n_steps"])):
+        gi, go = (lambda k: d[f"t{t}_in_{k}"]), (lambda k: d[f"t{t}_out_{k}"])
+        params, tiling = dev_params(kind, gi("params"), log)
+        out = ops.rollout_cost(env["spec"][kind], cu(gi("state")).reshape(1, -1), cu(gi("eps")).unsqueeze(0),
+                               theta=cu(gi("theta0")).unsqueeze(0), sigma=cu(d["sigma"]), params=params,
+                               param_tiling=tiling, alpha=1.0, want=("costs", "log_lik", "lik_weights", "grad_lik"))
+        costs = out["costs"][0].cpu()
+        assert rel_elem(costs, go("costs")) <= RTOL_COST
+        assert rel_max(out["log_lik"][0].cpu(), go("log_l")) <= RTOL_COST
+        actions = gi("theta0") + d["sigma"] * gi("eps")
+        g_ref = O.analytic_lik_grad(go("costs").double(), actions.double(), gi("theta0").double(), d["sigma"].double(), 1.0)
+        # the soft-min weights amplify cost differences by alpha: compare on the device's own costs too
+        g_dev = O.analytic_lik_grad(costs.double(), actions.double(), gi("theta0").double(), d["sigma"].double(), 1.0)
+        assert rel_max(out["grad_lik"][0].cpu(), g_dev) <= 1e-5
+        assert rel_max(out["grad_lik"][0].cpu(), g_ref) <= 5e-3
+
+
+def test_expected_cost_likelihood(env):
+    from dust_b200 import ops
+
+    d = load("fwd_pendulum_s0")
+    L = env["L"]
+    out = ops.rollout_cost(env["spec"]["pendulum"], cu(d["state"]).reshape(1, -1), cu(d["actions"]).unsqueeze(0),
+                           params=cu(d["params"]).unsqueeze(0), likelihood=L.LIK_EXPECTED_COST, alpha=0.5,
+                           want=("costs", "log_lik"))
+    assert rel_max(out["log_lik"][0].cpu(), O.expected_cost_log_prob(d["costs"], 0.5)) <= RTOL_COST
+
+
+def test_batched_instances_match_single_instance(env):
+    """B instances in one launch == B separate launches (bitwise), ragged S*N tile edge included."""
+    from dust_b200 import ops
+
+    torch.manual_seed(0)
+    B, S, N, H = 5, 37, 3, 11
+    for kind, ds, A, dp in (("pendulum", 2, 1, 2), ("particle", 4, 2, 1)):
+        state = torch.randn(B, ds, device=DEV)
+        if kind == "particle":
+            state = state * torch.tensor([6.0, 6.0, 1.0, 1.0], device=DEV)
+        theta = torch.randn(B, N, H, A, device=DEV)
+        eps = torch.randn(B, S, N, H, A, device=DEV)
+        sigma = torch.full((A,), 2.0, device=DEV)
+        params = torch.rand(B, 4, dp, device=DEV) + 0.7
+        want = ("costs", "log_lik", "grad_lik", "mix")
+        full = ops.rollout_cost(env["spec"][kind], state, eps, theta=theta, sigma=sigma, params=params, want=want)
+        for b in range(B):
+            one = ops.rollout_cost(env["spec"][kind], state[b:b + 1].contiguous(), eps[b:b + 1].contiguous(),
+                                   theta=theta[b:b + 1].contiguous(), sigma=sigma, params=params[b:b + 1].contiguous(),
+                                   want=want)
+            for k in want:
+                assert torch.equal(full[k][b], one[k][0]), (kind, k, b)
+        # and against the oracle
+        model = O.Model(kind, env["cfg"])
+        for b in (0, B - 1):
+            acts = (theta[b] + sigma * eps[b]).cpu()
+            ref = O.disco_forward(model, state[b].cpu(), acts, params[b].cpu())
+            assert rel_elem(full["costs"][b].cpu(), ref["costs"]) <= RTOL_COST
+
+
+# ---------------------------------------------------------------------------------------------
+# K3 GMM prior, K5 phi, K7 forward
+# ---------------------------------------------------------------------------------------------
+def test_gmm_score_and_log_prob(env):
+    from dust_b200 import ops
+
+    torch.manual_seed(1)
+    for (M, K, D) in ((3, 3, 30), (6, 6, 80), (50, 50, 2), (8, 8, 20), (33, 17, 200)):
+        x, mu = torch.randn(2, M, D), torch.randn(2, K, D)
+        mix = torch.rand(2, K)
+        mix[1, 0] = 0.0  # zero weight -> clamped to eps, not -inf (torch Categorical semantics)
+        var = torch.rand(D) + 0.5
+        lp, sc = ops.gmm(cu(x), cu(mu), cu(mix), cu(1.0 / var), ops.gmm_log_norm(var))
+        for b in range(2):
+            assert rel_max(lp[b].cpu(), O.gmm_log_prob(x[b].double(), mu[b].double(), mix[b].double(), var.double())) <= 1e-5
+            assert rel_max(sc[b].cpu(), O.gmm_score(x[b].double(), mu[b].double(), mix[b].double(), var.double())) <= 1e-4
+        lp2, _ = ops.gmm(cu(x), cu(mu), None, cu(1.0 / var), ops.gmm_log_norm(var), want_score=False)
+        assert rel_max(lp2[0].cpu(), O.gmm_log_prob(x[0].double(), mu[0].double(), torch.ones(K).double(), var.double())) <= 1e-5
+
+
+@pytest.mark.parametrize("N,D", [(3, 30), (6, 80), (8, 20), (64, 40), (200, 7)])
+def test_phi_small_all_variants(env, N, D):
+    from dust_b200 import ops
+
+    torch.manual_seed(N * 100 + D)
+    x, s = torch.randn(2, N, D) * 2.0, torch.randn(2, N, D)
+    for (gamma, c1, c2) in ((1 / (2 * O.GPYTORCH_DEFAULT_LENGTHSCALE ** 2), 1 / N, -1 / O.GPYTORCH_DEFAULT_LENGTHSCALE ** 2),
+                            (1 / (2 * 1.5 ** 2), 1 / N, 1 / (N * 1.5 ** 2)), (0.01, 1 / N, 2 * 0.01 / N)):
+        out = ops.svgd_phi(cu(x), cu(s), gamma=gamma, c1=c1, c2=c2, lr=0.25, want_update=True)
+        for b in range(2):
+            ref = O.phi_unified(x[b].double(), s[b].double(), gamma, c1, c2)
+            assert rel_max(out["phi"][b].cpu(), ref) <= RTOL_PHI
+            assert rel_max(out["x_out"][b].cpu(), x[b].double() + 0.25 * ref) <= RTOL_PHI
+    if N <= 64:
+        out = ops.svgd_phi(cu(x), cu(s), per_dim=True, want_bandwidths=True)
+        for b in range(2):
+            _, _, hs = O.iid_mp_eval(x[b], x[b].clone())
+            assert rel_max(out["bandwidths"][b].cpu(), hs) <= 1e-6
+            assert rel_max(out["phi"][b].cpu(), O.phi_svmpc_iid_mp(x[b], s[b])) <= RTOL_PHI
+
+
+def test_phi_row_range(env):
+    from dust_b200 import ops
+
+    torch.manual_seed(2)
+    x, s = cu(torch.randn(1, 40, 12)), cu(torch.randn(1, 40, 12))
+    full = ops.svgd_phi(x, s, gamma=0.05, c1=1 / 40, c2=0.01)["phi"]
+    part = torch.zeros_like(full)
+    for r in ((0, 13), (13, 40)):
+        a = ops.svgd_phi(x, s, gamma=0.05, c1=1 / 40, c2=0.01, rows=r)["phi"]
+        part[:, r[0]:r[1]] = a[:, r[0]:r[1]]
+    assert torch.equal(full, part)
+
+
+SEQ = [("svmpc_pendulum_rbf", "pendulum", "gpytorch"), ("svmpc_pendulum_mp", "pendulum", "mp"),
+       ("svmpc_particle_rbf", "particle", "gpytorch"), ("svmpc_particle_mp", "particle", "mp"),
+       ("dual_pendulum_bw", "pendulum", "gpytorch"), ("dual_particle", "particle", "gpytorch")]
+HYPER = {"pendulum": dict(alpha=1.0, lr=2.0, var=4.0, wp=False, log=False),
+         "particle": dict(alpha=1.0, lr=100.0, var=25.0, wp=True, log=True)}
+
+
+@pytest.mark.parametrize("name,kind,kern", SEQ)
+def test_svmpc_control_step_teacher_forced(env, name, kind, kern):
+    """SVMPC.optimize + SVMPC.forward on the recorded inputs of every control step."""
+    from dust_b200.inference.core import SvmpcCore
+
+    d = load(name)
+    c = HYPER[kind]
+    model = O.Model(kind, env["cfg"])
+    for t in range(int(d["n_steps"])):
+        gi, go = (lambda k: d[f"t{t}_in_{k}"]), (lambda k: d[f"t{t}_out_{k}"])
+        params, tiling = dev_params(kind, gi("params"), c["log"])
+        A = gi("theta0").shape[-1]
+        core = SvmpcCore(env["spec"][kind], cu(gi("theta0")).unsqueeze(0), cu(gi("mu0")).unsqueeze(0),
+                         cu(gi("mix0")).unsqueeze(0), torch.full((A,), c["var"]), d["sigma"], alpha=c["alpha"],
+                         temperature=1.0 / c["alpha"], lr=c["lr"], kernel=kern, weighted_prior=c["wp"], aliased=t > 0)
+        out = core.optimize_step(cu(gi("state")).reshape(1, -1), cu(gi("eps")).unsqueeze(0), params, tiling)
+        theta1 = core.theta[0].cpu()
+        a_seq, pw, i_star = core.forward_step()
+        # float64 restatement on the same inputs
+        st = O.SvmpcState(gi("theta0").double(), gi("mu0").double(), gi("mix0").double(), c["var"], aliased=t > 0)
+        p64 = gi("params").double() if gi("params").numel() else None
+        ref = O.svmpc_optimize(model, st, gi("state").double(), gi("eps").double(), d["sigma"].double(), p64,
+                               c["log"], c["alpha"], c["lr"], kernel="rbf" if kern == "gpytorch" else "mp")
+        assert rel_elem(out["costs"][0].cpu(), go("costs")) <= RTOL_COST
+        assert_close_to_reference(out["phi"][0].cpu(), go("phi"), ref["phi"], RTOL_PHI, f"{name} t{t} phi")
+        assert_close_to_reference(theta1, go("theta1"), ref["theta1"], RTOL_PHI, f"{name} t{t} theta1")
+        assert int(i_star[0]) == int(go("i_star"))
+        assert float((pw[0].cpu() - go("p_weights")).abs().max()) <= 1e-4
+        assert torch.equal(a_seq[0].cpu(), theta1[int(go("i_star"))])
+        rolled = theta1.roll(-1, dims=-2)
+        rolled[..., -1, :] = rolled[..., -2, :]
+        assert torch.equal(core.theta[0].cpu(), rolled)
+        mix2 = core.mix[0].cpu()
+        assert float((mix2 / mix2.sum() - go("mix2")).abs().max()) <= 1e-4
+
+
+def test_forward_mean_roll_and_argmax_ties(env):
+    from dust_b200 import ops
+
+    B, N, H, A = 3, 5, 7, 2
+    torch.manual_seed(3)
+    theta = torch.randn(B, N, H, A)
+    ll = torch.zeros(B, N)  # identical particles -> ties -> first index wins
+    theta[1] = theta[1, 0]
+    out = ops.svmpc_forward(cu(ll), cu(theta), cu(theta), None, cu(torch.ones(H * A)), 0.0, roll_strategy=1)
+    assert int(out["i_star"][1]) == 0
+    exp = theta.roll(-1, dims=-2)
+    exp[..., -1, :] = theta.mean(dim=-2)
+    assert rel_max(out["theta_next"].cpu(), exp) <= 1e-6
+    assert torch.equal(out["mix_next"].cpu(), torch.ones(B, N))
+
+
+@pytest.mark.parametrize("kind", ["pendulum", "particle"])
+def test_disco_step(env, kind):
+    from dust_b200 import ops
+
+    d = load(f"fwd_{kind}_s0")
+    lim = 2.0 if kind == "pendulum" else 10.0
+    A = d["a_mat1"].shape[-1]
+    lo, hi = cu(torch.full((A,), -lim)), cu(torch.full((A,), lim))
+    for strat, code in (("argmax", 0), ("average", 1)):
+        a_mat = cu(d["a_mat1"]).unsqueeze(0).clone()
+        nxt, a_seq = ops.disco_step(a_mat, cu(d["a_mix1"]).unsqueeze(0), lo, hi, code, 1)
+        assert rel_max(nxt[0].cpu(), d[f"step_{strat}_action"]) <= 1e-6
+        assert rel_max(a_seq[0].cpu(), d[f"step_{strat}_a_seq"]) <= 1e-6
+        assert rel_max(a_mat[0].cpu(), d[f"step_{strat}_a_mat"]) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 adjoint
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,kind,log", [("pathwise_pendulum_s4", "pendulum", False), ("pathwise_particle_s4", "particle", True),
+                                           ("pathwise_particle_s5", "particle", True)])
+def test_adjoint_matches_autograd_of_reference(env, name, kind, log):
+    from dust_b200 import ops
+
+    d = load(name)
+    params, tiling = dev_params(kind, d["params"], log)
+    args = dict(theta=cu(d["theta"]).unsqueeze(0), sigma=cu(d["sigma"]), params=params, param_tiling=tiling)
+    fwd = ops.rollout_cost(env["spec"][kind], cu(d["state"]).reshape(1, -1), cu(d["eps"]).unsqueeze(0), alpha=1.0,
+                           want=("costs", "log_lik", "lik_weights"), **args)
+    g = ops.rollout_adjoint(env["spec"][kind], cu(d["state"]).reshape(1, -1), cu(d["eps"]).unsqueeze(0),
+                            fwd["lik_weights"], alpha=1.0, **args)
+    assert rel_elem(fwd["costs"][0].cpu(), d["costs"]) <= RTOL_COST
+    g64 = O.pathwise_lik_grad_adjoint(O.Model(kind, env["cfg"]), d["state"].double(), d["theta"].double(), d["eps"].double(),
+                                      d["sigma"].double(), d["params"].double(), log, 1.0)[0]
+    assert_close_to_reference(g[0].cpu(), d["grad"], g64, RTOL_PHI, name)
+
+
+def test_adjoint_batched_and_expected_cost(env):
+    from dust_b200 import ops
+
+    torch.manual_seed(5)
+    L = env["L"]
+    B, S, N, H = 3, 19, 4, 9
+    for kind, ds, A, dp in (("pendulum", 2, 1, 2), ("particle", 4, 2, 1)):
+        state = torch.randn(B, ds) * (torch.tensor([6.0, 6.0, 1.0, 1.0]) if kind == "particle" else 1.0)
+        theta, eps = torch.randn(B, N, H, A), torch.randn(B, S, N, H, A)
+        sigma = torch.full((A,), 1.5)
+        params = torch.rand(B, 3, dp) + 0.7
+        model = O.Model(kind, env["cfg"])
+        for lik in (L.LIK_EXP_UTILITY, L.LIK_EXPECTED_COST):
+            fwd = ops.rollout_cost(env["spec"][kind], cu(state), cu(eps), theta=cu(theta), sigma=cu(sigma), params=cu(params),
+                                   likelihood=lik, alpha=0.7, want=("costs", "lik_weights"))
+            g = ops.rollout_adjoint(env["spec"][kind], cu(state), cu(eps), fwd["lik_weights"], theta=cu(theta),
+                                    sigma=cu(sigma), params=cu(params), likelihood=lik, alpha=0.7)
+            for b in range(B):
+                x = theta[b].double().clone().requires_grad_(True)
+                out = O.disco_forward(model, state[b].double(), x + sigma.double() * eps[b].double(), params[b].double())
+                ll = O.exp_utility_log_prob(out["costs"], 0.7) if lik == L.LIK_EXP_UTILITY else O.expected_cost_log_prob(out["costs"], 0.7)
+                (gr,) = torch.autograd.grad(ll.sum(), x)
+                assert rel_max(g[b].cpu(), gr) <= RTOL_PHI, (kind, lik, b)
+
+
+# ---------------------------------------------------------------------------------------------
+# MPF
+# ---------------------------------------------------------------------------------------------
+def test_mpf_against_reference(env):
+    from dust_b200 import ops
+
+    d = load("mpf_pendulum")
+    x = cu(d["x0"]).unsqueeze(0).clone()
+    gn = ops.mpf_optimize(env["spec"]["pendulum"], x, cu(d["obs0"]).reshape(1, -1), cu(d["action"]).reshape(1, -1),
+                          cu(d["obs1"]).reshape(1, -1), cu(torch.full((2,), 1 / 0.01)), 0.1, 0.1, 1e-3, 1, False)
+    phi0 = (x[0].cpu() - d["x0"]) / 1e-3
+    assert rel_max(phi0, d["phi0"]) <= 2e-3  # difference quotient of a float32 update
+    assert rel_max(gn[0, 0].cpu(), d["phi0"].norm()) <= RTOL_PHI
+    # 20 steps: unstable iteration (amplifies rounding ~1.4x per step) -> conditioning-aware bound
+    x = cu(d["x0"]).unsqueeze(0).clone()
+    ops.mpf_optimize(env["spec"]["pendulum"], x, cu(d["obs0"]).reshape(1, -1), cu(d["action"]).reshape(1, -1),
+                     cu(d["obs1"]).reshape(1, -1), cu(torch.full((2,), 1 / 0.01)), 0.1, 0.1, 1e-3, 20, False)
+    dd = {k: v.double() for k, v in d.items()}
+    x64, _ = O.mpf_optimize(O.Model("pendulum"), dd["x0"], dd["obs0"], dd["action"], dd["obs1"], 0.1, 0.01, 0.1, 1e-3, 20, False)
+    assert_close_to_reference(x[0].cpu(), d["x1"], x64, RTOL_PHI, "mpf pendulum x1")
+    d = load("mpf_particle")
+    x = cu(d["x0"]).unsqueeze(0).clone()
+    gn = ops.mpf_optimize(env["spec"]["particle"], x, cu(d["obs0"]).reshape(1, -1), cu(d["action"]).reshape(1, -1),
+                          cu(d["obs1"]).reshape(1, -1), cu(torch.full((1,), 1 / 0.01)), 0.1, 0.5, 0.01, 20, True)
+    assert rel_max(x[0].cpu(), d["x1"]) <= RTOL_PHI
+    assert rel_max(gn[0].cpu(), d["grad_norms"]) <= RTOL_PHI
+
+
+def test_mpf_dual_loop_steps(env):
+    from dust_b200 import ops
+
+    d = load("dual_particle")
+    for t in range(int(d["n_steps"])):
+        pv = float(d["mpf_prior_bw0"]) ** 2 if t == 0 else float(d[f"t{t-1}_out_mpf_bw"]) ** 2
+        x = cu(d[f"t{t}_in_mpf_x0"]).unsqueeze(0).clone()
+        ops.mpf_optimize(env["spec"]["particle"], x, cu(d[f"t{t}_in_state"]).reshape(1, -1),
+                         cu(d[f"t{t}_out_a_seq"][0]).reshape(1, -1), cu(d[f"t{t}_out_next_state"]).reshape(1, -1),
+                         cu(torch.full((1,), 1 / pv)), float(d["obs_std"]), float(d[f"t{t}_out_mpf_bw"]),
+                         float(d["mpf_lr"]), 20, True)
+        assert rel_max(x[0].cpu(), d[f"t{t}_out_mpf_x1"]) <= RTOL_PHI
+
+
+# ---------------------------------------------------------------------------------------------
+# K4 median + large-N phi
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [64, 257, 1024])
+def test_exact_median_and_svgd_phi_vs_reference(env, N):
+    from dust_b200 import ops
+
+    d = load(f"phi_svgd_N{N}")
+    x = cu(d["X"])
+    med = float(ops.median_sq_dist(x)[0])
+    # exact rank selection over the device's own float32 distances; the value agrees with the
+    # reference's MKL distances to rounding
+    assert abs(med - float(d["median_d2"])) <= 4e-6 * float(d["median_d2"])
+    bw = float(d["bw"])
+    out = ops.svgd_phi(x.unsqueeze(0), cu(d["score"]).unsqueeze(0), gamma=1 / (2 * bw * bw), c1=1 / N, c2=1 / (N * bw * bw))
+    p64 = O.phi_svgd(d["X"].double(), d["score"].double(), bw)
+    assert_close_to_reference(out["phi"][0].cpu(), d["phi"], p64, RTOL_PHI, f"phi N={N}")
+
+
+def test_median_is_exact_rank_statistic(env):
+    """Against a sort of the same float32 distance formula (odd/even N, duplicates, ragged tiles)."""
+    from dust_b200 import ops
+
+    torch.manual_seed(7)
+    for N, D in ((65, 3), (130, 40), (513, 8), (700, 17)):
+        X = torch.randn(N, D) * 3
+        X[N // 2:N // 2 + 5] = X[0]  # exact duplicates -> zero distances off the diagonal
+        med = float(ops.median_sq_dist(cu(X))[0])
+        d2 = O.sq_dists_addmm(X.double(), X.double())
+        srt = d2.reshape(-1).sort().values
+        k = (N * N - 1) // 2
+        lo, hi = float(srt[max(k - 3, 0)]), float(srt[min(k + 3, N * N - 1)])
+        assert lo - 1e-4 * abs(lo) - 1e-5 <= med <= hi + 1e-4 * abs(hi) + 1e-5
+
+
+def test_large_phi_properties(env):
+    """N = 4096: fused kernel vs float64 tiles; translation invariance; device-side bandwidth."""
+    from dust_b200 import ops
+
+    torch.manual_seed(11)
+    N, D = 4096, 40
+    X = torch.randn(N, D)
+    S = -X
+    x, s = cu(X).unsqueeze(0), cu(S).unsqueeze(0)
+    med = ops.median_sq_dist(x[0])
+    coef = ops.bandwidth_from_median(med, N, 1.0, 0)
+    out = ops.svgd_phi(x, s, gamma_dev=coef)
+    g, c1, c2, bw = [float(v) for v in coef.cpu()]
+    ref = O.phi_unified_tiled(X, S, g, c1, c2, tile=1024)
+    assert rel_max(out["phi"][0].cpu(), ref) <= RTOL_PHI
+    bw_ref, med_ref = O.bw_median(X)
+    assert abs(float(med[0]) - float(med_ref)) <= 4e-6 * float(med_ref)
+    assert abs(bw - float(bw_ref)) <= 1e-5 * float(bw_ref)
+    # rows split in blocks (what each rank computes) == the full result
+    a = ops.svgd_phi(x, s, gamma_dev=coef, rows=(0, 1500))["phi"]
+    b = ops.svgd_phi(x, s, gamma_dev=coef, rows=(1500, N))["phi"]
+    assert torch.equal(torch.cat([a[:, :1500], b[:, 1500:]], 1), out["phi"])
