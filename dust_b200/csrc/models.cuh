@@ -33,11 +33,52 @@ __device__ __forceinline__ PendulumCoef pendulum_coef_default(const ModelParams&
   return c;
 }
 
-// one step; returns the pre-clamp angular speed through *pre (the adjoint needs the mask)
+// sin and cos of one argument with a single Cody-Waite reduction (pi/2 in three parts, exact for
+// |x| < 100) and the Cephes single-precision minimax polynomials on [-pi/4, pi/4]; max abs error
+// 9.2e-8 (~1.5 ulp), the same class as sinf/cosf.  Larger arguments take the library path.
+// (the library path is kept out of line: inlined, its Payne-Hanek code would bloat the rollout
+// loop past the instruction cache)
+static __device__ __noinline__ void slow_sincosf(float x, float* s, float* c) {
+  *s = sinf(x);
+  *c = cosf(x);
+}
+__device__ __forceinline__ void fast_sincosf(float x, float& s, float& c) {
+  if (__builtin_expect(fabsf(x) > 64.0f, 0)) {
+    slow_sincosf(x, &s, &c);
+    return;
+  }
+  const float kf = rintf(x * 0.636619772f);
+  const int q = (int)kf;
+  float r = fmaf(kf, -1.5703125f, x);
+  r = fmaf(kf, -4.837512969970703125e-4f, r);
+  r = fmaf(kf, -7.54978995489188216e-8f, r);
+  const float r2 = r * r;
+  float ps = fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f);
+  ps = fmaf(ps, r2 * r, r);
+  float pc = fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f);
+  pc = fmaf(pc, r2 * r2, fmaf(-0.5f, r2, 1.0f));
+  const float sv = (q & 1) ? pc : ps;
+  const float cv = (q & 1) ? ps : pc;
+  s = (q & 2) ? -sv : sv;
+  c = ((q + 1) & 2) ? -cv : cv;
+}
+
+// one step; returns the pre-clamp angular speed through *pre (the adjoint needs the mask).
+// If cos_th is given it receives cos(th) of the state BEFORE the step, obtained from the same
+// reduction as sin(th + pi): with y = fl(th + pi_f) and the exact rounding error err of that sum
+// (2Sum), th = y - pi - e, e = (pi_f - pi) - err, so cos(th) = -cos(y - e) = -(cos y + e sin y) + O(e^2).
 __device__ __forceinline__ void pendulum_step(const ModelParams& m, const PendulumCoef& c, float& th, float& om,
-                                              float a, float* pre_out = nullptr) {
+                                              float a, float* pre_out = nullptr, float* cos_th = nullptr) {
   const float u = fminf(fmaxf(a, -m.max_torque), m.max_torque);
-  const float s = sinf(th + kPiF);
+  const float y = th + kPiF;
+  float s, cy;
+  fast_sincosf(y, s, cy);
+  if (cos_th) {
+    const float bb = y - th;
+    const float err = (th - (y - bb)) + (kPiF - bb);
+    const float e = 8.742278e-8f - err;
+    *cos_th = -fmaf(e, s, cy);
+  }
   const float acc = c.c1 * s + c.c2 * u;
   float pre = om + m.dt * acc;
   if (pre_out) *pre_out = pre;
@@ -46,10 +87,15 @@ __device__ __forceinline__ void pendulum_step(const ModelParams& m, const Pendul
 }
 
 // demo/pendulum_example.py:21-28
-__device__ __forceinline__ float pendulum_cost(const ModelParams& m, float th, float om) {
-  float t = cosf(th) - 1.0f;
+__device__ __forceinline__ float pendulum_cost_from_cos(const ModelParams& m, float cos_th, float om) {
+  float t = cos_th - 1.0f;
   t = t * t;
   return m.w_angle * t + m.w_speed * (om * om);
+}
+__device__ __forceinline__ float pendulum_cost(const ModelParams& m, float th, float om) {
+  float s, c;
+  fast_sincosf(th, s, c);
+  return pendulum_cost_from_cos(m, c, om);
 }
 
 // ---------------------------------------------------------------------------------------

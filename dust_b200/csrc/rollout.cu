@@ -39,7 +39,7 @@ struct RolloutKParams {
 
 // cooperative load of a [rows, HA] tile of the noise tensor into padded shared memory, fused
 // with actions = theta + sigma * eps (likelihoods.py:85-90; exact: one product, one sum).
-template <int A>
+template <int A, int NT>
 __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float* tile, int stride, long long inst,
                                                  int j0, int rows) {
   const int HA = k.HA;
@@ -53,11 +53,11 @@ __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float*
     float sg[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) sg[q] = th ? k.sigma[q % A] : 0.f;
-    for (int e = threadIdx.x; e < total4; e += kTile) {
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total4; e += NT) {
       const int row = e / HA4, c4 = e - row * HA4;
       float4 v = __ldg(reinterpret_cast<const float4*>(src) + e);
       if (th) {
-        // theta offset of this float4: ((j0+row) % N) * HA + 4*c4
         const int n = (j0 + row) % k.N;
         const float4 t = __ldg(reinterpret_cast<const float4*>(th + n * HA) + c4);
         v.x = t.x + sg[0] * v.x;
@@ -70,7 +70,7 @@ __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float*
   } else {
     const int total = rows * HA;
     const int wrap0 = (int)(((long long)j0 * HA) % NHA);
-    for (int e = threadIdx.x; e < total; e += kTile) {
+    for (int e = threadIdx.x; e < total; e += NT) {
       const int row = e / HA, c = e - row * HA;
       float v = __ldg(src + e);
       if (th) {
@@ -82,37 +82,13 @@ __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float*
   }
 }
 
+// cost of trajectory j (row `arow` of the action tile), summed over parameter samples [p_begin, p_end)
 template <int MODEL>
-__global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParams k) {
-  constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+__device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, const float* __restrict__ arow,
+                                                     const uint32_t* grid_s, long long inst, int j, int p_begin, int p_end) {
   constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
   constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
-  extern __shared__ __align__(16) float smem[];
-  const int stride = padded_stride(k.HA);
-  float* tile = smem;  // [kTile][stride]
-  uint32_t* grid_s = reinterpret_cast<uint32_t*>(smem + kTile * stride);
-
-  const int tiles_per_inst = (k.SN + kTile - 1) / kTile;
-  const long long inst = blockIdx.x / tiles_per_inst;
-  const int j0 = (blockIdx.x - (int)inst * tiles_per_inst) * kTile;
-  const int rows = min(kTile, k.SN - j0);
-  const int pc = blockIdx.y;
-
-  load_action_tile<A>(k, tile, stride, inst, j0, rows);
-  if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
-    const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
-    for (int w = threadIdx.x; w < words; w += kTile) grid_s[w] = __ldg(k.m.grid_bits + w);
-  }
-  __syncthreads();
-
-  const int row = threadIdx.x;
-  if (row >= rows) return;
-  const int j = j0 + row;
-  const float* __restrict__ arow = tile + row * stride;
   const float* __restrict__ x0 = k.state0 + inst * DS;
-  const int p_begin = pc * k.Pchunk;
-  const int p_end = min(k.P, p_begin + k.Pchunk);
-
   float csum = 0.f;
   for (int p = p_begin; p < p_end; ++p) {
     const float* prm = nullptr;
@@ -127,21 +103,27 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
       const PendulumCoef cf = prm ? pendulum_coef_sampled(k.m, __ldg(prm), __ldg(prm + 1)) : pendulum_coef_default(k.m);
       float th = __ldg(x0), om = __ldg(x0 + 1);
       if (st_out) { st_out[0] = th; st_out[1] = om; }
-#pragma unroll 4
-      for (int t = 0; t < k.H; ++t) {
-        cost = cost + pendulum_cost(k.m, th, om);
-        pendulum_step(k.m, cf, th, om, arow[t]);
+      // cost at x_t uses cos(th_t), which the step evaluates from the reduction it needs anyway
+      auto one = [&](float a, int t) {
+        const float om0 = om;
+        float cth;
+        pendulum_step(k.m, cf, th, om, a, nullptr, &cth);
+        cost = cost + pendulum_cost_from_cos(k.m, cth, om0);
         if (st_out) { st_out[(t + 1) * 2] = th; st_out[(t + 1) * 2 + 1] = om; }
+      };
+      int t = 0;
+      for (; t + 4 <= k.H; t += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + t);
+        one(a4.x, t); one(a4.y, t + 1); one(a4.z, t + 2); one(a4.w, t + 3);
       }
+      for (; t < k.H; ++t) one(arow[t], t);
       cost = cost + pendulum_cost(k.m, th, om);
     } else {
       const float mass = prm ? __ldg(prm) : k.m.default_mass;
       ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
       if (st_out) { st_out[0] = s.x; st_out[1] = s.y; st_out[2] = s.vx; st_out[3] = s.vy; }
       const bool has_grid = k.m.grid_bits != nullptr;
-#pragma unroll 2
-      for (int t = 0; t < k.H; ++t) {
-        const float ax = arow[2 * t], ay = arow[2 * t + 1];
+      auto one = [&](float ax, float ay, int t) {
         const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
         cost = cost + particle_inst_cost(k.m, s, ax, ay, c);
         particle_step(k.m, s, ax, ay, mass, c);
@@ -149,16 +131,162 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
           float* o = st_out + (t + 1) * 4;
           o[0] = s.x; o[1] = s.y; o[2] = s.vx; o[3] = s.vy;
         }
+      };
+      int t = 0;
+      for (; t + 2 <= k.H; t += 2) {
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + 2 * t);
+        one(a4.x, a4.y, t); one(a4.z, a4.w, t + 1);
       }
+      for (; t < k.H; ++t) one(arow[2 * t], arow[2 * t + 1], t);
       const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
       cost = cost + particle_term_cost(k.m, s, c);
     }
     csum = csum + cost;
   }
+  return csum;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParams k) {
+  constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  extern __shared__ __align__(16) float smem[];
+  const int stride = padded_stride(k.HA);
+  float* tile = smem;  // [kTile][stride]
+  uint32_t* grid_s = reinterpret_cast<uint32_t*>(smem + kTile * stride);
+
+  const int tiles_per_inst = (k.SN + kTile - 1) / kTile;
+  const long long inst = blockIdx.x / tiles_per_inst;
+  const int j0 = (blockIdx.x - (int)inst * tiles_per_inst) * kTile;
+  const int rows = min(kTile, k.SN - j0);
+  const int pc = blockIdx.y;
+
+  load_action_tile<A, kTile>(k, tile, stride, inst, j0, rows);
+  if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
+    const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
+    for (int w = threadIdx.x; w < words; w += kTile) grid_s[w] = __ldg(k.m.grid_bits + w);
+  }
+  __syncthreads();
+
+  const int row = threadIdx.x;
+  if (row >= rows) return;
+  const int j = j0 + row;
+  const int p_begin = pc * k.Pchunk;
+  const int p_end = min(k.P, p_begin + k.Pchunk);
+  const float csum = trajectory_cost_sum<MODEL>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end);
   if (k.PC == 1) {
     k.cost_out[inst * k.SN + j] = csum / (float)k.P;  // mean over parameter samples (disco.py:330)
   } else {
     k.cost_out[(inst * k.PC + pc) * (long long)k.SN + j] = csum;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// fused per-instance kernel: one CTA owns ALL trajectories of one MPC instance.  Every thread
+// keeps an online soft-min (running max, normaliser, weighted score row) over the trajectories it
+// rolls out, so the noise is read from HBM exactly once and costs / log-likelihood / analytic
+// likelihood gradient (svmpc.py:46-54) leave in the same launch.
+// ---------------------------------------------------------------------------------------
+constexpr int kFusedThreads = 256;
+
+struct FusedOut {
+  float* costs;     // [B,S,N] or null
+  float* log_lik;   // [B,N] or null
+  float* grad_lik;  // [B,N,HA] or null
+  int likelihood;
+  float alpha;
+};
+
+template <int MODEL, int ACC>
+__global__ void __launch_bounds__(kFusedThreads, 3) svmpc_instance_kernel(const RolloutKParams k, const FusedOut o) {
+  constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  extern __shared__ __align__(16) float smem[];
+  const int stride = padded_stride(k.HA);
+  const int HA = k.HA, N = k.N;
+  const int TN = (kFusedThreads / N) * N;  // rows per tile: a multiple of N, so tid % N is this thread's policy
+  float* tile = smem;                                   // [TN][stride]
+  float* th_s = tile + kFusedThreads * stride;          // [N*HA]
+  float* red_m = th_s + ((N * HA + 3) & ~3);            // [256]
+  float* red_z = red_m + kFusedThreads;                 // [256]
+  float* red_c = red_z + kFusedThreads;                 // [256]
+  uint32_t* grid_s = reinterpret_cast<uint32_t*>(red_c + kFusedThreads);
+  const long long inst = blockIdx.x;
+  const int tid = threadIdx.x;
+  const int n = tid % N;
+
+  for (int e = tid; e < N * HA; e += kFusedThreads) th_s[e] = k.theta[inst * (long long)N * HA + e];
+  if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
+    const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
+    for (int w = tid; w < words; w += kFusedThreads) grid_s[w] = __ldg(k.m.grid_bits + w);
+  }
+  float inv_s2[A];
+#pragma unroll
+  for (int a = 0; a < A; ++a) inv_s2[a] = 1.0f / (k.sigma[a] * k.sigma[a]);
+
+  // online soft-min relative to the running MINIMUM cost: weights are exp(-alpha (c - c_min)) with
+  // the difference formed first (exact), as softmax(-alpha c) does after its max shift
+  float m_run = INFINITY, z_run = 0.f, c_run = 0.f;
+  float acc[ACC];
+#pragma unroll
+  for (int c = 0; c < ACC; ++c) acc[c] = 0.f;
+
+  for (int j0 = 0; j0 < k.SN; j0 += TN) {
+    const int rows = min(TN, k.SN - j0);
+    __syncthreads();
+    load_action_tile<A, kFusedThreads>(k, tile, stride, inst, j0, rows);
+    __syncthreads();
+    if (tid < rows) {
+      const float* __restrict__ arow = tile + tid * stride;
+      const float cost = trajectory_cost_sum<MODEL>(k, arow, grid_s, inst, j0 + tid, 0, k.P) / (float)k.P;
+      if (o.costs) o.costs[inst * k.SN + j0 + tid] = cost;
+      c_run += cost;
+      float scale = 1.f, e = 1.f;
+      if (cost < m_run) {
+        scale = expf(-o.alpha * (m_run - cost));  // 0 on the first trajectory (m_run = +inf)
+        m_run = cost;
+      } else {
+        e = expf(-o.alpha * (cost - m_run));
+      }
+      z_run = z_run * scale + e;
+      const float* __restrict__ th = th_s + n * HA;
+#pragma unroll
+      for (int c = 0; c < ACC; ++c)
+        if (c < HA) acc[c] = acc[c] * scale + e * ((arow[c] - th[c]) * inv_s2[c % A]);
+    }
+  }
+  // combine the G = TN/N threads that share a policy
+  __syncthreads();
+  red_m[tid] = (tid < TN) ? m_run : INFINITY;
+  red_z[tid] = (tid < TN) ? z_run : 0.f;
+  red_c[tid] = (tid < TN) ? c_run : 0.f;
+  __syncthreads();
+  const int G = TN / N;
+  float m_n = INFINITY;
+  for (int g = 0; g < G; ++g) m_n = fminf(m_n, red_m[g * N + n]);
+  float z_n = 0.f, c_n = 0.f;
+  for (int g = 0; g < G; ++g) {
+    const float mg = red_m[g * N + n];
+    z_n += (mg == INFINITY) ? 0.f : red_z[g * N + n] * expf(-o.alpha * (mg - m_n));
+    c_n += red_c[g * N + n];
+  }
+  if (o.log_lik && tid < N) {
+    float ll;
+    if (o.likelihood == DUST_LIK_EXP_UTILITY) ll = (-o.alpha * m_n + logf(z_n)) - logf((float)k.S);  // likelihoods.py:133-135
+    else ll = -o.alpha * (c_n / (float)k.S);                                                          // likelihoods.py:119
+    o.log_lik[inst * N + tid] = ll;
+  }
+  if (o.grad_lik) {
+    const float f = (tid < TN && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) / z_n : 0.f;
+    float* crow = tile + tid * stride;  // the action tile is dead: reuse it for the partial rows
+#pragma unroll
+    for (int c = 0; c < ACC; ++c)
+      if (c < HA) crow[c] = acc[c] * f;
+    __syncthreads();
+    for (int col = tid; col < N * HA; col += kFusedThreads) {
+      const int n2 = col / HA, c = col - n2 * HA;
+      float sacc = 0.f;
+      for (int g = 0; g < G; ++g) sacc += tile[(g * N + n2) * stride + c];
+      o.grad_lik[inst * (long long)N * HA + col] = sacc;
+    }
   }
 }
 
@@ -403,8 +531,36 @@ extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
   k.states = a->states;
 
   const int stride = padded_stride(k.HA);
-  size_t smem = sizeof(float) * kTile * stride;
-  if (kind == DUST_MODEL_PARTICLE && a->model->grid_bits) smem += sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32);
+  const size_t grid_bytes = (kind == DUST_MODEL_PARTICLE && a->model->grid_bits)
+                                ? sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32) : 0;
+  // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
+  const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
+  const bool fused_ok = fused_outputs_only && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
+                        (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik);
+  if (fused_ok) {
+    const size_t fsmem = sizeof(float) * ((size_t)kFusedThreads * stride + ((a->N * k.HA + 3) & ~3) + 3 * kFusedThreads) + grid_bytes;
+    FusedOut o{a->costs, a->log_lik, a->grad_lik, a->likelihood, a->alpha};
+    k.cost_out = nullptr;
+#define DUST_FUSED(MODEL, ACC)                                                                                              \
+  do {                                                                                                                      \
+    if (fsmem > 48 * 1024)                                                                                                  \
+      DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_instance_kernel<MODEL, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+    { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_instance_kernel<MODEL, ACC><<<a->B, kFusedThreads, fsmem, stream>>>(k, o); } \
+  } while (0)
+    if (kind == DUST_MODEL_PENDULUM) {
+      if (k.HA <= 8) DUST_FUSED(DUST_MODEL_PENDULUM, 8);
+      else if (k.HA <= 16) DUST_FUSED(DUST_MODEL_PENDULUM, 16);
+      else if (k.HA <= 24) DUST_FUSED(DUST_MODEL_PENDULUM, 24);
+      else DUST_FUSED(DUST_MODEL_PENDULUM, 32);
+    } else {
+      if (k.HA <= 16) DUST_FUSED(DUST_MODEL_PARTICLE, 16);
+      else DUST_FUSED(DUST_MODEL_PARTICLE, 32);
+    }
+#undef DUST_FUSED
+    DUST_LAUNCH_OK("svmpc_instance_kernel");
+    return DUST_OK;
+  }
+  size_t smem = sizeof(float) * kTile * stride + grid_bytes;
   DUST_REQUIRE(smem <= 227 * 1024, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: H*A=%d needs %zu B of shared memory", k.HA, smem);
   const int tiles = ceil_div(SN, kTile);
   const long long gx = (long long)a->B * tiles;

@@ -65,9 +65,8 @@ class SvmpcCore:
         mu = self.theta if self.aliased else self.mu
         _, grad_pri = ops.gmm(self._flat(self.theta), self._flat(mu), self.mix, self.inv_var, self.log_norm,
                               want_log_prob=False)
-        want = ["costs", "log_lik", "lik_weights"]
-        if self.grad == "analytic":
-            want.append("grad_lik")
+        want = ["costs", "log_lik"]
+        want.append("grad_lik" if self.grad == "analytic" else "lik_weights")
         if want_states:
             want.append("states")
         out = ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
@@ -90,7 +89,7 @@ class SvmpcCore:
         self.theta = res["x_out"].reshape(self.B, self.N, self.H, self.A)
         self.last = dict(costs=out["costs"], log_lik=out["log_lik"], grad_lik=grad_lik, grad_pri=grad_pri,
                          phi=res["phi"].reshape(self.B, self.N, self.H, self.A), states=out.get("states"),
-                         lik_weights=out["lik_weights"])
+                         lik_weights=out.get("lik_weights"))
         return self.last
 
     def forward_step(self, log_lik=None):
