@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdust_b200.so")
+LIB_PATH = os.environ.get("DUST_B200_LIB", os.path.join(_HERE, "libdust_b200.so"))  # env override: A/B builds
 
 OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -4
 MODEL_PENDULUM, MODEL_PARTICLE = 0, 1

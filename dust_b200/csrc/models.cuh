@@ -42,8 +42,9 @@ static __device__ __noinline__ void slow_sincosf(float x, float* s, float* c) {
   *s = sinf(x);
   *c = cosf(x);
 }
+template <bool CHECK = true>
 __device__ __forceinline__ void fast_sincosf(float x, float& s, float& c) {
-  if (__builtin_expect(fabsf(x) > 64.0f, 0)) {
+  if (CHECK && __builtin_expect(fabsf(x) > 64.0f, 0)) {
     slow_sincosf(x, &s, &c);
     return;
   }
@@ -67,12 +68,14 @@ __device__ __forceinline__ void fast_sincosf(float x, float& s, float& c) {
 // If cos_th is given it receives cos(th) of the state BEFORE the step, obtained from the same
 // reduction as sin(th + pi): with y = fl(th + pi_f) and the exact rounding error err of that sum
 // (2Sum), th = y - pi - e, e = (pi_f - pi) - err, so cos(th) = -cos(y - e) = -(cos y + e sin y) + O(e^2).
+// CHECK = false: the caller guarantees |th + pi| <= 64 (no library fall-back in the loop).
+template <bool CHECK = true>
 __device__ __forceinline__ void pendulum_step(const ModelParams& m, const PendulumCoef& c, float& th, float& om,
                                               float a, float* pre_out = nullptr, float* cos_th = nullptr) {
   const float u = fminf(fmaxf(a, -m.max_torque), m.max_torque);
   const float y = th + kPiF;
   float s, cy;
-  fast_sincosf(y, s, cy);
+  fast_sincosf<CHECK>(y, s, cy);
   if (cos_th) {
     const float bb = y - th;
     const float err = (th - (y - bb)) + (kPiF - bb);

@@ -39,13 +39,13 @@ struct RolloutKParams {
 
 // cooperative load of a [rows, HA] tile of the noise tensor into padded shared memory, fused
 // with actions = theta + sigma * eps (likelihoods.py:85-90; exact: one product, one sum).
+// The (row, column, policy) walk of each thread is incremental: no division in the loop.
+// th: policy means of this instance (global or shared memory), or nullptr.
 template <int A, int NT>
 __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float* tile, int stride, long long inst,
-                                                 int j0, int rows) {
-  const int HA = k.HA;
+                                                 int j0, int rows, const float* __restrict__ th) {
+  const int HA = k.HA, N = k.N;
   const float* __restrict__ src = k.noise + (inst * k.SN + j0) * (long long)HA;
-  const float* __restrict__ th = k.theta ? k.theta + inst * (long long)k.N * HA : nullptr;
-  const int NHA = k.N * HA;
   const bool vec = ((HA & 3) == 0) && ((((uintptr_t)src) & 15) == 0) && (!th || ((((uintptr_t)th) & 15) == 0));
   if (vec) {
     const int HA4 = HA >> 2;
@@ -53,39 +53,57 @@ __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float*
     float sg[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) sg[q] = th ? k.sigma[q % A] : 0.f;
-#pragma unroll 4
+    const int drow = NT / HA4, dc = NT - drow * HA4, dn = drow % N;
+    int row = (int)threadIdx.x / HA4;
+    int c4 = (int)threadIdx.x - row * HA4;
+    int n = (j0 + row) % N;
+#pragma unroll 2
     for (int e = threadIdx.x; e < total4; e += NT) {
-      const int row = e / HA4, c4 = e - row * HA4;
       float4 v = __ldg(reinterpret_cast<const float4*>(src) + e);
       if (th) {
-        const int n = (j0 + row) % k.N;
-        const float4 t = __ldg(reinterpret_cast<const float4*>(th + n * HA) + c4);
+        const float4 t = *reinterpret_cast<const float4*>(th + n * HA + 4 * c4);
         v.x = t.x + sg[0] * v.x;
         v.y = t.y + sg[1] * v.y;
         v.z = t.z + sg[2] * v.z;
         v.w = t.w + sg[3] * v.w;
       }
       *reinterpret_cast<float4*>(tile + row * stride + 4 * c4) = v;
+      c4 += dc;
+      row += drow;
+      n += dn;
+      if (c4 >= HA4) { c4 -= HA4; row += 1; n += 1; }
+      if (n >= N) n -= N;
+      if (n >= N) n -= N;
     }
   } else {
     const int total = rows * HA;
-    const int wrap0 = (int)(((long long)j0 * HA) % NHA);
+    const int drow = NT / HA, dc = NT - drow * HA, dn = drow % N;
+    int row = (int)threadIdx.x / HA;
+    int c = (int)threadIdx.x - row * HA;
+    int n = (j0 + row) % N;
     for (int e = threadIdx.x; e < total; e += NT) {
-      const int row = e / HA, c = e - row * HA;
       float v = __ldg(src + e);
-      if (th) {
-        const int to = (wrap0 + e) % NHA;
-        v = __ldg(th + to) + k.sigma[c % A] * v;
-      }
+      if (th) v = th[n * HA + c] + k.sigma[c % A] * v;
       tile[row * stride + c] = v;
+      c += dc;
+      row += drow;
+      n += dn;
+      if (c >= HA) { c -= HA; row += 1; n += 1; }
+      if (n >= N) n -= N;
+      if (n >= N) n -= N;
     }
   }
 }
 
-// cost of trajectory j (row `arow` of the action tile), summed over parameter samples [p_begin, p_end)
-template <int MODEL>
+// SMALL: |theta| stays below the fast trig range for the whole horizon (decided per instance);
+// STORE: write the state trajectory (only the non-fused path offers it).
+// XFORM: `arow` holds the raw noise; the action is th_row[t] + sigma * eps[t], formed per step
+// (one product, one sum: the same float32 value as MultivariateNormal.rsample's loc + L eps).
+template <int MODEL, bool SMALL, bool STORE, bool XFORM = false>
 __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, const float* __restrict__ arow,
-                                                     const uint32_t* grid_s, long long inst, int j, int p_begin, int p_end) {
+                                                     const uint32_t* grid_s, long long inst, int j, int p_begin, int p_end,
+                                                     const float* __restrict__ th_row = nullptr, float sg0 = 0.f,
+                                                     float sg1 = 0.f) {
   constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
   constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
   const float* __restrict__ x0 = k.state0 + inst * DS;
@@ -97,53 +115,81 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
       prm = k.params + (inst * k.P + pi) * DP;
     }
     float* st_out = nullptr;
-    if (k.states) st_out = k.states + (((inst * k.P + p) * k.SN + j) * (long long)(k.H + 1)) * DS;
+    if (STORE) st_out = k.states + (((inst * k.P + p) * k.SN + j) * (long long)(k.H + 1)) * DS;
     float cost = 0.f;
     if (MODEL == DUST_MODEL_PENDULUM) {
       const PendulumCoef cf = prm ? pendulum_coef_sampled(k.m, __ldg(prm), __ldg(prm + 1)) : pendulum_coef_default(k.m);
       float th = __ldg(x0), om = __ldg(x0 + 1);
-      if (st_out) { st_out[0] = th; st_out[1] = om; }
+      if (STORE) { st_out[0] = th; st_out[1] = om; }
       // cost at x_t uses cos(th_t), which the step evaluates from the reduction it needs anyway
       auto one = [&](float a, int t) {
         const float om0 = om;
         float cth;
-        pendulum_step(k.m, cf, th, om, a, nullptr, &cth);
+        pendulum_step<!SMALL>(k.m, cf, th, om, a, nullptr, &cth);
         cost = cost + pendulum_cost_from_cos(k.m, cth, om0);
-        if (st_out) { st_out[(t + 1) * 2] = th; st_out[(t + 1) * 2 + 1] = om; }
+        if (STORE) { st_out[(t + 1) * 2] = th; st_out[(t + 1) * 2 + 1] = om; }
       };
       int t = 0;
       for (; t + 4 <= k.H; t += 4) {
-        const float4 a4 = *reinterpret_cast<const float4*>(arow + t);
+        float4 a4 = *reinterpret_cast<const float4*>(arow + t);
+        if (XFORM) {
+          const float4 t4 = *reinterpret_cast<const float4*>(th_row + t);
+          a4.x = t4.x + sg0 * a4.x; a4.y = t4.y + sg0 * a4.y; a4.z = t4.z + sg0 * a4.z; a4.w = t4.w + sg0 * a4.w;
+        }
         one(a4.x, t); one(a4.y, t + 1); one(a4.z, t + 2); one(a4.w, t + 3);
       }
-      for (; t < k.H; ++t) one(arow[t], t);
+      for (; t < k.H; ++t) one(XFORM ? th_row[t] + sg0 * arow[t] : arow[t], t);
       cost = cost + pendulum_cost(k.m, th, om);
     } else {
       const float mass = prm ? __ldg(prm) : k.m.default_mass;
       ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
-      if (st_out) { st_out[0] = s.x; st_out[1] = s.y; st_out[2] = s.vx; st_out[3] = s.vy; }
+      if (STORE) { st_out[0] = s.x; st_out[1] = s.y; st_out[2] = s.vx; st_out[3] = s.vy; }
       const bool has_grid = k.m.grid_bits != nullptr;
       auto one = [&](float ax, float ay, int t) {
         const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
         cost = cost + particle_inst_cost(k.m, s, ax, ay, c);
         particle_step(k.m, s, ax, ay, mass, c);
-        if (st_out) {
+        if (STORE) {
           float* o = st_out + (t + 1) * 4;
           o[0] = s.x; o[1] = s.y; o[2] = s.vx; o[3] = s.vy;
         }
       };
       int t = 0;
       for (; t + 2 <= k.H; t += 2) {
-        const float4 a4 = *reinterpret_cast<const float4*>(arow + 2 * t);
+        float4 a4 = *reinterpret_cast<const float4*>(arow + 2 * t);
+        if (XFORM) {
+          const float4 t4 = *reinterpret_cast<const float4*>(th_row + 2 * t);
+          a4.x = t4.x + sg0 * a4.x; a4.y = t4.y + sg1 * a4.y; a4.z = t4.z + sg0 * a4.z; a4.w = t4.w + sg1 * a4.w;
+        }
         one(a4.x, a4.y, t); one(a4.z, a4.w, t + 1);
       }
-      for (; t < k.H; ++t) one(arow[2 * t], arow[2 * t + 1], t);
+      for (; t < k.H; ++t) {
+        if (XFORM) one(th_row[2 * t] + sg0 * arow[2 * t], th_row[2 * t + 1] + sg1 * arow[2 * t + 1], t);
+        else one(arow[2 * t], arow[2 * t + 1], t);
+      }
       const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
       cost = cost + particle_term_cost(k.m, s, c);
     }
     csum = csum + cost;
   }
   return csum;
+}
+
+// |theta_t + pi| <= |theta_0| + t dt max_speed + pi: decided once per instance (uniform in the CTA)
+template <int MODEL>
+__device__ __forceinline__ bool small_angle_horizon(const RolloutKParams& k, long long inst) {
+  if (MODEL != DUST_MODEL_PENDULUM) return true;
+  const float th0 = __ldg(k.state0 + inst * 2);
+  return fabsf(th0) + (float)k.H * k.m.dt * k.m.max_speed_pend + 3.2f <= 64.0f;  // NaN -> false
+}
+
+template <int MODEL>
+__device__ __forceinline__ float trajectory_cost_dispatch(const RolloutKParams& k, const float* __restrict__ arow,
+                                                          const uint32_t* grid_s, long long inst, int j, int p_begin,
+                                                          int p_end, bool small) {
+  if (k.states) return trajectory_cost_sum<MODEL, false, true>(k, arow, grid_s, inst, j, p_begin, p_end);
+  if (small) return trajectory_cost_sum<MODEL, true, false>(k, arow, grid_s, inst, j, p_begin, p_end);
+  return trajectory_cost_sum<MODEL, false, false>(k, arow, grid_s, inst, j, p_begin, p_end);
 }
 
 template <int MODEL>
@@ -160,7 +206,8 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
   const int rows = min(kTile, k.SN - j0);
   const int pc = blockIdx.y;
 
-  load_action_tile<A, kTile>(k, tile, stride, inst, j0, rows);
+  load_action_tile<A, kTile>(k, tile, stride, inst, j0, rows,
+                             k.theta ? k.theta + inst * (long long)k.N * k.HA : nullptr);
   if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
     const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
     for (int w = threadIdx.x; w < words; w += kTile) grid_s[w] = __ldg(k.m.grid_bits + w);
@@ -172,7 +219,8 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
   const int j = j0 + row;
   const int p_begin = pc * k.Pchunk;
   const int p_end = min(k.P, p_begin + k.Pchunk);
-  const float csum = trajectory_cost_sum<MODEL>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end);
+  const float csum = trajectory_cost_dispatch<MODEL>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end,
+                                                     small_angle_horizon<MODEL>(k, inst));
   if (k.PC == 1) {
     k.cost_out[inst * k.SN + j] = csum / (float)k.P;  // mean over parameter samples (disco.py:330)
   } else {
@@ -196,31 +244,84 @@ struct FusedOut {
   float alpha;
 };
 
+#ifndef DUST_FUSED_MINB
+#define DUST_FUSED_MINB 4
+#endif
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N_) : "memory"); }
+
+// asynchronous copy of a [rows, HA] block of raw noise into a padded shared-memory tile; the walk
+// (row0, c0, drow, dc) is the thread's fixed stride pattern, computed once per kernel.
+template <bool VEC>
+__device__ __forceinline__ void stage_noise_async(const float* __restrict__ src, float* tile, int stride, int rows, int HA,
+                                                  int row0, int c0, int drow, int dc) {
+  const int W = VEC ? (HA >> 2) : HA;  // columns in units of the copy width
+  const int total = rows * W;
+  int row = row0, c = c0;
+  for (int e = threadIdx.x; e < total; e += kFusedThreads) {
+    if (VEC) cp_async16(tile + row * stride + 4 * c, reinterpret_cast<const float4*>(src) + e);
+    else cp_async4(tile + row * stride + c, src + e);
+    c += dc;
+    row += drow;
+    if (c >= W) { c -= W; row += 1; }
+  }
+}
+
 template <int MODEL, int ACC>
-__global__ void __launch_bounds__(kFusedThreads, 3) svmpc_instance_kernel(const RolloutKParams k, const FusedOut o) {
+__global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance_kernel(const RolloutKParams k, const FusedOut o) {
   constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
   extern __shared__ __align__(16) float smem[];
   const int stride = padded_stride(k.HA);
   const int HA = k.HA, N = k.N;
   const int TN = (kFusedThreads / N) * N;  // rows per tile: a multiple of N, so tid % N is this thread's policy
-  float* tile = smem;                                   // [TN][stride]
-  float* th_s = tile + kFusedThreads * stride;          // [N*HA]
-  float* red_m = th_s + ((N * HA + 3) & ~3);            // [256]
+  float* buf0 = smem;                                   // [256][stride] noise tile, double buffered
+  float* buf1 = buf0 + kFusedThreads * stride;
+  float* th_s = buf1 + kFusedThreads * stride;          // [N][thst] policy means
+  const int thst = (HA + 3) & ~3;                       // theta row stride (16-byte aligned rows)
+  float* red_m = th_s + N * thst;                       // [256]
   float* red_z = red_m + kFusedThreads;                 // [256]
   float* red_c = red_z + kFusedThreads;                 // [256]
   uint32_t* grid_s = reinterpret_cast<uint32_t*>(red_c + kFusedThreads);
   const long long inst = blockIdx.x;
   const int tid = threadIdx.x;
   const int n = tid % N;
+  const float* __restrict__ noise = k.noise + inst * (long long)k.SN * HA;
+  const bool vec = ((HA & 3) == 0) && ((((uintptr_t)noise) & 15) == 0);
+  const int W = vec ? (HA >> 2) : HA;
+  const int row0 = tid / W, c0 = tid - row0 * W;
+  const int drow = kFusedThreads / W, dc = kFusedThreads - drow * W;
+  const int ntiles = (k.SN + TN - 1) / TN;
 
-  for (int e = tid; e < N * HA; e += kFusedThreads) th_s[e] = k.theta[inst * (long long)N * HA + e];
+  auto prefetch = [&](int it) {
+    const int j0 = it * TN;
+    const int rows = min(TN, k.SN - j0);
+    float* dst = (it & 1) ? buf1 : buf0;
+    if (vec) stage_noise_async<true>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
+    else stage_noise_async<false>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
+    cp_async_commit();
+  };
+  prefetch(0);
+  for (int e = tid; e < N * HA; e += kFusedThreads) {
+    const int nn = e / HA;
+    th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
+  }
   if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
     const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
     for (int w = tid; w < words; w += kFusedThreads) grid_s[w] = __ldg(k.m.grid_bits + w);
   }
-  float inv_s2[A];
-#pragma unroll
-  for (int a = 0; a < A; ++a) inv_s2[a] = 1.0f / (k.sigma[a] * k.sigma[a]);
+  const float sg0 = k.sigma[0], sg1 = k.sigma[A - 1];
+  const float is0 = 1.0f / (sg0 * sg0), is1 = 1.0f / (sg1 * sg1);
+  const bool small = small_angle_horizon<MODEL>(k, inst);
+  const float* __restrict__ th_row = th_s + n * thst;
 
   // online soft-min relative to the running MINIMUM cost: weights are exp(-alpha (c - c_min)) with
   // the difference formed first (exact), as softmax(-alpha c) does after its max shift
@@ -229,14 +330,23 @@ __global__ void __launch_bounds__(kFusedThreads, 3) svmpc_instance_kernel(const 
 #pragma unroll
   for (int c = 0; c < ACC; ++c) acc[c] = 0.f;
 
-  for (int j0 = 0; j0 < k.SN; j0 += TN) {
+  for (int it = 0; it < ntiles; ++it) {
+    const int j0 = it * TN;
     const int rows = min(TN, k.SN - j0);
+    if (it + 1 < ntiles) {
+      prefetch(it + 1);      // overlaps this tile's rollouts
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
     __syncthreads();
-    load_action_tile<A, kFusedThreads>(k, tile, stride, inst, j0, rows);
-    __syncthreads();
+    const float* tile = (it & 1) ? buf1 : buf0;
     if (tid < rows) {
-      const float* __restrict__ arow = tile + tid * stride;
-      const float cost = trajectory_cost_sum<MODEL>(k, arow, grid_s, inst, j0 + tid, 0, k.P) / (float)k.P;
+      const float* __restrict__ erow = tile + tid * stride;
+      const float csum = small
+          ? trajectory_cost_sum<MODEL, true, false, true>(k, erow, grid_s, inst, j0 + tid, 0, k.P, th_row, sg0, sg1)
+          : trajectory_cost_sum<MODEL, false, false, true>(k, erow, grid_s, inst, j0 + tid, 0, k.P, th_row, sg0, sg1);
+      const float cost = csum / (float)k.P;
       if (o.costs) o.costs[inst * k.SN + j0 + tid] = cost;
       c_run += cost;
       float scale = 1.f, e = 1.f;
@@ -247,14 +357,37 @@ __global__ void __launch_bounds__(kFusedThreads, 3) svmpc_instance_kernel(const 
         e = expf(-o.alpha * (cost - m_run));
       }
       z_run = z_run * scale + e;
-      const float* __restrict__ th = th_s + n * HA;
+      // weighted score row (a - theta)/sigma^2 with a = fl(theta + fl(sigma eps)); skipped when the
+      // weight is below 1e-30 of the running maximum weight (invisible in float32)
+      if (scale != 1.f || e > 1e-30f) {
+        const float e0 = e * is0, e1 = e * is1;
+        if ((HA & 3) == 0) {
 #pragma unroll
-      for (int c = 0; c < ACC; ++c)
-        if (c < HA) acc[c] = acc[c] * scale + e * ((arow[c] - th[c]) * inv_s2[c % A]);
+          for (int c4 = 0; c4 < ACC / 4; ++c4) {
+            if (4 * c4 < HA) {
+              const float4 v = *reinterpret_cast<const float4*>(erow + 4 * c4);
+              const float4 t4 = *reinterpret_cast<const float4*>(th_row + 4 * c4);
+              const float sa = sg0, sb = (A == 1) ? sg0 : sg1;
+              const float ea = e0, eb = (A == 1) ? e0 : e1;
+              acc[4 * c4 + 0] = fmaf(acc[4 * c4 + 0], scale, ea * ((t4.x + sa * v.x) - t4.x));
+              acc[4 * c4 + 1] = fmaf(acc[4 * c4 + 1], scale, eb * ((t4.y + sb * v.y) - t4.y));
+              acc[4 * c4 + 2] = fmaf(acc[4 * c4 + 2], scale, ea * ((t4.z + sa * v.z) - t4.z));
+              acc[4 * c4 + 3] = fmaf(acc[4 * c4 + 3], scale, eb * ((t4.w + sb * v.w) - t4.w));
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < ACC; ++c)
+            if (c < HA) {
+              const float sc_ = (c % A) ? sg1 : sg0, ec_ = (c % A) ? e1 : e0;
+              acc[c] = fmaf(acc[c], scale, ec_ * ((th_row[c] + sc_ * erow[c]) - th_row[c]));
+            }
+        }
+      }
     }
+    __syncthreads();  // everyone is done with this buffer before it is refilled
   }
   // combine the G = TN/N threads that share a policy
-  __syncthreads();
   red_m[tid] = (tid < TN) ? m_run : INFINITY;
   red_z[tid] = (tid < TN) ? z_run : 0.f;
   red_c[tid] = (tid < TN) ? c_run : 0.f;
@@ -276,7 +409,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) svmpc_instance_kernel(const 
   }
   if (o.grad_lik) {
     const float f = (tid < TN && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) / z_n : 0.f;
-    float* crow = tile + tid * stride;  // the action tile is dead: reuse it for the partial rows
+    float* crow = buf0 + tid * stride;  // the noise tiles are dead: reuse buffer 0 for the partial rows
 #pragma unroll
     for (int c = 0; c < ACC; ++c)
       if (c < HA) crow[c] = acc[c] * f;
@@ -284,7 +417,7 @@ __global__ void __launch_bounds__(kFusedThreads, 3) svmpc_instance_kernel(const 
     for (int col = tid; col < N * HA; col += kFusedThreads) {
       const int n2 = col / HA, c = col - n2 * HA;
       float sacc = 0.f;
-      for (int g = 0; g < G; ++g) sacc += tile[(g * N + n2) * stride + c];
+      for (int g = 0; g < G; ++g) sacc += buf0[(g * N + n2) * stride + c];
       o.grad_lik[inst * (long long)N * HA + col] = sacc;
     }
   }
@@ -538,7 +671,7 @@ extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
   const bool fused_ok = fused_outputs_only && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
                         (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik);
   if (fused_ok) {
-    const size_t fsmem = sizeof(float) * ((size_t)kFusedThreads * stride + ((a->N * k.HA + 3) & ~3) + 3 * kFusedThreads) + grid_bytes;
+    const size_t fsmem = sizeof(float) * ((size_t)2 * kFusedThreads * stride + (size_t)a->N * ((k.HA + 3) & ~3) + 3 * kFusedThreads) + grid_bytes;
     FusedOut o{a->costs, a->log_lik, a->grad_lik, a->likelihood, a->alpha};
     k.cost_out = nullptr;
 #define DUST_FUSED(MODEL, ACC)                                                                                              \
@@ -550,6 +683,7 @@ extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
     if (kind == DUST_MODEL_PENDULUM) {
       if (k.HA <= 8) DUST_FUSED(DUST_MODEL_PENDULUM, 8);
       else if (k.HA <= 16) DUST_FUSED(DUST_MODEL_PENDULUM, 16);
+      else if (k.HA <= 20) DUST_FUSED(DUST_MODEL_PENDULUM, 20);
       else if (k.HA <= 24) DUST_FUSED(DUST_MODEL_PENDULUM, 24);
       else DUST_FUSED(DUST_MODEL_PENDULUM, 32);
     } else {
