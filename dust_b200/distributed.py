@@ -1,0 +1,79 @@
+"""Multi-GPU sharding of the hot path on one NVSwitch box (one process per GPU, torch.distributed).
+
+* Independent MPC instances (`shard_instances`): contiguous split of the batch, NO communication.
+* Large-N SVGD (`ShardedSVGD`): rank r owns a row block of X, score and phi.  One exchange per
+  evaluation: all-gather of [X | score] (N*2D*4 bytes in total), plus -- for the exact median
+  bandwidth -- an all-reduce (sum) of the 65536-bin radix histogram after each of the two passes.
+  Every rank then computes its own phi rows against all N columns; nothing else is reduced.
+
+The collectives go through torch.distributed (NCCL on GPUs; gloo in the CPU tests, where the
+compute callbacks are replaced by the oracle)."""
+import torch
+import torch.distributed as dist
+
+from . import ops as _ops
+
+
+def row_block(n, rank, world):
+    """Contiguous, balanced [begin, end) of `n` rows for `rank` of `world`."""
+    base, rem = divmod(n, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def shard_instances(n_instances, rank=None, world=None):
+    """Instance range of this rank for the batched controller (no data-path collective)."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    return row_block(n_instances, rank, world)
+
+
+class ShardedSVGD:
+    """phi = (K grad log p + sum grad k)/N for N particles split by row blocks over the ranks of
+    `group` (dust/inference/svgd.py:127-135 with the bw_median bandwidth, svgd.py:42-52)."""
+
+    def __init__(self, n_total, dim, group=None, ops=_ops, device=None):
+        self.N, self.D, self.group, self.ops = n_total, dim, group, ops
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if n_total % self.world:
+            raise ValueError(f"N={n_total} must be a multiple of the world size {self.world}")
+        self.rows = row_block(n_total, self.rank, self.world)
+        self.device = device
+        self._gathered = None
+        self._median_ws = None
+
+    def _all_gather(self, local):
+        """[n_loc, C] -> [N, C] (rank-major row order)."""
+        if self.world == 1:
+            return local
+        if self._gathered is None or self._gathered.shape[1] != local.shape[1]:
+            self._gathered = torch.empty((self.N, local.shape[1]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(self._gathered, local.contiguous(), group=self.group)
+        return self._gathered
+
+    def _all_reduce_hist(self, hist):
+        if self.world > 1:
+            dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
+
+    def gather(self, x_local, score_local):
+        xs = self._all_gather(torch.cat([x_local, score_local], dim=1))
+        return xs[:, : self.D].contiguous(), xs[:, self.D:].contiguous()
+
+    def median(self, x_all):
+        """Exact lower median of all N^2 squared distances: each rank histograms its row block."""
+        return self.ops.median_sq_dist(x_all, rows=self.rows, all_reduce=self._all_reduce_hist)
+
+    def phi(self, x_local, score_local, bw=None, bw_scale=1.0):
+        """Returns (phi_local [n_loc, D], coef) with coef = device {gamma, c1, c2, bw}."""
+        x_all, s_all = self.gather(x_local, score_local)
+        if bw is None:
+            med = self.median(x_all)
+            coef = self.ops.bandwidth_from_median(med, self.N, bw_scale, 0)
+            out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=self.rows)
+        else:
+            coef = None
+            out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma=1.0 / (2.0 * bw * bw),
+                                    c1=1.0 / self.N, c2=1.0 / (self.N * bw * bw), rows=self.rows)
+        b, e = self.rows
+        return out["phi"][0, b:e], coef

@@ -20,7 +20,7 @@ def _kernel_mode(kernel):
             "a plain RBF kernel inside SVMPC.phi raises in the reference as well (broadcast of k_XX [N,N] "
             "against the score, svmpc.py:68-71); use iid_mp(base_kernel=RBF()) or RBFKernel()")
     if hasattr(kernel, "lengthscale"):  # gpytorch RBFKernel or the bundled stand-in
-        return "gpytorch", float(torch.as_tensor(kernel.lengthscale).reshape(-1)[0]), 1.0
+        return "gpytorch", float(torch.as_tensor(kernel.lengthscale).detach().reshape(-1)[0]), 1.0
     raise NotImplementedError(f"kernel {kernel!r} has no device kernel")
 
 

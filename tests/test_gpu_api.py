@@ -1,0 +1,209 @@
+"""The reference-shaped classes (MultiDISCO / SVMPC / MPF / likelihoods / models) driven the way
+the reference's demos drive them, on the GPU, against the goldens recorded from the reference."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+import torch.distributions as dist
+
+from oracle import dust_oracle as O
+from tests.util import RTOL_COST, RTOL_PHI, assert_close_to_reference, golden_grid, load, rel_elem, rel_max
+
+pytestmark = pytest.mark.gpu
+
+ENV = dict(dt=0.015, control_type="acceleration", noise_std=[0.1, 0.1], init_state=[-9.0, -9.0, 0, 0],
+           target_state=[9.0, 9.0, 0, 0], can_crash=True, with_obstacle=True, deterministic=True,
+           cost_params=dict(w_qpos=0.5, w_qvel=0.25, w_ctrl=0.2, w_obs=1.0e6, w_qpos_T=1.0e3, w_qvel_T=0.1),
+           obst_preset="grid_4x4", obst_width=2.1, max_speed=5, max_accel=10, map_cell_size=0.1, map_size=[22, 22],
+           map_type="direct")
+
+
+class FixedParams:
+    """params_dist stand-in returning recorded samples (disco.py:168-174 contract)."""
+
+    def __init__(self, samples, event_shape):
+        self.samples, self.event_shape = samples, event_shape
+
+    def sample(self, shape):
+        return self.samples
+
+    def log_prob(self, x):
+        return torch.zeros(x.shape[0])
+
+
+def demo_inst_cost(states, controls=None, n_pol=1, debug=None):
+    # verbatim semantics of the demo's cost callable: the registry must recognise it by probing
+    theta, theta_d = states.chunk(2, dim=1)
+    return 50.0 * (theta.cos() - 1) ** 2 + 1.0 * theta_d ** 2
+
+
+def demo_term_cost(states, n_pol=1, debug=None):
+    return demo_inst_cost(states).squeeze()
+
+
+def build_pendulum(d, kernel):
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.inference.likelihoods import ExponentiatedUtility
+    from dust_b200.inference.svgd import get_gmm
+    from dust_b200.inference.svmpc import SVMPC
+    from dust_b200.kernels.base_kernels import RBF, RBFKernel
+    from dust_b200.kernels.composite_kernels import iid_mp
+    from dust_b200.models.pendulum import PendulumModel
+
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    N, H, A = d["t0_in_theta0"].shape
+    S = d["t0_in_eps"].shape[0]
+    ctrl = MultiDISCO(observation_space=model.observation_space, action_space=model.action_space, hz_len=H,
+                      n_policies=N, action_samples=S, params_samples=8, temperature=1.0, a_cov=4.0 * torch.eye(A),
+                      inst_cost_fn=demo_inst_cost, term_cost_fn=demo_term_cost, params_sampling=True)
+    prior = get_gmm(d["t0_in_mu0"], torch.ones(N), 4.0 * torch.eye(A))
+    k = RBFKernel() if kernel == "rbf" else iid_mp(base_kernel=RBF(bandwidth=-1), ctrl_dim=A, indep_controls=True)
+    lik = ExponentiatedUtility(1.0, n_samples=S, controller=ctrl, model=model)
+    sv = SVMPC(init_particles=d["t0_in_theta0"].clone(), prior=prior, likelihood=lik, kernel=k, n_particles=N,
+               bw_scale=1.0, n_steps=1, optimizer_class=torch.optim.SGD, lr=2.0, weighted_prior=False)
+    return model, ctrl, sv
+
+
+@pytest.mark.parametrize("name,kernel", [("svmpc_pendulum_rbf", "rbf"), ("svmpc_pendulum_mp", "mp")])
+def test_svmpc_closed_loop_free_running(name, kernel):
+    """optimize -> forward repeatedly, feeding only the recorded noise / parameter draws and plant
+    states: particles, weights and the selected policy follow the reference step after step."""
+    d = load(name)
+    model, ctrl, sv = build_pendulum(d, kernel)
+    for t in range(int(d["n_steps"])):
+        gi, go = (lambda k: d[f"t{t}_in_{k}"]), (lambda k: d[f"t{t}_out_{k}"])
+        pd = FixedParams(gi("params"), torch.Size([2]))
+        sv.optimize(gi("state"), pd, eps=gi("eps"))
+        assert rel_elem(sv.likelihood.last_costs.cpu(), go("costs")) <= 2e-4  # free running: inputs drift by rounding
+        theta1 = sv.theta.cpu().clone()
+        a_seq, pw = sv.forward(gi("state"), pd)
+        assert int(sv.i_star) == int(go("i_star"))
+        assert rel_max(theta1, go("theta1")) <= (5e-3 if kernel == "rbf" else 2e-4)
+        assert rel_max(a_seq.cpu(), go("a_seq")) <= (5e-3 if kernel == "rbf" else 2e-4)
+        assert float((pw.cpu() - go("p_weights")).abs().max()) <= 1e-3
+        assert sv.likelihood.last_states.shape == (8, d["t0_in_eps"].shape[0], 3, 31, 2)
+    # the prior exposed as a torch.distributions object is centred on the rolled particles
+    assert torch.equal(sv.prior.component_distribution.base_dist.loc, sv.theta)
+
+
+def test_multidisco_forward_and_step_api():
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.models.particle import Particle
+
+    d = load("fwd_particle_s0")
+    model = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+    S, N, H, A = d["actions"].shape
+    ctrl = MultiDISCO(model.observation_space, model.action_space, H, N, S, temperature=float(d["temp"]),
+                      a_cov=25.0 * torch.eye(A), params_sampling=True, params_samples=4, params_log_space=True,
+                      inst_cost_fn=model.default_inst_cost, term_cost_fn=model.default_term_cost)
+    ctrl.a_mat = d["a_mat0"].clone().cuda()
+    pd = FixedParams(d["params"], torch.Size([1]))
+    costs, states, actions, weights, plogp = ctrl.forward(d["state"], model, pd, d["actions"])
+    assert costs.shape == (S, N) and states.shape == (4, S, N, H + 1, 4) and actions.shape == (4, S, N, H, A)
+    assert rel_elem(costs.cpu(), d["costs"]) <= RTOL_COST
+    assert torch.equal(states[:, :8].cpu(), d["states_sub"])
+    assert rel_max(ctrl.a_mat.cpu(), d["a_mat1"]) <= 1e-4
+    c2 = copy.deepcopy(ctrl)
+    nxt = c2.step(strategy="argmax")
+    assert rel_max(nxt.cpu(), d["step_argmax_action"]) <= 1e-4
+    assert rel_max(c2.a_mat.cpu(), d["step_argmax_a_mat"]) <= 1e-4
+    with pytest.raises(ValueError):
+        ctrl.step(strategy="bogus")
+    # internal sampling path runs and updates the plan
+    ctrl.forward(d["state"], model, pd)
+    assert torch.isfinite(ctrl.a_mat).all()
+
+
+def test_model_step_and_costs_api():
+    from dust_b200.models.particle import Particle
+    from dust_b200.models.pendulum import PendulumModel
+
+    cfg = O.ParticleCfg(golden_grid())
+    torch.manual_seed(0)
+    model = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+    x = torch.randn(500, 4) * torch.tensor([7.0, 7.0, 2.0, 2.0])
+    a = torch.randn(500, 2) * 8
+    m = torch.rand(500, 1) + 1.0
+    assert torch.equal(model.step(x, a, {"mass": m}).cpu(), O.particle_step(cfg, x, a, m))
+    assert torch.equal(model.step(x, a).cpu(), O.particle_step(cfg, x, a, 2.0))
+    assert rel_max(model.default_inst_cost(x, a).cpu(), O.particle_inst_cost(cfg, x, a)) <= 1e-6
+    assert rel_max(model.default_term_cost(x).cpu(), O.particle_term_cost(cfg, x)) <= 1e-6
+    pend = PendulumModel(uncertain_params=("length", "mass"))
+    xs, us = torch.randn(300, 2) * 3, torch.randn(300, 1) * 3
+    lm = torch.rand(300, 2) * 0.7 + 0.6
+    ref = O.pendulum_step(xs, us, length=lm[:, :1], mass=lm[:, 1:])
+    assert rel_max(pend.step(xs, us, {"length": lm[:, :1], "mass": lm[:, 1:]}).cpu(), ref) <= 1e-6
+    assert rel_max(pend.step(xs, us).cpu(), O.pendulum_step(xs, us)) <= 1e-6
+    # very large angles leave the fast trig range and must still be right
+    big = torch.tensor([[1.0e4, 0.5], [-3.0e6, -1.0], [70.0, 0.0]])
+    assert rel_max(pend.step(big, torch.zeros(3, 1)).cpu(), O.pendulum_step(big, torch.zeros(3, 1))) <= 1e-6
+
+
+def test_mpf_class_matches_reference():
+    from dust_b200.inference.likelihoods import GaussianLikelihood
+    from dust_b200.inference.mpf import MPF
+    from dust_b200.models.particle import Particle
+
+    d = load("dual_particle")
+    model = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+    lik = GaussianLikelihood(initial_obs=d["t0_in_state"], obs_std=float(d["obs_std"]), model=model, log_space=True)
+    mpf = MPF(init_particles=d["t0_in_mpf_x0"].clone(), likelihood=lik, optimizer_class=torch.optim.SGD,
+              lr=float(d["mpf_lr"]), bw=float(d["mpf_prior_bw0"]), bw_scale=1.0)
+    prior0 = mpf.prior  # captured once, as the demos do (particle_example.py:171)
+    for t in range(int(d["n_steps"])):
+        gn, bw = mpf.optimize(d[f"t{t}_out_a_seq"][0], d[f"t{t}_out_next_state"], bw=0.5, n_steps=20)
+        assert rel_max(mpf.x.cpu(), d[f"t{t}_out_mpf_x1"]) <= 5e-4  # free running over 4 x 20 steps
+        assert gn.shape == (20,)
+    # the stale prior object tracks the particles through its aliased centres
+    assert torch.equal(prior0.component_distribution.base_dist.loc, mpf.x)
+    s = prior0.sample([4])
+    assert s.shape == (4, 1) and s.is_cuda
+
+
+def test_unsupported_paths_fail_loudly():
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.models.pendulum import PendulumModel
+
+    model = PendulumModel()
+    ctrl = MultiDISCO(model.observation_space, model.action_space, 5, 2, 4, inst_cost_fn=lambda s, *a, **k: s.sum(-1),
+                      params_sampling=None)
+    with pytest.raises(NotImplementedError):
+        ctrl.forward(torch.zeros(2), model, None, torch.zeros(4, 2, 5, 1))
+    with pytest.raises(NotImplementedError):
+        MultiDISCO(model.observation_space, model.action_space, 5, 2, 4, inst_cost_fn=demo_inst_cost, ctrl_penalty=0.5)
+    with pytest.raises(ValueError):
+        MultiDISCO(model.observation_space, model.action_space, 5, 2, 4, inst_cost_fn=demo_inst_cost,
+                   params_sampling="sometimes")
+    with pytest.raises(ValueError):
+        MultiDISCO(model.observation_space, model.action_space, 5, 2, 4)
+
+
+def test_batched_svmpc_equals_per_instance_runs():
+    """BatchedSVMPC (B instances, one launch per stage) == B independent single-instance cores."""
+    from dust_b200.batched import BatchedSVMPC
+    from dust_b200.inference.core import SvmpcCore
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    B = 80
+    ctl = BatchedSVMPC(PendulumModel(), B, 8, 64, 20, 2.0, 2.0, alpha=1.0, learning_rate=2.0, inst_cost_fn=inst_cost,
+                       term_cost_fn=term_cost, seed=3)
+    state = torch.randn(B, 2, device="cuda")
+    eps = ctl.draw_noise().clone()
+    theta0, mu0 = ctl.core.theta.clone(), ctl.core.mu.clone()
+    ctl.optimize(state, eps)
+    theta1 = ctl.core.theta.clone()
+    a_seq, pw, i_star = ctl.forward()
+    for b in (0, 41, B - 1):
+        one = SvmpcCore(ctl.spec, theta0[b:b + 1].contiguous(), mu0[b:b + 1].contiguous(), torch.ones(1, 8, device="cuda"),
+                        torch.tensor([4.0]), torch.tensor([2.0]), alpha=1.0, lr=2.0, kernel="gpytorch")
+        one.optimize_step(state[b:b + 1].contiguous(), eps[b:b + 1].contiguous())
+        assert rel_max(theta1[b].cpu(), one.theta[0].cpu()) <= 1e-5
+        a1, p1, i1 = one.forward_step()
+        assert int(i1[0]) == int(i_star[b])
+        assert rel_max(a_seq[b].cpu(), a1[0].cpu()) <= 1e-5
+        # and against the oracle
+        st = O.SvmpcState(theta0[b].cpu().double(), mu0[b].cpu().double(), torch.ones(8).double(), 4.0)
+        ref = O.svmpc_optimize(O.Model("pendulum"), st, state[b].cpu().double(), eps[b].cpu().double(),
+                               torch.tensor([2.0]).double(), None, False, 1.0, 2.0, kernel="rbf")
+        assert rel_max(theta1[b].cpu(), ref["theta1"]) <= RTOL_PHI

@@ -1,0 +1,200 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header declares, host
+logic (maps, registries, sharding, Silverman), and that the product never touches the oracle."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import dust_oracle as O
+from tests.util import golden_grid, load
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from dust_b200 import _lib
+
+    lib = _lib.load()  # dlopen works without a GPU (no compute call is made)
+    header = open(os.path.join(ROOT, "include", "dust_b200.h")).read()
+    declared = set(re.findall(r"\b(dust_[a-z0-9_]+)\s*\(", header))
+    declared -= {"dust_status"}
+    assert declared, "no prototypes found in the header"
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/dust_b200.h but not exported"
+        assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in dust_b200/_lib.py"
+    assert lib.dust_abi_version() == 1
+    assert b"sm_100a" in lib.dust_build_info()
+
+
+def test_struct_layouts_match_the_header():
+    """sizeof of every argument struct, computed by gcc from the header, equals ctypes'."""
+    import ctypes
+
+    from dust_b200 import _lib
+
+    names = {"dust_model_desc": _lib.ModelDesc, "dust_rollout_args": _lib.RolloutArgs, "dust_adjoint_args": _lib.AdjointArgs,
+             "dust_gmm_args": _lib.GmmArgs, "dust_median_args": _lib.MedianArgs, "dust_phi_args": _lib.PhiArgs,
+             "dust_svmpc_forward_args": _lib.SvmpcForwardArgs, "dust_disco_step_args": _lib.DiscoStepArgs,
+             "dust_mpf_args": _lib.MpfArgs}
+    src = '#include <stdio.h>\n#include "dust_b200.h"\nint main(){' + "".join(
+        f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
+    exe = "/tmp/dust_sizeof"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    out = subprocess.run([exe], capture_output=True, check=True).stdout.decode()
+    for line in out.strip().splitlines():
+        n, sz = line.split()
+        assert ctypes.sizeof(names[n]) == int(sz), n
+
+
+def test_no_cpu_fallback_without_a_device():
+    from dust_b200 import _lib
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        _lib.require_cuda()
+    from dust_b200.models.pendulum import PendulumModel
+
+    with pytest.raises(RuntimeError):
+        PendulumModel().step(torch.zeros(1, 2), torch.zeros(1, 1))
+
+
+def test_product_never_imports_the_oracle_or_the_reference():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "dust_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M) or "/root/reference" in txt or "refshim" in txt:
+                    bad.append(f)
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("preset,width,name", [("grid_4x4", 2.1, "map_grid4x4"), ("staggered_3-2-3", 2.0, "map_staggered_3-2-3"),
+                                               ("grid_3x3", 1.5, "map_grid_3x3"), ("single_centred", 3.0, "map_single_centred"),
+                                               ("staggered_4-3-4-3-4", 1.0, "map_staggered_4-3-4-3-4"), ("grid_6x6", 1.3, "map_grid_6x6")])
+def test_obstacle_map_matches_reference_generator(preset, width, name):
+    from dust_b200.utils.obstacle_map import generate_obstacle_map, get_obst_preset
+
+    om = generate_obstacle_map([22, 22], get_obst_preset(preset, width), 0.1, map_type="direct")
+    assert np.array_equal(om.map.astype(np.uint8), golden_grid(name))
+    # bit packing the kernels read: bit (ix*ny+iy), LSB first
+    words = om.device_bits("cpu").numpy().view(np.uint32)
+    cells = np.arange(om.map.size)
+    assert np.array_equal((words[cells >> 5] >> (cells & 31)) & 1, om.map.reshape(-1).astype(np.uint32))
+    d = load("map_collisions")
+    if preset == "grid_4x4":
+        assert torch.equal(om.get_collisions(d["X"]), d["coll"])
+    with pytest.raises(IOError):
+        get_obst_preset("nope", 1.0)
+
+
+def test_cost_registry_and_kernel_modes():
+    from dust_b200.inference.svmpc import _kernel_mode
+    from dust_b200.kernels.base_kernels import RBF, RBFKernel
+    from dust_b200.kernels.composite_kernels import iid_mp
+    from dust_b200.models.pendulum import SwingUpCost, _match_swingup
+
+    def demo(states, controls=None, n_pol=1, debug=None):
+        th, thd = states.chunk(2, dim=1)
+        return 50.0 * (th.cos() - 1) ** 2 + 1.0 * thd ** 2
+
+    assert _match_swingup(demo) == pytest.approx((50.0, 1.0), rel=1e-5)
+    assert _match_swingup(SwingUpCost(3.0, 0.5)) == (3.0, 0.5)
+    assert _match_swingup(lambda s, *a, **k: (s ** 2).sum(-1)) is None
+    mode, ell, _ = _kernel_mode(RBFKernel())
+    assert mode == "gpytorch" and abs(ell - np.log(2.0)) < 1e-6
+    assert _kernel_mode(iid_mp(base_kernel=RBF(bandwidth=-1), ctrl_dim=2))[0] == "mp"
+    with pytest.raises(NotImplementedError):
+        _kernel_mode(RBF())
+
+
+def test_silverman_and_box():
+    from dust_b200.inference.mpf import silvermans_rule
+    from dust_b200.utils.spaces import Box
+
+    d = load("dual_pendulum_silverman")
+    for t in range(int(d["n_steps"])):
+        bw = silvermans_rule(d[f"t{t}_in_mpf_x0"].numpy())
+        assert abs(bw - float(d[f"t{t}_out_mpf_bw"])) < 1e-6 * bw
+    b = Box(dim=2, low=-1.0, high=torch.tensor([1.0, 2.0]))
+    assert b.dim == 2 and b.shape == torch.Size([2]) and torch.equal(b.low, torch.tensor([-1.0, -1.0]))
+    with pytest.raises(AssertionError):
+        Box(dim=0)
+
+
+def test_row_blocks_partition():
+    from dust_b200.distributed import row_block
+
+    for n, w in ((65536, 8), (10, 3), (7, 8), (4096, 1)):
+        blocks = [row_block(n, r, w) for r in range(w)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(blocks, blocks[1:]))
+        assert max(e - b for b, e in blocks) - min(e - b for b, e in blocks) <= 1
+
+
+# ---- world_size-2 gloo run of the sharded SVGD host logic (compute callbacks = the oracle) --------
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DUST_ROOT"])
+from oracle import dust_oracle as O
+from dust_b200.distributed import ShardedSVGD, row_block
+
+class OracleOps:
+    """CPU stand-ins with the ABI's semantics: per-rank row-block histogram + all-reduce."""
+    @staticmethod
+    def median_sq_dist(x, rows=None, all_reduce=None):
+        d2 = O.sq_dists_addmm(x[rows[0]:rows[1]], x)
+        bits = d2.reshape(-1).view(torch.int32).to(torch.int64)
+        k = (x.shape[0] ** 2 - 1) // 2
+        hist = torch.bincount(bits >> 16, minlength=65536)
+        all_reduce(hist)
+        cum = hist.cumsum(0); hi = int((cum > k).nonzero()[0]); below = int(cum[hi - 1]) if hi else 0
+        hist2 = torch.bincount(bits[(bits >> 16) == hi] & 0xFFFF, minlength=65536)
+        all_reduce(hist2)
+        lo = int((hist2.cumsum(0) > (k - below)).nonzero()[0])
+        return torch.tensor([(hi << 16) | lo], dtype=torch.int32).view(torch.float32)
+    @staticmethod
+    def bandwidth_from_median(med, N, scale, mode):
+        bw = scale * max(float(torch.sqrt(0.5 * med[0])) / float(torch.tensor(N + 1.0).log()), 1e-5)
+        return torch.tensor([1 / (2 * bw * bw), 1 / N, 1 / (N * bw * bw), bw])
+    @staticmethod
+    def svgd_phi(x, s, gamma_dev=None, rows=None, **kw):
+        g, c1, c2 = [float(v) for v in gamma_dev[:3]]
+        full = O.phi_unified(x[0].double(), s[0].double(), g, c1, c2).float()
+        out = torch.zeros_like(x); out[0, rows[0]:rows[1]] = full[rows[0]:rows[1]]
+        return dict(phi=out)
+
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+N, D = 96, 7
+X = torch.randn(N, D); S = -X
+b, e = row_block(N, r, w)
+sh = ShardedSVGD(N, D, ops=OracleOps)
+phi_loc, coef = sh.phi(X[b:e].clone(), S[b:e].clone())
+bw_ref, med_ref = O.bw_median(X)
+ref = O.phi_svgd(X.double(), S.double(), float(bw_ref)).float()
+assert abs(float(coef[3]) - float(bw_ref)) < 1e-6, (float(coef[3]), float(bw_ref))
+assert float((phi_loc - ref[b:e]).abs().max()) < 1e-5
+gathered = [torch.empty_like(phi_loc) for _ in range(w)]
+dist.all_gather(gathered, phi_loc)
+assert float((torch.cat(gathered) - ref).abs().max()) < 1e-5
+dist.destroy_process_group()
+print("rank", r, "ok")
+'''
+
+
+def test_sharded_svgd_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, DUST_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631", str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2
