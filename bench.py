@@ -35,7 +35,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--instances", type=int, default=4096, help="MPC instances per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=48, help="instances in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="instances in the bounded CPU sample (default: sized for ~15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -81,29 +82,32 @@ def cpu_instance_steps(n_instances, n_steps, threads, seed=0):
     return n_instances * n_steps / dt, dt
 
 
-def best_cpu(n_instances, n_steps):
+def probe_threads():
+    """best intra-op thread count for the eager-torch port on this host (tiny tensors: more
+    threads are often slower)"""
     ncpu = os.cpu_count() or 1
-    best = None
-    for th in sorted({1, min(4, ncpu), min(16, ncpu)}):
+    probe = {}
+    for th in sorted({1, min(2, ncpu), min(4, ncpu), min(8, ncpu), min(16, ncpu)}):
         cpu_instance_steps(2, 1, th)  # warm-up
-        v, dt = cpu_instance_steps(max(2, n_instances // 4), 1, th)
-        if best is None or v > best[0]:
-            best = (v, th)
-    v, dt = cpu_instance_steps(n_instances, n_steps, best[1])
-    return v, best[1], dt
+        probe[th] = cpu_instance_steps(24, 1, th)[0]
+    return max(probe, key=probe.get), probe
+
+
+def best_cpu(n_instances, target_seconds=15.0):
+    th, probe = probe_threads()
+    if n_instances <= 0:
+        n_instances = max(64, int(probe[th] * target_seconds))
+    v, dt = cpu_instance_steps(n_instances, 1, th)
+    return v, th, dt, n_instances, probe
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
     ncpu = os.cpu_count() or 1
-    n = args.cpu_sample
     # thread sweep on a small probe, then K timed "steps", each a bounded sample of n instances
-    probe = {}
-    for th in sorted({1, min(4, ncpu), min(16, ncpu)}):
-        cpu_instance_steps(2, 1, th)
-        probe[th] = cpu_instance_steps(8, 1, th)[0]
-    th = max(probe, key=probe.get)
+    th, probe = probe_threads()
+    n = args.cpu_sample if args.cpu_sample > 0 else max(16, int(probe[th] * 60.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_instance_steps(max(2, n // 8), 1, th)
     t0 = time.perf_counter()
@@ -284,9 +288,10 @@ def run_ours(args, rank, world, local_rank):
     step_kernel_ms = {k: v[1] / K for k, v in prof.items()}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, th, dt = best_cpu(args.cpu_sample, 1)
+        v, th, dt, n_cpu, probe = best_cpu(args.cpu_sample)
         cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port", "host_cpus": os.cpu_count(),
-               "sample": f"{args.cpu_sample} of {B} instances, 1 step each, one instance at a time ({dt:.1f} s)"}
+               "thread_probe": {str(k): round(x, 1) for k, x in probe.items()},
+               "sample": f"{n_cpu} of {B} instances, 1 step each, one instance at a time ({dt:.1f} s of CPU work)"}
     cfg = workload_config(args, world)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
