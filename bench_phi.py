@@ -1,0 +1,120 @@
+#!/usr/bin/env python
+"""Large-N SVGD phi microbenchmark (BASELINE.json configs[3]): N particles, d = 40, canonical SVGD
+direction with the exact median bandwidth.  Reports time, algorithmic TFLOP/s (6 N^2 d for phi,
+4 N^2 d for the two median passes) and, under torchrun, the row-block sharded version
+(all-gather of [X|score] + histogram all-reduce over NCCL).
+
+  python bench_phi.py --n 65536 --steps 5
+  python -m torch.distributed.run --nproc-per-node 8 bench_phi.py --n 65536
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=65536)
+    ap.add_argument("--d", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--check", action="store_true", help="compare a row sample against the float64 oracle")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    import torch.distributed as dist
+
+    from dust_b200 import _lib as L
+    from dust_b200 import ops
+    from dust_b200.distributed import ShardedSVGD, row_block
+
+    torch.cuda.set_device(lr)
+    dev = torch.device("cuda", lr)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N, D = args.n, args.d
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = torch.randn(N, D, device=dev, generator=g)
+    S = -X
+    b, e = row_block(N, rank, world)
+    sh = ShardedSVGD(N, D, device=dev)
+    xl, sl = X[b:e].contiguous(), S[b:e].contiguous()
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn):
+        for _ in range(args.warmup):
+            fn()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms[0])
+
+    coef_holder = {}
+
+    def full():
+        phi, coef = sh.phi(xl, sl)
+        coef_holder["coef"], coef_holder["phi"] = coef, phi
+
+    ms_full = timed(full)
+    coef = coef_holder["coef"]
+    bw = float(coef[3])
+
+    def phi_only():
+        x_all, s_all = sh.gather(xl, sl)
+        ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=sh.rows)
+
+    ms_phi = timed(phi_only)
+    lib = L.load()
+    lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
+    full()
+    prof = L.profiler_report()
+    lib.dust_profiler_enable(0)
+    out = None
+    if rank == 0:
+        fl_phi, fl_med = 6.0 * N * N * D, 4.0 * N * N * D
+        out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "ms_phi_with_median": ms_full, "ms_phi": ms_phi,
+               "algorithmic_tflops_phi": fl_phi / (ms_phi * 1e-3) / 1e12,
+               "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12, "bandwidth": bw,
+               "kernels_ms": {k: v[1] for k, v in prof.items()}}
+    if args.check:
+        from oracle import dust_oracle as O
+        idx = torch.arange(b, e, max(1, (e - b) // 64), device=dev)[:64]
+        Xc, Sc = X.cpu().double(), S.cpu().double()
+        g_, c1, c2 = [float(v) for v in coef[:3].cpu()]
+        xi = Xc[idx.cpu()]
+        d2 = ((xi * xi).sum(-1, keepdim=True) + (Xc * Xc).sum(-1)[None, :] - 2 * xi @ Xc.t()).clamp(min=0)
+        K = (-g_ * d2).exp()
+        ref = c1 * (K @ Sc) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xc)
+        got = coef_holder["phi"][idx - b].cpu().double()
+        err = float((got - ref).abs().max() / ref.abs().max())
+        if rank == 0:
+            out["rel_err_vs_float64_rows"] = err
+            if N <= 16384:
+                bw_ref, _ = O.bw_median(X.cpu())
+                out["bandwidth_ref"] = float(bw_ref)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,8 @@
 //
 // Reference: squared_distance / bw_median dust/inference/svgd.py:28-52 (d2 = |x|^2+|y|^2-2xy,
 // clamped at 0; torch.median = lower median), SVGD.phi dust/inference/svgd.py:127-135.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dust {
@@ -239,19 +241,24 @@ __global__ void __launch_bounds__(kLThreads) phi_large_kernel(const PhiLKParams 
   }
 }
 
-size_t phi_large_workspace(const dust_phi_args* a) { return sizeof(float) * (size_t)a->B * a->N; }
-
 int phi_tc(const dust_phi_args* a, cudaStream_t stream);  // svgd_tc.cu (tcgen05 3xTF32)
 bool phi_tc_supported(const dust_phi_args* a);
+size_t phi_tc_workspace(const dust_phi_args* a);
+
+size_t phi_large_workspace(const dust_phi_args* a) {
+  const size_t simt = sizeof(float) * (size_t)a->B * a->N;
+  if (phi_tc_supported(a)) { const size_t tc = phi_tc_workspace(a); return tc > simt ? tc : simt; }
+  return simt;
+}
 
 int phi_large(const dust_phi_args* a, cudaStream_t stream) {
   const int D = a->D, C = 2 * D + 1;
   DUST_REQUIRE(a->workspace && a->workspace_bytes >= phi_large_workspace(a), DUST_ERR_WORKSPACE,
                "dust_svgd_phi: large-N path needs %zu bytes of workspace", phi_large_workspace(a));
+  if (phi_tc_supported(a) && !getenv("DUST_B200_NO_TC")) return phi_tc(a, stream);
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   const size_t smem = sizeof(float) * ((size_t)2 * D * kLT + 2 * kLT + kLT * (kLT + 1) + (size_t)kLT * C);
   DUST_REQUIRE(smem <= 227 * 1024 && C <= 4 * 68, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: D=%d too large for the tiled kernel", D);
-  if (phi_tc_supported(a)) return phi_tc(a, stream);
   for (int b = 0; b < a->B; ++b) {
     const float* x = a->x + (size_t)b * a->N * D;
     float* xn = (float*)a->workspace + (size_t)b * a->N;

@@ -1,11 +1,448 @@
-// tcgen05 / TMEM 3xTF32 flash-style phi for large N (placeholder until the kernel lands:
-// reports "unsupported" so that svgd_large.cu's SIMT tiles are used).
+// Large-N SVGD phi on the 5th-generation tensor cores (tcgen05 / TMEM), flash style: the Gram
+// tile S = X_i X_j^T and the products K [score | X | 1] run as 3xTF32 MMAs (hi*hi + hi*lo + lo*hi,
+// fp32 accumulation in TMEM) so float32 accuracy holds; exp and the hi/lo split of K happen in
+// registers between the two GEMMs and K is never materialised outside TMEM.
+//
+//   phi_i = c1 * sum_j K_ij s_j + c2 * (x_i sum_j K_ij - sum_j K_ij x_j),  K_ij = exp(-gamma d2_ij),
+//   d2_ij = max(|x_i|^2 + |x_j|^2 - 2 x_i.x_j, 0)          (dust/inference/svgd.py:28-39, 92-99, 127-135)
+//
+// One CTA per 128-row block, 12 warps:
+//   warp 0      producer   cp.async.bulk (1-D TMA) of pre-tiled hi/lo operand images into smem rings
+//   warp 1      MMA issuer one thread: GEMM1(j) -> S[j&1]; GEMM2(j-1): O += P[(j-1)&1] V_{j-1}
+//   warp 2      TMEM allocation
+//   warps 4-7   "softmax" warpgroup A: even column tiles  (tcgen05.ld S, exp, split, tcgen05.st P)
+//   warps 8-11  "softmax" warpgroup B: odd column tiles
+// TMEM columns (512 allocated): S[2] 0..127, P_hi[2] 128..255, P_lo[2] 256..383, O 384..384+NV.
+// Operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8x16B core
+// matrices); the prep kernel writes global memory already in that order, so every tile is one
+// contiguous bulk copy.
 #include "common.cuh"
 
 namespace dust {
-bool phi_tc_supported(const dust_phi_args*) { return false; }
-int phi_tc(const dust_phi_args*, cudaStream_t) {
-  set_error("tcgen05 phi kernel not built");
-  return DUST_ERR_UNSUPPORTED;
+
+constexpr int kTcBM = 128;      // rows per CTA (MMA M)
+constexpr int kTcBN = 64;       // columns per tile (GEMM1 N, GEMM2 K)
+constexpr int kTcThreads = 384;
+constexpr int kXbStages = 4;
+constexpr int kVbStages = 2;
+constexpr uint32_t kSpinCap = 1u << 28;
+
+struct TcParams {
+  int N, D, Dp, NV, T, row_begin;
+  const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *vb_hi, *vb_lo, *xn, *x;
+  float gamma, c1, c2;
+  const float* gamma_dev;
+  float lr;
+  float *phi, *x_out;
+};
+
+__host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+// float index of element (r, k) inside a [R x K] K-major core-matrix tile (K % 4 == 0)
+__host__ __device__ inline int core_index(int r, int k, int K) {
+  return ((r >> 3) * (K >> 2) + (k >> 2)) * 32 + (r & 7) * 4 + (k & 3);
 }
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float v, float hi) { return __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u); }
+
+// ---------------------------------------------------------------------------------------
+// prep: squared norms and the tiled hi / lo operand images
+// ---------------------------------------------------------------------------------------
+__global__ void tc_prep_x_kernel(const float* __restrict__ x, int N, int D, int Dp, float* __restrict__ xa_hi,
+                                 float* __restrict__ xa_lo, float* __restrict__ xb_hi, float* __restrict__ xb_lo,
+                                 float* __restrict__ xn) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)N * Dp) return;
+  const int row = (int)(e / Dp), k = (int)(e - (long long)row * Dp);
+  const float v = k < D ? x[(long long)row * D + k] : 0.f;
+  const float hi = tf32_hi(v), lo = tf32_lo(v, hi);
+  const long long ia = (long long)(row / kTcBM) * kTcBM * Dp + core_index(row % kTcBM, k, Dp);
+  const long long ib = (long long)(row / kTcBN) * kTcBN * Dp + core_index(row % kTcBN, k, Dp);
+  xa_hi[ia] = hi; xa_lo[ia] = lo;
+  xb_hi[ib] = hi; xb_lo[ib] = lo;
+  if (k == 0) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) { const float t = x[(long long)row * D + d]; s += t * t; }
+    xn[row] = s;
+  }
+}
+
+// V^T tiles: rows n2 in [0, NV) = [score dims | x dims | 1 | 0...], K = the 64 columns j of the tile
+__global__ void tc_prep_v_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D, int NV,
+                                 float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)N * NV) return;
+  const int j = (int)(e / NV), n2 = (int)(e - (long long)j * NV);
+  float v = 0.f;
+  if (n2 < D) v = score[(long long)j * D + n2];
+  else if (n2 < 2 * D) v = x[(long long)j * D + (n2 - D)];
+  else if (n2 == 2 * D) v = 1.f;
+  const float hi = tf32_hi(v), lo = tf32_lo(v, hi);
+  const long long idx = (long long)(j / kTcBN) * NV * kTcBN + core_index(n2, j % kTcBN, kTcBN);
+  vb_hi[idx] = hi;
+  vb_lo[idx] = lo;
+}
+
+// ---------------------------------------------------------------------------------------
+// PTX helpers
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; spin < kSpinCap; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();  // a lost arrival must surface as a launch failure, never as a hang
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, no swizzle: LBO = byte distance between K-adjacent core matrices, SBO = between 8-row groups
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3ffffu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4)                    // D format F32
+         | (2u << 7) | (2u << 10)     // A, B format TF32
+         | ((uint32_t)(N >> 3) << 17) // N
+         | ((uint32_t)(M >> 4) << 24);// M       (a_major = b_major = 0: K-major)
+}
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---------------------------------------------------------------------------------------
+// main kernel
+// ---------------------------------------------------------------------------------------
+struct TcSmem {
+  // byte offsets into dynamic shared memory
+  uint32_t a_hi, a_lo, xb, vb, bars, tmem_slot, total;
+  uint32_t xb_stage_bytes, vb_stage_bytes, xb_half, vb_half;
+};
+
+__host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
+  TcSmem s;
+  uint32_t off = 0;
+  s.a_hi = off; off += kTcBM * Dp * 4;
+  s.a_lo = off; off += kTcBM * Dp * 4;
+  s.xb_half = kTcBN * Dp * 4;
+  s.xb_stage_bytes = 2 * s.xb_half;
+  s.xb = off; off += kXbStages * s.xb_stage_bytes;
+  s.vb_half = NV * kTcBN * 4;
+  s.vb_stage_bytes = 2 * s.vb_half + kTcBN * 4;  // hi, lo, |x_j|^2
+  s.vb = off; off += kVbStages * s.vb_stage_bytes;
+  off = (off + 7) & ~7u;
+  s.bars = off; off += 32 * 8;
+  s.tmem_slot = off; off += 16;
+  s.total = off;
+  return s;
+}
+
+enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 11, BAR_S_FULL = 13, BAR_P_FULL = 15,
+       BAR_P_EMPTY = 17, BAR_O_FULL = 19 };
+
+__global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const TcSmem L = tc_smem_layout(p.Dp, p.NV);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rt = blockIdx.x;                 // row tile handled by this CTA
+  const int i0 = p.row_begin + rt * kTcBM;   // first global row
+  const int T = p.T;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[BAR_A], 1);
+    for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[BAR_XB_FULL + s], 1); mbar_init(&bars[BAR_XB_EMPTY + s], 1); }
+    for (int s = 0; s < kVbStages; ++s) { mbar_init(&bars[BAR_VB_FULL + s], 1); mbar_init(&bars[BAR_VB_EMPTY + s], 1); }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars[BAR_S_FULL + b], 1);
+      mbar_init(&bars[BAR_P_FULL + b], 4);   // one arrival per softmax warp of the group
+      mbar_init(&bars[BAR_P_EMPTY + b], 1);
+    }
+    mbar_init(&bars[BAR_O_FULL], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tS = tmem, tPhi = tmem + 128, tPlo = tmem + 256, tO = tmem + 384;
+
+  if (warp == 0) {
+    // ------------------------------ producer ------------------------------------------
+    if (lane == 0) {
+      const uint32_t a_bytes = kTcBM * p.Dp * 4;
+      const long long arow = (long long)(i0 / kTcBM) * kTcBM * p.Dp;
+      mbar_expect_tx(&bars[BAR_A], 2 * a_bytes);
+      bulk_g2s(smem + L.a_hi, p.xa_hi + arow, a_bytes, &bars[BAR_A]);
+      bulk_g2s(smem + L.a_lo, p.xa_lo + arow, a_bytes, &bars[BAR_A]);
+      for (int j = 0; j < T; ++j) {
+        const int sx = j % kXbStages;
+        mbar_wait(&bars[BAR_XB_EMPTY + sx], ((j / kXbStages) & 1) ^ 1);
+        unsigned char* xb = smem + L.xb + sx * L.xb_stage_bytes;
+        mbar_expect_tx(&bars[BAR_XB_FULL + sx], L.xb_stage_bytes);
+        bulk_g2s(xb, p.xb_hi + (long long)j * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+        bulk_g2s(xb + L.xb_half, p.xb_lo + (long long)j * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------ producer of the V^T tiles --------------------------
+    if (lane == 0) {
+      for (int j = 0; j < T; ++j) {
+        const int sv = j % kVbStages;
+        mbar_wait(&bars[BAR_VB_EMPTY + sv], ((j / kVbStages) & 1) ^ 1);
+        unsigned char* vb = smem + L.vb + sv * L.vb_stage_bytes;
+        mbar_expect_tx(&bars[BAR_VB_FULL + sv], L.vb_stage_bytes);
+        bulk_g2s(vb, p.vb_hi + (long long)j * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
+        bulk_g2s(vb + L.vb_half, p.vb_lo + (long long)j * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
+        bulk_g2s(vb + 2 * L.vb_half, p.xn + (long long)j * kTcBN, kTcBN * 4, &bars[BAR_VB_FULL + sv]);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ----------------------------------------
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
+      const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV);
+      const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;     // 8-row group stride of the X tiles
+      const uint32_t sbo2 = (uint32_t)(kTcBN / 4) * 128u;    // ... of the V^T tiles
+      const uint32_t a_hi = smem_u32(smem + L.a_hi), a_lo = smem_u32(smem + L.a_lo);
+      const int ks1 = p.Dp / 8, ks2 = kTcBN / 8;
+      mbar_wait(&bars[BAR_A], 0);
+      auto gemm2 = [&](int j) {
+        const int b = j & 1, sv = j % kVbStages;
+        mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);
+        mbar_wait(&bars[BAR_P_FULL + b], (j >> 1) & 1);
+        tc_fence_after();
+        const uint32_t vb_hi = smem_u32(smem + L.vb + sv * L.vb_stage_bytes), vb_lo = vb_hi + L.vb_half;
+        for (int kk = 0; kk < ks2; ++kk) {
+          const uint64_t bh = make_desc(vb_hi + kk * 256, 128, sbo2), bl = make_desc(vb_lo + kk * 256, 128, sbo2);
+          const uint32_t ph = tPhi + b * kTcBN + kk * 8, pl = tPlo + b * kTcBN + kk * 8;
+          mma_ts(tO, ph, bh, idesc2, (j > 0 || kk > 0) ? 1u : 0u);
+          mma_ts(tO, ph, bl, idesc2, 1u);
+          mma_ts(tO, pl, bh, idesc2, 1u);
+        }
+        tc_commit(&bars[BAR_P_EMPTY + b]);
+        tc_commit(&bars[BAR_VB_EMPTY + sv]);
+      };
+      for (int j = 0; j < T; ++j) {
+        const int b = j & 1, sx = j % kXbStages;
+        mbar_wait(&bars[BAR_XB_FULL + sx], (j / kXbStages) & 1);
+        tc_fence_after();
+        const uint32_t xb_hi = smem_u32(smem + L.xb + sx * L.xb_stage_bytes), xb_lo = xb_hi + L.xb_half;
+        for (int kk = 0; kk < ks1; ++kk) {
+          const uint64_t ah = make_desc(a_hi + kk * 256, 128, sbo1), al = make_desc(a_lo + kk * 256, 128, sbo1);
+          const uint64_t bh = make_desc(xb_hi + kk * 256, 128, sbo1), bl = make_desc(xb_lo + kk * 256, 128, sbo1);
+          mma_ss(tS + b * kTcBN, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+          mma_ss(tS + b * kTcBN, ah, bl, idesc1, 1u);
+          mma_ss(tS + b * kTcBN, al, bh, idesc1, 1u);
+        }
+        tc_commit(&bars[BAR_S_FULL + b]);
+        tc_commit(&bars[BAR_XB_EMPTY + sx]);
+        if (j >= 1) gemm2(j - 1);
+      }
+      gemm2(T - 1);
+      tc_commit(&bars[BAR_O_FULL]);
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ softmax warpgroups ---------------------------------
+    const int wg = (warp - 4) >> 2;          // 0: even tiles, 1: odd tiles
+    const int q = warp & 3;                  // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    float gamma = p.gamma;
+    if (p.gamma_dev) gamma = p.gamma_dev[0];
+    const float g2 = gamma * 1.4426950408889634f;  // exp(-g d2) = 2^(-g log2(e) d2)
+    const float xn_i = p.xn[i0 + row];
+    for (int j = wg; j < T; j += 2) {
+      const int b = wg, it = j >> 1, sv = j % kVbStages;
+      mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);   // |x_j|^2 of this tile
+      const float* xnj = reinterpret_cast<const float*>(smem + L.vb + sv * L.vb_stage_bytes + 2 * L.vb_half);
+      mbar_wait(&bars[BAR_S_FULL + b], it & 1);
+      mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32], lo[32];
+        tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float s = __uint_as_float(r[c]);
+          const float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
+          const float kv = ex2_approx(-g2 * d2);
+          const float hi = tf32_hi(kv);
+          r[c] = __float_as_uint(hi);
+          lo[c] = __float_as_uint(tf32_lo(kv, hi));
+        }
+        tmem_st32(tPhi + lane_base + b * kTcBN + half * 32, r);
+        tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
+    }
+    // ------------------------------ epilogue (warpgroup A) -----------------------------
+    if (wg == 0) {
+      mbar_wait(&bars[BAR_O_FULL], 0);
+      tc_fence_after();
+      float c1 = p.c1, c2 = p.c2;
+      if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
+      const int gi = i0 + row;
+      // O row -> local array: [0,D) = sum_j K s_j, [D,2D) = sum_j K x_j, [2D] = sum_j K
+      float o[128];
+      for (int c0 = 0; c0 < p.NV; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tO + lane_base + c0, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) o[c0 + c] = __uint_as_float(r[c]);
+      }
+      const float ksum = o[2 * p.D];
+      for (int d = 0; d < p.D; ++d) {
+        const float xv = p.x[(long long)gi * p.D + d];
+        const float ph = c1 * o[d] + c2 * (ksum * xv - o[p.D + d]);
+        if (p.phi) p.phi[(long long)gi * p.D + d] = ph;
+        if (p.x_out) p.x_out[(long long)gi * p.D + d] = xv + p.lr * ph;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+bool phi_tc_supported(const dust_phi_args* a) {
+  if (a->B != 1 || a->per_dim) return false;
+  const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
+  if (a->N % kTcBM || r0 % kTcBM || r1 % kTcBM || a->N < 1024) return false;
+  const int Dp = round_up(a->D, 8), NV = round_up(2 * a->D + 1, 32);
+  if (NV > 128 || Dp > 64) return false;
+  return tc_smem_layout(Dp, NV).total <= 227 * 1024;
+}
+
+size_t phi_tc_workspace(const dust_phi_args* a) {
+  const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D + 1, 32);
+  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64);
+}
+
+int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
+  const int N = a->N, D = a->D, Dp = round_up(D, 8), NV = round_up(2 * D + 1, 32);
+  DUST_REQUIRE(a->workspace && a->workspace_bytes >= phi_tc_workspace(a), DUST_ERR_WORKSPACE,
+               "dust_svgd_phi: tensor-core path needs %zu bytes of workspace", phi_tc_workspace(a));
+  float* ws = (float*)a->workspace;
+  float* xn = ws;              ws += (N + 63) / 64 * 64;
+  float* xa_hi = ws;           ws += (size_t)N * Dp;
+  float* xa_lo = ws;           ws += (size_t)N * Dp;
+  float* xb_hi = ws;           ws += (size_t)N * Dp;
+  float* xb_lo = ws;           ws += (size_t)N * Dp;
+  float* vb_hi = ws;           ws += (size_t)N * NV;
+  float* vb_lo = ws;
+  {
+    DUST_TIMED("tc_prep_x_kernel", stream);
+    tc_prep_x_kernel<<<ceil_div((long long)N * Dp, 256), 256, 0, stream>>>(a->x, N, D, Dp, xa_hi, xa_lo, xb_hi, xb_lo, xn);
+  }
+  DUST_LAUNCH_OK("tc_prep_x_kernel");
+  {
+    DUST_TIMED("tc_prep_v_kernel", stream);
+    tc_prep_v_kernel<<<ceil_div((long long)N * NV, 256), 256, 0, stream>>>(a->x, a->score, N, D, NV, vb_hi, vb_lo);
+  }
+  DUST_LAUNCH_OK("tc_prep_v_kernel");
+  const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
+  TcParams p;
+  p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0;
+  p.xa_hi = xa_hi; p.xa_lo = xa_lo; p.xb_hi = xb_hi; p.xb_lo = xb_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
+  p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out;
+  const TcSmem L = tc_smem_layout(Dp, NV);
+  DUST_CUDA_OK(cudaFuncSetAttribute(phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  {
+    DUST_TIMED("phi_tc_kernel", stream);
+    phi_tc_kernel<<<(r1 - r0) / kTcBM, kTcThreads, L.total, stream>>>(p);
+  }
+  DUST_LAUNCH_OK("phi_tc_kernel");
+  return DUST_OK;
+}
+
 }  // namespace dust
