@@ -10,9 +10,15 @@
 //   warp 0      producer   cp.async.bulk (1-D TMA) of pre-tiled hi/lo operand images into smem rings
 //   warp 1      MMA issuer one thread: GEMM1(j) -> S[j&1]; GEMM2(j-1): O += P[(j-1)&1] V_{j-1}
 //   warp 2      TMEM allocation
+//   warp 3      producer of the V^T tiles
 //   warps 4-7   "softmax" warpgroup A: even column tiles  (tcgen05.ld S, exp, split, tcgen05.st P)
 //   warps 8-11  "softmax" warpgroup B: odd column tiles
-// TMEM columns (512 allocated): S[2] 0..127, P_hi[2] 128..255, P_lo[2] 256..383, O 384..384+NV.
+//   warps 12-15 flush warpgroup: every kTcChunk column tiles the O accumulator is drained into
+//               round-to-nearest fp32 registers (the tensor core's own fp32 accumulation truncates:
+//               measured bias ~2e-8 per accumulation step, i.e. 5e-4 over the 24576 steps of
+//               N = 65536 if left in TMEM), then the final phi row is formed.
+// TMEM columns (512 allocated): S/P_hi[2] 0..127 (P_hi overwrites the S it was computed from),
+// P_lo[2] 128..255, O[2] 256..256+2*NV.
 // Operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8x16B core
 // matrices); the prep kernel writes global memory already in that order, so every tile is one
 // contiguous bulk copy.
@@ -22,7 +28,8 @@ namespace dust {
 
 constexpr int kTcBM = 128;      // rows per CTA (MMA M)
 constexpr int kTcBN = 64;       // columns per tile (GEMM1 N, GEMM2 K)
-constexpr int kTcThreads = 384;
+constexpr int kTcThreads = 512;
+constexpr int kTcChunk = 32;    // column tiles accumulated in TMEM between two flushes
 constexpr int kXbStages = 4;
 constexpr int kVbStages = 2;
 constexpr uint32_t kSpinCap = 1u << 28;
@@ -34,6 +41,7 @@ struct TcParams {
   const float* gamma_dev;
   float lr;
   float *phi, *x_out;
+  float* oacc;  // [grid][NV][128] running sums of the drained O chunks (column-major per CTA)
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -210,7 +218,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
 }
 
 enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 11, BAR_S_FULL = 13, BAR_P_FULL = 15,
-       BAR_P_EMPTY = 17, BAR_O_FULL = 19 };
+       BAR_P_EMPTY = 17, BAR_O_FULL = 19, BAR_O_EMPTY = 21 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -231,7 +239,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       mbar_init(&bars[BAR_P_FULL + b], 4);   // one arrival per softmax warp of the group
       mbar_init(&bars[BAR_P_EMPTY + b], 1);
     }
-    mbar_init(&bars[BAR_O_FULL], 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&bars[BAR_O_FULL + b], 1);
+      mbar_init(&bars[BAR_O_EMPTY + b], 4);  // one arrival per flush warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -243,7 +254,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tPhi = tmem + 128, tPlo = tmem + 256, tO = tmem + 384;
+  const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + 128, tO = tmem + 256;
+  const int n_chunks = (T + kTcChunk - 1) / kTcChunk;
 
   if (warp == 0) {
     // ------------------------------ producer ------------------------------------------
@@ -291,15 +303,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         mbar_wait(&bars[BAR_P_FULL + b], (j >> 1) & 1);
         tc_fence_after();
         const uint32_t vb_hi = smem_u32(smem + L.vb + sv * L.vb_stage_bytes), vb_lo = vb_hi + L.vb_half;
+        const int ch = j / kTcChunk, ob = ch & 1;
+        const bool first = (j % kTcChunk) == 0, last = (j % kTcChunk) == kTcChunk - 1 || j == T - 1;
+        if (first) {  // the flush warps must have drained this O buffer (two chunks ago)
+          mbar_wait(&bars[BAR_O_EMPTY + ob], ((ch >> 1) & 1) ^ 1);
+          tc_fence_after();
+        }
+        const uint32_t tOb = tO + ob * p.NV;
         for (int kk = 0; kk < ks2; ++kk) {
           const uint64_t bh = make_desc(vb_hi + kk * 256, 128, sbo2), bl = make_desc(vb_lo + kk * 256, 128, sbo2);
           const uint32_t ph = tPhi + b * kTcBN + kk * 8, pl = tPlo + b * kTcBN + kk * 8;
-          mma_ts(tO, ph, bh, idesc2, (j > 0 || kk > 0) ? 1u : 0u);
-          mma_ts(tO, ph, bl, idesc2, 1u);
-          mma_ts(tO, pl, bh, idesc2, 1u);
+          mma_ts(tOb, ph, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
+          mma_ts(tOb, ph, bl, idesc2, 1u);
+          mma_ts(tOb, pl, bh, idesc2, 1u);
         }
         tc_commit(&bars[BAR_P_EMPTY + b]);
         tc_commit(&bars[BAR_VB_EMPTY + sv]);
+        if (last) tc_commit(&bars[BAR_O_FULL + ob]);
       };
       for (int j = 0; j < T; ++j) {
         const int b = j & 1, sx = j % kXbStages;
@@ -318,9 +338,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         if (j >= 1) gemm2(j - 1);
       }
       gemm2(T - 1);
-      tc_commit(&bars[BAR_O_FULL]);
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------ softmax warpgroups ---------------------------------
     const int wg = (warp - 4) >> 2;          // 0: even tiles, 1: odd tiles
     const int q = warp & 3;                  // TMEM lane quarter this warp may touch
@@ -330,6 +349,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     if (p.gamma_dev) gamma = p.gamma_dev[0];
     const float g2 = gamma * 1.4426950408889634f;  // exp(-g d2) = 2^(-g log2(e) d2)
     const float xn_i = p.xn[i0 + row];
+    const int jdiag = (i0 + row) / kTcBN;
     for (int j = wg; j < T; j += 2) {
       const int b = wg, it = j >> 1, sv = j % kVbStages;
       mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);   // |x_j|^2 of this tile
@@ -337,11 +357,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       mbar_wait(&bars[BAR_S_FULL + b], it & 1);
       mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
       tc_fence_after();
+      // the tile that holds column i itself: d2_ii is exactly 0 (the 3xTF32 Gram entry only gives
+      // |x_i|^2 to ~1e-6 relative, which a narrow kernel would amplify)
+      const int cdiag = (j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32], lo[32];
         tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
         tmem_wait_ld();
+        if (cdiag >= half * 32 && cdiag < half * 32 + 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (half * 32 + c == cdiag) r[c] = __float_as_uint(0.5f * (xnj[half * 32 + c] + xn_i));  // => d2 = 0
+        }
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float s = __uint_as_float(r[c]);
@@ -359,29 +387,43 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
     }
-    // ------------------------------ epilogue (warpgroup A) -----------------------------
-    if (wg == 0) {
-      mbar_wait(&bars[BAR_O_FULL], 0);
+  } else if (warp >= 12) {
+    // ------------------------------ flush warpgroup + epilogue -------------------------
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    // running sums live in a per-CTA global scratch, column-major ([NV][128]: a warp touches 128
+    // contiguous bytes per column); only 32 columns are in registers at any time
+    float* og = p.oacc + (size_t)blockIdx.x * p.NV * kTcBM + row;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int ob = ch & 1;
+      mbar_wait(&bars[BAR_O_FULL + ob], (ch >> 1) & 1);
       tc_fence_after();
-      float c1 = p.c1, c2 = p.c2;
-      if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
-      const int gi = i0 + row;
-      // O row -> local array: [0,D) = sum_j K s_j, [D,2D) = sum_j K x_j, [2D] = sum_j K
-      float o[128];
       for (int c0 = 0; c0 < p.NV; c0 += 32) {
         uint32_t r[32];
-        tmem_ld32(tO + lane_base + c0, r);
+        tmem_ld32(tO + lane_base + ob * p.NV + c0, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) o[c0 + c] = __uint_as_float(r[c]);
+        for (int c = 0; c < 32; ++c) {
+          float v = __uint_as_float(r[c]);
+          if (ch > 0) v += og[(size_t)(c0 + c) * kTcBM];
+          og[(size_t)(c0 + c) * kTcBM] = v;
+        }
       }
-      const float ksum = o[2 * p.D];
-      for (int d = 0; d < p.D; ++d) {
-        const float xv = p.x[(long long)gi * p.D + d];
-        const float ph = c1 * o[d] + c2 * (ksum * xv - o[p.D + d]);
-        if (p.phi) p.phi[(long long)gi * p.D + d] = ph;
-        if (p.x_out) p.x_out[(long long)gi * p.D + d] = xv + p.lr * ph;
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_O_EMPTY + ob]);
+    }
+    float c1 = p.c1, c2 = p.c2;
+    if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
+    const int gi = i0 + row;
+    // [0,D) = sum_j K s_j, [D,2D) = sum_j K x_j, [2D] = sum_j K
+    const float ksum = og[(size_t)(2 * p.D) * kTcBM];
+    for (int d = 0; d < p.D; ++d) {
+      const float xv = p.x[(long long)gi * p.D + d];
+      const float ph = c1 * og[(size_t)d * kTcBM] + c2 * (ksum * xv - og[(size_t)(p.D + d) * kTcBM]);
+      if (p.phi) p.phi[(long long)gi * p.D + d] = ph;
+      if (p.x_out) p.x_out[(long long)gi * p.D + d] = xv + p.lr * ph;
     }
   }
   tc_fence_before();
@@ -399,13 +441,14 @@ bool phi_tc_supported(const dust_phi_args* a) {
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   if (a->N % kTcBM || r0 % kTcBM || r1 % kTcBM || a->N < 1024) return false;
   const int Dp = round_up(a->D, 8), NV = round_up(2 * a->D + 1, 32);
-  if (NV > 128 || Dp > 64) return false;
+  if (2 * NV > 256 || Dp > 64) return false;
   return tc_smem_layout(Dp, NV).total <= 227 * 1024;
 }
 
 size_t phi_tc_workspace(const dust_phi_args* a) {
   const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D + 1, 32);
-  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64);
+  const size_t rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
+  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64 + rows * NV);
 }
 
 int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
@@ -419,7 +462,8 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   float* xb_hi = ws;           ws += (size_t)N * Dp;
   float* xb_lo = ws;           ws += (size_t)N * Dp;
   float* vb_hi = ws;           ws += (size_t)N * NV;
-  float* vb_lo = ws;
+  float* vb_lo = ws;           ws += (size_t)N * NV;
+  float* oacc = ws;
   {
     DUST_TIMED("tc_prep_x_kernel", stream);
     tc_prep_x_kernel<<<ceil_div((long long)N * Dp, 256), 256, 0, stream>>>(a->x, N, D, Dp, xa_hi, xa_lo, xb_hi, xb_lo, xn);
@@ -434,7 +478,7 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   TcParams p;
   p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0;
   p.xa_hi = xa_hi; p.xa_lo = xa_lo; p.xb_hi = xb_hi; p.xb_lo = xb_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
-  p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out;
+  p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out; p.oacc = oacc;
   const TcSmem L = tc_smem_layout(Dp, NV);
   DUST_CUDA_OK(cudaFuncSetAttribute(phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   {

@@ -466,7 +466,58 @@ def test_large_phi_properties(env):
     bw_ref, med_ref = O.bw_median(X)
     assert abs(float(med[0]) - float(med_ref)) <= 4e-6 * float(med_ref)
     assert abs(bw - float(bw_ref)) <= 1e-5 * float(bw_ref)
-    # rows split in blocks (what each rank computes) == the full result
+    # rows split in blocks (what each rank computes) == the full result: bit for bit when the
+    # blocks are 128-aligned (same tensor-core tiles), to rounding otherwise (SIMT tiles)
+    a = ops.svgd_phi(x, s, gamma_dev=coef, rows=(0, 1536))["phi"]
+    b = ops.svgd_phi(x, s, gamma_dev=coef, rows=(1536, N))["phi"]
+    assert torch.equal(torch.cat([a[:, :1536], b[:, 1536:]], 1), out["phi"])
     a = ops.svgd_phi(x, s, gamma_dev=coef, rows=(0, 1500))["phi"]
     b = ops.svgd_phi(x, s, gamma_dev=coef, rows=(1500, N))["phi"]
-    assert torch.equal(torch.cat([a[:, :1500], b[:, 1500:]], 1), out["phi"])
+    assert rel_max(torch.cat([a[:, :1500], b[:, 1500:]], 1).cpu(), ref) <= RTOL_PHI
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 / TMEM 3xTF32 phi (N multiple of 128, N >= 1024, D <= 47)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,D,gamma", [(1024, 40, 0.02), (2048, 16, 0.05), (4096, 40, 0.015), (8192, 24, 0.03), (3072, 40, 1.5)])
+def test_tensor_core_phi_vs_float64_and_simt(env, N, D, gamma):
+    """wide kernels (every pair contributes) and a very narrow one (gamma = 1.5: only the exact-zero
+    diagonal and near neighbours survive) against the tiled float64 oracle; SIMT tiles as a second opinion."""
+    import os
+
+    from dust_b200 import ops
+
+    torch.manual_seed(N + D)
+    X, S = torch.randn(N, D), torch.randn(N, D)
+    x, s = cu(X).unsqueeze(0), cu(S).unsqueeze(0)
+    c1, c2 = 1.0 / N, 0.37 / N
+    os.environ.pop("DUST_B200_NO_TC", None)
+    tc = ops.svgd_phi(x, s, gamma=gamma, c1=c1, c2=c2, lr=0.5, want_update=True)
+    os.environ["DUST_B200_NO_TC"] = "1"
+    try:
+        simt = ops.svgd_phi(x, s, gamma=gamma, c1=c1, c2=c2)["phi"][0].cpu()
+    finally:
+        os.environ.pop("DUST_B200_NO_TC", None)
+    ref = O.phi_unified_tiled(X, S, gamma, c1, c2, tile=1024)
+    assert rel_max(tc["phi"][0].cpu(), ref) <= RTOL_PHI
+    assert rel_max(simt, ref) <= RTOL_PHI
+    assert rel_max(tc["x_out"][0].cpu(), X.double() + 0.5 * ref) <= RTOL_PHI
+    # row blocks (what each rank computes) reproduce the full result bit for bit
+    a = ops.svgd_phi(x, s, gamma=gamma, c1=c1, c2=c2, rows=(0, 384))["phi"]
+    b = ops.svgd_phi(x, s, gamma=gamma, c1=c1, c2=c2, rows=(384, N))["phi"]
+    assert torch.equal(torch.cat([a[:, :384], b[:, 384:]], 1), tc["phi"])
+
+
+def test_tensor_core_path_is_taken(env):
+    """the profiler must show phi_tc_kernel (not the SIMT tiles) for a qualifying shape"""
+    from dust_b200 import ops
+
+    L = env["L"]
+    lib = L.load()
+    x = torch.randn(1, 2048, 40, device=DEV)
+    lib.dust_profiler_reset()
+    lib.dust_profiler_enable(1)
+    ops.svgd_phi(x, -x, gamma=0.02, c1=1 / 2048, c2=1 / 2048)
+    prof = L.profiler_report()
+    lib.dust_profiler_enable(0)
+    assert "phi_tc_kernel" in prof and "phi_large_kernel" not in prof
