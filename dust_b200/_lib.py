@@ -110,6 +110,11 @@ SYMBOLS = {
     "dust_gmm_score": (C.c_int, [C.POINTER(GmmArgs), _p]),
     "dust_median_hist_pass": (C.c_int, [C.POINTER(MedianArgs), _i, _p]),
     "dust_median_select": (C.c_int, [C.POINTER(MedianArgs), _i, _p, _p]),
+    "dust_median_fast_supported": (C.c_int, [_i, _i]),
+    "dust_median_fast_workspace_bytes": (_sz, [_i, _i]),
+    "dust_median_fast_prepare": (C.c_int, [C.POINTER(MedianArgs), _p, _sz, _p]),
+    "dust_median_fast_count": (C.c_int, [C.POINTER(MedianArgs), _p, _sz, _p]),
+    "dust_median_fast_select": (C.c_int, [C.POINTER(MedianArgs), _p, _p]),
     "dust_phi_workspace_bytes": (_sz, [C.POINTER(PhiArgs)]),
     "dust_svgd_phi": (C.c_int, [C.POINTER(PhiArgs), _p]),
     "dust_bandwidth_from_median": (C.c_int, [_p, _i, _f, _i, _p, _p]),

@@ -70,6 +70,7 @@ struct HistKParams {
 
 __global__ void __launch_bounds__(kLThreads) median_hist_kernel(const HistKParams k) {
   extern __shared__ __align__(16) float sm[];
+  if (k.selected[5] != 0u) return;  // the tensor-core window pass already found the median
   float* xi_t = sm;                    // [D][64]
   float* xj_t = xi_t + k.D * kLT;      // [D][64]
   float* xn_i = xj_t + k.D * kLT;      // [64]
@@ -112,6 +113,7 @@ __global__ void __launch_bounds__(kLThreads) median_hist_kernel(const HistKParam
 // single-CTA scan of the 65536-bin histogram for the bin that holds rank `k`
 __global__ void __launch_bounds__(1024) median_select_kernel(unsigned long long* hist, uint32_t* selected, int pass,
                                                              long long n_total, float* median_out) {
+  if (selected[5] != 0u) return;
   __shared__ unsigned long long part[1024];
   __shared__ int s_chunk;
   __shared__ unsigned long long s_before;
@@ -307,6 +309,43 @@ extern "C" int dust_median_hist_pass(const dust_median_args* a, int32_t pass, vo
   { DUST_TIMED("median_hist_kernel", stream); median_hist_kernel<<<ceil_div(r1 - r0, kLT), kLThreads, smem, stream>>>(k); }
   DUST_LAUNCH_OK("median_hist_kernel");
   return DUST_OK;
+}
+
+namespace dust {
+bool median_tc_supported(int N, int D);
+size_t median_tc_workspace(int N, int D);
+int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t stream);
+int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t stream);
+int median_tc_select(const dust_median_args* a, float* median_out, cudaStream_t stream);
+}  // namespace dust
+
+extern "C" int dust_median_fast_supported(int32_t N, int32_t D) { return median_tc_supported(N, D) ? 1 : 0; }
+extern "C" size_t dust_median_fast_workspace_bytes(int32_t N, int32_t D) { return median_tc_workspace(N, D); }
+
+static int check_fast(const dust_median_args* a, const void* workspace, size_t bytes, const char* who) {
+  DUST_REQUIRE(a != nullptr && a->x && a->hist && a->selected, DUST_ERR_INVALID_ARG, "%s: x, hist, selected are required", who);
+  DUST_REQUIRE(median_tc_supported(a->N, a->D), DUST_ERR_UNSUPPORTED, "%s: shape N=%d D=%d not supported by the tensor-core pass", who, a->N, a->D);
+  DUST_REQUIRE(workspace && bytes >= median_tc_workspace(a->N, a->D), DUST_ERR_WORKSPACE, "%s: workspace needs %zu bytes", who,
+               median_tc_workspace(a->N, a->D));
+  const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
+  DUST_REQUIRE(r0 >= 0 && r1 <= a->N && r0 < r1 && r0 % 128 == 0 && r1 % 128 == 0, DUST_ERR_INVALID_ARG,
+               "%s: row range must be 128-aligned", who);
+  return DUST_OK;
+}
+
+extern "C" int dust_median_fast_prepare(const dust_median_args* a, void* workspace, size_t bytes, void* stream_) {
+  const int rc = check_fast(a, workspace, bytes, "dust_median_fast_prepare");
+  if (rc) return rc;
+  return median_tc_prepare(a, workspace, (cudaStream_t)stream_);
+}
+extern "C" int dust_median_fast_count(const dust_median_args* a, void* workspace, size_t bytes, void* stream_) {
+  const int rc = check_fast(a, workspace, bytes, "dust_median_fast_count");
+  if (rc) return rc;
+  return median_tc_count(a, workspace, (cudaStream_t)stream_);
+}
+extern "C" int dust_median_fast_select(const dust_median_args* a, float* median_out, void* stream_) {
+  DUST_REQUIRE(a != nullptr && a->hist && a->selected, DUST_ERR_INVALID_ARG, "dust_median_fast_select: hist and selected are required");
+  return median_tc_select(a, median_out, (cudaStream_t)stream_);
 }
 
 extern "C" int dust_median_select(const dust_median_args* a, int32_t pass, float* median_out, void* stream_) {

@@ -140,6 +140,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
   return d;                // base_offset 0, lbo_mode 0, layout_type 0 (SWIZZLE_NONE)
 }
+// descriptors of one operand differ only in the 14-bit start address: keep the high word, bump the low
+__device__ __forceinline__ uint64_t desc_lo_hi(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4)                    // D format F32
          | (2u << 7) | (2u << 10)     // A, B format TF32
@@ -294,15 +300,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV);
       const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;     // 8-row group stride of the X tiles
       const uint32_t sbo2 = (uint32_t)(kTcBN / 4) * 128u;    // ... of the V^T tiles
-      const uint32_t a_hi = smem_u32(smem + L.a_hi), a_lo = smem_u32(smem + L.a_lo);
-      const int ks1 = p.Dp / 8, ks2 = kTcBN / 8;
+      const int ks1 = p.Dp / 8;
+      constexpr int ks2 = kTcBN / 8;
+      // The issuing thread is a single warp: every integer op on the way to an MMA costs ~5 cycles.
+      // Descriptors are therefore built once; per MMA only the low word (start address >> 4) moves.
+      const uint64_t dA = make_desc(smem_u32(smem + L.a_hi), 128, sbo1), dX = make_desc(smem_u32(smem + L.xb), 128, sbo1);
+      const uint64_t dV = make_desc(smem_u32(smem + L.vb), 128, sbo2);
+      const uint32_t hiA = (uint32_t)(dA >> 32), hiV = (uint32_t)(dV >> 32);
+      const uint32_t loA_hi = (uint32_t)dA, loA_lo = loA_hi + ((kTcBM * p.Dp * 4) >> 4);
+      const uint32_t loX0 = (uint32_t)dX, loV0 = (uint32_t)dV;
+      const uint32_t xb_stage16 = L.xb_stage_bytes >> 4, xb_half16 = L.xb_half >> 4;
+      const uint32_t vb_stage16 = L.vb_stage_bytes >> 4, vb_half16 = L.vb_half >> 4;
       mbar_wait(&bars[BAR_A], 0);
       auto gemm2 = [&](int j) {
         const int b = j & 1, sv = j % kVbStages;
         mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);
         mbar_wait(&bars[BAR_P_FULL + b], (j >> 1) & 1);
         tc_fence_after();
-        const uint32_t vb_hi = smem_u32(smem + L.vb + sv * L.vb_stage_bytes), vb_lo = vb_hi + L.vb_half;
         const int ch = j / kTcChunk, ob = ch & 1;
         const bool first = (j % kTcChunk) == 0, last = (j % kTcChunk) == kTcChunk - 1 || j == T - 1;
         if (first) {  // the flush warps must have drained this O buffer (two chunks ago)
@@ -310,12 +324,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
           tc_fence_after();
         }
         const uint32_t tOb = tO + ob * p.NV;
+        const uint32_t vh = loV0 + sv * vb_stage16, vl = vh + vb_half16;
+        const uint32_t ph = tPhi + b * kTcBN, pl = tPlo + b * kTcBN;
+#pragma unroll
         for (int kk = 0; kk < ks2; ++kk) {
-          const uint64_t bh = make_desc(vb_hi + kk * 256, 128, sbo2), bl = make_desc(vb_lo + kk * 256, 128, sbo2);
-          const uint32_t ph = tPhi + b * kTcBN + kk * 8, pl = tPlo + b * kTcBN + kk * 8;
-          mma_ts(tOb, ph, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
-          mma_ts(tOb, ph, bl, idesc2, 1u);
-          mma_ts(tOb, pl, bh, idesc2, 1u);
+          const uint64_t bh = desc_lo_hi(vh + kk * 16, hiV), bl = desc_lo_hi(vl + kk * 16, hiV);
+          mma_ts(tOb, ph + kk * 8, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
+          mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
+          mma_ts(tOb, pl + kk * 8, bh, idesc2, 1u);
         }
         tc_commit(&bars[BAR_P_EMPTY + b]);
         tc_commit(&bars[BAR_VB_EMPTY + sv]);
@@ -325,13 +341,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         const int b = j & 1, sx = j % kXbStages;
         mbar_wait(&bars[BAR_XB_FULL + sx], (j / kXbStages) & 1);
         tc_fence_after();
-        const uint32_t xb_hi = smem_u32(smem + L.xb + sx * L.xb_stage_bytes), xb_lo = xb_hi + L.xb_half;
-        for (int kk = 0; kk < ks1; ++kk) {
-          const uint64_t ah = make_desc(a_hi + kk * 256, 128, sbo1), al = make_desc(a_lo + kk * 256, 128, sbo1);
-          const uint64_t bh = make_desc(xb_hi + kk * 256, 128, sbo1), bl = make_desc(xb_lo + kk * 256, 128, sbo1);
-          mma_ss(tS + b * kTcBN, ah, bh, idesc1, kk > 0 ? 1u : 0u);
-          mma_ss(tS + b * kTcBN, ah, bl, idesc1, 1u);
-          mma_ss(tS + b * kTcBN, al, bh, idesc1, 1u);
+        const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
+        const uint32_t tSb = tS + b * kTcBN;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < ks1) {
+            const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
+            const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+            mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+            mma_ss(tSb, ah, bl, idesc1, 1u);
+            mma_ss(tSb, al, bh, idesc1, 1u);
+          }
         }
         tc_commit(&bars[BAR_S_FULL + b]);
         tc_commit(&bars[BAR_XB_EMPTY + sx]);
@@ -431,6 +451,322 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
+}
+
+// =======================================================================================
+// exact median of the N^2 squared distances on the same pipeline
+//   1. a deterministic sample of 2^20 pairs locates the hi-16-bit bin h of the median;
+//   2. ONE full Gram pass (GEMM1 only) counts, per thread in registers, the values below the window
+//      [(h-1)<<16, (h+2)<<16) of float bit patterns and histograms only the values inside it
+//      (~3 % of them) with 64-bit reductions in global memory;
+//   3. a single CTA finds rank (N^2-1)/2 inside the window.  If the rank falls outside (sample
+//      off by > 65536 ulps, never observed) a flag is left clear and the robust two-pass radix
+//      select of svgd_large.cu runs instead (its kernels exit at once when the flag is set).
+// =======================================================================================
+constexpr int kMedWindowBins = 3 * 65536;
+constexpr int kMedSBufs = 6;        // S ring in TMEM (6 x 64 columns)
+constexpr int kMedSample = 1 << 20;
+
+__device__ __forceinline__ uint32_t hash32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+  return x;
+}
+
+// hist32[32768]: hi-16-bit histogram of the sample (non-negative floats: bits >> 16 < 32768)
+__global__ void med_sample_kernel(const float* __restrict__ x, const float* __restrict__ xn, int N, int D,
+                                  unsigned int* __restrict__ hist32) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= kMedSample) return;
+  const uint32_t i = hash32(2u * k + 1u) % (uint32_t)N, j = hash32(2u * k + 0x9e3779b9u) % (uint32_t)N;
+  float dot = 0.f;
+  for (int d = 0; d < D; ++d) dot = fmaf(x[(long long)i * D + d], x[(long long)j * D + d], dot);
+  const float d2 = (i == j) ? 0.f : fmaxf((xn[j] - 2.0f * dot) + xn[i], 0.f);
+  atomicAdd(&hist32[__float_as_uint(d2) >> 16], 1u);
+}
+
+// state[0] = window start (bit pattern), state[1] = ok flag (cleared here), state[2] = window width.
+// The median's position inside its hi-16 bin is interpolated from the sample counts; the window is
+// that position +- the bit-pattern distance that holds 8 standard deviations of the sample median's
+// quantile (0.5/sqrt(m)), clamped to [4096, kMedWindowBins/2] patterns.
+__global__ void med_sample_select_kernel(unsigned int* hist32, uint32_t* state) {
+  __shared__ unsigned int part[1024];
+  const int t = threadIdx.x;
+  unsigned int s = 0;
+  for (int b = 0; b < 32; ++b) s += hist32[t * 32 + b];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    const unsigned int rank = (kMedSample - 1) / 2;
+    unsigned int cum = 0, in_bin = 1;
+    int bin = 32767;
+    for (int q = 0; q < 1024; ++q) {
+      if (cum + part[q] > rank) {
+        for (int b = 0; b < 32; ++b) {
+          const unsigned int h = hist32[q * 32 + b];
+          if (cum + h > rank) { bin = q * 32 + b; in_bin = h; break; }
+          cum += h;
+        }
+        break;
+      }
+      cum += part[q];
+    }
+    const double frac = ((double)(rank - cum) + 0.5) / (double)in_bin;               // position inside the bin
+    const double centre = (double)bin * 65536.0 + frac * 65536.0;
+    const double mass_per_pattern = (double)in_bin / (double)kMedSample / 65536.0;   // local density estimate
+    double hw = 8.0 * (0.5 / sqrt((double)kMedSample)) / mass_per_pattern;
+    hw = fmin(fmax(hw, 4096.0), (double)(kMedWindowBins / 2));
+    double lo = centre - hw;
+    if (lo < 0.0) lo = 0.0;
+    state[0] = (uint32_t)lo;
+    state[1] = 0u;
+    state[2] = (uint32_t)(2.0 * hw);
+  }
+  __syncthreads();
+  for (int b = 0; b < 32; ++b) hist32[t * 32 + b] = 0u;
+}
+
+struct MedTcParams {
+  int N, Dp, T, row_begin;
+  const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *xn;
+  const uint32_t* state;             // [0] window start
+  unsigned long long* hist;          // [kMedWindowBins] window histogram, then [kMedWindowBins] = count below
+};
+
+enum { MB_A = 0, MB_XB_FULL = 1, MB_XB_EMPTY = 5, MB_S_FULL = 9, MB_S_EMPTY = 15 };
+
+__global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t a_bytes = kTcBM * p.Dp * 4, xb_half = kTcBN * p.Dp * 4, xb_stage = 2 * xb_half + kTcBN * 4;
+  const uint32_t off_a_hi = 0, off_a_lo = a_bytes, off_xb = 2 * a_bytes;
+  const uint32_t off_bars = (off_xb + kXbStages * xb_stage + 7) & ~7u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bars + 32 * 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i0 = p.row_begin + blockIdx.x * kTcBM;
+  const int T = p.T;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[MB_A], 1);
+    // an operand stage also carries |x_j|^2 for the consumers: it is recycled by their 4 warp arrivals
+    for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[MB_XB_FULL + s], 1); mbar_init(&bars[MB_XB_EMPTY + s], 4); }
+    for (int b = 0; b < kMedSBufs; ++b) { mbar_init(&bars[MB_S_FULL + b], 1); mbar_init(&bars[MB_S_EMPTY + b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const long long arow = (long long)(i0 / kTcBM) * kTcBM * p.Dp;
+      mbar_expect_tx(&bars[MB_A], 2 * a_bytes);
+      bulk_g2s(smem + off_a_hi, p.xa_hi + arow, a_bytes, &bars[MB_A]);
+      bulk_g2s(smem + off_a_lo, p.xa_lo + arow, a_bytes, &bars[MB_A]);
+      for (int j = 0; j < T; ++j) {
+        const int sx = j % kXbStages;
+        mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / kXbStages) & 1) ^ 1);
+        unsigned char* xb = smem + off_xb + sx * xb_stage;
+        mbar_expect_tx(&bars[MB_XB_FULL + sx], xb_stage);
+        bulk_g2s(xb, p.xb_hi + (long long)j * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
+        bulk_g2s(xb + xb_half, p.xb_lo + (long long)j * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
+        bulk_g2s(xb + 2 * xb_half, p.xn + (long long)j * kTcBN, kTcBN * 4, &bars[MB_XB_FULL + sx]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
+      const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;
+      const int ks1 = p.Dp / 8;
+      const uint64_t dA = make_desc(smem_u32(smem + off_a_hi), 128, sbo1), dX = make_desc(smem_u32(smem + off_xb), 128, sbo1);
+      const uint32_t hiA = (uint32_t)(dA >> 32);
+      const uint32_t loA_hi = (uint32_t)dA, loA_lo = loA_hi + (a_bytes >> 4), loX0 = (uint32_t)dX;
+      const uint32_t xb_stage16 = xb_stage >> 4, xb_half16 = xb_half >> 4;
+      mbar_wait(&bars[MB_A], 0);
+      for (int j = 0; j < T; ++j) {
+        const int b = j % kMedSBufs, sx = j % kXbStages;
+        mbar_wait(&bars[MB_XB_FULL + sx], (j / kXbStages) & 1);
+        mbar_wait(&bars[MB_S_EMPTY + b], ((j / kMedSBufs) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
+        const uint32_t tSb = tmem + b * kTcBN;
+#pragma unroll
+        for (int kk = 0; kk < 8; ++kk) {
+          if (kk < ks1) {
+            const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
+            const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+            mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+            mma_ss(tSb, ah, bl, idesc1, 1u);
+            mma_ss(tSb, al, bh, idesc1, 1u);
+          }
+        }
+        tc_commit(&bars[MB_S_FULL + b]);
+      }
+    }
+  } else if (warp >= 4) {
+    // three consumer warpgroups: tile j is handled by group j % 3, from S buffer j % 6
+    const int wg = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const float xn_i = p.xn[i0 + row];
+    const int jdiag = (i0 + row) / kTcBN;
+    const uint32_t win_lo = p.state[0], win_n = p.state[2];
+    unsigned int below = 0;
+    for (int j = wg; j < T; j += 3) {
+      const int b = j % kMedSBufs, sx = j % kXbStages;
+      const float* xnj = reinterpret_cast<const float*>(smem + off_xb + sx * xb_stage + 2 * xb_half);
+      mbar_wait(&bars[MB_S_FULL + b], (j / kMedSBufs) & 1);
+      tc_fence_after();
+      const int cdiag = (j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_base + b * kTcBN + half * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float s = __uint_as_float(r[c]);
+          float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
+          if (half * 32 + c == cdiag) d2 = 0.f;
+          const uint32_t bits = __float_as_uint(d2);
+          below += (bits < win_lo) ? 1u : 0u;
+          const uint32_t rel = bits - win_lo;
+          if (rel < win_n) atomicAdd(&p.hist[rel], 1ull);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars[MB_S_EMPTY + b]);
+        mbar_arrive(&bars[MB_XB_EMPTY + sx]);
+      }
+    }
+    below = __reduce_add_sync(0xffffffffu, below);
+    if (lane == 0 && below) atomicAdd(&p.hist[kMedWindowBins], (unsigned long long)below);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+// rank (N^2-1)/2 inside the window; state[1] = 1 and the median on success
+__global__ void __launch_bounds__(1024) med_window_select_kernel(unsigned long long* hist, uint32_t* state,
+                                                                 long long n_total, float* median_out) {
+  __shared__ unsigned long long part[1024];
+  constexpr int PER = kMedWindowBins / 1024;  // 192 bins per chunk
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int q = warp; q < 1024; q += 32) {   // one warp per chunk: coalesced reads
+    unsigned long long s = 0;
+    for (int b = lane; b < PER; b += 32) s += hist[q * PER + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) part[q] = s;
+  }
+  __syncthreads();
+  if (t == 0) {
+    const unsigned long long below = hist[kMedWindowBins];
+    const unsigned long long k = (unsigned long long)((n_total - 1) / 2);
+    unsigned long long total = 0;
+    for (int q = 0; q < 1024; ++q) total += part[q];
+    int ok = (k >= below) && (k - below < total);
+    if (ok) {
+      const unsigned long long rank = k - below;
+      unsigned long long cum = 0;
+      int ch = 1023;
+      for (int q = 0; q < 1024; ++q) {
+        if (cum + part[q] > rank) { ch = q; break; }
+        cum += part[q];
+      }
+      int bin = ch * PER + PER - 1;
+      for (int b = 0; b < PER; ++b) {
+        const unsigned long long h = hist[ch * PER + b];
+        if (cum + h > rank) { bin = ch * PER + b; break; }
+        cum += h;
+      }
+      const uint32_t bits = state[0] + (uint32_t)bin;
+      state[3] = bits;
+      if (median_out) *median_out = __uint_as_float(bits);
+    }
+    state[1] = ok ? 1u : 0u;
+  }
+  __syncthreads();
+  for (int b = t; b < kMedWindowBins; b += 1024) hist[b] = 0ull;  // leave the buffer clean for the fallback / next call
+  if (t == 0) hist[kMedWindowBins] = 0ull;
+}
+
+bool median_tc_supported(int N, int D) {
+  const int Dp = round_up(D, 8);
+  if (N % kTcBM || N < 1024 || Dp > 64) return false;
+  const size_t smem = (size_t)2 * kTcBM * Dp * 4 + (size_t)kXbStages * (2 * kTcBN * Dp * 4 + kTcBN * 4) + 32 * 8 + 64;
+  return smem <= 227 * 1024;
+}
+size_t median_tc_workspace(int N, int D) {
+  const size_t Dp = round_up(D, 8);
+  return sizeof(float) * ((size_t)N * (4 * Dp + 1) + 64) + sizeof(unsigned int) * 32768;
+}
+
+// sample + window (run by every rank on the same gathered X: no communication needed)
+int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t stream) {
+  const int N = a->N, D = a->D, Dp = round_up(D, 8);
+  float* ws = (float*)workspace;
+  float* xn = ws;    ws += (N + 63) / 64 * 64;
+  float* xa_hi = ws; ws += (size_t)N * Dp;
+  float* xa_lo = ws; ws += (size_t)N * Dp;
+  float* xb_hi = ws; ws += (size_t)N * Dp;
+  float* xb_lo = ws; ws += (size_t)N * Dp;
+  unsigned int* hist32 = (unsigned int*)ws;
+  DUST_CUDA_OK(cudaMemsetAsync(hist32, 0, sizeof(unsigned int) * 32768, stream));
+  {
+    DUST_TIMED("tc_prep_x_kernel", stream);
+    tc_prep_x_kernel<<<ceil_div((long long)N * Dp, 256), 256, 0, stream>>>(a->x, N, D, Dp, xa_hi, xa_lo, xb_hi, xb_lo, xn);
+  }
+  DUST_LAUNCH_OK("tc_prep_x_kernel");
+  {
+    DUST_TIMED("med_sample_kernel", stream);
+    med_sample_kernel<<<kMedSample / 256, 256, 0, stream>>>(a->x, xn, N, D, hist32);
+  }
+  DUST_LAUNCH_OK("med_sample_kernel");
+  {
+    DUST_TIMED("med_sample_select_kernel", stream);
+    med_sample_select_kernel<<<1, 1024, 0, stream>>>(hist32, a->selected + 4);
+  }
+  DUST_LAUNCH_OK("med_sample_select_kernel");
+  return DUST_OK;
+}
+
+int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t stream) {
+  const int N = a->N, D = a->D, Dp = round_up(D, 8);
+  float* ws = (float*)workspace;
+  float* xn = ws;    ws += (N + 63) / 64 * 64;
+  float* xa_hi = ws; ws += (size_t)N * Dp;
+  float* xa_lo = ws; ws += (size_t)N * Dp;
+  float* xb_hi = ws; ws += (size_t)N * Dp;
+  float* xb_lo = ws;
+  const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
+  MedTcParams p{N, Dp, N / kTcBN, r0, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
+  const size_t smem = (size_t)2 * kTcBM * Dp * 4 + (size_t)kXbStages * (2 * kTcBN * Dp * 4 + kTcBN * 4) + 32 * 8 + 64;
+  DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  {
+    DUST_TIMED("median_tc_kernel", stream);
+    median_tc_kernel<<<(r1 - r0) / kTcBM, kTcThreads, smem, stream>>>(p);
+  }
+  DUST_LAUNCH_OK("median_tc_kernel");
+  return DUST_OK;
+}
+
+int median_tc_select(const dust_median_args* a, float* median_out, cudaStream_t stream) {
+  {
+    DUST_TIMED("med_window_select_kernel", stream);
+    med_window_select_kernel<<<1, 1024, 0, stream>>>(a->hist, a->selected + 4, (long long)a->N * a->N, median_out);
+  }
+  DUST_LAUNCH_OK("med_window_select_kernel");
+  return DUST_OK;
 }
 
 // ---------------------------------------------------------------------------------------

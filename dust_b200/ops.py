@@ -125,27 +125,41 @@ def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, gamma_dev=None, per_dim=False,
 
 
 class MedianWorkspace:
-    """Device scratch for the radix select: 65536 u64 bins, 4 u32 of state, N row norms."""
+    """Device scratch for the median select: 3*65536+8 u64 bins, 8 u32 of state, N row norms, and
+    (when the tensor-core pass applies) the tiled operand images."""
 
-    def __init__(self, N, device):
-        self.hist = torch.zeros(65536, dtype=torch.int64, device=device)
-        self.selected = torch.zeros(4, dtype=torch.int32, device=device)
+    def __init__(self, N, D, device):
+        self.hist = torch.zeros(3 * 65536 + 8, dtype=torch.int64, device=device)
+        self.selected = torch.zeros(8, dtype=torch.int32, device=device)
         self.row_norms = torch.empty(N, dtype=torch.float32, device=device)
         self.median = torch.zeros(1, dtype=torch.float32, device=device)
+        lib = L.load()
+        self.fast = bool(lib.dust_median_fast_supported(N, D))
+        self.fast_bytes = lib.dust_median_fast_workspace_bytes(N, D) if self.fast else 0
+        self.fast_ws = _ws(self.fast_bytes, device) if self.fast else None
 
 
-def median_sq_dist(x, ws=None, rows=None, all_reduce=None):
+def median_sq_dist(x, ws=None, rows=None, all_reduce=None, allow_fast=True):
     """K4.  Exact lower median of the N^2 clamped squared distances of x [N,D] (device scalar).
     `rows` restricts the histogrammed row block; `all_reduce(hist)` (e.g. an NCCL sum) is called
-    between the histogram and the select of each pass when the rows are sharded over ranks."""
+    between the histogram and the select of each pass when the rows are sharded over ranks.
+    Qualifying shapes take the tensor-core window pass first; the two-pass radix select is always
+    enqueued behind it and does nothing when the fast path succeeded (no host synchronisation)."""
     L.require_cuda()
     N, D = x.shape
-    ws = ws or MedianWorkspace(N, x.device)
+    ws = ws or MedianWorkspace(N, D, x.device)
     a = L.MedianArgs()
     a.N, a.D = N, D
     a.row_begin, a.row_end = (0, N) if rows is None else rows
     a.x, a.hist, a.selected, a.row_norms = L.ptr(x), ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
     ws.hist.zero_()
+    ws.selected.zero_()
+    if allow_fast and ws.fast and a.row_begin % 128 == 0 and a.row_end % 128 == 0:
+        L.call("dust_median_fast_prepare", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream(), launches=4)
+        L.call("dust_median_fast_count", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream())
+        if all_reduce is not None:
+            all_reduce(ws.hist)
+        L.call("dust_median_fast_select", C.byref(a), ws.median.data_ptr(), L.stream())
     for p in (0, 1):
         L.call("dust_median_hist_pass", C.byref(a), p, L.stream(), launches=2 if p == 0 else 1)
         if all_reduce is not None:

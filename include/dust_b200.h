@@ -200,8 +200,10 @@ typedef struct dust_median_args {
   int32_t N, D;
   int32_t row_begin, row_end;
   const float* x;            /* [N, D]                                                 */
-  unsigned long long* hist;  /* [65536] device; pass kernels ADD into it (caller zeroes) */
-  uint32_t* selected;        /* [4] device: {hi16, rank_in_bin_lo, rank_in_bin_hi, bits} */
+  unsigned long long* hist;  /* [196616] device (65536 used by the two-pass select, 3*65536+1 by the
+                                fast path); kernels ADD into it (caller zeroes it once) */
+  uint32_t* selected;        /* [8] device, zeroed by the caller: {hi16, rank lo, rank hi, bits,
+                                window start, fast-path ok flag, -, bits (fast path)} */
   float* row_norms;          /* [N] device scratch: |x_i|^2, written by pass 0, read by pass 1 */
 } dust_median_args;
 
@@ -209,6 +211,19 @@ int dust_median_hist_pass(const dust_median_args* args, int32_t pass, void* stre
 /* pass 0: picks the hi-16 bin holding rank k=(N*N-1)/2 and the residual rank; pass 1: picks the
  * lo-16 value, writes the median's bit pattern to selected[3] and the float to *median_out. */
 int dust_median_select(const dust_median_args* args, int32_t pass, float* median_out, void* stream);
+
+/* Fast path of K4 on the tensor cores (N % 128 == 0, N >= 1024): a deterministic sample of 2^20 pairs
+ * picks a window of 3*65536 float bit patterns around the median (`prepare`, identical on every rank);
+ * ONE tcgen05 Gram pass over rows [row_begin,row_end) counts the values below the window in registers
+ * and histograms only those inside it (`count`; all-reduce `hist[0..196608]` when rows are sharded);
+ * `select` writes the median and sets selected[5] = 1, or leaves it 0 if the rank fell outside the
+ * window -- the two-pass entry points above then do the work (their kernels return at once when
+ * selected[5] is set, so they can always be enqueued behind the fast path without a host sync). */
+int dust_median_fast_supported(int32_t N, int32_t D);
+size_t dust_median_fast_workspace_bytes(int32_t N, int32_t D);
+int dust_median_fast_prepare(const dust_median_args* args, void* workspace, size_t workspace_bytes, void* stream);
+int dust_median_fast_count(const dust_median_args* args, void* workspace, size_t workspace_bytes, void* stream);
+int dust_median_fast_select(const dust_median_args* args, float* median_out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * K5  SVGD direction  phi = c1 * K S + c2 * (rowsum(K) o X - K X),  K_ij = exp(-gamma*|x_i-x_j|^2)
