@@ -30,8 +30,10 @@ constexpr int kTcBM = 128;      // rows per CTA (MMA M)
 constexpr int kTcBN = 64;       // columns per tile (GEMM1 N, GEMM2 K)
 constexpr int kTcThreads = 512;
 constexpr int kTcChunk = 32;    // column tiles accumulated in TMEM between two flushes
-constexpr int kXbStages = 4;
-constexpr int kVbStages = 2;
+constexpr int kXbStages = 3;
+constexpr int kVbStages = 3;
+constexpr int kMedXbStages = 6;   // operand ring of the median kernel (no V tiles there)
+constexpr int kXnStages = 16;     // |x_j|^2 ring of the median kernel
 constexpr uint32_t kSpinCap = 1u << 28;
 
 struct TcParams {
@@ -41,7 +43,7 @@ struct TcParams {
   const float* gamma_dev;
   float lr;
   float *phi, *x_out;
-  float* oacc;  // [grid][NV][128] running sums of the drained O chunks (column-major per CTA)
+  float* oacc;  // [grid][NV+2][128] running sums of the drained O chunks (column-major per CTA) + 2 row-sum halves
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -76,7 +78,8 @@ __global__ void tc_prep_x_kernel(const float* __restrict__ x, int N, int D, int 
   }
 }
 
-// V^T tiles: rows n2 in [0, NV) = [score dims | x dims | 1 | 0...], K = the 64 columns j of the tile
+// V^T tiles: rows n2 in [0, NV) = [score dims | x dims | 0...], K = the 64 columns j of the tile
+// (the row sums of K are accumulated exactly in the softmax warps' registers instead of a ones column)
 __global__ void tc_prep_v_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D, int NV,
                                  float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,7 +88,6 @@ __global__ void tc_prep_v_kernel(const float* __restrict__ x, const float* __res
   float v = 0.f;
   if (n2 < D) v = score[(long long)j * D + n2];
   else if (n2 < 2 * D) v = x[(long long)j * D + (n2 - D)];
-  else if (n2 == 2 * D) v = 1.f;
   const float hi = tf32_hi(v), lo = tf32_lo(v, hi);
   const long long idx = (long long)(j / kTcBN) * NV * kTcBN + core_index(n2, j % kTcBN, kTcBN);
   vb_hi[idx] = hi;
@@ -125,6 +127,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one elected lane of a fully converged warp (the compiler then keeps descriptors / addresses in
+// uniform registers and issues UTCHMMA directly, instead of an election loop per instruction)
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -188,6 +201,14 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -223,8 +244,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
   return s;
 }
 
-enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 11, BAR_S_FULL = 13, BAR_P_FULL = 15,
-       BAR_P_EMPTY = 17, BAR_O_FULL = 19, BAR_O_EMPTY = 21 };
+enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 13, BAR_S_FULL = 17, BAR_P_FULL = 19,
+       BAR_P_EMPTY = 21, BAR_O_FULL = 23, BAR_O_EMPTY = 25 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -242,7 +263,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     for (int s = 0; s < kVbStages; ++s) { mbar_init(&bars[BAR_VB_FULL + s], 1); mbar_init(&bars[BAR_VB_EMPTY + s], 1); }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars[BAR_S_FULL + b], 1);
-      mbar_init(&bars[BAR_P_FULL + b], 4);   // one arrival per softmax warp of the group
+      mbar_init(&bars[BAR_P_FULL + b], 8);   // one arrival per softmax warp (both groups work on every tile)
       mbar_init(&bars[BAR_P_EMPTY + b], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -295,7 +316,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ----------------------------------------
-    if (lane == 0) {
+    // the whole warp runs the loop converged (waits included); one elected lane issues
+    {
       const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
       const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV);
       const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;     // 8-row group stride of the X tiles
@@ -326,16 +348,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         const uint32_t tOb = tO + ob * p.NV;
         const uint32_t vh = loV0 + sv * vb_stage16, vl = vh + vb_half16;
         const uint32_t ph = tPhi + b * kTcBN, pl = tPlo + b * kTcBN;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < ks2; ++kk) {
-          const uint64_t bh = desc_lo_hi(vh + kk * 16, hiV), bl = desc_lo_hi(vl + kk * 16, hiV);
-          mma_ts(tOb, ph + kk * 8, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
-          mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
-          mma_ts(tOb, pl + kk * 8, bh, idesc2, 1u);
+          for (int kk = 0; kk < ks2; ++kk) {
+            const uint64_t bh = desc_lo_hi(vh + kk * 16, hiV), bl = desc_lo_hi(vl + kk * 16, hiV);
+            mma_ts(tOb, ph + kk * 8, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
+            mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
+            mma_ts(tOb, pl + kk * 8, bh, idesc2, 1u);
+          }
+          tc_commit(&bars[BAR_P_EMPTY + b]);
+          tc_commit(&bars[BAR_VB_EMPTY + sv]);
+          if (last) tc_commit(&bars[BAR_O_FULL + ob]);
         }
-        tc_commit(&bars[BAR_P_EMPTY + b]);
-        tc_commit(&bars[BAR_VB_EMPTY + sv]);
-        if (last) tc_commit(&bars[BAR_O_FULL + ob]);
+        __syncwarp();
       };
       for (int j = 0; j < T; ++j) {
         const int b = j & 1, sx = j % kXbStages;
@@ -343,25 +368,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         tc_fence_after();
         const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
         const uint32_t tSb = tS + b * kTcBN;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          if (kk < ks1) {
-            const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
-            const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
-            mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
-            mma_ss(tSb, ah, bl, idesc1, 1u);
-            mma_ss(tSb, al, bh, idesc1, 1u);
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < ks1) {
+              const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
+              const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+              mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+              mma_ss(tSb, ah, bl, idesc1, 1u);
+              mma_ss(tSb, al, bh, idesc1, 1u);
+            }
           }
+          tc_commit(&bars[BAR_S_FULL + b]);
+          tc_commit(&bars[BAR_XB_EMPTY + sx]);
         }
-        tc_commit(&bars[BAR_S_FULL + b]);
-        tc_commit(&bars[BAR_XB_EMPTY + sx]);
+        __syncwarp();
         if (j >= 1) gemm2(j - 1);
       }
       gemm2(T - 1);
     }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------ softmax warpgroups ---------------------------------
-    const int wg = (warp - 4) >> 2;          // 0: even tiles, 1: odd tiles
+    // Both warpgroups work on EVERY tile, one 32-column half each: with two S/P buffers the tile
+    // period is (softmax latency + MMA time) / 2, so the latency of this stage is what matters.
+    const int half = (warp - 4) >> 2;        // column half of the tile handled by this warpgroup
     const int q = warp & 3;                  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -370,43 +400,47 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     const float g2 = gamma * 1.4426950408889634f;  // exp(-g d2) = 2^(-g log2(e) d2)
     const float xn_i = p.xn[i0 + row];
     const int jdiag = (i0 + row) / kTcBN;
-    for (int j = wg; j < T; j += 2) {
-      const int b = wg, it = j >> 1, sv = j % kVbStages;
+    const int cdiag_all = (i0 + row) & (kTcBN - 1);
+    float ksum = 0.f;  // sum_j K_ij over this warpgroup's column halves (exact fp32, no ones column in V)
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1, it = j >> 1, sv = j % kVbStages;
       mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);   // |x_j|^2 of this tile
-      const float* xnj = reinterpret_cast<const float*>(smem + L.vb + sv * L.vb_stage_bytes + 2 * L.vb_half);
+      const float* xnj = reinterpret_cast<const float*>(smem + L.vb + sv * L.vb_stage_bytes + 2 * L.vb_half) + half * 32;
       mbar_wait(&bars[BAR_S_FULL + b], it & 1);
-      mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
       tc_fence_after();
+      uint32_t r[32], lo[32];
+      tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
+      tmem_wait_ld();
       // the tile that holds column i itself: d2_ii is exactly 0 (the 3xTF32 Gram entry only gives
       // |x_i|^2 to ~1e-6 relative, which a narrow kernel would amplify)
-      const int cdiag = (j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t r[32], lo[32];
-        tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
-        tmem_wait_ld();
-        if (cdiag >= half * 32 && cdiag < half * 32 + 32) {
+      if (j == jdiag && (cdiag_all >> 5) == half) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (half * 32 + c == cdiag) r[c] = __float_as_uint(0.5f * (xnj[half * 32 + c] + xn_i));  // => d2 = 0
-        }
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float s = __uint_as_float(r[c]);
-          const float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
-          const float kv = ex2_approx(-g2 * d2);
-          const float hi = tf32_hi(kv);
-          r[c] = __float_as_uint(hi);
-          lo[c] = __float_as_uint(tf32_lo(kv, hi));
-        }
-        tmem_st32(tPhi + lane_base + b * kTcBN + half * 32, r);
-        tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
+        for (int c = 0; c < 32; ++c)
+          if (c == (cdiag_all & 31)) r[c] = __float_as_uint(0.5f * (xnj[c] + xn_i));  // => d2 = 0
       }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        const float sv_ = __uint_as_float(r[c]);
+        const float d2 = fmaxf((xnj[c] - 2.0f * sv_) + xn_i, 0.f);
+        const float kv = ex2_approx(-g2 * d2);
+        ksum += kv;
+        const float hi = tf32_hi(kv);
+        r[c] = __float_as_uint(hi);
+        lo[c] = __float_as_uint(tf32_lo(kv, hi));
+      }
+      // P_hi overwrites the S columns it came from; GEMM2(j-2) must be done with P[b]
+      mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
+      tc_fence_after();
+      tmem_st32(tPhi + lane_base + b * kTcBN + half * 32, r);
+      tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
     }
+    p.oacc[(size_t)blockIdx.x * (p.NV + 2) * kTcBM + (size_t)(p.NV + half) * kTcBM + row] = ksum;
+    __threadfence_block();
+    asm volatile("bar.sync 1, 384;" ::: "memory");
   } else if (warp >= 12) {
     // ------------------------------ flush warpgroup + epilogue -------------------------
     const int q = warp & 3;
@@ -414,17 +448,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     // running sums live in a per-CTA global scratch, column-major ([NV][128]: a warp touches 128
     // contiguous bytes per column); only 32 columns are in registers at any time
-    float* og = p.oacc + (size_t)blockIdx.x * p.NV * kTcBM + row;
+    float* og = p.oacc + (size_t)blockIdx.x * (p.NV + 2) * kTcBM + row;
     for (int ch = 0; ch < n_chunks; ++ch) {
       const int ob = ch & 1;
       mbar_wait(&bars[BAR_O_FULL + ob], (ch >> 1) & 1);
       tc_fence_after();
-      for (int c0 = 0; c0 < p.NV; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tO + lane_base + ob * p.NV + c0, r);
+      for (int c0 = 0; c0 < p.NV; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tO + lane_base + ob * p.NV + c0, r);
         tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < 16; ++c) {
           float v = __uint_as_float(r[c]);
           if (ch > 0) v += og[(size_t)(c0 + c) * kTcBM];
           og[(size_t)(c0 + c) * kTcBM] = v;
@@ -437,8 +471,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     float c1 = p.c1, c2 = p.c2;
     if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
     const int gi = i0 + row;
-    // [0,D) = sum_j K s_j, [D,2D) = sum_j K x_j, [2D] = sum_j K
-    const float ksum = og[(size_t)(2 * p.D) * kTcBM];
+    // [0,D) = sum_j K s_j, [D,2D) = sum_j K x_j; the two column halves of sum_j K were written by
+    // the softmax warpgroups (same CTA; made visible by the barrier below)
+    asm volatile("bar.sync 1, 384;" ::: "memory");  // softmax warps 4-11 + flush warps 12-15
+    const float ksum = og[(size_t)p.NV * kTcBM] + og[(size_t)(p.NV + 1) * kTcBM];
     for (int d = 0; d < p.D; ++d) {
       const float xv = p.x[(long long)gi * p.D + d];
       const float ph = c1 * og[(size_t)d * kTcBM] + c2 * (ksum * xv - og[(size_t)(p.D + d) * kTcBM]);
@@ -532,23 +568,30 @@ struct MedTcParams {
   unsigned long long* hist;          // [kMedWindowBins] window histogram, then [kMedWindowBins] = count below
 };
 
-enum { MB_A = 0, MB_XB_FULL = 1, MB_XB_EMPTY = 5, MB_S_FULL = 9, MB_S_EMPTY = 15 };
+enum { MB_A = 0, MB_XB_FULL = 1, MB_XB_EMPTY = 7, MB_XN_FULL = 13, MB_XN_EMPTY = 29, MB_S_FULL = 45, MB_S_EMPTY = 51, MB_COUNT = 57 };
+
+__host__ __device__ inline size_t med_smem_bytes(int Dp) {
+  return (size_t)2 * kTcBM * Dp * 4 + (size_t)kMedXbStages * 2 * kTcBN * Dp * 4 + (size_t)kXnStages * kTcBN * 4 + 64 * 8 + 64;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t a_bytes = kTcBM * p.Dp * 4, xb_half = kTcBN * p.Dp * 4, xb_stage = 2 * xb_half + kTcBN * 4;
+  const uint32_t a_bytes = kTcBM * p.Dp * 4, xb_half = kTcBN * p.Dp * 4, xb_stage = 2 * xb_half;
   const uint32_t off_a_hi = 0, off_a_lo = a_bytes, off_xb = 2 * a_bytes;
-  const uint32_t off_bars = (off_xb + kXbStages * xb_stage + 7) & ~7u;
+  const uint32_t off_xn = off_xb + kMedXbStages * xb_stage;
+  const uint32_t off_bars = (off_xn + kXnStages * kTcBN * 4 + 7) & ~7u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bars + 32 * 8);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bars + 64 * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = p.row_begin + blockIdx.x * kTcBM;
   const int T = p.T;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[MB_A], 1);
-    // an operand stage also carries |x_j|^2 for the consumers: it is recycled by their 4 warp arrivals
-    for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[MB_XB_FULL + s], 1); mbar_init(&bars[MB_XB_EMPTY + s], 4); }
+    for (int s = 0; s < kMedXbStages; ++s) { mbar_init(&bars[MB_XB_FULL + s], 1); mbar_init(&bars[MB_XB_EMPTY + s], 1); }
+    // the |x_j|^2 slices ride in their own deep ring, recycled by the 4 consumer warps of a tile, so an
+    // operand stage is free as soon as its MMAs retire
+    for (int s = 0; s < kXnStages; ++s) { mbar_init(&bars[MB_XN_FULL + s], 1); mbar_init(&bars[MB_XN_EMPTY + s], 4); }
     for (int b = 0; b < kMedSBufs; ++b) { mbar_init(&bars[MB_S_FULL + b], 1); mbar_init(&bars[MB_S_EMPTY + b], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -569,17 +612,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       bulk_g2s(smem + off_a_hi, p.xa_hi + arow, a_bytes, &bars[MB_A]);
       bulk_g2s(smem + off_a_lo, p.xa_lo + arow, a_bytes, &bars[MB_A]);
       for (int j = 0; j < T; ++j) {
-        const int sx = j % kXbStages;
-        mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / kXbStages) & 1) ^ 1);
+        const int sx = j % kMedXbStages, sn = j % kXnStages;
+        mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / kMedXbStages) & 1) ^ 1);
         unsigned char* xb = smem + off_xb + sx * xb_stage;
         mbar_expect_tx(&bars[MB_XB_FULL + sx], xb_stage);
         bulk_g2s(xb, p.xb_hi + (long long)j * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
         bulk_g2s(xb + xb_half, p.xb_lo + (long long)j * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
-        bulk_g2s(xb + 2 * xb_half, p.xn + (long long)j * kTcBN, kTcBN * 4, &bars[MB_XB_FULL + sx]);
+        mbar_wait(&bars[MB_XN_EMPTY + sn], ((j / kXnStages) & 1) ^ 1);
+        mbar_expect_tx(&bars[MB_XN_FULL + sn], kTcBN * 4);
+        bulk_g2s(smem + off_xn + sn * kTcBN * 4, p.xn + (long long)j * kTcBN, kTcBN * 4, &bars[MB_XN_FULL + sn]);
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
       const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;
       const int ks1 = p.Dp / 8;
@@ -589,23 +634,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       const uint32_t xb_stage16 = xb_stage >> 4, xb_half16 = xb_half >> 4;
       mbar_wait(&bars[MB_A], 0);
       for (int j = 0; j < T; ++j) {
-        const int b = j % kMedSBufs, sx = j % kXbStages;
-        mbar_wait(&bars[MB_XB_FULL + sx], (j / kXbStages) & 1);
+        const int b = j % kMedSBufs, sx = j % kMedXbStages;
+        mbar_wait(&bars[MB_XB_FULL + sx], (j / kMedXbStages) & 1);
         mbar_wait(&bars[MB_S_EMPTY + b], ((j / kMedSBufs) & 1) ^ 1);
         tc_fence_after();
         const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
         const uint32_t tSb = tmem + b * kTcBN;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < 8; ++kk) {
-          if (kk < ks1) {
-            const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
-            const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
-            mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
-            mma_ss(tSb, ah, bl, idesc1, 1u);
-            mma_ss(tSb, al, bh, idesc1, 1u);
+          for (int kk = 0; kk < 8; ++kk) {
+            if (kk < ks1) {
+              const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
+              const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+              mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+              mma_ss(tSb, ah, bl, idesc1, 1u);
+              mma_ss(tSb, al, bh, idesc1, 1u);
+            }
           }
+          tc_commit(&bars[MB_S_FULL + b]);
+          tc_commit(&bars[MB_XB_EMPTY + sx]);
         }
-        tc_commit(&bars[MB_S_FULL + b]);
+        __syncwarp();
       }
     }
   } else if (warp >= 4) {
@@ -619,8 +668,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
     const uint32_t win_lo = p.state[0], win_n = p.state[2];
     unsigned int below = 0;
     for (int j = wg; j < T; j += 3) {
-      const int b = j % kMedSBufs, sx = j % kXbStages;
-      const float* xnj = reinterpret_cast<const float*>(smem + off_xb + sx * xb_stage + 2 * xb_half);
+      const int b = j % kMedSBufs, sn = j % kXnStages;
+      const float* xnj = reinterpret_cast<const float*>(smem + off_xn + sn * kTcBN * 4);
+      mbar_wait(&bars[MB_XN_FULL + sn], (j / kXnStages) & 1);
       mbar_wait(&bars[MB_S_FULL + b], (j / kMedSBufs) & 1);
       tc_fence_after();
       const int cdiag = (j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
@@ -629,22 +679,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
         uint32_t r[32];
         tmem_ld32(tmem + lane_base + b * kTcBN + half * 32, r);
         tmem_wait_ld();
+        if (cdiag >= half * 32 && cdiag < half * 32 + 32) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (half * 32 + c == cdiag) r[c] = __float_as_uint(0.5f * (xnj[half * 32 + c] + xn_i));  // => d2 = 0
+        }
+        // branch-free per element: a divergent `if (in window) atomicAdd` costs ~10 extra
+        // instructions of reconvergence bookkeeping per distance
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float s = __uint_as_float(r[c]);
-          float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
-          if (half * 32 + c == cdiag) d2 = 0.f;
-          const uint32_t bits = __float_as_uint(d2);
-          below += (bits < win_lo) ? 1u : 0u;
-          const uint32_t rel = bits - win_lo;
-          if (rel < win_n) atomicAdd(&p.hist[rel], 1ull);
+          const float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
+          const uint32_t rel = __float_as_uint(d2) - win_lo;   // wraps (top bit set) iff below the window
+          below += rel >> 31;
+          asm volatile(
+              "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
+              "setp.lt.u32 p, %1, %2;\n\t"
+              "mad.wide.u32 a, %1, 8, %0;\n\t"
+              "@p red.global.add.u64 [a], 1;\n\t}" ::"l"(p.hist), "r"(rel), "r"(win_n));
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&bars[MB_S_EMPTY + b]);
-        mbar_arrive(&bars[MB_XB_EMPTY + sx]);
+        mbar_arrive(&bars[MB_XN_EMPTY + sn]);
       }
     }
     below = __reduce_add_sync(0xffffffffu, below);
@@ -703,8 +762,7 @@ __global__ void __launch_bounds__(1024) med_window_select_kernel(unsigned long l
 bool median_tc_supported(int N, int D) {
   const int Dp = round_up(D, 8);
   if (N % kTcBM || N < 1024 || Dp > 64) return false;
-  const size_t smem = (size_t)2 * kTcBM * Dp * 4 + (size_t)kXbStages * (2 * kTcBN * Dp * 4 + kTcBN * 4) + 32 * 8 + 64;
-  return smem <= 227 * 1024;
+  return med_smem_bytes(Dp) <= 227 * 1024;
 }
 size_t median_tc_workspace(int N, int D) {
   const size_t Dp = round_up(D, 8);
@@ -750,7 +808,7 @@ int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t str
   float* xb_lo = ws;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
   MedTcParams p{N, Dp, N / kTcBN, r0, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
-  const size_t smem = (size_t)2 * kTcBM * Dp * 4 + (size_t)kXbStages * (2 * kTcBN * Dp * 4 + kTcBN * 4) + 32 * 8 + 64;
+  const size_t smem = med_smem_bytes(Dp);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     DUST_TIMED("median_tc_kernel", stream);
@@ -776,19 +834,19 @@ bool phi_tc_supported(const dust_phi_args* a) {
   if (a->B != 1 || a->per_dim) return false;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   if (a->N % kTcBM || r0 % kTcBM || r1 % kTcBM || a->N < 1024) return false;
-  const int Dp = round_up(a->D, 8), NV = round_up(2 * a->D + 1, 32);
+  const int Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
   if (2 * NV > 256 || Dp > 64) return false;
   return tc_smem_layout(Dp, NV).total <= 227 * 1024;
 }
 
 size_t phi_tc_workspace(const dust_phi_args* a) {
-  const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D + 1, 32);
+  const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
   const size_t rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
-  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64 + rows * NV);
+  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64 + rows * (NV + 2));
 }
 
 int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
-  const int N = a->N, D = a->D, Dp = round_up(D, 8), NV = round_up(2 * D + 1, 32);
+  const int N = a->N, D = a->D, Dp = round_up(D, 8), NV = round_up(2 * D, 16);
   DUST_REQUIRE(a->workspace && a->workspace_bytes >= phi_tc_workspace(a), DUST_ERR_WORKSPACE,
                "dust_svgd_phi: tensor-core path needs %zu bytes of workspace", phi_tc_workspace(a));
   float* ws = (float*)a->workspace;
