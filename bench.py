@@ -207,8 +207,7 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
 
     def step_resident():
-        ctl.optimize(state, eps)
-        ctl.forward()
+        ctl.control_step(state, eps)   # SVMPC.optimize + SVMPC.forward for every instance
 
     for _ in range(args.warmup):
         step_resident()
@@ -268,7 +267,7 @@ def run_ours(args, rank, world, local_rank):
     # 4 * B * (S*N*H*A noise read + S*N costs written + N*H*A theta read + ds state read)
     algo_bytes = 4.0 * B * (c["S"] * c["N"] * c["H"] * c["A"] + c["S"] * c["N"] + c["N"] * c["H"] * c["A"] + c["ds"])
     peak, peak_src = measured_peak()
-    dom = "svmpc_instance_kernel" if "svmpc_instance_kernel" in prof else "rollout_cost_kernel"
+    dom = "svmpc_instance_kernel" if "svmpc_instance_kernel" in prof else "rollout_cost_kernel"  # fused step kernel
     n_roll, ms_roll = prof.get(dom, (0, 0.0))
     roof = None
     if n_roll:

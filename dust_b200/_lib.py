@@ -44,6 +44,15 @@ class RolloutArgs(C.Structure):
     ]
 
 
+class SvmpcStepArgs(C.Structure):
+    _fields_ = [
+        ("rollout", RolloutArgs), ("do_forward", _i), ("roll_strategy", _i), ("weighted_prior", _i), ("prior_aliased", _i),
+        ("mu", _p), ("mix", _p), ("inv_var", _p), ("log_norm", _f), ("gamma", _f), ("c1", _f), ("c2", _f), ("lr", _f),
+        ("theta_out", _p), ("phi", _p), ("p_weights", _p), ("i_star", _p), ("a_seq", _p), ("theta_next", _p),
+        ("mix_next", _p),
+    ]
+
+
 class AdjointArgs(C.Structure):
     _fields_ = [
         ("model", C.POINTER(ModelDesc)), ("B", _i), ("N", _i), ("S", _i), ("P", _i), ("H", _i),
@@ -105,6 +114,7 @@ class MpfArgs(C.Structure):
 SYMBOLS = {
     "dust_rollout_workspace_bytes": (_sz, [C.POINTER(RolloutArgs)]),
     "dust_rollout_cost": (C.c_int, [C.POINTER(RolloutArgs), _p]),
+    "dust_svmpc_step": (C.c_int, [C.POINTER(SvmpcStepArgs), _p]),
     "dust_adjoint_workspace_bytes": (_sz, [C.POINTER(AdjointArgs)]),
     "dust_rollout_adjoint": (C.c_int, [C.POINTER(AdjointArgs), _p]),
     "dust_gmm_score": (C.c_int, [C.POINTER(GmmArgs), _p]),

@@ -52,6 +52,6 @@ class BatchedSVMPC:
 
     def control_step(self, state, eps=None, params=None):
         """optimize + forward for every instance; returns the actions to apply [B,A]."""
-        self.optimize(state, eps, params)
-        a_seq, _, _ = self.forward()
+        eps = self.draw_noise() if eps is None else eps
+        a_seq, _, _ = self.core.control_step(state, eps, params)
         return a_seq[:, 0]

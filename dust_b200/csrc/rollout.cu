@@ -7,6 +7,7 @@
 // dust/inference/likelihoods.py:81-135, dust/inference/svmpc.py:46-54.
 // Compiled with -fmad=false (see models.cuh).
 #include "models.cuh"
+#include "svgd_dev.cuh"
 
 namespace dust {
 
@@ -236,12 +237,31 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
 // ---------------------------------------------------------------------------------------
 constexpr int kFusedThreads = 256;
 
+// optional tail of the fused kernel: the rest of the SVGD step (and of SVMPC.forward) for the
+// instance this CTA owns -- prior score, phi, SGD update, weights / argmax / shift
+// (dust/inference/svmpc.py:38-95, 128-200).
+struct TailParams {
+  int enabled, do_forward, roll, weighted, aliased;
+  const float* mu;       // [B,N,D] prior centres (ignored when aliased: centres = particles)
+  const float* mix;      // [B,N] unnormalised mixture weights or null
+  const float* inv_var;  // [D]
+  float log_norm, gamma, c1, c2, lr;
+  float* theta_out;      // [B,N,D] updated particles (before the shift) or null
+  float* phi;            // [B,N,D] or null
+  float* p_weights;      // [B,N]
+  int* i_star;           // [B]
+  float* a_seq;          // [B,D]
+  float* theta_next;     // [B,N,D] shifted particles
+  float* mix_next;       // [B,N]
+};
+
 struct FusedOut {
   float* costs;     // [B,S,N] or null
   float* log_lik;   // [B,N] or null
   float* grad_lik;  // [B,N,HA] or null
   int likelihood;
   float alpha;
+  TailParams tail;
 };
 
 #ifndef DUST_FUSED_MINB
@@ -407,7 +427,19 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
     else ll = -o.alpha * (c_n / (float)k.S);                                                          // likelihoods.py:119
     o.log_lik[inst * N + tid] = ll;
   }
-  if (o.grad_lik) {
+  float* tail_s = reinterpret_cast<float*>(grid_s + ((MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits) ? ((k.m.grid_nx * k.m.grid_ny + 31) >> 5) : 0));
+  float* gl_s = tail_s;                    // [N][thst] likelihood gradient
+  float* sc_s = gl_s + N * thst;           // [N][thst] score = grad_lik + grad_prior
+  float* nw_s = sc_s + N * thst;           // [N][thst] updated particles
+  float* ll_s = nw_s + N * thst;           // [N] log-likelihood
+  float* lmix_s = ll_s + N;                // [N] log mixture weights
+  float* logw_s = lmix_s + N;              // [N]
+  float* logit_s = logw_s + N;             // [8 warps][N]
+  if (o.tail.enabled && tid < N) {
+    ll_s[tid] = (o.likelihood == DUST_LIK_EXP_UTILITY) ? (-o.alpha * m_n + logf(z_n)) - logf((float)k.S)
+                                                       : -o.alpha * (c_n / (float)k.S);
+  }
+  if (o.grad_lik || o.tail.enabled) {
     const float f = (tid < TN && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) / z_n : 0.f;
     float* crow = buf0 + tid * stride;  // the noise tiles are dead: reuse buffer 0 for the partial rows
 #pragma unroll
@@ -418,7 +450,121 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
       const int n2 = col / HA, c = col - n2 * HA;
       float sacc = 0.f;
       for (int g = 0; g < G; ++g) sacc += buf0[(g * N + n2) * stride + c];
-      o.grad_lik[inst * (long long)N * HA + col] = sacc;
+      if (o.grad_lik) o.grad_lik[inst * (long long)N * HA + col] = sacc;
+      if (o.tail.enabled) gl_s[n2 * thst + c] = sacc;
+    }
+  }
+  if (!o.tail.enabled) return;
+
+  // ------------------------------------------------------------------------------------
+  // tail: score = grad_lik + grad log GMM(theta); phi; theta += lr*phi; [weights, argmax, shift]
+  // one warp per particle; lanes over the flattened dimension (HA <= 32 here)
+  // ------------------------------------------------------------------------------------
+  const TailParams& t = o.tail;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = kFusedThreads >> 5;
+  const float* mu_g = t.mu ? t.mu + inst * (long long)N * HA : nullptr;
+  if (warp == 0) warp_log_mix(t.mix ? t.mix + inst * N : nullptr, N, lmix_s);
+  __syncthreads();
+  for (int n2 = warp; n2 < N; n2 += nwarps) {
+    float xr[kMaxDPerLane], sr[kMaxDPerLane];
+#pragma unroll
+    for (int q = 0; q < kMaxDPerLane; ++q) {
+      const int d = lane + 32 * q;
+      xr[q] = d < HA ? th_s[n2 * thst + d] : 0.f;
+    }
+    if (t.aliased) warp_gmm_point(xr, th_s, lmix_s, t.inv_var, N, HA, logit_s + warp * N, sr, thst);
+    else warp_gmm_point(xr, mu_g, lmix_s, t.inv_var, N, HA, logit_s + warp * N, sr, HA);
+#pragma unroll
+    for (int q = 0; q < kMaxDPerLane; ++q) {
+      const int d = lane + 32 * q;
+      if (d < HA) sc_s[n2 * thst + d] = gl_s[n2 * thst + d] + sr[q];
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < N; i += nwarps) {
+    const int d = lane;  // HA <= 32
+    const float xi = d < HA ? th_s[i * thst + d] : 0.f;
+    float accp = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float xj = d < HA ? th_s[j * thst + d] : 0.f;
+      const float df = xi - xj;
+      const float d2 = warp_sum(df * df);
+      const float kij = expf(-t.gamma * d2);
+      const float sj = d < HA ? sc_s[j * thst + d] : 0.f;
+      accp += kij * (t.c1 * sj + t.c2 * df);
+    }
+    if (d < HA) {
+      const float nv = xi + t.lr * accp;
+      nw_s[i * thst + d] = nv;
+      const long long oidx = (inst * N + i) * (long long)HA + d;
+      if (t.phi) t.phi[oidx] = accp;
+      if (t.theta_out) t.theta_out[oidx] = nv;
+    }
+  }
+  if (!t.do_forward) return;
+  __syncthreads();
+  // weights from the PRE-update costs and the prior evaluated at the POST-update particles
+  for (int n2 = warp; n2 < N; n2 += nwarps) {
+    float xr[kMaxDPerLane];
+#pragma unroll
+    for (int q = 0; q < kMaxDPerLane; ++q) {
+      const int d = lane + 32 * q;
+      xr[q] = d < HA ? nw_s[n2 * thst + d] : 0.f;
+    }
+    float lp;
+    if (t.aliased) lp = warp_gmm_point(xr, nw_s, lmix_s, t.inv_var, N, HA, logit_s + warp * N, nullptr, thst);
+    else lp = warp_gmm_point(xr, mu_g, lmix_s, t.inv_var, N, HA, logit_s + warp * N, nullptr, HA);
+    if (lane == 0) logw_s[n2] = ll_s[n2] + (lp + t.log_norm);
+  }
+  __syncthreads();
+  __shared__ int s_istar;
+  if (warp == 0) {
+    float mx = -INFINITY;
+    for (int n2 = lane; n2 < N; n2 += 32) mx = fmaxf(mx, logw_s[n2]);
+    mx = warp_max(mx);
+    float z = 0.f;
+    for (int n2 = lane; n2 < N; n2 += 32) z += expf(logw_s[n2] - mx);
+    z = warp_sum(z);
+    const float lse = mx + logf(z);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int n2 = lane; n2 < N; n2 += 32) {
+      const float pw = expf(logw_s[n2] - lse);
+      t.p_weights[inst * N + n2] = pw;
+      if (t.mix_next) t.mix_next[inst * N + n2] = t.weighted ? pw : 1.0f;
+      if (pw > best) { best = pw; bi = n2; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      s_istar = bi;
+      if (t.i_star) t.i_star[inst] = bi;
+    }
+  }
+  __syncthreads();
+  const int is = s_istar;
+  if (t.a_seq)
+    for (int d = tid; d < HA; d += kFusedThreads) t.a_seq[inst * HA + d] = nw_s[is * thst + d];
+  if (t.theta_next) {
+    const int shift_lim = (k.H - 1) * A;
+    for (int e = tid; e < N * HA; e += kFusedThreads) {
+      const int n2 = e / HA, d = e - n2 * HA;
+      float v;
+      if (d < shift_lim) {
+        v = nw_s[n2 * thst + d + A];
+      } else if (t.roll == DUST_ROLL_REPEAT) {
+        v = nw_s[n2 * thst + d];
+      } else {
+        const int a = d - shift_lim;
+        float sm = 0.f;
+        for (int h = 0; h < k.H; ++h) sm += nw_s[n2 * thst + h * A + a];
+        v = sm / (float)k.H;
+      }
+      t.theta_next[inst * (long long)N * HA + e] = v;
     }
   }
 }
@@ -592,11 +738,11 @@ struct RolloutPlan {
   size_t off_part, off_likw, off_mppiw, off_costs, total;
 };
 
-static RolloutPlan plan_rollout(const dust_rollout_args* a) {
+static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = false) {
   RolloutPlan pl{};
   const long long SN = (long long)a->S * a->N;
   const int P = a->params ? a->P : 1;
-  int pc = choose_param_chunks((long long)a->B * SN, P);
+  int pc = single_chunk ? 1 : choose_param_chunks((long long)a->B * SN, P);
   const int chunk = (P + pc - 1) / pc;
   pc = (P + chunk - 1) / chunk;
   pl.PC = pc;
@@ -625,7 +771,7 @@ extern "C" size_t dust_rollout_workspace_bytes(const dust_rollout_args* a) {
   return plan_rollout(a).total;
 }
 
-extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
+static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_rollout_cost: args is NULL");
   int rc = validate_model(a->model);
@@ -645,7 +791,7 @@ extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
   const long long SN = (long long)a->S * a->N;
   DUST_REQUIRE(SN < (1ll << 30), DUST_ERR_UNSUPPORTED, "dust_rollout_cost: S*N too large");
 
-  const RolloutPlan pl = plan_rollout(a);
+  const RolloutPlan pl = plan_rollout(a, tail != nullptr);
   DUST_REQUIRE(pl.total == 0 || (a->workspace && a->workspace_bytes >= pl.total), DUST_ERR_WORKSPACE,
                "dust_rollout_cost: workspace needs %zu bytes, got %zu", pl.total, a->workspace_bytes);
   char* ws = (char*)a->workspace;
@@ -669,10 +815,15 @@ extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
   // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
   const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
   const bool fused_ok = fused_outputs_only && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
-                        (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik);
+                        (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
+  DUST_REQUIRE(fused_ok || !tail, DUST_ERR_UNSUPPORTED,
+               "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");
   if (fused_ok) {
-    const size_t fsmem = sizeof(float) * ((size_t)2 * kFusedThreads * stride + (size_t)a->N * ((k.HA + 3) & ~3) + 3 * kFusedThreads) + grid_bytes;
-    FusedOut o{a->costs, a->log_lik, a->grad_lik, a->likelihood, a->alpha};
+    const int thst_h = (k.HA + 3) & ~3;
+    const size_t fsmem = sizeof(float) * ((size_t)2 * kFusedThreads * stride + (size_t)a->N * thst_h + 3 * kFusedThreads +
+                                          (size_t)3 * a->N * thst_h + (size_t)(3 + 8) * a->N) + grid_bytes;
+    FusedOut o{a->costs, a->log_lik, a->grad_lik, a->likelihood, a->alpha, TailParams{}};
+    if (tail) o.tail = *tail;
     k.cost_out = nullptr;
 #define DUST_FUSED(MODEL, ACC)                                                                                              \
   do {                                                                                                                      \
@@ -730,4 +881,26 @@ extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) {
     DUST_LAUNCH_OK("weighted_colsum_kernel");
   }
   return DUST_OK;
+}
+
+extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) { return rollout_cost_impl(a, nullptr, stream_); }
+
+extern "C" int dust_svmpc_step(const dust_svmpc_step_args* s, void* stream_) {
+  DUST_REQUIRE(s != nullptr, DUST_ERR_INVALID_ARG, "dust_svmpc_step: args is NULL");
+  const dust_rollout_args* a = &s->rollout;
+  DUST_REQUIRE(a->theta && a->sigma && s->inv_var, DUST_ERR_INVALID_ARG, "dust_svmpc_step: theta, sigma and inv_var are required");
+  DUST_REQUIRE(s->prior_aliased || s->mu, DUST_ERR_INVALID_ARG, "dust_svmpc_step: mu is required unless the prior aliases theta");
+  DUST_REQUIRE(s->theta_out || s->do_forward, DUST_ERR_INVALID_ARG, "dust_svmpc_step: no output requested");
+  DUST_REQUIRE(!s->do_forward || (s->p_weights && s->theta_next), DUST_ERR_INVALID_ARG,
+               "dust_svmpc_step: p_weights and theta_next are required with do_forward");
+  DUST_REQUIRE(s->roll_strategy == DUST_ROLL_REPEAT || s->roll_strategy == DUST_ROLL_MEAN, DUST_ERR_INVALID_ARG,
+               "dust_svmpc_step: invalid roll strategy %d", s->roll_strategy);
+  DUST_REQUIRE(s->theta_next != a->theta && s->theta_out != a->theta, DUST_ERR_INVALID_ARG,
+               "dust_svmpc_step: outputs must not alias theta");
+  TailParams t;
+  t.enabled = 1; t.do_forward = s->do_forward; t.roll = s->roll_strategy; t.weighted = s->weighted_prior;
+  t.aliased = s->prior_aliased; t.mu = s->mu; t.mix = s->mix; t.inv_var = s->inv_var; t.log_norm = s->log_norm;
+  t.gamma = s->gamma; t.c1 = s->c1; t.c2 = s->c2; t.lr = s->lr; t.theta_out = s->theta_out; t.phi = s->phi;
+  t.p_weights = s->p_weights; t.i_star = s->i_star; t.a_seq = s->a_seq; t.theta_next = s->theta_next; t.mix_next = s->mix_next;
+  return rollout_cost_impl(a, &t, stream_);
 }

@@ -92,6 +92,30 @@ class SvmpcCore:
                          lik_weights=out.get("lik_weights"))
         return self.last
 
+    def control_step(self, state0, eps, params=None, tiling=L.PARAMS_BLOCKED, want_phi=False):
+        """optimize_step + forward_step.  One kernel launch when the shape qualifies for the fused
+        instance kernel (B >= 74, H*A <= 32, analytic gradient, fixed-lengthscale kernel), else the
+        staged sequence.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])"""
+        if self.kernel == "gpytorch" and self.grad == "analytic" and getattr(self, "_fused_ok", True):
+            ell2 = self.lengthscale ** 2
+            want = ("costs", "log_lik", "theta_out") + (("phi",) if want_phi else ())
+            try:
+                out = ops.svmpc_step(self.spec, state0, eps, self.theta, self.sigma, self.mu, self.mix, self.inv_var,
+                                     self.log_norm, 1.0 / (2.0 * ell2), 1.0 / self.N, -1.0 / ell2, self.lr, params=params,
+                                     param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
+                                     temperature=self.temperature, aliased=self.aliased, do_forward=True,
+                                     roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior, want=want)
+            except NotImplementedError:
+                self._fused_ok = False
+            else:
+                self.last = dict(costs=out["costs"], log_lik=out["log_lik"], theta1=out["theta_out"], phi=out.get("phi"),
+                                 states=None, lik_weights=None)
+                self.theta = out["theta_next"]
+                self.mu, self.mix, self.aliased = self.theta, out["mix_next"], True
+                return out["a_seq"], out["p_weights"], out["i_star"]
+        self.optimize_step(state0, eps, params, tiling)
+        return self.forward_step()
+
     def forward_step(self, log_lik=None):
         """Weights, best particle, shift, prior refresh.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])."""
         log_lik = self.last["log_lik"] if log_lik is None else log_lik

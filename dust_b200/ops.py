@@ -59,6 +59,48 @@ def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param
     return out
 
 
+def svmpc_step(spec, state0, noise, theta, sigma, mu, mix, inv_var, log_norm, gamma, c1, c2, lr, params=None,
+               param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0, temperature=1.0,
+               aliased=False, do_forward=True, roll_strategy=L.ROLL_REPEAT, weighted_prior=False,
+               want=("costs", "log_lik", "theta_out")):
+    """The whole SVGD step (+ SVMPC.forward) in ONE launch (dust_svmpc_step).  Raises
+    NotImplementedError when the shape does not qualify (the caller then uses the staged path).
+    `want` subset of {costs, log_lik, grad_lik, theta_out, phi}."""
+    L.require_cuda()
+    dev = noise.device
+    B, S, N, H, A = noise.shape
+    P = 1 if params is None else params.shape[1]
+    f32 = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)  # noqa: E731
+    out = {}
+    for k, shape in (("costs", (B, S, N)), ("log_lik", (B, N)), ("grad_lik", (B, N, H, A)), ("theta_out", (B, N, H, A)),
+                     ("phi", (B, N, H, A))):
+        if k in want:
+            out[k] = f32(*shape)
+    s = L.SvmpcStepArgs()
+    a = s.rollout
+    a.model = C.pointer(spec.desc)
+    a.B, a.N, a.S, a.P, a.H = B, N, S, P, H
+    a.param_tiling, a.likelihood = param_tiling, likelihood
+    a.state0, a.theta, a.noise, a.sigma, a.params = L.ptr(state0), L.ptr(theta), L.ptr(noise), L.ptr(sigma), L.ptr(params)
+    a.alpha, a.temperature = float(alpha), float(temperature)
+    a.costs, a.log_lik, a.grad_lik = L.ptr(out.get("costs")), L.ptr(out.get("log_lik")), L.ptr(out.get("grad_lik"))
+    s.do_forward, s.roll_strategy = int(bool(do_forward)), int(roll_strategy)
+    s.weighted_prior, s.prior_aliased = int(bool(weighted_prior)), int(bool(aliased))
+    s.mu, s.mix, s.inv_var, s.log_norm = L.ptr(None if aliased else mu), L.ptr(mix), L.ptr(inv_var), float(log_norm)
+    s.gamma, s.c1, s.c2, s.lr = float(gamma), float(c1), float(c2), float(lr)
+    s.theta_out, s.phi = L.ptr(out.get("theta_out")), L.ptr(out.get("phi"))
+    if do_forward:
+        out.update(p_weights=f32(B, N), i_star=torch.empty((B,), dtype=torch.int32, device=dev), a_seq=f32(B, H, A),
+                   theta_next=f32(B, N, H, A), mix_next=f32(B, N))
+        s.p_weights, s.i_star, s.a_seq = L.ptr(out["p_weights"]), L.ptr(out["i_star"]), L.ptr(out["a_seq"])
+        s.theta_next, s.mix_next = L.ptr(out["theta_next"]), L.ptr(out["mix_next"])
+    nbytes = L.load().dust_rollout_workspace_bytes(C.byref(a))
+    ws = _ws(nbytes, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    L.call("dust_svmpc_step", C.byref(s), L.stream(), launches=1)
+    return out
+
+
 def rollout_adjoint(spec, state0, noise, lik_weights, theta=None, sigma=None, params=None,
                     param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0):
     """K2.  Returns grad_theta [B,N,H,A] = d sum_n log_l_n / d theta (pathwise)."""

@@ -134,6 +134,34 @@ typedef struct dust_rollout_args {
 size_t dust_rollout_workspace_bytes(const dust_rollout_args* args);
 int dust_rollout_cost(const dust_rollout_args* args, void* stream);
 
+/* The whole SVGD step of SVMPC (and optionally SVMPC.forward) for B instances in ONE launch:
+ * K1 with its fused per-instance kernel, then -- in the tail of the same CTA -- the GMM prior score,
+ * phi (gamma, c1, c2 as for dust_svgd_phi), the SGD update theta_out = theta + lr*phi and, with
+ * do_forward, the weights / argmax / shift / mixture refresh of dust_svmpc_forward.
+ * replaces: SVMPC.step + SVMPC.forward  dust/inference/svmpc.py:87-95, 172-200 (one call each).
+ * `rollout` carries the K1 inputs (theta, noise, sigma, state0, params ...) and the optional K1
+ * outputs costs / log_lik / grad_lik; its weights / MPPI / states outputs must be NULL.
+ * Returns DUST_ERR_UNSUPPORTED when the shape does not qualify (B < 74, H*A > 32, parameter loop
+ * split over chunks): call the staged entry points instead. */
+typedef struct dust_svmpc_step_args {
+  dust_rollout_args rollout;
+  int32_t do_forward, roll_strategy, weighted_prior, prior_aliased;
+  const float* mu;           /* [B, N, H, A] prior centres (unused when prior_aliased)  */
+  const float* mix;          /* [B, N] or NULL                                          */
+  const float* inv_var;      /* [H*A]                                                   */
+  float log_norm;
+  float gamma, c1, c2, lr;
+  float* theta_out;          /* [B, N, H, A] updated particles before the shift, or NULL */
+  float* phi;                /* [B, N, H, A] or NULL                                    */
+  float* p_weights;          /* [B, N]        (do_forward)                              */
+  int32_t* i_star;           /* [B]                                                     */
+  float* a_seq;              /* [B, H, A]                                               */
+  float* theta_next;         /* [B, N, H, A]                                            */
+  float* mix_next;           /* [B, N]                                                  */
+} dust_svmpc_step_args;
+
+int dust_svmpc_step(const dust_svmpc_step_args* args, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * K2  pathwise likelihood gradient by a hand-derived reverse-time adjoint
  * replaces: torch.autograd.grad(log_l.sum(), x) through rsample -> rollout -> cost,

@@ -207,3 +207,51 @@ def test_batched_svmpc_equals_per_instance_runs():
         ref = O.svmpc_optimize(O.Model("pendulum"), st, state[b].cpu().double(), eps[b].cpu().double(),
                                torch.tensor([2.0]).double(), None, False, 1.0, 2.0, kernel="rbf")
         assert rel_max(theta1[b].cpu(), ref["theta1"]) <= RTOL_PHI
+
+
+@pytest.mark.parametrize("kind,N,S,H,wp", [("pendulum", 8, 64, 20, False), ("pendulum", 3, 40, 30, True), ("particle", 5, 33, 12, True)])
+def test_one_launch_control_step_matches_staged_path(kind, N, S, H, wp):
+    """dust_svmpc_step (everything in the fused kernel's tail) == optimize_step + forward_step,
+    first with a free-standing prior, then with the prior aliasing the particles."""
+    from dust_b200 import _lib as L
+    from dust_b200.inference.core import SvmpcCore
+    from dust_b200.models.particle import Particle
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    torch.manual_seed(N * 7 + S)
+    B = 90
+    if kind == "pendulum":
+        spec = PendulumModel(uncertain_params=("length", "mass")).device_spec(inst_cost, term_cost, "cuda")
+        ds, A, dp = 2, 1, 2
+    else:
+        m = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+        spec = m.device_spec(m.default_inst_cost, m.default_term_cost, "cuda")
+        ds, A, dp = 4, 2, 1
+    dev = "cuda"
+    state = torch.randn(B, ds, device=dev) * (torch.tensor([6.0, 6.0, 1.0, 1.0], device=dev) if kind == "particle" else 1.5)
+    theta, mu = torch.randn(B, N, H, A, device=dev) * 2, torch.randn(B, N, H, A, device=dev)
+    mix = torch.rand(B, N, device=dev) + 0.1
+    params = torch.rand(B, 2, dp, device=dev) + 0.8
+    mk = lambda: SvmpcCore(spec, theta.clone(), mu.clone(), mix.clone(), torch.full((A,), 4.0), torch.full((A,), 2.0),  # noqa: E731
+                           alpha=1.0, lr=0.5, kernel="gpytorch", weighted_prior=wp)
+    fused, staged = mk(), mk()
+    lib = L.load()
+    for step in range(2):  # step 0: free-standing prior; step 1: aliased prior
+        eps = torch.randn(B, S, N, H, A, device=dev)
+        lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
+        a1, p1, i1 = fused.control_step(state, eps, params, want_phi=True)
+        prof = L.profiler_report(); lib.dust_profiler_enable(0)
+        assert list(prof) == ["svmpc_instance_kernel"] and prof["svmpc_instance_kernel"][0] == 1, prof
+        staged.optimize_step(state, eps, params)
+        phi2 = staged.last["phi"]
+        a2, p2, i2 = staged.forward_step()
+        assert torch.equal(fused.last["costs"], staged.last["costs"])
+        assert rel_max(fused.last["phi"].cpu(), phi2.cpu()) <= 1e-4
+        assert rel_max(fused.theta.cpu(), staged.theta.cpu()) <= 1e-5
+        assert torch.equal(i1, i2)
+        assert float((p1 - p2).abs().max()) <= 1e-4
+        assert rel_max(a1.cpu(), a2.cpu()) <= 1e-5
+        assert rel_max(fused.mix.cpu(), staged.mix.cpu()) <= 1e-4
+        # identical inputs for the next step (the two paths round differently at the 1e-7 level)
+        staged.theta = fused.theta.clone()
+        staged.mu, staged.mix = staged.theta, fused.mix.clone()

@@ -36,7 +36,7 @@ def test_struct_layouts_match_the_header():
 
     from dust_b200 import _lib
 
-    names = {"dust_model_desc": _lib.ModelDesc, "dust_rollout_args": _lib.RolloutArgs, "dust_adjoint_args": _lib.AdjointArgs,
+    names = {"dust_model_desc": _lib.ModelDesc, "dust_rollout_args": _lib.RolloutArgs, "dust_svmpc_step_args": _lib.SvmpcStepArgs, "dust_adjoint_args": _lib.AdjointArgs,
              "dust_gmm_args": _lib.GmmArgs, "dust_median_args": _lib.MedianArgs, "dust_phi_args": _lib.PhiArgs,
              "dust_svmpc_forward_args": _lib.SvmpcForwardArgs, "dust_disco_step_args": _lib.DiscoStepArgs,
              "dust_mpf_args": _lib.MpfArgs}
