@@ -466,19 +466,12 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   if (warp == 0) warp_log_mix(t.mix ? t.mix + inst * N : nullptr, N, lmix_s);
   __syncthreads();
   for (int n2 = warp; n2 < N; n2 += nwarps) {
-    float xr[kMaxDPerLane], sr[kMaxDPerLane];
-#pragma unroll
-    for (int q = 0; q < kMaxDPerLane; ++q) {
-      const int d = lane + 32 * q;
-      xr[q] = d < HA ? th_s[n2 * thst + d] : 0.f;
-    }
-    if (t.aliased) warp_gmm_point(xr, th_s, lmix_s, t.inv_var, N, HA, logit_s + warp * N, sr, thst);
-    else warp_gmm_point(xr, mu_g, lmix_s, t.inv_var, N, HA, logit_s + warp * N, sr, HA);
-#pragma unroll
-    for (int q = 0; q < kMaxDPerLane; ++q) {
-      const int d = lane + 32 * q;
-      if (d < HA) sc_s[n2 * thst + d] = gl_s[n2 * thst + d] + sr[q];
-    }
+    // HA <= 32 on this path: one lane slot per dimension
+    float xr[1], sr[1];
+    xr[0] = lane < HA ? th_s[n2 * thst + lane] : 0.f;
+    if (t.aliased) warp_gmm_point<1>(xr, th_s, lmix_s, t.inv_var, N, HA, logit_s + warp * N, sr, thst);
+    else warp_gmm_point<1>(xr, mu_g, lmix_s, t.inv_var, N, HA, logit_s + warp * N, sr, HA);
+    if (lane < HA) sc_s[n2 * thst + lane] = gl_s[n2 * thst + lane] + sr[0];
   }
   __syncthreads();
   for (int i = warp; i < N; i += nwarps) {
@@ -505,15 +498,11 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   __syncthreads();
   // weights from the PRE-update costs and the prior evaluated at the POST-update particles
   for (int n2 = warp; n2 < N; n2 += nwarps) {
-    float xr[kMaxDPerLane];
-#pragma unroll
-    for (int q = 0; q < kMaxDPerLane; ++q) {
-      const int d = lane + 32 * q;
-      xr[q] = d < HA ? nw_s[n2 * thst + d] : 0.f;
-    }
+    float xr[1];
+    xr[0] = lane < HA ? nw_s[n2 * thst + lane] : 0.f;
     float lp;
-    if (t.aliased) lp = warp_gmm_point(xr, nw_s, lmix_s, t.inv_var, N, HA, logit_s + warp * N, nullptr, thst);
-    else lp = warp_gmm_point(xr, mu_g, lmix_s, t.inv_var, N, HA, logit_s + warp * N, nullptr, HA);
+    if (t.aliased) lp = warp_gmm_point<1>(xr, nw_s, lmix_s, t.inv_var, N, HA, logit_s + warp * N, nullptr, thst);
+    else lp = warp_gmm_point<1>(xr, mu_g, lmix_s, t.inv_var, N, HA, logit_s + warp * N, nullptr, HA);
     if (lane == 0) logw_s[n2] = ll_s[n2] + (lp + t.log_norm);
   }
   __syncthreads();

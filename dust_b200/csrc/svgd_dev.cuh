@@ -42,14 +42,15 @@ __device__ __forceinline__ void warp_log_mix(const float* __restrict__ mix, int 
 
 // log GMM(x; mu, logmix, inv_var) and (optionally) its score for ONE point handled by a warp.
 // xr: this lane's slice of x (d = lane + 32 q).  logits: per-warp scratch [K] in shared memory.
+template <int QMAX = kMaxDPerLane>
 __device__ __forceinline__ float warp_gmm_point(const float* xr, const float* __restrict__ mu, const float* logmix,
                                 const float* __restrict__ inv_var, int K, int D, float* logits, float* score_r,
                                                 int mu_stride = 0) {
   if (mu_stride == 0) mu_stride = D;
   const int lane = threadIdx.x & 31;
-  float iv[kMaxDPerLane];
+  float iv[QMAX];
 #pragma unroll
-  for (int q = 0; q < kMaxDPerLane; ++q) {
+  for (int q = 0; q < QMAX; ++q) {
     const int d = lane + 32 * q;
     iv[q] = d < D ? inv_var[d] : 0.f;
   }
@@ -57,7 +58,7 @@ __device__ __forceinline__ float warp_gmm_point(const float* xr, const float* __
   for (int k = 0; k < K; ++k) {
     float part = 0.f;
 #pragma unroll
-    for (int q = 0; q < kMaxDPerLane; ++q) {
+    for (int q = 0; q < QMAX; ++q) {
       const int d = lane + 32 * q;
       if (d < D) {
         const float df = xr[q] - mu[(long long)k * mu_stride + d];
@@ -71,15 +72,15 @@ __device__ __forceinline__ float warp_gmm_point(const float* xr, const float* __
   }
   __syncwarp();
   float z = 0.f;
-  float acc[kMaxDPerLane];
+  float acc[QMAX];
 #pragma unroll
-  for (int q = 0; q < kMaxDPerLane; ++q) acc[q] = 0.f;
+  for (int q = 0; q < QMAX; ++q) acc[q] = 0.f;
   for (int k = 0; k < K; ++k) {
     const float e = expf(logits[k] - mx);
     z += e;
     if (score_r) {
 #pragma unroll
-      for (int q = 0; q < kMaxDPerLane; ++q) {
+      for (int q = 0; q < QMAX; ++q) {
         const int d = lane + 32 * q;
         if (d < D) acc[q] += e * (mu[(long long)k * mu_stride + d] - xr[q]);
       }
@@ -88,7 +89,7 @@ __device__ __forceinline__ float warp_gmm_point(const float* xr, const float* __
   if (score_r) {
     const float invz = 1.f / z;
 #pragma unroll
-    for (int q = 0; q < kMaxDPerLane; ++q) score_r[q] = acc[q] * invz * iv[q];
+    for (int q = 0; q < QMAX; ++q) score_r[q] = acc[q] * invz * iv[q];
   }
   __syncwarp();
   return mx + logf(z);
