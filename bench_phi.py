@@ -4,8 +4,8 @@ direction with the exact median bandwidth.  Reports time, algorithmic TFLOP/s (6
 4 N^2 d for the two median passes) and, under torchrun, the row-block sharded version
 (all-gather of [X|score] + histogram all-reduce over NCCL).
 
-  python bench_phi.py --n 65536 --steps 5
-  python -m torch.distributed.run --nproc-per-node 8 bench_phi.py --n 65536
+  python bench_phi.py --particles 65536 --steps 5
+  python -m torch.distributed.run --nproc-per-node 8 bench_phi.py --particles 65536
 """
 import argparse
 import json
@@ -19,8 +19,8 @@ import torch  # noqa: E402
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=65536)
-    ap.add_argument("--d", type=int, default=40)
+    ap.add_argument("--particles", type=int, default=65536)
+    ap.add_argument("--dim", type=int, default=40)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="compare a row sample against the float64 oracle")
@@ -39,7 +39,7 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    N, D = args.n, args.d
+    N, D = args.particles, args.dim
     g = torch.Generator(device=dev).manual_seed(0)
     X = torch.randn(N, D, device=dev, generator=g)
     S = -X
@@ -87,13 +87,36 @@ def main():
     full()
     prof = L.profiler_report()
     lib.dust_profiler_enable(0)
+    # roofline denominator: measured cuBLAS TF32 GEMM throughput on this GPU (8192^3, best of 5)
+    tf32_peak = None
+    if rank == 0:
+        torch.backends.cuda.matmul.allow_tf32 = True
+        A_ = torch.randn(8192, 8192, device=dev); B_ = torch.randn(8192, 8192, device=dev)
+        for _ in range(2):
+            A_ @ B_
+        best = 1e9
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); A_ @ B_; e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        del A_, B_
     out = None
     if rank == 0:
         fl_phi, fl_med = 6.0 * N * N * D, 4.0 * N * N * D
+        Dp, NV = (D + 7) // 8 * 8, (2 * D + 15) // 16 * 16
+        issued = 3 * 2.0 * N * N * (Dp + NV) / world   # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
+        t_phi_kernel = prof.get("phi_tc_kernel", (0, 0.0))[1]
         out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "ms_phi_with_median": ms_full, "ms_phi": ms_phi,
                "algorithmic_tflops_phi": fl_phi / (ms_phi * 1e-3) / 1e12,
                "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12, "bandwidth": bw,
-               "kernels_ms": {k: v[1] for k, v in prof.items()}}
+               "kernels_ms": {k: v[1] for k, v in prof.items()},
+               "roofline": None if not t_phi_kernel else {
+                   "kernel": "phi_tc_kernel", "bound": "tensor", "unit": "TFLOP/s",
+                   "achieved": issued / (t_phi_kernel * 1e-3) / 1e12, "peak": tf32_peak,
+                   "frac": issued / (t_phi_kernel * 1e-3) / 1e12 / tf32_peak,
+                   "peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this run (torch.matmul, allow_tf32)",
+                   "note": "achieved counts the TF32 MMA FLOPs actually issued (3 per algorithmic product)"}}
     if args.check:
         from oracle import dust_oracle as O
         idx = torch.arange(b, e, max(1, (e - b) // 64), device=dev)[:64]

@@ -38,6 +38,7 @@ constexpr uint32_t kSpinCap = 1u << 28;
 
 struct TcParams {
   int N, D, Dp, NV, T, row_begin;
+  int ksplit;  // CTAs per row tile: CTA (rt, h) handles column tiles [h*T/ksplit, (h+1)*T/ksplit)
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *vb_hi, *vb_lo, *xn, *x;
   float gamma, c1, c2;
   const float* gamma_dev;
@@ -253,9 +254,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rt = blockIdx.x;                 // row tile handled by this CTA
+  const int rt = blockIdx.x / p.ksplit;      // row tile handled by this CTA
   const int i0 = p.row_begin + rt * kTcBM;   // first global row
-  const int T = p.T;
+  const int T = p.T / p.ksplit;              // column tiles handled by this CTA ...
+  const int jbase = (blockIdx.x % p.ksplit) * T;  // ... starting at this one
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[BAR_A], 1);
@@ -297,8 +299,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         mbar_wait(&bars[BAR_XB_EMPTY + sx], ((j / kXbStages) & 1) ^ 1);
         unsigned char* xb = smem + L.xb + sx * L.xb_stage_bytes;
         mbar_expect_tx(&bars[BAR_XB_FULL + sx], L.xb_stage_bytes);
-        bulk_g2s(xb, p.xb_hi + (long long)j * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
-        bulk_g2s(xb + L.xb_half, p.xb_lo + (long long)j * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+        bulk_g2s(xb, p.xb_hi + (long long)(jbase + j) * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+        bulk_g2s(xb + L.xb_half, p.xb_lo + (long long)(jbase + j) * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
       }
     }
   } else if (warp == 3) {
@@ -309,9 +311,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         mbar_wait(&bars[BAR_VB_EMPTY + sv], ((j / kVbStages) & 1) ^ 1);
         unsigned char* vb = smem + L.vb + sv * L.vb_stage_bytes;
         mbar_expect_tx(&bars[BAR_VB_FULL + sv], L.vb_stage_bytes);
-        bulk_g2s(vb, p.vb_hi + (long long)j * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
-        bulk_g2s(vb + L.vb_half, p.vb_lo + (long long)j * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
-        bulk_g2s(vb + 2 * L.vb_half, p.xn + (long long)j * kTcBN, kTcBN * 4, &bars[BAR_VB_FULL + sv]);
+        bulk_g2s(vb, p.vb_hi + (long long)(jbase + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
+        bulk_g2s(vb + L.vb_half, p.vb_lo + (long long)(jbase + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
+        bulk_g2s(vb + 2 * L.vb_half, p.xn + (long long)(jbase + j) * kTcBN, kTcBN * 4, &bars[BAR_VB_FULL + sv]);
       }
     }
   } else if (warp == 1) {
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       tmem_wait_ld();
       // the tile that holds column i itself: d2_ii is exactly 0 (the 3xTF32 Gram entry only gives
       // |x_i|^2 to ~1e-6 relative, which a narrow kernel would amplify)
-      if (j == jdiag && (cdiag_all >> 5) == half) {
+      if (jbase + j == jdiag && (cdiag_all >> 5) == half) {
 #pragma unroll
         for (int c = 0; c < 32; ++c)
           if (c == (cdiag_all & 31)) r[c] = __float_as_uint(0.5f * (xnj[c] + xn_i));  // => d2 = 0
@@ -439,8 +441,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
     }
     p.oacc[(size_t)blockIdx.x * (p.NV + 2) * kTcBM + (size_t)(p.NV + half) * kTcBM + row] = ksum;
-    __threadfence_block();
-    asm volatile("bar.sync 1, 384;" ::: "memory");
   } else if (warp >= 12) {
     // ------------------------------ flush warpgroup + epilogue -------------------------
     const int q = warp & 3;
@@ -468,25 +468,48 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_O_EMPTY + ob]);
     }
-    float c1 = p.c1, c2 = p.c2;
-    if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
-    const int gi = i0 + row;
-    // [0,D) = sum_j K s_j, [D,2D) = sum_j K x_j; the two column halves of sum_j K were written by
-    // the softmax warpgroups (same CTA; made visible by the barrier below)
-    asm volatile("bar.sync 1, 384;" ::: "memory");  // softmax warps 4-11 + flush warps 12-15
-    const float ksum = og[(size_t)p.NV * kTcBM] + og[(size_t)(p.NV + 1) * kTcBM];
-    for (int d = 0; d < p.D; ++d) {
-      const float xv = p.x[(long long)gi * p.D + d];
-      const float ph = c1 * og[(size_t)d * kTcBM] + c2 * (ksum * xv - og[(size_t)(p.D + d) * kTcBM]);
-      if (p.phi) p.phi[(long long)gi * p.D + d] = ph;
-      if (p.x_out) p.x_out[(long long)gi * p.D + d] = xv + p.lr * ph;
-    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
   }
+}
+
+// combine the per-CTA partial sums of one row tile and form phi (coalesced: thread <-> row)
+__global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) {
+  const int rt = blockIdx.x, row = threadIdx.x;
+  const int gi = p.row_begin + rt * kTcBM + row;
+  float c1 = p.c1, c2 = p.c2;
+  if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
+  const size_t cta_stride = (size_t)(p.NV + 2) * kTcBM;
+  const float* og = p.oacc + (size_t)rt * p.ksplit * cta_stride + row;
+  float ksum = 0.f;
+  for (int h = 0; h < p.ksplit; ++h) ksum += og[h * cta_stride + (size_t)p.NV * kTcBM] + og[h * cta_stride + (size_t)(p.NV + 1) * kTcBM];
+  for (int d = 0; d < p.D; ++d) {
+    float ks = 0.f, kx = 0.f;  // sum_j K s_j, sum_j K x_j
+    for (int h = 0; h < p.ksplit; ++h) {
+      ks += og[h * cta_stride + (size_t)d * kTcBM];
+      kx += og[h * cta_stride + (size_t)(p.D + d) * kTcBM];
+    }
+    const float xv = p.x[(long long)gi * p.D + d];
+    const float ph = c1 * ks + c2 * (ksum * xv - kx);
+    if (p.phi) p.phi[(long long)gi * p.D + d] = ph;
+    if (p.x_out) p.x_out[(long long)gi * p.D + d] = xv + p.lr * ph;
+  }
+}
+
+// CTAs per row tile so that the grid fills whole waves of the 148 SMs
+static int choose_ksplit(int row_tiles, int T) {
+  int best = 1;
+  double best_cost = 1e30;
+  for (int ks = 1; ks <= 8; ++ks) {
+    if (T % ks) continue;
+    const int waves = ceil_div((long long)row_tiles * ks, kNumSMs);
+    const double cost = (double)waves / ks + 0.004 * ks;  // tiny per-CTA overhead term
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
+  }
+  return best;
 }
 
 // =======================================================================================
@@ -562,7 +585,7 @@ __global__ void med_sample_select_kernel(unsigned int* hist32, uint32_t* state) 
 }
 
 struct MedTcParams {
-  int N, Dp, T, row_begin;
+  int N, Dp, T, row_begin, ksplit;
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *xn;
   const uint32_t* state;             // [0] window start
   unsigned long long* hist;          // [kMedWindowBins] window histogram, then [kMedWindowBins] = count below
@@ -583,8 +606,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bars + 64 * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int i0 = p.row_begin + blockIdx.x * kTcBM;
-  const int T = p.T;
+  const int i0 = p.row_begin + (blockIdx.x / p.ksplit) * kTcBM;
+  const int T = p.T / p.ksplit;
+  const int jbase = (blockIdx.x % p.ksplit) * T;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[MB_A], 1);
@@ -616,11 +640,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
         mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / kMedXbStages) & 1) ^ 1);
         unsigned char* xb = smem + off_xb + sx * xb_stage;
         mbar_expect_tx(&bars[MB_XB_FULL + sx], xb_stage);
-        bulk_g2s(xb, p.xb_hi + (long long)j * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
-        bulk_g2s(xb + xb_half, p.xb_lo + (long long)j * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
+        bulk_g2s(xb, p.xb_hi + (long long)(jbase + j) * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
+        bulk_g2s(xb + xb_half, p.xb_lo + (long long)(jbase + j) * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
         mbar_wait(&bars[MB_XN_EMPTY + sn], ((j / kXnStages) & 1) ^ 1);
         mbar_expect_tx(&bars[MB_XN_FULL + sn], kTcBN * 4);
-        bulk_g2s(smem + off_xn + sn * kTcBN * 4, p.xn + (long long)j * kTcBN, kTcBN * 4, &bars[MB_XN_FULL + sn]);
+        bulk_g2s(smem + off_xn + sn * kTcBN * 4, p.xn + (long long)(jbase + j) * kTcBN, kTcBN * 4, &bars[MB_XN_FULL + sn]);
       }
     }
   } else if (warp == 1) {
@@ -673,7 +697,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       mbar_wait(&bars[MB_XN_FULL + sn], (j / kXnStages) & 1);
       mbar_wait(&bars[MB_S_FULL + b], (j / kMedSBufs) & 1);
       tc_fence_after();
-      const int cdiag = (j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
+      const int cdiag = (jbase + j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
@@ -807,12 +831,14 @@ int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t str
   float* xb_hi = ws; ws += (size_t)N * Dp;
   float* xb_lo = ws;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
-  MedTcParams p{N, Dp, N / kTcBN, r0, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
+  const int row_tiles = (r1 - r0) / kTcBM;
+  const int ksplit = choose_ksplit(row_tiles, N / kTcBN);
+  MedTcParams p{N, Dp, N / kTcBN, r0, ksplit, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
   const size_t smem = med_smem_bytes(Dp);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     DUST_TIMED("median_tc_kernel", stream);
-    median_tc_kernel<<<(r1 - r0) / kTcBM, kTcThreads, smem, stream>>>(p);
+    median_tc_kernel<<<row_tiles * ksplit, kTcThreads, smem, stream>>>(p);
   }
   DUST_LAUNCH_OK("median_tc_kernel");
   return DUST_OK;
@@ -842,7 +868,7 @@ bool phi_tc_supported(const dust_phi_args* a) {
 size_t phi_tc_workspace(const dust_phi_args* a) {
   const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
   const size_t rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
-  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64 + rows * (NV + 2));
+  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64 + rows * 8 * (NV + 2));  // up to 8 column splits
 }
 
 int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
@@ -875,11 +901,18 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out; p.oacc = oacc;
   const TcSmem L = tc_smem_layout(Dp, NV);
   DUST_CUDA_OK(cudaFuncSetAttribute(phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const int row_tiles = (r1 - r0) / kTcBM;
+  p.ksplit = choose_ksplit(row_tiles, p.T);
   {
     DUST_TIMED("phi_tc_kernel", stream);
-    phi_tc_kernel<<<(r1 - r0) / kTcBM, kTcThreads, L.total, stream>>>(p);
+    phi_tc_kernel<<<row_tiles * p.ksplit, kTcThreads, L.total, stream>>>(p);
   }
   DUST_LAUNCH_OK("phi_tc_kernel");
+  {
+    DUST_TIMED("phi_tc_finish_kernel", stream);
+    phi_tc_finish_kernel<<<row_tiles, kTcBM, 0, stream>>>(p);
+  }
+  DUST_LAUNCH_OK("phi_tc_finish_kernel");
   return DUST_OK;
 }
 
