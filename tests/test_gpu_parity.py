@@ -466,11 +466,11 @@ def test_large_phi_properties(env):
     bw_ref, med_ref = O.bw_median(X)
     assert abs(float(med[0]) - float(med_ref)) <= 4e-6 * float(med_ref)
     assert abs(bw - float(bw_ref)) <= 1e-5 * float(bw_ref)
-    # rows split in blocks (what each rank computes) == the full result: bit for bit when the
-    # blocks are 128-aligned (same tensor-core tiles), to rounding otherwise (SIMT tiles)
+    # rows split in blocks (what each rank computes) == the full result, to rounding: the number of
+    # column splits per row tile depends on how many tiles a call covers, so partial sums group differently
     a = ops.svgd_phi(x, s, gamma_dev=coef, rows=(0, 1536))["phi"]
     b = ops.svgd_phi(x, s, gamma_dev=coef, rows=(1536, N))["phi"]
-    assert torch.equal(torch.cat([a[:, :1536], b[:, 1536:]], 1), out["phi"])
+    assert rel_max(torch.cat([a[:, :1536], b[:, 1536:]], 1).cpu(), out["phi"].cpu()) <= 2e-6
     a = ops.svgd_phi(x, s, gamma_dev=coef, rows=(0, 1500))["phi"]
     b = ops.svgd_phi(x, s, gamma_dev=coef, rows=(1500, N))["phi"]
     assert rel_max(torch.cat([a[:, :1500], b[:, 1500:]], 1).cpu(), ref) <= RTOL_PHI
@@ -502,10 +502,10 @@ def test_tensor_core_phi_vs_float64_and_simt(env, N, D, gamma):
     assert rel_max(tc["phi"][0].cpu(), ref) <= RTOL_PHI
     assert rel_max(simt, ref) <= RTOL_PHI
     assert rel_max(tc["x_out"][0].cpu(), X.double() + 0.5 * ref) <= RTOL_PHI
-    # row blocks (what each rank computes) reproduce the full result bit for bit
+    # row blocks (what each rank computes) reproduce the full result to rounding
     a = ops.svgd_phi(x, s, gamma=gamma, c1=c1, c2=c2, rows=(0, 384))["phi"]
     b = ops.svgd_phi(x, s, gamma=gamma, c1=c1, c2=c2, rows=(384, N))["phi"]
-    assert torch.equal(torch.cat([a[:, :384], b[:, 384:]], 1), tc["phi"])
+    assert rel_max(torch.cat([a[:, :384], b[:, 384:]], 1).cpu(), tc["phi"].cpu()) <= 2e-6
 
 
 def test_tensor_core_path_is_taken(env):
