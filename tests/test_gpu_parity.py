@@ -1,6 +1,8 @@
 """Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden vectors
 generated from the unmodified reference.  Tolerances are BASELINE.json's: costs / rollouts
 <= 1e-5 relative (float32), phi and updated particles <= 1e-4 relative, indices exact."""
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -446,6 +448,49 @@ def test_median_is_exact_rank_statistic(env):
         k = (N * N - 1) // 2
         lo, hi = float(srt[max(k - 3, 0)]), float(srt[min(k + 3, N * N - 1)])
         assert lo - 1e-4 * abs(lo) - 1e-5 <= med <= hi + 1e-4 * abs(hi) + 1e-5
+
+
+def _median_cases():
+    g = torch.Generator().manual_seed(23)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    cauchy = torch.tan(math.pi * (torch.rand(4096, 16, generator=g) - 0.5))
+    return {
+        "normal_2048": rn(2048, 40),
+        "normal_8192": rn(8192, 40),
+        "anisotropic": rn(4096, 40) * (torch.arange(1, 41).float() / 10),
+        "low_dim": rn(4096, 8),
+        "heavy_tailed": cauchy,
+        "two_clusters": torch.cat([rn(2048, 24), rn(2048, 24) + 30.0]),
+        "all_identical": torch.full((2048, 40), 0.3),
+        "mostly_duplicates": torch.cat([torch.zeros(3072, 16), rn(1024, 16)]),
+    }
+
+
+@pytest.mark.parametrize("case", list(_median_cases()))
+def test_tensor_core_median_vs_radix_select(env, case):
+    """The sampled-window tensor-core pass and the two-pass radix select are both exact rank
+    selections, over distances formed in a different order (3xTF32 Gram vs fp32 FMA chain): they
+    agree to distance rounding.  Degenerate inputs (zero median, ties wider than the window) must
+    either succeed or hand over on the device; either way the value returned is the radix one."""
+    from dust_b200 import ops
+
+    x = cu(_median_cases()[case])
+    N, D = x.shape
+    ws = ops.MedianWorkspace(N, D, x.device)
+    assert ws.fast, "shape should qualify for the tensor-core pass"
+    fast = float(ops.median_sq_dist(x, ws=ws)[0])
+    took_fast = int(ws.selected[5])
+    robust = float(ops.median_sq_dist(x, allow_fast=False)[0])
+    assert abs(fast - robust) <= 4e-6 * abs(robust) + 1e-12, (case, fast, robust, took_fast)
+    if case.startswith("normal") or case in ("anisotropic", "low_dim"):
+        assert took_fast == 1, "well-behaved cloud should not need the fallback"
+    # float64 sort of the same points brackets both
+    X = _median_cases()[case].double()
+    if N <= 4096:
+        srt = O.sq_dists_addmm(X, X).reshape(-1).sort().values
+        k = (N * N - 1) // 2
+        lo, hi = float(srt[k - 8]), float(srt[k + 8])
+        assert lo - 1e-5 * abs(lo) - 1e-6 <= fast <= hi + 1e-5 * abs(hi) + 1e-6
 
 
 def test_large_phi_properties(env):
