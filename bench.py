@@ -96,7 +96,7 @@ def probe_threads():
 def best_cpu(n_instances, target_seconds=15.0):
     th, probe = probe_threads()
     if n_instances <= 0:
-        n_instances = max(64, int(probe[th] * target_seconds))
+        n_instances = min(4096, max(64, int(probe[th] * target_seconds)))
     v, dt = cpu_instance_steps(n_instances, 1, th)
     return v, th, dt, n_instances, probe
 
@@ -107,7 +107,7 @@ def run_reference(args, rank):
     ncpu = os.cpu_count() or 1
     # thread sweep on a small probe, then K timed "steps", each a bounded sample of n instances
     th, probe = probe_threads()
-    n = args.cpu_sample if args.cpu_sample > 0 else max(16, int(probe[th] * 60.0 / max(1, args.steps + args.warmup)))
+    n = args.cpu_sample if args.cpu_sample > 0 else min(args.instances * args.gpus, max(16, int(probe[th] * 60.0 / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
         cpu_instance_steps(max(2, n // 8), 1, th)
     t0 = time.perf_counter()
