@@ -1,9 +1,22 @@
 // Device-side forward models and costs.  Every translation unit that includes this file is
 // compiled with -fmad=false: the expressions below follow the reference's float32 op order
 // one rounding at a time, so the particle trajectories are bit-identical
-// to the CPU reference and the pendulum ones differ only by sinf/cosf ulps.
+// to the CPU reference.  The pendulum cannot be (its sinf/cosf are not the reference's libm): its
+// step and cost use explicit fmaf, staying within a few 1e-7 relative of the reference.
 #pragma once
 #include "common.cuh"
+
+// DUST_PEND_OPT: which of the pendulum instruction-count reductions are compiled in (bit mask;
+// the variants exist so that their effect on parity can be measured one by one)
+//   1 two-part reduction + mantissa-trick rounding   2 Horner cosine   4 contracted dynamics
+//   8 unweighted running cost sums                   16 sigma*eps score rows (rollout.cu)
+// Measured on B200 with profiles/variant_check.py: every mask leaves the cost
+// error at 2.5e-7 relative; 8 is left OUT because it abandons the reference's summation order
+// (step cost rounded, then added), and with it the soft-min weights of the hardest fixture moved
+// from 7e-5 to 2.3e-4 of the reference (weights are exp(-cost differences), one cost ulp = 5e-4).
+#ifndef DUST_PEND_OPT
+#define DUST_PEND_OPT 23
+#endif
 
 namespace dust {
 
@@ -33,8 +46,8 @@ __device__ __forceinline__ PendulumCoef pendulum_coef_default(const ModelParams&
   return c;
 }
 
-// sin and cos of one argument with a single Cody-Waite reduction (pi/2 in three parts, exact for
-// |x| < 100) and the Cephes single-precision minimax polynomials on [-pi/4, pi/4]; max abs error
+// sin and cos of one argument with a single Cody-Waite reduction (pi/2 in two parts, |x| <= 64)
+// and the Cephes single-precision minimax polynomials on [-pi/4, pi/4]; max abs error
 // 9.2e-8 (~1.5 ulp), the same class as sinf/cosf.  Larger arguments take the library path.
 // (the library path is kept out of line: inlined, its Payne-Hanek code would bloat the rollout
 // loop past the instruction cache)
@@ -48,20 +61,37 @@ __device__ __forceinline__ void fast_sincosf(float x, float& s, float& c) {
     slow_sincosf(x, &s, &c);
     return;
   }
+#if DUST_PEND_OPT & 1
+  // k = rint(x * 2/pi) by the 1.5*2^23 trick: the integer sits in the low mantissa bits of t, no
+  // FRND / F2I.  |k| <= 41, so the reduction needs only two parts of pi/2: x - k*hi is exact (both
+  // are multiples of 2^-24 and the difference is below 1), the low part is carried to 2^-53.
+  const float t = fmaf(x, 0.636619772f, 12582912.0f);
+  const float kf = t - 12582912.0f;
+  const uint32_t q = __float_as_uint(t);
+  float r = fmaf(kf, -1.57079637050628662109375f, x);
+  r = fmaf(kf, 4.37113900018624283e-8f, r);
+#else
   const float kf = rintf(x * 0.636619772f);
-  const int q = (int)kf;
+  const uint32_t q = (uint32_t)(int)kf;
   float r = fmaf(kf, -1.5703125f, x);
   r = fmaf(kf, -4.837512969970703125e-4f, r);
   r = fmaf(kf, -7.54978995489188216e-8f, r);
+#endif
   const float r2 = r * r;
   float ps = fmaf(fmaf(-1.9515295891e-4f, r2, 8.3321608736e-3f), r2, -1.6666654611e-1f);
   ps = fmaf(ps, r2 * r, r);
   float pc = fmaf(fmaf(2.443315711809948e-5f, r2, -1.388731625493765e-3f), r2, 4.166664568298827e-2f);
+#if DUST_PEND_OPT & 2
+  pc = fmaf(fmaf(pc, r2, -0.5f), r2, 1.0f);
+#else
   pc = fmaf(pc, r2 * r2, fmaf(-0.5f, r2, 1.0f));
-  const float sv = (q & 1) ? pc : ps;
-  const float cv = (q & 1) ? ps : pc;
-  s = (q & 2) ? -sv : sv;
-  c = ((q + 1) & 2) ? -cv : cv;
+#endif
+  const bool odd = (q & 1u) != 0u;
+  const float sv = odd ? pc : ps;
+  const float cv = odd ? ps : pc;
+  // sign bits: sin is negative in quadrants 2,3 (bit 1 of q), cos in quadrants 1,2 (bit 1 of q+1)
+  s = __uint_as_float(__float_as_uint(sv) ^ ((q << 30) & 0x80000000u));
+  c = __uint_as_float(__float_as_uint(cv) ^ (((q << 30) + 0x40000000u) & 0x80000000u));
 }
 
 // one step; returns the pre-clamp angular speed through *pre (the adjoint needs the mask).
@@ -79,14 +109,25 @@ __device__ __forceinline__ void pendulum_step(const ModelParams& m, const Pendul
   if (cos_th) {
     const float bb = y - th;
     const float err = (th - (y - bb)) + (kPiF - bb);
-    const float e = 8.742278e-8f - err;
-    *cos_th = -fmaf(e, s, cy);
+    const float ne = err - 8.742278e-8f;  // -e
+    *cos_th = fmaf(ne, s, -cy);
   }
+  // the trig above is already a few 1e-8 from the reference's libm: the products below are
+  // contracted (one rounding instead of two), a deviation of the same order and a shorter loop
+#if DUST_PEND_OPT & 4
+  const float acc = fmaf(c.c1, s, c.c2 * u);
+  const float pre = fmaf(m.dt, acc, om);
+#else
   const float acc = c.c1 * s + c.c2 * u;
-  float pre = om + m.dt * acc;
+  const float pre = om + m.dt * acc;
+#endif
   if (pre_out) *pre_out = pre;
   om = fminf(fmaxf(pre, -m.max_speed_pend), m.max_speed_pend);
+#if DUST_PEND_OPT & 4
+  th = fmaf(om, m.dt, th);
+#else
   th = th + om * m.dt;
+#endif
 }
 
 // demo/pendulum_example.py:21-28
@@ -95,6 +136,26 @@ __device__ __forceinline__ float pendulum_cost_from_cos(const ModelParams& m, fl
   t = t * t;
   return m.w_angle * t + m.w_speed * (om * om);
 }
+// running cost of a trajectory: the two quadratic terms are summed unweighted (one fused
+// multiply-add each per step) and the weights applied once, sum_t [w_a (cos th_t - 1)^2 + w_s om_t^2]
+#if DUST_PEND_OPT & 8
+struct PendulumCostSum {
+  float ang = 0.f, spd = 0.f;
+  __device__ __forceinline__ void add(const ModelParams&, float cos_th, float om) {
+    const float t = cos_th - 1.0f;
+    ang = fmaf(t, t, ang);
+    spd = fmaf(om, om, spd);
+  }
+  __device__ __forceinline__ float total(const ModelParams& m) const { return fmaf(m.w_angle, ang, m.w_speed * spd); }
+};
+#else
+// the reference's own order: every step cost rounded, then added to the running sum
+struct PendulumCostSum {
+  float sum = 0.f;
+  __device__ __forceinline__ void add(const ModelParams& m, float cos_th, float om) { sum = sum + pendulum_cost_from_cos(m, cos_th, om); }
+  __device__ __forceinline__ float total(const ModelParams&) const { return sum; }
+};
+#endif
 __device__ __forceinline__ float pendulum_cost(const ModelParams& m, float th, float om) {
   float s, c;
   fast_sincosf(th, s, c);

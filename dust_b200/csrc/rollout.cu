@@ -123,11 +123,12 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
       float th = __ldg(x0), om = __ldg(x0 + 1);
       if (STORE) { st_out[0] = th; st_out[1] = om; }
       // cost at x_t uses cos(th_t), which the step evaluates from the reduction it needs anyway
+      PendulumCostSum run;
       auto one = [&](float a, int t) {
         const float om0 = om;
         float cth;
         pendulum_step<!SMALL>(k.m, cf, th, om, a, nullptr, &cth);
-        cost = cost + pendulum_cost_from_cos(k.m, cth, om0);
+        run.add(k.m, cth, om0);
         if (STORE) { st_out[(t + 1) * 2] = th; st_out[(t + 1) * 2 + 1] = om; }
       };
       int t = 0;
@@ -140,7 +141,7 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
         one(a4.x, t); one(a4.y, t + 1); one(a4.z, t + 2); one(a4.w, t + 3);
       }
       for (; t < k.H; ++t) one(XFORM ? th_row[t] + sg0 * arow[t] : arow[t], t);
-      cost = cost + pendulum_cost(k.m, th, om);
+      cost = run.total(k.m) + pendulum_cost(k.m, th, om);
     } else {
       const float mass = prm ? __ldg(prm) : k.m.default_mass;
       ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
@@ -369,40 +370,47 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
       const float cost = csum / (float)k.P;
       if (o.costs) o.costs[inst * k.SN + j0 + tid] = cost;
       c_run += cost;
-      float scale = 1.f, e = 1.f;
-      if (cost < m_run) {
-        scale = expf(-o.alpha * (m_run - cost));  // 0 on the first trajectory (m_run = +inf)
-        m_run = cost;
-      } else {
-        e = expf(-o.alpha * (cost - m_run));
-      }
+      // exactly one of {rescale of the running sums, weight of this trajectory} differs from 1
+      const float dlt = cost - m_run;                 // -inf on the first trajectory
+      const float ex = expf(-o.alpha * fabsf(dlt));   // 0 there
+      const bool lower = dlt < 0.f;
+      const float scale = lower ? ex : 1.f, e = lower ? 1.f : ex;
+      if (lower) m_run = cost;
       z_run = z_run * scale + e;
-      // weighted score row (a - theta)/sigma^2 with a = fl(theta + fl(sigma eps)); skipped when the
-      // weight is below 1e-30 of the running maximum weight (invisible in float32)
+      // weighted score row (a - theta)/sigma^2 = eps/sigma (the reference's a - theta differs from
+      // sigma*eps by the rounding of the sum, ~1e-7 relative); skipped when the weight is below
+      // 1e-30 of the running maximum weight (invisible in float32)
       if (scale != 1.f || e > 1e-30f) {
+#if DUST_PEND_OPT & 16
+        const float e0 = e * (is0 * sg0), e1 = e * (is1 * sg1);
+#define DUST_SCORE_TERM(w, sg, th, v) ((w) * (v))
+#else
         const float e0 = e * is0, e1 = e * is1;
+#define DUST_SCORE_TERM(w, sg, th, v) ((w) * (((th) + (sg) * (v)) - (th)))
+#endif
         if ((HA & 3) == 0) {
 #pragma unroll
           for (int c4 = 0; c4 < ACC / 4; ++c4) {
             if (4 * c4 < HA) {
               const float4 v = *reinterpret_cast<const float4*>(erow + 4 * c4);
+#if !(DUST_PEND_OPT & 16)
               const float4 t4 = *reinterpret_cast<const float4*>(th_row + 4 * c4);
+#endif
               const float sa = sg0, sb = (A == 1) ? sg0 : sg1;
               const float ea = e0, eb = (A == 1) ? e0 : e1;
-              acc[4 * c4 + 0] = fmaf(acc[4 * c4 + 0], scale, ea * ((t4.x + sa * v.x) - t4.x));
-              acc[4 * c4 + 1] = fmaf(acc[4 * c4 + 1], scale, eb * ((t4.y + sb * v.y) - t4.y));
-              acc[4 * c4 + 2] = fmaf(acc[4 * c4 + 2], scale, ea * ((t4.z + sa * v.z) - t4.z));
-              acc[4 * c4 + 3] = fmaf(acc[4 * c4 + 3], scale, eb * ((t4.w + sb * v.w) - t4.w));
+              (void)sa; (void)sb;
+              acc[4 * c4 + 0] = fmaf(acc[4 * c4 + 0], scale, DUST_SCORE_TERM(ea, sa, t4.x, v.x));
+              acc[4 * c4 + 1] = fmaf(acc[4 * c4 + 1], scale, DUST_SCORE_TERM(eb, sb, t4.y, v.y));
+              acc[4 * c4 + 2] = fmaf(acc[4 * c4 + 2], scale, DUST_SCORE_TERM(ea, sa, t4.z, v.z));
+              acc[4 * c4 + 3] = fmaf(acc[4 * c4 + 3], scale, DUST_SCORE_TERM(eb, sb, t4.w, v.w));
             }
           }
         } else {
 #pragma unroll
           for (int c = 0; c < ACC; ++c)
-            if (c < HA) {
-              const float sc_ = (c % A) ? sg1 : sg0, ec_ = (c % A) ? e1 : e0;
-              acc[c] = fmaf(acc[c], scale, ec_ * ((th_row[c] + sc_ * erow[c]) - th_row[c]));
-            }
+            if (c < HA) acc[c] = fmaf(acc[c], scale, DUST_SCORE_TERM((c % A) ? e1 : e0, (c % A) ? sg1 : sg0, th_row[c], erow[c]));
         }
+#undef DUST_SCORE_TERM
       }
     }
     __syncthreads();  // everyone is done with this buffer before it is refilled
