@@ -156,9 +156,10 @@ struct PendulumCostSum {
   __device__ __forceinline__ float total(const ModelParams&) const { return sum; }
 };
 #endif
+template <bool CHECK = true>
 __device__ __forceinline__ float pendulum_cost(const ModelParams& m, float th, float om) {
   float s, c;
-  fast_sincosf(th, s, c);
+  fast_sincosf<CHECK>(th, s, c);
   return pendulum_cost_from_cos(m, c, om);
 }
 

@@ -141,7 +141,7 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
         one(a4.x, t); one(a4.y, t + 1); one(a4.z, t + 2); one(a4.w, t + 3);
       }
       for (; t < k.H; ++t) one(XFORM ? th_row[t] + sg0 * arow[t] : arow[t], t);
-      cost = run.total(k.m) + pendulum_cost(k.m, th, om);
+      cost = run.total(k.m) + pendulum_cost<!SMALL>(k.m, th, om);
     } else {
       const float mass = prm ? __ldg(prm) : k.m.default_mass;
       ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
@@ -322,14 +322,32 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   const int drow = kFusedThreads / W, dc = kFusedThreads - drow * W;
   const int ntiles = (k.SN + TN - 1) / TN;
 
+  // unpadded rows (stride == HA): a tile is one contiguous block of global memory, fetched by a
+  // single 1-D bulk copy (TMA) that one thread issues and an mbarrier completes -- no per-thread
+  // copy instructions or address arithmetic.  Padded rows keep the 16-byte cp.async walk.
+  __shared__ __align__(8) uint64_t tile_bar[2];
+  const bool bulk = vec && stride == HA;
   auto prefetch = [&](int it) {
     const int j0 = it * TN;
     const int rows = min(TN, k.SN - j0);
     float* dst = (it & 1) ? buf1 : buf0;
+    if (bulk) {
+      if (tid == 0) {
+        const uint32_t bytes = (uint32_t)rows * (uint32_t)HA * 4u;
+        mbar_expect_tx(&tile_bar[it & 1], bytes);
+        bulk_g2s(dst, noise + (long long)j0 * HA, bytes, &tile_bar[it & 1]);
+      }
+      return;
+    }
     if (vec) stage_noise_async<true>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
     else stage_noise_async<false>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
     cp_async_commit();
   };
+  if (bulk && tid == 0) {
+    mbar_init(&tile_bar[0], 1);
+    mbar_init(&tile_bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   prefetch(0);
   for (int e = tid; e < N * HA; e += kFusedThreads) {
     const int nn = e / HA;
@@ -339,6 +357,7 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
     const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
     for (int w = tid; w < words; w += kFusedThreads) grid_s[w] = __ldg(k.m.grid_bits + w);
   }
+  __syncthreads();  // theta / grid / barrier initialisation visible to everyone
   const float sg0 = k.sigma[0], sg1 = k.sigma[A - 1];
   const float is0 = 1.0f / (sg0 * sg0), is1 = 1.0f / (sg1 * sg1);
   const bool small = small_angle_horizon<MODEL>(k, inst);
@@ -354,13 +373,14 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   for (int it = 0; it < ntiles; ++it) {
     const int j0 = it * TN;
     const int rows = min(TN, k.SN - j0);
-    if (it + 1 < ntiles) {
-      prefetch(it + 1);      // overlaps this tile's rollouts
-      cp_async_wait<1>();
+    if (it + 1 < ntiles) prefetch(it + 1);  // overlaps this tile's rollouts
+    if (bulk) {
+      mbar_wait(&tile_bar[it & 1], (uint32_t)(it >> 1) & 1u);
     } else {
-      cp_async_wait<0>();
+      if (it + 1 < ntiles) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncthreads();
     }
-    __syncthreads();
     const float* tile = (it & 1) ? buf1 : buf0;
     if (tid < rows) {
       const float* __restrict__ erow = tile + tid * stride;
@@ -417,18 +437,20 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   }
   // combine the G = TN/N threads that share a policy
   red_m[tid] = (tid < TN) ? m_run : INFINITY;
-  red_z[tid] = (tid < TN) ? z_run : 0.f;
   red_c[tid] = (tid < TN) ? c_run : 0.f;
   __syncthreads();
   const int G = TN / N;
   float m_n = INFINITY;
   for (int g = 0; g < G; ++g) m_n = fminf(m_n, red_m[g * N + n]);
+  // every thread rescales its OWN partial normaliser to the policy minimum (one exponential per
+  // thread instead of G), then the G slots of a policy are summed in a fixed order
+  const float own = (tid < TN && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) : 0.f;
+  red_z[tid] = z_run * own;
+  __syncthreads();
   float z_n = 0.f, c_n = 0.f;
-  for (int g = 0; g < G; ++g) {
-    const float mg = red_m[g * N + n];
-    z_n += (mg == INFINITY) ? 0.f : red_z[g * N + n] * expf(-o.alpha * (mg - m_n));
-    c_n += red_c[g * N + n];
-  }
+  for (int g = 0; g < G; ++g) z_n += red_z[g * N + n];
+  if (tid < N)
+    for (int g = 0; g < G; ++g) c_n += red_c[g * N + n];
   if (o.log_lik && tid < N) {
     float ll;
     if (o.likelihood == DUST_LIK_EXP_UTILITY) ll = (-o.alpha * m_n + logf(z_n)) - logf((float)k.S);  // likelihoods.py:133-135
@@ -448,7 +470,7 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
                                                        : -o.alpha * (c_n / (float)k.S);
   }
   if (o.grad_lik || o.tail.enabled) {
-    const float f = (tid < TN && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) / z_n : 0.f;
+    const float f = own / z_n;
     float* crow = buf0 + tid * stride;  // the noise tiles are dead: reuse buffer 0 for the partial rows
 #pragma unroll
     for (int c = 0; c < ACC; ++c)
