@@ -164,6 +164,66 @@ __device__ __forceinline__ float pendulum_cost(const ModelParams& m, float th, f
 }
 
 // ---------------------------------------------------------------------------------------
+// two pendulum trajectories per thread on the packed FP32 instructions of sm_100 (FFMA2 / FADD2 /
+// FMUL2: one issue slot, both lanes).  Operation for operation the scalar step above (mask 23),
+// each lane rounded exactly as the scalar instruction would: results are bit-identical to it.
+// Caller guarantees |th + pi| <= 64 (the SMALL horizon).
+// ---------------------------------------------------------------------------------------
+#if DUST_PEND_OPT == 23
+#define DUST_PEND_PAIR 1
+__device__ __forceinline__ float2 bc2(float c) { return make_float2(c, c); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+// a product that must NOT be contracted with a following add: ptxas (12.9) fuses mul.rn.f32x2 +
+// add.rn.f32x2 into FFMA2 even under --fmad=false, which it never does for the scalar .rn forms
+__device__ __forceinline__ float2 mul2_unfused(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+__device__ __forceinline__ float flip_sign(float v, uint32_t bits) {
+  return __uint_as_float(__float_as_uint(v) ^ (bits & 0x80000000u));
+}
+struct PendulumCoef2 {
+  float2 c1, c2;
+};
+// one step of both trajectories; `sum` accumulates the cost of the states BEFORE the step
+__device__ __forceinline__ void pendulum_step_pair(const ModelParams& m, const PendulumCoef2& c, float2& th, float2& om,
+                                                   float2 a, float2& sum) {
+  const float2 u = make_float2(fminf(fmaxf(a.x, -m.max_torque), m.max_torque), fminf(fmaxf(a.y, -m.max_torque), m.max_torque));
+  const float2 y = add2(th, bc2(kPiF));
+  const float2 t = fma2(y, bc2(0.636619772f), bc2(12582912.0f));
+  const float2 kf = add2(t, bc2(-12582912.0f));
+  float2 r = fma2(kf, bc2(-1.57079637050628662109375f), y);
+  r = fma2(kf, bc2(4.37113900018624283e-8f), r);
+  const float2 r2 = mul2(r, r);
+  float2 ps = fma2(fma2(bc2(-1.9515295891e-4f), r2, bc2(8.3321608736e-3f)), r2, bc2(-1.6666654611e-1f));
+  ps = fma2(ps, mul2(r2, r), r);
+  float2 pc = fma2(fma2(bc2(2.443315711809948e-5f), r2, bc2(-1.388731625493765e-3f)), r2, bc2(4.166664568298827e-2f));
+  pc = fma2(fma2(pc, r2, bc2(-0.5f)), r2, bc2(1.0f));
+  const uint32_t qa = __float_as_uint(t.x), qb = __float_as_uint(t.y);
+  const bool oa = (qa & 1u) != 0u, ob = (qb & 1u) != 0u;
+  float2 s, ncy;  // sin(y) and -cos(y)
+  s.x = flip_sign(oa ? pc.x : ps.x, qa << 30);
+  s.y = flip_sign(ob ? pc.y : ps.y, qb << 30);
+  ncy.x = flip_sign(oa ? ps.x : pc.x, (qa << 30) + 0xC0000000u);
+  ncy.y = flip_sign(ob ? ps.y : pc.y, (qb << 30) + 0xC0000000u);
+  const float2 bb = sub2(y, th);
+  const float2 err = add2(sub2(th, sub2(y, bb)), sub2(bc2(kPiF), bb));
+  const float2 ne = add2(err, bc2(-8.742278e-8f));
+  const float2 cth = fma2(ne, s, ncy);
+  float2 tt = add2(cth, bc2(-1.0f));
+  tt = mul2(tt, tt);
+  sum = add2(sum, add2(mul2_unfused(bc2(m.w_angle), tt), mul2_unfused(bc2(m.w_speed), mul2(om, om))));
+  const float2 acc = fma2(c.c1, s, mul2(c.c2, u));
+  const float2 pre = fma2(bc2(m.dt), acc, om);
+  om = make_float2(fminf(fmaxf(pre.x, -m.max_speed_pend), m.max_speed_pend),
+                   fminf(fmaxf(pre.y, -m.max_speed_pend), m.max_speed_pend));
+  th = fma2(om, bc2(m.dt), th);
+}
+#else
+#define DUST_PEND_PAIR 0
+#endif
+
+// ---------------------------------------------------------------------------------------
 // 2-D point mass among obstacles  (dust/models/particle.py:136-225, dust/utils/obstacle_map.py:64-93)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ float grid_lookup(const ModelParams& m, const uint32_t* __restrict__ bits, float x, float y) {

@@ -6,6 +6,8 @@
 // Reference: dust/controllers/disco.py:139-209 (rollout), :294-346 (cost), :380-393 (soft-min),
 // dust/inference/likelihoods.py:81-135, dust/inference/svmpc.py:46-54.
 // Compiled with -fmad=false (see models.cuh).
+#include <stdlib.h>
+
 #include "models.cuh"
 #include "svgd_dev.cuh"
 
@@ -177,6 +179,49 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
   return csum;
 }
 
+#if DUST_PEND_PAIR
+// rows jA and jB (same policy, hence the same theta row) rolled out together on the packed FP32
+// instructions; XFORM actions th_row[t] + sigma * eps[t].  Small-angle horizon only.
+__device__ __forceinline__ float2 pendulum_pair_cost_sum(const RolloutKParams& k, const float* __restrict__ rowA,
+                                                         const float* __restrict__ rowB, long long inst, int jA, int jB,
+                                                         const float* __restrict__ th_row, float sg0) {
+  const float* __restrict__ x0 = k.state0 + inst * 2;
+  const float th0 = __ldg(x0), om0 = __ldg(x0 + 1);
+  float2 csum = make_float2(0.f, 0.f);
+  const float2 sg = bc2(sg0);
+  for (int p = 0; p < k.P; ++p) {
+    PendulumCoef ca, cb;
+    if (k.params) {
+      const int pa = k.interleaved ? (int)(((long long)p * k.SN + jA) % k.P) : p;
+      const int pb = k.interleaved ? (int)(((long long)p * k.SN + jB) % k.P) : p;
+      const float* qa = k.params + (inst * k.P + pa) * 2;
+      const float* qb = k.params + (inst * k.P + pb) * 2;
+      ca = pendulum_coef_sampled(k.m, __ldg(qa), __ldg(qa + 1));
+      cb = (pb == pa) ? ca : pendulum_coef_sampled(k.m, __ldg(qb), __ldg(qb + 1));
+    } else {
+      ca = cb = pendulum_coef_default(k.m);
+    }
+    const PendulumCoef2 cf{make_float2(ca.c1, cb.c1), make_float2(ca.c2, cb.c2)};
+    float2 th = bc2(th0), om = bc2(om0), run = make_float2(0.f, 0.f);
+    int t = 0;
+    for (; t + 4 <= k.H; t += 4) {
+      const float4 ea = *reinterpret_cast<const float4*>(rowA + t);
+      const float4 eb = *reinterpret_cast<const float4*>(rowB + t);
+      const float4 t4 = *reinterpret_cast<const float4*>(th_row + t);
+      pendulum_step_pair(k.m, cf, th, om, add2(bc2(t4.x), mul2_unfused(sg, make_float2(ea.x, eb.x))), run);
+      pendulum_step_pair(k.m, cf, th, om, add2(bc2(t4.y), mul2_unfused(sg, make_float2(ea.y, eb.y))), run);
+      pendulum_step_pair(k.m, cf, th, om, add2(bc2(t4.z), mul2_unfused(sg, make_float2(ea.z, eb.z))), run);
+      pendulum_step_pair(k.m, cf, th, om, add2(bc2(t4.w), mul2_unfused(sg, make_float2(ea.w, eb.w))), run);
+    }
+    for (; t < k.H; ++t)
+      pendulum_step_pair(k.m, cf, th, om, add2(bc2(th_row[t]), mul2_unfused(sg, make_float2(rowA[t], rowB[t]))), run);
+    const float2 term = make_float2(pendulum_cost<false>(k.m, th.x, om.x), pendulum_cost<false>(k.m, th.y, om.y));
+    csum = add2(csum, add2(run, term));
+  }
+  return csum;
+}
+#endif
+
 // |theta_t + pi| <= |theta_0| + t dt max_speed + pi: decided once per instance (uniform in the CTA)
 template <int MODEL>
 __device__ __forceinline__ bool small_angle_horizon(const RolloutKParams& k, long long inst) {
@@ -282,13 +327,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 // asynchronous copy of a [rows, HA] block of raw noise into a padded shared-memory tile; the walk
 // (row0, c0, drow, dc) is the thread's fixed stride pattern, computed once per kernel.
-template <bool VEC>
+template <bool VEC, int NT>
 __device__ __forceinline__ void stage_noise_async(const float* __restrict__ src, float* tile, int stride, int rows, int HA,
                                                   int row0, int c0, int drow, int dc) {
   const int W = VEC ? (HA >> 2) : HA;  // columns in units of the copy width
   const int total = rows * W;
   int row = row0, c = c0;
-  for (int e = threadIdx.x; e < total; e += kFusedThreads) {
+  for (int e = threadIdx.x; e < total; e += NT) {
     if (VEC) cp_async16(tile + row * stride + 4 * c, reinterpret_cast<const float4*>(src) + e);
     else cp_async4(tile + row * stride + c, src + e);
     c += dc;
@@ -297,9 +342,13 @@ __device__ __forceinline__ void stage_noise_async(const float* __restrict__ src,
   }
 }
 
-template <int MODEL, int ACC>
-__global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance_kernel(const RolloutKParams k, const FusedOut o) {
+// TPT: trajectories per thread.  2 = the packed pendulum path: NT = 128 threads, thread tid owns rows
+// tid and tid + TN/2 of every 256-row tile (same policy: the host checks that TN/2 is a multiple of N).
+template <int MODEL, int ACC, int TPT>
+__global__ void __launch_bounds__(kFusedThreads / TPT, TPT == 2 ? 5 : DUST_FUSED_MINB) svmpc_instance_kernel(const RolloutKParams k, const FusedOut o) {
   constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  constexpr int NT = kFusedThreads / TPT;   // threads of the CTA
+  static_assert(TPT == 1 || (MODEL == DUST_MODEL_PENDULUM && DUST_PEND_PAIR), "the packed path is the pendulum's");
   extern __shared__ __align__(16) float smem[];
   const int stride = padded_stride(k.HA);
   const int HA = k.HA, N = k.N;
@@ -308,10 +357,10 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   float* buf1 = buf0 + kFusedThreads * stride;
   float* th_s = buf1 + kFusedThreads * stride;          // [N][thst] policy means
   const int thst = (HA + 3) & ~3;                       // theta row stride (16-byte aligned rows)
-  float* red_m = th_s + N * thst;                       // [256]
-  float* red_z = red_m + kFusedThreads;                 // [256]
-  float* red_c = red_z + kFusedThreads;                 // [256]
-  uint32_t* grid_s = reinterpret_cast<uint32_t*>(red_c + kFusedThreads);
+  float* red_m = buf1;                                  // [256] the reductions after the tile loop live in the
+  float* red_z = red_m + kFusedThreads;                 // [256] second noise buffer, which is dead by then
+  float* red_c = red_z + kFusedThreads;                 // [256] (stride >= 4 floats per row: 1024 >= 768)
+  uint32_t* grid_s = reinterpret_cast<uint32_t*>(th_s + N * thst);
   const long long inst = blockIdx.x;
   const int tid = threadIdx.x;
   const int n = tid % N;
@@ -319,7 +368,7 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   const bool vec = ((HA & 3) == 0) && ((((uintptr_t)noise) & 15) == 0);
   const int W = vec ? (HA >> 2) : HA;
   const int row0 = tid / W, c0 = tid - row0 * W;
-  const int drow = kFusedThreads / W, dc = kFusedThreads - drow * W;
+  const int drow = NT / W, dc = NT - drow * W;
   const int ntiles = (k.SN + TN - 1) / TN;
 
   // unpadded rows (stride == HA): a tile is one contiguous block of global memory, fetched by a
@@ -339,8 +388,8 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
       }
       return;
     }
-    if (vec) stage_noise_async<true>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
-    else stage_noise_async<false>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
+    if (vec) stage_noise_async<true, NT>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
+    else stage_noise_async<false, NT>(noise + (long long)j0 * HA, dst, stride, rows, HA, row0, c0, drow, dc);
     cp_async_commit();
   };
   if (bulk && tid == 0) {
@@ -349,13 +398,13 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   prefetch(0);
-  for (int e = tid; e < N * HA; e += kFusedThreads) {
+  for (int e = tid; e < N * HA; e += NT) {
     const int nn = e / HA;
     th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
   }
   if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
     const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
-    for (int w = tid; w < words; w += kFusedThreads) grid_s[w] = __ldg(k.m.grid_bits + w);
+    for (int w = tid; w < words; w += NT) grid_s[w] = __ldg(k.m.grid_bits + w);
   }
   __syncthreads();  // theta / grid / barrier initialisation visible to everyone
   const float sg0 = k.sigma[0], sg1 = k.sigma[A - 1];
@@ -382,13 +431,11 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
       __syncthreads();
     }
     const float* tile = (it & 1) ? buf1 : buf0;
-    if (tid < rows) {
-      const float* __restrict__ erow = tile + tid * stride;
-      const float csum = small
-          ? trajectory_cost_sum<MODEL, true, false, true>(k, erow, grid_s, inst, j0 + tid, 0, k.P, th_row, sg0, sg1)
-          : trajectory_cost_sum<MODEL, false, false, true>(k, erow, grid_s, inst, j0 + tid, 0, k.P, th_row, sg0, sg1);
+    // fold one finished trajectory (row `erow`, index j, summed cost csum) into this thread's running
+    // soft-min state; both rows of a packed thread belong to the same policy and share that state
+    auto fold = [&](float csum, const float* __restrict__ erow, int j) {
       const float cost = csum / (float)k.P;
-      if (o.costs) o.costs[inst * k.SN + j0 + tid] = cost;
+      if (o.costs) o.costs[inst * k.SN + j] = cost;
       c_run += cost;
       // exactly one of {rescale of the running sums, weight of this trajectory} differs from 1
       const float dlt = cost - m_run;                 // -inf on the first trajectory
@@ -432,19 +479,59 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
         }
 #undef DUST_SCORE_TERM
       }
+    };
+    if (TPT == 1) {
+      if (tid < rows) {
+        const float* __restrict__ erow = tile + tid * stride;
+        const float csum = small
+            ? trajectory_cost_sum<MODEL, true, false, true>(k, erow, grid_s, inst, j0 + tid, 0, k.P, th_row, sg0, sg1)
+            : trajectory_cost_sum<MODEL, false, false, true>(k, erow, grid_s, inst, j0 + tid, 0, k.P, th_row, sg0, sg1);
+        fold(csum, erow, j0 + tid);
+      }
+    } else {
+#if DUST_PEND_PAIR
+      const int half = TN >> 1;
+      const int ra = tid, rb = tid + half;
+      if (tid < half && ra < rows) {
+        const float* __restrict__ rowA = tile + ra * stride;
+        const float* __restrict__ rowB = tile + rb * stride;
+        const int nv = (rb < rows) ? 2 : 1;
+        float csA, csB = 0.f;
+        if (small && nv == 2) {
+          const float2 cs = pendulum_pair_cost_sum(k, rowA, rowB, inst, j0 + ra, j0 + rb, th_row, sg0);
+          csA = cs.x;
+          csB = cs.y;
+        } else {
+          // ragged last tile, or an angle beyond the fast range: the scalar step, same arithmetic.
+          // Rare: kept as ONE copy of the code (no unrolling) so the kernel stays small.
+          csA = 0.f;
+#pragma unroll 1
+          for (int q = 0; q < nv; ++q) {
+            const float* __restrict__ row = q ? rowB : rowA;
+            const int jj = j0 + (q ? rb : ra);
+            const float v = small ? trajectory_cost_sum<MODEL, true, false, true>(k, row, grid_s, inst, jj, 0, k.P, th_row, sg0, sg1)
+                                  : trajectory_cost_sum<MODEL, false, false, true>(k, row, grid_s, inst, jj, 0, k.P, th_row, sg0, sg1);
+            if (q) csB = v; else csA = v;
+          }
+        }
+#pragma unroll 1
+        for (int q = 0; q < nv; ++q) fold(q ? csB : csA, q ? rowB : rowA, j0 + (q ? rb : ra));
+      }
+#endif
     }
     __syncthreads();  // everyone is done with this buffer before it is refilled
   }
   // combine the G = TN/N threads that share a policy
-  red_m[tid] = (tid < TN) ? m_run : INFINITY;
-  red_c[tid] = (tid < TN) ? c_run : 0.f;
+  const int TNT = TN / TPT;  // threads that own trajectories; tid % N is their policy
+  red_m[tid] = (tid < TNT) ? m_run : INFINITY;
+  red_c[tid] = (tid < TNT) ? c_run : 0.f;
   __syncthreads();
-  const int G = TN / N;
+  const int G = TNT / N;
   float m_n = INFINITY;
   for (int g = 0; g < G; ++g) m_n = fminf(m_n, red_m[g * N + n]);
   // every thread rescales its OWN partial normaliser to the policy minimum (one exponential per
   // thread instead of G), then the G slots of a policy are summed in a fixed order
-  const float own = (tid < TN && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) : 0.f;
+  const float own = (tid < TNT && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) : 0.f;
   red_z[tid] = z_run * own;
   __syncthreads();
   float z_n = 0.f, c_n = 0.f;
@@ -476,7 +563,7 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
     for (int c = 0; c < ACC; ++c)
       if (c < HA) crow[c] = acc[c] * f;
     __syncthreads();
-    for (int col = tid; col < N * HA; col += kFusedThreads) {
+    for (int col = tid; col < N * HA; col += NT) {
       const int n2 = col / HA, c = col - n2 * HA;
       float sacc = 0.f;
       for (int g = 0; g < G; ++g) sacc += buf0[(g * N + n2) * stride + c];
@@ -491,7 +578,7 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   // one warp per particle; lanes over the flattened dimension (HA <= 32 here)
   // ------------------------------------------------------------------------------------
   const TailParams& t = o.tail;
-  const int warp = tid >> 5, lane = tid & 31, nwarps = kFusedThreads >> 5;
+  const int warp = tid >> 5, lane = tid & 31, nwarps = NT >> 5;
   const float* mu_g = t.mu ? t.mu + inst * (long long)N * HA : nullptr;
   if (warp == 0) warp_log_mix(t.mix ? t.mix + inst * N : nullptr, N, lmix_s);
   __syncthreads();
@@ -567,10 +654,10 @@ __global__ void __launch_bounds__(kFusedThreads, DUST_FUSED_MINB) svmpc_instance
   __syncthreads();
   const int is = s_istar;
   if (t.a_seq)
-    for (int d = tid; d < HA; d += kFusedThreads) t.a_seq[inst * HA + d] = nw_s[is * thst + d];
+    for (int d = tid; d < HA; d += NT) t.a_seq[inst * HA + d] = nw_s[is * thst + d];
   if (t.theta_next) {
     const int shift_lim = (k.H - 1) * A;
-    for (int e = tid; e < N * HA; e += kFusedThreads) {
+    for (int e = tid; e < N * HA; e += NT) {
       const int n2 = e / HA, d = e - n2 * HA;
       float v;
       if (d < shift_lim) {
@@ -839,26 +926,37 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
                "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");
   if (fused_ok) {
     const int thst_h = (k.HA + 3) & ~3;
-    const size_t fsmem = sizeof(float) * ((size_t)2 * kFusedThreads * stride + (size_t)a->N * thst_h + 3 * kFusedThreads +
+    const size_t fsmem = sizeof(float) * ((size_t)2 * kFusedThreads * stride + (size_t)a->N * thst_h +
                                           (size_t)3 * a->N * thst_h + (size_t)(3 + 8) * a->N) + grid_bytes;
     FusedOut o{a->costs, a->log_lik, a->grad_lik, a->likelihood, a->alpha, TailParams{}};
     if (tail) o.tail = *tail;
     k.cost_out = nullptr;
-#define DUST_FUSED(MODEL, ACC)                                                                                              \
+#define DUST_FUSED(MODEL, ACC, TPT)                                                                                         \
   do {                                                                                                                      \
     if (fsmem > 48 * 1024)                                                                                                  \
-      DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_instance_kernel<MODEL, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
-    { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_instance_kernel<MODEL, ACC><<<a->B, kFusedThreads, fsmem, stream>>>(k, o); } \
+      DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_instance_kernel<MODEL, ACC, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
+    { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_instance_kernel<MODEL, ACC, TPT><<<a->B, kFusedThreads / TPT, fsmem, stream>>>(k, o); } \
   } while (0)
     if (kind == DUST_MODEL_PENDULUM) {
-      if (k.HA <= 8) DUST_FUSED(DUST_MODEL_PENDULUM, 8);
-      else if (k.HA <= 16) DUST_FUSED(DUST_MODEL_PENDULUM, 16);
-      else if (k.HA <= 20) DUST_FUSED(DUST_MODEL_PENDULUM, 20);
-      else if (k.HA <= 24) DUST_FUSED(DUST_MODEL_PENDULUM, 24);
-      else DUST_FUSED(DUST_MODEL_PENDULUM, 32);
+      // two trajectories per thread on the packed FP32 pipe when both rows of a thread share a policy
+      // (half a tile is a whole number of policy groups); DUST_B200_NO_PAIR=1 forces the scalar kernel
+      static const bool no_pair = getenv("DUST_B200_NO_PAIR") != nullptr;
+      const bool pair = DUST_PEND_PAIR && !no_pair && ((kFusedThreads / a->N) % 2 == 0) && a->N <= kFusedThreads / 2;
+#if DUST_PEND_PAIR
+#define DUST_FUSED_PEND(ACC) do { if (pair) DUST_FUSED(DUST_MODEL_PENDULUM, ACC, 2); else DUST_FUSED(DUST_MODEL_PENDULUM, ACC, 1); } while (0)
+#else
+#define DUST_FUSED_PEND(ACC) DUST_FUSED(DUST_MODEL_PENDULUM, ACC, 1)
+      (void)pair;
+#endif
+      if (k.HA <= 8) DUST_FUSED_PEND(8);
+      else if (k.HA <= 16) DUST_FUSED_PEND(16);
+      else if (k.HA <= 20) DUST_FUSED_PEND(20);
+      else if (k.HA <= 24) DUST_FUSED_PEND(24);
+      else DUST_FUSED_PEND(32);
+#undef DUST_FUSED_PEND
     } else {
-      if (k.HA <= 16) DUST_FUSED(DUST_MODEL_PARTICLE, 16);
-      else DUST_FUSED(DUST_MODEL_PARTICLE, 32);
+      if (k.HA <= 16) DUST_FUSED(DUST_MODEL_PARTICLE, 16, 1);
+      else DUST_FUSED(DUST_MODEL_PARTICLE, 32, 1);
     }
 #undef DUST_FUSED
     DUST_LAUNCH_OK("svmpc_instance_kernel");
