@@ -133,6 +133,7 @@ SYMBOLS = {
     "dust_mpf_optimize": (C.c_int, [C.POINTER(MpfArgs), _p]),
     "dust_model_step": (C.c_int, [C.POINTER(ModelDesc), _i, _p, _p, _p, _p, _p]),
     "dust_model_cost": (C.c_int, [C.POINTER(ModelDesc), _i, _i, _p, _p, _p, _p]),
+    "dust_noise_normal": (C.c_int, [_p, C.c_int64, C.c_uint64, C.c_uint64, _p]),
     "dust_profiler_enable": (None, [C.c_int]),
     "dust_profiler_reset": (None, []),
     "dust_profiler_report": (C.c_int, [C.c_char_p, _sz]),

@@ -4,6 +4,7 @@ batch dimension); same per-instance semantics as `dust_b200.inference.svmpc.SVMP
 import torch
 
 from . import _lib as L
+from . import ops
 from .inference.core import GPYTORCH_DEFAULT_LENGTHSCALE, SvmpcCore
 
 
@@ -11,7 +12,7 @@ class BatchedSVMPC:
     def __init__(self, model, n_instances, n_policies, action_samples, horizon, ctrl_sigma, prior_sigma,
                  alpha=1.0, learning_rate=1.0, kernel="gpytorch", inst_cost_fn=None, term_cost_fn=None,
                  weighted_prior=False, roll_strategy="repeat", grad="analytic", params_samples=0,
-                 device="cuda", seed=0):
+                 device="cuda", seed=0, noise_stream=0):
         L.require_cuda()
         self.device = torch.device(device)
         self.model = model
@@ -32,13 +33,16 @@ class BatchedSVMPC:
                               lengthscale=GPYTORCH_DEFAULT_LENGTHSCALE, grad=grad, roll_strategy=roll_strategy,
                               weighted_prior=weighted_prior)
         self.eps = torch.empty(B, self.S, N, H, A, device=self.device)
+        # action noise: the library's counter-based generator, one Philox stream per (rank, draw)
+        self.seed, self.noise_stream, self.draws = int(seed), int(noise_stream), 0
 
     @property
     def theta(self):
         return self.core.theta
 
     def draw_noise(self):
-        self.eps.normal_(generator=self.gen)
+        ops.noise_normal(self.eps, self.seed, (self.noise_stream << 40) + self.draws)
+        self.draws += 1
         return self.eps
 
     def optimize(self, state, eps=None, params=None):

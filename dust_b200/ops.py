@@ -210,6 +210,16 @@ def median_sq_dist(x, ws=None, rows=None, all_reduce=None, allow_fast=True):
     return ws.median
 
 
+def noise_normal(out, seed, offset):
+    """Fill the float32 CUDA tensor `out` with standard-normal noise: Philox4x32-10 keyed by `seed`,
+    stream selected by `offset` (one offset per draw / per rank), Box-Muller.  Returns `out`."""
+    L.require_cuda()
+    if out.dtype != torch.float32:
+        raise ValueError("dust_b200: noise_normal fills float32 tensors")
+    L.call("dust_noise_normal", L.ptr(out), out.numel(), int(seed) & (2 ** 64 - 1), int(offset) & (2 ** 64 - 1), L.stream())
+    return out
+
+
 def bandwidth_from_median(median, N, scale=1.0, mode=0):
     """-> device tensor {gamma, c1, c2, bw|h}."""
     out = torch.empty(4, dtype=torch.float32, device=median.device)

@@ -374,6 +374,12 @@ int dust_model_step(const dust_model_desc* model, int32_t M, const float* states
 int dust_model_cost(const dust_model_desc* model, int32_t M, int32_t terminal, const float* states,
                     const float* actions, float* costs, void* stream);
 
+/* Standard-normal action noise, replacing the rsample draws of dust/inference/likelihoods.py:97-103
+ * and dust/controllers/disco.py:211-230.  Counter-based (Philox4x32-10 + Box-Muller): block i of four
+ * values depends only on (seed, offset, i), so a fill is reproducible, and ranks / successive steps
+ * draw independent streams by using distinct offsets.  out: n floats, 16-byte aligned. */
+int dust_noise_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
 /* Optional per-kernel timing for benchmarks: when enabled every kernel launch of the library is
  * bracketed by CUDA events on its stream.  dust_profiler_report synchronises the device and
  * writes "<kernel> <launches> <total_ms>" lines.  dust_launch_count: kernels launched so far. */

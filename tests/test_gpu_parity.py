@@ -566,3 +566,65 @@ def test_tensor_core_path_is_taken(env):
     prof = L.profiler_report()
     lib.dust_profiler_enable(0)
     assert "phi_tc_kernel" in prof and "phi_large_kernel" not in prof
+
+
+# ---------------------------------------------------------------------------------------------
+# action-noise generator (Philox4x32-10 + Box-Muller)
+# ---------------------------------------------------------------------------------------------
+def _philox4x32_10(index, offset, seed):
+    """numpy restatement of the published Philox4x32-10 (Salmon et al., SC'11) for known-answer checks."""
+    M0, M1, W0, W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+    c = [index & 0xFFFFFFFF, index >> 32, offset & 0xFFFFFFFF, offset >> 32]
+    k = [seed & 0xFFFFFFFF, seed >> 32]
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [(p1 >> 32) ^ c[1] ^ k[0], p1 & 0xFFFFFFFF, (p0 >> 32) ^ c[3] ^ k[1], p0 & 0xFFFFFFFF]
+        k = [(k[0] + W0) & 0xFFFFFFFF, (k[1] + W1) & 0xFFFFFFFF]
+    return c
+
+
+def test_philox_known_answers():
+    """Random123's published vectors for philox4x32-10: counter/key all zero, and all ones."""
+    assert _philox4x32_10(0, 0, 0) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    ones = (1 << 64) - 1
+    assert _philox4x32_10(ones, ones, ones) == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+
+
+def test_noise_generator_matches_philox_and_is_normal(env):
+    from dust_b200 import ops
+
+    # bit-level: the first blocks against the host restatement pushed through the same Box-Muller
+    seed, offset = 0x1234_5678_9ABC_DEF0, 77
+    out = ops.noise_normal(torch.empty(64, device=DEV), seed, offset).cpu().double()
+    for i in range(16):
+        w = _philox4x32_10(i, offset, seed)
+        for h, (a, b) in enumerate(((w[0], w[1]), (w[2], w[3]))):
+            u = (a + 1) * 2.0 ** -32
+            rev = (b >> 9) * 2.0 ** -23
+            r = math.sqrt(-2.0 * math.log(u))
+            exp = (r * math.cos(2 * math.pi * rev), r * math.sin(2 * math.pi * rev))
+            got = out[4 * i + 2 * h: 4 * i + 2 * h + 2]
+            assert abs(float(got[0]) - exp[0]) <= 2e-5 * max(1.0, r) and abs(float(got[1]) - exp[1]) <= 2e-5 * max(1.0, r)
+    # reproducible; other offsets / seeds give other streams; ragged length
+    a = ops.noise_normal(torch.empty(1003, device=DEV), 5, 9)
+    assert torch.equal(a, ops.noise_normal(torch.empty(1003, device=DEV), 5, 9))
+    assert torch.equal(a[:1000], ops.noise_normal(torch.empty(1000, device=DEV), 5, 9))
+    assert not torch.equal(a, ops.noise_normal(torch.empty(1003, device=DEV), 5, 10))
+    assert not torch.equal(a, ops.noise_normal(torch.empty(1003, device=DEV), 6, 9))
+    # distribution: moments, Kolmogorov-Smirnov against the normal CDF, independence of neighbours and streams
+    n = 1 << 24
+    z = ops.noise_normal(torch.empty(n, device=DEV), 42, 0).double()
+    assert abs(float(z.mean())) < 5 / math.sqrt(n)
+    assert abs(float(z.var()) - 1) < 5 * math.sqrt(2 / n)
+    assert abs(float((z ** 3).mean())) < 5 * math.sqrt(15 / n)
+    assert abs(float((z ** 4).mean()) - 3) < 5 * math.sqrt(96 / n)
+    assert 5.0 < float(z.abs().max()) < 7.0
+    srt = z.sort().values
+    cdf = 0.5 * (1 + torch.erf(srt / math.sqrt(2)))
+    emp = (torch.arange(1, n + 1, device=DEV, dtype=torch.float64)) / n
+    ks = float(torch.maximum((emp - cdf).abs(), (emp - 1 / n - cdf).abs()).max())
+    assert ks < 1.95 / math.sqrt(n)  # 0.1 % critical value
+    for lag in (1, 2, 3, 4, 5, 8):
+        assert abs(float((z[:-lag] * z[lag:]).mean())) < 5 / math.sqrt(n)
+    z2 = ops.noise_normal(torch.empty(n, device=DEV), 42, 1).double()
+    assert abs(float((z * z2).mean())) < 5 / math.sqrt(n)
