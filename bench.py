@@ -283,7 +283,7 @@ def run_ours(args, rank, world, local_rank):
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                 "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
                 "ms_per_launch": per, "peak_source": peak_src,
-                "note": "kernel is FP32-issue/SFU bound (sinf+cosf per model step), see DESIGN.md"}
+                "note": "not HBM-limited: ~31 issue slots per model step vs 4 bytes of noise; issue/latency bound at 20 warps/SM, see DESIGN.md section 3"}
     step_kernel_ms = {k: v[1] / K for k, v in prof.items()}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
