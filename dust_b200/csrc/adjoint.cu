@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
     else
       coef = -k.alpha / ((float)k.S * (float)k.P);
 
-    for (int p = p_begin; p < p_end; ++p) {
+    constexpr int Q = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;   // parameter draws advanced together per thread
+    for (int p = p_begin; p < p_end; p += Q) {
       const float* prm = nullptr;
       if (k.params) {
         const int pi = k.interleaved ? (int)(((long long)p * k.SN + j) % k.P) : p;
@@ -114,45 +115,119 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
           lam_om = g + 2.0f * k.m.w_speed * omt;
         }
       } else {
-        const float mass = prm ? __ldg(prm) : k.m.default_mass;
-        float xs[MAXH + 1][4];
-        uint32_t cbit[(MAXH + 31) / 32], mvx[(MAXH + 31) / 32], mvy[(MAXH + 31) / 32];
-#pragma unroll
-        for (int w = 0; w < (MAXH + 31) / 32; ++w) { cbit[w] = 0u; mvx[w] = 0u; mvy[w] = 0u; }
-        ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
+        // Checkpointed reverse sweep: the forward pass keeps the state every SEG steps (a handful of
+        // 16-byte entries); each segment is then rolled out again into REGISTERS and reversed.  Three
+        // model-step sweeps instead of two, but a tenth of the local-memory traffic of storing the
+        // whole trajectory (which went through L2: the shared-memory tiles leave almost no L1).
+        // Q = 2 parameter draws run side by side in one thread: the tiles cost 832 B of shared memory
+        // per thread, so an SM holds only 8 warps and the second, independent chain fills the gaps.
+        constexpr int SEG = 10;
+        constexpr int NSEG = (MAXH + SEG - 1) / SEG;
         const bool has_grid = k.m.grid_bits != nullptr;
-        for (int t = 0; t < k.H; ++t) {
-          xs[t][0] = s.x; xs[t][1] = s.y; xs[t][2] = s.vx; xs[t][3] = s.vy;
-          const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
-          float vpre[2];
-          particle_step(k.m, s, arow[2 * t], arow[2 * t + 1], mass, c, vpre);
-          if (c != 0.f) cbit[t >> 5] |= 1u << (t & 31);
-          if (vpre[0] >= -k.m.max_speed && vpre[0] <= k.m.max_speed) mvx[t >> 5] |= 1u << (t & 31);
-          if (vpre[1] >= -k.m.max_speed && vpre[1] <= k.m.max_speed) mvy[t >> 5] |= 1u << (t & 31);
+        const int nseg = (k.H + SEG - 1) / SEG;
+        float mass[Q], rmass[Q], cq[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          const bool live = p + q < p_end;
+          float mq = k.m.default_mass;
+          if (k.params) {
+            const int pq = live ? p + q : p;
+            const int pi = k.interleaved ? (int)(((long long)pq * k.SN + j) % k.P) : pq;
+            mq = __ldg(k.params + (inst * k.P + pi) * DP);
+          }
+          mass[q] = mq;
+          rmass[q] = 1.0f / mq;
+          cq[q] = live ? coef : 0.f;   // a padding chain contributes nothing
         }
-        float lam[4];
-        lam[0] = 2.0f * k.m.w_term[0] * (s.x - k.m.target[0]);
-        lam[1] = 2.0f * k.m.w_term[1] * (s.y - k.m.target[1]);
-        lam[2] = 2.0f * k.m.w_term[2] * (s.vx - k.m.target[2]);
-        lam[3] = 2.0f * k.m.w_term[3] * (s.vy - k.m.target[3]);
-        for (int t = k.H - 1; t >= 0; --t) {
-          const float ax = arow[2 * t], ay = arow[2 * t + 1];
-          const float amx = ax / mass, amy = ay / mass;
-          const bool max_ = (amx >= -k.m.max_accel) && (amx <= k.m.max_accel);
-          const bool may_ = (amy >= -k.m.max_accel) && (amy <= k.m.max_accel);
-          const bool crashed = (cbit[t >> 5] >> (t & 31)) & 1u;
-          const float kk = (k.m.can_crash && crashed) ? 0.f : k.m.dt;
-          const float gvx = ((mvx[t >> 5] >> (t & 31)) & 1u) ? lam[2] : 0.f;
-          const float gvy = ((mvy[t >> 5] >> (t & 31)) & 1u) ? lam[3] : 0.f;
-          const float gax = (max_ ? kk * gvx / mass : 0.f) + 2.0f * k.m.w_ctrl[0] * ax;
-          const float gay = (may_ ? kk * gvy / mass : 0.f) + 2.0f * k.m.w_ctrl[1] * ay;
-          grow[2 * t] += coef * gax;
-          grow[2 * t + 1] += coef * gay;
-          const float l0 = lam[0] + 2.0f * k.m.w_state[0] * (xs[t][0] - k.m.target[0]);
-          const float l1 = lam[1] + 2.0f * k.m.w_state[1] * (xs[t][1] - k.m.target[1]);
-          const float l2 = gvx + kk * lam[0] + 2.0f * k.m.w_state[2] * (xs[t][2] - k.m.target[2]);
-          const float l3 = gvy + kk * lam[1] + 2.0f * k.m.w_state[3] * (xs[t][3] - k.m.target[3]);
-          lam[0] = l0; lam[1] = l1; lam[2] = l2; lam[3] = l3;
+        float4 ck[NSEG][Q];
+        uint32_t occ[NSEG][Q];   // occupancy of the cell the state sits in, step by step (first sweep -> recompute)
+        ParticleState s[Q];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) s[q] = ParticleState{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
+        for (int sg = 0; sg < nseg; ++sg) {
+#pragma unroll
+          for (int q = 0; q < Q; ++q) ck[sg][q] = make_float4(s[q].x, s[q].y, s[q].vx, s[q].vy);
+          uint32_t ob[Q];
+#pragma unroll
+          for (int q = 0; q < Q; ++q) ob[q] = 0u;
+#pragma unroll
+          for (int i = 0; i < SEG; ++i) {
+            const int t = sg * SEG + i;
+            if (t < k.H) {
+              const float ax = arow[2 * t], ay = arow[2 * t + 1];
+#pragma unroll
+              for (int q = 0; q < Q; ++q) {
+                const float c = has_grid ? grid_lookup(k.m, grid_s, s[q].x, s[q].y) : 0.f;
+                if (c != 0.f) ob[q] |= 1u << i;
+                particle_step(k.m, s[q], ax, ay, mass[q], c);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < Q; ++q) occ[sg][q] = ob[q];
+        }
+        float lam[Q][4];
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          lam[q][0] = 2.0f * k.m.w_term[0] * (s[q].x - k.m.target[0]);
+          lam[q][1] = 2.0f * k.m.w_term[1] * (s[q].y - k.m.target[1]);
+          lam[q][2] = 2.0f * k.m.w_term[2] * (s[q].vx - k.m.target[2]);
+          lam[q][3] = 2.0f * k.m.w_term[3] * (s[q].vy - k.m.target[3]);
+        }
+        for (int sg = nseg - 1; sg >= 0; --sg) {
+          float xs[Q][SEG][4];
+          uint32_t cbit[Q], mvx[Q], mvy[Q], max_[Q], may_[Q];
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const float4 c4 = ck[sg][q];
+            s[q] = ParticleState{c4.x, c4.y, c4.z, c4.w};
+            cbit[q] = occ[sg][q];
+            mvx[q] = mvy[q] = max_[q] = may_[q] = 0u;
+          }
+#pragma unroll
+          for (int i = 0; i < SEG; ++i) {
+            const int t = sg * SEG + i;
+            if (t < k.H) {
+              const float ax = arow[2 * t], ay = arow[2 * t + 1];
+#pragma unroll
+              for (int q = 0; q < Q; ++q) {
+                xs[q][i][0] = s[q].x; xs[q][i][1] = s[q].y; xs[q][i][2] = s[q].vx; xs[q][i][3] = s[q].vy;
+                const float c = (float)((cbit[q] >> i) & 1u);   // same state as in the first sweep: same cell
+                float vpre[2], apre[2];
+                particle_step(k.m, s[q], ax, ay, mass[q], c, vpre, apre);
+                if (vpre[0] >= -k.m.max_speed && vpre[0] <= k.m.max_speed) mvx[q] |= 1u << i;
+                if (vpre[1] >= -k.m.max_speed && vpre[1] <= k.m.max_speed) mvy[q] |= 1u << i;
+                if (apre[0] >= -k.m.max_accel && apre[0] <= k.m.max_accel) max_[q] |= 1u << i;
+                if (apre[1] >= -k.m.max_accel && apre[1] <= k.m.max_accel) may_[q] |= 1u << i;
+              }
+            }
+          }
+#pragma unroll
+          for (int i = SEG - 1; i >= 0; --i) {
+            const int t = sg * SEG + i;
+            if (t < k.H) {
+              const float ax = arow[2 * t], ay = arow[2 * t + 1];
+              float gx = 0.f, gy = 0.f;   // this row's gradient contributions, draw after draw (the order of the scalar loop)
+#pragma unroll
+              for (int q = 0; q < Q; ++q) {
+                const bool crashed = (cbit[q] >> i) & 1u;
+                const float kk = (k.m.can_crash && crashed) ? 0.f : k.m.dt;
+                const float gvx = ((mvx[q] >> i) & 1u) ? lam[q][2] : 0.f;
+                const float gvy = ((mvy[q] >> i) & 1u) ? lam[q][3] : 0.f;
+                const float gax = (((max_[q] >> i) & 1u) ? kk * gvx * rmass[q] : 0.f) + 2.0f * k.m.w_ctrl[0] * ax;
+                const float gay = (((may_[q] >> i) & 1u) ? kk * gvy * rmass[q] : 0.f) + 2.0f * k.m.w_ctrl[1] * ay;
+                gx += cq[q] * gax;
+                gy += cq[q] * gay;
+                const float l0 = lam[q][0] + 2.0f * k.m.w_state[0] * (xs[q][i][0] - k.m.target[0]);
+                const float l1 = lam[q][1] + 2.0f * k.m.w_state[1] * (xs[q][i][1] - k.m.target[1]);
+                const float l2 = gvx + kk * lam[q][0] + 2.0f * k.m.w_state[2] * (xs[q][i][2] - k.m.target[2]);
+                const float l3 = gvy + kk * lam[q][1] + 2.0f * k.m.w_state[3] * (xs[q][i][3] - k.m.target[3]);
+                lam[q][0] = l0; lam[q][1] = l1; lam[q][2] = l2; lam[q][3] = l3;
+              }
+              grow[2 * t] += gx;
+              grow[2 * t + 1] += gy;
+            }
+          }
         }
       }
     }

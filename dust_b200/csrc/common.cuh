@@ -57,6 +57,7 @@ struct ModelParams {
   float target[4], w_state[4], w_term[4], w_ctrl[2];
   float w_obs, inv_cell, c_offset[2];
   int grid_nx, grid_ny, can_crash, with_obstacle;
+  float grid_xmax, grid_ymax;   // (float)(grid_nx - 1), (float)(grid_ny - 1): the clamp bounds of the cell lookup
   const uint32_t* grid_bits;
 };
 
@@ -70,6 +71,7 @@ inline ModelParams to_params(const dust_model_desc& d) {
   m.w_ctrl[0] = d.w_ctrl[0]; m.w_ctrl[1] = d.w_ctrl[1];
   m.w_obs = d.w_obs; m.inv_cell = d.inv_cell; m.c_offset[0] = d.c_offset[0]; m.c_offset[1] = d.c_offset[1];
   m.grid_nx = d.grid_nx; m.grid_ny = d.grid_ny; m.can_crash = d.can_crash; m.with_obstacle = d.with_obstacle;
+  m.grid_xmax = (float)(d.grid_nx - 1); m.grid_ymax = (float)(d.grid_ny - 1);
   m.grid_bits = d.grid_bits;
   return m;
 }

@@ -229,8 +229,8 @@ __device__ __forceinline__ void pendulum_step_pair(const ModelParams& m, const P
 __device__ __forceinline__ float grid_lookup(const ModelParams& m, const uint32_t* __restrict__ bits, float x, float y) {
   float fx = floorf(x * m.inv_cell + m.c_offset[0]);
   float fy = floorf(y * m.inv_cell + m.c_offset[1]);
-  fx = fminf(fmaxf(fx, 0.0f), (float)(m.grid_nx - 1));
-  fy = fminf(fmaxf(fy, 0.0f), (float)(m.grid_ny - 1));
+  fx = fminf(fmaxf(fx, 0.0f), m.grid_xmax);
+  fy = fminf(fmaxf(fy, 0.0f), m.grid_ymax);
   const int cell = (int)fx * m.grid_ny + (int)fy;
   return (float)((bits[cell >> 5] >> (cell & 31)) & 1u);
 }
@@ -241,9 +241,11 @@ struct ParticleState {
 
 // c: occupancy (0/1) of the CURRENT cell (shared by the step and the instantaneous cost)
 __device__ __forceinline__ void particle_step(const ModelParams& m, ParticleState& s, float ax, float ay, float mass,
-                                              float c, float* vpre = nullptr) {
-  const float ux = fminf(fmaxf(ax / mass, -m.max_accel), m.max_accel);
-  const float uy = fminf(fmaxf(ay / mass, -m.max_accel), m.max_accel);
+                                              float c, float* vpre = nullptr, float* apre = nullptr) {
+  const float qx = ax / mass, qy = ay / mass;
+  if (apre) { apre[0] = qx; apre[1] = qy; }   // pre-clamp accelerations (the adjoint needs the masks)
+  const float ux = fminf(fmaxf(qx, -m.max_accel), m.max_accel);
+  const float uy = fminf(fmaxf(qy, -m.max_accel), m.max_accel);
   float nx, ny, nvx, nvy;
   if (m.can_crash) {
     const float k = 1.0f - c;
