@@ -15,7 +15,7 @@ OK, ERR_INVALID_ARG, ERR_UNSUPPORTED, ERR_WORKSPACE, ERR_CUDA = 0, -1, -2, -3, -
 MODEL_PENDULUM, MODEL_PARTICLE = 0, 1
 PARAMS_BLOCKED, PARAMS_INTERLEAVED = 0, 1
 LIK_EXP_UTILITY, LIK_EXPECTED_COST = 0, 1
-ROLL_REPEAT, ROLL_MEAN = 0, 1
+ROLL_REPEAT, ROLL_MEAN, ROLL_RESAMPLE = 0, 1, 2
 SELECT_ARGMAX, SELECT_AVERAGE = 0, 1
 
 _f, _i, _p, _sz = C.c_float, C.c_int32, C.c_void_p, C.c_size_t
@@ -91,6 +91,7 @@ class SvmpcForwardArgs(C.Structure):
         ("B", _i), ("N", _i), ("H", _i), ("A", _i), ("roll_strategy", _i), ("weighted_prior", _i),
         ("log_lik", _p), ("theta", _p), ("mu", _p), ("mix", _p), ("inv_var", _p), ("log_norm", _f),
         ("p_weights", _p), ("i_star", _p), ("a_seq", _p), ("theta_next", _p), ("mix_next", _p),
+        ("resample_noise", _p),
     ]
 
 

@@ -217,6 +217,7 @@ struct FwdKParams {
   float* p_weights;
   int* i_star;
   float *a_seq, *theta_next, *mix_next;
+  const float* resample_noise;
 };
 
 constexpr int kFwdWarps = 4;
@@ -286,6 +287,19 @@ __global__ void __launch_bounds__(kFwdWarps * 32) svmpc_forward_kernel(const Fwd
         v = theta[(long long)n * k.D + d + k.A];  // theta.roll(-1, dims=-2)
       } else if (k.roll == DUST_ROLL_REPEAT) {
         v = theta[(long long)n * k.D + d];        // last step repeated (svmpc.py:145-147)
+      } else if (k.roll == DUST_ROLL_RESAMPLE) {
+        // last step of a sample of the current prior (svmpc.py:148-150): component by inverse CDF
+        // over the (clamped, normalised) mixture weights, then centre + sigma_prior * z
+        const int a = d - HA_shift;
+        const float* z = k.resample_noise + (inst * k.N + n) * (long long)(k.A + 1);
+        const float u = 0.5f * erfcf(-z[k.A] * 0.70710678118654752f);
+        int comp = k.N - 1;
+        float cum = 0.f;
+        for (int c = 0; c < k.N; ++c) {
+          cum += expf(logmix[c]);
+          if (u <= cum) { comp = c; break; }
+        }
+        v = mu[(long long)comp * k.D + d] + rsqrtf(k.inv_var[d]) * z[a];
       } else {
         const int a = d - HA_shift;               // mean over the horizon (svmpc.py:151-153)
         float s = 0.f;
@@ -436,14 +450,16 @@ extern "C" int dust_svmpc_forward(const dust_svmpc_forward_args* a, void* stream
   DUST_REQUIRE(a->log_lik && a->theta && a->mu && a->inv_var && a->p_weights, DUST_ERR_INVALID_ARG,
                "dust_svmpc_forward: log_lik, theta, mu, inv_var, p_weights are required");
   DUST_REQUIRE(a->theta_next != a->theta, DUST_ERR_INVALID_ARG, "dust_svmpc_forward: theta_next must not alias theta");
-  DUST_REQUIRE(a->roll_strategy == DUST_ROLL_REPEAT || a->roll_strategy == DUST_ROLL_MEAN, DUST_ERR_INVALID_ARG,
+  DUST_REQUIRE(a->roll_strategy != DUST_ROLL_RESAMPLE || a->resample_noise != nullptr, DUST_ERR_INVALID_ARG,
+               "dust_svmpc_forward: roll strategy 'resample' needs resample_noise [B,N,A+1]");
+  DUST_REQUIRE(a->roll_strategy == DUST_ROLL_REPEAT || a->roll_strategy == DUST_ROLL_MEAN || a->roll_strategy == DUST_ROLL_RESAMPLE, DUST_ERR_INVALID_ARG,
                "dust_svmpc_forward: invalid roll strategy %d", a->roll_strategy);
   const int D = a->H * a->A;
   DUST_REQUIRE(D <= 32 * kMaxDPerLane, DUST_ERR_UNSUPPORTED, "dust_svmpc_forward: H*A=%d > %d", D, 32 * kMaxDPerLane);
   const size_t smem = sizeof(float) * a->N * (2 + kFwdWarps);
   DUST_REQUIRE(smem <= 48 * 1024, DUST_ERR_UNSUPPORTED, "dust_svmpc_forward: N=%d too large", a->N);
   FwdKParams k{a->B, a->N, a->H, a->A, D, a->roll_strategy, a->weighted_prior, a->log_lik, a->theta, a->mu, a->mix,
-               a->inv_var, a->log_norm, a->p_weights, a->i_star, a->a_seq, a->theta_next, a->mix_next};
+               a->inv_var, a->log_norm, a->p_weights, a->i_star, a->a_seq, a->theta_next, a->mix_next, a->resample_noise};
   { DUST_TIMED("svmpc_forward_kernel", (cudaStream_t)stream_); svmpc_forward_kernel<<<a->B, kFwdWarps * 32, smem, (cudaStream_t)stream_>>>(k); }
   DUST_LAUNCH_OK("svmpc_forward_kernel");
   return DUST_OK;

@@ -19,7 +19,7 @@ class SvmpcCore:
     def __init__(self, spec, theta, mu, mix, prior_var, sigma, alpha=1.0, temperature=1.0, lr=1.0,
                  kernel="gpytorch", lengthscale=GPYTORCH_DEFAULT_LENGTHSCALE, bw_scale=1.0,
                  likelihood=L.LIK_EXP_UTILITY, grad="analytic", roll_strategy="repeat", weighted_prior=False,
-                 aliased=False):
+                 aliased=False, seed=0):
         """theta, mu [B,N,H,A]; mix [B,N]; prior_var [A] (diagonal, shared by all components);
         sigma [A]."""
         self.spec = spec
@@ -37,11 +37,11 @@ class SvmpcCore:
         if grad not in ("analytic", "pathwise"):
             raise ValueError(grad)
         self.grad = grad
-        if roll_strategy not in ("repeat", "mean"):
-            if roll_strategy == "resample":
-                raise NotImplementedError("roll_strategy='resample' (device RNG) is not available yet")
+        if roll_strategy not in ("repeat", "mean", "resample"):
             raise ValueError("{} is an invalid roll strategy.".format(roll_strategy))
-        self.roll_strategy = L.ROLL_REPEAT if roll_strategy == "repeat" else L.ROLL_MEAN
+        self.roll_strategy = {"repeat": L.ROLL_REPEAT, "mean": L.ROLL_MEAN, "resample": L.ROLL_RESAMPLE}[roll_strategy]
+        # 'resample' draws the new last action from the prior with the library's generator
+        self.seed, self.resample_draws = int(seed), 0
         self.weighted_prior = bool(weighted_prior)
         self.aliased = bool(aliased)
         self.last = {}
@@ -96,7 +96,8 @@ class SvmpcCore:
         """optimize_step + forward_step.  One kernel launch when the shape qualifies for the fused
         instance kernel (B >= 74, H*A <= 32, analytic gradient, fixed-lengthscale kernel), else the
         staged sequence.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])"""
-        if self.kernel == "gpytorch" and self.grad == "analytic" and getattr(self, "_fused_ok", True):
+        if (self.kernel == "gpytorch" and self.grad == "analytic" and self.roll_strategy != L.ROLL_RESAMPLE
+                and getattr(self, "_fused_ok", True)):
             ell2 = self.lengthscale ** 2
             want = ("costs", "log_lik", "theta_out") + (("phi",) if want_phi else ())
             try:
@@ -116,12 +117,22 @@ class SvmpcCore:
         self.optimize_step(state0, eps, params, tiling)
         return self.forward_step()
 
+    def draw_resample_noise(self):
+        """[B,N,A+1] standard normals for roll strategy 'resample' (stream 2^62 + draw index: disjoint
+        from the action-noise streams of the batched controller)."""
+        buf = torch.empty(self.B, self.N, self.A + 1, device=self.theta.device)
+        ops.noise_normal(buf, self.seed, (1 << 62) + self.resample_draws)
+        self.resample_draws += 1
+        return buf
+
     def forward_step(self, log_lik=None):
         """Weights, best particle, shift, prior refresh.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])."""
         log_lik = self.last["log_lik"] if log_lik is None else log_lik
         mu = self.theta if self.aliased else self.mu
+        noise = None if self.roll_strategy != L.ROLL_RESAMPLE else self.draw_resample_noise()
         out = ops.svmpc_forward(log_lik, self.theta, mu, self.mix, self.inv_var, self.log_norm,
-                                roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior)
+                                roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior,
+                                resample_noise=noise)
         self.theta = out["theta_next"]
         self.mu = self.theta
         self.mix = out["mix_next"]

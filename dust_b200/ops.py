@@ -228,7 +228,8 @@ def bandwidth_from_median(median, N, scale=1.0, mode=0):
     return out
 
 
-def svmpc_forward(log_lik, theta, mu, mix, inv_var, log_norm, roll_strategy=L.ROLL_REPEAT, weighted_prior=False):
+def svmpc_forward(log_lik, theta, mu, mix, inv_var, log_norm, roll_strategy=L.ROLL_REPEAT, weighted_prior=False,
+                  resample_noise=None):
     """K7.  theta, mu [B,N,H,A].  Returns dict(p_weights, i_star, a_seq, theta_next, mix_next)."""
     L.require_cuda()
     B, N, H, A = theta.shape
@@ -242,7 +243,8 @@ def svmpc_forward(log_lik, theta, mu, mix, inv_var, log_norm, roll_strategy=L.RO
     )
     a = L.SvmpcForwardArgs(B, N, H, A, int(roll_strategy), int(bool(weighted_prior)), L.ptr(log_lik), L.ptr(theta),
                            L.ptr(mu), L.ptr(mix), L.ptr(inv_var), float(log_norm), L.ptr(out["p_weights"]),
-                           L.ptr(out["i_star"]), L.ptr(out["a_seq"]), L.ptr(out["theta_next"]), L.ptr(out["mix_next"]))
+                           L.ptr(out["i_star"]), L.ptr(out["a_seq"]), L.ptr(out["theta_next"]), L.ptr(out["mix_next"]),
+                           L.ptr(resample_noise))
     L.call("dust_svmpc_forward", C.byref(a), L.stream())
     return out
 

@@ -54,7 +54,7 @@ typedef enum dust_param_tiling { DUST_PARAMS_BLOCKED = 0, DUST_PARAMS_INTERLEAVE
 typedef enum dust_likelihood_kind { DUST_LIK_EXP_UTILITY = 0, DUST_LIK_EXPECTED_COST = 1 } dust_likelihood_kind;
 
 /* dust/inference/svmpc.py:142-158 */
-typedef enum dust_roll_strategy { DUST_ROLL_REPEAT = 0, DUST_ROLL_MEAN = 1 } dust_roll_strategy;
+typedef enum dust_roll_strategy { DUST_ROLL_REPEAT = 0, DUST_ROLL_MEAN = 1, DUST_ROLL_RESAMPLE = 2 } dust_roll_strategy;
 
 /* dust/controllers/disco.py:396-417 */
 typedef enum dust_select_strategy { DUST_SELECT_ARGMAX = 0, DUST_SELECT_AVERAGE = 1 } dust_select_strategy;
@@ -315,6 +315,10 @@ typedef struct dust_svmpc_forward_args {
   float* a_seq;              /* [B, H, A]                                              */
   float* theta_next;         /* [B, N, H, A] rolled particles (must not alias theta)   */
   float* mix_next;           /* [B, N]                                                 */
+  const float* resample_noise; /* [B, N, A+1] standard normals (dust_noise_normal), required for
+                              * DUST_ROLL_RESAMPLE (svmpc.py:148-150: the new last action of particle n is
+                              * the last step of a draw from the CURRENT prior): columns 0..A-1 perturb
+                              * the chosen centre, column A picks the component (through the normal CDF) */
 } dust_svmpc_forward_args;
 
 int dust_svmpc_forward(const dust_svmpc_forward_args* args, void* stream);

@@ -628,3 +628,57 @@ def test_noise_generator_matches_philox_and_is_normal(env):
         assert abs(float((z[:-lag] * z[lag:]).mean())) < 5 / math.sqrt(n)
     z2 = ops.noise_normal(torch.empty(n, device=DEV), 42, 1).double()
     assert abs(float((z * z2).mean())) < 5 / math.sqrt(n)
+
+
+def test_roll_strategy_resample(env):
+    """svmpc.py:148-150: the new last action is the last step of a sample of the current prior.  With
+    the noise buffer given, the kernel's choice is a deterministic function of it (checked against a
+    host restatement); over many draws the components follow the mixture weights (H22 clamp included)."""
+    from dust_b200 import ops
+
+    L = env["L"]
+    torch.manual_seed(5)
+    B, N, H, A = 3, 6, 7, 2
+    D = H * A
+    theta, mu = torch.randn(B, N, H, A), torch.randn(B, N, H, A) * 3
+    mix = torch.rand(B, N) + 0.05
+    mix[1, 2] = 0.0                       # a zero weight is clamped to float eps, practically never drawn
+    var = torch.tensor([4.0, 0.25]).repeat(H)
+    noise = torch.randn(B, N, A + 1)
+    out = ops.svmpc_forward(cu(torch.zeros(B, N)), cu(theta), cu(mu), cu(mix), cu(1.0 / var), 0.0,
+                            roll_strategy=L.ROLL_RESAMPLE, resample_noise=cu(noise))
+    nxt = out["theta_next"].cpu()
+    assert torch.equal(nxt[:, :, :-1], theta[:, :, 1:])      # shifted along time
+    pm = (mix / mix.sum(1, keepdim=True)).clamp(1.19209290e-07, 1 - 1.19209290e-07)
+    pm = pm / pm.sum(1, keepdim=True)
+    u = 0.5 * torch.erfc(-noise[..., A].double() / math.sqrt(2.0))
+    cdf = pm.double().cumsum(1)
+    for b in range(B):
+        for n in range(N):
+            comp = min(int((cdf[b] < u[b, n]).sum()), N - 1)
+            exp = mu[b, comp, -1] + var[-A:].sqrt() * noise[b, n, :A]
+            assert rel_max(nxt[b, n, -1], exp) <= 1e-6, (b, n, comp)
+    with pytest.raises(Exception):
+        ops.svmpc_forward(cu(torch.zeros(B, N)), cu(theta), cu(mu), cu(mix), cu(1.0 / var), 0.0,
+                          roll_strategy=L.ROLL_RESAMPLE)
+    # distribution of the chosen component over many instances, identical centres per component
+    Bn = 4096
+    mu2 = torch.arange(N, dtype=torch.float32).reshape(1, N, 1, 1).expand(Bn, N, H, A).contiguous() * 100.0
+    mix2 = torch.tensor([1.0, 2.0, 3.0, 0.0, 2.0, 2.0]).expand(Bn, N).contiguous()
+    nz = ops.noise_normal(torch.empty(Bn, N, A + 1, device=DEV), 3, 1)
+    o2 = ops.svmpc_forward(cu(torch.zeros(Bn, N)), cu(torch.zeros(Bn, N, H, A)), cu(mu2), cu(mix2), cu(1.0 / var), 0.0,
+                           roll_strategy=L.ROLL_RESAMPLE, resample_noise=nz)
+    comp = (o2["theta_next"][:, :, -1, 1] / 100.0).round().long().clamp(0, N - 1).flatten().cpu()   # sigma 0.5 on column 1
+    freq = torch.bincount(comp, minlength=N).double() / comp.numel()
+    assert float((freq - mix2[0].double() / 10.0).abs().max()) < 0.01
+    # the reference-shaped core draws its own noise and stays reproducible
+    from dust_b200.inference.core import SvmpcCore
+    mk = lambda: SvmpcCore(env["spec"]["particle"], cu(theta), cu(mu), cu(mix), torch.tensor([4.0, 0.25]), torch.ones(A),
+                           roll_strategy="resample", seed=11)
+    c1, c2 = mk(), mk()
+    ll = cu(torch.zeros(B, N))
+    c1.forward_step(ll); c2.forward_step(ll)
+    assert torch.equal(c1.theta, c2.theta)
+    first = c1.theta.clone()
+    c1.forward_step(ll)
+    assert not torch.equal(c1.theta[:, :, -1], first[:, :, -1])
