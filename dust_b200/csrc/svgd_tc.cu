@@ -555,6 +555,7 @@ __global__ void med_sample_select_kernel(unsigned int* hist32, uint32_t* state) 
 
 struct MedTcParams {
   int N, Dp, T, row_begin, ksplit;
+  int kcount, kchunk;                // circular half band: T/2 + 1 column tiles per row tile, kchunk of them per CTA
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *xn;
   const uint32_t* state;             // [0] window start
   unsigned long long* hist;          // [kMedWindowBins] window histogram, then [kMedWindowBins] = count below
@@ -576,8 +577,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bars + 64 * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = p.row_begin + (blockIdx.x / p.ksplit) * kTcBM;
-  const int T = p.T / p.ksplit;
-  const int jbase = (blockIdx.x % p.ksplit) * T;
+  // d2 is symmetric: in units of 128-point blocks (Tb = N/128 of them; a block is one row tile and
+  // kBlk = 2 column tiles), row block i visits the circular half band of column blocks i, i+1, ...,
+  // i+Tb/2 (mod Tb).  Every unordered block pair is met exactly once -- except the diagonal (offset 0)
+  // and, for even Tb, the opposite block (offset Tb/2), which both of its rows meet -- so those two
+  // count once and every other block twice.  All row tiles carry the same work, whatever row block
+  // a rank owns.  p.kcount = kBlk * (Tb/2 + 1) column tiles per row tile, p.kchunk of them per CTA.
+  constexpr int kBlk = kTcBM / kTcBN;
+  const int itile = i0 / kTcBM;
+  const int Tb = p.T / kBlk;
+  const int kbase = (blockIdx.x % p.ksplit) * p.kchunk;
+  const int T = max(0, min(p.kchunk, p.kcount - kbase));   // column tiles of this CTA
+  auto col_tile = [&](int j) { return (kBlk * itile + kbase + j) % p.T; };
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[MB_A], 1);
@@ -599,7 +610,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && T > 0) {
       const long long arow = (long long)(i0 / kTcBM) * kTcBM * p.Dp;
       mbar_expect_tx(&bars[MB_A], 2 * a_bytes);
       bulk_g2s(smem + off_a_hi, p.xa_hi + arow, a_bytes, &bars[MB_A]);
@@ -609,11 +620,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
         mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / kMedXbStages) & 1) ^ 1);
         unsigned char* xb = smem + off_xb + sx * xb_stage;
         mbar_expect_tx(&bars[MB_XB_FULL + sx], xb_stage);
-        bulk_g2s(xb, p.xb_hi + (long long)(jbase + j) * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
-        bulk_g2s(xb + xb_half, p.xb_lo + (long long)(jbase + j) * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
+        const long long jt = col_tile(j);
+        bulk_g2s(xb, p.xb_hi + jt * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
+        bulk_g2s(xb + xb_half, p.xb_lo + jt * kTcBN * p.Dp, xb_half, &bars[MB_XB_FULL + sx]);
         mbar_wait(&bars[MB_XN_EMPTY + sn], ((j / kXnStages) & 1) ^ 1);
         mbar_expect_tx(&bars[MB_XN_FULL + sn], kTcBN * 4);
-        bulk_g2s(smem + off_xn + sn * kTcBN * 4, p.xn + (long long)(jbase + j) * kTcBN, kTcBN * 4, &bars[MB_XN_FULL + sn]);
+        bulk_g2s(smem + off_xn + sn * kTcBN * 4, p.xn + jt * kTcBN, kTcBN * 4, &bars[MB_XN_FULL + sn]);
       }
     }
   } else if (warp == 1) {
@@ -625,7 +637,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       const uint32_t hiA = (uint32_t)(dA >> 32);
       const uint32_t loA_hi = (uint32_t)dA, loA_lo = loA_hi + (a_bytes >> 4), loX0 = (uint32_t)dX;
       const uint32_t xb_stage16 = xb_stage >> 4, xb_half16 = xb_half >> 4;
-      mbar_wait(&bars[MB_A], 0);
+      if (T > 0) mbar_wait(&bars[MB_A], 0);
       for (int j = 0; j < T; ++j) {
         const int b = j % kMedSBufs, sx = j % kMedXbStages;
         mbar_wait(&bars[MB_XB_FULL + sx], (j / kMedXbStages) & 1);
@@ -666,7 +678,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       mbar_wait(&bars[MB_XN_FULL + sn], (j / kXnStages) & 1);
       mbar_wait(&bars[MB_S_FULL + b], (j / kMedSBufs) & 1);
       tc_fence_after();
-      const int cdiag = (jbase + j == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
+      const int kb = (kbase + j) / kBlk;   // block offset inside the band
+      const int cdiag = (col_tile(j) == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
+      const uint32_t wgt = (kb == 0 || 2 * kb == Tb) ? 1u : 2u;
+      const unsigned long long wgt64 = wgt;
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
@@ -684,12 +699,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
           const float s = __uint_as_float(r[c]);
           const float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
           const uint32_t rel = __float_as_uint(d2) - win_lo;   // wraps (top bit set) iff below the window
-          below += rel >> 31;
+          below += (rel >> 31) * wgt;
           asm volatile(
               "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
               "setp.lt.u32 p, %1, %2;\n\t"
               "mad.wide.u32 a, %1, 8, %0;\n\t"
-              "@p red.global.add.u64 [a], 1;\n\t}" ::"l"(p.hist), "r"(rel), "r"(win_n));
+              "@p red.global.add.u64 [a], %3;\n\t}" ::"l"(p.hist), "r"(rel), "r"(win_n), "l"(wgt64));
         }
       }
       tc_fence_before();
@@ -801,8 +816,17 @@ int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t str
   float* xb_lo = ws;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
   const int row_tiles = (r1 - r0) / kTcBM;
-  const int ksplit = choose_ksplit(row_tiles, N / kTcBN);
-  MedTcParams p{N, Dp, N / kTcBN, r0, ksplit, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
+  // half band of (N/128)/2 + 1 column blocks (two 64-wide tiles each) per row tile, cut into ksplit chunks
+  const int T = N / kTcBN, kcount = (kTcBM / kTcBN) * ((N / kTcBM) / 2 + 1);
+  int ksplit = 1, kchunk = kcount;
+  double best_cost = 1e30;
+  for (int ks = 1; ks <= 8 && ks <= kcount; ++ks) {
+    const int chunk = ceil_div(kcount, ks);
+    if ((ks - 1) * chunk >= kcount) continue;   // would leave a CTA without tiles
+    const double cost = (double)ceil_div((long long)row_tiles * ks, kNumSMs) * (chunk + 1.5);  // + per-CTA prologue
+    if (cost < best_cost - 1e-9) { best_cost = cost; ksplit = ks; kchunk = chunk; }
+  }
+  MedTcParams p{N, Dp, T, r0, ksplit, kcount, kchunk, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
   const size_t smem = med_smem_bytes(Dp);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
