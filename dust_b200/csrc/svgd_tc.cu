@@ -506,10 +506,24 @@ __global__ void med_sample_kernel(const float* __restrict__ x, const float* __re
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= kMedSample) return;
   const uint32_t i = hash32(2u * k + 1u) % (uint32_t)N, j = hash32(2u * k + 0x9e3779b9u) % (uint32_t)N;
+  const float* __restrict__ xi = x + (long long)i * D;
+  const float* __restrict__ xj = x + (long long)j * D;
   float dot = 0.f;
-  for (int d = 0; d < D; ++d) dot = fmaf(x[(long long)i * D + d], x[(long long)j * D + d], dot);
+  if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0)) {   // rows are 16-byte aligned: independent 128-bit loads
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int d = 0; d < D; d += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(xi + d)), b = __ldg(reinterpret_cast<const float4*>(xj + d));
+      acc.x = fmaf(a.x, b.x, acc.x); acc.y = fmaf(a.y, b.y, acc.y); acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);
+    }
+    dot = (acc.x + acc.y) + (acc.z + acc.w);
+  } else {
+    for (int d = 0; d < D; ++d) dot = fmaf(xi[d], xj[d], dot);
+  }
   const float d2 = (i == j) ? 0.f : fmaxf((xn[j] - 2.0f * dot) + xn[i], 0.f);
-  atomicAdd(&hist32[__float_as_uint(d2) >> 16], 1u);
+  // the sample lands in a handful of bins: one atomic per distinct bin per warp, not one per thread
+  const uint32_t bin = __float_as_uint(d2) >> 16;
+  const uint32_t peers = __match_any_sync(__activemask(), bin);
+  if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist32[bin], (unsigned int)__popc(peers));
 }
 
 // state[0] = window start (bit pattern), state[1] = ok flag (cleared here), state[2] = window width.

@@ -4,6 +4,7 @@ import math
 import torch
 
 from .. import _lib as L
+from .. import ops
 
 
 class GaussianLikelihood:
@@ -56,6 +57,22 @@ class CostLikelihood:
         self.controller = controller
         self.model = model
         self._last = {}
+        # action noise: the library's counter-based generator (one Philox stream per draw), keyed by
+        # torch's seed at construction so that torch.manual_seed still fixes a run.  `noise_fn(shape)`,
+        # if set, supplies the standard-normal tensor instead (replay of recorded draws).
+        self.noise_fn = None
+        self._noise_seed = int(torch.initial_seed()) & (2 ** 63 - 1)
+        self._noise_draws = 0
+
+    def draw_noise(self, shape):
+        """Standard-normal action noise [S,N,H,A] on the controller's device (the rsample draw of
+        likelihoods.py:90)."""
+        dev = self.controller.device
+        if self.noise_fn is not None:
+            return torch.as_tensor(self.noise_fn(tuple(shape)), dtype=torch.float32).to(dev).contiguous()
+        eps = ops.noise_normal(torch.empty(tuple(shape), device=dev), self._noise_seed, (1 << 61) + self._noise_draws)
+        self._noise_draws += 1
+        return eps
 
     def sample(self, theta, state, params_dist, eps=None, want=("costs", "log_lik", "lik_weights", "grad_lik")):
         """likelihoods.py:81-101: actions = theta + L eps (rsample), rollouts, costs.  `eps`
@@ -64,7 +81,7 @@ class CostLikelihood:
         dev = ctrl.device
         theta = torch.as_tensor(theta, dtype=torch.float32).to(dev).contiguous()
         if eps is None:
-            eps = torch.randn((self.n_samples,) + tuple(theta.shape), device=dev)
+            eps = self.draw_noise((self.n_samples,) + tuple(theta.shape))
         else:
             eps = torch.as_tensor(eps, dtype=torch.float32).to(dev).contiguous()
         res = ctrl.evaluate(state, self.model, params_dist, eps, theta=theta, want=want, likelihood=self.kind,

@@ -82,7 +82,7 @@ class SVMPC(SVGD):
     def _evaluate(self, state, params_dist, eps=None):
         ctrl, lik, c = self.likelihood.controller, self.likelihood, self._core
         if eps is None:
-            eps = torch.randn((lik.n_samples, c.N, c.H, c.A), device=self.device)
+            eps = lik.draw_noise((lik.n_samples, c.N, c.H, c.A))
         else:
             eps = torch.as_tensor(eps, dtype=torch.float32).to(self.device).contiguous()
         params, tiling, params_log_p = ctrl._sample_params(lik.model, params_dist)

@@ -579,14 +579,50 @@ def gen_pathwise():
              sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt())
 
 
+# ----------------------------------------------------------------------------------
+# G8: a whole episode through the reference's own driver (dust/utils/simulations.py:197-260)
+# ----------------------------------------------------------------------------------
+def gen_episode():
+    print("G8 run_particle_episode (reference driver)")
+    sims = ref_import("utils.simulations")
+    w = make_particle(3, kernel="mp", n_pol=4, S=32, H=20, P=2)
+    sv, model, ctrl = w["svmpc"], w["model"], w["ctrl"]
+    theta0, mu0 = sv.theta.detach().clone(), prior_mu(sv.prior)
+    dyn = RecordingDist(w["dyn"])
+    plant_states = []
+    orig_cost = ctrl.inst_cost_fn
+
+    def spy_cost(states, *a, **k):   # the driver evaluates the cost of every new plant state (simulations.py:237)
+        if states.ndim == 2 and states.shape[0] == 1 and not a and not k:
+            plant_states.append(states.detach().clone().view(-1))
+        return orig_cost(states, *a, **k)
+
+    ctrl._BaseController__inst_cost_fn = spy_cost   # read-only property over a name-mangled attribute (controllers/base.py:54-62)
+    steps, warm_up, load = 8, 2, 1.0
+    with NoiseRecorder() as rec:
+        cum = sims.run_particle_episode(w["state"].clone(), model, dyn, ctrl, use_svmpc=True, warm_up=warm_up,
+                                        svmpc=sv, load=load, steps=steps)
+    eps = [d for d in rec.draws if d.ndim == 4]
+    assert len(eps) == steps and len(plant_states) == steps, (len(eps), len(plant_states))
+    save("episode_particle_mp", tags=["shim-dependent:KDEpy(dead value)"],
+         sigma=ctrl.a_dist.covariance_matrix.diag().sqrt(), theta0=theta0, mu0=mu0, init_state=w["state"],
+         eps=torch.stack(eps), params=torch.stack([x.reshape(-1) for x in dyn.samples]),
+         plant_states=torch.stack(plant_states), cum_cost=np.array(float(cum)), theta_end=sv.theta.detach().clone(),
+         steps=np.array(steps), warm_up=np.array(warm_up), load=np.array(load),
+         n_param_draws=np.array(len(dyn.samples)))
+
+
+GENERATORS = dict(map=gen_map, forward=gen_forward_all, svmpc=gen_svmpc, dual=gen_dual, mpf=gen_mpf, phi=gen_phi,
+                  pathwise=gen_pathwise, episode=gen_episode)
+
 if __name__ == "__main__":
-    gen_map()
-    gen_forward_all()
-    gen_svmpc()
-    gen_dual()
-    gen_mpf()
-    gen_phi()
-    gen_pathwise()
+    # no arguments: everything; otherwise only the named groups, merged into the existing manifest
+    picked = sys.argv[1:] or list(GENERATORS)
+    mpath = os.path.join(HERE, "MANIFEST.json")
+    if sys.argv[1:] and os.path.isfile(mpath):
+        MANIFEST.update(json.load(open(mpath))["fixtures"])
+    for g in picked:
+        GENERATORS[g]()
     with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
         json.dump({"generator": "tests/golden/make_golden.py", "torch": torch.__version__,
                    "fixtures": MANIFEST}, f, indent=1, sort_keys=True)
