@@ -194,3 +194,35 @@ def test_adjoint_parameter_gradient_matches_autograd():
     gp = O.pathwise_lik_grad_adjoint(model, d["state"], d["theta"], d["eps"], d["sigma"],
                                      d["params"], False, 1.0, want_param_grad=True)[3]
     assert rel_max(gp, gp_auto) < 1e-9
+
+
+def test_particle_episode_against_reference_driver(cfg):
+    """The oracle's control step closed into the loop of dust/utils/simulations.py:197-260 (optimize every
+    step, zero action during warm-up, forward afterwards, plant = model step with the load added at
+    steps//4), replayed on the noise and parameter draws of an episode run by the reference's own
+    driver."""
+    d = load("episode_particle_mp")
+    model = O.Model("particle", cfg)
+    c = HYPER["particle"]
+    st = O.SvmpcState(d["theta0"].clone(), d["mu0"].clone(), torch.ones(d["theta0"].shape[0]), c["var"])
+    state = d["init_state"].clone()
+    steps, warm_up, load_ = int(d["steps"]), int(d["warm_up"]), float(d["load"])
+    mass, cum, errs = 2.0, 0.0, []
+    for step in range(steps):
+        if step == steps // 4:
+            mass = mass + load_
+        out = O.svmpc_optimize(model, st, state, d["eps"][step], d["sigma"], d["params"][step], c["log"], c["alpha"],
+                               c["lr"], kernel="mp")
+        if step < warm_up:
+            action = torch.zeros(2)
+        else:
+            a_seq, _, _ = O.svmpc_forward(st, out["costs"], c["alpha"], c["wp"])
+            action = a_seq[0]
+        state = O.particle_step(cfg, state.view(1, -1), action.view(1, -1), mass).view(-1)
+        cum += float(O.particle_inst_cost(cfg, state.view(1, -1), torch.zeros(1, 2)))
+        errs.append(rel_max(state, d["plant_states"][step]))
+    # ulp-level differences in phi are amplified by the free-running loop (lr = 100, peaked weights),
+    # roughly doubling per step: exact through the warm-up, a few 1e-7 on the first controlled steps
+    assert errs[0] == 0.0 and errs[1] == 0.0, errs
+    assert max(errs[:5]) <= 2e-6 and max(errs) <= 2e-3, errs
+    assert abs(cum - float(d["cum_cost"])) <= 1e-3 * float(d["cum_cost"])
