@@ -10,7 +10,7 @@
 
 namespace dust {
 
-constexpr int kMpfThreads = 256;
+constexpr int kMpfMaxThreads = 1024;
 constexpr int kMaxDp = 2;
 
 struct MpfKParams {
@@ -63,7 +63,7 @@ __device__ __forceinline__ void mpf_lik_grad(const ModelParams& m, const float* 
 }
 
 template <int MODEL>
-__global__ void __launch_bounds__(kMpfThreads) mpf_kernel(const MpfKParams k) {
+__global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k) {
   constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
   constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
   constexpr int DA = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(kMpfThreads) mpf_kernel(const MpfKParams k) {
   float* xs = sm;                       // [Np][DP]
   float* sc = sm + k.Np * DP;           // [Np][DP] score
   float* ph = sc + k.Np * DP;           // [Np][DP] phi
-  __shared__ float red[kMpfThreads / 32];
+  __shared__ float red[kMpfMaxThreads / 32];
   __shared__ float s_cell;
   const long long inst = blockIdx.x;
   float* xg = k.x + inst * (long long)k.Np * DP;
@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(kMpfThreads) mpf_kernel(const MpfKParams k) {
   for (int i = 0; i < DA; ++i) act[i] = k.action[inst * DA + i];
 #pragma unroll
   for (int i = 0; i < DP; ++i) piv[i] = k.prior_inv_var[i];
-  for (int e = threadIdx.x; e < k.Np * DP; e += kMpfThreads) xs[e] = xg[e];
+  for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) xs[e] = xg[e];
   if (threadIdx.x == 0) {
     float c = 0.f;
     if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits) c = grid_lookup(k.m, k.m.grid_bits, o0[0], o0[1]);
@@ -93,43 +93,45 @@ __global__ void __launch_bounds__(kMpfThreads) mpf_kernel(const MpfKParams k) {
   const float inv_bw2 = 1.0f / (k.bw * k.bw);
   const float inv_np = 1.0f / (float)k.Np;
 
+  // One WARP per particle, lanes over the other particles (warp-shuffle sums): with a thread per
+  // particle the 512-particle stress shape was three serial passes of 512 exponentials per thread.
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int step = 0; step < k.n_steps; ++step) {
-    // score_i = grad log-likelihood + grad log GMM(x_i; centres = current particles)
-    for (int i = threadIdx.x; i < k.Np; i += kMpfThreads) {
+    // score_i = grad log-likelihood + grad log GMM(x_i; centres = current particles).  The centres
+    // ARE the particles (mpf.py:32-38): the j = i term has exponent 0 and every other one is <= 0,
+    // so the max shift of the log-sum-exp is exactly 0 and needs no pass of its own.
+    for (int i = warp; i < k.Np; i += nwarps) {
       float xi[DP], g[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) xi[d] = xs[i * DP + d];
       mpf_lik_grad<MODEL>(k.m, xi, k.log_space, o0, act, o1, k.inv_obs_var, c_cell, g);
-      float mx = -INFINITY;
-      for (int j = 0; j < k.Np; ++j) {
-        float q = 0.f;
-#pragma unroll
-        for (int d = 0; d < DP; ++d) { const float df = xi[d] - xs[j * DP + d]; q += df * df * piv[d]; }
-        mx = fmaxf(mx, -0.5f * q);
-      }
       float z = 0.f, acc[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) acc[d] = 0.f;
-      for (int j = 0; j < k.Np; ++j) {
+      for (int j = lane; j < k.Np; j += 32) {
         float q = 0.f;
 #pragma unroll
         for (int d = 0; d < DP; ++d) { const float df = xi[d] - xs[j * DP + d]; q += df * df * piv[d]; }
-        const float e = expf(-0.5f * q - mx);
+        const float e = expf(-0.5f * q);
         z += e;
 #pragma unroll
         for (int d = 0; d < DP; ++d) acc[d] += e * (xs[j * DP + d] - xi[d]);
       }
+      z = warp_sum(z);
 #pragma unroll
-      for (int d = 0; d < DP; ++d) sc[i * DP + d] = g[d] + acc[d] / z * piv[d];
+      for (int d = 0; d < DP; ++d) {
+        const float a_d = warp_sum(acc[d]);
+        if (lane == 0) sc[i * DP + d] = g[d] + a_d / z * piv[d];
+      }
     }
     __syncthreads();
     // phi_i = (1/Np) sum_j K_ij s_j - (1/bw^2) sum_j K_ij (x_i - x_j)     (mpf.py:53-56)
     float nrm = 0.f;
-    for (int i = threadIdx.x; i < k.Np; i += kMpfThreads) {
+    for (int i = warp; i < k.Np; i += nwarps) {
       float xi[DP], acc[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) { xi[d] = xs[i * DP + d]; acc[d] = 0.f; }
-      for (int j = 0; j < k.Np; ++j) {
+      for (int j = lane; j < k.Np; j += 32) {
         float d2 = 0.f, df[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) { df[d] = xi[d] - xs[j * DP + d]; d2 += df[d] * df[d]; }
@@ -138,20 +140,22 @@ __global__ void __launch_bounds__(kMpfThreads) mpf_kernel(const MpfKParams k) {
         for (int d = 0; d < DP; ++d) acc[d] += kij * (inv_np * sc[j * DP + d] - inv_bw2 * df[d]);
       }
 #pragma unroll
-      for (int d = 0; d < DP; ++d) { ph[i * DP + d] = acc[d]; nrm += acc[d] * acc[d]; }
+      for (int d = 0; d < DP; ++d) {
+        const float a_d = warp_sum(acc[d]);
+        if (lane == 0) { ph[i * DP + d] = a_d; nrm += a_d * a_d; }
+      }
     }
-    nrm = warp_sum(nrm);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = nrm;
+    if (lane == 0) red[warp] = nrm;
     __syncthreads();
     if (threadIdx.x == 0 && k.grad_norms) {
       float t = 0.f;
-      for (int w = 0; w < kMpfThreads / 32; ++w) t += red[w];
+      for (int w = 0; w < nwarps; ++w) t += red[w];
       k.grad_norms[inst * k.n_steps + step] = sqrtf(t);
     }
-    for (int e = threadIdx.x; e < k.Np * DP; e += kMpfThreads) xs[e] = xs[e] + k.lr * ph[e];  // SGD (mpf.py:59-62)
+    for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) xs[e] = xs[e] + k.lr * ph[e];  // SGD (mpf.py:59-62)
     __syncthreads();
   }
-  for (int e = threadIdx.x; e < k.Np * DP; e += kMpfThreads) xg[e] = xs[e];
+  for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) xg[e] = xs[e];
 }
 
 template <int MODEL>
@@ -210,6 +214,10 @@ extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   k.x = a->x; k.obs0 = a->obs0; k.action = a->action; k.obs1 = a->obs1; k.prior_inv_var = a->prior_inv_var;
   k.inv_obs_var = 1.0f / (a->obs_std * a->obs_std); k.bw = a->bw; k.lr = a->lr; k.grad_norms = a->grad_norms;
   cudaStream_t stream = (cudaStream_t)stream_;
+  // a warp per particle: as many warps as particles, up to a full CTA; fewer when many instances share the GPU
+  int kMpfThreads = 32 * (a->Np < 32 ? a->Np : 32);
+  if ((long long)a->B * kMpfThreads > (long long)kNumSMs * 2048) kMpfThreads = 256;
+  if (kMpfThreads < 64) kMpfThreads = 64;
   if (kind == DUST_MODEL_PENDULUM) {
     if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(mpf_kernel<DUST_MODEL_PENDULUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { DUST_TIMED("mpf_kernel", stream); mpf_kernel<DUST_MODEL_PENDULUM><<<a->B, kMpfThreads, smem, stream>>>(k); }
