@@ -192,6 +192,33 @@ def test_fused_instance_kernel_matches_two_stage_path_and_oracle(env, kind, N, S
             assert rel_max(fused["grad_lik"][b].cpu(), g_dev) <= 1e-5
 
 
+@pytest.mark.parametrize("N,S,H,P,tiling", [(4, 70, 18, 3, 0), (16, 33, 20, 2, 0), (32, 9, 12, 5, 1), (8, 64, 20, 4, 1),
+                                            (64, 5, 6, 0, 0), (2, 200, 31, 2, 0)])
+def test_packed_pendulum_kernel_shapes(env, N, S, H, P, tiling):
+    """The two-trajectories-per-thread kernel (FFMA2/FADD2/FMUL2) across its branches: horizons that
+    are not a multiple of 4, ragged last tiles (scalar fallback for an unpaired row), blocked and
+    interleaved parameter tiling (the two rows of a thread then use different draws).  Every lane is
+    IEEE-rounded like the scalar instruction: costs must equal the scalar staged path BIT FOR BIT."""
+    from dust_b200 import ops
+
+    torch.manual_seed(N * 131 + S)
+    B = 80
+    state = torch.randn(B, 2) * torch.tensor([2.5, 2.0])
+    theta, eps = torch.randn(B, N, H, 1) * 2, torch.randn(B, S, N, H, 1)
+    sigma = torch.tensor([1.3])
+    params = cu(torch.rand(B, P, 2) * 0.7 + 0.6) if P else None
+    kw = dict(theta=cu(theta), sigma=cu(sigma), params=params, param_tiling=tiling, alpha=0.8,
+              want=("costs", "log_lik", "grad_lik"))
+    packed = ops.rollout_cost(env["spec"]["pendulum"], cu(state), cu(eps), **kw)
+    for b in (0, B // 2, B - 1):
+        one = ops.rollout_cost(env["spec"]["pendulum"], cu(state[b:b + 1]), cu(eps[b:b + 1]), theta=cu(theta[b:b + 1]),
+                               sigma=cu(sigma), params=None if params is None else params[b:b + 1].contiguous(),
+                               param_tiling=tiling, alpha=0.8, want=("costs", "log_lik", "grad_lik"))
+        assert torch.equal(packed["costs"][b], one["costs"][0]), (N, S, H, P, tiling, b)
+        assert rel_max(packed["log_lik"][b].cpu(), one["log_lik"][0].cpu()) <= 1e-6
+        assert rel_max(packed["grad_lik"][b].cpu(), one["grad_lik"][0].cpu()) <= 1e-5
+
+
 # ---------------------------------------------------------------------------------------------
 # K3 GMM prior, K5 phi, K7 forward
 # ---------------------------------------------------------------------------------------------
