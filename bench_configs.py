@@ -40,7 +40,7 @@ CONFIGS = {
 }
 
 
-def build(cfg, dev, seed=0):
+def build(cfg, dev, seed=0, alpha=1.0):
     from dust_b200.inference.core import SvmpcCore
     from dust_b200.models.particle import Particle
     from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
@@ -65,7 +65,7 @@ def build(cfg, dev, seed=0):
     mu = rn(1, N, H, A)
     theta = mu + cfg["prior_sigma"] * rn(1, N, H, A)
     core = SvmpcCore(spec, theta, mu, torch.ones(1, N, device=dev), torch.full((A,), cfg["prior_sigma"] ** 2),
-                     torch.full((A,), cfg["sigma"]), alpha=1.0, temperature=1.0, lr=cfg["lr"], kernel="gpytorch",
+                     torch.full((A,), cfg["sigma"]), alpha=alpha, temperature=1.0 / alpha, lr=cfg["lr"], kernel="gpytorch",
                      grad=cfg["grad"], weighted_prior=cfg["weighted_prior"])
     eps = rn(1, S, N, H, A)
     return dict(spec=spec, core=core, state=state.contiguous(), params=params.contiguous(), eps=eps, mpf_x=mpf_x.contiguous(), A=A)
@@ -91,6 +91,7 @@ def main():
     ap.add_argument("--configs", default="pendulum_demo,particle_demo,dual_stress")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--alpha", type=float, default=1.0, help="likelihood temperature (demos: 1); a tiny value makes every soft-min weight non-zero")
     args = ap.parse_args()
     from dust_b200 import _lib as L
 
@@ -98,7 +99,7 @@ def main():
     dev = torch.device("cuda", 0)
     for name in args.configs.split(","):
         cfg = CONFIGS[name]
-        p = build(cfg, dev)
+        p = build(cfg, dev, alpha=args.alpha)
         for _ in range(args.warmup):
             dual_step(cfg, p)
         torch.cuda.synchronize()
@@ -124,7 +125,10 @@ def main():
                 "device_ms_per_dual_step": dev_ms, "wall_ms_per_dual_step": wall_ms,
                 "dual_steps_per_sec": 1e3 / dev_ms, "rollouts_per_sec": cfg["P"] * cfg["S"] * cfg["N"] * 1e3 / dev_ms,
                 "model_steps_per_control_step": model_steps, "kernel_ms_per_step": prof, "steps": args.steps,
-                "warmup": args.warmup, "data": "synthetic"}
+                "warmup": args.warmup, "data": "synthetic", "alpha": args.alpha}
+        lw = p["core"].last.get("lik_weights")
+        if lw is not None:   # pathwise gradient: rows with an exactly-zero weight are not rolled out by the adjoint
+            line["nonzero_weight_fraction"] = float((lw != 0).float().mean())
         print(json.dumps(line), flush=True)
 
 

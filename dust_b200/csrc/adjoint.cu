@@ -42,6 +42,42 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
   const int pc = blockIdx.y;
   const int HA = k.HA;
 
+  // The cotangent of a trajectory is its soft-min weight: rows whose weight is EXACTLY zero in float32
+  // (cost more than ~100/alpha above the policy's best: with the demos' cost scales that is nearly all
+  // of them) contribute exactly nothing and are not rolled out; a tile without any live row returns
+  // before staging anything.  ExpectedCost weighs every row alike and skips none.
+  const int row = threadIdx.x;
+  float coef = 0.f;
+  if (row < rows) {
+    if (k.likelihood == DUST_LIK_EXP_UTILITY)
+      coef = -k.alpha * __ldg(k.lik_w + inst * k.SN + j0 + row) / (float)k.P;
+    else
+      coef = -k.alpha / ((float)k.S * (float)k.P);
+  }
+  const bool live = (row < rows) && (coef != 0.f);   // NaN weights stay live and propagate
+  if (!__syncthreads_or(live ? 1 : 0)) {
+    float* out0 = k.partial + ((inst * k.tiles + tile_idx) * (long long)k.PC + pc) * (long long)(k.N * HA);
+    for (int col = threadIdx.x; col < k.N * HA; col += kAdjTile) out0[col] = 0.f;
+    return;
+  }
+  // Deterministic compaction of the live rows (ballot + prefix over the 4 warps).  When at most half
+  // of the tile is live, the idle threads take slices of the live rows' parameter loops: thread t
+  // serves live row t / G with the draws p_begin + Q*(t % G), stepping Q*G, into its OWN gradient
+  // slot, and the slots are summed per policy in slot order afterwards.
+  __shared__ int s_live[kAdjTile], s_slot_row[kAdjTile], s_wcnt[kAdjTile / 32];   // s_slot_row: policy of the slot, -1 = unused
+  const int warp_ = threadIdx.x >> 5, lane_ = threadIdx.x & 31;
+  const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+  if (lane_ == 0) s_wcnt[warp_] = __popc(live_mask);
+  __syncthreads();
+  int n_live = 0, live_base = 0;
+#pragma unroll
+  for (int w = 0; w < kAdjTile / 32; ++w) {
+    if (w < warp_) live_base += s_wcnt[w];
+    n_live += s_wcnt[w];
+  }
+  if (live) s_live[live_base + __popc(live_mask & ((1u << lane_) - 1u))] = row;
+  const bool spread = 2 * n_live <= kAdjTile;
+
   {  // stage actions = theta + sigma*eps
     const float* __restrict__ src = k.noise + (inst * k.SN + j0) * (long long)HA;
     const float* __restrict__ th = k.theta ? k.theta + inst * (long long)k.N * HA : nullptr;
@@ -61,21 +97,27 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
   }
   __syncthreads();
 
-  const int row = threadIdx.x;
-  if (row < rows) {
-    const int j = j0 + row;
-    const float* __restrict__ arow = tile + row * stride;
-    float* __restrict__ grow = gacc + row * stride;
+  constexpr int Q = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;   // parameter draws advanced together per thread
+  int my_row = live ? row : -1, p_first = 0, p_step = Q;
+  const int chunk_len = min(k.P, pc * k.Pchunk + k.Pchunk) - pc * k.Pchunk;   // draws of this CTA
+  const int G = spread ? kAdjTile / n_live : 1;                               // thread slots per live row
+  const int g_used = min(G, (chunk_len + Q - 1) / Q);                         // ... of which this many get draws
+  if (spread) {
+    const int l = threadIdx.x / G, g = threadIdx.x % G;
+    my_row = (l < n_live && g < g_used) ? s_live[l] : -1;
+    p_first = Q * g;
+    p_step = Q * G;
+    if (my_row >= 0 && k.likelihood == DUST_LIK_EXP_UTILITY)
+      coef = -k.alpha * __ldg(k.lik_w + inst * k.SN + j0 + my_row) / (float)k.P;
+  }
+  s_slot_row[threadIdx.x] = my_row >= 0 ? (j0 + my_row) % k.N : -1;   // the slot's policy
+  if (my_row >= 0) {
+    const int j = j0 + my_row;
+    const float* __restrict__ arow = tile + my_row * stride;
+    float* __restrict__ grow = gacc + threadIdx.x * stride;
     const float* __restrict__ x0 = k.state0 + inst * DS;
-    const int p_begin = pc * k.Pchunk, p_end = min(k.P, p_begin + k.Pchunk);
-    float coef;
-    if (k.likelihood == DUST_LIK_EXP_UTILITY)
-      coef = -k.alpha * __ldg(k.lik_w + inst * k.SN + j) / (float)k.P;
-    else
-      coef = -k.alpha / ((float)k.S * (float)k.P);
-
-    constexpr int Q = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;   // parameter draws advanced together per thread
-    for (int p = p_begin; p < p_end; p += Q) {
+    const int p_begin = pc * k.Pchunk + p_first, p_end = min(k.P, pc * k.Pchunk + k.Pchunk);
+    for (int p = p_begin; p < p_end; p += p_step) {
       const float* prm = nullptr;
       if (k.params) {
         const int pi = k.interleaved ? (int)(((long long)p * k.SN + j) % k.P) : p;
@@ -240,7 +282,14 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
     int r0 = (n - (j0 % k.N)) % k.N;
     if (r0 < 0) r0 += k.N;
     float acc = 0.f;
-    for (int r = r0; r < rows; r += k.N) acc += gacc[r * stride + c];
+    if (!spread) {
+      for (int r = r0; r < rows; r += k.N) acc += gacc[r * stride + c];
+    } else {
+      for (int l = 0; l < n_live; ++l) {            // live rows in row order, their slots in draw order
+        if (s_slot_row[l * G] != n) continue;
+        for (int g = 0; g < g_used; ++g) acc += gacc[(l * G + g) * stride + c];
+      }
+    }
     out[col] = acc;
   }
 }
