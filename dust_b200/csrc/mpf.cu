@@ -6,6 +6,8 @@
 // per parameter particle; the autograd call of mpf.py:50 is replaced by the closed-form
 // Jacobian of each shipped model, SURVEY.md §9 "MPF one-step").
 // Compiled with -fmad=false (models.cuh).
+#include <cooperative_groups.h>
+
 #include "models.cuh"
 
 namespace dust {
@@ -158,6 +160,98 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
   for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) xg[e] = xs[e];
 }
 
+// One large instance (B = 1) spread over many SMs: the same warp-per-particle arithmetic, particles and
+// scores in global memory (read through L2: other SMs wrote them), two grid barriers per SVGD step.
+// ws: [Np*DP] second particle buffer | [Np*DP] scores | [gridDim.x] partial squared norms.
+namespace cg = cooperative_groups;
+template <int MODEL>
+__global__ void __launch_bounds__(256) mpf_coop_kernel(const MpfKParams k, float* ws) {
+  constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
+  constexpr int DS = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 4;
+  constexpr int DA = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ float red[8];
+  float* cur = k.x;
+  float* nxt = ws;
+  float* sc = ws + k.Np * DP;
+  float* part = sc + k.Np * DP;
+  float o0[DS], o1[DS], act[DA], piv[DP];
+#pragma unroll
+  for (int i = 0; i < DS; ++i) { o0[i] = k.obs0[i]; o1[i] = k.obs1[i]; }
+#pragma unroll
+  for (int i = 0; i < DA; ++i) act[i] = k.action[i];
+#pragma unroll
+  for (int i = 0; i < DP; ++i) piv[i] = k.prior_inv_var[i];
+  float c_cell = 0.f;
+  if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits) c_cell = grid_lookup(k.m, k.m.grid_bits, o0[0], o0[1]);
+  const float inv_bw2 = 1.0f / (k.bw * k.bw);
+  const float inv_np = 1.0f / (float)k.Np;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int gwarp = blockIdx.x * nwarps + warp, total_warps = gridDim.x * nwarps;
+  for (int step = 0; step < k.n_steps; ++step) {
+    for (int i = gwarp; i < k.Np; i += total_warps) {
+      float xi[DP], g[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) xi[d] = __ldcg(cur + i * DP + d);
+      mpf_lik_grad<MODEL>(k.m, xi, k.log_space, o0, act, o1, k.inv_obs_var, c_cell, g);
+      float z = 0.f, acc[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) acc[d] = 0.f;
+      for (int j = lane; j < k.Np; j += 32) {
+        float q = 0.f, xj[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { xj[d] = __ldcg(cur + j * DP + d); const float df = xi[d] - xj[d]; q += df * df * piv[d]; }
+        const float e = expf(-0.5f * q);
+        z += e;
+#pragma unroll
+        for (int d = 0; d < DP; ++d) acc[d] += e * (xj[d] - xi[d]);
+      }
+      z = warp_sum(z);
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float a_d = warp_sum(acc[d]);
+        if (lane == 0) sc[i * DP + d] = g[d] + a_d / z * piv[d];
+      }
+    }
+    grid.sync();
+    float nrm = 0.f;
+    for (int i = gwarp; i < k.Np; i += total_warps) {
+      float xi[DP], acc[DP];
+#pragma unroll
+      for (int d = 0; d < DP; ++d) { xi[d] = __ldcg(cur + i * DP + d); acc[d] = 0.f; }
+      for (int j = lane; j < k.Np; j += 32) {
+        float d2 = 0.f, df[DP];
+#pragma unroll
+        for (int d = 0; d < DP; ++d) { df[d] = xi[d] - __ldcg(cur + j * DP + d); d2 += df[d] * df[d]; }
+        const float kij = expf(-d2 * inv_bw2 * 0.5f);
+#pragma unroll
+        for (int d = 0; d < DP; ++d) acc[d] += kij * (inv_np * __ldcg(sc + j * DP + d) - inv_bw2 * df[d]);
+      }
+#pragma unroll
+      for (int d = 0; d < DP; ++d) {
+        const float a_d = warp_sum(acc[d]);
+        if (lane == 0) { nxt[i * DP + d] = xi[d] + k.lr * a_d; nrm += a_d * a_d; }   // SGD (mpf.py:59-62)
+      }
+    }
+    if (lane == 0) red[warp] = nrm;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < nwarps; ++w) t += red[w];
+      part[blockIdx.x] = t;
+    }
+    grid.sync();
+    if (blockIdx.x == 0 && threadIdx.x == 0 && k.grad_norms) {
+      float t = 0.f;
+      for (int b = 0; b < (int)gridDim.x; ++b) t += __ldcg(part + b);
+      k.grad_norms[step] = sqrtf(t);
+    }
+    float* tmp = cur; cur = nxt; nxt = tmp;
+  }
+  if (cur != k.x)   // an odd number of steps left the result in the workspace
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k.Np * DP; e += gridDim.x * blockDim.x) k.x[e] = __ldcg(cur + e);
+}
+
 template <int MODEL>
 __global__ void model_step_kernel(const ModelParams m, int M, const float* __restrict__ states,
                                   const float* __restrict__ actions, const float* __restrict__ params,
@@ -197,6 +291,18 @@ __global__ void model_cost_kernel(const ModelParams m, int M, int terminal, cons
 
 using namespace dust;
 
+static int mpf_coop_grid(const dust_mpf_args* a) {
+  if (a->B != 1 || a->Np < 128) return 0;
+  const int g = (a->Np + 7) / 8;   // 8 warps per CTA, one particle per warp and pass where possible
+  return g < kNumSMs ? g : kNumSMs;
+}
+
+extern "C" size_t dust_mpf_workspace_bytes(const dust_mpf_args* a) {
+  if (a == nullptr || a->model == nullptr) return 0;
+  const int g = mpf_coop_grid(a);
+  return g ? sizeof(float) * ((size_t)2 * a->Np * model_dp(a->model->kind) + g) : 0;
+}
+
 extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_mpf_optimize: args is NULL");
   int rc = validate_model(a->model);
@@ -214,6 +320,16 @@ extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   k.x = a->x; k.obs0 = a->obs0; k.action = a->action; k.obs1 = a->obs1; k.prior_inv_var = a->prior_inv_var;
   k.inv_obs_var = 1.0f / (a->obs_std * a->obs_std); k.bw = a->bw; k.lr = a->lr; k.grad_norms = a->grad_norms;
   cudaStream_t stream = (cudaStream_t)stream_;
+  const int coop = mpf_coop_grid(a);
+  if (coop && a->workspace && a->workspace_bytes >= dust_mpf_workspace_bytes(a) && a->n_steps > 0) {
+    float* ws = (float*)a->workspace;
+    void* kargs[] = {(void*)&k, (void*)&ws};
+    const void* fn = kind == DUST_MODEL_PENDULUM ? (const void*)mpf_coop_kernel<DUST_MODEL_PENDULUM>
+                                                 : (const void*)mpf_coop_kernel<DUST_MODEL_PARTICLE>;
+    { DUST_TIMED("mpf_coop_kernel", stream); DUST_CUDA_OK(cudaLaunchCooperativeKernel(fn, dim3(coop), dim3(256), kargs, 0, stream)); }
+    DUST_LAUNCH_OK("mpf_coop_kernel");
+    return DUST_OK;
+  }
   // a warp per particle: as many warps as particles, up to a full CTA; fewer when many instances share the GPU
   int kMpfThreads = 32 * (a->Np < 32 ? a->Np : 32);
   if ((long long)a->B * kMpfThreads > (long long)kNumSMs * 2048) kMpfThreads = 256;

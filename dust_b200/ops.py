@@ -262,7 +262,7 @@ def disco_step(a_mat, a_mix, a_low, a_high, strategy=L.SELECT_ARGMAX, steps=1):
     return nxt, a_seq
 
 
-def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space):
+def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space, cooperative=True):
     """x [B,Np,dp] is updated IN PLACE.  -> grad_norms [B,n_steps]."""
     L.require_cuda()
     B, Np, dp = x.shape
@@ -275,6 +275,10 @@ def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_
     a.prior_inv_var = L.ptr(prior_inv_var)
     a.obs_std, a.bw, a.lr = float(obs_std), float(bw), float(lr)
     a.grad_norms = L.ptr(gn)
+    # > 0: one large instance, cooperative multi-SM kernel (cooperative=False keeps the one-CTA kernel)
+    nbytes = L.load().dust_mpf_workspace_bytes(C.byref(a)) if cooperative else 0
+    ws = _ws(nbytes, x.device) if nbytes else None
+    a.workspace, a.workspace_bytes = (ws.data_ptr() if nbytes else None), nbytes
     L.call("dust_mpf_optimize", C.byref(a), L.stream())
     return gn
 

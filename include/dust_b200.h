@@ -364,8 +364,13 @@ typedef struct dust_mpf_args {
   const float* prior_inv_var;/* [dp]                                                   */
   float obs_std, bw, lr;
   float* grad_norms;         /* [B, n_steps] or NULL                                   */
+  void* workspace;           /* optional, dust_mpf_workspace_bytes(): a single instance with many particles
+                              * (B = 1, Np >= 128) is then spread over many SMs by a cooperative launch
+                              * (two grid barriers per SVGD step, same per-particle arithmetic)            */
+  size_t workspace_bytes;
 } dust_mpf_args;
 
+size_t dust_mpf_workspace_bytes(const dust_mpf_args* args);   /* 0: the one-CTA-per-instance kernel is used */
 int dust_mpf_optimize(const dust_mpf_args* args, void* stream);
 
 /* one model step for M (state, action, params) triples: BaseModel.step

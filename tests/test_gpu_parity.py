@@ -464,6 +464,36 @@ def test_mpf_against_reference(env):
     assert rel_max(gn[0].cpu(), d["grad_norms"]) <= RTOL_PHI
 
 
+@pytest.mark.parametrize("kind,Np,steps", [("particle", 512, 20), ("pendulum", 300, 7), ("particle", 131, 1)])
+def test_mpf_cooperative_kernel_equals_single_cta(env, kind, Np, steps):
+    """One large instance spread over many SMs (cooperative launch, two grid barriers per step): every
+    particle keeps its own warp and lane order, so the particles come out BIT-IDENTICAL to the
+    one-CTA kernel; odd step counts leave the result in the workspace and copy it back."""
+    from dust_b200 import ops
+
+    torch.manual_seed(Np)
+    spec = env["spec"][kind]
+    if kind == "particle":
+        x0 = math.log(2.0) + 0.1 * torch.randn(1, Np, 1)
+        obs0, act = torch.tensor([[-9.0, -9.0, 0.3, 0.1]]), torch.tensor([[4.0, -3.0]])
+        log_space, lr, bw = True, 1e-2, 0.5
+        obs1 = ops.model_step(spec, cu(obs0), cu(act), cu(torch.tensor([[2.6]]))).cpu()
+    else:
+        x0 = 0.6 + 0.7 * torch.rand(1, Np, 2)
+        obs0, act = torch.tensor([[3.0, 0.2]]), torch.tensor([[1.5]])
+        log_space, lr, bw = False, 1e-3, 0.05
+        obs1 = ops.model_step(spec, cu(obs0), cu(act), cu(torch.tensor([[1.1, 0.8]]))).cpu()
+    piv = cu(torch.full((spec.dp,), 1.0 / bw ** 2))
+    outs = []
+    for coop in (True, False):
+        x = cu(x0).clone()
+        gn = ops.mpf_optimize(spec, x, cu(obs0), cu(act), cu(obs1), piv, 0.1, bw, lr, steps, log_space, cooperative=coop)
+        outs.append((x.cpu(), gn.cpu()))
+    assert not torch.equal(outs[0][0], x0)
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert rel_max(outs[0][1], outs[1][1]) <= 1e-5
+
+
 def test_mpf_dual_loop_steps(env):
     from dust_b200 import ops
 
