@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="compare a row sample against the float64 oracle")
+    ap.add_argument("--emulate-world", type=int, default=1,
+                    help="single process only: time the row block ONE rank of a world of this size computes (all N "
+                         "columns resident, no collective) -- the per-rank device work of the sharded run")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -43,9 +46,13 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0)
     X = torch.randn(N, D, device=dev, generator=g)
     S = -X
-    b, e = row_block(N, rank, world)
+    emu = args.emulate_world if world == 1 else 1
+    b, e = row_block(N, rank, world) if emu == 1 else row_block(N, emu // 2, emu)
     sh = ShardedSVGD(N, D, device=dev)
     xl, sl = X[b:e].contiguous(), S[b:e].contiguous()
+    if emu > 1:   # this process plays rank emu // 2: its row block against the resident columns
+        sh.rows = (b, e)
+        sh.gather = lambda x_local, s_local: (X, S)
 
     def sync():
         if world > 1:
@@ -72,6 +79,17 @@ def main():
     def full():
         phi, coef = sh.phi(xl, sl)
         coef_holder["coef"], coef_holder["phi"] = coef, phi
+
+    if emu > 1:
+        # one rank's histogram alone selects nothing (the all-reduce over the other ranks is missing):
+        # take the bandwidth from a full single-GPU pass, untimed, and time only the phi row block
+        med = ops.median_sq_dist(X)
+        coef_full = ops.bandwidth_from_median(med, N, 1.0, 0)
+
+        def full():  # noqa: F811
+            x_all, s_all = sh.gather(xl, sl)
+            out_ = ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef_full, rows=sh.rows)
+            coef_holder["coef"], coef_holder["phi"] = coef_full, out_["phi"][0, b:e]
 
     ms_full = timed(full)
     coef = coef_holder["coef"]
@@ -103,13 +121,14 @@ def main():
         del A_, B_
     out = None
     if rank == 0:
-        fl_phi, fl_med = 6.0 * N * N * D, 4.0 * N * N * D
+        fl_phi, fl_med = 6.0 * N * N * D / emu, 4.0 * N * N * D / emu
         Dp, NV = (D + 7) // 8 * 8, (2 * D + 15) // 16 * 16
-        issued = 3 * 2.0 * N * N * (Dp + NV) / world   # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
+        issued = 3 * 2.0 * N * N * (Dp + NV) / (world * emu)   # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
         t_phi_kernel = prof.get("phi_tc_kernel", (0, 0.0))[1]
-        out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "ms_phi_with_median": ms_full, "ms_phi": ms_phi,
+        out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "emulated_world": emu, "rows": [b, e],
+               "ms_phi_with_median": ms_full if emu == 1 else None, "ms_phi": ms_phi,
                "algorithmic_tflops_phi": fl_phi / (ms_phi * 1e-3) / 1e12,
-               "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12, "bandwidth": bw,
+               "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12 if emu == 1 else None, "bandwidth": bw,
                "kernels_ms": {k: v[1] for k, v in prof.items()},
                "roofline": None if not t_phi_kernel else {
                    "kernel": "phi_tc_kernel", "bound": "tensor", "unit": "TFLOP/s",

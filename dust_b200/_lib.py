@@ -38,6 +38,7 @@ class RolloutArgs(C.Structure):
         ("param_tiling", _i), ("likelihood", _i),
         ("state0", _p), ("theta", _p), ("noise", _p), ("sigma", _p), ("params", _p), ("a_seq", _p),
         ("pert", _p), ("alpha", _f), ("temperature", _f),
+        ("sigma_weights", _p), ("ctrl_mat", _p), ("ctrl_reg", _f),
         ("costs", _p), ("log_lik", _p), ("lik_weights", _p), ("grad_lik", _p), ("mppi_weights", _p),
         ("mppi_delta", _p), ("mix", _p), ("states", _p),
         ("workspace", _p), ("workspace_bytes", _sz),

@@ -4,6 +4,7 @@ import torch
 
 from .. import _lib as L
 from .. import ops
+from ..utils.utf import MerweScaledUTF
 from .base import BaseController
 
 Empty = torch.Size([])
@@ -26,8 +27,6 @@ class MultiDISCO(BaseController):
         self.n_actions = action_samples
         self.temp = temperature
         self.a_reg = temperature * (1 - ctrl_penalty)
-        if self.a_reg != 0:
-            raise NotImplementedError("ctrl_penalty != 1 (control regulariser, disco.py:338-344) has no device kernel yet")
         dev = self.device
         a_cov = torch.eye(self.dim_a) if a_cov is None else torch.as_tensor(a_cov, dtype=torch.float32)
         self._sigma = diag_sigma(a_cov.cpu()).to(dev)
@@ -42,16 +41,21 @@ class MultiDISCO(BaseController):
         self.a_mix = torch.ones(self.n_pol, device=dev)
         self._params_sampling = params_sampling
         self._params_log_space = params_log_space
+        self._tf = None
         if params_sampling is False or params_sampling is None or (isinstance(params_sampling, str) and params_sampling == "none"):
             self.n_params, self._params_shape = 1, None
         elif params_sampling is True:
             self.n_params, self._params_shape = params_samples, [params_samples]
-        elif type(params_sampling).__name__ == "MerweScaledUTF":
-            raise NotImplementedError("unscented-transform parameter tiling (_sigma_rollout, disco.py:211-292) "
-                                      "has no device kernel yet")
+        elif isinstance(params_sampling, MerweScaledUTF):
+            assert self._params_log_space is False, "Distribution must not be on log space if using UTF."
+            if self.a_reg != 0:
+                raise NotImplementedError("sigma-point rollouts with ctrl_penalty != 1: the reference forms that "
+                                          "control cost from action sample 0 only (disco.py:334-344 on the "
+                                          "unexpanded actions); not reproduced")
+            self.n_params, self._params_shape = 1, None     # disco.py:128-131: sic
+            self._tf = params_sampling
         else:
             raise ValueError("Invalid value for 'params_sampling': {}".format(params_sampling))
-        self._tf = None
         self.n_rollouts = self.n_params * self.n_actions * self.n_pol
         self.return_states = return_states
         self._spec_cache = {}
@@ -89,20 +93,51 @@ class MultiDISCO(BaseController):
         dev_params = model.device_params(params, self.device).unsqueeze(0)
         return dev_params, tiling, params_log_p
 
+    def _sigma_points(self, model, params_dist):
+        """disco.py:238-251, 262-264, 285-291: sigma points of the parameter belief as device params
+        [1, pts, dp], their weights, and the (identical for every rollout) weighted log-probability."""
+        try:
+            cov, mean = params_dist.covariance_matrix, params_dist.mean
+        except AttributeError:
+            cov, mean = params_dist.variance.diag(), params_dist.mean
+        params_sp = self._tf.compute_sigma_points(mean.cpu(), cov.cpu())          # [n, pts]
+        pts = params_sp.T.contiguous()                                             # row k = sigma point k
+        w = self._tf.loc_weights
+        log_p = params_dist.log_prob(pts.to(mean.device))                          # [pts]
+        log_p = log_p.expand(self.n_actions, self.n_pol, self._tf.pts) @ w.to(log_p.device)
+        return model.device_params(pts, self.device).unsqueeze(0), w.to(self.device).contiguous(), log_p
+
     def evaluate(self, state, model, params_dist, noise, theta=None, want=("costs",), likelihood=L.LIK_EXP_UTILITY,
                  alpha=1.0, pert=None):
         """Run K1 for this controller's shapes.  noise [S,N,H,A] (eps when theta is given, else actions)."""
         spec = self._spec(model)
         dev = self.device
         state0 = torch.as_tensor(state, dtype=torch.float32).reshape(1, -1).to(dev).contiguous()
-        params, tiling, params_log_p = self._sample_params(model, params_dist)
+        sigma_w = None
+        if self._tf is not None:
+            params, sigma_w, params_log_p = self._sigma_points(model, params_dist)
+            tiling = L.PARAMS_BLOCKED
+        else:
+            params, tiling, params_log_p = self._sample_params(model, params_dist)
         want = tuple(want) + (("states",) if self.return_states and "states" not in want else ())
+        ctrl_mat = None
+        if self.a_reg != 0:
+            # the regulariser reads a_mat, and the reference's forward moves a_mat / a_mix on EVERY call, also
+            # when SVMPC drives it with external actions (disco.py:392-393): keep both in step
+            ctrl_mat = (self.a_mat @ self.a_pre).unsqueeze(0).contiguous()
+            want = want + tuple(k for k in ("mppi_delta", "mix") if k not in want)
         out = ops.rollout_cost(
             spec, state0, noise.unsqueeze(0), theta=None if theta is None else theta.unsqueeze(0),
             sigma=self._sigma if theta is not None else None, params=params, param_tiling=tiling,
             likelihood=likelihood, a_seq=self.a_seq.unsqueeze(0).contiguous(),
-            pert=None if pert is None else pert.unsqueeze(0), alpha=alpha, temperature=self.temp, want=want)
+            pert=None if pert is None else pert.unsqueeze(0), alpha=alpha, temperature=self.temp, want=want,
+            sigma_weights=sigma_w, ctrl_mat=ctrl_mat, ctrl_reg=self.a_reg)
         res = {k: v[0] for k, v in out.items()}
+        if self._tf is not None and "states" in res:
+            # the reference's row order is (sample, policy, sigma point) relabelled as [S*pts, N] (disco.py:281-284)
+            st = res["states"]                                   # [pts, S, N, H+1, ds]
+            res["states"] = st.permute(1, 2, 0, 3, 4).reshape(self.n_actions * self._tf.pts, self.n_pol, self.hz_len + 1,
+                                                              self.dim_s)
         res["params_log_p"] = params_log_p
         return res
 
@@ -122,7 +157,8 @@ class MultiDISCO(BaseController):
         self.a_mat += res["mppi_delta"]
         self.a_mix = res["mix"]
         states = res.get("states")
-        acts = actions.unsqueeze(0).expand(self.n_params, -1, -1, -1, -1)
+        # _sigma_rollout hands the actions back as given, _rollout tiled over the parameter draws
+        acts = actions if self._tf is not None else actions.unsqueeze(0).expand(self.n_params, -1, -1, -1, -1)
         return res["costs"], states, acts, res["mppi_weights"], res["params_log_p"]
 
     def step(self, strategy="argmax", steps=1, ext_actions=None):

@@ -38,6 +38,25 @@ struct RolloutKParams {
   const float* params;
   float* cost_out;     // PC==1: costs [B,S,N] (already divided by P); else partial sums [B,PC,SN]
   float* states;       // optional [B,P,S,N,H+1,ds]
+  const float* ut_w;   // [P] unscented-transform weights (sigma-point mode, PC == 1) or nullptr
+  const float* ctrl_mat;  // [B,N,HA] a_mat @ a_pre (control regulariser, PC == 1) or nullptr
+  const float* a_seq;  // [B,HA] or nullptr (zeros)
+  float ctrl_reg;
+};
+
+// Weighted cost of the sigma-point mode exactly as disco.py:312-323 groups it: the instantaneous costs of
+// one (sample, policy) pair, in the order (sigma point p, step t), are cut into runs of P; every run is
+// one dot product with the weights, the runs are summed, and the weighted terminal costs are added.
+struct UtCostSum {
+  const float* w;
+  int P, i = 0;
+  float dot = 0.f, inst = 0.f, term = 0.f;
+  __device__ __forceinline__ void add(float c) {
+    dot = dot + __ldg(w + i) * c;
+    if (++i == P) { inst = inst + dot; dot = 0.f; i = 0; }
+  }
+  __device__ __forceinline__ void add_term(int p, float c) { term = term + __ldg(w + p) * c; }
+  __device__ __forceinline__ float total() const { return inst + term; }
 };
 
 // cooperative load of a [rows, HA] tile of the noise tensor into padded shared memory, fused
@@ -102,7 +121,7 @@ __device__ __forceinline__ void load_action_tile(const RolloutKParams& k, float*
 // STORE: write the state trajectory (only the non-fused path offers it).
 // XFORM: `arow` holds the raw noise; the action is th_row[t] + sigma * eps[t], formed per step
 // (one product, one sum: the same float32 value as MultivariateNormal.rsample's loc + L eps).
-template <int MODEL, bool SMALL, bool STORE, bool XFORM = false>
+template <int MODEL, bool SMALL, bool STORE, bool XFORM = false, bool UT = false>
 __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, const float* __restrict__ arow,
                                                      const uint32_t* grid_s, long long inst, int j, int p_begin, int p_end,
                                                      const float* __restrict__ th_row = nullptr, float sg0 = 0.f,
@@ -111,6 +130,7 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
   constexpr int DP = (MODEL == DUST_MODEL_PENDULUM) ? 2 : 1;
   const float* __restrict__ x0 = k.state0 + inst * DS;
   float csum = 0.f;
+  UtCostSum ut{k.ut_w, k.P};
   for (int p = p_begin; p < p_end; ++p) {
     const float* prm = nullptr;
     if (k.params) {
@@ -130,7 +150,8 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
         const float om0 = om;
         float cth;
         pendulum_step<!SMALL>(k.m, cf, th, om, a, nullptr, &cth);
-        run.add(k.m, cth, om0);
+        if (UT) ut.add(pendulum_cost_from_cos(k.m, cth, om0));
+        else run.add(k.m, cth, om0);
         if (STORE) { st_out[(t + 1) * 2] = th; st_out[(t + 1) * 2 + 1] = om; }
       };
       int t = 0;
@@ -143,7 +164,8 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
         one(a4.x, t); one(a4.y, t + 1); one(a4.z, t + 2); one(a4.w, t + 3);
       }
       for (; t < k.H; ++t) one(XFORM ? th_row[t] + sg0 * arow[t] : arow[t], t);
-      cost = run.total(k.m) + pendulum_cost<!SMALL>(k.m, th, om);
+      if (UT) ut.add_term(p, pendulum_cost<!SMALL>(k.m, th, om));
+      else cost = run.total(k.m) + pendulum_cost<!SMALL>(k.m, th, om);
     } else {
       const float mass = prm ? __ldg(prm) : k.m.default_mass;
       ParticleState s{__ldg(x0), __ldg(x0 + 1), __ldg(x0 + 2), __ldg(x0 + 3)};
@@ -151,7 +173,8 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
       const bool has_grid = k.m.grid_bits != nullptr;
       auto one = [&](float ax, float ay, int t) {
         const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
-        cost = cost + particle_inst_cost(k.m, s, ax, ay, c);
+        if (UT) ut.add(particle_inst_cost(k.m, s, ax, ay, c));
+        else cost = cost + particle_inst_cost(k.m, s, ax, ay, c);
         particle_step(k.m, s, ax, ay, mass, c);
         if (STORE) {
           float* o = st_out + (t + 1) * 4;
@@ -172,11 +195,12 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
         else one(arow[2 * t], arow[2 * t + 1], t);
       }
       const float c = has_grid ? grid_lookup(k.m, grid_s, s.x, s.y) : 0.f;
-      cost = cost + particle_term_cost(k.m, s, c);
+      if (UT) ut.add_term(p, particle_term_cost(k.m, s, c));
+      else cost = cost + particle_term_cost(k.m, s, c);
     }
     csum = csum + cost;
   }
-  return csum;
+  return UT ? ut.total() : csum;
 }
 
 #if DUST_PEND_PAIR
@@ -234,6 +258,10 @@ template <int MODEL>
 __device__ __forceinline__ float trajectory_cost_dispatch(const RolloutKParams& k, const float* __restrict__ arow,
                                                           const uint32_t* grid_s, long long inst, int j, int p_begin,
                                                           int p_end, bool small) {
+  if (k.ut_w) {
+    if (k.states) return trajectory_cost_sum<MODEL, false, true, false, true>(k, arow, grid_s, inst, j, p_begin, p_end);
+    return trajectory_cost_sum<MODEL, false, false, false, true>(k, arow, grid_s, inst, j, p_begin, p_end);
+  }
   if (k.states) return trajectory_cost_sum<MODEL, false, true>(k, arow, grid_s, inst, j, p_begin, p_end);
   if (small) return trajectory_cost_sum<MODEL, true, false>(k, arow, grid_s, inst, j, p_begin, p_end);
   return trajectory_cost_sum<MODEL, false, false>(k, arow, grid_s, inst, j, p_begin, p_end);
@@ -269,7 +297,17 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
   const float csum = trajectory_cost_dispatch<MODEL>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end,
                                                      small_angle_horizon<MODEL>(k, inst));
   if (k.PC == 1) {
-    k.cost_out[inst * k.SN + j] = csum / (float)k.P;  // mean over parameter samples (disco.py:330)
+    float cost = k.ut_w ? csum : csum / (float)k.P;  // sigma-point weights, or the mean over parameter samples (disco.py:330)
+    if (k.ctrl_mat) {
+      // control regulariser (disco.py:334-344): a_reg * sum_{h,a} -(action - a_seq) (a_mat a_pre)[n]
+      const float* act = tile + row * stride;
+      const float* cm = k.ctrl_mat + (inst * k.N + j % k.N) * (long long)k.HA;
+      const float* as = k.a_seq ? k.a_seq + inst * k.HA : nullptr;
+      float dot = 0.f;
+      for (int e = 0; e < k.HA; ++e) dot = fmaf(-(act[e] - (as ? __ldg(as + e) : 0.f)), __ldg(cm + e), dot);
+      cost = cost + k.ctrl_reg * dot;
+    }
+    k.cost_out[inst * k.SN + j] = cost;
   } else {
     k.cost_out[(inst * k.PC + pc) * (long long)k.SN + j] = csum;
   }
@@ -850,6 +888,7 @@ static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = 
   RolloutPlan pl{};
   const long long SN = (long long)a->S * a->N;
   const int P = a->params ? a->P : 1;
+  if (a->sigma_weights || a->ctrl_mat) single_chunk = true;   // weighted / regularised costs are formed in one thread
   int pc = single_chunk ? 1 : choose_param_chunks((long long)a->B * SN, P);
   const int chunk = (P + pc - 1) / pc;
   pc = (P + chunk - 1) / chunk;
@@ -916,13 +955,18 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   k.state0 = a->state0; k.theta = a->theta; k.noise = a->noise; k.sigma = a->sigma; k.params = a->params;
   k.cost_out = pl.PC > 1 ? part : costs;
   k.states = a->states;
+  k.ut_w = a->sigma_weights; k.ctrl_mat = a->ctrl_mat; k.a_seq = a->a_seq; k.ctrl_reg = a->ctrl_reg;
+  DUST_REQUIRE(!a->sigma_weights || (a->params && a->param_tiling == DUST_PARAMS_BLOCKED), DUST_ERR_INVALID_ARG,
+               "dust_rollout_cost: sigma_weights needs the sigma points in params (blocked tiling)");
+  DUST_REQUIRE(!(a->sigma_weights || a->ctrl_mat) || !tail, DUST_ERR_UNSUPPORTED,
+               "dust_svmpc_step: sigma-point weights and the control regulariser need the staged path");
 
   const int stride = padded_stride(k.HA);
   const size_t grid_bytes = (kind == DUST_MODEL_PARTICLE && a->model->grid_bits)
                                 ? sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32) : 0;
   // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
   const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
-  const bool fused_ok = fused_outputs_only && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
+  const bool fused_ok = fused_outputs_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
                         (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
   DUST_REQUIRE(fused_ok || !tail, DUST_ERR_UNSUPPORTED,
                "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");

@@ -37,13 +37,17 @@ constexpr int kXnStages = 16;     // |x_j|^2 ring of the median kernel
 
 struct TcParams {
   int N, D, Dp, NV, T, row_begin;
-  int ksplit;  // CTAs per row tile: CTA (rt, h) handles column tiles [h*T/ksplit, (h+1)*T/ksplit)
+  // The (row tile, column tile) pairs of a call are numbered row-major, u = rt * T + j, and cut into equal
+  // contiguous ranges: CTA c owns units [c * units_per_cta, (c + 1) * units_per_cta).  A range that crosses
+  // a row-tile boundary is worked off as consecutive SEGMENTS (one per row tile), each with its own slot
+  // of the scratch; every SM carries the same number of tile pairs whatever row block a rank owns.
+  int units_per_cta, total_units, max_seg;
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *vb_hi, *vb_lo, *xn, *x;
   float gamma, c1, c2;
   const float* gamma_dev;
   float lr;
   float *phi, *x_out;
-  float* oacc;  // [grid][NV+2][128] running sums of the drained O chunks (column-major per CTA) + 2 row-sum halves
+  float* oacc;  // [grid][max_seg][NV+2][128] running sums of the drained O chunks (column-major per slot) + 2 row-sum halves
 };
 
 __host__ __device__ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -59,39 +63,102 @@ __device__ __forceinline__ float tf32_lo(float v, float hi) { return __uint_as_f
 // ---------------------------------------------------------------------------------------
 // prep: squared norms and the tiled hi / lo operand images
 // ---------------------------------------------------------------------------------------
-__global__ void tc_prep_x_kernel(const float* __restrict__ x, int N, int D, int Dp, float* __restrict__ xa_hi,
-                                 float* __restrict__ xa_lo, float* __restrict__ xb_hi, float* __restrict__ xb_lo,
-                                 float* __restrict__ xn) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)N * Dp) return;
-  const int row = (int)(e / Dp), k = (int)(e - (long long)row * Dp);
-  const float v = k < D ? x[(long long)row * D + k] : 0.f;
-  const float hi = tf32_hi(v), lo = tf32_lo(v, hi);
-  const long long ia = (long long)(row / kTcBM) * kTcBM * Dp + core_index(row % kTcBM, k, Dp);
-  const long long ib = (long long)(row / kTcBN) * kTcBN * Dp + core_index(row % kTcBN, k, Dp);
-  xa_hi[ia] = hi; xa_lo[ia] = lo;
-  xb_hi[ib] = hi; xb_lo[ib] = lo;
-  if (k == 0) {
-    float s = 0.f;
-    for (int d = 0; d < D; ++d) { const float t = x[(long long)row * D + d]; s += t * t; }
-    xn[row] = s;
+// One image serves both operand roles: element (row, k) sits at
+//   ((row >> 3) * (Dp / 4) + (k >> 2)) * 32 + (row & 7) * 4 + (k & 3),
+// which is core_index() inside a 128-row tile AND inside a 64-row tile (both are whole 8-row groups
+// laid out in row order).  Thread <-> one 16-byte core-matrix row, in image order: a warp writes 512
+// contiguous bytes per image and reads 64-byte pieces of 8 rows.
+__device__ __forceinline__ void tc_prep_x_block(int block, const float* __restrict__ x, int N, int D, int Dp,
+                                                float* __restrict__ x_hi, float* __restrict__ x_lo) {
+  const long long e = (long long)block * blockDim.x + threadIdx.x;   // index of the float4 in the image
+  const int kq = Dp >> 2;
+  if (e >= (long long)N * kq) return;
+  const int r7 = (int)(e & 7);
+  const long long t = e >> 3;
+  const int kg = (int)(t % kq);
+  const int row = (int)(t / kq) * 8 + r7, k = kg * 4;
+  float v[4];
+  const float* xr = x + (long long)row * D;
+  if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0) && k + 3 < D) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(xr + k));
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = (k + c < D) ? xr[k + c] : 0.f;
   }
+  float4 hi, lo;
+  hi.x = tf32_hi(v[0]); hi.y = tf32_hi(v[1]); hi.z = tf32_hi(v[2]); hi.w = tf32_hi(v[3]);
+  lo.x = tf32_lo(v[0], hi.x); lo.y = tf32_lo(v[1], hi.y); lo.z = tf32_lo(v[2], hi.z); lo.w = tf32_lo(v[3], hi.w);
+  reinterpret_cast<float4*>(x_hi)[e] = hi;
+  reinterpret_cast<float4*>(x_lo)[e] = lo;
+}
+
+// |x_i|^2 as one fused-multiply-add chain over d = 0 .. D-1 per row (a warp reads 32 consecutive rows)
+__device__ __forceinline__ void tc_norms_block(int block, const float* __restrict__ x, int N, int D, float* __restrict__ xn) {
+  const int row = block * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  const float* xr = x + (long long)row * D;
+  float s = 0.f;
+  if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0)) {
+    for (int d = 0; d < D; d += 4) {
+      const float4 q = __ldg(reinterpret_cast<const float4*>(xr + d));
+      s = fmaf(q.x, q.x, s); s = fmaf(q.y, q.y, s); s = fmaf(q.z, q.z, s); s = fmaf(q.w, q.w, s);
+    }
+  } else {
+    for (int d = 0; d < D; ++d) { const float t = xr[d]; s = fmaf(t, t, s); }
+  }
+  xn[row] = s;
 }
 
 // V^T tiles: rows n2 in [0, NV) = [score dims | x dims | 0...], K = the 64 columns j of the tile
-// (the row sums of K are accumulated exactly in the softmax warps' registers instead of a ones column)
-__global__ void tc_prep_v_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D, int NV,
-                                 float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)N * NV) return;
-  const int j = (int)(e / NV), n2 = (int)(e - (long long)j * NV);
-  float v = 0.f;
-  if (n2 < D) v = score[(long long)j * D + n2];
-  else if (n2 < 2 * D) v = x[(long long)j * D + (n2 - D)];
-  const float hi = tf32_hi(v), lo = tf32_lo(v, hi);
-  const long long idx = (long long)(j / kTcBN) * NV * kTcBN + core_index(n2, j % kTcBN, kTcBN);
-  vb_hi[idx] = hi;
-  vb_lo[idx] = lo;
+// (the row sums of K are accumulated exactly in the softmax warps' registers instead of a ones column).
+// Thread <-> one 16-byte core-matrix row = 4 consecutive particles of one dimension, in image order:
+// element (n2, jj) of tile jt sits at jt * NV * 64 + ((n2 >> 3) * 16 + (jj >> 2)) * 32 + (n2 & 7) * 4 + (jj & 3).
+__device__ __forceinline__ void tc_prep_v_block(int block, const float* __restrict__ x, const float* __restrict__ score, int N,
+                                                int D, int NV, float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
+  const long long e = (long long)block * blockDim.x + threadIdx.x;   // index of the float4 in the image
+  if (e >= (long long)(N >> 2) * NV) return;
+  const int per_tile = NV * (kTcBN >> 2);
+  const int jt = (int)(e / per_tile), w = (int)(e - (long long)jt * per_tile);
+  const int n7 = w & 7, jq = (w >> 3) & 15, ng = w >> 7;
+  const int n2 = ng * 8 + n7, j = jt * kTcBN + jq * 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (n2 < 2 * D) {
+    const float* src = n2 < D ? score + n2 : x + (n2 - D);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) v[c] = __ldg(src + (long long)(j + c) * D);
+  }
+  float4 hi, lo;
+  hi.x = tf32_hi(v[0]); hi.y = tf32_hi(v[1]); hi.z = tf32_hi(v[2]); hi.w = tf32_hi(v[3]);
+  lo.x = tf32_lo(v[0], hi.x); lo.y = tf32_lo(v[1], hi.y); lo.z = tf32_lo(v[2], hi.z); lo.w = tf32_lo(v[3], hi.w);
+  reinterpret_cast<float4*>(vb_hi)[e] = hi;
+  reinterpret_cast<float4*>(vb_lo)[e] = lo;
+}
+
+// ONE launch prepares everything a pass needs: CTAs [0, nbx) write the X images, [nbx, nbx + nbv) the
+// V^T images (nbv = 0 for the median pass, which has no second GEMM), the rest the squared norms --
+// three small memory-bound jobs that overlap instead of queueing behind each other's launch
+__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D,
+                                                      int Dp, int NV, float* __restrict__ x_hi, float* __restrict__ x_lo,
+                                                      float* __restrict__ vb_hi, float* __restrict__ vb_lo,
+                                                      float* __restrict__ xn, int nbx, int nbv) {
+  const int b = blockIdx.x;
+  if (b < nbx) tc_prep_x_block(b, x, N, D, Dp, x_hi, x_lo);
+  else if (b < nbx + nbv) tc_prep_v_block(b - nbx, x, score, N, D, NV, vb_hi, vb_lo);
+  else tc_norms_block(b - nbx - nbv, x, N, D, xn);
+}
+
+static int tc_prep(const float* x, const float* score, int N, int D, int Dp, int NV, float* x_hi, float* x_lo, float* vb_hi,
+                   float* vb_lo, float* xn, cudaStream_t stream) {
+  const int nbx = ceil_div((long long)N * (Dp / 4), 256);
+  const int nbv = score ? ceil_div((long long)(N / 4) * NV, 256) : 0;
+  const int nbn = ceil_div(N, 256);
+  {
+    DUST_TIMED("tc_prep_kernel", stream);
+    tc_prep_kernel<<<nbx + nbv + nbn, 256, 0, stream>>>(x, score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, nbx, nbv);
+  }
+  DUST_LAUNCH_OK("tc_prep_kernel");
+  return DUST_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -215,7 +282,25 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
 }
 
 enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 13, BAR_S_FULL = 17, BAR_P_FULL = 19,
-       BAR_P_EMPTY = 21, BAR_O_FULL = 23, BAR_O_EMPTY = 25 };
+       BAR_P_EMPTY = 21, BAR_O_FULL = 23, BAR_O_EMPTY = 25, BAR_A_EMPTY = 27 };
+
+// the segments of a CTA's unit range: `for (TcSegIter s(p); s.valid(); s.next())` gives row tile s.rt,
+// first column tile s.j0 and tile count s.len of segment s.seg
+struct TcSegIter {
+  int u, u1, T, seg, rt, j0, len;
+  __device__ __forceinline__ explicit TcSegIter(const TcParams& p) : T(p.T), seg(0) {
+    u = blockIdx.x * p.units_per_cta;
+    u1 = min(u + p.units_per_cta, p.total_units);
+    split();
+  }
+  __device__ __forceinline__ void split() {
+    rt = u / T;
+    j0 = u - rt * T;
+    len = min(T - j0, u1 - u);
+  }
+  __device__ __forceinline__ bool valid() const { return u < u1; }
+  __device__ __forceinline__ void next() { u += len; ++seg; split(); }
+};
 
 __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -223,13 +308,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rt = blockIdx.x / p.ksplit;      // row tile handled by this CTA
-  const int i0 = p.row_begin + rt * kTcBM;   // first global row
-  const int T = p.T / p.ksplit;              // column tiles handled by this CTA ...
-  const int jbase = (blockIdx.x % p.ksplit) * T;  // ... starting at this one
+  const size_t slot_stride = (size_t)(p.NV + 2) * kTcBM;
+  float* const oacc_cta = p.oacc + (size_t)blockIdx.x * p.max_seg * slot_stride;
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[BAR_A], 1);
+    mbar_init(&bars[BAR_A_EMPTY], 1);
     for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[BAR_XB_FULL + s], 1); mbar_init(&bars[BAR_XB_EMPTY + s], 1); }
     for (int s = 0; s < kVbStages; ++s) { mbar_init(&bars[BAR_VB_FULL + s], 1); mbar_init(&bars[BAR_VB_EMPTY + s], 1); }
     for (int b = 0; b < 2; ++b) {
@@ -253,36 +337,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + 128, tO = tmem + 256;
-  const int n_chunks = (T + kTcChunk - 1) / kTcChunk;
+  // Ring stages, S/P buffers and O buffers are indexed by counters that run on ACROSS segments
+  // (g: tiles, cg: flushed chunks), so the pipelines never drain at a row-tile boundary; only the
+  // A operand (the row tile itself) is exchanged there.
 
   if (warp == 0) {
     // ------------------------------ producer ------------------------------------------
     if (lane == 0) {
       const uint32_t a_bytes = kTcBM * p.Dp * 4;
-      const long long arow = (long long)(i0 / kTcBM) * kTcBM * p.Dp;
-      mbar_expect_tx(&bars[BAR_A], 2 * a_bytes);
-      bulk_g2s(smem + L.a_hi, p.xa_hi + arow, a_bytes, &bars[BAR_A]);
-      bulk_g2s(smem + L.a_lo, p.xa_lo + arow, a_bytes, &bars[BAR_A]);
-      for (int j = 0; j < T; ++j) {
-        const int sx = j % kXbStages;
-        mbar_wait(&bars[BAR_XB_EMPTY + sx], ((j / kXbStages) & 1) ^ 1);
-        unsigned char* xb = smem + L.xb + sx * L.xb_stage_bytes;
-        mbar_expect_tx(&bars[BAR_XB_FULL + sx], L.xb_stage_bytes);
-        bulk_g2s(xb, p.xb_hi + (long long)(jbase + j) * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
-        bulk_g2s(xb + L.xb_half, p.xb_lo + (long long)(jbase + j) * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+      int g = 0;
+      for (TcSegIter s(p); s.valid(); s.next()) {
+        // the GEMM1s of the previous segment must have retired before their A operand is overwritten
+        if (s.seg > 0) mbar_wait(&bars[BAR_A_EMPTY], (s.seg - 1) & 1);
+        const long long arow = (long long)(p.row_begin / kTcBM + s.rt) * kTcBM * p.Dp;
+        mbar_expect_tx(&bars[BAR_A], 2 * a_bytes);
+        bulk_g2s(smem + L.a_hi, p.xa_hi + arow, a_bytes, &bars[BAR_A]);
+        bulk_g2s(smem + L.a_lo, p.xa_lo + arow, a_bytes, &bars[BAR_A]);
+        for (int j = 0; j < s.len; ++j, ++g) {
+          const int sx = g % kXbStages;
+          mbar_wait(&bars[BAR_XB_EMPTY + sx], ((g / kXbStages) & 1) ^ 1);
+          unsigned char* xb = smem + L.xb + sx * L.xb_stage_bytes;
+          mbar_expect_tx(&bars[BAR_XB_FULL + sx], L.xb_stage_bytes);
+          bulk_g2s(xb, p.xb_hi + (long long)(s.j0 + j) * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+          bulk_g2s(xb + L.xb_half, p.xb_lo + (long long)(s.j0 + j) * kTcBN * p.Dp, L.xb_half, &bars[BAR_XB_FULL + sx]);
+        }
       }
     }
   } else if (warp == 3) {
     // ------------------------------ producer of the V^T tiles --------------------------
     if (lane == 0) {
-      for (int j = 0; j < T; ++j) {
-        const int sv = j % kVbStages;
-        mbar_wait(&bars[BAR_VB_EMPTY + sv], ((j / kVbStages) & 1) ^ 1);
-        unsigned char* vb = smem + L.vb + sv * L.vb_stage_bytes;
-        mbar_expect_tx(&bars[BAR_VB_FULL + sv], L.vb_stage_bytes);
-        bulk_g2s(vb, p.vb_hi + (long long)(jbase + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
-        bulk_g2s(vb + L.vb_half, p.vb_lo + (long long)(jbase + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
-        bulk_g2s(vb + 2 * L.vb_half, p.xn + (long long)(jbase + j) * kTcBN, kTcBN * 4, &bars[BAR_VB_FULL + sv]);
+      int g = 0;
+      for (TcSegIter s(p); s.valid(); s.next()) {
+        for (int j = 0; j < s.len; ++j, ++g) {
+          const int sv = g % kVbStages;
+          mbar_wait(&bars[BAR_VB_EMPTY + sv], ((g / kVbStages) & 1) ^ 1);
+          unsigned char* vb = smem + L.vb + sv * L.vb_stage_bytes;
+          mbar_expect_tx(&bars[BAR_VB_FULL + sv], L.vb_stage_bytes);
+          bulk_g2s(vb, p.vb_hi + (long long)(s.j0 + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
+          bulk_g2s(vb + L.vb_half, p.vb_lo + (long long)(s.j0 + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
+          bulk_g2s(vb + 2 * L.vb_half, p.xn + (long long)(s.j0 + j) * kTcBN, kTcBN * 4, &bars[BAR_VB_FULL + sv]);
+        }
       }
     }
   } else if (warp == 1) {
@@ -304,14 +398,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       const uint32_t loX0 = (uint32_t)dX, loV0 = (uint32_t)dV;
       const uint32_t xb_stage16 = L.xb_stage_bytes >> 4, xb_half16 = L.xb_half >> 4;
       const uint32_t vb_stage16 = L.vb_stage_bytes >> 4, vb_half16 = L.vb_half >> 4;
-      mbar_wait(&bars[BAR_A], 0);
-      auto gemm2 = [&](int j) {
-        const int b = j & 1, sv = j % kVbStages;
-        mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);
-        mbar_wait(&bars[BAR_P_FULL + b], (j >> 1) & 1);
+      // GEMM2 of running tile g: O[ch & 1] (+)= P[g & 1] V_g; first / last tile of flush chunk ch
+      auto gemm2 = [&](int g, int ch, bool first, bool last) {
+        const int b = g & 1, sv = g % kVbStages;
+        mbar_wait(&bars[BAR_VB_FULL + sv], (g / kVbStages) & 1);
+        mbar_wait(&bars[BAR_P_FULL + b], (g >> 1) & 1);
         tc_fence_after();
-        const int ch = j / kTcChunk, ob = ch & 1;
-        const bool first = (j % kTcChunk) == 0, last = (j % kTcChunk) == kTcChunk - 1 || j == T - 1;
+        const int ob = ch & 1;
         if (first) {  // the flush warps must have drained this O buffer (two chunks ago)
           mbar_wait(&bars[BAR_O_EMPTY + ob], ((ch >> 1) & 1) ^ 1);
           tc_fence_after();
@@ -333,30 +426,41 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         }
         __syncwarp();
       };
-      for (int j = 0; j < T; ++j) {
-        const int b = j & 1, sx = j % kXbStages;
-        mbar_wait(&bars[BAR_XB_FULL + sx], (j / kXbStages) & 1);
-        tc_fence_after();
-        const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
-        const uint32_t tSb = tS + b * kTcBN;
-        if (elect_one_sync()) {
+      int g = 0, cg = 0;                       // running tile / chunk counters
+      int pch = 0;                             // GEMM2 runs one tile behind GEMM1: chunk info of tile g - 1
+      bool pfirst = false, plast = false;
+      for (TcSegIter s(p); s.valid(); s.next()) {
+        mbar_wait(&bars[BAR_A], s.seg & 1);
+        for (int j = 0; j < s.len; ++j, ++g) {
+          const int b = g & 1, sx = g % kXbStages;
+          mbar_wait(&bars[BAR_XB_FULL + sx], (g / kXbStages) & 1);
+          tc_fence_after();
+          const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
+          const uint32_t tSb = tS + b * kTcBN;
+          if (elect_one_sync()) {
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            if (kk < ks1) {
-              const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
-              const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
-              mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
-              mma_ss(tSb, ah, bl, idesc1, 1u);
-              mma_ss(tSb, al, bh, idesc1, 1u);
+            for (int kk = 0; kk < 8; ++kk) {
+              if (kk < ks1) {
+                const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
+                const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+                mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+                mma_ss(tSb, ah, bl, idesc1, 1u);
+                mma_ss(tSb, al, bh, idesc1, 1u);
+              }
             }
+            tc_commit(&bars[BAR_S_FULL + b]);
+            tc_commit(&bars[BAR_XB_EMPTY + sx]);
+            if (j == s.len - 1) tc_commit(&bars[BAR_A_EMPTY]);   // last reader of this segment's A operand
           }
-          tc_commit(&bars[BAR_S_FULL + b]);
-          tc_commit(&bars[BAR_XB_EMPTY + sx]);
+          __syncwarp();
+          if (g >= 1) gemm2(g - 1, pch, pfirst, plast);
+          pch = cg;
+          pfirst = (j % kTcChunk) == 0;
+          plast = (j % kTcChunk) == kTcChunk - 1 || j == s.len - 1;
+          if (plast) ++cg;
         }
-        __syncwarp();
-        if (j >= 1) gemm2(j - 1);
       }
-      gemm2(T - 1);
+      if (g >= 1) gemm2(g - 1, pch, pfirst, plast);
     }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------ softmax warpgroups ---------------------------------
@@ -369,73 +473,81 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     float gamma = p.gamma;
     if (p.gamma_dev) gamma = p.gamma_dev[0];
     const float g2 = gamma * 1.4426950408889634f;  // exp(-g d2) = 2^(-g log2(e) d2)
-    const float xn_i = p.xn[i0 + row];
-    const int jdiag = (i0 + row) / kTcBN;
-    const int cdiag_all = (i0 + row) & (kTcBN - 1);
-    float ksum = 0.f;  // sum_j K_ij over this warpgroup's column halves (exact fp32, no ones column in V)
-    for (int j = 0; j < T; ++j) {
-      const int b = j & 1, it = j >> 1, sv = j % kVbStages;
-      mbar_wait(&bars[BAR_VB_FULL + sv], (j / kVbStages) & 1);   // |x_j|^2 of this tile
-      const float* xnj = reinterpret_cast<const float*>(smem + L.vb + sv * L.vb_stage_bytes + 2 * L.vb_half) + half * 32;
-      mbar_wait(&bars[BAR_S_FULL + b], it & 1);
-      tc_fence_after();
-      uint32_t r[32], lo[32];
-      tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
-      tmem_wait_ld();
-      // the tile that holds column i itself: d2_ii is exactly 0 (the 3xTF32 Gram entry only gives
-      // |x_i|^2 to ~1e-6 relative, which a narrow kernel would amplify)
-      if (jbase + j == jdiag && (cdiag_all >> 5) == half) {
+    int g = 0;
+    for (TcSegIter s(p); s.valid(); s.next()) {
+      const int i0 = p.row_begin + s.rt * kTcBM;   // first global row of this segment's row tile
+      const float xn_i = p.xn[i0 + row];
+      const int jdiag = (i0 + row) / kTcBN;
+      const int cdiag_all = (i0 + row) & (kTcBN - 1);
+      float ksum = 0.f;  // sum_j K_ij over this warpgroup's column halves (exact fp32, no ones column in V)
+      for (int j = 0; j < s.len; ++j, ++g) {
+        const int b = g & 1, it = g >> 1, sv = g % kVbStages;
+        mbar_wait(&bars[BAR_VB_FULL + sv], (g / kVbStages) & 1);   // |x_j|^2 of this tile
+        const float* xnj = reinterpret_cast<const float*>(smem + L.vb + sv * L.vb_stage_bytes + 2 * L.vb_half) + half * 32;
+        mbar_wait(&bars[BAR_S_FULL + b], it & 1);
+        tc_fence_after();
+        uint32_t r[32], lo[32];
+        tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
+        tmem_wait_ld();
+        // the tile that holds column i itself: d2_ii is exactly 0 (the 3xTF32 Gram entry only gives
+        // |x_i|^2 to ~1e-6 relative, which a narrow kernel would amplify)
+        if (s.j0 + j == jdiag && (cdiag_all >> 5) == half) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c)
-          if (c == (cdiag_all & 31)) r[c] = __float_as_uint(0.5f * (xnj[c] + xn_i));  // => d2 = 0
-      }
+          for (int c = 0; c < 32; ++c)
+            if (c == (cdiag_all & 31)) r[c] = __float_as_uint(0.5f * (xnj[c] + xn_i));  // => d2 = 0
+        }
 #pragma unroll
-      for (int c = 0; c < 32; ++c) {
-        const float sv_ = __uint_as_float(r[c]);
-        const float d2 = fmaxf((xnj[c] - 2.0f * sv_) + xn_i, 0.f);
-        const float kv = ex2_approx(-g2 * d2);
-        ksum += kv;
-        const float hi = tf32_hi(kv);
-        r[c] = __float_as_uint(hi);
-        lo[c] = __float_as_uint(tf32_lo(kv, hi));
+        for (int c = 0; c < 32; ++c) {
+          const float sv_ = __uint_as_float(r[c]);
+          const float d2 = fmaxf((xnj[c] - 2.0f * sv_) + xn_i, 0.f);
+          const float kv = ex2_approx(-g2 * d2);
+          ksum += kv;
+          const float hi = tf32_hi(kv);
+          r[c] = __float_as_uint(hi);
+          lo[c] = __float_as_uint(tf32_lo(kv, hi));
+        }
+        // P_hi overwrites the S columns it came from; GEMM2(g-2) must be done with P[b]
+        mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
+        tc_fence_after();
+        tmem_st32(tPhi + lane_base + b * kTcBN + half * 32, r);
+        tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
       }
-      // P_hi overwrites the S columns it came from; GEMM2(j-2) must be done with P[b]
-      mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
-      tc_fence_after();
-      tmem_st32(tPhi + lane_base + b * kTcBN + half * 32, r);
-      tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
+      oacc_cta[(size_t)s.seg * slot_stride + (size_t)(p.NV + half) * kTcBM + row] = ksum;
     }
-    p.oacc[(size_t)blockIdx.x * (p.NV + 2) * kTcBM + (size_t)(p.NV + half) * kTcBM + row] = ksum;
   } else if (warp >= 12) {
     // ------------------------------ flush warpgroup + epilogue -------------------------
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    // running sums live in a per-CTA global scratch, column-major ([NV][128]: a warp touches 128
-    // contiguous bytes per column); only 32 columns are in registers at any time
-    float* og = p.oacc + (size_t)blockIdx.x * (p.NV + 2) * kTcBM + row;
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int ob = ch & 1;
-      mbar_wait(&bars[BAR_O_FULL + ob], (ch >> 1) & 1);
-      tc_fence_after();
-      for (int c0 = 0; c0 < p.NV; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tO + lane_base + ob * p.NV + c0, r);
-        tmem_wait_ld();
+    // running sums live in a per-segment global scratch, column-major ([NV][128]: a warp touches 128
+    // contiguous bytes per column); only 16 columns are in registers at any time
+    int cg = 0;
+    for (TcSegIter s(p); s.valid(); s.next()) {
+      float* og = oacc_cta + (size_t)s.seg * slot_stride + row;
+      const int n_chunks = (s.len + kTcChunk - 1) / kTcChunk;
+      for (int ch = 0; ch < n_chunks; ++ch, ++cg) {
+        const int ob = cg & 1;
+        mbar_wait(&bars[BAR_O_FULL + ob], (cg >> 1) & 1);
+        tc_fence_after();
+        for (int c0 = 0; c0 < p.NV; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tO + lane_base + ob * p.NV + c0, r);
+          tmem_wait_ld();
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          float v = __uint_as_float(r[c]);
-          if (ch > 0) v += og[(size_t)(c0 + c) * kTcBM];
-          og[(size_t)(c0 + c) * kTcBM] = v;
+          for (int c = 0; c < 16; ++c) {
+            float v = __uint_as_float(r[c]);
+            if (ch > 0) v += og[(size_t)(c0 + c) * kTcBM];
+            og[(size_t)(c0 + c) * kTcBM] = v;
+          }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_O_EMPTY + ob]);
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[BAR_O_EMPTY + ob]);
     }
   }
   tc_fence_before();
@@ -445,21 +557,30 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   }
 }
 
-// combine the per-CTA partial sums of one row tile and form phi (coalesced: thread <-> row)
+// combine the partial sums of one row tile (every segment that worked on it, in CTA order) and form
+// phi; grid (row tiles, ceil(D / 8)): thread <-> row, 8 dimensions per CTA
 __global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) {
   const int rt = blockIdx.x, row = threadIdx.x;
   const int gi = p.row_begin + rt * kTcBM + row;
   float c1 = p.c1, c2 = p.c2;
   if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
-  const size_t cta_stride = (size_t)(p.NV + 2) * kTcBM;
-  const float* og = p.oacc + (size_t)rt * p.ksplit * cta_stride + row;
+  const size_t slot_stride = (size_t)(p.NV + 2) * kTcBM;
+  const long long W = p.units_per_cta, T = p.T;
+  const int c_first = (int)((rt * T) / W), c_last = (int)(((rt + 1) * T - 1) / W);
+  // slot of CTA c's segment on row tile rt: its segments start at row tile (c * W) / T
+  auto slot = [&](int c) { return p.oacc + ((size_t)c * p.max_seg + (size_t)(rt - (c * W) / T)) * slot_stride + row; };
   float ksum = 0.f;
-  for (int h = 0; h < p.ksplit; ++h) ksum += og[h * cta_stride + (size_t)p.NV * kTcBM] + og[h * cta_stride + (size_t)(p.NV + 1) * kTcBM];
-  for (int d = 0; d < p.D; ++d) {
+  for (int c = c_first; c <= c_last; ++c) {
+    const float* og = slot(c);
+    ksum += og[(size_t)p.NV * kTcBM] + og[(size_t)(p.NV + 1) * kTcBM];
+  }
+  const int d0 = blockIdx.y * 8, d1 = min(d0 + 8, p.D);
+  for (int d = d0; d < d1; ++d) {
     float ks = 0.f, kx = 0.f;  // sum_j K s_j, sum_j K x_j
-    for (int h = 0; h < p.ksplit; ++h) {
-      ks += og[h * cta_stride + (size_t)d * kTcBM];
-      kx += og[h * cta_stride + (size_t)(p.D + d) * kTcBM];
+    for (int c = c_first; c <= c_last; ++c) {
+      const float* og = slot(c);
+      ks += og[(size_t)d * kTcBM];
+      kx += og[(size_t)(p.D + d) * kTcBM];
     }
     const float xv = p.x[(long long)gi * p.D + d];
     const float ph = c1 * ks + c2 * (ksum * xv - kx);
@@ -468,17 +589,19 @@ __global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) 
   }
 }
 
-// CTAs per row tile so that the grid fills whole waves of the 148 SMs
-static int choose_ksplit(int row_tiles, int T) {
-  int best = 1;
-  double best_cost = 1e30;
-  for (int ks = 1; ks <= 8; ++ks) {
-    if (T % ks) continue;
-    const int waves = ceil_div((long long)row_tiles * ks, kNumSMs);
-    const double cost = (double)waves / ks + 0.004 * ks;  // tiny per-CTA overhead term
-    if (cost < best_cost - 1e-9) { best_cost = cost; best = ks; }
-  }
-  return best;
+// equal contiguous unit ranges over at most one CTA per SM; a floor on the range length keeps the
+// per-CTA prologue (TMEM allocation, A operand, pipeline fill, O drain: ~5 tile times) amortised
+struct TcPlan { int grid, units_per_cta, total_units, max_seg; };
+static TcPlan tc_plan(int row_tiles, int T) {
+  TcPlan pl;
+  pl.total_units = row_tiles * T;
+  const int floor_units = T < 16 ? T : 16;
+  int W = ceil_div(pl.total_units, kNumSMs);
+  if (W < floor_units) W = floor_units;
+  pl.units_per_cta = W;
+  pl.grid = ceil_div(pl.total_units, W);
+  pl.max_seg = (W + T - 2) / T + 1;
+  return pl;
 }
 
 // =======================================================================================
@@ -500,71 +623,113 @@ __device__ __forceinline__ uint32_t hash32(uint32_t x) {
   return x;
 }
 
-// hist32[32768]: hi-16-bit histogram of the sample (non-negative floats: bits >> 16 < 32768)
-__global__ void med_sample_kernel(const float* __restrict__ x, const float* __restrict__ xn, int N, int D,
-                                  unsigned int* __restrict__ hist32) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= kMedSample) return;
-  const uint32_t i = hash32(2u * k + 1u) % (uint32_t)N, j = hash32(2u * k + 0x9e3779b9u) % (uint32_t)N;
-  const float* __restrict__ xi = x + (long long)i * D;
-  const float* __restrict__ xj = x + (long long)j * D;
-  float dot = 0.f;
-  if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0)) {   // rows are 16-byte aligned: independent 128-bit loads
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int d = 0; d < D; d += 4) {
-      const float4 a = __ldg(reinterpret_cast<const float4*>(xi + d)), b = __ldg(reinterpret_cast<const float4*>(xj + d));
-      acc.x = fmaf(a.x, b.x, acc.x); acc.y = fmaf(a.y, b.y, acc.y); acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);
-    }
-    dot = (acc.x + acc.y) + (acc.z + acc.w);
-  } else {
-    for (int d = 0; d < D; ++d) dot = fmaf(xi[d], xj[d], dot);
+constexpr int kMedSampleGrid = kNumSMs, kMedSampleThreads = 1024;
+
+// first index q of arr[0 .. 32 * per_lane) whose running sum exceeds `rank` (cum = the sum before q), found
+// by one whole warp: a serial pass over per_lane consecutive entries per lane, a shuffle scan across
+// the lanes, and a second serial pass inside the lane that holds the rank.  q = -1 if the total <= rank.
+template <typename T>
+__device__ __forceinline__ void warp_find_rank(const T* arr, int per_lane, unsigned long long rank, int& q, unsigned long long& cum) {
+  const int lane = threadIdx.x & 31;
+  unsigned long long s = 0;
+  for (int i = 0; i < per_lane; ++i) s += (unsigned long long)arr[lane * per_lane + i];
+  unsigned long long incl = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
   }
-  const float d2 = (i == j) ? 0.f : fmaxf((xn[j] - 2.0f * dot) + xn[i], 0.f);
-  // the sample lands in a handful of bins: one atomic per distinct bin per warp, not one per thread
-  const uint32_t bin = __float_as_uint(d2) >> 16;
-  const uint32_t peers = __match_any_sync(__activemask(), bin);
-  if ((threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) atomicAdd(&hist32[bin], (unsigned int)__popc(peers));
+  const unsigned long long excl = incl - s;
+  const unsigned int hit = __ballot_sync(0xffffffffu, excl <= rank && rank < incl);
+  q = -1; cum = 0;
+  if (hit == 0) return;
+  const int src = __ffs(hit) - 1;
+  int qq = 0;
+  unsigned long long cc = excl;
+  if (lane == src) {
+    for (int i = 0; i < per_lane; ++i) {
+      const unsigned long long v = (unsigned long long)arr[lane * per_lane + i];
+      if (cc + v > rank) { qq = lane * per_lane + i; break; }
+      cc += v;
+    }
+  }
+  q = __shfl_sync(0xffffffffu, qq, src);
+  cum = __shfl_sync(0xffffffffu, cc, src);
+}
+
+// hist32[32768]: hi-16-bit histogram of the sample (non-negative floats: bits >> 16 < 32768).
+// One CTA per SM keeps the whole histogram in shared memory (128 KB) and adds its non-empty bins to
+// the global one at the end (the sample spreads over a few hundred bins: per-sample global atomics
+// queue up on them).
+__global__ void __launch_bounds__(kMedSampleThreads) med_sample_kernel(const float* __restrict__ x, const float* __restrict__ xn,
+                                                                       int N, int D, unsigned int* __restrict__ hist32) {
+  extern __shared__ unsigned int hs[];   // [32768]
+  for (int b = threadIdx.x; b < 32768; b += blockDim.x) hs[b] = 0u;
+  __syncthreads();
+  const bool vec = (D & 3) == 0 && ((((uintptr_t)x) & 15) == 0);   // rows are 16-byte aligned: independent 128-bit loads
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < kMedSample; k += gridDim.x * blockDim.x) {
+    const uint32_t i = hash32(2u * k + 1u) % (uint32_t)N, j = hash32(2u * k + 0x9e3779b9u) % (uint32_t)N;
+    const float* __restrict__ xi = x + (long long)i * D;
+    const float* __restrict__ xj = x + (long long)j * D;
+    float dot = 0.f;
+    if (vec) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int d = 0; d < D; d += 4) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(xi + d)), b = __ldg(reinterpret_cast<const float4*>(xj + d));
+        acc.x = fmaf(a.x, b.x, acc.x); acc.y = fmaf(a.y, b.y, acc.y); acc.z = fmaf(a.z, b.z, acc.z); acc.w = fmaf(a.w, b.w, acc.w);
+      }
+      dot = (acc.x + acc.y) + (acc.z + acc.w);
+    } else {
+      for (int d = 0; d < D; ++d) dot = fmaf(xi[d], xj[d], dot);
+    }
+    const float d2 = (i == j) ? 0.f : fmaxf((xn[j] - 2.0f * dot) + xn[i], 0.f);
+    atomicAdd(&hs[__float_as_uint(d2) >> 16], 1u);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < 32768; b += blockDim.x) {
+    const unsigned int c = hs[b];
+    if (c) atomicAdd(&hist32[b], c);
+  }
 }
 
 // state[0] = window start (bit pattern), state[1] = ok flag (cleared here), state[2] = window width.
 // The median's position inside its hi-16 bin is interpolated from the sample counts; the window is
 // that position +- the bit-pattern distance that holds 8 standard deviations of the sample median's
 // quantile (0.5/sqrt(m)), clamped to [4096, kMedWindowBins/2] patterns.
-__global__ void med_sample_select_kernel(unsigned int* hist32, uint32_t* state) {
+__global__ void __launch_bounds__(1024) med_sample_select_kernel(unsigned int* hist32, uint32_t* state) {
   __shared__ unsigned int part[1024];
-  const int t = threadIdx.x;
-  unsigned int s = 0;
-  for (int b = 0; b < 32; ++b) s += hist32[t * 32 + b];
-  part[t] = s;
-  __syncthreads();
-  if (t == 0) {
-    const unsigned int rank = (kMedSample - 1) / 2;
-    unsigned int cum = 0, in_bin = 1;
-    int bin = 32767;
-    for (int q = 0; q < 1024; ++q) {
-      if (cum + part[q] > rank) {
-        for (int b = 0; b < 32; ++b) {
-          const unsigned int h = hist32[q * 32 + b];
-          if (cum + h > rank) { bin = q * 32 + b; in_bin = h; break; }
-          cum += h;
-        }
-        break;
-      }
-      cum += part[q];
-    }
-    const double frac = ((double)(rank - cum) + 0.5) / (double)in_bin;               // position inside the bin
-    const double centre = (double)bin * 65536.0 + frac * 65536.0;
-    const double mass_per_pattern = (double)in_bin / (double)kMedSample / 65536.0;   // local density estimate
-    double hw = 8.0 * (0.5 / sqrt((double)kMedSample)) / mass_per_pattern;
-    hw = fmin(fmax(hw, 4096.0), (double)(kMedWindowBins / 2));
-    double lo = centre - hw;
-    if (lo < 0.0) lo = 0.0;
-    state[0] = (uint32_t)lo;
-    state[1] = 0u;
-    state[2] = (uint32_t)(2.0 * hw);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  for (int q = warp; q < 1024; q += 32) {   // one warp per chunk of 32 bins: coalesced reads
+    const unsigned int s = __reduce_add_sync(0xffffffffu, hist32[q * 32 + lane]);
+    if (lane == 0) part[q] = s;
   }
   __syncthreads();
-  for (int b = 0; b < 32; ++b) hist32[t * 32 + b] = 0u;
+  if (warp == 0) {
+    const unsigned long long rank = (kMedSample - 1) / 2;
+    int q, b;
+    unsigned long long cum, cum_b;
+    warp_find_rank(part, 32, rank, q, cum);
+    int bin = 32767;
+    unsigned int in_bin = 1;
+    if (q >= 0) {
+      warp_find_rank(hist32 + q * 32, 1, rank - cum, b, cum_b);
+      if (b >= 0) { bin = q * 32 + b; in_bin = hist32[bin]; cum += cum_b; }
+    }
+    if (lane == 0) {
+      const double frac = ((double)(rank - cum) + 0.5) / (double)in_bin;               // position inside the bin
+      const double centre = (double)bin * 65536.0 + frac * 65536.0;
+      const double mass_per_pattern = (double)in_bin / (double)kMedSample / 65536.0;   // local density estimate
+      double hw = 8.0 * (0.5 / sqrt((double)kMedSample)) / mass_per_pattern;
+      hw = fmin(fmax(hw, 4096.0), (double)(kMedWindowBins / 2));
+      double lo = centre - hw;
+      if (lo < 0.0) lo = 0.0;
+      state[0] = (uint32_t)lo;
+      state[1] = 0u;
+      state[2] = (uint32_t)(2.0 * hw);
+    }
+  }
+  __syncthreads();
+  for (int b = t; b < 32768; b += 1024) hist32[b] = 0u;
 }
 
 struct MedTcParams {
@@ -737,48 +902,42 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
 }
 
 // rank (N^2-1)/2 inside the window; state[1] = 1 and the median on success
-__global__ void __launch_bounds__(1024) med_window_select_kernel(unsigned long long* hist, uint32_t* state,
+__global__ void __launch_bounds__(1024) med_window_select_kernel(const unsigned long long* hist, uint32_t* state,
                                                                  long long n_total, float* median_out) {
   __shared__ unsigned long long part[1024];
   constexpr int PER = kMedWindowBins / 1024;  // 192 bins per chunk
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   for (int q = warp; q < 1024; q += 32) {   // one warp per chunk: coalesced reads
     unsigned long long s = 0;
-    for (int b = lane; b < PER; b += 32) s += hist[q * PER + b];
+#pragma unroll
+    for (int b = 0; b < PER / 32; ++b) s += hist[q * PER + b * 32 + lane];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) part[q] = s;
   }
   __syncthreads();
-  if (t == 0) {
+  if (warp == 0) {
     const unsigned long long below = hist[kMedWindowBins];
     const unsigned long long k = (unsigned long long)((n_total - 1) / 2);
-    unsigned long long total = 0;
-    for (int q = 0; q < 1024; ++q) total += part[q];
-    int ok = (k >= below) && (k - below < total);
-    if (ok) {
-      const unsigned long long rank = k - below;
-      unsigned long long cum = 0;
-      int ch = 1023;
-      for (int q = 0; q < 1024; ++q) {
-        if (cum + part[q] > rank) { ch = q; break; }
-        cum += part[q];
+    int ok = 0;
+    if (k >= below) {
+      int ch, b;
+      unsigned long long cum, cum_b;
+      warp_find_rank(part, 32, k - below, ch, cum);          // -1: the rank lies above the window
+      if (ch >= 0) {
+        warp_find_rank(hist + ch * PER, PER / 32, k - below - cum, b, cum_b);
+        if (b >= 0) {
+          ok = 1;
+          if (lane == 0) {
+            const uint32_t bits = state[0] + (uint32_t)(ch * PER + b);
+            state[3] = bits;
+            if (median_out) *median_out = __uint_as_float(bits);
+          }
+        }
       }
-      int bin = ch * PER + PER - 1;
-      for (int b = 0; b < PER; ++b) {
-        const unsigned long long h = hist[ch * PER + b];
-        if (cum + h > rank) { bin = ch * PER + b; break; }
-        cum += h;
-      }
-      const uint32_t bits = state[0] + (uint32_t)bin;
-      state[3] = bits;
-      if (median_out) *median_out = __uint_as_float(bits);
     }
-    state[1] = ok ? 1u : 0u;
+    if (lane == 0) state[1] = ok ? 1u : 0u;
   }
-  __syncthreads();
-  for (int b = t; b < kMedWindowBins; b += 1024) hist[b] = 0ull;  // leave the buffer clean for the fallback / next call
-  if (t == 0) hist[kMedWindowBins] = 0ull;
 }
 
 bool median_tc_supported(int N, int D) {
@@ -788,7 +947,7 @@ bool median_tc_supported(int N, int D) {
 }
 size_t median_tc_workspace(int N, int D) {
   const size_t Dp = round_up(D, 8);
-  return sizeof(float) * ((size_t)N * (4 * Dp + 1) + 64) + sizeof(unsigned int) * 32768;
+  return sizeof(float) * ((size_t)N * (2 * Dp + 1) + 64) + sizeof(unsigned int) * 32768;
 }
 
 // sample + window (run by every rank on the same gathered X: no communication needed)
@@ -796,20 +955,16 @@ int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t s
   const int N = a->N, D = a->D, Dp = round_up(D, 8);
   float* ws = (float*)workspace;
   float* xn = ws;    ws += (N + 63) / 64 * 64;
-  float* xa_hi = ws; ws += (size_t)N * Dp;
-  float* xa_lo = ws; ws += (size_t)N * Dp;
-  float* xb_hi = ws; ws += (size_t)N * Dp;
-  float* xb_lo = ws; ws += (size_t)N * Dp;
+  float* x_hi = ws;  ws += (size_t)N * Dp;
+  float* x_lo = ws;  ws += (size_t)N * Dp;
   unsigned int* hist32 = (unsigned int*)ws;
   DUST_CUDA_OK(cudaMemsetAsync(hist32, 0, sizeof(unsigned int) * 32768, stream));
-  {
-    DUST_TIMED("tc_prep_x_kernel", stream);
-    tc_prep_x_kernel<<<ceil_div((long long)N * Dp, 256), 256, 0, stream>>>(a->x, N, D, Dp, xa_hi, xa_lo, xb_hi, xb_lo, xn);
-  }
-  DUST_LAUNCH_OK("tc_prep_x_kernel");
+  int rc = tc_prep(a->x, nullptr, N, D, Dp, 0, x_hi, x_lo, nullptr, nullptr, xn, stream);
+  if (rc != DUST_OK) return rc;
+  DUST_CUDA_OK(cudaFuncSetAttribute(med_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned int) * 32768)));
   {
     DUST_TIMED("med_sample_kernel", stream);
-    med_sample_kernel<<<kMedSample / 256, 256, 0, stream>>>(a->x, xn, N, D, hist32);
+    med_sample_kernel<<<kMedSampleGrid, kMedSampleThreads, sizeof(unsigned int) * 32768, stream>>>(a->x, xn, N, D, hist32);
   }
   DUST_LAUNCH_OK("med_sample_kernel");
   {
@@ -824,23 +979,23 @@ int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t str
   const int N = a->N, D = a->D, Dp = round_up(D, 8);
   float* ws = (float*)workspace;
   float* xn = ws;    ws += (N + 63) / 64 * 64;
-  float* xa_hi = ws; ws += (size_t)N * Dp;
-  float* xa_lo = ws; ws += (size_t)N * Dp;
-  float* xb_hi = ws; ws += (size_t)N * Dp;
-  float* xb_lo = ws;
+  float* x_hi = ws;  ws += (size_t)N * Dp;
+  float* x_lo = ws;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
   const int row_tiles = (r1 - r0) / kTcBM;
+  if (row_tiles == 0) return DUST_OK;
   // half band of (N/128)/2 + 1 column blocks (two 64-wide tiles each) per row tile, cut into ksplit chunks
+  // (the chunks only feed integer counters: any split gives the same histogram)
   const int T = N / kTcBN, kcount = (kTcBM / kTcBN) * ((N / kTcBM) / 2 + 1);
   int ksplit = 1, kchunk = kcount;
   double best_cost = 1e30;
-  for (int ks = 1; ks <= 8 && ks <= kcount; ++ks) {
+  for (int ks = 1; ks <= 64 && ks <= kcount; ++ks) {
     const int chunk = ceil_div(kcount, ks);
     if ((ks - 1) * chunk >= kcount) continue;   // would leave a CTA without tiles
-    const double cost = (double)ceil_div((long long)row_tiles * ks, kNumSMs) * (chunk + 1.5);  // + per-CTA prologue
+    const double cost = (double)ceil_div((long long)row_tiles * ks, kNumSMs) * (chunk + 3.0);  // + per-CTA prologue
     if (cost < best_cost - 1e-9) { best_cost = cost; ksplit = ks; kchunk = chunk; }
   }
-  MedTcParams p{N, Dp, T, r0, ksplit, kcount, kchunk, xa_hi, xa_lo, xb_hi, xb_lo, xn, a->selected + 4, a->hist};
+  MedTcParams p{N, Dp, T, r0, ksplit, kcount, kchunk, x_hi, x_lo, x_hi, x_lo, xn, a->selected + 4, a->hist};
   const size_t smem = med_smem_bytes(Dp);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
@@ -857,6 +1012,8 @@ int median_tc_select(const dust_median_args* a, float* median_out, cudaStream_t 
     med_window_select_kernel<<<1, 1024, 0, stream>>>(a->hist, a->selected + 4, (long long)a->N * a->N, median_out);
   }
   DUST_LAUNCH_OK("med_window_select_kernel");
+  // leave the buffer clean for the fallback / next call
+  DUST_CUDA_OK(cudaMemsetAsync(a->hist, 0, sizeof(unsigned long long) * (kMedWindowBins + 1), stream));
   return DUST_OK;
 }
 
@@ -874,8 +1031,9 @@ bool phi_tc_supported(const dust_phi_args* a) {
 
 size_t phi_tc_workspace(const dust_phi_args* a) {
   const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
-  const size_t rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
-  return sizeof(float) * (N * (4 * Dp + 2 * NV + 1) + 64 + rows * 8 * (NV + 2));  // up to 8 column splits
+  const int rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
+  const TcPlan pl = tc_plan(rows / kTcBM, a->N / kTcBN);
+  return sizeof(float) * (N * (2 * Dp + 2 * NV + 1) + 64 + (size_t)pl.grid * pl.max_seg * (NV + 2) * kTcBM);
 }
 
 int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
@@ -884,40 +1042,34 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
                "dust_svgd_phi: tensor-core path needs %zu bytes of workspace", phi_tc_workspace(a));
   float* ws = (float*)a->workspace;
   float* xn = ws;              ws += (N + 63) / 64 * 64;
-  float* xa_hi = ws;           ws += (size_t)N * Dp;
-  float* xa_lo = ws;           ws += (size_t)N * Dp;
-  float* xb_hi = ws;           ws += (size_t)N * Dp;
-  float* xb_lo = ws;           ws += (size_t)N * Dp;
+  float* x_hi = ws;            ws += (size_t)N * Dp;
+  float* x_lo = ws;            ws += (size_t)N * Dp;
   float* vb_hi = ws;           ws += (size_t)N * NV;
   float* vb_lo = ws;           ws += (size_t)N * NV;
   float* oacc = ws;
-  {
-    DUST_TIMED("tc_prep_x_kernel", stream);
-    tc_prep_x_kernel<<<ceil_div((long long)N * Dp, 256), 256, 0, stream>>>(a->x, N, D, Dp, xa_hi, xa_lo, xb_hi, xb_lo, xn);
-  }
-  DUST_LAUNCH_OK("tc_prep_x_kernel");
-  {
-    DUST_TIMED("tc_prep_v_kernel", stream);
-    tc_prep_v_kernel<<<ceil_div((long long)N * NV, 256), 256, 0, stream>>>(a->x, a->score, N, D, NV, vb_hi, vb_lo);
-  }
-  DUST_LAUNCH_OK("tc_prep_v_kernel");
+  int rc = tc_prep(a->x, a->score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream);
+  if (rc != DUST_OK) return rc;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
+  const int row_tiles = (r1 - r0) / kTcBM;
+  if (row_tiles == 0) return DUST_OK;
   TcParams p;
   p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0;
-  p.xa_hi = xa_hi; p.xa_lo = xa_lo; p.xb_hi = xb_hi; p.xb_lo = xb_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
+  // a 128-row tile and a 64-row tile of the core-matrix image are both whole 8-row groups in row order:
+  // ONE image serves as the A operand (row tiles) and as the B operand (column tiles)
+  p.xa_hi = x_hi; p.xa_lo = x_lo; p.xb_hi = x_hi; p.xb_lo = x_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
   p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out; p.oacc = oacc;
+  const TcPlan pl = tc_plan(row_tiles, p.T);
+  p.units_per_cta = pl.units_per_cta; p.total_units = pl.total_units; p.max_seg = pl.max_seg;
   const TcSmem L = tc_smem_layout(Dp, NV);
   DUST_CUDA_OK(cudaFuncSetAttribute(phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  const int row_tiles = (r1 - r0) / kTcBM;
-  p.ksplit = choose_ksplit(row_tiles, p.T);
   {
     DUST_TIMED("phi_tc_kernel", stream);
-    phi_tc_kernel<<<row_tiles * p.ksplit, kTcThreads, L.total, stream>>>(p);
+    phi_tc_kernel<<<pl.grid, kTcThreads, L.total, stream>>>(p);
   }
   DUST_LAUNCH_OK("phi_tc_kernel");
   {
     DUST_TIMED("phi_tc_finish_kernel", stream);
-    phi_tc_finish_kernel<<<row_tiles, kTcBM, 0, stream>>>(p);
+    phi_tc_finish_kernel<<<dim3(row_tiles, ceil_div(D, 8)), kTcBM, 0, stream>>>(p);
   }
   DUST_LAUNCH_OK("phi_tc_finish_kernel");
   return DUST_OK;

@@ -45,6 +45,9 @@ class SVMPC(SVGD):
         self._prior_cov = cov
         mix = prior.mixture_distribution.probs.detach().to(dev, torch.float32)
         mode, ell, scale = _kernel_mode(self.kernel)
+        if getattr(ctrl, "a_reg", 0) != 0 or getattr(ctrl, "_tf", None) is not None:
+            raise NotImplementedError("SVMPC drives the rollout kernel directly: a controller with ctrl_penalty != 1 or "
+                                      "sigma-point parameter tiling is only supported stand-alone (MultiDISCO.forward)")
         if self.optimizer_class is not torch.optim.SGD or any(
                 k in self.opt_args and self.opt_args[k] for k in ("momentum", "weight_decay", "nesterov", "dampening")):
             raise NotImplementedError("SVMPC: only plain SGD is fused into the update kernel "

@@ -25,9 +25,11 @@ def _ws(nbytes, device):
 
 def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param_tiling=L.PARAMS_BLOCKED,
                  likelihood=L.LIK_EXP_UTILITY, a_seq=None, pert=None, alpha=1.0, temperature=1.0,
-                 want=("costs", "log_lik"), out=None):
+                 want=("costs", "log_lik"), out=None, sigma_weights=None, ctrl_mat=None, ctrl_reg=0.0):
     """K1.  noise [B,S,N,H,A]; theta [B,N,H,A] or None (noise = actions); params [B,P,dp] or None.
     `want` subset of {costs, log_lik, lik_weights, grad_lik, mppi_weights, mppi_delta, mix, states}.
+    sigma_weights [P]: unscented-transform mode (params = the sigma points, disco.py:211-323);
+    ctrl_mat [B,N,H,A] + ctrl_reg: control regulariser (disco.py:334-344).
     Returns a dict of CUDA tensors."""
     L.require_cuda()
     dev = noise.device
@@ -50,6 +52,9 @@ def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param
     a.state0, a.theta, a.noise = L.ptr(state0), L.ptr(theta), L.ptr(noise)
     a.sigma, a.params, a.a_seq, a.pert = L.ptr(sigma), L.ptr(params), L.ptr(a_seq), L.ptr(pert)
     a.alpha, a.temperature = float(alpha), float(temperature)
+    if sigma_weights is not None:
+        assert sigma_weights.numel() == P and params is not None
+    a.sigma_weights, a.ctrl_mat, a.ctrl_reg = L.ptr(sigma_weights), L.ptr(ctrl_mat), float(ctrl_reg)
     for k in shapes:
         setattr(a, k, L.ptr(out.get(k)) if k in want else None)
     nbytes = L.load().dust_rollout_workspace_bytes(C.byref(a))

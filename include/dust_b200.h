@@ -117,6 +117,17 @@ typedef struct dust_rollout_args {
                                 (internal sampling, disco.py:157-160); overrides a_seq */
   float alpha;               /* likelihood inverse temperature (likelihoods.py:105,123)*/
   float temperature;         /* controller temperature (disco.py:89)                   */
+  const float* sigma_weights;/* [P] or NULL: unscented-transform mode (MultiDISCO._sigma_rollout,
+                                disco.py:211-292): `params` holds the P = 2n+1 sigma points and the
+                                trajectory cost is the reference's weighted sum (disco.py:312-323,
+                                INCLUDING its grouping of the instantaneous costs: the flat
+                                (sigma point, step) index m = p*H + t takes weight [m mod P], and
+                                each run of P consecutive m is one dot product) instead of the
+                                mean over P                                            */
+  const float* ctrl_mat;     /* [B, N, H, A] or NULL: a_mat @ a_pre; with ctrl_reg it adds the control
+                                regulariser ctrl_reg * sum_{h,a} (a_seq - action) * ctrl_mat[n]
+                                (disco.py:334-344) to every trajectory cost           */
+  float ctrl_reg;            /* a_reg = temperature * (1 - ctrl_penalty) (disco.py:90)   */
   /* outputs (any may be NULL) */
   float* costs;              /* [B, S, N]      trajectory costs, mean over P           */
   float* log_lik;            /* [B, N]         likelihoods.py:113-135                  */

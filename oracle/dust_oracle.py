@@ -199,6 +199,60 @@ def disco_forward(model, state, actions, params=None, log_space=False, temp=1.0,
     return dict(costs=costs, states=states, weights=w, delta=delta, a_mix=a_mix)
 
 
+def merwe_weights(n, alpha=1e-3, beta=2.0, kappa=0.0):
+    """utf.py:81-91 -> (loc_weights, cov_weights), float32 [2n+1]."""
+    lam = alpha ** 2 * (n + kappa) - n
+    c = 0.5 / (n + lam)
+    loc = torch.ones(2 * n + 1, dtype=torch.float) * c
+    cov = torch.ones(2 * n + 1, dtype=torch.float) * c
+    cov[0] = lam / (n + lam) + (1 - alpha ** 2 + beta)
+    loc[0] = lam / (n + lam)
+    return loc, cov
+
+
+def merwe_sigma_points(mu, K, alpha=1e-3, kappa=0.0):
+    """utf.py:93-123 -> sigmas [n, 2n+1] (upper Cholesky factor U of (lambda + n) K; mu[i] is added to ROW i)."""
+    mu, K = torch.as_tensor(mu, dtype=torch.float), torch.as_tensor(K, dtype=torch.float)
+    n = mu.shape[0]
+    lam = alpha ** 2 * (n + kappa) - n
+    U = torch.linalg.cholesky(((lam + n) * K).transpose(-2, -1)).transpose(-2, -1)
+    sig = torch.zeros(n, 2 * n + 1, dtype=torch.float)
+    sig[:, 0] = mu
+    sig[:, 1:n + 1] = U + mu.view(-1, 1)
+    sig[:, n + 1:] = -U + mu.view(-1, 1)
+    return sig
+
+
+def disco_forward_sigma(model, state, actions, sigmas, loc_w, temp=1.0, a_seq=None):
+    """MultiDISCO.forward with a MerweScaledUTF transformer (disco.py:211-292, 312-323, 380-393).
+    actions [S,N,H,A]; sigmas [n, pts].  Rollout row r = (s*N + n)*pts + k carries action row (s, n) and
+    sigma point k.  Cost quirk reproduced: the flat instantaneous costs (index r*H + t) are viewed as
+    (-1, pts), i.e. weighted in runs of pts CONSECUTIVE (k, t) entries, not across the sigma points of
+    one step; the terminal costs (index r) are grouped by sigma point as intended.
+    Returns dict(costs [S,N], states [S*pts, N, H+1, ds], weights, delta, a_mix)."""
+    S, N, H, A = actions.shape
+    pts = sigmas.shape[1]
+    acts = actions.repeat(1, 1, pts, 1).reshape(-1, H, A)          # disco.py:257-259
+    prm = sigmas.T.repeat(S * N, 1)                                 # disco.py:262-264
+    x = state.reshape(1, -1).to(actions.dtype).expand(S * N * pts, -1)
+    states = [x]
+    for t in range(H):
+        x = model.step(x, acts[:, t], prm)
+        states.append(x)
+    states = torch.stack(states, dim=1).reshape(S * pts, N, H + 1, model.ds)   # disco.py:281-284 (relabels rows)
+    x_vec = states[..., :-1, :].reshape(-1, model.ds)
+    x_fin = states[..., -1, :].reshape(-1, model.ds)
+    a_vec = actions.reshape(-1, A)     # only its shape matters for the pendulum cost; see below for the particle
+    if model.kind == "particle":       # inst_cost_fn(x_vec, a_vec) needs matching rows: the reference would fail here
+        raise NotImplementedError("sigma-point costs with an action-dependent cost: shapes differ in the reference")
+    inst = model.inst_cost(x_vec, a_vec).reshape(-1, pts) @ loc_w
+    term = model.term_cost(x_fin).reshape(-1, pts) @ loc_w
+    costs = inst.view(S, N, H).sum(dim=-1) + term.view(S, N)
+    eps = actions if a_seq is None else actions - a_seq
+    w, delta, a_mix = softmin_update(costs, eps, temp)
+    return dict(costs=costs, states=states, weights=w, delta=delta, a_mix=a_mix)
+
+
 def disco_step(a_mat, a_mix, low, high, strategy="argmax", steps=1):
     """disco.py:396-417.  Returns (next_actions[steps,A], a_seq', a_mat').
     Quirk: with "argmax" the reference's a_seq is a VIEW of a_mat[i*] (integer-like index), so

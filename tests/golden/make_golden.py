@@ -612,8 +612,82 @@ def gen_episode():
          n_param_draws=np.array(len(dyn.samples)))
 
 
+# ----------------------------------------------------------------------------------
+# G9: the next rows of SURVEY 8(f): control regulariser (ctrl_penalty != 1, disco.py:334-344) and
+# sigma-point rollouts (MerweScaledUTF + MultiDISCO._sigma_rollout, disco.py:211-292, 312-323)
+# ----------------------------------------------------------------------------------
+def gen_widen():
+    print("G9 control regulariser / sigma-point rollouts")
+    utf_mod = ref_import("utils.utf")
+    # --- ctrl_penalty != 1: stand-alone controller, two consecutive forward + step calls (a_seq != 0 on the second)
+    for kind, seed, pen in (("pendulum", 11, 0.7), ("particle", 12, 0.25)):
+        w = make_pendulum(seed) if kind == "pendulum" else make_particle(seed)
+        ref, model = w["ctrl"], w["model"]
+        kw = dict(observation_space=model.observation_space, action_space=model.action_space, hz_len=ref.hz_len,
+                  n_policies=ref.n_pol, action_samples=ref.n_actions, temperature=ref.temp, ctrl_penalty=pen,
+                  a_cov=ref.a_dist.covariance_matrix, inst_cost_fn=ref.inst_cost_fn, term_cost_fn=ref.term_cost_fn,
+                  params_sampling=True, params_samples=ref.n_params, params_log_space=ref._params_log_space)
+        c = disco.MultiDISCO(**kw)
+        S, N, H, A = c.n_actions, c.n_pol, c.hz_len, c.dim_a
+        torch.manual_seed(2000 + seed)
+        c.a_mat = 0.5 * torch.randn(N, H, A)
+        if kind == "pendulum":
+            pd = RecordingDist(w["dyn"])
+            state = torch.tensor([2.5, -0.7])
+        else:
+            x = dist.Normal(2.0, 0.1).sample([50, 1]).clamp(min=1e-6).log()
+            comp = dist.Independent(dist.MultivariateNormal(loc=x, covariance_matrix=0.04 * torch.eye(1)), 0)
+            pd = RecordingDist(dist.MixtureSameFamily(dist.Categorical(torch.ones(50)), comp))
+            state = torch.tensor([-6.0, -7.0, 0.5, 0.8])
+        out = dict(state=state, a_mat0=c.a_mat.clone(), ctrl_penalty=np.array(pen), temp=np.array(c.temp),
+                   sigma=c.a_dist.covariance_matrix.diag().sqrt(), log_space=np.array(bool(c._params_log_space)))
+        for it in range(2):
+            actions = c.a_mat.unsqueeze(0) + out["sigma"] * torch.randn(S, N, H, A)
+            out[f"a_seq_in{it}"] = c.a_seq.clone()
+            out[f"a_mat_in{it}"] = c.a_mat.clone()
+            costs, states, acts, weights, plogp = c.forward(state, model, pd, actions)
+            out.update({f"actions{it}": actions, f"params{it}": pd.samples[it], f"costs{it}": costs, f"weights{it}": weights,
+                        f"a_mat_fwd{it}": c.a_mat.clone(), f"a_mix{it}": c.a_mix.clone()})
+            out[f"action{it}"] = c.step(strategy="average", steps=1).clone()
+        save(f"ctrlpen_{kind}", **out)
+    # --- sigma points: the demo's transformer (pendulum_config.yaml utf: n=2, alpha=0.5) on the pendulum with a
+    # GMM belief (variance.diag() branch) and an MVN belief (covariance_matrix branch); n_pol = 1 as in the demo
+    # and n_pol = 3 (the reference's state relabelling, costs unaffected)
+    tf = utf_mod.MerweScaledUTF(n=PEND["utf"]["n"], alpha=PEND["utf"]["alpha"])
+    save("utf_points", loc_weights=tf.loc_weights, cov_weights=tf.cov_weights,
+         mean=torch.tensor([0.9, 1.2]), cov=torch.tensor([[0.04, 0.01], [0.01, 0.09]]),
+         sigmas=tf.compute_sigma_points(torch.tensor([0.9, 1.2]), torch.tensor([[0.04, 0.01], [0.01, 0.09]])))
+    for name, n_pol, belief in (("utf_pendulum_n1_gmm", 1, "gmm"), ("utf_pendulum_n3_mvn", 3, "mvn")):
+        w = make_pendulum(21 + n_pol, n_pol=n_pol, S=32, H=12)
+        ref, model = w["ctrl"], w["model"]
+        c = disco.MultiDISCO(observation_space=model.observation_space, action_space=model.action_space, hz_len=ref.hz_len,
+                             n_policies=n_pol, action_samples=ref.n_actions, temperature=ref.temp,
+                             a_cov=ref.a_dist.covariance_matrix, inst_cost_fn=ref.inst_cost_fn, term_cost_fn=ref.term_cost_fn,
+                             params_sampling=tf, params_log_space=False)
+        S, N, H, A = c.n_actions, c.n_pol, c.hz_len, c.dim_a
+        torch.manual_seed(3000 + n_pol)
+        c.a_mat = 0.5 * torch.randn(N, H, A)
+        a_mat0 = c.a_mat.clone()
+        if belief == "gmm":   # the demo's dynamics prior: 4 components, sigma 0.1 (pendulum_example.py)
+            locs = torch.tensor(PEND["exp_params"]["params_prior_loc"], dtype=torch.float)
+            comp = dist.Independent(dist.Normal(locs, PEND["exp_params"]["params_prior_sigma"]), 1)
+            pd = dist.MixtureSameFamily(dist.Categorical(torch.ones(4)), comp)
+            mean, cov = pd.mean, pd.variance.diag()
+        else:
+            mean, cov = torch.tensor([0.9, 1.2]), torch.tensor([[0.04, 0.01], [0.01, 0.09]])
+            pd = dist.MultivariateNormal(mean, cov)
+        state = torch.tensor([2.8, 0.4])
+        actions = c.a_mat.unsqueeze(0) + 2.0 * torch.randn(S, N, H, A)
+        costs, states, acts, weights, plogp = c.forward(state, model, pd, actions)
+        save(name, state=state, a_mat0=a_mat0, actions=actions, mean=mean, cov=cov, belief_is_mvn=np.array(belief == "mvn"),
+             locs=locs if belief == "gmm" else np.zeros((0,)), comp_sigma=np.array(PEND["exp_params"]["params_prior_sigma"]),
+             loc_weights=tf.loc_weights, costs=costs, weights=weights, states=states, acts_shape=np.array(acts.shape),
+             params_log_p=plogp, a_mat1=c.a_mat, a_mix1=c.a_mix, temp=np.array(c.temp),
+             sigma=c.a_dist.covariance_matrix.diag().sqrt(), action_avg=deepcopy(c).step(strategy="average").clone())
+
+
 GENERATORS = dict(map=gen_map, forward=gen_forward_all, svmpc=gen_svmpc, dual=gen_dual, mpf=gen_mpf, phi=gen_phi,
-                  pathwise=gen_pathwise, episode=gen_episode)
+                  pathwise=gen_pathwise, episode=gen_episode, widen=gen_widen)
 
 if __name__ == "__main__":
     # no arguments: everything; otherwise only the named groups, merged into the existing manifest

@@ -115,6 +115,109 @@ def test_multidisco_forward_and_step_api():
     assert torch.isfinite(ctrl.a_mat).all()
 
 
+@pytest.mark.parametrize("kind", ["pendulum", "particle"])
+def test_multidisco_control_regulariser(kind):
+    """ctrl_penalty != 1 (disco.py:90, 334-344) in the stand-alone controller, two forward + step rounds
+    against the reference's recording: costs, weights, plan update, mixture and the applied action."""
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.models.particle import Particle
+    from dust_b200.models.pendulum import PendulumModel
+
+    d = load(f"ctrlpen_{kind}")
+    S, N, H, A = d["actions0"].shape
+    if kind == "pendulum":
+        model = PendulumModel(uncertain_params=("length", "mass"))
+        cost = dict(inst_cost_fn=demo_inst_cost, term_cost_fn=demo_term_cost)
+        ev = torch.Size([2])
+    else:
+        model = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+        cost = dict(inst_cost_fn=model.default_inst_cost, term_cost_fn=model.default_term_cost)
+        ev = torch.Size([1])
+    ctrl = MultiDISCO(model.observation_space, model.action_space, H, N, S, temperature=float(d["temp"]),
+                      ctrl_penalty=float(d["ctrl_penalty"]), a_cov=torch.diag(d["sigma"] ** 2), params_sampling=True,
+                      params_samples=d["params0"].shape[0], params_log_space=bool(d["log_space"]), **cost)
+    assert abs(ctrl.a_reg - float(d["temp"]) * (1 - float(d["ctrl_penalty"]))) < 1e-7
+    ctrl.a_mat = d["a_mat0"].clone().cuda()
+    for it in range(2):
+        assert rel_max(ctrl.a_seq.cpu(), d[f"a_seq_in{it}"]) <= 1e-4 or float(d[f"a_seq_in{it}"].abs().max()) == 0.0
+        pd = FixedParams(d[f"params{it}"], ev)
+        costs, states, actions, weights, _ = ctrl.forward(d["state"], model, pd, d[f"actions{it}"])
+        assert rel_elem(costs.cpu(), d[f"costs{it}"]) <= (RTOL_COST if it == 0 else 1e-4)   # second round: inputs drift by rounding
+        # soft-min weights against the oracle's reduction of the DEVICE costs (exact arithmetic check) ...
+        w_o, delta_o, mix_o = O.softmin_update(costs.cpu().double(), (d[f"actions{it}"] - d[f"a_seq_in{it}"]).double(),
+                                               float(d["temp"]))
+        assert float((weights.cpu() - w_o).abs().max()) <= 1e-5
+        assert rel_max(ctrl.a_mat.cpu(), d[f"a_mat_in{it}"].double() + delta_o) <= 1e-5
+        assert float((ctrl.a_mix.cpu() - mix_o).abs().max()) <= 1e-5
+        # ... and against the reference's own numbers where those are not rounding noise: with the particle
+        # costs (4e7 inside an obstacle, float32 ulp 4) a cost ulp moves exp(-cost) by e^4, in the reference too
+        if kind == "pendulum":
+            assert float((weights.cpu() - d[f"weights{it}"]).abs().max()) <= 2e-3
+            assert rel_max(ctrl.a_mat.cpu(), d[f"a_mat_fwd{it}"]) <= 2e-3
+            assert rel_max(ctrl.a_mix.cpu(), d[f"a_mix{it}"]) <= 2e-3
+        nxt = ctrl.step(strategy="average")
+        if kind == "pendulum":
+            assert rel_max(nxt.cpu(), d[f"action{it}"]) <= 2e-3
+        # keep the second round on the reference's inputs (teacher forcing), so it checks the round itself
+        if it == 0:
+            ctrl.a_mat = d["a_mat_in1"].clone().cuda()
+            ctrl.a_seq = d["a_seq_in1"].clone().cuda()
+
+
+def test_merwe_transformer_matches_reference():
+    from dust_b200.utils.utf import MerweScaledUTF
+
+    d = load("utf_points")
+    tf = MerweScaledUTF(n=2, alpha=0.5)
+    assert tf.pts == 5
+    assert torch.equal(tf.loc_weights, d["loc_weights"]) and torch.equal(tf.cov_weights, d["cov_weights"])
+    sig = tf.compute_sigma_points(d["mean"], d["cov"])
+    assert torch.equal(sig, d["sigmas"])
+    mu, K = tf.unscented_transform(sig)
+    assert rel_max(mu, d["mean"]) <= 1e-5 and rel_max(K, d["cov"]) <= 1e-4
+    with pytest.raises(ValueError):
+        tf.compute_sigma_points(torch.zeros(3), torch.eye(3))
+
+
+@pytest.mark.parametrize("name", ["utf_pendulum_n1_gmm", "utf_pendulum_n3_mvn"])
+def test_multidisco_sigma_point_rollouts(name):
+    """params_sampling = MerweScaledUTF (the demo's "DISCO" case, pendulum_example.py:143-147, 240-258):
+    sigma points of the parameter belief rolled out on the device, the reference's weighted costs
+    (disco.py:312-323, grouping quirk included), its state row order and its return shapes."""
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.models.pendulum import PendulumModel
+    from dust_b200.utils.utf import MerweScaledUTF
+
+    d = load(name)
+    S, N, H, A = d["actions"].shape
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    tf = MerweScaledUTF(n=2, alpha=0.5)
+    ctrl = MultiDISCO(model.observation_space, model.action_space, H, N, S, temperature=float(d["temp"]),
+                      a_cov=torch.diag(d["sigma"] ** 2), inst_cost_fn=demo_inst_cost, term_cost_fn=demo_term_cost,
+                      params_sampling=tf, params_log_space=False)
+    assert ctrl.n_params == 1 and ctrl.n_rollouts == S * N
+    ctrl.a_mat = d["a_mat0"].clone().cuda()
+    if bool(d["belief_is_mvn"]):
+        pd = dist.MultivariateNormal(d["mean"], d["cov"])
+    else:
+        comp = dist.Independent(dist.Normal(d["locs"], float(d["comp_sigma"])), 1)
+        pd = dist.MixtureSameFamily(dist.Categorical(torch.ones(d["locs"].shape[0])), comp)
+    costs, states, actions, weights, plogp = ctrl.forward(d["state"], model, pd, d["actions"])
+    assert tuple(actions.shape) == tuple(int(v) for v in d["acts_shape"])
+    assert states.shape == d["states"].shape
+    # trajectories: the device trig differs from libm by ~1e-7, states are compared to that
+    assert float((states.cpu() - d["states"]).abs().max()) <= 2e-4
+    assert rel_elem(costs.cpu(), d["costs"]) <= RTOL_COST
+    assert float((weights.cpu() - d["weights"]).abs().max()) <= 5e-3
+    assert rel_max(plogp.cpu(), d["params_log_p"]) <= 1e-5
+    assert rel_max(ctrl.a_mat.cpu(), d["a_mat1"]) <= 5e-3
+    nxt = copy.deepcopy(ctrl).step(strategy="average")
+    assert rel_max(nxt.cpu(), d["action_avg"]) <= 5e-3
+    with pytest.raises(NotImplementedError):
+        MultiDISCO(model.observation_space, model.action_space, H, N, S, ctrl_penalty=0.5, params_sampling=tf,
+                   inst_cost_fn=demo_inst_cost, term_cost_fn=demo_term_cost)
+
+
 def test_model_step_and_costs_api():
     from dust_b200.models.particle import Particle
     from dust_b200.models.pendulum import PendulumModel

@@ -42,6 +42,46 @@ def test_disco_forward_bit_exact(cfg, kind, seed):
         assert rel_max(a_mat, d[f"step_{strat}_a_mat"]) < 1e-6
 
 
+@pytest.mark.parametrize("kind", ["pendulum", "particle"])
+def test_control_regulariser_two_steps(cfg, kind):
+    """ctrl_penalty != 1 (disco.py:90, 334-344): two forward + step("average") rounds of the stand-alone
+    controller; the second has a non-zero a_seq and the a_mat the first one left."""
+    d = load(f"ctrlpen_{kind}")
+    model = O.Model(kind, cfg)
+    a_reg = float(d["temp"]) * (1.0 - float(d["ctrl_penalty"]))
+    a_pre = torch.inverse(torch.diag(d["sigma"] ** 2))
+    lim = 2.0 if kind == "pendulum" else 10.0
+    for it in range(2):
+        out = O.disco_forward(model, d["state"], d[f"actions{it}"], d[f"params{it}"], bool(d["log_space"]), float(d["temp"]),
+                              a_seq=d[f"a_seq_in{it}"], a_reg=a_reg, a_mat=d[f"a_mat_in{it}"], a_pre=a_pre)
+        assert rel_elem(out["costs"], d[f"costs{it}"]) < 1e-6
+        assert rel_max(out["weights"], d[f"weights{it}"]) < 1e-5
+        assert rel_max(d[f"a_mat_in{it}"] + out["delta"], d[f"a_mat_fwd{it}"]) < 1e-5
+        assert rel_max(out["a_mix"], d[f"a_mix{it}"]) < 1e-5
+        nxt, _, _ = O.disco_step(d[f"a_mat_fwd{it}"], d[f"a_mix{it}"], torch.tensor(-lim), torch.tensor(lim), "average")
+        assert rel_max(nxt, d[f"action{it}"]) < 1e-5
+
+
+def test_merwe_sigma_points_and_weights():
+    d = load("utf_points")
+    loc, cov = O.merwe_weights(2, alpha=0.5)
+    assert torch.equal(loc, d["loc_weights"]) and torch.equal(cov, d["cov_weights"])
+    assert torch.equal(O.merwe_sigma_points(d["mean"], d["cov"], alpha=0.5), d["sigmas"])
+
+
+@pytest.mark.parametrize("name", ["utf_pendulum_n1_gmm", "utf_pendulum_n3_mvn"])
+def test_sigma_point_forward(name):
+    """MultiDISCO.forward with the demo's MerweScaledUTF (disco.py:211-292, 312-323)."""
+    d = load(name)
+    sig = O.merwe_sigma_points(d["mean"], d["cov"], alpha=0.5)
+    out = O.disco_forward_sigma(O.Model("pendulum"), d["state"], d["actions"], sig, d["loc_weights"], float(d["temp"]))
+    assert torch.equal(out["states"], d["states"])
+    assert rel_elem(out["costs"], d["costs"]) < 1e-6
+    assert rel_max(out["weights"], d["weights"]) < 1e-5
+    assert rel_max(d["a_mat0"] + out["delta"], d["a_mat1"]) < 1e-5
+    assert rel_max(out["a_mix"], d["a_mix1"]) < 1e-5
+
+
 def test_disco_forward_default_params():
     d = load("fwd_pendulum_nops")
     out = O.disco_forward(O.Model("pendulum"), d["state"], d["actions"], None)
