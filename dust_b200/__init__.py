@@ -18,7 +18,7 @@ _SUBMODULES = [
     "inference", "inference.svgd", "inference.likelihoods", "inference.svmpc", "inference.mpf",
     "kernels", "kernels.base_kernels", "kernels.composite_kernels",
     "models", "models.base", "models.pendulum", "models.particle",
-    "utils", "utils.spaces", "utils.obstacle_map",
+    "utils", "utils.spaces", "utils.obstacle_map", "utils.utf", "utils.simulations",
 ]
 
 

@@ -654,9 +654,10 @@ def gen_widen():
     # GMM belief (variance.diag() branch) and an MVN belief (covariance_matrix branch); n_pol = 1 as in the demo
     # and n_pol = 3 (the reference's state relabelling, costs unaffected)
     tf = utf_mod.MerweScaledUTF(n=PEND["utf"]["n"], alpha=PEND["utf"]["alpha"])
+    sig0 = tf.compute_sigma_points(torch.tensor([0.9, 1.2]), torch.tensor([[0.04, 0.01], [0.01, 0.09]]))
+    ut_mean, ut_cov = tf.unscented_transform(sig0)   # NOT the input covariance: the points use rows of the upper factor
     save("utf_points", loc_weights=tf.loc_weights, cov_weights=tf.cov_weights,
-         mean=torch.tensor([0.9, 1.2]), cov=torch.tensor([[0.04, 0.01], [0.01, 0.09]]),
-         sigmas=tf.compute_sigma_points(torch.tensor([0.9, 1.2]), torch.tensor([[0.04, 0.01], [0.01, 0.09]])))
+         mean=torch.tensor([0.9, 1.2]), cov=torch.tensor([[0.04, 0.01], [0.01, 0.09]]), sigmas=sig0, ut_mean=ut_mean, ut_cov=ut_cov)
     for name, n_pol, belief in (("utf_pendulum_n1_gmm", 1, "gmm"), ("utf_pendulum_n3_mvn", 3, "mvn")):
         w = make_pendulum(21 + n_pol, n_pol=n_pol, S=32, H=12)
         ref, model = w["ctrl"], w["model"]

@@ -164,21 +164,6 @@ def test_multidisco_control_regulariser(kind):
             ctrl.a_seq = d["a_seq_in1"].clone().cuda()
 
 
-def test_merwe_transformer_matches_reference():
-    from dust_b200.utils.utf import MerweScaledUTF
-
-    d = load("utf_points")
-    tf = MerweScaledUTF(n=2, alpha=0.5)
-    assert tf.pts == 5
-    assert torch.equal(tf.loc_weights, d["loc_weights"]) and torch.equal(tf.cov_weights, d["cov_weights"])
-    sig = tf.compute_sigma_points(d["mean"], d["cov"])
-    assert torch.equal(sig, d["sigmas"])
-    mu, K = tf.unscented_transform(sig)
-    assert rel_max(mu, d["mean"]) <= 1e-5 and rel_max(K, d["cov"]) <= 1e-4
-    with pytest.raises(ValueError):
-        tf.compute_sigma_points(torch.zeros(3), torch.eye(3))
-
-
 @pytest.mark.parametrize("name", ["utf_pendulum_n1_gmm", "utf_pendulum_n3_mvn"])
 def test_multidisco_sigma_point_rollouts(name):
     """params_sampling = MerweScaledUTF (the demo's "DISCO" case, pendulum_example.py:143-147, 240-258):
@@ -464,3 +449,29 @@ def test_pendulum_simulation_driver_runs_the_dual_loop():
     assert torch.equal(mpf.x, x0)          # the driver works on deep copies (simulations.py:62,78)
     moved = torch.tensor(df["DynParticles"].iloc[5])
     assert float((moved - x0.cpu()).abs().max()) > 0
+
+
+def test_demo_runners_short_episodes():
+    """demo/pendulum_example.py (all four cases, incl. the sigma-point DISCO baseline) and
+    demo/particle_example.py (SVMPC + parameter filter) for a few control steps on their default
+    configurations: finite records with the reference's columns; the swing-up cost does not blow up."""
+    import math
+
+    from demo import configs, particle_example, pendulum_example
+
+    df = pendulum_example.run(configs.load(None, configs.PENDULUM), steps=12, episodes=1, seed=3)
+    assert set(df["Case"]) == set(pendulum_example.CASES) and len(df) == 4 * 12
+    for col in ("Cost", "Position", "Speed", "Actions", "AvgCumCost"):
+        assert all(math.isfinite(v) for v in df[col]), col
+    # MultiDISCO.step clips the plan to the action space (disco.py:408-410); SVMPC's best particle is logged as is
+    assert df[df["Case"].isin(["MPPI Baseline", "DISCO"])]["Actions"].abs().max() <= 2.0 + 1e-6
+    dual = df[df["Case"] == "DuSt-MPC"]
+    assert all(len(p) == 50 for p in dual["DynParticles"])          # the filter's particles are logged each step
+    cfg = configs.load(None, configs.PARTICLE)
+    res = particle_example.run(cfg, steps=9, episodes=1, seed=1)
+    r = res[0]
+    assert r["steps"] == 9 and math.isfinite(r["cum_cost"])
+    assert 1.0 < r["mass_estimate"] < 4.0
+    assert all(abs(a) <= 10.0 + 1e-5 for row in r["actions"] for a in row)
+    # warm-up steps apply the zero action (particle_example.py:182-184)
+    assert all(a == 0.0 for row in r["actions"][: cfg["sim_params"]["warm_up"]] for a in row)

@@ -198,3 +198,45 @@ def test_sharded_svgd_host_logic_gloo_world2(tmp_path):
                          env=env, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
     assert res.stdout.count("ok") == 2
+
+
+def test_demo_default_configs_equal_the_reference_yaml():
+    """demo/configs.py carries the reference's two configurations key for key; where the reference tree is
+    mounted (the build container) its yaml files must load to the same dictionaries."""
+    import os
+
+    import pytest
+    import yaml
+
+    from demo import configs
+
+    ref = "/root/reference/demo"
+    if not os.path.isdir(ref):
+        pytest.skip("reference tree not mounted")
+    for name, default in (("pendulum", configs.PENDULUM), ("particle", configs.PARTICLE)):
+        path = os.path.join(ref, name + "_config.yaml")
+        with open(path) as f:
+            assert yaml.load(f, yaml.FullLoader) == default, name
+        assert configs.load(path, None) == default
+    assert configs.load(None, configs.PENDULUM) is not configs.PENDULUM
+
+
+def test_merwe_transformer_matches_reference():
+    import pytest
+    import torch
+
+    from tests.util import load, rel_max
+    from dust_b200.utils.utf import MerweScaledUTF
+
+    d = load("utf_points")
+    tf = MerweScaledUTF(n=2, alpha=0.5)
+    assert tf.pts == 5
+    assert torch.equal(tf.loc_weights, d["loc_weights"]) and torch.equal(tf.cov_weights, d["cov_weights"])
+    sig = tf.compute_sigma_points(d["mean"], d["cov"])
+    assert torch.equal(sig, d["sigmas"])
+    mu, K = tf.unscented_transform(sig)
+    # the reference's transform of its own points (their spread uses the ROWS of the upper Cholesky factor, so
+    # the covariance that comes back is not the one that went in -- reproduced, not corrected)
+    assert rel_max(mu, d["ut_mean"]) <= 1e-6 and rel_max(K, d["ut_cov"]) <= 1e-6
+    with pytest.raises(ValueError):
+        tf.compute_sigma_points(torch.zeros(3), torch.eye(3))
