@@ -92,26 +92,54 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--alpha", type=float, default=1.0, help="likelihood temperature (demos: 1); a tiny value makes every soft-min weight non-zero")
+    ap.add_argument("--emulate-world", type=int, default=1,
+                    help="single process: time the parameter-draw share ONE rank of a world of this size rolls out "
+                         "(no all-reduce: the device work of a rank, not a valid control step)")
     args = ap.parse_args()
+    import os
+
+    import torch.distributed as dist
+
     from dust_b200 import _lib as L
+    from dust_b200.distributed import ShardedRollout, row_block
 
     L.require_cuda()
-    dev = torch.device("cuda", 0)
+    rank, world, lrank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lrank)
+    dev = torch.device("cuda", lrank)
+    if world > 1:   # one instance, its parameter draws split over the ranks (inputs replicated: same seed everywhere)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for name in args.configs.split(","):
         cfg = CONFIGS[name]
         p = build(cfg, dev, alpha=args.alpha)
+        if world > 1 or args.emulate_world > 1:
+            sh = ShardedRollout(cfg["P"])
+            if args.emulate_world > 1:
+                sh.p_range = row_block(cfg["P"], args.emulate_world // 2, args.emulate_world)
+            p["core"].sharded = sh
         for _ in range(args.warmup):
             dual_step(cfg, p)
-        torch.cuda.synchronize()
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         w0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             dual_step(cfg, p)
         e1.record()
-        torch.cuda.synchronize()
+        sync()
         wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
         dev_ms = e0.elapsed_time(e1) / args.steps
+        if world > 1:   # device time of the slowest rank
+            t = torch.tensor([dev_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms = float(t[0])
         lib = L.load()
         lib.dust_profiler_reset()
         lib.dust_profiler_enable(1)
@@ -125,11 +153,17 @@ def main():
                 "device_ms_per_dual_step": dev_ms, "wall_ms_per_dual_step": wall_ms,
                 "dual_steps_per_sec": 1e3 / dev_ms, "rollouts_per_sec": cfg["P"] * cfg["S"] * cfg["N"] * 1e3 / dev_ms,
                 "model_steps_per_control_step": model_steps, "kernel_ms_per_step": prof, "steps": args.steps,
-                "warmup": args.warmup, "data": "synthetic", "alpha": args.alpha}
+                "warmup": args.warmup, "data": "synthetic", "alpha": args.alpha, "n_gpus": world,
+                "emulated_world": args.emulate_world,
+                "sharding": None if p["core"].sharded is None else "parameter draws %s of %d on this rank" % (
+                    list(p["core"].sharded.p_range), cfg["P"])}
         lw = p["core"].last.get("lik_weights")
         if lw is not None:   # pathwise gradient: rows with an exactly-zero weight are not rolled out by the adjoint
             line["nonzero_weight_fraction"] = float((lw != 0).float().mean())
-        print(json.dumps(line), flush=True)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

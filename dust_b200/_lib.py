@@ -38,7 +38,7 @@ class RolloutArgs(C.Structure):
         ("param_tiling", _i), ("likelihood", _i),
         ("state0", _p), ("theta", _p), ("noise", _p), ("sigma", _p), ("params", _p), ("a_seq", _p),
         ("pert", _p), ("alpha", _f), ("temperature", _f),
-        ("sigma_weights", _p), ("ctrl_mat", _p), ("ctrl_reg", _f),
+        ("sigma_weights", _p), ("ctrl_mat", _p), ("ctrl_reg", _f), ("p_begin", _i), ("p_end", _i),
         ("costs", _p), ("log_lik", _p), ("lik_weights", _p), ("grad_lik", _p), ("mppi_weights", _p),
         ("mppi_delta", _p), ("mix", _p), ("states", _p),
         ("workspace", _p), ("workspace_bytes", _sz),
@@ -60,7 +60,7 @@ class AdjointArgs(C.Structure):
         ("param_tiling", _i), ("likelihood", _i),
         ("state0", _p), ("theta", _p), ("noise", _p), ("sigma", _p), ("params", _p), ("lik_weights", _p),
         ("alpha", _f), ("grad_theta", _p), ("grad_params", _p),
-        ("workspace", _p), ("workspace_bytes", _sz),
+        ("workspace", _p), ("workspace_bytes", _sz), ("p_begin", _i), ("p_end", _i),
     ]
 
 
@@ -117,6 +117,7 @@ class MpfArgs(C.Structure):
 SYMBOLS = {
     "dust_rollout_workspace_bytes": (_sz, [C.POINTER(RolloutArgs)]),
     "dust_rollout_cost": (C.c_int, [C.POINTER(RolloutArgs), _p]),
+    "dust_cost_reduce": (C.c_int, [C.POINTER(RolloutArgs), _p]),
     "dust_svmpc_step": (C.c_int, [C.POINTER(SvmpcStepArgs), _p]),
     "dust_adjoint_workspace_bytes": (_sz, [C.POINTER(AdjointArgs)]),
     "dust_rollout_adjoint": (C.c_int, [C.POINTER(AdjointArgs), _p]),

@@ -19,6 +19,7 @@ __host__ __device__ inline int adj_stride(int HA) {
 struct AdjKParams {
   ModelParams m;
   int B, N, S, P, H, A, SN, HA, PC, Pchunk, interleaved, likelihood, tiles;
+  int p0, p1;      // draws [p0, p1) of the P resident ones are covered by this call (a rank's share)
   const float *state0, *theta, *noise, *sigma, *params, *lik_w;
   float alpha;
   float* partial;  // [B, tiles, PC, N*HA]
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
 
   constexpr int Q = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;   // parameter draws advanced together per thread
   int my_row = live ? row : -1, p_first = 0, p_step = Q;
-  const int chunk_len = min(k.P, pc * k.Pchunk + k.Pchunk) - pc * k.Pchunk;   // draws of this CTA
+  const int chunk_len = min(k.p1, k.p0 + pc * k.Pchunk + k.Pchunk) - (k.p0 + pc * k.Pchunk);   // draws of this CTA
   const int G = spread ? kAdjTile / n_live : 1;                               // thread slots per live row
   const int g_used = min(G, (chunk_len + Q - 1) / Q);                         // ... of which this many get draws
   if (spread) {
@@ -116,7 +117,7 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
     const float* __restrict__ arow = tile + my_row * stride;
     float* __restrict__ grow = gacc + threadIdx.x * stride;
     const float* __restrict__ x0 = k.state0 + inst * DS;
-    const int p_begin = pc * k.Pchunk + p_first, p_end = min(k.P, pc * k.Pchunk + k.Pchunk);
+    const int p_begin = k.p0 + pc * k.Pchunk + p_first, p_end = min(k.p1, k.p0 + pc * k.Pchunk + k.Pchunk);
     for (int p = p_begin; p < p_end; p += p_step) {
       const float* prm = nullptr;
       if (k.params) {
@@ -312,7 +313,7 @@ struct AdjPlan {
 static AdjPlan plan_adjoint(const dust_adjoint_args* a) {
   AdjPlan pl{};
   const long long SN = (long long)a->S * a->N;
-  const int P = a->params ? a->P : 1;
+  const int P = a->p_end > a->p_begin ? a->p_end - a->p_begin : (a->params ? a->P : 1);   // draws this call covers
   const long long target_threads = (long long)kNumSMs * 2048 * 2;
   long long pc = 1;
   if (P > 1 && a->B * SN < target_threads) pc = (target_threads + a->B * SN - 1) / (a->B * SN);
@@ -367,6 +368,9 @@ extern "C" int dust_rollout_adjoint(const dust_adjoint_args* a, void* stream_) {
   k.m = to_params(*a->model);
   k.B = a->B; k.N = a->N; k.S = a->S; k.P = a->params ? a->P : 1; k.H = a->H; k.A = A;
   k.SN = a->S * a->N; k.HA = a->H * A; k.PC = pl.PC; k.Pchunk = pl.Pchunk;
+  k.p0 = a->p_end > a->p_begin ? a->p_begin : 0; k.p1 = a->p_end > a->p_begin ? a->p_end : k.P;
+  DUST_REQUIRE(a->p_begin >= 0 && a->p_end >= a->p_begin && a->p_end <= k.P, DUST_ERR_INVALID_ARG,
+               "dust_rollout_adjoint: draw range [%d, %d) outside [0, %d)", a->p_begin, a->p_end, k.P);
   k.interleaved = a->param_tiling == DUST_PARAMS_INTERLEAVED; k.likelihood = a->likelihood; k.tiles = pl.tiles;
   k.state0 = a->state0; k.theta = a->theta; k.noise = a->noise; k.sigma = a->sigma; k.params = a->params;
   k.lik_w = a->lik_weights; k.alpha = a->alpha; k.partial = (float*)a->workspace;

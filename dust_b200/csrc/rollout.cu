@@ -30,6 +30,7 @@ struct RolloutKParams {
   int HA;          // H*A
   int PC;          // number of parameter chunks (grid.y)
   int Pchunk;      // parameters per chunk
+  int p0, p1;      // draws [p0, p1) of the P resident ones are rolled out by this call (a rank's share)
   int interleaved;
   const float* state0;
   const float* theta;
@@ -254,11 +255,13 @@ __device__ __forceinline__ bool small_angle_horizon(const RolloutKParams& k, lon
   return fabsf(th0) + (float)k.H * k.m.dt * k.m.max_speed_pend + 3.2f <= 64.0f;  // NaN -> false
 }
 
-template <int MODEL>
+// EXT: the instantiation that also knows the sigma-point weights and the control regulariser; the plain one
+// (every hot path) carries none of that code
+template <int MODEL, bool EXT>
 __device__ __forceinline__ float trajectory_cost_dispatch(const RolloutKParams& k, const float* __restrict__ arow,
                                                           const uint32_t* grid_s, long long inst, int j, int p_begin,
                                                           int p_end, bool small) {
-  if (k.ut_w) {
+  if (EXT && k.ut_w) {
     if (k.states) return trajectory_cost_sum<MODEL, false, true, false, true>(k, arow, grid_s, inst, j, p_begin, p_end);
     return trajectory_cost_sum<MODEL, false, false, false, true>(k, arow, grid_s, inst, j, p_begin, p_end);
   }
@@ -267,7 +270,7 @@ __device__ __forceinline__ float trajectory_cost_dispatch(const RolloutKParams& 
   return trajectory_cost_sum<MODEL, false, false>(k, arow, grid_s, inst, j, p_begin, p_end);
 }
 
-template <int MODEL>
+template <int MODEL, bool EXT>
 __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParams k) {
   constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
   extern __shared__ __align__(16) float smem[];
@@ -292,13 +295,13 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
   const int row = threadIdx.x;
   if (row >= rows) return;
   const int j = j0 + row;
-  const int p_begin = pc * k.Pchunk;
-  const int p_end = min(k.P, p_begin + k.Pchunk);
-  const float csum = trajectory_cost_dispatch<MODEL>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end,
-                                                     small_angle_horizon<MODEL>(k, inst));
+  const int p_begin = k.p0 + pc * k.Pchunk;
+  const int p_end = min(k.p1, p_begin + k.Pchunk);
+  const float csum = trajectory_cost_dispatch<MODEL, EXT>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end,
+                                                          small_angle_horizon<MODEL>(k, inst));
   if (k.PC == 1) {
-    float cost = k.ut_w ? csum : csum / (float)k.P;  // sigma-point weights, or the mean over parameter samples (disco.py:330)
-    if (k.ctrl_mat) {
+    float cost = (EXT && k.ut_w) ? csum : csum / (float)k.P;  // sigma-point weights, or the mean over parameter samples (disco.py:330)
+    if (EXT && k.ctrl_mat) {
       // control regulariser (disco.py:334-344): a_reg * sum_{h,a} -(action - a_seq) (a_mat a_pre)[n]
       const float* act = tile + row * stride;
       const float* cm = k.ctrl_mat + (inst * k.N + j % k.N) * (long long)k.HA;
@@ -887,7 +890,7 @@ struct RolloutPlan {
 static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = false) {
   RolloutPlan pl{};
   const long long SN = (long long)a->S * a->N;
-  const int P = a->params ? a->P : 1;
+  const int P = a->p_end > a->p_begin ? a->p_end - a->p_begin : (a->params ? a->P : 1);   // draws this call rolls out
   if (a->sigma_weights || a->ctrl_mat) single_chunk = true;   // weighted / regularised costs are formed in one thread
   int pc = single_chunk ? 1 : choose_param_chunks((long long)a->B * SN, P);
   const int chunk = (P + pc - 1) / pc;
@@ -918,7 +921,8 @@ extern "C" size_t dust_rollout_workspace_bytes(const dust_rollout_args* a) {
   return plan_rollout(a).total;
 }
 
-static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail, void* stream_) {
+// reduce_only: `costs` is complete on entry (dust_cost_reduce); only the reductions after it run
+static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail, void* stream_, bool reduce_only = false) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_rollout_cost: args is NULL");
   int rc = validate_model(a->model);
@@ -938,7 +942,15 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   const long long SN = (long long)a->S * a->N;
   DUST_REQUIRE(SN < (1ll << 30), DUST_ERR_UNSUPPORTED, "dust_rollout_cost: S*N too large");
 
-  const RolloutPlan pl = plan_rollout(a, tail != nullptr);
+  const bool ranged = a->p_end > a->p_begin;
+  DUST_REQUIRE(a->p_begin >= 0 && a->p_end >= a->p_begin && a->p_end <= P, DUST_ERR_INVALID_ARG,
+               "dust_rollout_cost: draw range [%d, %d) outside [0, %d)", a->p_begin, a->p_end, P);
+  DUST_REQUIRE(!ranged || (!tail && !reduce_only && a->costs && !a->log_lik && !a->lik_weights && !a->grad_lik &&
+                           !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states && !a->sigma_weights && !a->ctrl_mat),
+               DUST_ERR_INVALID_ARG, "dust_rollout_cost: a draw range only produces `costs` (its share of the mean)");
+  DUST_REQUIRE(!reduce_only || a->costs, DUST_ERR_INVALID_ARG, "dust_cost_reduce: costs (input) is required");
+  RolloutPlan pl = plan_rollout(a, tail != nullptr);
+  if (reduce_only) pl.PC = 1;
   DUST_REQUIRE(pl.total == 0 || (a->workspace && a->workspace_bytes >= pl.total), DUST_ERR_WORKSPACE,
                "dust_rollout_cost: workspace needs %zu bytes, got %zu", pl.total, a->workspace_bytes);
   char* ws = (char*)a->workspace;
@@ -951,6 +963,7 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   k.m = to_params(*a->model);
   k.B = a->B; k.N = a->N; k.S = a->S; k.P = P; k.H = a->H; k.A = A;
   k.SN = (int)SN; k.HA = a->H * A; k.PC = pl.PC; k.Pchunk = pl.Pchunk;
+  k.p0 = ranged ? a->p_begin : 0; k.p1 = ranged ? a->p_end : P;
   k.interleaved = a->param_tiling == DUST_PARAMS_INTERLEAVED;
   k.state0 = a->state0; k.theta = a->theta; k.noise = a->noise; k.sigma = a->sigma; k.params = a->params;
   k.cost_out = pl.PC > 1 ? part : costs;
@@ -966,7 +979,7 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
                                 ? sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32) : 0;
   // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
   const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
-  const bool fused_ok = fused_outputs_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
+  const bool fused_ok = fused_outputs_only && !ranged && !reduce_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
                         (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
   DUST_REQUIRE(fused_ok || !tail, DUST_ERR_UNSUPPORTED,
                "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");
@@ -1008,20 +1021,28 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
     DUST_LAUNCH_OK("svmpc_instance_kernel");
     return DUST_OK;
   }
+  if (!reduce_only) {
   size_t smem = sizeof(float) * kTile * stride + grid_bytes;
   DUST_REQUIRE(smem <= 227 * 1024, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: H*A=%d needs %zu B of shared memory", k.HA, smem);
   const int tiles = ceil_div(SN, kTile);
   const long long gx = (long long)a->B * tiles;
   DUST_REQUIRE(gx < (1ll << 31) && pl.PC <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: grid too large");
   dim3 grid((unsigned)gx, (unsigned)pl.PC, 1);
+  const bool ext = a->sigma_weights || a->ctrl_mat;
+#define DUST_ROLLOUT(MODEL, EXT)                                                                                       \
+  do {                                                                                                                 \
+    if (smem > 48 * 1024)                                                                                              \
+      DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<MODEL, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<MODEL, EXT><<<grid, kTile, smem, stream>>>(k); }  \
+  } while (0)
   if (kind == DUST_MODEL_PENDULUM) {
-    if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<DUST_MODEL_PENDULUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<DUST_MODEL_PENDULUM><<<grid, kTile, smem, stream>>>(k); }
+    if (ext) DUST_ROLLOUT(DUST_MODEL_PENDULUM, true); else DUST_ROLLOUT(DUST_MODEL_PENDULUM, false);
   } else {
-    if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<DUST_MODEL_PARTICLE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<DUST_MODEL_PARTICLE><<<grid, kTile, smem, stream>>>(k); }
+    if (ext) DUST_ROLLOUT(DUST_MODEL_PARTICLE, true); else DUST_ROLLOUT(DUST_MODEL_PARTICLE, false);
   }
+#undef DUST_ROLLOUT
   DUST_LAUNCH_OK("rollout_cost_kernel");
+  }
 
   const bool need_stats = pl.PC > 1 || a->log_lik || likw || mppiw || a->mix;
   if (need_stats) {
@@ -1047,6 +1068,8 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
 }
 
 extern "C" int dust_rollout_cost(const dust_rollout_args* a, void* stream_) { return rollout_cost_impl(a, nullptr, stream_); }
+
+extern "C" int dust_cost_reduce(const dust_rollout_args* a, void* stream_) { return rollout_cost_impl(a, nullptr, stream_, true); }
 
 extern "C" int dust_svmpc_step(const dust_svmpc_step_args* s, void* stream_) {
   DUST_REQUIRE(s != nullptr, DUST_ERR_INVALID_ARG, "dust_svmpc_step: args is NULL");

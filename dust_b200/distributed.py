@@ -1,6 +1,10 @@
 """Multi-GPU sharding of the hot path on one NVSwitch box (one process per GPU, torch.distributed).
 
 * Independent MPC instances (`shard_instances`): contiguous split of the batch, NO communication.
+* ONE large instance (`ShardedRollout`): the P dynamics-parameter draws are split over the ranks; the
+  trajectory cost is a mean over the draws (disco.py:330), so every rank rolls out its share and one
+  all-reduce (sum) of the [S, N] cost shares (and, for the pathwise gradient, of the [N, H, A] gradient
+  shares) completes it.  The soft-min / likelihood reductions then run replicated on every rank.
 * Large-N SVGD (`ShardedSVGD`): rank r owns a row block of X, score and phi.  One exchange per
   evaluation: all-gather of [X | score] (N*2D*4 bytes in total), plus -- for the exact median
   bandwidth -- an all-reduce (sum) of the 65536-bin radix histogram after each of the two passes.
@@ -77,3 +81,44 @@ class ShardedSVGD:
                                     c1=1.0 / self.N, c2=1.0 / (self.N * bw * bw), rows=self.rows)
         b, e = self.rows
         return out["phi"][0, b:e], coef
+
+
+class ShardedRollout:
+    """Rollout, cost, likelihood and likelihood gradient of ONE instance with its P parameter draws split
+    over the ranks of `group` (SURVEY 8(e), "rollouts of one instance"; disco.py:139-209, 294-346;
+    likelihoods.py:113-135; svmpc.py:46-60).  Inputs are replicated (state, theta, noise, all P draws:
+    the draws are a few KB); each rank rolls out draws [p0, p1)."""
+
+    def __init__(self, n_params, group=None, ops=_ops):
+        self.P, self.group, self.ops = int(n_params), group, ops
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.p_range = row_block(self.P, self.rank, self.world)
+
+    def _all_reduce(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+    def evaluate(self, spec, state0, noise, theta, sigma, params, param_tiling=0, likelihood=0, alpha=1.0, temperature=1.0,
+                 grad="analytic"):
+        """state0 [1,ds], noise [1,S,N,H,A], theta [1,N,H,A], params [1,P,dp].
+        -> dict(costs [1,S,N], log_lik [1,N], grad_lik [1,N,H,A][, lik_weights])."""
+        assert params.shape[1] == self.P
+        kw = dict(theta=theta, sigma=sigma, params=params, param_tiling=param_tiling, likelihood=likelihood, alpha=alpha)
+        p0, p1 = self.p_range
+        if p1 > p0:
+            out = self.ops.rollout_cost(spec, state0, noise, temperature=temperature, want=("costs",), p_range=(p0, p1), **kw)
+        else:   # more ranks than draws: this rank contributes nothing
+            out = {"costs": noise.new_zeros(noise.shape[:3])}
+        self._all_reduce(out["costs"])
+        want = ("log_lik", "grad_lik") if grad == "analytic" else ("log_lik", "lik_weights")
+        res = self.ops.rollout_cost(spec, state0, noise, temperature=temperature, want=want, out={"costs": out["costs"]},
+                                    reduce_only=True, **kw)
+        if grad != "analytic":
+            if p1 > p0:
+                g = self.ops.rollout_adjoint(spec, state0, noise, res["lik_weights"], p_range=(p0, p1), **kw)
+            else:
+                g = theta.new_zeros(theta.shape)
+            res["grad_lik"] = self._all_reduce(g)
+        return res

@@ -19,9 +19,10 @@ class SvmpcCore:
     def __init__(self, spec, theta, mu, mix, prior_var, sigma, alpha=1.0, temperature=1.0, lr=1.0,
                  kernel="gpytorch", lengthscale=GPYTORCH_DEFAULT_LENGTHSCALE, bw_scale=1.0,
                  likelihood=L.LIK_EXP_UTILITY, grad="analytic", roll_strategy="repeat", weighted_prior=False,
-                 aliased=False, seed=0):
+                 aliased=False, seed=0, sharded=None):
         """theta, mu [B,N,H,A]; mix [B,N]; prior_var [A] (diagonal, shared by all components);
-        sigma [A]."""
+        sigma [A].  sharded: a `distributed.ShardedRollout` -- ONE instance (B = 1) whose parameter draws are
+        split over the ranks of its group (every rank holds the same particles and noise)."""
         self.spec = spec
         self.theta, self.mu, self.mix = theta.contiguous(), mu.contiguous(), mix.contiguous()
         self.B, self.N, self.H, self.A = theta.shape
@@ -44,6 +45,7 @@ class SvmpcCore:
         self.seed, self.resample_draws = int(seed), 0
         self.weighted_prior = bool(weighted_prior)
         self.aliased = bool(aliased)
+        self.sharded = sharded
         self.last = {}
 
     def set_prior_var(self, prior_var):
@@ -69,10 +71,17 @@ class SvmpcCore:
         want.append("grad_lik" if self.grad == "analytic" else "lik_weights")
         if want_states:
             want.append("states")
-        out = ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
-                               param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
-                               temperature=self.temperature, want=tuple(want))
-        if self.grad == "analytic":
+        if self.sharded is not None and params is not None:
+            out = self.sharded.evaluate(self.spec, state0, eps, self.theta, self.sigma, params, tiling, self.likelihood,
+                                        self.alpha, self.temperature, grad=self.grad)
+            grad_lik = out["grad_lik"]
+        else:
+            out = ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
+                                   param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
+                                   temperature=self.temperature, want=tuple(want))
+        if self.sharded is not None and params is not None:
+            pass
+        elif self.grad == "analytic":
             grad_lik = out["grad_lik"]
         else:
             grad_lik = ops.rollout_adjoint(self.spec, state0, eps, out["lik_weights"], theta=self.theta,

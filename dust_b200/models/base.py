@@ -16,6 +16,11 @@ class DeviceModelSpec:
         self.dp = 2 if kind == L.MODEL_PENDULUM else 1
         self._keepalive = tuple(keepalive)
 
+    def __deepcopy__(self, memo):
+        # an immutable description (ctypes struct + the device tensors it points to): copies of the objects
+        # that hold it (the demos deep-copy controller / SVMPC / MPF per episode) share it
+        return self
+
 
 class BaseModel:
     def __init__(self, dt=0.05, params_dict=None, uncertain_params=None):

@@ -25,11 +25,15 @@ def _ws(nbytes, device):
 
 def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param_tiling=L.PARAMS_BLOCKED,
                  likelihood=L.LIK_EXP_UTILITY, a_seq=None, pert=None, alpha=1.0, temperature=1.0,
-                 want=("costs", "log_lik"), out=None, sigma_weights=None, ctrl_mat=None, ctrl_reg=0.0):
+                 want=("costs", "log_lik"), out=None, sigma_weights=None, ctrl_mat=None, ctrl_reg=0.0, p_range=None,
+                 reduce_only=False):
     """K1.  noise [B,S,N,H,A]; theta [B,N,H,A] or None (noise = actions); params [B,P,dp] or None.
     `want` subset of {costs, log_lik, lik_weights, grad_lik, mppi_weights, mppi_delta, mix, states}.
     sigma_weights [P]: unscented-transform mode (params = the sigma points, disco.py:211-323);
     ctrl_mat [B,N,H,A] + ctrl_reg: control regulariser (disco.py:334-344).
+    p_range (p0, p1): roll out only those parameter draws; `costs` is then their share of the mean
+    (sum the shares over the ranks).  reduce_only: `out["costs"]` is complete, only the reductions after
+    the costs run (dust_cost_reduce).
     Returns a dict of CUDA tensors."""
     L.require_cuda()
     dev = noise.device
@@ -55,12 +59,15 @@ def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param
     if sigma_weights is not None:
         assert sigma_weights.numel() == P and params is not None
     a.sigma_weights, a.ctrl_mat, a.ctrl_reg = L.ptr(sigma_weights), L.ptr(ctrl_mat), float(ctrl_reg)
+    a.p_begin, a.p_end = (0, 0) if p_range is None else (int(p_range[0]), int(p_range[1]))
     for k in shapes:
         setattr(a, k, L.ptr(out.get(k)) if k in want else None)
+    if reduce_only:
+        a.costs = L.ptr(out["costs"])
     nbytes = L.load().dust_rollout_workspace_bytes(C.byref(a))
     ws = _ws(nbytes, dev)
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
-    L.call("dust_rollout_cost", C.byref(a), L.stream(), launches=3)
+    L.call("dust_cost_reduce" if reduce_only else "dust_rollout_cost", C.byref(a), L.stream(), launches=3)
     return out
 
 
@@ -107,8 +114,9 @@ def svmpc_step(spec, state0, noise, theta, sigma, mu, mix, inv_var, log_norm, ga
 
 
 def rollout_adjoint(spec, state0, noise, lik_weights, theta=None, sigma=None, params=None,
-                    param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0):
-    """K2.  Returns grad_theta [B,N,H,A] = d sum_n log_l_n / d theta (pathwise)."""
+                    param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0, p_range=None):
+    """K2.  Returns grad_theta [B,N,H,A] = d sum_n log_l_n / d theta (pathwise); with p_range (p0, p1) the
+    share of those parameter draws (sum the shares over the ranks)."""
     L.require_cuda()
     dev = noise.device
     B, S, N, H, A = noise.shape
@@ -121,6 +129,7 @@ def rollout_adjoint(spec, state0, noise, lik_weights, theta=None, sigma=None, pa
     a.state0, a.theta, a.noise, a.sigma = L.ptr(state0), L.ptr(theta), L.ptr(noise), L.ptr(sigma)
     a.params, a.lik_weights, a.alpha = L.ptr(params), L.ptr(lik_weights), float(alpha)
     a.grad_theta, a.grad_params = L.ptr(g), None
+    a.p_begin, a.p_end = (0, 0) if p_range is None else (int(p_range[0]), int(p_range[1]))
     nbytes = L.load().dust_adjoint_workspace_bytes(C.byref(a))
     ws = _ws(nbytes, dev)
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes

@@ -128,6 +128,11 @@ typedef struct dust_rollout_args {
                                 regulariser ctrl_reg * sum_{h,a} (a_seq - action) * ctrl_mat[n]
                                 (disco.py:334-344) to every trajectory cost           */
   float ctrl_reg;            /* a_reg = temperature * (1 - ctrl_penalty) (disco.py:90)   */
+  int32_t p_begin, p_end;    /* 0, 0: all P draws.  Otherwise (multi-GPU sharding of ONE instance over its
+                                parameter draws) this call rolls out draws [p_begin, p_end) of the P resident
+                                ones and `costs` receives their share of the mean, (1/P) * sum over the range;
+                                no other output may be requested.  Sum the shares over the ranks (all-reduce)
+                                and finish with dust_cost_reduce                        */
   /* outputs (any may be NULL) */
   float* costs;              /* [B, S, N]      trajectory costs, mean over P           */
   float* log_lik;            /* [B, N]         likelihoods.py:113-135                  */
@@ -144,6 +149,11 @@ typedef struct dust_rollout_args {
 
 size_t dust_rollout_workspace_bytes(const dust_rollout_args* args);
 int dust_rollout_cost(const dust_rollout_args* args, void* stream);
+/* The reductions that follow the costs, on their own: `costs` [B,S,N] is an INPUT (complete trajectory
+ * costs, e.g. all-reduced shares); log_lik / lik_weights / grad_lik / mppi_weights / mppi_delta / mix are
+ * written as dust_rollout_cost would (disco.py:380-393, likelihoods.py:113-135, svmpc.py:46-54).
+ * Same workspace as dust_rollout_cost. */
+int dust_cost_reduce(const dust_rollout_args* args, void* stream);
 
 /* The whole SVGD step of SVMPC (and optionally SVMPC.forward) for B instances in ONE launch:
  * K1 with its fused per-instance kernel, then -- in the tail of the same CTA -- the GMM prior score,
@@ -198,6 +208,8 @@ typedef struct dust_adjoint_args {
   float* grad_params;        /* [B, P, dp] or NULL */
   void* workspace;
   size_t workspace_bytes;
+  int32_t p_begin, p_end;    /* 0, 0: all draws; else only draws [p_begin, p_end): grad_theta receives their
+                                share of the gradient (the 1/P of the mean included) -- sum over the ranks */
 } dust_adjoint_args;
 
 size_t dust_adjoint_workspace_bytes(const dust_adjoint_args* args);

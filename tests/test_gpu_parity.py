@@ -615,6 +615,50 @@ def test_large_phi_properties(env):
 
 
 # ---------------------------------------------------------------------------------------------
+# one instance sharded over its parameter draws (what each rank of ShardedRollout computes)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,P,world", [("pendulum", 8, 2), ("particle", 37, 3), ("particle", 5, 8)])
+def test_parameter_draw_shares_sum_to_the_full_rollout(env, kind, P, world):
+    """Draw ranges [p0, p1) (blocked and -- particle, scalar-event belief -- interleaved tiling) give their share of
+    the mean cost and of the pathwise gradient; the shares of all ranks sum to the single-call result, and
+    dust_cost_reduce on the summed costs reproduces its likelihood, weights and analytic gradient."""
+    from dust_b200 import ops
+    from dust_b200.distributed import row_block
+
+    torch.manual_seed(P)
+    spec = env["spec"][kind]
+    S, N, H = 48, 4, 14
+    if kind == "pendulum":
+        state0, sigma, A = cu(torch.tensor([[2.5, 0.3]])), cu(torch.tensor([2.0])), 1
+        params, tiling, alpha = cu(torch.rand(1, P, 2) * 0.7 + 0.6), 0, 0.05
+    else:
+        state0, sigma, A = cu(torch.tensor([[-6.0, -7.0, 0.5, 0.8]])), cu(torch.tensor([5.0, 5.0])), 2
+        params, tiling, alpha = cu(torch.randn(1, P, 1) * 0.1 + math.log(2.0)).exp(), 1, 1e-4
+    theta, noise = cu(torch.randn(1, N, H, A)), cu(torch.randn(1, S, N, H, A))
+    kw = dict(theta=theta, sigma=sigma, params=params, param_tiling=tiling, alpha=alpha)
+    full = ops.rollout_cost(spec, state0, noise, want=("costs", "log_lik", "lik_weights", "grad_lik"), **kw)
+    g_full = ops.rollout_adjoint(spec, state0, noise, full["lik_weights"], **kw)
+    costs = torch.zeros_like(full["costs"])
+    grad = torch.zeros_like(g_full)
+    for r in range(world):
+        p0, p1 = row_block(P, r, world)
+        if p1 == p0:
+            continue
+        costs += ops.rollout_cost(spec, state0, noise, want=("costs",), p_range=(p0, p1), **kw)["costs"]
+        grad += ops.rollout_adjoint(spec, state0, noise, full["lik_weights"], p_range=(p0, p1), **kw)
+    assert rel_elem(costs.cpu(), full["costs"].cpu()) <= 2e-6
+    assert rel_max(grad.cpu(), g_full.cpu()) <= 1e-5
+    red = ops.rollout_cost(spec, state0, noise, want=("log_lik", "lik_weights", "grad_lik"), out={"costs": full["costs"].clone()},
+                           reduce_only=True, **kw)
+    for k in ("log_lik", "lik_weights", "grad_lik"):
+        assert torch.equal(red[k], full[k]), k
+    with pytest.raises(ValueError):
+        ops.rollout_cost(spec, state0, noise, want=("costs", "log_lik"), p_range=(0, 1), **kw)
+    with pytest.raises(ValueError):
+        ops.rollout_cost(spec, state0, noise, want=("costs",), p_range=(0, P + 1), **kw)
+
+
+# ---------------------------------------------------------------------------------------------
 # tcgen05 / TMEM 3xTF32 phi (N multiple of 128, N >= 1024, D <= 47)
 # ---------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,D,gamma", [(1024, 40, 0.02), (2048, 16, 0.05), (4096, 40, 0.015), (8192, 24, 0.03), (3072, 40, 1.5)])

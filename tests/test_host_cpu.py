@@ -200,6 +200,73 @@ def test_sharded_svgd_host_logic_gloo_world2(tmp_path):
     assert res.stdout.count("ok") == 2
 
 
+# ---- world_size-2 gloo run of the parameter-draw sharding of one instance (compute callbacks = the oracle) ----
+_WORKER_ROLLOUT = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["DUST_ROOT"])
+from oracle import dust_oracle as O
+from dust_b200.distributed import ShardedRollout
+
+MODEL = O.Model("pendulum")
+
+class OracleOps:
+    """CPU stand-ins with the ABI's semantics: a draw range yields its share of the mean cost / gradient."""
+    @staticmethod
+    def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, alpha=1.0, want=(), out=None, p_range=None,
+                     reduce_only=False, **kw):
+        actions = theta[0] + sigma * noise[0]
+        if not reduce_only:
+            P = params.shape[1]
+            st = O.rollout(MODEL, state0[0], actions, params[0, p_range[0]:p_range[1]])
+            c = O.trajectory_costs(MODEL, st, actions) * (p_range[1] - p_range[0]) / P
+            return {"costs": c.unsqueeze(0)}
+        costs = out["costs"][0]
+        res = {"costs": out["costs"], "log_lik": O.exp_utility_log_prob(costs, alpha).unsqueeze(0)}
+        w = torch.softmax(-alpha * costs, 0)
+        res["lik_weights"] = w.unsqueeze(0)
+        res["grad_lik"] = O.analytic_lik_grad(costs, actions, theta[0], sigma, alpha).unsqueeze(0)
+        return res
+    @staticmethod
+    def rollout_adjoint(spec, state0, noise, lik_w, theta=None, sigma=None, params=None, alpha=1.0, p_range=None, **kw):
+        P = params.shape[1]
+        th = theta[0].clone().requires_grad_(True)
+        actions = th + sigma * noise[0]
+        st = O.rollout(MODEL, state0[0], actions, params[0, p_range[0]:p_range[1]])
+        c = O.trajectory_costs(MODEL, st, actions) * (p_range[1] - p_range[0]) / P
+        (g,) = torch.autograd.grad((-alpha * lik_w[0] * c).sum(), th)     # d log_l / d theta through the costs
+        return g.unsqueeze(0)
+
+dist.init_process_group("gloo")
+r, w = dist.get_rank(), dist.get_world_size()
+torch.manual_seed(0)
+S, N, H, P = 16, 3, 8, 5
+state0, theta, sigma = torch.tensor([[2.5, 0.3]]), torch.randn(1, N, H, 1), torch.tensor([2.0])
+noise, params = torch.randn(1, S, N, H, 1), torch.rand(1, P, 2) * 0.7 + 0.6
+sh = ShardedRollout(P, ops=OracleOps)
+assert sh.p_range == ((0, 3) if r == 0 else (3, 5))
+full = ShardedRollout.__new__(ShardedRollout); full.P, full.group, full.ops, full.rank, full.world, full.p_range = P, None, OracleOps, 0, 1, (0, P)
+for grad in ("analytic", "pathwise"):
+    a = sh.evaluate(None, state0, noise, theta, sigma, params, alpha=0.01, grad=grad)
+    b = full.evaluate(None, state0, noise, theta, sigma, params, alpha=0.01, grad=grad)
+    for k in ("costs", "log_lik", "grad_lik"):
+        err = float((a[k] - b[k]).abs().max() / b[k].abs().max())
+        assert err < 1e-5, (grad, k, err)
+dist.destroy_process_group()
+print("rank", r, "ok")
+'''
+
+
+def test_sharded_rollout_host_logic_gloo_world2(tmp_path):
+    script = tmp_path / "worker_rollout.py"
+    script.write_text(_WORKER_ROLLOUT)
+    env = dict(os.environ, DUST_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29633", str(script)],
+                         env=env, capture_output=True, text=True, timeout=240)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert res.stdout.count("ok") == 2
+
+
 def test_demo_default_configs_equal_the_reference_yaml():
     """demo/configs.py carries the reference's two configurations key for key; where the reference tree is
     mounted (the build container) its yaml files must load to the same dictionaries."""
