@@ -295,14 +295,27 @@ __global__ void __launch_bounds__(kAdjTile) rollout_adjoint_kernel(const AdjKPar
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int W, int parts) {
+// out[inst][col] = sum over the `parts` partial rows, in a fixed order: a CTA owns 32 columns, its 8 warps
+// take the rows r = w, w + 8, ... (128-byte coalesced reads), and the 8 sub-sums are added in warp order
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partial, float* __restrict__ out, int W,
+                                                              int parts) {
+  __shared__ float sub[8][33];
   const long long inst = blockIdx.y;
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= W) return;
-  const float* p = partial + inst * (long long)parts * W + col;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int q = 0; q < parts; ++q) acc += p[(long long)q * W];
-  out[inst * W + col] = acc;
+  if (col < W) {
+    const float* p = partial + inst * (long long)parts * W + col;
+    for (int q = warp; q < parts; q += 8) acc += p[(long long)q * W];
+  }
+  sub[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0 && col < W) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sub[w][lane];
+    out[inst * W + col] = t;
+  }
 }
 
 struct AdjPlan {
@@ -391,7 +404,7 @@ extern "C" int dust_rollout_adjoint(const dust_adjoint_args* a, void* stream_) {
   }
   if (rc) return rc;
   const int W = a->N * k.HA;
-  { DUST_TIMED("reduce_partials_kernel", stream); reduce_partials_kernel<<<dim3((unsigned)ceil_div(W, 256), (unsigned)a->B, 1), 256, 0, stream>>>(
+  { DUST_TIMED("reduce_partials_kernel", stream); reduce_partials_kernel<<<dim3((unsigned)ceil_div(W, 32), (unsigned)a->B, 1), 256, 0, stream>>>(
       k.partial, a->grad_theta, W, pl.tiles * pl.PC); }
   DUST_LAUNCH_OK("reduce_partials_kernel");
   return DUST_OK;

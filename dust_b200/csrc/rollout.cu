@@ -732,15 +732,42 @@ struct SoftminKParams {
   float* lik_w;            // [B,S,N] or null
   float* mppi_w;           // [B,S,N] or null
   float* mix;              // [B,N] or null
+  float* eta;              // [B,N] scratch for a_mix when spread (may be null if mix is not requested)
+  int spread;              // the policies of an instance are spread over grid.y; chunk sums were combined before
 };
 
 constexpr int kSoftminThreads = 256;
+
+// few instances: the chunk sums are combined by a grid over the trajectories (same order of additions as
+// the one-CTA loop below), the policies are spread over grid.y, and a_mix is formed from the etas afterwards
+__global__ void __launch_bounds__(256) combine_cost_chunks_kernel(const SoftminKParams k) {
+  const long long inst = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= k.SN) return;
+  const float* part = k.cost_part + inst * (long long)k.PC * k.SN;
+  float acc = 0.f;
+  for (int c = 0; c < k.PC; ++c) acc = acc + part[(long long)c * k.SN + j];
+  k.costs[inst * k.SN + j] = acc / (float)k.P;
+}
+
+__global__ void __launch_bounds__(32) policy_mix_kernel(const float* __restrict__ eta, float* __restrict__ mix, int N) {
+  const long long inst = blockIdx.x;
+  const int lane = threadIdx.x;
+  const float* e = eta + inst * N;
+  float mx = -INFINITY;
+  for (int n = lane; n < N; n += 32) mx = fmaxf(mx, e[n]);
+  mx = warp_max(mx);
+  float z = 0.f;
+  for (int n = lane; n < N; n += 32) z += expf(e[n] - mx);
+  z = warp_sum(z);
+  for (int n = lane; n < N; n += 32) mix[inst * N + n] = expf(e[n] - mx) / z;
+}
 
 __global__ void __launch_bounds__(kSoftminThreads) policy_softmin_kernel(const SoftminKParams k) {
   extern __shared__ float sm_eta[];  // [N] eta_n
   const long long inst = blockIdx.x;
   float* costs = k.costs + inst * k.SN;
-  if (k.PC > 1) {
+  if (k.PC > 1 && !k.spread) {
     const float* part = k.cost_part + inst * (long long)k.PC * k.SN;
     for (int j = threadIdx.x; j < k.SN; j += blockDim.x) {
       float acc = 0.f;
@@ -751,7 +778,7 @@ __global__ void __launch_bounds__(kSoftminThreads) policy_softmin_kernel(const S
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const bool need_mppi = (k.mppi_w != nullptr) || (k.mix != nullptr);
-  for (int n = warp; n < k.N; n += nwarps) {
+  for (int n = blockIdx.y * nwarps + warp; n < k.N; n += nwarps * gridDim.y) {
     float cmin = INFINITY, csum = 0.f;
     for (int s = lane; s < k.S; s += 32) {
       const float c = costs[s * k.N + n];
@@ -782,9 +809,13 @@ __global__ void __launch_bounds__(kSoftminThreads) policy_softmin_kernel(const S
       if (k.lik_w) k.lik_w[inst * k.SN + s * k.N + n] = expf(-k.alpha * (c - cmin)) * inv_za;
       if (k.mppi_w) k.mppi_w[inst * k.SN + s * k.N + n] = expf(-(c - cmin) * k.inv_temp) * inv_zt;
     }
-    if (need_mppi && lane == 0) sm_eta[n] = -cmin * k.inv_temp + logf(zt);  // eta_n + beta/temp
+    if (need_mppi && lane == 0) {
+      const float eta = -cmin * k.inv_temp + logf(zt);  // eta_n + beta/temp
+      if (!k.spread) sm_eta[n] = eta;
+      else if (k.eta) k.eta[inst * k.N + n] = eta;
+    }
   }
-  if (k.mix) {
+  if (k.mix && !k.spread) {
     __syncthreads();
     // a_mix = softmax_n(eta) (disco.py:393); the global shift beta cancels
     if (warp == 0) {
@@ -884,7 +915,7 @@ static int choose_param_chunks(long long BSN, int P) {
 
 struct RolloutPlan {
   int PC, Pchunk;
-  size_t off_part, off_likw, off_mppiw, off_costs, total;
+  size_t off_part, off_likw, off_mppiw, off_costs, off_eta, total;
 };
 
 static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = false) {
@@ -908,6 +939,7 @@ static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = 
   pl.off_likw = take(a->grad_lik && !a->lik_weights, per_traj);
   pl.off_mppiw = take(a->mppi_delta && !a->mppi_weights, per_traj);
   pl.off_costs = take(!a->costs, per_traj);
+  pl.off_eta = take(a->mix != nullptr, sizeof(float) * (size_t)a->B * a->N);
   pl.total = off;
   return pl;
 }
@@ -1050,8 +1082,27 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
     s.B = a->B; s.N = a->N; s.S = a->S; s.P = P; s.PC = pl.PC; s.SN = (int)SN;
     s.likelihood = a->likelihood; s.alpha = a->alpha; s.inv_temp = 1.0f / a->temperature;
     s.cost_part = part; s.costs = costs; s.log_lik = a->log_lik; s.lik_w = likw; s.mppi_w = mppiw; s.mix = a->mix;
-    { DUST_TIMED("policy_softmin_kernel", stream); policy_softmin_kernel<<<a->B, kSoftminThreads, sizeof(float) * a->N, stream>>>(s); }
-    DUST_LAUNCH_OK("policy_softmin_kernel");
+    s.eta = nullptr; s.spread = 0;
+    if (a->B * 2 >= kNumSMs) {   // many instances: one CTA each
+      { DUST_TIMED("policy_softmin_kernel", stream); policy_softmin_kernel<<<a->B, kSoftminThreads, sizeof(float) * a->N, stream>>>(s); }
+      DUST_LAUNCH_OK("policy_softmin_kernel");
+    } else {                     // few: spread the trajectories, then the policies (two warps per CTA), over the SMs
+      DUST_REQUIRE(a->B <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: B > 65535");
+      s.spread = 1;
+      s.eta = a->mix ? (float*)(ws + pl.off_eta) : nullptr;
+      if (pl.PC > 1) {
+        { DUST_TIMED("combine_cost_chunks_kernel", stream); combine_cost_chunks_kernel<<<dim3((unsigned)ceil_div(SN, 256), (unsigned)a->B, 1), 256, 0, stream>>>(s); }
+        DUST_LAUNCH_OK("combine_cost_chunks_kernel");
+      }
+      if (a->log_lik || likw || mppiw || a->mix) {
+        { DUST_TIMED("policy_softmin_kernel", stream); policy_softmin_kernel<<<dim3((unsigned)a->B, (unsigned)ceil_div(a->N, 2), 1), 64, sizeof(float) * a->N, stream>>>(s); }
+        DUST_LAUNCH_OK("policy_softmin_kernel");
+      }
+      if (a->mix) {
+        { DUST_TIMED("policy_mix_kernel", stream); policy_mix_kernel<<<a->B, 32, 0, stream>>>(s.eta, a->mix, a->N); }
+        DUST_LAUNCH_OK("policy_mix_kernel");
+      }
+    }
   }
   if (a->grad_lik || a->mppi_delta) {
     ColsumKParams c;

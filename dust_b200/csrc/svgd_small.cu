@@ -220,9 +220,10 @@ struct FwdKParams {
   const float* resample_noise;
 };
 
-constexpr int kFwdWarps = 4;
+constexpr int kFwdWarps = 4;        // many instances: small CTAs, several per SM
+constexpr int kFwdWarpsWide = 32;   // a few instances: a warp per policy
 
-__global__ void __launch_bounds__(kFwdWarps * 32) svmpc_forward_kernel(const FwdKParams k) {
+__global__ void __launch_bounds__(kFwdWarpsWide * 32) svmpc_forward_kernel(const FwdKParams k) {
   extern __shared__ float sm[];
   float* logmix = sm;                       // [N]
   float* logw = sm + k.N;                   // [N]
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) svmpc_forward_kernel(const Fwd
   const float* mu = k.mu + inst * (long long)k.N * k.D;
   if (warp == 0) warp_log_mix(k.mix ? k.mix + inst * k.N : nullptr, k.N, logmix);
   __syncthreads();
-  for (int n = warp; n < k.N; n += kFwdWarps) {
+  for (int n = warp; n < k.N; n += (int)(blockDim.x >> 5)) {
     float xr[kMaxDPerLane];
 #pragma unroll
     for (int q = 0; q < kMaxDPerLane; ++q) {
@@ -456,11 +457,14 @@ extern "C" int dust_svmpc_forward(const dust_svmpc_forward_args* a, void* stream
                "dust_svmpc_forward: invalid roll strategy %d", a->roll_strategy);
   const int D = a->H * a->A;
   DUST_REQUIRE(D <= 32 * kMaxDPerLane, DUST_ERR_UNSUPPORTED, "dust_svmpc_forward: H*A=%d > %d", D, 32 * kMaxDPerLane);
-  const size_t smem = sizeof(float) * a->N * (2 + kFwdWarps);
+  // few instances: as many warps as policies (the CTA is alone on its SM anyway)
+  int warps = kFwdWarps;
+  if (a->B < kNumSMs) { warps = a->N < kFwdWarpsWide ? a->N : kFwdWarpsWide; if (warps < kFwdWarps) warps = kFwdWarps; }
+  const size_t smem = sizeof(float) * a->N * (2 + warps);
   DUST_REQUIRE(smem <= 48 * 1024, DUST_ERR_UNSUPPORTED, "dust_svmpc_forward: N=%d too large", a->N);
   FwdKParams k{a->B, a->N, a->H, a->A, D, a->roll_strategy, a->weighted_prior, a->log_lik, a->theta, a->mu, a->mix,
                a->inv_var, a->log_norm, a->p_weights, a->i_star, a->a_seq, a->theta_next, a->mix_next, a->resample_noise};
-  { DUST_TIMED("svmpc_forward_kernel", (cudaStream_t)stream_); svmpc_forward_kernel<<<a->B, kFwdWarps * 32, smem, (cudaStream_t)stream_>>>(k); }
+  { DUST_TIMED("svmpc_forward_kernel", (cudaStream_t)stream_); svmpc_forward_kernel<<<a->B, warps * 32, smem, (cudaStream_t)stream_>>>(k); }
   DUST_LAUNCH_OK("svmpc_forward_kernel");
   return DUST_OK;
 }
