@@ -30,6 +30,7 @@ struct RolloutKParams {
   int HA;          // H*A
   int PC;          // number of parameter chunks (grid.y)
   int Pchunk;      // parameters per chunk
+  int parts;       // partial cost rows per instance = PC * (sub-chunks per CTA); 1: the CTA writes final costs
   int p0, p1;      // draws [p0, p1) of the P resident ones are rolled out by this call (a rank's share)
   int interleaved;
   const float* state0;
@@ -270,8 +271,11 @@ __device__ __forceinline__ float trajectory_cost_dispatch(const RolloutKParams& 
   return trajectory_cost_sum<MODEL, false, false>(k, arow, grid_s, inst, j, p_begin, p_end);
 }
 
-template <int MODEL, bool EXT>
-__global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParams k) {
+// NSUB: sub-chunks per CTA.  The action tile of 128 trajectories (52 KB at H*A = 100) limits an SM to a few
+// CTAs; with NSUB > 1 the tile is shared by NSUB groups of 128 threads, each rolling out its own slice of the
+// CTA's parameter chunk into its own partial row (fixed order of partial rows: deterministic).
+template <int MODEL, bool EXT, int NSUB>
+__global__ void __launch_bounds__(kTile * NSUB) rollout_cost_kernel(const RolloutKParams k) {
   constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
   extern __shared__ __align__(16) float smem[];
   const int stride = padded_stride(k.HA);
@@ -284,22 +288,27 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
   const int rows = min(kTile, k.SN - j0);
   const int pc = blockIdx.y;
 
-  load_action_tile<A, kTile>(k, tile, stride, inst, j0, rows,
-                             k.theta ? k.theta + inst * (long long)k.N * k.HA : nullptr);
+  load_action_tile<A, kTile * NSUB>(k, tile, stride, inst, j0, rows,
+                                    k.theta ? k.theta + inst * (long long)k.N * k.HA : nullptr);
   if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
     const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
-    for (int w = threadIdx.x; w < words; w += kTile) grid_s[w] = __ldg(k.m.grid_bits + w);
+    for (int w = threadIdx.x; w < words; w += kTile * NSUB) grid_s[w] = __ldg(k.m.grid_bits + w);
   }
   __syncthreads();
 
-  const int row = threadIdx.x;
+  const int row = threadIdx.x % kTile, sub = threadIdx.x / kTile;
   if (row >= rows) return;
   const int j = j0 + row;
-  const int p_begin = k.p0 + pc * k.Pchunk;
-  const int p_end = min(k.p1, p_begin + k.Pchunk);
+  int p_begin = k.p0 + pc * k.Pchunk;
+  int p_end = min(k.p1, p_begin + k.Pchunk);
+  if (NSUB > 1) {   // this thread group's slice of the chunk (possibly empty: it then contributes an exact 0)
+    const int sl = (p_end - p_begin + NSUB - 1) / NSUB;
+    p_begin += sub * sl;
+    p_end = min(p_end, p_begin + sl);
+  }
   const float csum = trajectory_cost_dispatch<MODEL, EXT>(k, tile + row * stride, grid_s, inst, j, p_begin, p_end,
                                                           small_angle_horizon<MODEL>(k, inst));
-  if (k.PC == 1) {
+  if (k.parts == 1) {
     float cost = (EXT && k.ut_w) ? csum : csum / (float)k.P;  // sigma-point weights, or the mean over parameter samples (disco.py:330)
     if (EXT && k.ctrl_mat) {
       // control regulariser (disco.py:334-344): a_reg * sum_{h,a} -(action - a_seq) (a_mat a_pre)[n]
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(kTile) rollout_cost_kernel(const RolloutKParam
     }
     k.cost_out[inst * k.SN + j] = cost;
   } else {
-    k.cost_out[(inst * k.PC + pc) * (long long)k.SN + j] = csum;
+    k.cost_out[(inst * k.parts + pc * NSUB + sub) * (long long)k.SN + j] = csum;
   }
 }
 
@@ -914,7 +923,7 @@ static int choose_param_chunks(long long BSN, int P) {
 }
 
 struct RolloutPlan {
-  int PC, Pchunk;
+  int PC, Pchunk, NSUB, parts;
   size_t off_part, off_likw, off_mppiw, off_costs, off_eta, total;
 };
 
@@ -928,6 +937,14 @@ static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = 
   pc = (P + chunk - 1) / chunk;
   pl.PC = pc;
   pl.Pchunk = chunk;
+  // a wide action tile leaves room for only a few 128-thread CTAs per SM: let up to 4 thread groups share one
+  pl.NSUB = 1;
+  {
+    const int A = model_da(a->model->kind);
+    const size_t tile_bytes = sizeof(float) * kTile * padded_stride(a->H * A);
+    if (!single_chunk && !a->states && tile_bytes * 6 > 227 * 1024) pl.NSUB = chunk >= 8 ? 4 : (chunk >= 4 ? 2 : 1);
+  }
+  pl.parts = pl.PC * pl.NSUB;
   size_t off = 0;
   auto take = [&](bool needed, size_t bytes) {
     const size_t o = off;
@@ -935,7 +952,7 @@ static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = 
     return o;
   };
   const size_t per_traj = sizeof(float) * (size_t)a->B * (size_t)SN;
-  pl.off_part = take(pc > 1, per_traj * pc);
+  pl.off_part = take(pl.parts > 1, per_traj * pl.parts);
   pl.off_likw = take(a->grad_lik && !a->lik_weights, per_traj);
   pl.off_mppiw = take(a->mppi_delta && !a->mppi_weights, per_traj);
   pl.off_costs = take(!a->costs, per_traj);
@@ -982,23 +999,23 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
                DUST_ERR_INVALID_ARG, "dust_rollout_cost: a draw range only produces `costs` (its share of the mean)");
   DUST_REQUIRE(!reduce_only || a->costs, DUST_ERR_INVALID_ARG, "dust_cost_reduce: costs (input) is required");
   RolloutPlan pl = plan_rollout(a, tail != nullptr);
-  if (reduce_only) pl.PC = 1;
+  if (reduce_only) { pl.PC = 1; pl.NSUB = 1; pl.parts = 1; }
   DUST_REQUIRE(pl.total == 0 || (a->workspace && a->workspace_bytes >= pl.total), DUST_ERR_WORKSPACE,
                "dust_rollout_cost: workspace needs %zu bytes, got %zu", pl.total, a->workspace_bytes);
   char* ws = (char*)a->workspace;
   float* costs = a->costs ? a->costs : (float*)(ws + pl.off_costs);
-  float* part = pl.PC > 1 ? (float*)(ws + pl.off_part) : nullptr;
+  float* part = pl.parts > 1 ? (float*)(ws + pl.off_part) : nullptr;
   float* likw = a->lik_weights ? a->lik_weights : ((a->grad_lik) ? (float*)(ws + pl.off_likw) : nullptr);
   float* mppiw = a->mppi_weights ? a->mppi_weights : ((a->mppi_delta) ? (float*)(ws + pl.off_mppiw) : nullptr);
 
   RolloutKParams k;
   k.m = to_params(*a->model);
   k.B = a->B; k.N = a->N; k.S = a->S; k.P = P; k.H = a->H; k.A = A;
-  k.SN = (int)SN; k.HA = a->H * A; k.PC = pl.PC; k.Pchunk = pl.Pchunk;
+  k.SN = (int)SN; k.HA = a->H * A; k.PC = pl.PC; k.Pchunk = pl.Pchunk; k.parts = pl.parts;
   k.p0 = ranged ? a->p_begin : 0; k.p1 = ranged ? a->p_end : P;
   k.interleaved = a->param_tiling == DUST_PARAMS_INTERLEAVED;
   k.state0 = a->state0; k.theta = a->theta; k.noise = a->noise; k.sigma = a->sigma; k.params = a->params;
-  k.cost_out = pl.PC > 1 ? part : costs;
+  k.cost_out = pl.parts > 1 ? part : costs;
   k.states = a->states;
   k.ut_w = a->sigma_weights; k.ctrl_mat = a->ctrl_mat; k.a_seq = a->a_seq; k.ctrl_reg = a->ctrl_reg;
   DUST_REQUIRE(!a->sigma_weights || (a->params && a->param_tiling == DUST_PARAMS_BLOCKED), DUST_ERR_INVALID_ARG,
@@ -1011,7 +1028,7 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
                                 ? sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32) : 0;
   // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
   const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
-  const bool fused_ok = fused_outputs_only && !ranged && !reduce_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.PC == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
+  const bool fused_ok = fused_outputs_only && !ranged && !reduce_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.parts == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
                         (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
   DUST_REQUIRE(fused_ok || !tail, DUST_ERR_UNSUPPORTED,
                "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");
@@ -1061,25 +1078,30 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   DUST_REQUIRE(gx < (1ll << 31) && pl.PC <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: grid too large");
   dim3 grid((unsigned)gx, (unsigned)pl.PC, 1);
   const bool ext = a->sigma_weights || a->ctrl_mat;
-#define DUST_ROLLOUT(MODEL, EXT)                                                                                       \
+#define DUST_ROLLOUT(MODEL, EXT, NSUB)                                                                                 \
   do {                                                                                                                 \
     if (smem > 48 * 1024)                                                                                              \
-      DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<MODEL, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<MODEL, EXT><<<grid, kTile, smem, stream>>>(k); }  \
+      DUST_CUDA_OK(cudaFuncSetAttribute(rollout_cost_kernel<MODEL, EXT, NSUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    { DUST_TIMED("rollout_cost_kernel", stream); rollout_cost_kernel<MODEL, EXT, NSUB><<<grid, kTile * NSUB, smem, stream>>>(k); }  \
   } while (0)
-  if (kind == DUST_MODEL_PENDULUM) {
-    if (ext) DUST_ROLLOUT(DUST_MODEL_PENDULUM, true); else DUST_ROLLOUT(DUST_MODEL_PENDULUM, false);
-  } else {
-    if (ext) DUST_ROLLOUT(DUST_MODEL_PARTICLE, true); else DUST_ROLLOUT(DUST_MODEL_PARTICLE, false);
-  }
+#define DUST_ROLLOUT_SUB(MODEL)                                                                                        \
+  do {                                                                                                                 \
+    if (ext) DUST_ROLLOUT(MODEL, true, 1);                                                                             \
+    else if (pl.NSUB == 4) DUST_ROLLOUT(MODEL, false, 4);                                                              \
+    else if (pl.NSUB == 2) DUST_ROLLOUT(MODEL, false, 2);                                                              \
+    else DUST_ROLLOUT(MODEL, false, 1);                                                                                \
+  } while (0)
+  if (kind == DUST_MODEL_PENDULUM) DUST_ROLLOUT_SUB(DUST_MODEL_PENDULUM);
+  else DUST_ROLLOUT_SUB(DUST_MODEL_PARTICLE);
+#undef DUST_ROLLOUT_SUB
 #undef DUST_ROLLOUT
   DUST_LAUNCH_OK("rollout_cost_kernel");
   }
 
-  const bool need_stats = pl.PC > 1 || a->log_lik || likw || mppiw || a->mix;
+  const bool need_stats = pl.parts > 1 || a->log_lik || likw || mppiw || a->mix;
   if (need_stats) {
     SoftminKParams s;
-    s.B = a->B; s.N = a->N; s.S = a->S; s.P = P; s.PC = pl.PC; s.SN = (int)SN;
+    s.B = a->B; s.N = a->N; s.S = a->S; s.P = P; s.PC = pl.parts; s.SN = (int)SN;
     s.likelihood = a->likelihood; s.alpha = a->alpha; s.inv_temp = 1.0f / a->temperature;
     s.cost_part = part; s.costs = costs; s.log_lik = a->log_lik; s.lik_w = likw; s.mppi_w = mppiw; s.mix = a->mix;
     s.eta = nullptr; s.spread = 0;
@@ -1090,7 +1112,7 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
       DUST_REQUIRE(a->B <= 65535, DUST_ERR_UNSUPPORTED, "dust_rollout_cost: B > 65535");
       s.spread = 1;
       s.eta = a->mix ? (float*)(ws + pl.off_eta) : nullptr;
-      if (pl.PC > 1) {
+      if (pl.parts > 1) {
         { DUST_TIMED("combine_cost_chunks_kernel", stream); combine_cost_chunks_kernel<<<dim3((unsigned)ceil_div(SN, 256), (unsigned)a->B, 1), 256, 0, stream>>>(s); }
         DUST_LAUNCH_OK("combine_cost_chunks_kernel");
       }

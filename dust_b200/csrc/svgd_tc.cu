@@ -591,9 +591,10 @@ __global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) 
 
 // equal contiguous unit ranges over at most one CTA per SM; a floor on the range length keeps the
 // per-CTA prologue (TMEM allocation, A operand, pipeline fill, O drain: ~5 tile times) amortised
-struct TcPlan { int grid, units_per_cta, total_units, max_seg; };
+struct TcPlan { int grid, units_per_cta, total_units, max_seg, row_tile0, row_tiles; };
 static TcPlan tc_plan(int row_tiles, int T) {
   TcPlan pl;
+  pl.row_tile0 = 0; pl.row_tiles = row_tiles;
   pl.total_units = row_tiles * T;
   const int floor_units = T < 16 ? T : 16;
   int W = ceil_div(pl.total_units, kNumSMs);
@@ -602,6 +603,27 @@ static TcPlan tc_plan(int row_tiles, int T) {
   pl.grid = ceil_div(pl.total_units, W);
   pl.max_seg = (W + T - 2) / T + 1;
   return pl;
+}
+// A call is cut into at most two launches.  First k = row_tiles / 148 WHOLE row tiles per SM: every CTA
+// starts at column tile 0 and they sweep the column images together, so a tile fetched from HBM by one
+// CTA is an L2 hit for the other 147 (with ranges that start at scattered column phases the 63 MB of
+// operand images are streamed by every CTA on its own schedule and no longer stay resident: 2.1 GB of
+// DRAM reads per launch instead of ~0.4).  Then the remaining row tiles, as equal unit ranges.
+static int tc_launch_plans(int row_tiles, int T, TcPlan out[2]) {
+  int n = 0;
+  const int k = row_tiles / kNumSMs;
+  if (k >= 1) {
+    TcPlan& a = out[n++];
+    a.row_tile0 = 0; a.row_tiles = k * kNumSMs;
+    a.total_units = a.row_tiles * T; a.units_per_cta = k * T; a.grid = kNumSMs; a.max_seg = k;
+  }
+  const int rest = row_tiles - k * kNumSMs;
+  if (rest > 0) {
+    out[n] = tc_plan(rest, T);
+    out[n].row_tile0 = k * kNumSMs;
+    ++n;
+  }
+  return n;
 }
 
 // =======================================================================================
@@ -1032,8 +1054,11 @@ bool phi_tc_supported(const dust_phi_args* a) {
 size_t phi_tc_workspace(const dust_phi_args* a) {
   const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
   const int rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
-  const TcPlan pl = tc_plan(rows / kTcBM, a->N / kTcBN);
-  return sizeof(float) * (N * (2 * Dp + 2 * NV + 1) + 64 + (size_t)pl.grid * pl.max_seg * (NV + 2) * kTcBM);
+  TcPlan pl[2];
+  const int n = tc_launch_plans(rows / kTcBM, a->N / kTcBN, pl);
+  size_t slots = 0;
+  for (int i = 0; i < n; ++i) slots += (size_t)pl[i].grid * pl[i].max_seg;
+  return sizeof(float) * (N * (2 * Dp + 2 * NV + 1) + 64 + slots * (NV + 2) * kTcBM);
 }
 
 int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
@@ -1058,20 +1083,26 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   // ONE image serves as the A operand (row tiles) and as the B operand (column tiles)
   p.xa_hi = x_hi; p.xa_lo = x_lo; p.xb_hi = x_hi; p.xb_lo = x_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
   p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out; p.oacc = oacc;
-  const TcPlan pl = tc_plan(row_tiles, p.T);
-  p.units_per_cta = pl.units_per_cta; p.total_units = pl.total_units; p.max_seg = pl.max_seg;
   const TcSmem L = tc_smem_layout(Dp, NV);
   DUST_CUDA_OK(cudaFuncSetAttribute(phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
-  {
-    DUST_TIMED("phi_tc_kernel", stream);
-    phi_tc_kernel<<<pl.grid, kTcThreads, L.total, stream>>>(p);
+  TcPlan plans[2];
+  const int n_plans = tc_launch_plans(row_tiles, p.T, plans);
+  for (int i = 0; i < n_plans; ++i) {
+    const TcPlan& pl = plans[i];
+    p.row_begin = r0 + pl.row_tile0 * kTcBM;
+    p.units_per_cta = pl.units_per_cta; p.total_units = pl.total_units; p.max_seg = pl.max_seg;
+    {
+      DUST_TIMED("phi_tc_kernel", stream);
+      phi_tc_kernel<<<pl.grid, kTcThreads, L.total, stream>>>(p);
+    }
+    DUST_LAUNCH_OK("phi_tc_kernel");
+    {
+      DUST_TIMED("phi_tc_finish_kernel", stream);
+      phi_tc_finish_kernel<<<dim3(pl.row_tiles, ceil_div(D, 8)), kTcBM, 0, stream>>>(p);
+    }
+    DUST_LAUNCH_OK("phi_tc_finish_kernel");
+    p.oacc += (size_t)pl.grid * pl.max_seg * (NV + 2) * kTcBM;
   }
-  DUST_LAUNCH_OK("phi_tc_kernel");
-  {
-    DUST_TIMED("phi_tc_finish_kernel", stream);
-    phi_tc_finish_kernel<<<dim3(row_tiles, ceil_div(D, 8)), kTcBM, 0, stream>>>(p);
-  }
-  DUST_LAUNCH_OK("phi_tc_finish_kernel");
   return DUST_OK;
 }
 

@@ -258,8 +258,17 @@ def test_unsupported_paths_fail_loudly():
                       params_sampling=None)
     with pytest.raises(NotImplementedError):
         ctrl.forward(torch.zeros(2), model, None, torch.zeros(4, 2, 5, 1))
+    # the control regulariser is supported stand-alone (test_multidisco_control_regulariser), not under SVMPC
+    reg = MultiDISCO(model.observation_space, model.action_space, 5, 2, 4, inst_cost_fn=demo_inst_cost, ctrl_penalty=0.5)
+    assert reg.a_reg == 0.5
+    from dust_b200.inference.likelihoods import ExponentiatedUtility
+    from dust_b200.inference.svgd import get_gmm
+    from dust_b200.inference.svmpc import SVMPC
+    from dust_b200.kernels.base_kernels import RBFKernel
     with pytest.raises(NotImplementedError):
-        MultiDISCO(model.observation_space, model.action_space, 5, 2, 4, inst_cost_fn=demo_inst_cost, ctrl_penalty=0.5)
+        SVMPC(init_particles=torch.zeros(2, 5, 1), prior=get_gmm(torch.zeros(2, 5, 1), torch.ones(2), torch.eye(1)),
+              likelihood=ExponentiatedUtility(1.0, n_samples=4, controller=reg, model=model), kernel=RBFKernel(), n_particles=2,
+              n_steps=1, optimizer_class=torch.optim.SGD, lr=1.0)
     with pytest.raises(ValueError):
         MultiDISCO(model.observation_space, model.action_space, 5, 2, 4, inst_cost_fn=demo_inst_cost,
                    params_sampling="sometimes")
