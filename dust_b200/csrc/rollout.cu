@@ -939,7 +939,7 @@ static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = 
   pl.Pchunk = chunk;
   // a wide action tile leaves room for only a few 128-thread CTAs per SM: let up to 4 thread groups share one
   pl.NSUB = 1;
-  {
+  if (a->model != nullptr) {
     const int A = model_da(a->model->kind);
     const size_t tile_bytes = sizeof(float) * kTile * padded_stride(a->H * A);
     if (!single_chunk && !a->states && tile_bytes * 6 > 227 * 1024) pl.NSUB = chunk >= 8 ? 4 : (chunk >= 4 ? 2 : 1);

@@ -48,6 +48,32 @@ def test_struct_layouts_match_the_header():
     for line in out.strip().splitlines():
         n, sz = line.split()
         assert ctypes.sizeof(names[n]) == int(sz), n
+    # ... and every field sits at the offset the C compiler gives it (same names on both sides)
+    fields = [(n, f[0]) for n, cls in names.items() for f in cls._fields_]
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "dust_b200.h"\nint main(){' + "".join(
+        f'printf("{n} {f} %zu\\n", offsetof({n}, {f}));' for n, f in fields) + "return 0;}"
+    subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=src.encode(), check=True)
+    out = subprocess.run([exe], capture_output=True, check=True).stdout.decode()
+    for line in out.strip().splitlines():
+        n, f, off = line.split()
+        assert getattr(names[n], f).offset == int(off), (n, f)
+
+
+def test_workspace_queries_tolerate_incomplete_arguments():
+    """The *_workspace_bytes functions are called before validation: zeroed / model-less structs must not crash."""
+    import ctypes as C
+
+    from dust_b200 import _lib
+
+    lib = _lib.load()
+    a = _lib.RolloutArgs()
+    assert lib.dust_rollout_workspace_bytes(C.byref(a)) == 0
+    a.B, a.N, a.S, a.P, a.H = 1, 4, 64, 8, 50          # sizes set, model still NULL
+    assert lib.dust_rollout_workspace_bytes(C.byref(a)) >= 0
+    adj = _lib.AdjointArgs()
+    assert lib.dust_adjoint_workspace_bytes(C.byref(adj)) == 0
+    m = _lib.MpfArgs()
+    assert lib.dust_mpf_workspace_bytes(C.byref(m)) == 0
 
 
 def test_no_cpu_fallback_without_a_device():
