@@ -6,17 +6,19 @@
 //   phi_i = c1 * sum_j K_ij s_j + c2 * (x_i sum_j K_ij - sum_j K_ij x_j),  K_ij = exp(-gamma d2_ij),
 //   d2_ij = max(|x_i|^2 + |x_j|^2 - 2 x_i.x_j, 0)          (dust/inference/svgd.py:28-39, 92-99, 127-135)
 //
-// One CTA per 128-row block, 12 warps:
+// At most one CTA per SM, resident for the whole launch; it works off an equal contiguous range of
+// (128-row tile, 64-column tile) pairs, segment by segment when the range crosses row tiles.  16 warps:
 //   warp 0      producer   cp.async.bulk (1-D TMA) of pre-tiled hi/lo operand images into smem rings
 //   warp 1      MMA issuer one thread: GEMM1(j) -> S[j&1]; GEMM2(j-1): O += P[(j-1)&1] V_{j-1}
 //   warp 2      TMEM allocation
 //   warp 3      producer of the V^T tiles
-//   warps 4-7   "softmax" warpgroup A: even column tiles  (tcgen05.ld S, exp, split, tcgen05.st P)
-//   warps 8-11  "softmax" warpgroup B: odd column tiles
+//   warps 4-7   "softmax" warpgroup A: columns 0..31 of every tile  (tcgen05.ld S, exp, split, tcgen05.st P)
+//   warps 8-11  "softmax" warpgroup B: columns 32..63 of every tile
 //   warps 12-15 flush warpgroup: every kTcChunk column tiles the O accumulator is drained into
 //               round-to-nearest fp32 registers (the tensor core's own fp32 accumulation truncates:
 //               measured bias ~2e-8 per accumulation step, i.e. 5e-4 over the 24576 steps of
-//               N = 65536 if left in TMEM), then the final phi row is formed.
+//               N = 65536 if left in TMEM) and added to the segment's slot of a global scratch;
+//               phi_tc_finish_kernel sums the slots of a row tile and forms the phi rows.
 // TMEM columns (512 allocated): S/P_hi[2] 0..127 (P_hi overwrites the S it was computed from),
 // P_lo[2] 128..255, O[2] 256..256+2*NV.
 // Operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8x16B core
