@@ -19,10 +19,17 @@ class SvmpcCore:
     def __init__(self, spec, theta, mu, mix, prior_var, sigma, alpha=1.0, temperature=1.0, lr=1.0,
                  kernel="gpytorch", lengthscale=GPYTORCH_DEFAULT_LENGTHSCALE, bw_scale=1.0,
                  likelihood=L.LIK_EXP_UTILITY, grad="analytic", roll_strategy="repeat", weighted_prior=False,
-                 aliased=False, seed=0, sharded=None):
+                 aliased=False, seed=0, sharded=None, optimizer=None, ops_module=None):
         """theta, mu [B,N,H,A]; mix [B,N]; prior_var [A] (diagonal, shared by all components);
         sigma [A].  sharded: a `distributed.ShardedRollout` -- ONE instance (B = 1) whose parameter draws are
-        split over the ranks of its group (every rank holds the same particles and noise)."""
+        split over the ranks of its group (every rank holds the same particles and noise).
+        optimizer: None = plain SGD, fused into the phi kernel (and into the one-launch step); otherwise a
+        callable `params -> torch.optim.Optimizer` (svgd.py:115-124: Adam by default in the reference): phi comes
+        from the kernel and the optimiser applies `grad = -phi` to the particles in place (svmpc.py:92-94).
+        Its state is keyed by the particle tensor, which `forward_step` replaces -- so, as in the reference
+        (svmpc.py:144,158), moment estimates start afresh after every roll.
+        ops_module: stand-in for `dust_b200.ops` (host-logic tests run this class on CPU with oracle-backed ops)."""
+        self._ops_module = ops_module      # None: the library (kept out of __dict__ as a module so deepcopy works)
         self.spec = spec
         self.theta, self.mu, self.mix = theta.contiguous(), mu.contiguous(), mix.contiguous()
         self.B, self.N, self.H, self.A = theta.shape
@@ -46,7 +53,12 @@ class SvmpcCore:
         self.weighted_prior = bool(weighted_prior)
         self.aliased = bool(aliased)
         self.sharded = sharded
+        self._make_opt, self._opt = optimizer, None
         self.last = {}
+
+    @property
+    def ops(self):
+        return ops if self._ops_module is None else self._ops_module
 
     def set_prior_var(self, prior_var):
         dev = self.theta.device
@@ -56,7 +68,7 @@ class SvmpcCore:
         self.prior_var = pv.clone()
         full = pv.repeat(self.H)
         self.inv_var = (1.0 / full).to(dev).contiguous()
-        self.log_norm = ops.gmm_log_norm(full)
+        self.log_norm = self.ops.gmm_log_norm(full)
 
     def _flat(self, t):
         return t.reshape(self.B, self.N, self.D)
@@ -65,7 +77,7 @@ class SvmpcCore:
         """One SVGD step on the policy particles.  state0 [B,ds], eps [B,S,N,H,A] standard normal,
         params [B,P,dp] | None.  Updates theta in place of the old tensor (new storage)."""
         mu = self.theta if self.aliased else self.mu
-        _, grad_pri = ops.gmm(self._flat(self.theta), self._flat(mu), self.mix, self.inv_var, self.log_norm,
+        _, grad_pri = self.ops.gmm(self._flat(self.theta), self._flat(mu), self.mix, self.inv_var, self.log_norm,
                               want_log_prob=False)
         want = ["costs", "log_lik"]
         want.append("grad_lik" if self.grad == "analytic" else "lik_weights")
@@ -76,7 +88,7 @@ class SvmpcCore:
                                         self.alpha, self.temperature, grad=self.grad)
             grad_lik = out["grad_lik"]
         else:
-            out = ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
+            out = self.ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
                                    param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
                                    temperature=self.temperature, want=tuple(want))
         if self.sharded is not None and params is not None:
@@ -84,18 +96,27 @@ class SvmpcCore:
         elif self.grad == "analytic":
             grad_lik = out["grad_lik"]
         else:
-            grad_lik = ops.rollout_adjoint(self.spec, state0, eps, out["lik_weights"], theta=self.theta,
+            grad_lik = self.ops.rollout_adjoint(self.spec, state0, eps, out["lik_weights"], theta=self.theta,
                                            sigma=self.sigma, params=params, param_tiling=tiling,
                                            likelihood=self.likelihood, alpha=self.alpha)
         score = grad_lik.reshape(self.B, self.N, self.D) + grad_pri
         x = self._flat(self.theta)
+        fused_sgd = self._make_opt is None
         if self.kernel == "gpytorch":
             ell2 = self.lengthscale ** 2
-            res = ops.svgd_phi(x, score, gamma=1.0 / (2.0 * ell2), c1=1.0 / self.N, c2=-1.0 / ell2, lr=self.lr,
-                               want_update=True)
+            res = self.ops.svgd_phi(x, score, gamma=1.0 / (2.0 * ell2), c1=1.0 / self.N, c2=-1.0 / ell2, lr=self.lr,
+                                    want_update=fused_sgd)
         else:
-            res = ops.svgd_phi(x, score, per_dim=True, bw_scale=self.bw_scale, lr=self.lr, want_update=True)
-        self.theta = res["x_out"].reshape(self.B, self.N, self.H, self.A)
+            res = self.ops.svgd_phi(x, score, per_dim=True, bw_scale=self.bw_scale, lr=self.lr, want_update=fused_sgd)
+        if fused_sgd:
+            self.theta = res["x_out"].reshape(self.B, self.N, self.H, self.A)
+        else:
+            if self._opt is None or self._opt.param_groups[0]["params"][0] is not self.theta:
+                self._opt = self._make_opt([self.theta])      # new particle tensor (first step, or after a roll)
+            self._opt.zero_grad()
+            self.theta.grad = -res["phi"].reshape(self.B, self.N, self.H, self.A)
+            self._opt.step()
+            self.theta.grad = None
         self.last = dict(costs=out["costs"], log_lik=out["log_lik"], grad_lik=grad_lik, grad_pri=grad_pri,
                          phi=res["phi"].reshape(self.B, self.N, self.H, self.A), states=out.get("states"),
                          lik_weights=out.get("lik_weights"))
@@ -106,11 +127,11 @@ class SvmpcCore:
         instance kernel (B >= 74, H*A <= 32, analytic gradient, fixed-lengthscale kernel), else the
         staged sequence.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])"""
         if (self.kernel == "gpytorch" and self.grad == "analytic" and self.roll_strategy != L.ROLL_RESAMPLE
-                and getattr(self, "_fused_ok", True)):
+                and self._make_opt is None and getattr(self, "_fused_ok", True)):
             ell2 = self.lengthscale ** 2
             want = ("costs", "log_lik", "theta_out") + (("phi",) if want_phi else ())
             try:
-                out = ops.svmpc_step(self.spec, state0, eps, self.theta, self.sigma, self.mu, self.mix, self.inv_var,
+                out = self.ops.svmpc_step(self.spec, state0, eps, self.theta, self.sigma, self.mu, self.mix, self.inv_var,
                                      self.log_norm, 1.0 / (2.0 * ell2), 1.0 / self.N, -1.0 / ell2, self.lr, params=params,
                                      param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
                                      temperature=self.temperature, aliased=self.aliased, do_forward=True,
@@ -130,7 +151,7 @@ class SvmpcCore:
         """[B,N,A+1] standard normals for roll strategy 'resample' (stream 2^62 + draw index: disjoint
         from the action-noise streams of the batched controller)."""
         buf = torch.empty(self.B, self.N, self.A + 1, device=self.theta.device)
-        ops.noise_normal(buf, self.seed, (1 << 62) + self.resample_draws)
+        self.ops.noise_normal(buf, self.seed, (1 << 62) + self.resample_draws)
         self.resample_draws += 1
         return buf
 
@@ -139,7 +160,7 @@ class SvmpcCore:
         log_lik = self.last["log_lik"] if log_lik is None else log_lik
         mu = self.theta if self.aliased else self.mu
         noise = None if self.roll_strategy != L.ROLL_RESAMPLE else self.draw_resample_noise()
-        out = ops.svmpc_forward(log_lik, self.theta, mu, self.mix, self.inv_var, self.log_norm,
+        out = self.ops.svmpc_forward(log_lik, self.theta, mu, self.mix, self.inv_var, self.log_norm,
                                 roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior,
                                 resample_noise=noise)
         self.theta = out["theta_next"]

@@ -48,16 +48,18 @@ class SVMPC(SVGD):
         if getattr(ctrl, "a_reg", 0) != 0 or getattr(ctrl, "_tf", None) is not None:
             raise NotImplementedError("SVMPC drives the rollout kernel directly: a controller with ctrl_penalty != 1 or "
                                       "sigma-point parameter tiling is only supported stand-alone (MultiDISCO.forward)")
-        if self.optimizer_class is not torch.optim.SGD or any(
-                k in self.opt_args and self.opt_args[k] for k in ("momentum", "weight_decay", "nesterov", "dampening")):
-            raise NotImplementedError("SVMPC: only plain SGD is fused into the update kernel "
-                                      "(the reference's demos use torch.optim.SGD)")
+        plain_sgd = self.optimizer_class is torch.optim.SGD and not any(
+            k in self.opt_args and self.opt_args[k] for k in ("momentum", "weight_decay", "nesterov", "dampening"))
+        # plain SGD (the demos) is fused into the update kernels; any other torch optimiser (svgd.py:115: Adam by
+        # default) takes phi from the kernel and steps the particles in place on the device (svmpc.py:92-94)
+        import functools
+        opt = None if plain_sgd else functools.partial(self.optimizer_class, **self.opt_args)
         self._core = SvmpcCore(
             spec=ctrl._spec(likelihood.model), theta=theta.unsqueeze(0), mu=mu.unsqueeze(0), mix=mix.unsqueeze(0),
             prior_var=cov.diag(), sigma=ctrl._sigma, alpha=likelihood.alpha, temperature=ctrl.temp,
             lr=self.opt_args.get("lr", 1e-3), kernel=mode, lengthscale=ell if mode == "gpytorch" else 1.0,
             bw_scale=scale, likelihood=likelihood.kind, grad=grad, roll_strategy=roll_strategy,
-            weighted_prior=weighted_prior)
+            weighted_prior=weighted_prior, optimizer=opt)
         self._prior_obj = prior
         self._prior_stale = False
         self.last_phi = None

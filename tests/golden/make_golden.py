@@ -131,7 +131,7 @@ def pend_term_cost(states, n_pol=1, debug=None):
 
 
 def make_pendulum(seed, kernel="rbf", params_sampling=True, n_pol=None, S=None, H=None, P=None,
-                  log_space=False):
+                  log_space=False, optimizer_class=torch.optim.SGD, lr=None, svgd_steps=1, **opt_args):
     ep = PEND["exp_params"]
     torch.manual_seed(seed)
     H = H or ep["horizon"]
@@ -173,10 +173,11 @@ def make_pendulum(seed, kernel="rbf", params_sampling=True, n_pol=None, S=None, 
         kernel=k,
         n_particles=N,
         bw_scale=ep["bandwidth_scaling"],
-        n_steps=1,
-        optimizer_class=torch.optim.SGD,
-        lr=ep["learning_rate"],
+        n_steps=svgd_steps,
+        optimizer_class=optimizer_class,
+        lr=ep["learning_rate"] if lr is None else lr,
         weighted_prior=ep["weighted_prior"],
+        **opt_args,
     )
     state = torch.as_tensor(ep["init_state"]).clone()
     return dict(model=model, ctrl=ctrl, svmpc=sv, dyn=dyn, state=state, prior=prior, cfg=ep)
@@ -687,8 +688,43 @@ def gen_widen():
              sigma=c.a_dist.covariance_matrix.diag().sqrt(), action_avg=deepcopy(c).step(strategy="average").clone())
 
 
+# ----------------------------------------------------------------------------------
+# G10: SVMPC with a non-SGD optimiser (svgd.py:115: Adam is the SVGD default), two SVGD steps per control step
+# ----------------------------------------------------------------------------------
+def gen_optim():
+    print("G10 SVMPC with Adam / momentum SGD")
+    pp = {"length": torch.tensor([[1.1]]), "mass": torch.tensor([[0.8]])}
+    for name, kw in (("svmpc_pendulum_adam", dict(optimizer_class=torch.optim.Adam, lr=0.05)),
+                     ("svmpc_pendulum_momentum", dict(optimizer_class=torch.optim.SGD, lr=0.5, momentum=0.9))):
+        w = make_pendulum(31, kernel="rbf", n_pol=4, S=32, H=10, P=3, svgd_steps=2, **kw)
+        sv, model = w["svmpc"], w["model"]
+        state = w["state"].clone()
+        dyn = RecordingDist(w["dyn"])
+        out = dict(sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(), theta_init=sv.theta.detach().clone(),
+                   mu_init=prior_mu(sv.prior), prior_var=np.array(PEND["exp_params"]["prior_sigma"] ** 2), lr=np.array(kw["lr"]))
+        n_ctrl = 3
+        for t in range(n_ctrl):
+            dyn.samples.clear()
+            with NoiseRecorder() as rec:
+                sv.optimize(state, dyn)
+            eps = [d for d in rec.draws if d.ndim == 4]
+            assert len(eps) == 2 and len(dyn.samples) == 2
+            out[f"t{t}_state"] = state.clone()
+            out[f"t{t}_eps"] = torch.stack(eps)
+            out[f"t{t}_params"] = torch.stack([p.clone() for p in dyn.samples])
+            out[f"t{t}_theta1"] = sv.theta.detach().clone()
+            out[f"t{t}_costs"] = sv.likelihood.last_costs.detach().clone()
+            a_seq, p_w = sv.forward(state, dyn)
+            out[f"t{t}_a_seq"], out[f"t{t}_p_weights"] = a_seq.clone(), p_w.clone()
+            out[f"t{t}_i_star"] = np.array(int(p_w.argmax()))
+            out[f"t{t}_theta2"] = sv.theta.detach().clone()
+            state = model.step(state.view(1, -1), a_seq[0].view(1, -1), pp).view(-1)
+        out["n_ctrl"] = np.array(n_ctrl)
+        save(name, tags=["shim-dependent:gpytorch", "shim-dependent:KDEpy(dead value)"], **out)
+
+
 GENERATORS = dict(map=gen_map, forward=gen_forward_all, svmpc=gen_svmpc, dual=gen_dual, mpf=gen_mpf, phi=gen_phi,
-                  pathwise=gen_pathwise, episode=gen_episode, widen=gen_widen)
+                  pathwise=gen_pathwise, episode=gen_episode, widen=gen_widen, optim=gen_optim)
 
 if __name__ == "__main__":
     # no arguments: everything; otherwise only the named groups, merged into the existing manifest

@@ -1,0 +1,109 @@
+"""Host logic of the non-SGD optimiser path of SVMPC (svgd.py:115: Adam is the reference's default; plain SGD is
+what the demos use and what the update kernels fuse).  `SvmpcCore` is run HERE ON CPU with oracle-backed stand-ins
+for the library's ops, against recordings of the unmodified reference stepping Adam / momentum SGD: this pins the
+optimiser plumbing -- `grad = -phi`, in-place steps, two SVGD steps per control step, and the reference's quirk
+that the optimiser state is keyed by the particle tensor and therefore starts afresh after every roll
+(svmpc.py:144,158).  The device kernels behind the real ops have their own parity tests (`-m gpu`)."""
+import functools
+
+import pytest
+import torch
+
+from oracle import dust_oracle as O
+from tests.util import load, rel_max
+
+torch.set_num_threads(1)
+MODEL = O.Model("pendulum")
+
+
+class OracleOps:
+    """CPU stand-ins with the signatures `SvmpcCore` uses (B = 1), computed in float64 by the oracle."""
+
+    @staticmethod
+    def gmm_log_norm(var_full):
+        from dust_b200 import ops
+
+        return ops.gmm_log_norm(var_full)
+
+    @staticmethod
+    def gmm(x, mu, mix, inv_var, log_norm, want_log_prob=True, want_score=True):
+        var = 1.0 / inv_var.double()
+        return None, O.gmm_score(x[0].double(), mu[0].double(), mix[0].double(), var).float().unsqueeze(0)
+
+    @staticmethod
+    def rollout_cost(spec, state0, eps, theta=None, sigma=None, params=None, alpha=1.0, want=(), **kw):
+        actions = theta[0].double() + sigma.double() * eps[0].double()
+        out = O.disco_forward(MODEL, state0[0].double(), actions, None if params is None else params[0].double())
+        costs = out["costs"]
+        res = {"costs": costs.float().unsqueeze(0), "log_lik": O.exp_utility_log_prob(costs, alpha).float().unsqueeze(0)}
+        res["grad_lik"] = O.analytic_lik_grad(costs, actions, theta[0].double(), sigma.double(), alpha).float().unsqueeze(0)
+        return res
+
+    @staticmethod
+    def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, lr=0.0, want_update=False, **kw):
+        phi = O.phi_unified(x[0].double(), score[0].double(), gamma, c1, c2).float().unsqueeze(0)
+        return {"phi": phi, "x_out": (x + lr * phi) if want_update else None}
+
+    @staticmethod
+    def svmpc_step(*a, **k):
+        raise NotImplementedError("no one-launch step in the stand-in")
+
+    @staticmethod
+    def svmpc_forward(log_lik, theta, mu, mix, inv_var, log_norm, roll_strategy=0, weighted_prior=False, resample_noise=None):
+        N = theta.shape[1]
+        flat = lambda t: t[0].reshape(N, -1).double()  # noqa: E731
+        log_w = log_lik[0].double() + O.gmm_log_prob(flat(theta), flat(mu), mix[0].double(), 1.0 / inv_var.double())
+        p = (log_w - log_w.logsumexp(0)).exp()
+        i_star = int(p.argmax())
+        th = theta[0].roll(-1, dims=-2).clone()
+        th[..., -1, :] = th[..., -2, :]
+        mix_next = p.float() if weighted_prior else torch.ones(N)
+        return dict(a_seq=theta[0, i_star].clone().unsqueeze(0), p_weights=p.float().unsqueeze(0),
+                    i_star=torch.tensor([i_star]), theta_next=th.unsqueeze(0), mix_next=mix_next.unsqueeze(0))
+
+
+@pytest.mark.parametrize("name,opt", [("svmpc_pendulum_adam", functools.partial(torch.optim.Adam)),
+                                      ("svmpc_pendulum_momentum", functools.partial(torch.optim.SGD, momentum=0.9))])
+def test_svmpc_core_with_torch_optimizers_follows_the_reference(name, opt):
+    from dust_b200.inference.core import SvmpcCore
+
+    d = load(name)
+    N = d["theta_init"].shape[0]
+    core = SvmpcCore(None, d["theta_init"].clone().unsqueeze(0), d["mu_init"].clone().unsqueeze(0), torch.ones(1, N),
+                     torch.tensor([float(d["prior_var"])]), d["sigma"], alpha=1.0, lr=float(d["lr"]), kernel="gpytorch",
+                     optimizer=functools.partial(opt, lr=float(d["lr"])), ops_module=OracleOps)
+    for t in range(int(d["n_ctrl"])):
+        state0 = d[f"t{t}_state"].reshape(1, -1)
+        first_opt = None
+        for k in range(2):                      # n_steps = 2: two SVGD steps per control step, own draws each
+            core.optimize_step(state0, d[f"t{t}_eps"][k].unsqueeze(0), d[f"t{t}_params"][k].unsqueeze(0))
+            first_opt = first_opt or core._opt
+            assert core._opt is first_opt        # one optimiser (and one state) within a control step ...
+        assert rel_max(core.last["costs"][0], d[f"t{t}_costs"]) <= 1e-5
+        assert rel_max(core.theta[0], d[f"t{t}_theta1"]) <= 2e-4
+        a_seq, p_w, i_star = core.forward_step()
+        assert int(i_star[0]) == int(d[f"t{t}_i_star"])
+        assert rel_max(a_seq[0], d[f"t{t}_a_seq"]) <= 2e-4
+        assert float((p_w[0] - d[f"t{t}_p_weights"]).abs().max()) <= 1e-3
+        assert rel_max(core.theta[0], d[f"t{t}_theta2"]) <= 2e-4
+    # ... and a new one after the roll replaced the particle tensor
+    core.optimize_step(state0, d["t0_eps"][0].unsqueeze(0), d["t0_params"][0].unsqueeze(0))
+    assert core._opt is not first_opt
+
+
+def test_plain_sgd_keeps_the_fused_update():
+    """optimizer=None: the update comes out of the phi kernel (x_out); the staged fallback of control_step is
+    taken when the one-launch step declines."""
+    from dust_b200.inference.core import SvmpcCore
+
+    d = load("svmpc_pendulum_adam")
+    N = d["theta_init"].shape[0]
+    core = SvmpcCore(None, d["theta_init"].clone().unsqueeze(0), d["mu_init"].clone().unsqueeze(0), torch.ones(1, N),
+                     torch.tensor([float(d["prior_var"])]), d["sigma"], alpha=1.0, lr=0.5, kernel="gpytorch", ops_module=OracleOps)
+    theta0 = core.theta.clone()
+    a_seq, p_w, i_star = core.control_step(d["t0_state"].reshape(1, -1), d["t0_eps"][0].unsqueeze(0), d["t0_params"][0].unsqueeze(0))
+    assert core._opt is None and core._fused_ok is False
+    assert a_seq.shape == (1, theta0.shape[2], theta0.shape[3]) and not torch.equal(core.theta, theta0)
+    import copy
+
+    assert copy.deepcopy(core).theta.shape == core.theta.shape      # the ops stand-in / module never blocks deepcopy
