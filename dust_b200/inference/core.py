@@ -147,6 +147,15 @@ class SvmpcCore:
         self.optimize_step(state0, eps, params, tiling)
         return self.forward_step()
 
+    def likelihood_at_particles(self, state0, eps, params=None, tiling=L.PARAMS_BLOCKED):
+        """Fresh rollouts at the CURRENT (updated) particles: what `SVMPC.get_weights(fast_pred=False)` does before
+        weighing them (svmpc.py:135-137).  -> log_lik [B,N]; the new costs replace the stored ones."""
+        out = self.ops.rollout_cost(self.spec, state0, eps, theta=self.theta, sigma=self.sigma, params=params,
+                                    param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
+                                    temperature=self.temperature, want=("costs", "log_lik"))
+        self.last = dict(self.last, costs=out["costs"], log_lik=out["log_lik"])
+        return out["log_lik"]
+
     def draw_resample_noise(self):
         """[B,N,A+1] standard normals for roll strategy 'resample' (stream 2^62 + draw index: disjoint
         from the action-noise streams of the batched controller)."""

@@ -115,23 +115,34 @@ class SVMPC(SVGD):
         for _ in range(n_steps):
             self.step(state, params_dist, bw, None, eps=eps)
 
-    def get_weights(self, state, params_dist, fast_pred=True):
-        if not fast_pred:
-            raise NotImplementedError("get_weights(fast_pred=False) re-samples the likelihood; call optimize first")
-        return self._peek_weights()
+    def _resample_likelihood(self, state, params_dist, eps=None):
+        """svmpc.py:135-136: new action noise and parameter draws, rollouts at the updated particles."""
+        lik, c = self.likelihood, self._core
+        state0, eps, params, tiling, params_log_p = self._evaluate(state, params_dist, eps)
+        log_lik = c.likelihood_at_particles(state0, eps, params, tiling)
+        lik._last = {"log_lik": log_lik[0]}
+        lik.last_costs = c.last["costs"][0]
+        lik.last_states, lik.last_actions = None, None
+        lik.params_log_p = params_log_p
+        return log_lik
 
-    def _peek_weights(self):
+    def get_weights(self, state, params_dist, fast_pred=True, eps=None):
+        """svmpc.py:128-140.  fast_pred re-uses the costs of the optimise step; otherwise the likelihood is
+        sampled again at the updated particles (`eps`: optional recorded noise, as in `optimize`)."""
+        log_lik = None if fast_pred else self._resample_likelihood(state, params_dist, eps)
+        return self._peek_weights(log_lik)
+
+    def _peek_weights(self, log_lik=None):
         import copy
         c = copy.copy(self._core)
-        return c.forward_step()[1][0]
+        return c.forward_step(log_lik)[1][0]
 
-    def forward(self, state, params_dist, steps=-1, fast_pred=True):
+    def forward(self, state, params_dist, steps=-1, fast_pred=True, eps=None):
         """svmpc.py:172-200 -> (a_seq [H,A], p_weights [N])."""
         if steps != -1:
             raise NotImplementedError("SVMPC.forward: only steps=-1 (shift by one) is supported")
-        if not fast_pred:
-            raise NotImplementedError("SVMPC.forward(fast_pred=False) is not available")
-        a_seq, p_w, i_star = self._core.forward_step()
+        log_lik = None if fast_pred else self._resample_likelihood(state, params_dist, eps)
+        a_seq, p_w, i_star = self._core.forward_step(log_lik)
         self._prior_stale = True
         self.i_star = i_star[0]
         return a_seq[0], p_w[0]

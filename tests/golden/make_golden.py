@@ -721,6 +721,30 @@ def gen_optim():
             state = model.step(state.view(1, -1), a_seq[0].view(1, -1), pp).view(-1)
         out["n_ctrl"] = np.array(n_ctrl)
         save(name, tags=["shim-dependent:gpytorch", "shim-dependent:KDEpy(dead value)"], **out)
+    # forward(fast_pred=False): the likelihood is sampled again at the updated particles (svmpc.py:135-136)
+    w = make_pendulum(33, kernel="rbf", n_pol=4, S=32, H=10, P=3)
+    sv, model = w["svmpc"], w["model"]
+    state = w["state"].clone()
+    dyn = RecordingDist(w["dyn"])
+    out = dict(sigma=w["ctrl"].a_dist.covariance_matrix.diag().sqrt(), theta_init=sv.theta.detach().clone(),
+               mu_init=prior_mu(sv.prior), prior_var=np.array(PEND["exp_params"]["prior_sigma"] ** 2),
+               lr=np.array(PEND["exp_params"]["learning_rate"]))
+    for t in range(2):
+        dyn.samples.clear()
+        with NoiseRecorder() as rec:
+            sv.optimize(state, dyn)
+            peek = sv.get_weights(state, dyn, fast_pred=False)
+            a_seq, p_w = sv.forward(state, dyn, fast_pred=False)
+        eps = [d for d in rec.draws if d.ndim == 4]
+        assert len(eps) == 3 and len(dyn.samples) == 3      # optimise, get_weights, forward
+        out[f"t{t}_state"], out[f"t{t}_eps"] = state.clone(), torch.stack(eps)
+        out[f"t{t}_params"] = torch.stack([p.clone() for p in dyn.samples])
+        out[f"t{t}_peek"], out[f"t{t}_a_seq"], out[f"t{t}_p_weights"] = peek.clone(), a_seq.clone(), p_w.clone()
+        out[f"t{t}_costs_fwd"] = sv.likelihood.last_costs.detach().clone()
+        out[f"t{t}_theta2"] = sv.theta.detach().clone()
+        state = model.step(state.view(1, -1), a_seq[0].view(1, -1), pp).view(-1)
+    out["n_ctrl"] = np.array(2)
+    save("svmpc_pendulum_slow_pred", tags=["shim-dependent:gpytorch", "shim-dependent:KDEpy(dead value)"], **out)
 
 
 GENERATORS = dict(map=gen_map, forward=gen_forward_all, svmpc=gen_svmpc, dual=gen_dual, mpf=gen_mpf, phi=gen_phi,

@@ -107,3 +107,31 @@ def test_plain_sgd_keeps_the_fused_update():
     import copy
 
     assert copy.deepcopy(core).theta.shape == core.theta.shape      # the ops stand-in / module never blocks deepcopy
+
+
+def test_weights_from_a_fresh_likelihood_sample():
+    """`get_weights(fast_pred=False)` / `forward(fast_pred=False)` (svmpc.py:128-140, 172-200): new noise and
+    parameter draws, rollouts at the UPDATED particles, weights from those costs -- against the reference's run
+    (optimise, peek at the weights, forward; three draws per control step)."""
+    import copy
+
+    from dust_b200.inference.core import SvmpcCore
+
+    d = load("svmpc_pendulum_slow_pred")
+    N = d["theta_init"].shape[0]
+    core = SvmpcCore(None, d["theta_init"].clone().unsqueeze(0), d["mu_init"].clone().unsqueeze(0), torch.ones(1, N),
+                     torch.tensor([float(d["prior_var"])]), d["sigma"], alpha=1.0, lr=float(d["lr"]), kernel="gpytorch",
+                     ops_module=OracleOps)
+    for t in range(int(d["n_ctrl"])):
+        state0 = d[f"t{t}_state"].reshape(1, -1)
+        eps, params = d[f"t{t}_eps"], d[f"t{t}_params"]
+        core.optimize_step(state0, eps[0].unsqueeze(0), params[0].unsqueeze(0))
+        peek = copy.copy(core)                                                   # SVMPC._peek_weights
+        pw_peek = peek.forward_step(peek.likelihood_at_particles(state0, eps[1].unsqueeze(0), params[1].unsqueeze(0)))[1][0]
+        assert float((pw_peek - d[f"t{t}_peek"]).abs().max()) <= 2e-3
+        log_lik = core.likelihood_at_particles(state0, eps[2].unsqueeze(0), params[2].unsqueeze(0))
+        assert rel_max(core.last["costs"][0], d[f"t{t}_costs_fwd"]) <= 1e-4
+        a_seq, p_w, _ = core.forward_step(log_lik)
+        assert float((p_w[0] - d[f"t{t}_p_weights"]).abs().max()) <= 2e-3
+        assert rel_max(a_seq[0], d[f"t{t}_a_seq"]) <= 5e-4
+        assert rel_max(core.theta[0], d[f"t{t}_theta2"]) <= 5e-4
