@@ -1,4 +1,4 @@
-"""Host logic of the non-SGD optimiser path of SVMPC (svgd.py:115: Adam is the reference's default; plain SGD is
+"""Host logic of the reference-shaped classes on CPU, first of all the non-SGD optimiser path of SVMPC (svgd.py:115: Adam is the reference's default; plain SGD is
 what the demos use and what the update kernels fuse).  `SvmpcCore` is run HERE ON CPU with oracle-backed stand-ins
 for the library's ops, against recordings of the unmodified reference stepping Adam / momentum SGD: this pins the
 optimiser plumbing -- `grad = -phi`, in-place steps, two SVGD steps per control step, and the reference's quirk
@@ -40,8 +40,11 @@ class OracleOps:
         return res
 
     @staticmethod
-    def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, lr=0.0, want_update=False, **kw):
-        phi = O.phi_unified(x[0].double(), score[0].double(), gamma, c1, c2).float().unsqueeze(0)
+    def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, lr=0.0, want_update=False, per_dim=False, **kw):
+        if per_dim:      # the message-passing kernel (composite_kernels.py:33-64, svmpc.py:64-74)
+            phi = O.phi_svmpc_iid_mp(x[0].double(), score[0].double()).float().unsqueeze(0)
+        else:
+            phi = O.phi_unified(x[0].double(), score[0].double(), gamma, c1, c2).float().unsqueeze(0)
         return {"phi": phi, "x_out": (x + lr * phi) if want_update else None}
 
     @staticmethod
@@ -135,3 +138,120 @@ def test_weights_from_a_fresh_likelihood_sample():
         assert float((p_w[0] - d[f"t{t}_p_weights"]).abs().max()) <= 2e-3
         assert rel_max(a_seq[0], d[f"t{t}_a_seq"]) <= 5e-4
         assert rel_max(core.theta[0], d[f"t{t}_theta2"]) <= 5e-4
+
+
+# ---- the drop-in SVMPC class itself, on CPU: device="cpu" objects + the oracle-backed ops ---------------------
+class _FixedParams:
+    """params_dist stand-in returning a recorded draw (disco.py:168-174 contract)."""
+
+    def __init__(self, samples):
+        self.samples, self.event_shape = samples, torch.Size([samples.shape[-1]])
+
+    def sample(self, shape):
+        return self.samples
+
+    def log_prob(self, x):
+        return torch.zeros(x.shape[0])
+
+
+def _swingup_cost(states, controls=None, n_pol=1, debug=None):
+    theta, theta_d = states.chunk(2, dim=1)
+    return 50.0 * (theta.cos() - 1) ** 2 + 1.0 * theta_d ** 2
+
+
+def _build_svmpc(d, **svmpc_kwargs):
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.inference.likelihoods import ExponentiatedUtility
+    from dust_b200.inference.svgd import get_gmm
+    from dust_b200.inference.svmpc import SVMPC
+    from dust_b200.kernels.base_kernels import RBFKernel
+    from dust_b200.models.pendulum import PendulumModel
+
+    N, H, A = d["theta_init"].shape
+    S = d["t0_eps"].shape[1]
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    ctrl = MultiDISCO(observation_space=model.observation_space, action_space=model.action_space, hz_len=H, n_policies=N,
+                      action_samples=S, params_samples=3, temperature=1.0, a_cov=4.0 * torch.eye(A), inst_cost_fn=_swingup_cost,
+                      term_cost_fn=lambda s, **k: _swingup_cost(s).squeeze(), params_sampling=True, device="cpu")
+    lik = ExponentiatedUtility(1.0, n_samples=S, controller=ctrl, model=model)
+    sv = SVMPC(init_particles=d["theta_init"].clone(), prior=get_gmm(d["mu_init"], torch.ones(N), 4.0 * torch.eye(A)),
+               likelihood=lik, kernel=RBFKernel(), n_particles=N, bw_scale=1.0, lr=float(d["lr"]), **svmpc_kwargs)
+    sv._core._ops_module = OracleOps
+    return sv
+
+
+@pytest.mark.parametrize("name,kw", [("svmpc_pendulum_adam", dict(optimizer_class=torch.optim.Adam)),
+                                     ("svmpc_pendulum_momentum", dict(optimizer_class=torch.optim.SGD, momentum=0.9))])
+def test_svmpc_class_with_torch_optimizers(name, kw):
+    """`SVMPC(optimizer_class=...)` as a user of the reference writes it, stepped through `step` / `forward`."""
+    d = load(name)
+    sv = _build_svmpc(d, n_steps=2, **kw)
+    assert sv._core._make_opt is not None
+    for t in range(int(d["n_ctrl"])):
+        st = d[f"t{t}_state"]
+        for k in range(2):
+            sv.step(st, _FixedParams(d[f"t{t}_params"][k]), eps=d[f"t{t}_eps"][k])
+        assert rel_max(sv.theta, d[f"t{t}_theta1"]) <= 2e-4
+        a_seq, pw = sv.forward(st, None)
+        assert int(sv.i_star) == int(d[f"t{t}_i_star"])
+        assert rel_max(a_seq, d[f"t{t}_a_seq"]) <= 2e-4 and rel_max(sv.theta, d[f"t{t}_theta2"]) <= 2e-4
+        assert torch.equal(sv.prior.component_distribution.base_dist.loc, sv.theta)      # prior refreshed on the rolled particles
+
+
+def test_svmpc_class_slow_prediction_and_plain_sgd():
+    import copy
+
+    d = load("svmpc_pendulum_slow_pred")
+    sv = _build_svmpc(d, n_steps=1, optimizer_class=torch.optim.SGD)
+    assert sv._core._make_opt is None                                   # plain SGD: the fused update
+    for t in range(int(d["n_ctrl"])):
+        st, eps, prm = d[f"t{t}_state"], d[f"t{t}_eps"], d[f"t{t}_params"]
+        sv.optimize(st, _FixedParams(prm[0]), eps=eps[0])
+        theta1 = sv.theta.clone()
+        pk = sv.get_weights(st, _FixedParams(prm[1]), fast_pred=False, eps=eps[1])
+        assert torch.equal(sv.theta, theta1), "peeking at the weights must not roll the particles"
+        assert float((pk - d[f"t{t}_peek"]).abs().max()) <= 2e-3
+        a_seq, pw = sv.forward(st, _FixedParams(prm[2]), fast_pred=False, eps=eps[2])
+        assert rel_max(sv.likelihood.last_costs, d[f"t{t}_costs_fwd"]) <= 1e-4
+        assert float((pw - d[f"t{t}_p_weights"]).abs().max()) <= 2e-3
+        assert rel_max(a_seq, d[f"t{t}_a_seq"]) <= 5e-4 and rel_max(sv.theta, d[f"t{t}_theta2"]) <= 5e-4
+    assert copy.deepcopy(sv).theta.shape == sv.theta.shape             # the demos deep-copy the optimiser per episode
+    with pytest.raises(NotImplementedError):
+        sv.forward(d["t0_state"], None, steps=-2)
+
+
+@pytest.mark.parametrize("name,kernel", [("svmpc_pendulum_rbf", "rbf"), ("svmpc_pendulum_mp", "mp")])
+def test_svmpc_class_closed_loop_on_cpu(name, kernel):
+    """The CPU twin of the GPU closed-loop test: the reference-shaped classes (MultiDISCO, ExponentiatedUtility,
+    SVMPC) driven as the demos drive them, with the oracle standing in for the device ops -- so a break in the
+    host layer shows up in the CPU suite, not only on a B200."""
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.inference.likelihoods import ExponentiatedUtility
+    from dust_b200.inference.svgd import get_gmm
+    from dust_b200.inference.svmpc import SVMPC
+    from dust_b200.kernels.base_kernels import RBF, RBFKernel
+    from dust_b200.kernels.composite_kernels import iid_mp
+    from dust_b200.models.pendulum import PendulumModel
+
+    d = load(name)
+    N, H, A = d["t0_in_theta0"].shape
+    S = d["t0_in_eps"].shape[0]
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    ctrl = MultiDISCO(observation_space=model.observation_space, action_space=model.action_space, hz_len=H, n_policies=N,
+                      action_samples=S, params_samples=8, temperature=1.0, a_cov=4.0 * torch.eye(A), inst_cost_fn=_swingup_cost,
+                      term_cost_fn=lambda s, **k: _swingup_cost(s).squeeze(), params_sampling=True, device="cpu")
+    k = RBFKernel() if kernel == "rbf" else iid_mp(base_kernel=RBF(bandwidth=-1), ctrl_dim=A, indep_controls=True)
+    sv = SVMPC(init_particles=d["t0_in_theta0"].clone(), prior=get_gmm(d["t0_in_mu0"], torch.ones(N), 4.0 * torch.eye(A)),
+               likelihood=ExponentiatedUtility(1.0, n_samples=S, controller=ctrl, model=model), kernel=k, n_particles=N,
+               bw_scale=1.0, n_steps=1, optimizer_class=torch.optim.SGD, lr=2.0, weighted_prior=False)
+    sv._core._ops_module = OracleOps
+    for t in range(int(d["n_steps"])):
+        gi, go = (lambda key: d[f"t{t}_in_{key}"]), (lambda key: d[f"t{t}_out_{key}"])
+        sv.optimize(gi("state"), _FixedParams(gi("params")), eps=gi("eps"))
+        assert rel_max(sv.likelihood.last_costs, go("costs")) <= 2e-4
+        theta1 = sv.theta.clone()
+        a_seq, pw = sv.forward(gi("state"), None)
+        assert int(sv.i_star) == int(go("i_star"))
+        assert rel_max(theta1, go("theta1")) <= (5e-3 if kernel == "rbf" else 2e-4)
+        assert rel_max(a_seq, go("a_seq")) <= (5e-3 if kernel == "rbf" else 2e-4)
+        assert float((pw - go("p_weights")).abs().max()) <= 1e-3
