@@ -255,3 +255,85 @@ def test_svmpc_class_closed_loop_on_cpu(name, kernel):
         assert rel_max(theta1, go("theta1")) <= (5e-3 if kernel == "rbf" else 2e-4)
         assert rel_max(a_seq, go("a_seq")) <= (5e-3 if kernel == "rbf" else 2e-4)
         assert float((pw - go("p_weights")).abs().max()) <= 1e-3
+
+
+# ---- the stand-alone controller on CPU: dust_b200.controllers.disco.ops replaced by oracle-backed stand-ins ----
+class OracleControllerOps:
+    @staticmethod
+    def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param_tiling=0, a_seq=None, pert=None,
+                     temperature=1.0, want=(), sigma_weights=None, ctrl_mat=None, ctrl_reg=0.0, **kw):
+        actions = (noise[0] if theta is None else theta[0] + sigma * noise[0]).double()
+        aseq = None if a_seq is None else a_seq[0].double()
+        if sigma_weights is not None:
+            out = O.disco_forward_sigma(MODEL, state0[0].double(), actions, params[0].T.double(), sigma_weights.double(),
+                                        temperature, aseq)
+            S, N, H, A = actions.shape
+            pts = sigma_weights.numel()
+            states = out["states"].reshape(S, N, pts, H + 1, MODEL.ds).permute(2, 0, 1, 3, 4)     # the device layout [P,S,N,..]
+        else:
+            prm = None if params is None else (params[0].reshape(-1) if param_tiling == 1 else params[0]).double()
+            out = O.disco_forward(MODEL, state0[0].double(), actions, prm, False, temperature, a_seq=aseq, a_reg=ctrl_reg,
+                                  a_mat=None if ctrl_mat is None else ctrl_mat[0].double(), a_pre=torch.eye(actions.shape[-1]).double(),
+                                  eps=None if pert is None else pert[0].double())
+            states = out["states"]
+        res = dict(costs=out["costs"], mppi_weights=out["weights"], mppi_delta=out["delta"], mix=out["a_mix"], states=states)
+        return {k: v.float().unsqueeze(0) for k, v in res.items() if k in want}
+
+    @staticmethod
+    def disco_step(a_mat, a_mix, low, high, strategy=0, steps=1):
+        nxt, a_seq, new_mat = O.disco_step(a_mat[0], a_mix[0], low, high, "argmax" if strategy == 0 else "average", steps)
+        a_mat[0] = new_mat
+        return nxt.unsqueeze(0), a_seq.unsqueeze(0)
+
+
+def _controller(monkeypatch, d, S, N, H, A, **kw):
+    from dust_b200.controllers import disco as disco_module
+    from dust_b200.models.pendulum import PendulumModel
+
+    monkeypatch.setattr(disco_module, "ops", OracleControllerOps)
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    ctrl = disco_module.MultiDISCO(model.observation_space, model.action_space, H, N, S, temperature=float(d["temp"]),
+                                   a_cov=torch.diag(d["sigma"] ** 2), inst_cost_fn=_swingup_cost,
+                                   term_cost_fn=lambda s, **k: _swingup_cost(s).squeeze(), device="cpu", **kw)
+    return model, ctrl
+
+
+def test_multidisco_control_regulariser_on_cpu(monkeypatch):
+    """Host side of ctrl_penalty != 1 (disco.py:90, 334-344): a_reg, the a_mat @ a_pre the kernel is handed, the plan
+    update and `step("average")`, two rounds against the reference's recording."""
+    d = load("ctrlpen_pendulum")
+    S, N, H, A = d["actions0"].shape
+    model, ctrl = _controller(monkeypatch, d, S, N, H, A, ctrl_penalty=float(d["ctrl_penalty"]), params_sampling=True,
+                              params_samples=d["params0"].shape[0])
+    ctrl.a_mat = d["a_mat0"].clone()
+    for it in range(2):
+        costs, states, actions, weights, _ = ctrl.forward(d["state"], model, _FixedParams(d[f"params{it}"]), d[f"actions{it}"])
+        assert states.shape == (d["params0"].shape[0], S, N, H + 1, 2) and actions.shape == (d["params0"].shape[0], S, N, H, A)
+        assert rel_max(costs, d[f"costs{it}"]) <= 1e-5
+        assert rel_max(ctrl.a_mat, d[f"a_mat_fwd{it}"]) <= 1e-4 and rel_max(ctrl.a_mix, d[f"a_mix{it}"]) <= 1e-4
+        assert rel_max(ctrl.step(strategy="average"), d[f"action{it}"]) <= 1e-4
+
+
+@pytest.mark.parametrize("name", ["utf_pendulum_n1_gmm", "utf_pendulum_n3_mvn"])
+def test_multidisco_sigma_points_on_cpu(monkeypatch, name):
+    """Host side of params_sampling = MerweScaledUTF (disco.py:211-292): sigma points of the belief (both the
+    `covariance_matrix` and the `variance.diag()` branch), their weighted log-probability, the reference's state row
+    order and its un-tiled actions."""
+    import torch.distributions as dist
+
+    from dust_b200.utils.utf import MerweScaledUTF
+
+    d = load(name)
+    S, N, H, A = d["actions"].shape
+    model, ctrl = _controller(monkeypatch, d, S, N, H, A, params_sampling=MerweScaledUTF(n=2, alpha=0.5), params_log_space=False)
+    ctrl.a_mat = d["a_mat0"].clone()
+    if bool(d["belief_is_mvn"]):
+        pd = dist.MultivariateNormal(d["mean"], d["cov"])
+    else:
+        pd = dist.MixtureSameFamily(dist.Categorical(torch.ones(d["locs"].shape[0])),
+                                    dist.Independent(dist.Normal(d["locs"], float(d["comp_sigma"])), 1))
+    costs, states, actions, weights, plogp = ctrl.forward(d["state"], model, pd, d["actions"])
+    assert tuple(actions.shape) == tuple(int(v) for v in d["acts_shape"])
+    assert rel_max(states, d["states"]) <= 1e-6 and rel_max(costs, d["costs"]) <= 1e-6
+    assert rel_max(plogp, d["params_log_p"]) <= 1e-5
+    assert rel_max(ctrl.a_mat, d["a_mat1"]) <= 1e-4
