@@ -337,3 +337,43 @@ def test_multidisco_sigma_points_on_cpu(monkeypatch, name):
     assert rel_max(states, d["states"]) <= 1e-6 and rel_max(costs, d["costs"]) <= 1e-6
     assert rel_max(plogp, d["params_log_p"]) <= 1e-5
     assert rel_max(ctrl.a_mat, d["a_mat1"]) <= 1e-4
+
+
+def test_mpf_class_on_cpu(monkeypatch):
+    """Host side of the parameter filter (mpf.py:12-86): conditioning on the observed transition, the prior whose
+    centres alias the particles (H24), the bandwidth handed to the kernel -- the particle demo's filter, four
+    control steps of 20 SVGD steps, with the oracle standing in for `dust_mpf_optimize`."""
+    from dust_b200.inference import mpf as mpf_module
+    from dust_b200.inference.likelihoods import GaussianLikelihood
+    from dust_b200.models.particle import Particle
+    from tests.util import golden_grid
+
+    env = dict(dt=0.015, control_type="acceleration", noise_std=[0.1, 0.1], init_state=[-9.0, -9.0, 0, 0],
+               target_state=[9.0, 9.0, 0, 0], can_crash=True, with_obstacle=True, deterministic=True,
+               cost_params=dict(w_qpos=0.5, w_qvel=0.25, w_ctrl=0.2, w_obs=1.0e6, w_qpos_T=1.0e3, w_qvel_T=0.1),
+               obst_preset="grid_4x4", obst_width=2.1, max_speed=5, max_accel=10, map_cell_size=0.1, map_size=[22, 22],
+               map_type="direct")
+    model_o = O.Model("particle", O.ParticleCfg(golden_grid()))
+
+    class Ops:
+        @staticmethod
+        def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space, **kw):
+            x1, gn = O.mpf_optimize(model_o, x[0].double(), obs0[0].double(), action[0].double(), obs1[0].double(), obs_std,
+                                    (1.0 / prior_inv_var).double(), bw, lr, n_steps, log_space)
+            x[0] = x1.float()                       # in place, as the kernel does
+            return gn.float().unsqueeze(0)
+
+    monkeypatch.setattr(mpf_module, "ops", Ops)
+    d = load("dual_particle")
+    model = Particle(**env, uncertain_params=["mass"], mass=2.0)
+    lik = GaussianLikelihood(initial_obs=d["t0_in_state"], obs_std=float(d["obs_std"]), model=model, log_space=True)
+    mpf = mpf_module.MPF(init_particles=d["t0_in_mpf_x0"].clone(), likelihood=lik, optimizer_class=torch.optim.SGD,
+                         lr=float(d["mpf_lr"]), bw=float(d["mpf_prior_bw0"]), bw_scale=1.0, device="cpu")
+    prior0 = mpf.prior                                 # captured once, as the demos do (particle_example.py:171)
+    for t in range(int(d["n_steps"])):
+        gn, bw = mpf.optimize(d[f"t{t}_out_a_seq"][0], d[f"t{t}_out_next_state"], bw=0.5, n_steps=20)
+        assert rel_max(mpf.x, d[f"t{t}_out_mpf_x1"]) <= 5e-4 and gn.shape == (20,)
+        assert rel_max(gn, d[f"t{t}_out_mpf_grad_norms"]) <= 5e-3
+    assert torch.equal(prior0.component_distribution.base_dist.loc, mpf.x)
+    with pytest.raises(NotImplementedError):
+        mpf_module.MPF(init_particles=d["t0_in_mpf_x0"].clone(), likelihood=lik, optimizer_class=torch.optim.Adam, device="cpu")
