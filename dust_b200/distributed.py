@@ -36,7 +36,14 @@ class ShardedSVGD:
     """phi = (K grad log p + sum grad k)/N for N particles split by row blocks over the ranks of
     `group` (dust/inference/svgd.py:127-135 with the bw_median bandwidth, svgd.py:42-52)."""
 
-    def __init__(self, n_total, dim, group=None, ops=_ops, device=None):
+    def __init__(self, n_total, dim, group=None, ops=_ops, device=None, gather="packed"):
+        """gather: "packed" = one all-gather of [X | score] (concatenate before, slice after: the measured default);
+        "separate" = X and score gathered straight into their own contiguous [N, D] buffers (two collectives, no
+        staging copies; not yet measured on 8 GPUs)."""
+        if gather not in ("packed", "separate"):
+            raise ValueError(gather)
+        self.gather_mode = gather
+        self._gathered2 = {}
         self.N, self.D, self.group, self.ops = n_total, dim, group, ops
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -61,6 +68,15 @@ class ShardedSVGD:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
 
     def gather(self, x_local, score_local):
+        if self.gather_mode == "separate" and self.world > 1:
+            out = []
+            for key, loc in (("x", x_local), ("score", score_local)):
+                buf = self._gathered2.get(key)
+                if buf is None or buf.dtype != loc.dtype or buf.device != loc.device:
+                    buf = self._gathered2[key] = torch.empty((self.N, self.D), dtype=loc.dtype, device=loc.device)
+                dist.all_gather_into_tensor(buf, loc.contiguous(), group=self.group)
+                out.append(buf)
+            return out[0], out[1]
         xs = self._all_gather(torch.cat([x_local, score_local], dim=1))
         return xs[:, : self.D].contiguous(), xs[:, self.D:].contiguous()
 

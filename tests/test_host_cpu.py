@@ -203,6 +203,9 @@ X = torch.randn(N, D); S = -X
 b, e = row_block(N, r, w)
 sh = ShardedSVGD(N, D, ops=OracleOps)
 phi_loc, coef = sh.phi(X[b:e].clone(), S[b:e].clone())
+sh2 = ShardedSVGD(N, D, ops=OracleOps, gather="separate")      # X and score gathered separately: same result
+phi_loc2, coef2 = sh2.phi(X[b:e].clone(), S[b:e].clone())
+assert torch.equal(phi_loc2, phi_loc) and torch.equal(coef2, coef)
 bw_ref, med_ref = O.bw_median(X)
 ref = O.phi_svgd(X.double(), S.double(), float(bw_ref)).float()
 assert abs(float(coef[3]) - float(bw_ref)) < 1e-6, (float(coef[3]), float(bw_ref))
