@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--check", action="store_true", help="compare a row sample against the float64 oracle")
+    ap.add_argument("--gather", default="packed", choices=["packed", "separate"],
+                    help="sharded runs: one all-gather of [X | score] (default) or X and score gathered separately")
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="single process only: time the row block ONE rank of a world of this size computes (all N "
                          "columns resident, no collective) -- the per-rank device work of the sharded run")
@@ -48,7 +50,7 @@ def main():
     S = -X
     emu = args.emulate_world if world == 1 else 1
     b, e = row_block(N, rank, world) if emu == 1 else row_block(N, emu // 2, emu)
-    sh = ShardedSVGD(N, D, device=dev)
+    sh = ShardedSVGD(N, D, device=dev, gather=args.gather)
     xl, sl = X[b:e].contiguous(), S[b:e].contiguous()
     if emu > 1:   # this process plays rank emu // 2: its row block against the resident columns
         sh.rows = (b, e)
@@ -125,7 +127,7 @@ def main():
         Dp, NV = (D + 7) // 8 * 8, (2 * D + 15) // 16 * 16
         issued = 3 * 2.0 * N * N * (Dp + NV) / (world * emu)   # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
         t_phi_kernel = prof.get("phi_tc_kernel", (0, 0.0))[1]
-        out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "emulated_world": emu, "rows": [b, e],
+        out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "emulated_world": emu, "rows": [b, e], "gather": args.gather,
                "ms_phi_with_median": ms_full if emu == 1 else None, "ms_phi": ms_phi,
                "algorithmic_tflops_phi": fl_phi / (ms_phi * 1e-3) / 1e12,
                "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12 if emu == 1 else None, "bandwidth": bw,
