@@ -38,6 +38,10 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="instances in the bounded CPU sample (default: sized for ~15 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-phi", action="store_true", help="skip the large-N SVGD phi block (configs[3])")
+    ap.add_argument("--no-configs", action="store_true", help="skip the demo / dual-stress block (configs[0], [1], [4])")
+    ap.add_argument("--phi-steps", type=int, default=5)
+    ap.add_argument("--config-steps", type=int, default=10)
     return ap.parse_args()
 
 
@@ -80,6 +84,51 @@ def cpu_instance_steps(n_instances, n_steps, threads, seed=0):
             O.svmpc_forward(st, out["costs"], c["alpha"], False)
     dt = time.perf_counter() - t0
     return n_instances * n_steps / dt, dt
+
+
+def cpu_demo_steps(threads, seconds=6.0):
+    """The two demo configurations (configs[0], [1]) on the CPU port: one dual control step = SVMPC optimize +
+    forward, plant step, 20 MPF steps (particle_example.py:177-207).  -> {name: ms per dual step}."""
+    from bench_configs import CONFIGS, PARTICLE_ENV
+    from dust_b200.models.particle import Particle
+    from oracle import dust_oracle as O
+
+    torch.set_num_threads(threads)
+    out = {}
+    for name in ("pendulum_demo", "particle_demo"):
+        c = CONFIGS[name]
+        g = torch.Generator().manual_seed(0)
+        if c["kind"] == "pendulum":
+            model, A, state = O.Model("pendulum"), 1, torch.tensor([3.0, 0.0])
+            params = 0.6 + 0.7 * torch.rand(c["P"], 2, generator=g)
+            x = 0.6 + 0.7 * torch.rand(c["Np"], 2, generator=g)
+        else:
+            model, A, state = O.Model("particle", O.ParticleCfg(Particle(**PARTICLE_ENV, uncertain_params=["mass"], mass=2.0).obst_map.map)), 2, torch.tensor([-9.0, -9.0, 0.0, 0.0])
+            params = 0.693 + 0.1 * torch.randn(c["P"], 1, generator=g)
+            x = 0.693 + 0.1 * torch.randn(c["Np"], 1, generator=g)
+        N, H, S = c["N"], c["H"], c["S"]
+        mu = torch.randn(N, H, A, generator=g)
+        st = O.SvmpcState(mu + c["prior_sigma"] * torch.randn(N, H, A, generator=g), mu, torch.ones(N), c["prior_sigma"] ** 2)
+        sigma = torch.full((A,), c["sigma"])
+
+        def dual():
+            nonlocal x
+            eps = torch.randn(S, N, H, A, generator=g)
+            o = O.svmpc_optimize(model, st, state, eps, sigma, params, c["log_space"], 1.0, c["lr"], kernel="rbf")
+            a_seq, _, _ = O.svmpc_forward(st, o["costs"], 1.0, c["weighted_prior"])
+            act = a_seq[0]
+            nxt = model.step(state.reshape(1, -1), act.reshape(1, -1)).reshape(-1)
+            x, _ = O.mpf_optimize(model, x, state, act, nxt, c["obs_std"], torch.full((model.dp,), c["mpf_bw"] ** 2), c["mpf_bw"],
+                                  c["mpf_lr"], c["mpf_steps"], c["log_space"])
+
+        dual()
+        n, t0 = 0, time.perf_counter()
+        while time.perf_counter() - t0 < seconds and n < 200:
+            dual()
+            n += 1
+        ms = (time.perf_counter() - t0) * 1e3 / n
+        out[name] = {"ms_per_dual_step": ms, "dual_steps_per_sec": 1e3 / ms, "steps_timed": n, "cores": threads, "kind": "port"}
+    return out
 
 
 def probe_threads():
@@ -131,54 +180,9 @@ def run_reference(args, rank):
 # ---------------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------------
-class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+from bench_common import ClockSampler, committed_traffic, measured_peaks  # noqa: E402
 
-    def __init__(self, index):
-        self.p = None
-        try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        except Exception:
-            self.p = None
-
-    def stop(self):
-        if self.p is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.p.terminate()
-        try:
-            out, _ = self.p.communicate(timeout=5)
-        except Exception:
-            self.p.kill()
-            out = ""
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in out.strip().splitlines():
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
-
-
-def measured_peak():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(p):
-        try:
-            return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
-        except Exception:
-            pass
-    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)"
+ROLLOUT_SOURCES = ("dust_b200/csrc/rollout.cu", "dust_b200/csrc/models.cuh", "dust_b200/csrc/common.cuh")
 
 
 def run_ours(args, rank, world, local_rank):
@@ -257,6 +261,19 @@ def run_ours(args, rank, world, local_rank):
         dist.all_reduce(ms2, op=dist.ReduceOp.MAX)
     e2e_ms_total = float(ms2[0])
 
+    # ---- the other BASELINE configurations, in the same process (every rank takes part in the collectives) ----
+    del eps, ctl
+    torch.cuda.empty_cache()
+    phi = cfgs = None
+    if not args.no_phi:
+        from bench_phi import phi_block
+
+        phi = phi_block(rank, world, dev, steps=args.phi_steps, warmup=3)
+        torch.cuda.empty_cache()
+    if not args.no_configs:
+        from bench_configs import configs_block
+
+        cfgs = configs_block(rank, world, dev, steps=args.config_steps, warmup=3)
     if rank != 0:
         return
     K = args.steps
@@ -266,24 +283,20 @@ def run_ours(args, rank, world, local_rank):
     # roofline of the dominant kernel (rollout + cost): algorithmic bytes per launch =
     # 4 * B * (S*N*H*A noise read + S*N costs written + N*H*A theta read + ds state read)
     algo_bytes = 4.0 * B * (c["S"] * c["N"] * c["H"] * c["A"] + c["S"] * c["N"] + c["N"] * c["H"] * c["A"] + c["ds"])
-    peak, peak_src = measured_peak()
+    peaks = measured_peaks()
+    peak, peak_src = peaks["hbm_gbs"], peaks["source"] + " hbm_gbs (measured copy bandwidth)"
     dom = "svmpc_instance_kernel" if "svmpc_instance_kernel" in prof else "rollout_cost_kernel"  # fused step kernel
     n_roll, ms_roll = prof.get(dom, (0, 0.0))
     roof = None
     if n_roll:
         per = ms_roll / n_roll
         ach = algo_bytes / (per * 1e-3) / 1e9
-        traffic = None
-        tp = os.path.join(ROOT, "profiles", "rollout_traffic.json")
-        if os.path.isfile(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
-            except Exception:
-                traffic = None
+        # ncu dram__bytes_read + write of this kernel, committed with the hash of the sources it was captured on
+        traffic, traffic_note = committed_traffic(dom, ROLLOUT_SOURCES)
         roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak, "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes,
+                "frac": ach / peak, "traffic": traffic, "traffic_note": traffic_note, "algorithmic_bytes_per_launch": algo_bytes,
                 "ms_per_launch": per, "peak_source": peak_src,
-                "note": "not HBM-limited: ~31 issue slots per model step vs 4 bytes of noise; issue/latency bound at 20 warps/SM, see DESIGN.md section 3"}
+                "note": "issue-bound, not HBM-limited (~30 issue slots per model step against 4 bytes of noise): see DESIGN.md section 3"}
     step_kernel_ms = {k: v[1] / K for k, v in prof.items()}
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -291,6 +304,8 @@ def run_ours(args, rank, world, local_rank):
         cpu = {"value": v, "unit": UNIT, "cores": th, "kind": "port", "host_cpus": os.cpu_count(),
                "thread_probe": {str(k): round(x, 1) for k, x in probe.items()},
                "sample": f"{n_cpu} of {B} instances, 1 step each, one instance at a time ({dt:.1f} s of CPU work)"}
+        if cfgs is not None:
+            cpu["configs"] = cpu_demo_steps(th)
     cfg = workload_config(args, world)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
@@ -300,7 +315,7 @@ def run_ours(args, rank, world, local_rank):
                 "h2d_bytes_per_step": B * c["ds"] * 4, "d2h_bytes_per_step": B * c["A"] * 4,
                 "note": "state in (pinned host) -> action out (pinned host); noise drawn on the device inside the call"},
         "gpu_launches": launches, "kernel_ms_per_step": step_kernel_ms, "roofline": roof, "cpu_baseline": cpu,
-        "clocks": clocks,
+        "clocks": clocks, "phi": phi, "configs": cfgs,
     }
     print(json.dumps(line), flush=True)
 

@@ -12,6 +12,12 @@ One JSON line per configuration: device ms per step (CUDA events over the timed 
 step (host overhead included), per-kernel ms from the library profiler and rollouts per second.
 The reference's own CPU timings of the two demo shapes are in SURVEY.md section 6 / BASELINE.md.
 
+`configs_block()` is what bench.py embeds in its JSON line: the kernel-level step (`SvmpcCore` + ops, device and wall
+ms) AND, for the two demo shapes, the same dual step through the drop-in classes a user of the reference calls
+(`SVMPC.optimize` / `SVMPC.forward` / `MPF.optimize`, wall clock, launches per step).  Under torchrun the stress shape's
+parameter draws are split over the ranks (`ShardedRollout`, NCCL all-reduce of the cost and gradient shares) and rank
+0 also runs the unsharded step in the same process: strong scaling and a parity figure.
+
 Synthetic inputs, seeded; noise resident on the device.  Not a parity test (tests/ hold those)."""
 import argparse
 import json
@@ -86,6 +92,187 @@ def dual_step(cfg, p):
     return nxt
 
 
+def class_objects(name, dev, seed=0):
+    """The reference-shaped objects of a demo configuration (demo/*_example.py), on the device."""
+    import torch.distributions as dist
+
+    from demo import configs
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.inference.likelihoods import ExponentiatedUtility, GaussianLikelihood
+    from dust_b200.inference.mpf import MPF
+    from dust_b200.inference.svgd import get_gmm
+    from dust_b200.inference.svmpc import SVMPC
+    from dust_b200.kernels.base_kernels import RBFKernel
+    from dust_b200.models.pendulum import PendulumModel
+    from dust_b200.models.pendulum import inst_cost as pend_inst
+    from dust_b200.models.pendulum import term_cost as pend_term
+
+    torch.manual_seed(seed)
+    if name == "particle_demo":
+        from demo.particle_example import build as build_particle
+
+        cfg = configs.load(None, configs.PARTICLE)
+        controller, svmpc, mpf, model, _ = build_particle(cfg, seed)
+        ep = cfg["exp_params"]
+        state = torch.as_tensor(cfg["env_params"]["init_state"], dtype=torch.float).to(dev)
+        return dict(svmpc=svmpc, mpf=mpf, plant=model, state=state, mpf_bw=ep["mpf_bandwidth"], mpf_steps=ep["mpf_steps"])
+    cfg = configs.load(None, configs.PENDULUM)
+    ep = cfg["exp_params"]
+    H, N, S, A = ep["horizon"], ep["n_particles"], ep["action_samples"], ep["ctrl_dim"]
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    prior = get_gmm(torch.randn(N, H, A), torch.ones(N), ep["prior_sigma"] ** 2 * torch.eye(A))
+    theta0 = prior.sample([N])
+    dyn_prior = dist.Independent(dist.Uniform(torch.tensor([0.6, 0.6]), torch.tensor([1.3, 1.3])), 1)
+    ctrl = MultiDISCO(observation_space=model.observation_space, action_space=model.action_space, hz_len=H, n_policies=N,
+                      action_samples=S, params_samples=ep["params_samples"], temperature=1 / ep["alpha"],
+                      a_cov=ep["ctrl_sigma"] ** 2 * torch.eye(A), inst_cost_fn=pend_inst, term_cost_fn=pend_term,
+                      params_sampling=True, params_log_space=ep["mpf_log_space"])
+    lik = ExponentiatedUtility(ep["alpha"], n_samples=S, controller=ctrl, model=model)
+    svmpc = SVMPC(init_particles=theta0, prior=prior, likelihood=lik, kernel=RBFKernel(), n_particles=N,
+                  bw_scale=ep["bandwidth_scaling"], n_steps=1, optimizer_class=torch.optim.SGD, lr=ep["learning_rate"])
+    state = torch.as_tensor(ep["init_state"], dtype=torch.float).to(dev)
+    mpf_init = dyn_prior.sample([ep["mpf_n_particles"]])
+    dyn_lik = GaussianLikelihood(initial_obs=state, obs_std=ep["mpf_obs_std"], model=model, log_space=ep["mpf_log_space"])
+    mpf = MPF(init_particles=mpf_init, likelihood=dyn_lik, optimizer_class=torch.optim.SGD, lr=ep["mpf_learning_rate"],
+              bw=ep["mpf_bandwidth"], bw_scale=ep["mpf_bandwidth_scaling"])
+    plant = PendulumModel(length=1.0, mass=1.0)
+    return dict(svmpc=svmpc, mpf=mpf, plant=plant, state=state, mpf_bw=ep["mpf_bandwidth"], mpf_steps=ep["mpf_steps"])
+
+
+def class_dual_step(o):
+    """One control step exactly as the reference's drivers make it (particle_example.py:177-207,
+    simulations.py:104-138): optimise, act, step the plant, condition the parameter filter."""
+    sv, mpf = o["svmpc"], o["mpf"]
+    dyn = mpf.prior
+    sv.optimize(o["state"], dyn)
+    a_seq, _ = sv.forward(o["state"], dyn)
+    action = a_seq[0]
+    nxt = o["plant"].step(o["state"].reshape(1, -1), action.reshape(1, -1)).reshape(-1)
+    mpf.optimize(action.squeeze(), nxt, bw=o["mpf_bw"], n_steps=o["mpf_steps"])
+    return nxt
+
+
+def time_class_path(name, dev, steps, warmup):
+    from dust_b200 import _lib as L
+
+    lib = L.load()
+    o = class_objects(name, dev)
+    for _ in range(warmup):
+        class_dual_step(o)       # the state is held fixed: a timing loop, not an episode
+    torch.cuda.synchronize()
+    n0 = lib.dust_launch_count()
+    w0 = time.perf_counter()
+    for _ in range(steps):
+        class_dual_step(o)
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+    return {"wall_ms_per_dual_step": wall_ms, "dual_steps_per_sec": 1e3 / wall_ms,
+            "library_launches_per_step": (lib.dust_launch_count() - n0) / steps,
+            "api": "SVMPC.optimize + SVMPC.forward + model.step + MPF.optimize (drop-in classes, belief = mpf.prior)"}
+
+
+def configs_block(rank, world, dev, names=("pendulum_demo", "particle_demo", "dual_stress"), steps=10, warmup=3, alpha=1.0,
+                  emulate_world=1, class_path=True):
+    """-> {config name: timing dict} on rank 0 (None elsewhere)."""
+    import torch.distributed as dist
+
+    from bench_common import ClockSampler
+    from dust_b200 import _lib as L
+    from dust_b200.distributed import ShardedRollout, row_block
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    for name in names:
+        cfg = CONFIGS[name]
+        if world > 1 and name != "dual_stress":
+            continue           # the demo shapes are single-instance, single-GPU problems ("replicas only")
+        p = build(cfg, dev, alpha=alpha)
+        if world > 1 or emulate_world > 1:
+            sh = ShardedRollout(cfg["P"])
+            if emulate_world > 1:
+                sh.p_range = row_block(cfg["P"], emulate_world // 2, emulate_world)
+            p["core"].sharded = sh
+        for _ in range(warmup):
+            dual_step(cfg, p)
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            dual_step(cfg, p)
+        e1.record()
+        sync()
+        wall_ms = (time.perf_counter() - w0) * 1e3 / steps
+        dev_ms = e0.elapsed_time(e1) / steps
+        if world > 1:   # device time of the slowest rank
+            t = torch.tensor([dev_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dev_ms = float(t[0])
+        lib = L.load()
+        lib.dust_profiler_reset()
+        lib.dust_profiler_enable(1)
+        n0 = lib.dust_launch_count()
+        for _ in range(steps):
+            dual_step(cfg, p)
+        torch.cuda.synchronize()
+        launches = (lib.dust_launch_count() - n0) / steps
+        prof = {k: v[1] / steps for k, v in L.profiler_report().items()}
+        lib.dust_profiler_enable(0)
+        model_steps = cfg["P"] * cfg["S"] * cfg["N"] * cfg["H"]
+        line = {"shape": {k: cfg[k] for k in ("kind", "H", "N", "S", "P", "Np", "mpf_steps", "grad")},
+                "device_ms_per_dual_step": dev_ms, "wall_ms_per_dual_step": wall_ms,
+                "dual_steps_per_sec": 1e3 / dev_ms, "rollouts_per_sec": cfg["P"] * cfg["S"] * cfg["N"] * 1e3 / dev_ms,
+                "model_steps_per_control_step": model_steps, "library_launches_per_step": launches,
+                "kernel_ms_per_step": prof, "steps": steps, "warmup": warmup, "alpha": alpha, "n_gpus": world,
+                "emulated_world": emulate_world,
+                "sharding": None if p["core"].sharded is None else "parameter draws %s of %d on rank 0" % (
+                    list(p["core"].sharded.p_range), cfg["P"])}
+        lw = p["core"].last.get("lik_weights")
+        if lw is not None:   # pathwise gradient: rows with an exactly-zero weight are not rolled out by the adjoint
+            line["nonzero_weight_fraction"] = float((lw != 0).float().mean())
+        if world > 1:
+            # the same step unsharded on rank 0 alone (same process, same inputs): strong scaling + parity of one step
+            q = build(cfg, dev, alpha=alpha)
+            single_ms = None
+            if rank == 0:
+                for _ in range(warmup):
+                    dual_step(cfg, q)
+                torch.cuda.synchronize()
+                f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                f0.record()
+                for _ in range(steps):
+                    dual_step(cfg, q)
+                f1.record()
+                torch.cuda.synchronize()
+                single_ms = f0.elapsed_time(f1) / steps
+            sync()
+            a, b = build(cfg, dev, alpha=alpha), build(cfg, dev, alpha=alpha)
+            a["core"].sharded = ShardedRollout(cfg["P"])
+            a["core"].optimize_step(a["state"], a["eps"], a["params"])       # collective: every rank
+            if rank == 0:
+                b["core"].optimize_step(b["state"], b["eps"], b["params"])
+                rel = lambda x, y: float((x - y).abs().max() / y.abs().max())  # noqa: E731
+                line["single_gpu_same_process_ms"] = single_ms
+                line["strong_scaling"] = single_ms / (world * dev_ms)
+                line["max_rel_diff_vs_single_gpu"] = {"costs": rel(a["core"].last["costs"], b["core"].last["costs"]),
+                                                      "grad_lik": rel(a["core"].last["grad_lik"], b["core"].last["grad_lik"]),
+                                                      "theta": rel(a["core"].theta, b["core"].theta)}
+                line["collectives"] = {"costs_all_reduce_bytes": 4 * cfg["S"] * cfg["N"],
+                                       "gradient_all_reduce_bytes": 4 * cfg["N"] * cfg["H"] * p["A"] if cfg["grad"] == "pathwise" else 0}
+            sync()
+        if class_path and world == 1 and emulate_world == 1 and name != "dual_stress":
+            line["drop_in_classes"] = time_class_path(name, dev, steps, warmup)
+        out[name] = line
+    if sampler:
+        out["clocks"] = sampler.stop()
+    return out if rank == 0 else None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--configs", default="pendulum_demo,particle_demo,dual_stress")
@@ -96,12 +283,9 @@ def main():
                     help="single process: time the parameter-draw share ONE rank of a world of this size rolls out "
                          "(no all-reduce: the device work of a rank, not a valid control step)")
     args = ap.parse_args()
-    import os
-
     import torch.distributed as dist
 
     from dust_b200 import _lib as L
-    from dust_b200.distributed import ShardedRollout, row_block
 
     L.require_cuda()
     rank, world, lrank = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
@@ -110,58 +294,10 @@ def main():
     if world > 1:   # one instance, its parameter draws split over the ranks (inputs replicated: same seed everywhere)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for name in args.configs.split(","):
-        cfg = CONFIGS[name]
-        p = build(cfg, dev, alpha=args.alpha)
-        if world > 1 or args.emulate_world > 1:
-            sh = ShardedRollout(cfg["P"])
-            if args.emulate_world > 1:
-                sh.p_range = row_block(cfg["P"], args.emulate_world // 2, args.emulate_world)
-            p["core"].sharded = sh
-        for _ in range(args.warmup):
-            dual_step(cfg, p)
-        sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        e0.record()
-        for _ in range(args.steps):
-            dual_step(cfg, p)
-        e1.record()
-        sync()
-        wall_ms = (time.perf_counter() - w0) * 1e3 / args.steps
-        dev_ms = e0.elapsed_time(e1) / args.steps
-        if world > 1:   # device time of the slowest rank
-            t = torch.tensor([dev_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dev_ms = float(t[0])
-        lib = L.load()
-        lib.dust_profiler_reset()
-        lib.dust_profiler_enable(1)
-        for _ in range(args.steps):
-            dual_step(cfg, p)
-        torch.cuda.synchronize()
-        prof = {k: v[1] / args.steps for k, v in L.profiler_report().items()}
-        lib.dust_profiler_enable(0)
-        model_steps = cfg["P"] * cfg["S"] * cfg["N"] * cfg["H"]
-        line = {"config": name, "shape": {k: cfg[k] for k in ("kind", "H", "N", "S", "P", "Np", "mpf_steps", "grad")},
-                "device_ms_per_dual_step": dev_ms, "wall_ms_per_dual_step": wall_ms,
-                "dual_steps_per_sec": 1e3 / dev_ms, "rollouts_per_sec": cfg["P"] * cfg["S"] * cfg["N"] * 1e3 / dev_ms,
-                "model_steps_per_control_step": model_steps, "kernel_ms_per_step": prof, "steps": args.steps,
-                "warmup": args.warmup, "data": "synthetic", "alpha": args.alpha, "n_gpus": world,
-                "emulated_world": args.emulate_world,
-                "sharding": None if p["core"].sharded is None else "parameter draws %s of %d on this rank" % (
-                    list(p["core"].sharded.p_range), cfg["P"])}
-        lw = p["core"].last.get("lik_weights")
-        if lw is not None:   # pathwise gradient: rows with an exactly-zero weight are not rolled out by the adjoint
-            line["nonzero_weight_fraction"] = float((lw != 0).float().mean())
-        if rank == 0:
-            print(json.dumps(line), flush=True)
+    out = configs_block(rank, world, dev, tuple(args.configs.split(",")), args.steps, args.warmup, args.alpha, args.emulate_world)
+    if rank == 0:
+        for name, line in out.items():
+            print(json.dumps({"config": name, **line} if isinstance(line, dict) and name != "clocks" else {name: line}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

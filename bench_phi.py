@@ -1,11 +1,16 @@
 #!/usr/bin/env python
-"""Large-N SVGD phi microbenchmark (BASELINE.json configs[3]): N particles, d = 40, canonical SVGD
-direction with the exact median bandwidth.  Reports time, algorithmic TFLOP/s (6 N^2 d for phi,
-4 N^2 d for the two median passes) and, under torchrun, the row-block sharded version
-(all-gather of [X|score] + histogram all-reduce over NCCL).
+"""Large-N SVGD phi (BASELINE.json configs[3]): N particles, d = 40, canonical SVGD direction
+(dust/inference/svgd.py:127-135) with the exact median bandwidth (svgd.py:42-52).
+
+`phi_block()` is what bench.py embeds in its JSON line on every run: time, tensor-pipe roofline of
+`phi_tc_kernel` (issued 3xTF32 FLOPs against bf16_tflops/2 of MEASURED_PEAKS.json AND against cuBLAS TF32
+measured in the same run), its own clock sample, and in-run checks (sampled rows against float64, the
+tensor-core median against the SIMT radix select).  Under torchrun the rows are sharded over the ranks
+(`ShardedSVGD`: all-gather of X and score, all-reduce of the bandwidth histogram, NCCL), then rank 0 times the
+full problem alone in the same process: `strong_scaling = t1 / (n * tn)` and `max_rel_diff_vs_single_gpu`.
 
   python bench_phi.py --particles 65536 --steps 5
-  python -m torch.distributed.run --nproc-per-node 8 bench_phi.py --particles 65536
+  python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 bench_phi.py
 """
 import argparse
 import json
@@ -16,16 +21,157 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
+from bench_common import ClockSampler, cublas_tf32_tflops, measured_peaks, timed_ms  # noqa: E402
+
+
+def float64_rows(X, S, idx, gamma, c1, c2):
+    """phi rows `idx` in float64 with torch on the device: c1 K S + c2 (rowsum(K) x - K X), K = exp(-gamma d^2)
+    (the unified form of svgd.py:127-135)."""
+    Xd, Sd = X.double(), S.double()
+    xi = Xd[idx]
+    d2 = ((xi * xi).sum(-1, keepdim=True) + (Xd * Xd).sum(-1)[None, :] - 2 * xi @ Xd.t()).clamp(min=0)
+    d2[torch.arange(len(idx), device=X.device), idx] = 0.0
+    K = (-gamma * d2).exp()
+    return c1 * (K @ Sd) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xd)
+
+
+def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="separate", emulate_world=1, checks=True):
+    import torch.distributed as dist
+
+    from dust_b200 import _lib as L
+    from dust_b200 import ops
+    from dust_b200.distributed import ShardedSVGD, row_block
+
+    lib = L.load()
+    g = torch.Generator(device=dev).manual_seed(0)
+    X = torch.randn(N, D, device=dev, generator=g)       # same seed on every rank: each holds the full cloud,
+    S = -X                                               # uses only its row block as its local input
+    emu = emulate_world if world == 1 else 1
+    b, e = row_block(N, rank, world) if emu == 1 else row_block(N, emu // 2, emu)
+    sh = ShardedSVGD(N, D, device=dev, gather=gather)
+    xl, sl = X[b:e].contiguous(), S[b:e].contiguous()
+    if emu > 1:   # this process plays rank emu // 2: its row block against the resident columns
+        sh.rows = (b, e)
+        sh.gather = lambda x_local, s_local: (X, S)
+    hold = {}
+
+    def sharded_full():
+        hold["phi"], hold["coef"] = sh.phi(xl, sl)
+
+    if emu > 1:
+        # one rank's histogram alone selects nothing (the all-reduce over the other ranks is missing): take the
+        # bandwidth from a full single-GPU pass, untimed, and time only the phi row block
+        coef_full = ops.bandwidth_from_median(ops.median_sq_dist(X), N, 1.0, 0)
+
+        def sharded_full():  # noqa: F811
+            x_all, s_all = sh.gather(xl, sl)
+            out_ = ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef_full, rows=sh.rows)
+            hold["phi"], hold["coef"] = out_["phi"][0, b:e], coef_full
+
+    sampler = ClockSampler(dev.index or 0) if rank == 0 else None
+    ms_full = timed_ms(sharded_full, steps, warmup, dev, world)
+    coef = hold["coef"]
+
+    def sharded_phi_only():
+        x_all, s_all = sh.gather(xl, sl)
+        ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=sh.rows)
+
+    ms_phi = timed_ms(sharded_phi_only, steps, warmup, dev, world)
+    lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
+    sharded_full()
+    prof = L.profiler_report()
+    lib.dust_profiler_enable(0)
+    phi_sharded = hold["phi"].clone()
+
+    single = None
+    if world > 1:
+        # rank 0 alone, full problem, same process and clocks; the other ranks wait at the barrier inside timed_ms
+        def single_full():
+            med = ops.median_sq_dist(X)
+            c = ops.bandwidth_from_median(med, N, 1.0, 0)
+            hold["phi1"], hold["coef1"] = ops.svgd_phi(X.unsqueeze(0), S.unsqueeze(0), gamma_dev=c)["phi"][0], c
+
+        def single_phi_only():
+            ops.svgd_phi(X.unsqueeze(0), S.unsqueeze(0), gamma_dev=coef)
+
+        def noop():
+            pass
+
+        t1_full = timed_ms(single_full if rank == 0 else noop, steps, warmup, dev, world)
+        t1_phi = timed_ms(single_phi_only if rank == 0 else noop, steps, warmup, dev, world)
+        # parity of the sharded rows against the single-GPU rows (gathered on every rank; rank 0 compares)
+        allphi = torch.empty(N, D, device=dev)
+        dist.all_gather_into_tensor(allphi, phi_sharded.contiguous())
+        single = {"t1_full": t1_full, "t1_phi": t1_phi}
+        if rank == 0:
+            ref = hold["phi1"]
+            single["max_rel_diff"] = float((allphi - ref).abs().max() / ref.abs().max())
+            single["bandwidth_bits_equal"] = bool(torch.equal(hold["coef1"], coef))
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        return None
+
+    peaks = measured_peaks()
+    tf32_inrun = cublas_tf32_tflops(dev)
+    Dp, NV = (D + 7) // 8 * 8, (2 * D + 15) // 16 * 16
+    issued = 3 * 2.0 * N * N * (Dp + NV) / (world * emu)       # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
+    n_phi, t_phi_kernel = prof.get("phi_tc_kernel", (0, 0.0))
+    n_med, t_med_kernel = prof.get("median_tc_kernel", (0, 0.0))
+    peak = peaks["bf16_tflops"] / 2.0
+    fl_phi, fl_med = 6.0 * N * N * D, 4.0 * N * N * D
+    out = {"workload": "large-N SVGD phi (BASELINE.json configs[3])", "N": N, "d": D, "n_gpus": world, "emulated_world": emu,
+           "rows_of_rank0": [b, e], "gather": gather if world > 1 else None, "steps": steps, "warmup": warmup,
+           "ms_phi": ms_phi, "ms_phi_with_median": ms_full if emu == 1 else None,
+           "algorithmic_tflops_phi": fl_phi / emu / (ms_phi * 1e-3) / 1e12,    # whole job (all ranks) over its time
+           "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12 if emu == 1 else None,
+           "bandwidth": float(coef[3]), "kernels_ms": {k: v[1] for k, v in prof.items()}, "clocks": clocks,
+           "l2_policy": "operands (31 MB) are L2-resident by design: tensor-pipe bound, HBM traffic negligible"}
+    if n_phi:
+        ach = issued / (t_phi_kernel * 1e-3) / 1e12
+        out["roofline"] = {"kernel": "phi_tc_kernel", "bound": "tensor", "unit": "TFLOP/s", "achieved": ach, "peak": peak,
+                           "frac": ach / peak, "peak_source": f"{peaks['source']} bf16_tflops / 2 (nominal TF32:BF16 = 1:2)",
+                           "peak_inrun_cublas_tf32": tf32_inrun, "frac_vs_inrun_cublas_tf32": ach / tf32_inrun,
+                           "ms_per_launch_sum": t_phi_kernel, "launches": n_phi, "traffic": None,
+                           "note": "achieved counts the TF32 MMA FLOPs issued (3 per algorithmic product, K padded to 8 / NV to 16); "
+                                   "algorithmic FLOPs are a third of it"}
+    if n_med:
+        issued_med = 3 * 2.0 * N * N * Dp / 2 / (world * emu)   # symmetric half band of tile pairs
+        out["median_kernel"] = {"kernel": "median_tc_kernel", "ms": t_med_kernel,
+                                "issued_tflops": issued_med / (t_med_kernel * 1e-3) / 1e12,
+                                "frac_of_bf16_half": issued_med / (t_med_kernel * 1e-3) / 1e12 / peak}
+    if single is not None:
+        out["single_gpu_same_process"] = {"ms_phi": single["t1_phi"], "ms_phi_with_median": single["t1_full"]}
+        out["strong_scaling"] = single["t1_phi"] / (world * ms_phi)
+        out["strong_scaling_with_median"] = single["t1_full"] / (world * ms_full)
+        out["max_rel_diff_vs_single_gpu"] = single["max_rel_diff"]
+        out["bandwidth_bits_equal_to_single_gpu"] = single["bandwidth_bits_equal"]
+    if checks and emu == 1:
+        gam, c1, c2 = [float(v) for v in coef[:3].cpu()]
+        gi = torch.Generator(device=dev).manual_seed(1)
+        idx = torch.cat([torch.arange(b, e, max(1, (e - b) // 64), device=dev)[:64],
+                         torch.randint(b, e, (64,), device=dev, generator=gi)])
+        ref = float64_rows(X, S, idx, gam, c1, c2)
+        got = phi_sharded[idx - b].double()
+        out["rel_err_vs_float64_rows"] = float((got - ref).abs().max() / ref.abs().max())
+        out["rows_checked"] = int(idx.numel())
+        if world == 1:
+            fast = ops.median_sq_dist(X).clone()
+            robust = ops.median_sq_dist(X, allow_fast=False).clone()
+            bits = lambda t: int(t.view(torch.int32)[0])  # noqa: E731
+            out["median"] = {"tensor_core_window": float(fast[0]), "simt_radix_select": float(robust[0]),
+                             "ulp_distance": abs(bits(fast) - bits(robust)),
+                             "note": "two exact rank selections over differently rounded distances (3xTF32 Gram vs fp32 FMA chain)"}
+    return out
+
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--particles", type=int, default=65536)
     ap.add_argument("--dim", type=int, default=40)
     ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=2)
-    ap.add_argument("--check", action="store_true", help="compare a row sample against the float64 oracle")
-    ap.add_argument("--gather", default="packed", choices=["packed", "separate"],
-                    help="sharded runs: one all-gather of [X | score] (default) or X and score gathered separately")
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--gather", default="separate", choices=["packed", "separate"],
+                    help="sharded runs: X and score gathered into their own buffers (default) or one all-gather of [X | score]")
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="single process only: time the row block ONE rank of a world of this size computes (all N "
                          "columns resident, no collective) -- the per-rank device work of the sharded run")
@@ -35,125 +181,12 @@ def main():
     lr = int(os.environ.get("LOCAL_RANK", "0"))
     import torch.distributed as dist
 
-    from dust_b200 import _lib as L
-    from dust_b200 import ops
-    from dust_b200.distributed import ShardedSVGD, row_block
-
     torch.cuda.set_device(lr)
     dev = torch.device("cuda", lr)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    N, D = args.particles, args.dim
-    g = torch.Generator(device=dev).manual_seed(0)
-    X = torch.randn(N, D, device=dev, generator=g)
-    S = -X
-    emu = args.emulate_world if world == 1 else 1
-    b, e = row_block(N, rank, world) if emu == 1 else row_block(N, emu // 2, emu)
-    sh = ShardedSVGD(N, D, device=dev, gather=args.gather)
-    xl, sl = X[b:e].contiguous(), S[b:e].contiguous()
-    if emu > 1:   # this process plays rank emu // 2: its row block against the resident columns
-        sh.rows = (b, e)
-        sh.gather = lambda x_local, s_local: (X, S)
-
-    def sync():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn):
-        for _ in range(args.warmup):
-            fn()
-        sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            fn()
-        e1.record()
-        sync()
-        ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms[0])
-
-    coef_holder = {}
-
-    def full():
-        phi, coef = sh.phi(xl, sl)
-        coef_holder["coef"], coef_holder["phi"] = coef, phi
-
-    if emu > 1:
-        # one rank's histogram alone selects nothing (the all-reduce over the other ranks is missing):
-        # take the bandwidth from a full single-GPU pass, untimed, and time only the phi row block
-        med = ops.median_sq_dist(X)
-        coef_full = ops.bandwidth_from_median(med, N, 1.0, 0)
-
-        def full():  # noqa: F811
-            x_all, s_all = sh.gather(xl, sl)
-            out_ = ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef_full, rows=sh.rows)
-            coef_holder["coef"], coef_holder["phi"] = coef_full, out_["phi"][0, b:e]
-
-    ms_full = timed(full)
-    coef = coef_holder["coef"]
-    bw = float(coef[3])
-
-    def phi_only():
-        x_all, s_all = sh.gather(xl, sl)
-        ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=sh.rows)
-
-    ms_phi = timed(phi_only)
-    lib = L.load()
-    lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
-    full()
-    prof = L.profiler_report()
-    lib.dust_profiler_enable(0)
-    # roofline denominator: measured cuBLAS TF32 GEMM throughput on this GPU (8192^3, best of 5)
-    tf32_peak = None
-    if rank == 0:
-        torch.backends.cuda.matmul.allow_tf32 = True
-        A_ = torch.randn(8192, 8192, device=dev); B_ = torch.randn(8192, 8192, device=dev)
-        for _ in range(2):
-            A_ @ B_
-        best = 1e9
-        for _ in range(5):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); A_ @ B_; e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        tf32_peak = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
-        del A_, B_
-    out = None
-    if rank == 0:
-        fl_phi, fl_med = 6.0 * N * N * D / emu, 4.0 * N * N * D / emu
-        Dp, NV = (D + 7) // 8 * 8, (2 * D + 15) // 16 * 16
-        issued = 3 * 2.0 * N * N * (Dp + NV) / (world * emu)   # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
-        t_phi_kernel = prof.get("phi_tc_kernel", (0, 0.0))[1]
-        out = {"metric": "svgd_phi_large_n", "N": N, "d": D, "n_gpus": world, "emulated_world": emu, "rows": [b, e], "gather": args.gather,
-               "ms_phi_with_median": ms_full if emu == 1 else None, "ms_phi": ms_phi,
-               "algorithmic_tflops_phi": fl_phi / (ms_phi * 1e-3) / 1e12,
-               "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12 if emu == 1 else None, "bandwidth": bw,
-               "kernels_ms": {k: v[1] for k, v in prof.items()},
-               "roofline": None if not t_phi_kernel else {
-                   "kernel": "phi_tc_kernel", "bound": "tensor", "unit": "TFLOP/s",
-                   "achieved": issued / (t_phi_kernel * 1e-3) / 1e12, "peak": tf32_peak,
-                   "frac": issued / (t_phi_kernel * 1e-3) / 1e12 / tf32_peak,
-                   "peak_source": "cuBLAS TF32 GEMM 8192^3 measured in this run (torch.matmul, allow_tf32)",
-                   "note": "achieved counts the TF32 MMA FLOPs actually issued (3 per algorithmic product)"}}
-    if args.check:
-        from oracle import dust_oracle as O
-        idx = torch.arange(b, e, max(1, (e - b) // 64), device=dev)[:64]
-        Xc, Sc = X.cpu().double(), S.cpu().double()
-        g_, c1, c2 = [float(v) for v in coef[:3].cpu()]
-        xi = Xc[idx.cpu()]
-        d2 = ((xi * xi).sum(-1, keepdim=True) + (Xc * Xc).sum(-1)[None, :] - 2 * xi @ Xc.t()).clamp(min=0)
-        K = (-g_ * d2).exp()
-        ref = c1 * (K @ Sc) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xc)
-        got = coef_holder["phi"][idx - b].cpu().double()
-        err = float((got - ref).abs().max() / ref.abs().max())
-        if rank == 0:
-            out["rel_err_vs_float64_rows"] = err
-            if N <= 16384:
-                bw_ref, _ = O.bw_median(X.cpu())
-                out["bandwidth_ref"] = float(bw_ref)
+    out = phi_block(rank, world, dev, args.steps, args.warmup, args.particles, args.dim, args.gather, args.emulate_world)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

@@ -117,10 +117,12 @@ class MpfArgs(C.Structure):
 SYMBOLS = {
     "dust_rollout_workspace_bytes": (_sz, [C.POINTER(RolloutArgs)]),
     "dust_rollout_cost": (C.c_int, [C.POINTER(RolloutArgs), _p]),
+    "dust_rollout_plan": (C.c_int, [C.POINTER(RolloutArgs), C.POINTER(_i * 5)]),
     "dust_cost_reduce": (C.c_int, [C.POINTER(RolloutArgs), _p]),
     "dust_svmpc_step": (C.c_int, [C.POINTER(SvmpcStepArgs), _p]),
     "dust_adjoint_workspace_bytes": (_sz, [C.POINTER(AdjointArgs)]),
     "dust_rollout_adjoint": (C.c_int, [C.POINTER(AdjointArgs), _p]),
+    "dust_adjoint_plan": (C.c_int, [C.POINTER(AdjointArgs), C.POINTER(_i * 5)]),
     "dust_gmm_score": (C.c_int, [C.POINTER(GmmArgs), _p]),
     "dust_median_hist_pass": (C.c_int, [C.POINTER(MedianArgs), _i, _p]),
     "dust_median_select": (C.c_int, [C.POINTER(MedianArgs), _i, _p, _p]),

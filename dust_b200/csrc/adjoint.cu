@@ -358,6 +358,18 @@ extern "C" size_t dust_adjoint_workspace_bytes(const dust_adjoint_args* a) {
   return plan_adjoint(a).total;
 }
 
+extern "C" int dust_adjoint_plan(const dust_adjoint_args* a, int32_t plan[5]) {
+  DUST_REQUIRE(a != nullptr && plan != nullptr, DUST_ERR_INVALID_ARG, "dust_adjoint_plan: NULL argument");
+  int rc = validate_model(a->model);
+  if (rc) return rc;
+  DUST_REQUIRE(a->B > 0 && a->N > 0 && a->S > 0 && a->H > 0 && a->H <= 128, DUST_ERR_INVALID_ARG, "dust_adjoint_plan: bad sizes");
+  const AdjPlan pl = plan_adjoint(a);
+  plan[0] = pl.PC; plan[1] = pl.Pchunk; plan[2] = pl.tiles;
+  plan[3] = a->model->kind == DUST_MODEL_PARTICLE ? (a->H + 9) / 10 : 1;   // SEG = 10 in rollout_adjoint_kernel
+  plan[4] = a->H <= 32 ? 32 : (a->H <= 64 ? 64 : 128);
+  return DUST_OK;
+}
+
 extern "C" int dust_rollout_adjoint(const dust_adjoint_args* a, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_rollout_adjoint: args is NULL");

@@ -961,9 +961,28 @@ static RolloutPlan plan_rollout(const dust_rollout_args* a, bool single_chunk = 
   return pl;
 }
 
+// the fused per-instance kernel takes a call when it only asks for what that kernel produces
+static bool fused_path_ok(const dust_rollout_args* a, const RolloutPlan& pl, bool tail, bool reduce_only) {
+  const bool ranged = a->p_end > a->p_begin;
+  const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
+  const int HA = a->H * model_da(a->model->kind);
+  return fused_outputs_only && !ranged && !reduce_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.parts == 1 &&
+         HA <= 32 && a->N <= kFusedThreads && (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
+}
+
 }  // namespace dust
 
 using namespace dust;
+
+extern "C" int dust_rollout_plan(const dust_rollout_args* a, int32_t plan[5]) {
+  DUST_REQUIRE(a != nullptr && plan != nullptr, DUST_ERR_INVALID_ARG, "dust_rollout_plan: NULL argument");
+  int rc = validate_model(a->model);
+  if (rc) return rc;
+  const RolloutPlan pl = plan_rollout(a);
+  plan[0] = fused_path_ok(a, pl, false, false) ? 1 : 0;
+  plan[1] = pl.PC; plan[2] = pl.Pchunk; plan[3] = pl.NSUB; plan[4] = pl.parts;
+  return DUST_OK;
+}
 
 extern "C" size_t dust_rollout_workspace_bytes(const dust_rollout_args* a) {
   if (!a || a->B <= 0 || a->N <= 0 || a->S <= 0) return 0;
@@ -1027,9 +1046,7 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   const size_t grid_bytes = (kind == DUST_MODEL_PARTICLE && a->model->grid_bits)
                                 ? sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32) : 0;
   // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
-  const bool fused_outputs_only = !a->lik_weights && !a->mppi_weights && !a->mppi_delta && !a->mix && !a->states;
-  const bool fused_ok = fused_outputs_only && !ranged && !reduce_only && !a->sigma_weights && !a->ctrl_mat && a->theta && pl.parts == 1 && k.HA <= 32 && a->N <= kFusedThreads &&
-                        (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
+  const bool fused_ok = fused_path_ok(a, pl, tail != nullptr, reduce_only);
   DUST_REQUIRE(fused_ok || !tail, DUST_ERR_UNSUPPORTED,
                "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");
   if (fused_ok) {

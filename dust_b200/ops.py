@@ -26,7 +26,7 @@ def _ws(nbytes, device):
 def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param_tiling=L.PARAMS_BLOCKED,
                  likelihood=L.LIK_EXP_UTILITY, a_seq=None, pert=None, alpha=1.0, temperature=1.0,
                  want=("costs", "log_lik"), out=None, sigma_weights=None, ctrl_mat=None, ctrl_reg=0.0, p_range=None,
-                 reduce_only=False):
+                 reduce_only=False, plan_only=False):
     """K1.  noise [B,S,N,H,A]; theta [B,N,H,A] or None (noise = actions); params [B,P,dp] or None.
     `want` subset of {costs, log_lik, lik_weights, grad_lik, mppi_weights, mppi_delta, mix, states}.
     sigma_weights [P]: unscented-transform mode (params = the sigma points, disco.py:211-323);
@@ -34,6 +34,7 @@ def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param
     p_range (p0, p1): roll out only those parameter draws; `costs` is then their share of the mean
     (sum the shares over the ranks).  reduce_only: `out["costs"]` is complete, only the reductions after
     the costs run (dust_cost_reduce).
+    plan_only: launch nothing; return dict(fused, param_chunks, chunk, nsub, parts) -- how the library would run it.
     Returns a dict of CUDA tensors."""
     L.require_cuda()
     dev = noise.device
@@ -64,6 +65,10 @@ def rollout_cost(spec, state0, noise, theta=None, sigma=None, params=None, param
         setattr(a, k, L.ptr(out.get(k)) if k in want else None)
     if reduce_only:
         a.costs = L.ptr(out["costs"])
+    if plan_only:
+        plan = (C.c_int32 * 5)()
+        L.check(L.load().dust_rollout_plan(C.byref(a), C.byref(plan)))
+        return dict(zip(("fused", "param_chunks", "chunk", "nsub", "parts"), (int(v) for v in plan)))
     nbytes = L.load().dust_rollout_workspace_bytes(C.byref(a))
     ws = _ws(nbytes, dev)
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
@@ -114,7 +119,7 @@ def svmpc_step(spec, state0, noise, theta, sigma, mu, mix, inv_var, log_norm, ga
 
 
 def rollout_adjoint(spec, state0, noise, lik_weights, theta=None, sigma=None, params=None,
-                    param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0, p_range=None):
+                    param_tiling=L.PARAMS_BLOCKED, likelihood=L.LIK_EXP_UTILITY, alpha=1.0, p_range=None, plan_only=False):
     """K2.  Returns grad_theta [B,N,H,A] = d sum_n log_l_n / d theta (pathwise); with p_range (p0, p1) the
     share of those parameter draws (sum the shares over the ranks)."""
     L.require_cuda()
@@ -130,6 +135,10 @@ def rollout_adjoint(spec, state0, noise, lik_weights, theta=None, sigma=None, pa
     a.params, a.lik_weights, a.alpha = L.ptr(params), L.ptr(lik_weights), float(alpha)
     a.grad_theta, a.grad_params = L.ptr(g), None
     a.p_begin, a.p_end = (0, 0) if p_range is None else (int(p_range[0]), int(p_range[1]))
+    if plan_only:
+        plan = (C.c_int32 * 5)()
+        L.check(L.load().dust_adjoint_plan(C.byref(a), C.byref(plan)))
+        return dict(zip(("param_chunks", "chunk", "tiles", "segments", "max_h"), (int(v) for v in plan)))
     nbytes = L.load().dust_adjoint_workspace_bytes(C.byref(a))
     ws = _ws(nbytes, dev)
     a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes

@@ -149,6 +149,11 @@ typedef struct dust_rollout_args {
 
 size_t dust_rollout_workspace_bytes(const dust_rollout_args* args);
 int dust_rollout_cost(const dust_rollout_args* args, void* stream);
+/* How dust_rollout_cost will run these arguments (no launch): plan[0] = 1 if the fused per-instance kernel
+ * takes them, plan[1] = parameter chunks over grid.y, plan[2] = draws per chunk, plan[3] = thread groups
+ * that share one action tile (NSUB), plan[4] = partial cost rows per instance.  Tests use it to prove that
+ * a shape reaches the variant it is meant to exercise. */
+int dust_rollout_plan(const dust_rollout_args* args, int32_t plan[5]);
 /* The reductions that follow the costs, on their own: `costs` [B,S,N] is an INPUT (complete trajectory
  * costs, e.g. all-reduced shares); log_lik / lik_weights / grad_lik / mppi_weights / mppi_delta / mix are
  * written as dust_rollout_cost would (disco.py:380-393, likelihoods.py:113-135, svmpc.py:46-54).
@@ -214,6 +219,10 @@ typedef struct dust_adjoint_args {
 
 size_t dust_adjoint_workspace_bytes(const dust_adjoint_args* args);
 int dust_rollout_adjoint(const dust_adjoint_args* args, void* stream);
+/* plan[0] = parameter chunks, plan[1] = draws per chunk, plan[2] = trajectory tiles per instance,
+ * plan[3] = checkpointed segments of the reverse sweep (particle model; 1 = stored trajectory),
+ * plan[4] = compiled horizon bound (32 / 64 / 128). */
+int dust_adjoint_plan(const dust_adjoint_args* args, int32_t plan[5]);
 
 /* ------------------------------------------------------------------------------------------
  * K3  Gaussian-mixture prior: log-density and score

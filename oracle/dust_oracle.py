@@ -309,7 +309,7 @@ def pathwise_lik_grad_autograd(model, state, theta, eps, sigma, params, log_spac
 
 
 def pathwise_lik_grad_adjoint(model, state, theta, eps, sigma, params, log_space, alpha,
-                              want_param_grad=False):
+                              want_param_grad=False, weights=None):
     """Hand-derived reverse-time adjoint of rollout+cost (SURVEY.md §9 "Adjoint equations"),
     the CPU statement of what the CUDA adjoint kernels compute.  Forward: disco.py:139-209,
     294-346; clamp sub-gradients are inclusive (torch.clamp backward, H18); floor/collision
@@ -318,7 +318,9 @@ def pathwise_lik_grad_adjoint(model, state, theta, eps, sigma, params, log_space
     actions = theta + sigma * eps
     states = rollout(model, state, actions, params, log_space)  # [P,S,N,H+1,ds]
     costs = trajectory_costs(model, states, actions)
-    w = torch.softmax(-alpha * costs, dim=0)  # d log_l_n / d C[s,n] = -alpha w[s,n]
+    # d log_l_n / d C[s,n] = -alpha w[s,n]; `weights` holds them fixed (the adjoint is linear in them: tests feed
+    # the device's own soft-min weights so that cost rounding inside exp(-alpha C) does not dominate)
+    w = torch.softmax(-alpha * costs, dim=0) if weights is None else weights.to(costs.dtype)
     P = states.shape[0]
     dt = states.dtype
     a = actions.unsqueeze(0).expand(P, -1, -1, -1, -1)

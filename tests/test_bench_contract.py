@@ -59,3 +59,16 @@ def test_device_arm_line():
     c = d["clocks"]
     assert "sm_mhz" in c and "sm_max_mhz" in c and isinstance(c["reasons"], list)
     assert "l2_policy" in d["config"]
+    # the other half of BASELINE's metric rides in the same line: large-N phi with its own roofline, clocks and in-run checks
+    ph = d["phi"]
+    assert ph["N"] == 65536 and ph["d"] == 40 and ph["ms_phi"] > 0 and ph["ms_phi_with_median"] > ph["ms_phi"]
+    pr = ph["roofline"]
+    assert pr["kernel"] == "phi_tc_kernel" and pr["bound"] == "tensor" and abs(pr["frac"] - pr["achieved"] / pr["peak"]) < 1e-9
+    assert pr["frac_vs_inrun_cublas_tf32"] > 0 and "sm_mhz" in ph["clocks"]
+    assert ph["rel_err_vs_float64_rows"] <= 1e-4 and ph["median"]["ulp_distance"] <= 4
+    cf = d["configs"]
+    for name in ("pendulum_demo", "particle_demo", "dual_stress"):
+        assert cf[name]["device_ms_per_dual_step"] > 0 and cf[name]["wall_ms_per_dual_step"] > 0, name
+    for name in ("pendulum_demo", "particle_demo"):
+        assert cf[name]["drop_in_classes"]["wall_ms_per_dual_step"] > 0
+        assert cb["configs"][name]["ms_per_dual_step"] > 0

@@ -1,0 +1,221 @@
+"""Round-2 hardware parity: the shapes and paths the first suite never reached on a B200 --
+N = 65536 phi / median (BASELINE configs[3]), the non-SGD optimiser path and `fast_pred=False`
+through the `SVMPC` class (svgd.py:115, svmpc.py:128-140), the NSUB = 2 / 4 rollout variants and the
+five-segment checkpointed adjoint of the dual-stress shape (configs[4], scaled)."""
+import functools
+import math
+import time
+
+import pytest
+import torch
+
+from oracle import dust_oracle as O
+from tests.test_gpu_api import ENV, FixedParams, demo_inst_cost, demo_term_cost
+from tests.util import RTOL_COST, RTOL_PHI, golden_grid, load, record_parity, rel_elem, rel_max
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def cu(t):
+    return None if t is None else torch.as_tensor(t, dtype=torch.float32).to(DEV).contiguous()
+
+
+def ulp_distance(a, b):
+    """distance in float32 representable steps between two positive floats"""
+    ia = int(torch.tensor([a], dtype=torch.float32).view(torch.int32)[0])
+    ib = int(torch.tensor([b], dtype=torch.float32).view(torch.int32)[0])
+    return abs(ia - ib)
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[3] at its full size
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cloud", ["isotropic", "anisotropic"])
+def test_phi_and_median_at_65536(cloud):
+    """N = 65536, d = 40 (SURVEY 8(d) cfg 4): the exact median against the tiled radix oracle, sampled phi rows
+    against float64 (the reference itself cannot run here: K alone is 17 GB).  O is drained from TMEM every 32
+    column tiles (svgd_tc.cu), an accumulation-depth effect that only shows at this size."""
+    from dust_b200 import _lib as L
+    from dust_b200 import ops
+
+    N, D = 65536, 40
+    g = torch.Generator().manual_seed(0 if cloud == "isotropic" else 1)
+    X = torch.randn(N, D, generator=g)
+    if cloud == "anisotropic":
+        X = X * (torch.arange(1, D + 1).float() / 10)
+    S = -X
+    x = cu(X)
+    lib = L.load()
+    lib.dust_profiler_reset()
+    lib.dust_profiler_enable(1)
+    ws = ops.MedianWorkspace(N, D, x.device)
+    med = ops.median_sq_dist(x, ws=ws)
+    coef = ops.bandwidth_from_median(med, N, 1.0, 0)
+    out = ops.svgd_phi(x.unsqueeze(0), cu(S).unsqueeze(0), gamma_dev=coef)
+    prof = L.profiler_report()
+    lib.dust_profiler_enable(0)
+    assert "phi_tc_kernel" in prof and "median_tc_kernel" in prof and "phi_large_kernel" not in prof
+    assert int(ws.selected[5]) == 1, "a well-behaved cloud must not need the radix fallback"
+    med_dev = float(med[0])
+    robust = float(ops.median_sq_dist(x, allow_fast=False)[0])      # SIMT two-pass radix select, own distance code
+    t0 = time.time()
+    med_ref = float(O.median_sq_dist_tiled(X))                       # exact rank over torch's float32 distances
+    t_oracle = time.time() - t0
+    u_ref, u_rob = ulp_distance(med_dev, med_ref), ulp_distance(med_dev, robust)
+    record_parity(f"median N=65536 {cloud}", device=med_dev, oracle=med_ref, radix_simt=robust, ulp_vs_oracle=u_ref,
+                  ulp_vs_radix_simt=u_rob, oracle_seconds=t_oracle)
+    # three exact rank selections over distances rounded three different ways (3xTF32 Gram, fp32 FMA chain,
+    # MKL sgemm): the order statistic of 4.3e9 values moves by far less than one distance rounding
+    assert u_ref <= 4 and u_rob <= 4, (med_dev, med_ref, robust)
+    gam, c1, c2, bw = [float(v) for v in coef.cpu()]
+    bw_ref = max(math.sqrt(0.5 * med_ref) / math.log(N + 1), 1e-5)   # svgd.py:42-52
+    assert abs(bw - bw_ref) <= 1e-6 * bw_ref
+    # phi rows: 256 of them, spread over every row tile position, against float64 over all N columns
+    idx = torch.cat([torch.arange(0, N, N // 128), torch.randint(0, N, (128,), generator=g)])
+    Xd, Sd = X.double(), S.double()
+    xi = Xd[idx]
+    d2 = ((xi * xi).sum(-1, keepdim=True) + (Xd * Xd).sum(-1)[None, :] - 2 * xi @ Xd.t()).clamp(min=0)
+    d2[torch.arange(len(idx)), idx] = 0.0
+    K = (-gam * d2).exp()
+    ref = c1 * (K @ Sd) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xd)
+    got = out["phi"][0].cpu()[idx].double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    err_rows = float(((got - ref).norm(dim=1) / ref.norm(dim=1)).max())
+    record_parity(f"phi N=65536 {cloud}", err_vs_float64_max=err, err_vs_float64_rowwise=err_rows, rtol=RTOL_PHI)
+    assert err <= RTOL_PHI and err_rows <= RTOL_PHI
+    # one rank's row block of 8 equals the same rows of the full call to rounding
+    blk = ops.svgd_phi(x.unsqueeze(0), cu(S).unsqueeze(0), gamma_dev=coef, rows=(3 * N // 8, 4 * N // 8))["phi"][0]
+    e_blk = rel_max(blk[3 * N // 8: 4 * N // 8].cpu(), out["phi"][0, 3 * N // 8: 4 * N // 8].cpu())
+    record_parity(f"phi N=65536 {cloud} row block 3/8", err_vs_full_call=e_blk)
+    assert e_blk <= 2e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# non-SGD optimisers and fast_pred=False through the SVMPC class, on the device
+# ---------------------------------------------------------------------------------------------
+def build_svmpc(d, n_steps=1, **opt):
+    from dust_b200.controllers.disco import MultiDISCO
+    from dust_b200.inference.likelihoods import ExponentiatedUtility
+    from dust_b200.inference.svgd import get_gmm
+    from dust_b200.inference.svmpc import SVMPC
+    from dust_b200.kernels.base_kernels import RBFKernel
+    from dust_b200.models.pendulum import PendulumModel
+
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    N, H, A = d["theta_init"].shape
+    S = d["t0_eps"].shape[1]
+    P = d["t0_params"].shape[1]
+    pv = float(d["prior_var"])
+    ctrl = MultiDISCO(observation_space=model.observation_space, action_space=model.action_space, hz_len=H, n_policies=N,
+                      action_samples=S, params_samples=P, temperature=1.0, a_cov=torch.diag(d["sigma"] ** 2),
+                      inst_cost_fn=demo_inst_cost, term_cost_fn=demo_term_cost, params_sampling=True)
+    prior = get_gmm(d["mu_init"], torch.ones(N), pv * torch.eye(A))
+    lik = ExponentiatedUtility(1.0, n_samples=S, controller=ctrl, model=model)
+    return SVMPC(init_particles=d["theta_init"].clone(), prior=prior, likelihood=lik, kernel=RBFKernel(), n_particles=N,
+                 bw_scale=1.0, n_steps=n_steps, weighted_prior=False, **opt)
+
+
+@pytest.mark.parametrize("name,opt", [("svmpc_pendulum_adam", dict(optimizer_class=torch.optim.Adam)),
+                                      ("svmpc_pendulum_momentum", dict(optimizer_class=torch.optim.SGD, momentum=0.9))])
+def test_svmpc_class_with_torch_optimizers_on_device(name, opt):
+    """The reference stepping Adam (its default, svgd.py:115) and momentum SGD, two SVGD steps per control step:
+    phi from the kernel, `torch.optim` on the device particles, optimiser state renewed after every roll."""
+    d = load(name)
+    sv = build_svmpc(d, n_steps=2, lr=float(d["lr"]), **opt)
+    assert sv._core._make_opt is not None, "a non-plain optimiser must not take the fused SGD update"
+    worst = {}
+    for t in range(int(d["n_ctrl"])):
+        state = d[f"t{t}_state"]
+        for k in range(2):
+            sv.step(state, FixedParams(d[f"t{t}_params"][k], torch.Size([2])), eps=d[f"t{t}_eps"][k])
+        e_c = rel_elem(sv.likelihood.last_costs.cpu(), d[f"t{t}_costs"])
+        e_t1 = rel_max(sv.theta.cpu(), d[f"t{t}_theta1"])
+        a_seq, p_w = sv.forward(state, FixedParams(d[f"t{t}_params"][1], torch.Size([2])))
+        e_a, e_t2 = rel_max(a_seq.cpu(), d[f"t{t}_a_seq"]), rel_max(sv.theta.cpu(), d[f"t{t}_theta2"])
+        e_w = float((p_w.cpu() - d[f"t{t}_p_weights"]).abs().max())
+        for key, v in (("costs", e_c), ("theta1", e_t1), ("a_seq", e_a), ("theta2", e_t2), ("p_weights_abs", e_w)):
+            worst[key] = max(worst.get(key, 0.0), v)
+        assert int(sv.i_star) == int(d[f"t{t}_i_star"])
+        # free running over three control steps: the inputs of later steps carry earlier rounding
+        assert e_c <= 2e-4 and e_t1 <= 2e-4 and e_a <= 2e-4 and e_t2 <= 2e-4 and e_w <= 1e-3, (t, e_c, e_t1, e_a, e_t2, e_w)
+    record_parity(f"SVMPC class {name}", **worst)
+
+
+def test_svmpc_class_fresh_likelihood_weights_on_device():
+    """get_weights(fast_pred=False) / forward(fast_pred=False), svmpc.py:128-140: the likelihood sampled again at the
+    updated particles (three noise + parameter draws per control step)."""
+    d = load("svmpc_pendulum_slow_pred")
+    sv = build_svmpc(d, n_steps=1, optimizer_class=torch.optim.SGD, lr=float(d["lr"]))
+    worst = {}
+    for t in range(int(d["n_ctrl"])):
+        state, eps, params = d[f"t{t}_state"], d[f"t{t}_eps"], d[f"t{t}_params"]
+        pd = [FixedParams(params[k], torch.Size([2])) for k in range(3)]
+        sv.optimize(state, pd[0], eps=eps[0])
+        peek = sv.get_weights(state, pd[1], fast_pred=False, eps=eps[1])
+        e_peek = float((peek.cpu() - d[f"t{t}_peek"]).abs().max())
+        a_seq, p_w = sv.forward(state, pd[2], fast_pred=False, eps=eps[2])
+        e_c = rel_elem(sv.likelihood.last_costs.cpu(), d[f"t{t}_costs_fwd"])
+        e_w = float((p_w.cpu() - d[f"t{t}_p_weights"]).abs().max())
+        e_a, e_t2 = rel_max(a_seq.cpu(), d[f"t{t}_a_seq"]), rel_max(sv.theta.cpu(), d[f"t{t}_theta2"])
+        for key, v in (("peek_abs", e_peek), ("costs_fwd", e_c), ("p_weights_abs", e_w), ("a_seq", e_a), ("theta2", e_t2)):
+            worst[key] = max(worst.get(key, 0.0), v)
+        assert e_peek <= 2e-3 and e_w <= 2e-3 and e_c <= 2e-4 and e_a <= 5e-4 and e_t2 <= 5e-4, (t, e_peek, e_w, e_c, e_a, e_t2)
+    record_parity("SVMPC class svmpc_pendulum_slow_pred", **worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# configs[4], scaled: the variants only the dual-stress shape selects
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def particle_env():
+    from dust_b200.models.particle import Particle
+
+    part = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+    return dict(spec=part.device_spec(part.default_inst_cost, part.default_term_cost, DEV), cfg=O.ParticleCfg(golden_grid()))
+
+
+@pytest.mark.parametrize("B,nsub", [(8, 2), (16, 4)])
+def test_stress_shape_variants_are_reached_and_match_the_oracle(particle_env, B, nsub):
+    """Particle model, H = 50 (H*A = 100: a 51 KB action tile, three CTAs per SM), 296 parameter draws over 1024
+    trajectories per instance: the plan must select `rollout_cost_kernel<.., NSUB = 2 | 4>` (thread groups sharing one
+    action tile) and the adjoint its five checkpointed segments of ten steps; costs and the pathwise gradient are
+    then compared with the oracle on the first and last instance."""
+    from dust_b200 import ops
+
+    spec, cfg = particle_env["spec"], particle_env["cfg"]
+    torch.manual_seed(100 + B)
+    S, N, H, P, A = 32, 32, 50, 296, 2
+    state = torch.tensor([-9.0, -9.0, 0.0, 0.0]).repeat(B, 1) + torch.randn(B, 4) * torch.tensor([2.0, 2.0, 0.5, 0.5])
+    theta = torch.randn(B, N, H, A) * 3
+    eps = torch.randn(B, S, N, H, A)
+    sigma = torch.tensor([5.0, 5.0])
+    params = (torch.randn(B, P, 1) * 0.1 + math.log(2.0)).exp()
+    alpha = 1e-5          # dense soft-min weights: every rollout is reversed by the adjoint
+    kw = dict(theta=cu(theta), sigma=cu(sigma), params=cu(params), param_tiling=0, alpha=alpha)
+    want = ("costs", "log_lik", "lik_weights", "grad_lik")
+    plan = ops.rollout_cost(spec, cu(state), cu(eps), want=want, plan_only=True, **kw)
+    assert plan["nsub"] == nsub and plan["fused"] == 0 and plan["chunk"] >= 2 * nsub, plan
+    out = ops.rollout_cost(spec, cu(state), cu(eps), want=want, **kw)
+    aplan = ops.rollout_adjoint(spec, cu(state), cu(eps), out["lik_weights"], plan_only=True, **kw)
+    assert aplan["segments"] == 5 and aplan["max_h"] == 64, aplan
+    grad = ops.rollout_adjoint(spec, cu(state), cu(eps), out["lik_weights"], **kw)
+    model = O.Model("particle", cfg)
+    worst = {}
+    for b in (0, B - 1):
+        acts = theta[b] + sigma * eps[b]
+        ref = O.disco_forward(model, state[b], acts, params[b])
+        e_c = rel_elem(out["costs"][b].cpu(), ref["costs"])
+        assert e_c <= RTOL_COST, (b, e_c)
+        costs = out["costs"][b].cpu().double()
+        g_dev = O.analytic_lik_grad(costs, acts.double(), theta[b].double(), sigma.double(), alpha)
+        e_g = rel_max(out["grad_lik"][b].cpu(), g_dev)
+        assert e_g <= 1e-5, (b, e_g)
+        # pathwise gradient with the device's soft-min weights held fixed (the adjoint is linear in them)
+        g64 = O.pathwise_lik_grad_adjoint(model, state[b].double(), theta[b].double(), eps[b].double(), sigma.double(),
+                                          params[b].double(), False, alpha, weights=out["lik_weights"][b].cpu().double())[0]
+        e_p = rel_max(grad[b].cpu(), g64)
+        assert e_p <= RTOL_PHI, (b, e_p)
+        for key, v in (("costs", e_c), ("grad_lik_vs_own_costs", e_g), ("pathwise_grad", e_p)):
+            worst[key] = max(worst.get(key, 0.0), v)
+    record_parity(f"stress-shape particle H=50 P=296 NSUB={nsub}", **worst)

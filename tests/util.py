@@ -42,8 +42,23 @@ def assert_close_to_reference(actual, golden, truth64, rtol, what=""):
     ref_noise = rel_max(golden, truth64)
     err_truth = rel_max(actual, truth64)
     err_gold = rel_max(actual, golden)
+    record_parity(what or "unnamed", err_truth=err_truth, err_gold=err_gold, ref_noise=ref_noise, rtol=rtol)
     assert err_truth <= rtol or err_gold <= rtol, (
         f"{what}: |actual-truth64|={err_truth:.3e}, |actual-golden|={err_gold:.3e}, "
         f"reference noise |golden-truth64|={ref_noise:.3e}, rtol={rtol:.1e}")
     assert err_gold <= rtol + 2.0 * ref_noise, (
         f"{what}: |actual-golden|={err_gold:.3e} > rtol + 2*refnoise ({ref_noise:.3e})")
+
+
+def record_parity(case, **values):
+    """Append the observed errors of a parity check to gpurun_out/parity_table.jsonl (scratch; summarised into
+    profiles/r2_parity_table.md by profiles/parity_table.py).  Never fails a test."""
+    import json
+
+    try:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        os.makedirs(os.path.join(root, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(root, "gpurun_out", "parity_table.jsonl"), "a") as f:
+            f.write(json.dumps({"case": case, **{k: (float(v) if isinstance(v, (int, float)) else v) for k, v in values.items()}}) + "\n")
+    except Exception:
+        pass
