@@ -728,6 +728,357 @@ __global__ void __launch_bounds__(kFusedThreads / TPT, TPT == 2 ? 5 : DUST_FUSED
 }
 
 // ---------------------------------------------------------------------------------------
+// Second generation of the fused per-instance kernel (packed pendulum path; H*A a multiple of 4, N <= 32).
+//
+// What limited the first one (ncu, profiles/r1_fused_instance_kernel_ncu.md): 96 registers -- 20 of them the
+// per-thread score-row accumulators -- held an SM at 20 warps; every 256-row tile ended in a CTA-wide barrier;
+// and the tail (one warp per particle, lanes over D, a shuffle reduction per pair) cost 19 % of the
+// instructions for a few thousand multiply-adds.  Here
+//   * a WARP owns its tiles: 2*La consecutive rows (La = 32/N * N lanes, rows l and l + La of a lane share
+//     the policy l % N), fetched by one TMA bulk copy that the warp which frees a buffer issues itself and
+//     whose arrival only the consuming warp waits for (an mbarrier per buffer) -- no CTA barrier in the loop.
+//     NBUF >= 4 buffers rotate over the CTA's tile sequence: tile t lives in buffer t % NBUF and is requested
+//     when tile t - NBUF retires, i.e. (NBUF - 4) tile-quarters ahead of its use;
+//   * the weighted score row of a lane lives in shared memory (conflict-free 16-byte rows) and is updated for
+//     both trajectories of the lane at once on the packed pipe: no accumulator survives the rollout loop;
+//   * the tail works on (particle, centre) pairs and (particle, dimension) items with all threads.
+// Costs are produced by the same pendulum_pair_cost_sum / trajectory_cost_sum calls as before: bit-identical.
+// ---------------------------------------------------------------------------------------
+constexpr int kWarpKernelThreads = 128;
+constexpr int kWarpKernelWarps = kWarpKernelThreads / 32;
+
+struct WarpKernelSmem {
+  int stride, thst, tile_floats, off_tile, off_acc, off_th, off_tail, off_bar, total_bytes;
+};
+__host__ __device__ inline WarpKernelSmem warp_kernel_smem(int N, int HA, int nbuf) {
+  WarpKernelSmem L;
+  L.stride = padded_stride(HA);
+  L.thst = (HA + 3) & ~3;
+  const int La = (32 / N) * N;
+  L.tile_floats = 2 * La * L.stride;
+  // tail scratch (gl, sc, nw [N][thst]; Lg, Kx [N][N]; ll, lmix, logw, lse [N]; reductions 3 x [threads]) lives in
+  // the tile ring, which is dead once every warp has left the rollout loop
+  const int tail = 3 * N * L.thst + 2 * N * N + 4 * N + 3 * kWarpKernelThreads;
+  const int ring = nbuf * L.tile_floats;
+  L.off_tile = 0;                                              // [nbuf][2*La][stride]
+  L.off_tail = 0;
+  L.off_acc = ((ring > tail ? ring : tail) + 3) & ~3;          // [threads][stride] weighted score rows
+  L.off_th = L.off_acc + kWarpKernelThreads * L.stride;        // [N][thst] policy means
+  L.off_bar = (L.off_th + N * L.thst + 1) & ~1;                // 8-byte aligned mbarriers
+  L.total_bytes = 4 * L.off_bar + 8 * nbuf;
+  return L;
+}
+
+#if DUST_PEND_PAIR
+__global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const RolloutKParams k, const FusedOut o, const int nbuf) {
+  extern __shared__ __align__(16) float smem[];
+  const int HA = k.HA, N = k.N;
+  const WarpKernelSmem L = warp_kernel_smem(N, HA, nbuf);
+  const int stride = L.stride, thst = L.thst;
+  const int La = (32 / N) * N, WT = 2 * La;
+  float* tiles = smem + L.off_tile;
+  float* th_s = smem + L.off_th;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  const long long inst = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool active = lane < La;
+  const int slot = warp * La + lane;             // dense index of an active lane; slot % N == lane % N
+  const int n = lane % N;
+  float* acc_row = smem + L.off_acc + (active ? slot : 0) * stride;
+  const float* __restrict__ noise = k.noise + inst * (long long)k.SN * HA;
+  const int ntiles = (k.SN + WT - 1) / WT;
+  const bool bulk = stride == HA;                // unpadded rows: a tile is one contiguous block
+
+  // request tile t (rows [t*WT, ..)) into buffer t % nbuf; called by a whole warp
+  auto request = [&](int t) {
+    const int j0 = t * WT;
+    const int rows = min(WT, k.SN - j0);
+    float* dst = tiles + (t % nbuf) * L.tile_floats;
+    uint64_t* bar = &full_bar[t % nbuf];
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's reads of the buffer are done
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)rows * (uint32_t)HA * 4u);
+    if (bulk) {
+      if (lane == 0) bulk_g2s(dst, noise + (long long)j0 * HA, (uint32_t)rows * (uint32_t)HA * 4u, bar);
+    } else {
+      __syncwarp();
+      for (int r = lane; r < rows; r += 32) bulk_g2s(dst + r * stride, noise + (long long)(j0 + r) * HA, (uint32_t)HA * 4u, bar);
+    }
+  };
+  if (tid == 0) {
+    for (int b = 0; b < nbuf; ++b) mbar_init(&full_bar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // the first nbuf tiles, spread over the warps
+  for (int t = warp; t < min(nbuf, ntiles); t += kWarpKernelWarps) request(t);
+  for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
+    const int nn = e / HA;
+    th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
+  }
+  if (active)
+    for (int c = 0; c < stride; c += 4) *reinterpret_cast<float4*>(acc_row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const float sg0 = k.sigma[0];
+  const bool small = small_angle_horizon<DUST_MODEL_PENDULUM>(k, inst);
+  const float* __restrict__ th_row = th_s + n * thst;
+  const float inv_P = 1.0f / (float)k.P;
+  (void)inv_P;
+
+  float m_run = INFINITY, z_run = 0.f, c_run = 0.f;
+  for (int t = warp; t < ntiles; t += kWarpKernelWarps) {
+    const int j0 = t * WT;
+    const int rows = min(WT, k.SN - j0);
+    const float* tile = tiles + (t % nbuf) * L.tile_floats;
+    mbar_wait(&full_bar[t % nbuf], (uint32_t)(t / nbuf) & 1u);
+    const int ra = lane, rb = lane + La;
+    if (active && ra < rows) {
+      const float* __restrict__ rowA = tile + ra * stride;
+      const float* __restrict__ rowB = tile + rb * stride;
+      const int nv = (rb < rows) ? 2 : 1;
+      float csA, csB = 0.f;
+      if (small && nv == 2) {
+        const float2 cs = pendulum_pair_cost_sum(k, rowA, rowB, inst, j0 + ra, j0 + rb, th_row, sg0);
+        csA = cs.x;
+        csB = cs.y;
+      } else {
+        // ragged last tile, or an angle beyond the fast range: the scalar step, same arithmetic (one copy of the code)
+        csA = 0.f;
+#pragma unroll 1
+        for (int q = 0; q < nv; ++q) {
+          const float* __restrict__ row = q ? rowB : rowA;
+          const int jj = j0 + (q ? rb : ra);
+          const float v = small ? trajectory_cost_sum<DUST_MODEL_PENDULUM, true, false, true>(k, row, nullptr, inst, jj, 0, k.P, th_row, sg0, sg0)
+                                : trajectory_cost_sum<DUST_MODEL_PENDULUM, false, false, true>(k, row, nullptr, inst, jj, 0, k.P, th_row, sg0, sg0);
+          if (q) csB = v; else csA = v;
+        }
+      }
+      const float costA = (k.P == 1) ? csA : csA / (float)k.P;
+      const float costB = (nv == 2) ? ((k.P == 1) ? csB : csB / (float)k.P) : INFINITY;
+      if (o.costs) {
+        o.costs[inst * k.SN + j0 + ra] = costA;
+        if (nv == 2) o.costs[inst * k.SN + j0 + rb] = costB;
+      }
+      c_run += costA;
+      if (nv == 2) c_run += costB;
+      // online soft-min of this lane's rows relative to its running minimum: both new rows are folded at once
+      const float m_new = fminf(m_run, fminf(costA, costB));
+      const float scale = expf(-o.alpha * (m_run - m_new));          // 0 on the first tile (m_run = inf), 1 if the minimum stands
+      const float eA = expf(-o.alpha * (costA - m_new));
+      const float eB = expf(-o.alpha * (costB - m_new));             // 0 for a missing row (cost = inf)
+      m_run = m_new;
+      z_run = z_run * scale + (eA + eB);
+      if (scale != 1.f || eA > 1e-30f || eB > 1e-30f) {              // else: invisible in float32
+        const float2 sc2 = bc2(scale), ea2 = bc2(eA), eb2 = bc2(eB);
+        for (int c = 0; c < HA; c += 4) {
+          const float4 a4 = *reinterpret_cast<const float4*>(acc_row + c);
+          const float4 va = *reinterpret_cast<const float4*>(rowA + c);
+          const float4 vb = (nv == 2) ? *reinterpret_cast<const float4*>(rowB + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float2 lo = fma2(make_float2(a4.x, a4.y), sc2, fma2(ea2, make_float2(va.x, va.y), mul2(eb2, make_float2(vb.x, vb.y))));
+          const float2 hi = fma2(make_float2(a4.z, a4.w), sc2, fma2(ea2, make_float2(va.z, va.w), mul2(eb2, make_float2(vb.z, vb.w))));
+          *reinterpret_cast<float4*>(acc_row + c) = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+      }
+    }
+    __syncwarp();
+    if (t + nbuf < ntiles) request(t + nbuf);    // this buffer's next occupant (consumed by warp (t + nbuf) % 4)
+  }
+
+  // ---- combine the G = 4*La/N lanes that share a policy -----------------------------------------------
+  float* tail_s = smem + L.off_tail;
+  float* gl_s = tail_s;                    // [N][thst] likelihood gradient
+  float* sc_s = gl_s + N * thst;           // [N][thst] score = grad_lik + grad_prior
+  float* nw_s = sc_s + N * thst;           // [N][thst] updated particles
+  float* Lg_s = nw_s + N * thst;           // [N][N] mixture logits / responsibilities
+  float* Kx_s = Lg_s + N * N;              // [N][N] kernel matrix among the particles
+  float* ll_s = Kx_s + N * N;              // [N] log-likelihood
+  float* lmix_s = ll_s + N;                // [N] log mixture weights
+  float* logw_s = lmix_s + N;              // [N]
+  float* lse_s = logw_s + N;               // [N]
+  float* red_m = lse_s + N;                // [threads]
+  float* red_z = red_m + kWarpKernelThreads;
+  float* red_c = red_z + kWarpKernelThreads;
+  const int TNT = kWarpKernelWarps * La;   // lanes that own trajectories
+  __syncthreads();                         // every warp is done with the tile ring: the scratch above may overwrite it
+  if (active) { red_m[slot] = m_run; red_c[slot] = c_run; }
+  __syncthreads();
+  const int G = TNT / N;
+  float m_n = INFINITY;
+  for (int g = 0; g < G; ++g) m_n = fminf(m_n, red_m[g * N + n]);
+  const float own = (active && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) : 0.f;
+  if (active) red_z[slot] = z_run * own;
+  __syncthreads();
+  float z_n = 0.f, c_n = 0.f;
+  for (int g = 0; g < G; ++g) z_n += red_z[g * N + n];
+  if (tid < N) {
+    for (int g = 0; g < G; ++g) c_n += red_c[g * N + n];
+    const float ll = (o.likelihood == DUST_LIK_EXP_UTILITY) ? (-o.alpha * m_n + logf(z_n)) - logf((float)k.S)   // likelihoods.py:133-135
+                                                            : -o.alpha * (c_n / (float)k.S);                    // likelihoods.py:119
+    if (o.log_lik) o.log_lik[inst * N + tid] = ll;
+    ll_s[tid] = ll;
+  }
+  if (o.grad_lik || o.tail.enabled) {
+    // (a - theta)/sigma^2 = eps/sigma: the factor 1/sigma is applied once per row here
+    const float f = (own / z_n) * ((1.0f / (sg0 * sg0)) * sg0);
+    if (active)
+      for (int c = 0; c < HA; c += 4) {
+        float4 v = *reinterpret_cast<float4*>(acc_row + c);
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        *reinterpret_cast<float4*>(acc_row + c) = v;
+      }
+    __syncthreads();
+    const float* accs = smem + L.off_acc;
+    for (int col = tid; col < N * HA; col += kWarpKernelThreads) {
+      const int n2 = col / HA, c = col - n2 * HA;
+      float sacc = 0.f;
+      for (int g = 0; g < G; ++g) sacc += accs[(g * N + n2) * stride + c];
+      if (o.grad_lik) o.grad_lik[inst * (long long)N * HA + col] = sacc;
+      gl_s[n2 * thst + c] = sacc;
+    }
+  }
+  if (!o.tail.enabled) return;
+
+  // ------------------------------------------------------------------------------------
+  // tail (svmpc.py:38-95, 128-200): prior score, phi, SGD step, weights / argmax / shift, on pairs and items
+  // ------------------------------------------------------------------------------------
+  const TailParams& t = o.tail;
+  const float* mu_g = t.mu ? t.mu + inst * (long long)N * HA : nullptr;
+  if (warp == 0) warp_log_mix(t.mix ? t.mix + inst * N : nullptr, N, lmix_s);
+  __syncthreads();
+  // (i, k): iv-weighted distance to centre k (GMM logits) and the kernel among the particles
+  for (int p = tid; p < N * N; p += kWarpKernelThreads) {
+    const int i = p / N, kk = p - i * N;
+    const float* xi = th_s + i * thst;
+    const float* xk = th_s + kk * thst;
+    float q = 0.f, dxx = 0.f;
+    if (t.aliased) {
+      for (int d = 0; d < HA; ++d) {
+        const float df = xi[d] - xk[d];
+        const float d2 = df * df;
+        dxx += d2;
+        q = fmaf(d2, __ldg(t.inv_var + d), q);
+      }
+    } else {
+      const float* ck = mu_g + kk * HA;
+      for (int d = 0; d < HA; ++d) {
+        const float df = xi[d] - xk[d];
+        dxx = fmaf(df, df, dxx);
+        const float dc = xi[d] - __ldg(ck + d);
+        q = fmaf(dc * dc, __ldg(t.inv_var + d), q);
+      }
+    }
+    Lg_s[p] = lmix_s[kk] - 0.5f * q;
+    Kx_s[p] = expf(-t.gamma * dxx);
+  }
+  __syncthreads();
+  // responsibilities r_ik = softmax_k(logits): a warp per particle, lanes over the centres (N <= 32)
+  for (int i = warp; i < N; i += kWarpKernelWarps) {
+    const float l = lane < N ? Lg_s[i * N + lane] : -INFINITY;
+    const float mx = warp_max(l);
+    const float e = lane < N ? expf(l - mx) : 0.f;
+    const float z = warp_sum(e);
+    if (lane < N) Lg_s[i * N + lane] = e / z;
+  }
+  __syncthreads();
+  // (i, d): prior score, total score
+  for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
+    const int i = e / HA, d = e - i * HA;
+    const float xi = th_s[i * thst + d];
+    float a = 0.f;
+    if (t.aliased) {
+      for (int kk = 0; kk < N; ++kk) a = fmaf(Lg_s[i * N + kk], th_s[kk * thst + d] - xi, a);
+    } else {
+      for (int kk = 0; kk < N; ++kk) a = fmaf(Lg_s[i * N + kk], __ldg(mu_g + kk * HA + d) - xi, a);
+    }
+    sc_s[i * thst + d] = gl_s[i * thst + d] + a * __ldg(t.inv_var + d);
+  }
+  __syncthreads();
+  // (i, d): phi_i = sum_j K_ij (c1 score_j + c2 (x_i - x_j)); SGD step
+  for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
+    const int i = e / HA, d = e - i * HA;
+    const float xi = th_s[i * thst + d];
+    float accp = 0.f;
+    for (int j = 0; j < N; ++j) accp = fmaf(Kx_s[i * N + j], fmaf(t.c2, xi - th_s[j * thst + d], t.c1 * sc_s[j * thst + d]), accp);
+    const float nv = xi + t.lr * accp;
+    nw_s[i * thst + d] = nv;
+    const long long oidx = (inst * N + i) * (long long)HA + d;
+    if (t.phi) t.phi[oidx] = accp;
+    if (t.theta_out) t.theta_out[oidx] = nv;
+  }
+  if (!t.do_forward) return;
+  __syncthreads();
+  // weights from the PRE-update costs and the prior evaluated at the POST-update particles (quirk H19: an
+  // aliased prior's centres are the updated particles themselves)
+  for (int p = tid; p < N * N; p += kWarpKernelThreads) {
+    const int i = p / N, kk = p - i * N;
+    const float* xi = nw_s + i * thst;
+    float q = 0.f;
+    if (t.aliased) {
+      const float* ck = nw_s + kk * thst;
+      for (int d = 0; d < HA; ++d) { const float dc = xi[d] - ck[d]; q = fmaf(dc * dc, __ldg(t.inv_var + d), q); }
+    } else {
+      const float* ck = mu_g + kk * HA;
+      for (int d = 0; d < HA; ++d) { const float dc = xi[d] - __ldg(ck + d); q = fmaf(dc * dc, __ldg(t.inv_var + d), q); }
+    }
+    Lg_s[p] = lmix_s[kk] - 0.5f * q;
+  }
+  __syncthreads();
+  for (int i = warp; i < N; i += kWarpKernelWarps) {
+    const float l = lane < N ? Lg_s[i * N + lane] : -INFINITY;
+    const float mx = warp_max(l);
+    const float z = warp_sum(lane < N ? expf(l - mx) : 0.f);
+    if (lane == 0) logw_s[i] = ll_s[i] + ((mx + logf(z)) + t.log_norm);
+  }
+  __syncthreads();
+  __shared__ int s_istar;
+  if (warp == 0) {
+    const float lw = lane < N ? logw_s[lane] : -INFINITY;
+    const float mx = warp_max(lw);
+    const float z = warp_sum(lane < N ? expf(lw - mx) : 0.f);
+    const float lse = mx + logf(z);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    if (lane < N) {
+      const float pw = expf(lw - lse);
+      t.p_weights[inst * N + lane] = pw;
+      if (t.mix_next) t.mix_next[inst * N + lane] = t.weighted ? pw : 1.0f;
+      best = pw; bi = lane;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      s_istar = bi;
+      if (t.i_star) t.i_star[inst] = bi;
+    }
+  }
+  __syncthreads();
+  const int is = s_istar;
+  if (t.a_seq)
+    for (int d = tid; d < HA; d += kWarpKernelThreads) t.a_seq[inst * HA + d] = nw_s[is * thst + d];
+  if (t.theta_next) {
+    const int shift_lim = (k.H - 1);     // A = 1
+    for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
+      const int n2 = e / HA, d = e - n2 * HA;
+      float v;
+      if (d < shift_lim) {
+        v = nw_s[n2 * thst + d + 1];
+      } else if (t.roll == DUST_ROLL_REPEAT) {
+        v = nw_s[n2 * thst + d];
+      } else {
+        float sm = 0.f;
+        for (int h = 0; h < k.H; ++h) sm += nw_s[n2 * thst + h];
+        v = sm / (float)k.H;
+      }
+      t.theta_next[inst * (long long)N * HA + e] = v;
+    }
+  }
+}
+#endif
+
+// ---------------------------------------------------------------------------------------
 // per-policy statistics: combine parameter chunks, log-likelihood, soft-min weights, mixture
 // one CTA per instance; warp w handles policies w, w+nwarps, ...
 // ---------------------------------------------------------------------------------------
@@ -1062,6 +1413,25 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
       DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_instance_kernel<MODEL, ACC, TPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsmem)); \
     { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_instance_kernel<MODEL, ACC, TPT><<<a->B, kFusedThreads / TPT, fsmem, stream>>>(k, o); } \
   } while (0)
+#if DUST_PEND_PAIR
+    // second-generation kernel: packed pendulum path with 16-byte rows and at most 32 policies; DUST_B200_FUSED_V1=1
+    // forces the first one (A/B measurements), DUST_B200_NBUF=4..8 sets the tile ring depth
+    static const bool force_v1 = getenv("DUST_B200_FUSED_V1") != nullptr || getenv("DUST_B200_NO_PAIR") != nullptr;
+    if (kind == DUST_MODEL_PENDULUM && !force_v1 && (k.HA & 3) == 0 && a->N <= 32 && ((((uintptr_t)a->noise) & 15) == 0)) {
+      static const int nbuf_env = getenv("DUST_B200_NBUF") ? atoi(getenv("DUST_B200_NBUF")) : 0;
+      int nbuf = nbuf_env >= kWarpKernelWarps && nbuf_env <= 8 ? nbuf_env : 4;
+      const int ntiles_w = ceil_div(SN, 2 * (32 / a->N) * a->N);
+      if (nbuf > ntiles_w) nbuf = ntiles_w < kWarpKernelWarps ? kWarpKernelWarps : ntiles_w;
+      const WarpKernelSmem Lw = warp_kernel_smem(a->N, k.HA, nbuf);
+      if (Lw.total_bytes <= 227 * 1024) {
+        if (Lw.total_bytes > 48 * 1024)
+          DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Lw.total_bytes));
+        { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_warp_kernel<<<a->B, kWarpKernelThreads, Lw.total_bytes, stream>>>(k, o, nbuf); }
+        DUST_LAUNCH_OK("svmpc_instance_kernel");
+        return DUST_OK;
+      }
+    }
+#endif
     if (kind == DUST_MODEL_PENDULUM) {
       // two trajectories per thread on the packed FP32 pipe when both rows of a thread share a policy
       // (half a tile is a whole number of policy groups); DUST_B200_NO_PAIR=1 forces the scalar kernel
