@@ -196,6 +196,11 @@ def ptr(t):
         raise ValueError("dust_b200: tensor must live on a CUDA device")
     if not t.is_contiguous():
         raise ValueError("dust_b200: tensor must be contiguous")
+    if t.dtype not in (torch.float32, torch.int32):
+        raise ValueError(f"dust_b200: tensor must be float32 (int32 for indices), got {t.dtype}")
+    if t.device.index != torch.cuda.current_device():
+        raise ValueError(f"dust_b200: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
+                         "(kernels are enqueued on the current device's stream: wrap the call in torch.cuda.device(...))")
     return t.data_ptr()
 
 

@@ -63,9 +63,11 @@ class MultiDISCO(BaseController):
     # ------------------------------------------------------------------------------------
     def _spec(self, model):
         key = id(model)
-        if key not in self._spec_cache:
-            self._spec_cache[key] = (model, model.device_spec(self._inst_cost_fn, self._term_cost_fn, self.device))
-        return self._spec_cache[key][1]
+        fp = model.spec_fingerprint() if hasattr(model, "spec_fingerprint") else None
+        ent = self._spec_cache.get(key)
+        if ent is None or ent[2] != fp:     # first use, or the model's defaults / cost weights were changed in place
+            ent = self._spec_cache[key] = (model, model.device_spec(self._inst_cost_fn, self._term_cost_fn, self.device), fp)
+        return ent[1]
 
     def __deepcopy__(self, memo):
         import copy

@@ -9,7 +9,7 @@
 // At most one CTA per SM, resident for the whole launch; it works off an equal contiguous range of
 // (128-row tile, 64-column tile) pairs, segment by segment when the range crosses row tiles.  16 warps:
 //   warp 0      producer   cp.async.bulk (1-D TMA) of pre-tiled hi/lo operand images into smem rings
-//   warp 1      MMA issuer one thread: GEMM1(j) -> S[j&1]; GEMM2(j-1): O += P[(j-1)&1] V_{j-1}
+//   warp 1      MMA issuer one thread: GEMM1(j) -> S[j%3]; GEMM2(j-2): O += P(j-2) V_{j-2}  (two tiles behind)
 //   warp 2      TMEM allocation
 //   warp 3      producer of the V^T tiles
 //   warps 4-7   "softmax" warpgroup A: columns 0..31 of every tile  (tcgen05.ld S, exp, split, tcgen05.st P)
@@ -19,8 +19,8 @@
 //               measured bias ~2e-8 per accumulation step, i.e. 5e-4 over the 24576 steps of
 //               N = 65536 if left in TMEM) and added to the segment's slot of a global scratch;
 //               phi_tc_finish_kernel sums the slots of a row tile and forms the phi rows.
-// TMEM columns (512 allocated): S/P_hi[2] 0..127 (P_hi overwrites the S it was computed from),
-// P_lo[2] 128..255, O[2] 256..256+2*NV.
+// TMEM columns (512 allocated): S/P_hi[3] 0..191 (P_hi overwrites the S it was computed from),
+// P_lo[2] 192..319, O[2] 320..320+2*NV (NV <= 96).
 // Operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8x16B core
 // matrices); the prep kernel writes global memory already in that order, so every tile is one
 // contiguous bulk copy.
@@ -283,8 +283,15 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
   return s;
 }
 
-enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 13, BAR_S_FULL = 17, BAR_P_FULL = 19,
-       BAR_P_EMPTY = 21, BAR_O_FULL = 23, BAR_O_EMPTY = 25, BAR_A_EMPTY = 27 };
+// S / P_hi ring of kSBufs = 3 (P_hi overwrites the S it came from), P_lo ring of 2: GEMM1 runs TWO tiles ahead of
+// GEMM2, so the softmax stage of a tile has two tile periods (not one) before the tensor pipe waits for it
+#ifndef DUST_TC_SBUFS
+#define DUST_TC_SBUFS 3          // 2 = the previous pipeline (GEMM1 one tile ahead), kept for A/B builds
+#endif
+constexpr int kSBufs = DUST_TC_SBUFS;
+constexpr int kLag = kSBufs - 1;  // tiles GEMM2 runs behind GEMM1
+enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 13, BAR_S_FULL = 17, BAR_P_FULL = 20,
+       BAR_P_EMPTY = 23, BAR_O_FULL = 25, BAR_O_EMPTY = 27, BAR_A_EMPTY = 29 };
 
 // the segments of a CTA's unit range: `for (TcSegIter s(p); s.valid(); s.next())` gives row tile s.rt,
 // first column tile s.j0 and tile count s.len of segment s.seg
@@ -318,11 +325,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     mbar_init(&bars[BAR_A_EMPTY], 1);
     for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[BAR_XB_FULL + s], 1); mbar_init(&bars[BAR_XB_EMPTY + s], 1); }
     for (int s = 0; s < kVbStages; ++s) { mbar_init(&bars[BAR_VB_FULL + s], 1); mbar_init(&bars[BAR_VB_EMPTY + s], 1); }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < kSBufs; ++b) {
       mbar_init(&bars[BAR_S_FULL + b], 1);
       mbar_init(&bars[BAR_P_FULL + b], 8);   // one arrival per softmax warp (both groups work on every tile)
-      mbar_init(&bars[BAR_P_EMPTY + b], 1);
     }
+    for (int b = 0; b < 2; ++b) mbar_init(&bars[BAR_P_EMPTY + b], 1);   // P_lo ring
     for (int b = 0; b < 2; ++b) {
       mbar_init(&bars[BAR_O_FULL + b], 1);
       mbar_init(&bars[BAR_O_EMPTY + b], 4);  // one arrival per flush warp
@@ -338,7 +345,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + 128, tO = tmem + 256;
+  const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + kSBufs * kTcBN, tO = tPlo + 2 * kTcBN;   // 192 + 128 + 2 NV <= 512
   // Ring stages, S/P buffers and O buffers are indexed by counters that run on ACROSS segments
   // (g: tiles, cg: flushed chunks), so the pipelines never drain at a row-tile boundary; only the
   // A operand (the row tile itself) is exchanged there.
@@ -402,9 +409,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       const uint32_t vb_stage16 = L.vb_stage_bytes >> 4, vb_half16 = L.vb_half >> 4;
       // GEMM2 of running tile g: O[ch & 1] (+)= P[g & 1] V_g; first / last tile of flush chunk ch
       auto gemm2 = [&](int g, int ch, bool first, bool last) {
-        const int b = g & 1, sv = g % kVbStages;
+        const int b = g & 1, b3 = g % kSBufs, sv = g % kVbStages;
         mbar_wait(&bars[BAR_VB_FULL + sv], (g / kVbStages) & 1);
-        mbar_wait(&bars[BAR_P_FULL + b], (g >> 1) & 1);
+        mbar_wait(&bars[BAR_P_FULL + b3], (g / kSBufs) & 1);
         tc_fence_after();
         const int ob = ch & 1;
         if (first) {  // the flush warps must have drained this O buffer (two chunks ago)
@@ -413,7 +420,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         }
         const uint32_t tOb = tO + ob * p.NV;
         const uint32_t vh = loV0 + sv * vb_stage16, vl = vh + vb_half16;
-        const uint32_t ph = tPhi + b * kTcBN, pl = tPlo + b * kTcBN;
+        const uint32_t ph = tPhi + b3 * kTcBN, pl = tPlo + b * kTcBN;
         if (elect_one_sync()) {
 #pragma unroll
           for (int kk = 0; kk < ks2; ++kk) {
@@ -429,12 +436,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         __syncwarp();
       };
       int g = 0, cg = 0;                       // running tile / chunk counters
-      int pch = 0;                             // GEMM2 runs one tile behind GEMM1: chunk info of tile g - 1
-      bool pfirst = false, plast = false;
+      // GEMM2 runs kLag tiles behind GEMM1: flush-chunk info of the tiles in between (slot = tile % kLag)
+      int pch[2] = {0, 0};
+      bool pfirst[2] = {false, false}, plast[2] = {false, false};
       for (TcSegIter s(p); s.valid(); s.next()) {
         mbar_wait(&bars[BAR_A], s.seg & 1);
         for (int j = 0; j < s.len; ++j, ++g) {
-          const int b = g & 1, sx = g % kXbStages;
+          const int b = g % kSBufs, sx = g % kXbStages;
           mbar_wait(&bars[BAR_XB_FULL + sx], (g / kXbStages) & 1);
           tc_fence_after();
           const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
@@ -455,14 +463,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
             if (j == s.len - 1) tc_commit(&bars[BAR_A_EMPTY]);   // last reader of this segment's A operand
           }
           __syncwarp();
-          if (g >= 1) gemm2(g - 1, pch, pfirst, plast);
-          pch = cg;
-          pfirst = (j % kTcChunk) == 0;
-          plast = (j % kTcChunk) == kTcChunk - 1 || j == s.len - 1;
-          if (plast) ++cg;
+          const int q = g % kLag;
+          if (g >= kLag) gemm2(g - kLag, pch[q], pfirst[q], plast[q]);
+          pch[q] = cg;
+          pfirst[q] = (j % kTcChunk) == 0;
+          plast[q] = (j % kTcChunk) == kTcChunk - 1 || j == s.len - 1;
+          if (plast[q]) ++cg;
         }
       }
-      if (g >= 1) gemm2(g - 1, pch, pfirst, plast);
+#pragma unroll
+      for (int l = kLag; l >= 1; --l)
+        if (g >= l) gemm2(g - l, pch[(g - l) % kLag], pfirst[(g - l) % kLag], plast[(g - l) % kLag]);
     }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------ softmax warpgroups ---------------------------------
@@ -483,13 +494,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       const int cdiag_all = (i0 + row) & (kTcBN - 1);
       float ksum = 0.f;  // sum_j K_ij over this warpgroup's column halves (exact fp32, no ones column in V)
       for (int j = 0; j < s.len; ++j, ++g) {
-        const int b = g & 1, it = g >> 1, sv = g % kVbStages;
+        const int b = g & 1, it = g >> 1, b3 = g % kSBufs, it3 = g / kSBufs, sv = g % kVbStages;
         mbar_wait(&bars[BAR_VB_FULL + sv], (g / kVbStages) & 1);   // |x_j|^2 of this tile
         const float* xnj = reinterpret_cast<const float*>(smem + L.vb + sv * L.vb_stage_bytes + 2 * L.vb_half) + half * 32;
-        mbar_wait(&bars[BAR_S_FULL + b], it & 1);
+        mbar_wait(&bars[BAR_S_FULL + b3], it3 & 1);
         tc_fence_after();
         uint32_t r[32], lo[32];
-        tmem_ld32(tS + lane_base + b * kTcBN + half * 32, r);
+        tmem_ld32(tS + lane_base + b3 * kTcBN + half * 32, r);
         tmem_wait_ld();
         // the tile that holds column i itself: d2_ii is exactly 0 (the 3xTF32 Gram entry only gives
         // |x_i|^2 to ~1e-6 relative, which a narrow kernel would amplify)
@@ -508,15 +519,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
           r[c] = __float_as_uint(hi);
           lo[c] = __float_as_uint(tf32_lo(kv, hi));
         }
-        // P_hi overwrites the S columns it came from; GEMM2(g-2) must be done with P[b]
+        // P_hi overwrites the S columns it came from (this tile's own buffer); GEMM2(g-2) must be done with P_lo[b]
         mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
         tc_fence_after();
-        tmem_st32(tPhi + lane_base + b * kTcBN + half * 32, r);
+        tmem_st32(tPhi + lane_base + b3 * kTcBN + half * 32, r);
         tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b]);
+        if (lane == 0) mbar_arrive(&bars[BAR_P_FULL + b3]);
       }
       oacc_cta[(size_t)s.seg * slot_stride + (size_t)(p.NV + half) * kTcBM + row] = ksum;
     }
@@ -1049,7 +1060,7 @@ bool phi_tc_supported(const dust_phi_args* a) {
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   if (a->N % kTcBM || r0 % kTcBM || r1 % kTcBM || a->N < 1024) return false;
   const int Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
-  if (2 * NV > 256 || Dp > 64) return false;
+  if ((kSBufs + 2) * kTcBN + 2 * NV > 512 || Dp > 64) return false;   // TMEM columns: S/P_hi ring, P_lo ring, two O buffers
   return tc_smem_layout(Dp, NV).total <= 227 * 1024;
 }
 

@@ -67,35 +67,66 @@ class ShardedSVGD:
         if self.world > 1:
             dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=self.group)
 
-    def gather(self, x_local, score_local):
-        if self.gather_mode == "separate" and self.world > 1:
-            out = []
+    def gather_async(self, x_local, score_local):
+        """-> (x_all, score_all, wait_x, wait_score): the two collectives are enqueued back to back; `wait_x()` /
+        `wait_score()` make the current stream wait for one of them, so the score gather overlaps whatever only
+        needs X (the bandwidth pass)."""
+        nothing = lambda: None  # noqa: E731
+        if self.world == 1:
+            return x_local, score_local, nothing, nothing
+        if self.gather_mode == "separate":
+            out, waits = [], []
             for key, loc in (("x", x_local), ("score", score_local)):
                 buf = self._gathered2.get(key)
                 if buf is None or buf.dtype != loc.dtype or buf.device != loc.device:
                     buf = self._gathered2[key] = torch.empty((self.N, self.D), dtype=loc.dtype, device=loc.device)
-                dist.all_gather_into_tensor(buf, loc.contiguous(), group=self.group)
+                work = dist.all_gather_into_tensor(buf, loc.contiguous(), group=self.group, async_op=True)
                 out.append(buf)
-            return out[0], out[1]
+                waits.append(work.wait)
+            return out[0], out[1], waits[0], waits[1]
         xs = self._all_gather(torch.cat([x_local, score_local], dim=1))
-        return xs[:, : self.D].contiguous(), xs[:, self.D:].contiguous()
+        return xs[:, : self.D].contiguous(), xs[:, self.D:].contiguous(), nothing, nothing
 
-    def median(self, x_all):
-        """Exact lower median of all N^2 squared distances: each rank histograms its row block."""
-        return self.ops.median_sq_dist(x_all, rows=self.rows, all_reduce=self._all_reduce_hist)
+    def gather(self, x_local, score_local):
+        x_all, s_all, wait_x, wait_s = self.gather_async(x_local, score_local)
+        wait_x()
+        wait_s()
+        return x_all, s_all
+
+    def median(self, x_all, defer_fallback=False):
+        """Exact lower median of all N^2 squared distances: each rank histograms its row block.
+        defer_fallback (library ops only): run the tensor-core window pass alone and return (median, check);
+        `check()` tells -- without stalling the kernels queued after it -- whether the rank fell inside the window
+        (the decision is taken on the all-reduced counts, so every rank sees the same answer)."""
+        if getattr(self.ops, "MedianWorkspace", None) is None:     # stand-in ops (host-logic tests)
+            return self.ops.median_sq_dist(x_all, rows=self.rows, all_reduce=self._all_reduce_hist), None
+        if self._median_ws is None:
+            self._median_ws = self.ops.MedianWorkspace(self.N, self.D, x_all.device)
+        if defer_fallback:
+            return self.ops.median_sq_dist_deferred(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist)
+        return self.ops.median_sq_dist(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist), None
 
     def phi(self, x_local, score_local, bw=None, bw_scale=1.0):
         """Returns (phi_local [n_loc, D], coef) with coef = device {gamma, c1, c2, bw}."""
-        x_all, s_all = self.gather(x_local, score_local)
-        if bw is None:
-            med = self.median(x_all)
-            coef = self.ops.bandwidth_from_median(med, self.N, bw_scale, 0)
-            out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=self.rows)
-        else:
-            coef = None
+        x_all, s_all, wait_x, wait_s = self.gather_async(x_local, score_local)
+        b, e = self.rows
+        if bw is not None:
+            wait_x()
+            wait_s()
             out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma=1.0 / (2.0 * bw * bw),
                                     c1=1.0 / self.N, c2=1.0 / (self.N * bw * bw), rows=self.rows)
-        b, e = self.rows
+            return out["phi"][0, b:e], None
+        wait_x()
+        med, check = self.median(x_all, defer_fallback=True)
+        coef = self.ops.bandwidth_from_median(med, self.N, bw_scale, 0)
+        wait_s()
+        out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=self.rows)
+        if check is not None and not check():
+            # the rank fell outside the sampled window (ties, clusters): the two-pass radix select, then phi again
+            med = self.ops.median_sq_dist(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist,
+                                          allow_fast=False)
+            coef = self.ops.bandwidth_from_median(med, self.N, bw_scale, 0)
+            out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=self.rows)
         return out["phi"][0, b:e], coef
 
 

@@ -42,8 +42,11 @@ class MPF(SVGD):
         self.device = torch.device(device)
         self.x = torch.as_tensor(init_particles, dtype=torch.float32).to(self.device).contiguous()
         self.likelihood = likelihood
-        if self.optimizer_class is not torch.optim.SGD:
-            raise NotImplementedError("MPF: only plain SGD is fused into the update kernel")
+        plain_sgd = self.optimizer_class is torch.optim.SGD and not any(
+            self.opt_args.get(k) for k in ("momentum", "weight_decay", "nesterov", "dampening"))
+        if not plain_sgd:
+            raise NotImplementedError("MPF: only plain SGD (no momentum / weight decay / nesterov / dampening) is fused "
+                                      "into the update kernel; other optimisers are not implemented")
         self._spec = None
         self.update_prior(bw)
 

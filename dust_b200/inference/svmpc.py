@@ -14,7 +14,15 @@ def _kernel_mode(kernel):
     if isinstance(kernel, iid_mp):
         if not kernel.indep_controls:
             raise NotImplementedError("iid_mp(indep_controls=False) has no device kernel")
-        return "mp", 0.0, kernel.base_kernel.ell_scale
+        base = kernel.base_kernel
+        # the per-dimension device kernel implements the median heuristic with the default clamp only
+        # (base_kernels.py:64-89 with ell < 0, minimum_bw = 1e-5): anything else must not pass silently
+        if getattr(base, "ell", -1) >= 0:
+            raise NotImplementedError("iid_mp(base_kernel=RBF(bandwidth >= 0)): a fixed bandwidth has no device kernel "
+                                      "(use bandwidth=-1, the median heuristic)")
+        if float(getattr(base, "minimum_bw", 1e-5)) != 1e-5:
+            raise NotImplementedError("iid_mp(base_kernel=RBF(minimum_bw != 1e-5)) has no device kernel")
+        return "mp", 0.0, base.ell_scale
     if isinstance(kernel, RBF):
         raise NotImplementedError(
             "a plain RBF kernel inside SVMPC.phi raises in the reference as well (broadcast of k_XX [N,N] "

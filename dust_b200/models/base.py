@@ -55,6 +55,22 @@ class BaseModel:
     def dict_to_params(self, params_dict):
         return torch.cat([params_dict[key] for key in self._params_keys], dim=1)
 
+    def spec_fingerprint(self):
+        """What a DeviceModelSpec bakes in (default parameters, cost weights): holders of a cached spec compare it
+        and rebuild the spec when the model was changed in place (the reference reads params_dict on every step)."""
+        out = []
+        for k in sorted(self._params_dict):
+            v = self._params_dict[k]
+            if torch.is_tensor(v):
+                out.append((k, id(v), v._version) if v.is_cuda else (k, tuple(v.reshape(-1).tolist())))
+            else:
+                out.append((k, v))
+        for name in ("w_state", "w_ctrl", "w_term", "w_obs", "target"):
+            t = getattr(self, name, None)
+            if torch.is_tensor(t):
+                out.append((name, tuple(t.reshape(-1).tolist())))
+        return tuple(out)
+
     # --- device side -------------------------------------------------------------------
     #: order of the parameter columns the kernels expect
     device_param_order = ()

@@ -94,7 +94,7 @@ class Particle(BaseModel):
 
     def step(self, states, actions, params_dict=None):
         L.require_cuda()
-        dev = torch.device("cuda")
+        dev = states.device if torch.is_tensor(states) and states.is_cuda else torch.device("cuda", torch.cuda.current_device())
         shape = torch.as_tensor(states).shape
         st = torch.as_tensor(states, dtype=torch.float32).reshape(-1, 4).to(dev).contiguous()
         M = st.shape[0]
@@ -104,7 +104,7 @@ class Particle(BaseModel):
 
     def _cost(self, states, actions, terminal):
         L.require_cuda()
-        dev = torch.device("cuda")
+        dev = states.device if torch.is_tensor(states) and states.is_cuda else torch.device("cuda", torch.cuda.current_device())
         st = torch.as_tensor(states, dtype=torch.float32).reshape(-1, 4).to(dev).contiguous()
         ac = None
         if actions is not None and torch.is_tensor(actions):

@@ -98,7 +98,7 @@ class PendulumModel(BaseModel):
     def step(self, states, actions, params_dict=None):
         """One transition for a batch of (state, action[, params]) rows, on the GPU."""
         L.require_cuda()
-        dev = torch.device("cuda")
+        dev = states.device if torch.is_tensor(states) and states.is_cuda else torch.device("cuda", torch.cuda.current_device())
         st = torch.as_tensor(states, dtype=torch.float32).reshape(-1, 2).to(dev).contiguous()
         M = st.shape[0]
         ac = torch.as_tensor(actions, dtype=torch.float32).reshape(-1, 1).to(dev).expand(M, 1).contiguous()

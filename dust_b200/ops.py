@@ -202,6 +202,32 @@ class MedianWorkspace:
         self.fast = bool(lib.dust_median_fast_supported(N, D))
         self.fast_bytes = lib.dust_median_fast_workspace_bytes(N, D) if self.fast else 0
         self.fast_ws = _ws(self.fast_bytes, device) if self.fast else None
+        self.flag_host, self.flag_event = None, None      # pinned success flag of the deferred (sharded) form
+
+
+def _median_args(x, ws, rows):
+    N, D = x.shape
+    a = L.MedianArgs()
+    a.N, a.D = N, D
+    a.row_begin, a.row_end = (0, N) if rows is None else rows
+    a.x, a.hist, a.selected, a.row_norms = L.ptr(x), ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
+    return a
+
+
+def _median_fast(a, ws, all_reduce):
+    L.call("dust_median_fast_prepare", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream(), launches=4)
+    L.call("dust_median_fast_count", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream())
+    if all_reduce is not None:
+        all_reduce(ws.hist)
+    L.call("dust_median_fast_select", C.byref(a), ws.median.data_ptr(), L.stream())
+
+
+def _median_radix(a, ws, all_reduce):
+    for p in (0, 1):
+        L.call("dust_median_hist_pass", C.byref(a), p, L.stream(), launches=2 if p == 0 else 1)
+        if all_reduce is not None:
+            all_reduce(ws.hist)
+        L.call("dust_median_select", C.byref(a), p, ws.median.data_ptr(), L.stream())
 
 
 def median_sq_dist(x, ws=None, rows=None, all_reduce=None, allow_fast=True):
@@ -213,24 +239,43 @@ def median_sq_dist(x, ws=None, rows=None, all_reduce=None, allow_fast=True):
     L.require_cuda()
     N, D = x.shape
     ws = ws or MedianWorkspace(N, D, x.device)
-    a = L.MedianArgs()
-    a.N, a.D = N, D
-    a.row_begin, a.row_end = (0, N) if rows is None else rows
-    a.x, a.hist, a.selected, a.row_norms = L.ptr(x), ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
+    a = _median_args(x, ws, rows)
     ws.hist.zero_()
     ws.selected.zero_()
     if allow_fast and ws.fast and a.row_begin % 128 == 0 and a.row_end % 128 == 0:
-        L.call("dust_median_fast_prepare", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream(), launches=4)
-        L.call("dust_median_fast_count", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream())
-        if all_reduce is not None:
-            all_reduce(ws.hist)
-        L.call("dust_median_fast_select", C.byref(a), ws.median.data_ptr(), L.stream())
-    for p in (0, 1):
-        L.call("dust_median_hist_pass", C.byref(a), p, L.stream(), launches=2 if p == 0 else 1)
-        if all_reduce is not None:
-            all_reduce(ws.hist)
-        L.call("dust_median_select", C.byref(a), p, ws.median.data_ptr(), L.stream())
+        _median_fast(a, ws, all_reduce)
+    _median_radix(a, ws, all_reduce)
     return ws.median
+
+
+def median_sq_dist_deferred(x, ws=None, rows=None, all_reduce=None):
+    """The sharded form of `median_sq_dist`: when the tensor-core window pass applies it runs ALONE -- the radix
+    kernels behind it would drag two more histogram all-reduces along that do nothing in the common case -- and
+    the success flag travels to pinned host memory behind an event.  -> (median, check): `check()` waits for that
+    event only (kernels queued after it keep the GPU busy) and returns False when the rank fell outside the
+    window; the caller then runs `median_sq_dist(..., allow_fast=False)`.  The flag is computed from the
+    all-reduced counts: every rank takes the same branch."""
+    L.require_cuda()
+    N, D = x.shape
+    ws = ws or MedianWorkspace(N, D, x.device)
+    a = _median_args(x, ws, rows)
+    ws.hist.zero_()
+    ws.selected.zero_()
+    if not (ws.fast and a.row_begin % 128 == 0 and a.row_end % 128 == 0):
+        _median_radix(a, ws, all_reduce)
+        return ws.median, None
+    _median_fast(a, ws, all_reduce)
+    if ws.flag_host is None:
+        ws.flag_host, ws.flag_event = torch.empty(1, dtype=torch.int32).pin_memory(), torch.cuda.Event()
+    flag, ev = ws.flag_host, ws.flag_event
+    flag.copy_(ws.selected[5:6], non_blocking=True)
+    ev.record()
+
+    def check():
+        ev.synchronize()
+        return bool(int(flag[0]))
+
+    return ws.median, check
 
 
 def noise_normal(out, seed, offset):

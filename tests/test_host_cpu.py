@@ -173,7 +173,7 @@ from dust_b200.distributed import ShardedSVGD, row_block
 class OracleOps:
     """CPU stand-ins with the ABI's semantics: per-rank row-block histogram + all-reduce."""
     @staticmethod
-    def median_sq_dist(x, rows=None, all_reduce=None):
+    def median_sq_dist(x, rows=None, all_reduce=None, **kw):
         d2 = O.sq_dists_addmm(x[rows[0]:rows[1]], x)
         bits = d2.reshape(-1).view(torch.int32).to(torch.int64)
         k = (x.shape[0] ** 2 - 1) // 2
