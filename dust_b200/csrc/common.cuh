@@ -58,6 +58,7 @@ struct ModelParams {
   float w_obs, inv_cell, c_offset[2];
   int grid_nx, grid_ny, can_crash, with_obstacle;
   float grid_xmax, grid_ymax;   // (float)(grid_nx - 1), (float)(grid_ny - 1): the clamp bounds of the cell lookup
+  float pend_c1, pend_c2;       // default-parameter dynamics coefficients, formed in double on the host (models.cuh)
   const uint32_t* grid_bits;
 };
 
@@ -72,6 +73,13 @@ inline ModelParams to_params(const dust_model_desc& d) {
   m.w_obs = d.w_obs; m.inv_cell = d.inv_cell; m.c_offset[0] = d.c_offset[0]; m.c_offset[1] = d.c_offset[1];
   m.grid_nx = d.grid_nx; m.grid_ny = d.grid_ny; m.can_crash = d.can_crash; m.with_obstacle = d.with_obstacle;
   m.grid_xmax = (float)(d.grid_nx - 1); m.grid_ymax = (float)(d.grid_ny - 1);
+  {
+    // python-float defaults: the quotients are formed in double before the cast (pendulum.py:93-97); done here once
+    // instead of with FP64 instructions in every thread
+    const double l = (double)d.default_length, ms = (double)d.default_mass;
+    m.pend_c1 = (float)(-3.0 * (double)d.g / (2.0 * l));
+    m.pend_c2 = (float)(3.0 / (ms * l * l));
+  }
   m.grid_bits = d.grid_bits;
   return m;
 }

@@ -40,9 +40,8 @@ __device__ __forceinline__ PendulumCoef pendulum_coef_sampled(const ModelParams&
 }
 __device__ __forceinline__ PendulumCoef pendulum_coef_default(const ModelParams& m) {
   PendulumCoef c;
-  const double l = (double)m.default_length, ms = (double)m.default_mass;
-  c.c1 = (float)(-3.0 * (double)m.g / (2.0 * l));
-  c.c2 = (float)(3.0 / (ms * l * l));
+  c.c1 = m.pend_c1;   // (float)(-3 g / (2 l)) and (float)(3 / (m l^2)) in double: to_params() (common.cuh)
+  c.c2 = m.pend_c2;
   return c;
 }
 

@@ -210,9 +210,7 @@ __device__ __forceinline__ float trajectory_cost_sum(const RolloutKParams& k, co
 // instructions; XFORM actions th_row[t] + sigma * eps[t].  Small-angle horizon only.
 __device__ __forceinline__ float2 pendulum_pair_cost_sum(const RolloutKParams& k, const float* __restrict__ rowA,
                                                          const float* __restrict__ rowB, long long inst, int jA, int jB,
-                                                         const float* __restrict__ th_row, float sg0) {
-  const float* __restrict__ x0 = k.state0 + inst * 2;
-  const float th0 = __ldg(x0), om0 = __ldg(x0 + 1);
+                                                         const float* __restrict__ th_row, float sg0, float th0, float om0) {
   float2 csum = make_float2(0.f, 0.f);
   const float2 sg = bc2(sg0);
   for (int p = 0; p < k.P; ++p) {
@@ -548,7 +546,8 @@ __global__ void __launch_bounds__(kFusedThreads / TPT, TPT == 2 ? 5 : DUST_FUSED
         const int nv = (rb < rows) ? 2 : 1;
         float csA, csB = 0.f;
         if (small && nv == 2) {
-          const float2 cs = pendulum_pair_cost_sum(k, rowA, rowB, inst, j0 + ra, j0 + rb, th_row, sg0);
+          const float2 cs = pendulum_pair_cost_sum(k, rowA, rowB, inst, j0 + ra, j0 + rb, th_row, sg0,
+                                                   __ldg(k.state0 + inst * 2), __ldg(k.state0 + inst * 2 + 1));
           csA = cs.x;
           csB = cs.y;
         } else {
@@ -750,33 +749,55 @@ constexpr int kWarpKernelWarps = kWarpKernelThreads / 32;
 struct WarpKernelSmem {
   int stride, thst, tile_floats, off_tile, off_acc, off_th, off_tail, off_bar, total_bytes;
 };
-__host__ __device__ inline WarpKernelSmem warp_kernel_smem(int N, int HA, int nbuf) {
+__host__ __device__ inline WarpKernelSmem warp_kernel_smem(int N, int HA) {
   WarpKernelSmem L;
   L.stride = padded_stride(HA);
   L.thst = (HA + 3) & ~3;
   const int La = (32 / N) * N;
   L.tile_floats = 2 * La * L.stride;
   // tail scratch (gl, sc, nw [N][thst]; Lg, Kx [N][N]; ll, lmix, logw, lse [N]; reductions 3 x [threads]) lives in
-  // the tile ring, which is dead once every warp has left the rollout loop
+  // the tile buffers, which are dead once every warp has left the rollout loop
   const int tail = 3 * N * L.thst + 2 * N * N + 4 * N + 3 * kWarpKernelThreads;
-  const int ring = nbuf * L.tile_floats;
-  L.off_tile = 0;                                              // [nbuf][2*La][stride]
+  const int ring = kWarpKernelWarps * L.tile_floats;
+  L.off_tile = 0;                                              // [warps][2*La][stride]: one buffer per warp
   L.off_tail = 0;
   L.off_acc = ((ring > tail ? ring : tail) + 3) & ~3;          // [threads][stride] weighted score rows
   L.off_th = L.off_acc + kWarpKernelThreads * L.stride;        // [N][thst] policy means
   L.off_bar = (L.off_th + N * L.thst + 1) & ~1;                // 8-byte aligned mbarriers
-  L.total_bytes = 4 * L.off_bar + 8 * nbuf;
+  L.total_bytes = 4 * L.off_bar + 8 * kWarpKernelWarps;
   return L;
 }
 
 #if DUST_PEND_PAIR
-__global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const RolloutKParams k, const FusedOut o, const int nbuf) {
+// acc <- acc * scale + eA * rowA + eB * rowB over one score row, both trajectories of the lane at once (packed pipe)
+template <int HA4>
+__device__ __forceinline__ void fold_score_rows(float* __restrict__ acc_row, const float* __restrict__ rowA,
+                                                const float* __restrict__ rowB, bool hasB, float scale, float eA, float eB, int HA) {
+  const float2 sc2 = bc2(scale), ea2 = bc2(eA), eb2 = bc2(eB);
+  auto chunk = [&](int c) {
+    const float4 a4 = *reinterpret_cast<const float4*>(acc_row + c);
+    const float4 va = *reinterpret_cast<const float4*>(rowA + c);
+    const float4 vb = hasB ? *reinterpret_cast<const float4*>(rowB + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float2 lo = fma2(make_float2(a4.x, a4.y), sc2, fma2(ea2, make_float2(va.x, va.y), mul2(eb2, make_float2(vb.x, vb.y))));
+    const float2 hi = fma2(make_float2(a4.z, a4.w), sc2, fma2(ea2, make_float2(va.z, va.w), mul2(eb2, make_float2(vb.z, vb.w))));
+    *reinterpret_cast<float4*>(acc_row + c) = make_float4(lo.x, lo.y, hi.x, hi.y);
+  };
+  if (HA4 > 0) {
+#pragma unroll
+    for (int c4 = 0; c4 < HA4; ++c4) chunk(4 * c4);
+  } else {
+    for (int c = 0; c < HA; c += 4) chunk(c);
+  }
+}
+
+// HA4 = H*A/4 when it is a compile-time constant (the bench shape: 5), 0 = any multiple of 4 up to 32
+template <int HA4>
+__global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const RolloutKParams k, const FusedOut o) {
   extern __shared__ __align__(16) float smem[];
-  const int HA = k.HA, N = k.N;
-  const WarpKernelSmem L = warp_kernel_smem(N, HA, nbuf);
+  const int HA = HA4 > 0 ? 4 * HA4 : k.HA, N = k.N;
+  const WarpKernelSmem L = warp_kernel_smem(N, HA);
   const int stride = L.stride, thst = L.thst;
   const int La = (32 / N) * N, WT = 2 * La;
-  float* tiles = smem + L.off_tile;
   float* th_s = smem + L.off_th;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   const long long inst = blockIdx.x;
@@ -788,78 +809,83 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
   const float* __restrict__ noise = k.noise + inst * (long long)k.SN * HA;
   const int ntiles = (k.SN + WT - 1) / WT;
   const bool bulk = stride == HA;                // unpadded rows: a tile is one contiguous block
+  // this warp's tile buffer and "tile landed" barrier: tile t of the instance goes to warp t % 4, which requests its
+  // next tile itself as soon as it has folded the current one -- no CTA barrier, no index arithmetic in the loop
+  float* const my_tile = smem + L.off_tile + warp * L.tile_floats;
+  uint64_t* const my_bar = &full_bar[warp];
+  const float* __restrict__ rowA = my_tile + lane * stride;
+  const float* __restrict__ rowB = my_tile + (lane + La) * stride;
+  const uint32_t tile_bytes = (uint32_t)WT * (uint32_t)HA * 4u;
 
-  // request tile t (rows [t*WT, ..)) into buffer t % nbuf; called by a whole warp
-  auto request = [&](int t) {
+  auto request = [&](int t) {                    // rows [t*WT, ..) into this warp's buffer; called by the whole warp
     const int j0 = t * WT;
-    const int rows = min(WT, k.SN - j0);
-    float* dst = tiles + (t % nbuf) * L.tile_floats;
-    uint64_t* bar = &full_bar[t % nbuf];
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's reads of the buffer are done
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)rows * (uint32_t)HA * 4u);
     if (bulk) {
-      if (lane == 0) bulk_g2s(dst, noise + (long long)j0 * HA, (uint32_t)rows * (uint32_t)HA * 4u, bar);
+      if (lane == 0) {
+        const uint32_t bytes = (j0 + WT <= k.SN) ? tile_bytes : (uint32_t)(k.SN - j0) * (uint32_t)HA * 4u;
+        mbar_expect_tx(my_bar, bytes);
+        bulk_g2s(my_tile, noise + (long long)j0 * HA, bytes, my_bar);
+      }
     } else {
+      const int rows = min(WT, k.SN - j0);
+      if (lane == 0) mbar_expect_tx(my_bar, (uint32_t)rows * (uint32_t)HA * 4u);
       __syncwarp();
-      for (int r = lane; r < rows; r += 32) bulk_g2s(dst + r * stride, noise + (long long)(j0 + r) * HA, (uint32_t)HA * 4u, bar);
+      for (int r = lane; r < rows; r += 32) bulk_g2s(my_tile + r * stride, noise + (long long)(j0 + r) * HA, (uint32_t)HA * 4u, my_bar);
     }
   };
-  if (tid == 0) {
-    for (int b = 0; b < nbuf; ++b) mbar_init(&full_bar[b], 1);
+  if (lane == 0) {
+    mbar_init(my_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncthreads();
-  // the first nbuf tiles, spread over the warps
-  for (int t = warp; t < min(nbuf, ntiles); t += kWarpKernelWarps) request(t);
+  __syncwarp();
+  if (warp < ntiles) request(warp);
   for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
     const int nn = e / HA;
     th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
   }
   if (active)
     for (int c = 0; c < stride; c += 4) *reinterpret_cast<float4*>(acc_row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
   const float sg0 = k.sigma[0];
+  const float th0 = __ldg(k.state0 + inst * 2), om0 = __ldg(k.state0 + inst * 2 + 1);
   const bool small = small_angle_horizon<DUST_MODEL_PENDULUM>(k, inst);
   const float* __restrict__ th_row = th_s + n * thst;
-  const float inv_P = 1.0f / (float)k.P;
-  (void)inv_P;
+  float* cost_ptr = o.costs ? o.costs + inst * k.SN + warp * WT + lane : nullptr;
+  __syncthreads();                               // policy means visible to every warp
 
   float m_run = INFINITY, z_run = 0.f, c_run = 0.f;
+  uint32_t parity = 0;
   for (int t = warp; t < ntiles; t += kWarpKernelWarps) {
     const int j0 = t * WT;
     const int rows = min(WT, k.SN - j0);
-    const float* tile = tiles + (t % nbuf) * L.tile_floats;
-    mbar_wait(&full_bar[t % nbuf], (uint32_t)(t / nbuf) & 1u);
-    const int ra = lane, rb = lane + La;
-    if (active && ra < rows) {
-      const float* __restrict__ rowA = tile + ra * stride;
-      const float* __restrict__ rowB = tile + rb * stride;
-      const int nv = (rb < rows) ? 2 : 1;
+    mbar_wait(my_bar, parity);
+    parity ^= 1u;
+    if (active && lane < rows) {
+      const bool hasB = lane + La < rows;
       float csA, csB = 0.f;
-      if (small && nv == 2) {
-        const float2 cs = pendulum_pair_cost_sum(k, rowA, rowB, inst, j0 + ra, j0 + rb, th_row, sg0);
+      if (small && hasB) {
+        const float2 cs = pendulum_pair_cost_sum(k, rowA, rowB, inst, j0 + lane, j0 + lane + La, th_row, sg0, th0, om0);
         csA = cs.x;
         csB = cs.y;
       } else {
         // ragged last tile, or an angle beyond the fast range: the scalar step, same arithmetic (one copy of the code)
         csA = 0.f;
 #pragma unroll 1
-        for (int q = 0; q < nv; ++q) {
+        for (int q = 0; q < (hasB ? 2 : 1); ++q) {
           const float* __restrict__ row = q ? rowB : rowA;
-          const int jj = j0 + (q ? rb : ra);
+          const int jj = j0 + lane + (q ? La : 0);
           const float v = small ? trajectory_cost_sum<DUST_MODEL_PENDULUM, true, false, true>(k, row, nullptr, inst, jj, 0, k.P, th_row, sg0, sg0)
                                 : trajectory_cost_sum<DUST_MODEL_PENDULUM, false, false, true>(k, row, nullptr, inst, jj, 0, k.P, th_row, sg0, sg0);
           if (q) csB = v; else csA = v;
         }
       }
       const float costA = (k.P == 1) ? csA : csA / (float)k.P;
-      const float costB = (nv == 2) ? ((k.P == 1) ? csB : csB / (float)k.P) : INFINITY;
-      if (o.costs) {
-        o.costs[inst * k.SN + j0 + ra] = costA;
-        if (nv == 2) o.costs[inst * k.SN + j0 + rb] = costB;
+      const float costB = hasB ? ((k.P == 1) ? csB : csB / (float)k.P) : INFINITY;
+      if (cost_ptr) {
+        cost_ptr[0] = costA;
+        if (hasB) cost_ptr[La] = costB;
       }
       c_run += costA;
-      if (nv == 2) c_run += costB;
+      if (hasB) c_run += costB;
       // online soft-min of this lane's rows relative to its running minimum: both new rows are folded at once
       const float m_new = fminf(m_run, fminf(costA, costB));
       const float scale = expf(-o.alpha * (m_run - m_new));          // 0 on the first tile (m_run = inf), 1 if the minimum stands
@@ -867,20 +893,12 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
       const float eB = expf(-o.alpha * (costB - m_new));             // 0 for a missing row (cost = inf)
       m_run = m_new;
       z_run = z_run * scale + (eA + eB);
-      if (scale != 1.f || eA > 1e-30f || eB > 1e-30f) {              // else: invisible in float32
-        const float2 sc2 = bc2(scale), ea2 = bc2(eA), eb2 = bc2(eB);
-        for (int c = 0; c < HA; c += 4) {
-          const float4 a4 = *reinterpret_cast<const float4*>(acc_row + c);
-          const float4 va = *reinterpret_cast<const float4*>(rowA + c);
-          const float4 vb = (nv == 2) ? *reinterpret_cast<const float4*>(rowB + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-          const float2 lo = fma2(make_float2(a4.x, a4.y), sc2, fma2(ea2, make_float2(va.x, va.y), mul2(eb2, make_float2(vb.x, vb.y))));
-          const float2 hi = fma2(make_float2(a4.z, a4.w), sc2, fma2(ea2, make_float2(va.z, va.w), mul2(eb2, make_float2(vb.z, vb.w))));
-          *reinterpret_cast<float4*>(acc_row + c) = make_float4(lo.x, lo.y, hi.x, hi.y);
-        }
-      }
+      if (scale != 1.f || eA > 1e-30f || eB > 1e-30f)                // else: invisible in float32
+        fold_score_rows<HA4>(acc_row, rowA, rowB, hasB, scale, eA, eB, HA);
     }
+    if (cost_ptr) cost_ptr += kWarpKernelWarps * WT;
     __syncwarp();
-    if (t + nbuf < ntiles) request(t + nbuf);    // this buffer's next occupant (consumed by warp (t + nbuf) % 4)
+    if (t + kWarpKernelWarps < ntiles) request(t + kWarpKernelWarps);
   }
 
   // ---- combine the G = 4*La/N lanes that share a policy -----------------------------------------------
@@ -1415,18 +1433,20 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   } while (0)
 #if DUST_PEND_PAIR
     // second-generation kernel: packed pendulum path with 16-byte rows and at most 32 policies; DUST_B200_FUSED_V1=1
-    // forces the first one (A/B measurements), DUST_B200_NBUF=4..8 sets the tile ring depth
+    // forces the first one (A/B measurements)
     static const bool force_v1 = getenv("DUST_B200_FUSED_V1") != nullptr || getenv("DUST_B200_NO_PAIR") != nullptr;
     if (kind == DUST_MODEL_PENDULUM && !force_v1 && (k.HA & 3) == 0 && a->N <= 32 && ((((uintptr_t)a->noise) & 15) == 0)) {
-      static const int nbuf_env = getenv("DUST_B200_NBUF") ? atoi(getenv("DUST_B200_NBUF")) : 0;
-      int nbuf = nbuf_env >= kWarpKernelWarps && nbuf_env <= 8 ? nbuf_env : 4;
-      const int ntiles_w = ceil_div(SN, 2 * (32 / a->N) * a->N);
-      if (nbuf > ntiles_w) nbuf = ntiles_w < kWarpKernelWarps ? kWarpKernelWarps : ntiles_w;
-      const WarpKernelSmem Lw = warp_kernel_smem(a->N, k.HA, nbuf);
+      const WarpKernelSmem Lw = warp_kernel_smem(a->N, k.HA);
       if (Lw.total_bytes <= 227 * 1024) {
-        if (Lw.total_bytes > 48 * 1024)
-          DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Lw.total_bytes));
-        { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_warp_kernel<<<a->B, kWarpKernelThreads, Lw.total_bytes, stream>>>(k, o, nbuf); }
+#define DUST_WARP_KERNEL(HA4)                                                                                              \
+  do {                                                                                                                     \
+    if (Lw.total_bytes > 48 * 1024)                                                                                        \
+      DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_warp_kernel<HA4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lw.total_bytes)); \
+    { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_warp_kernel<HA4><<<a->B, kWarpKernelThreads, Lw.total_bytes, stream>>>(k, o); } \
+  } while (0)
+        if (k.HA == 20) DUST_WARP_KERNEL(5);
+        else DUST_WARP_KERNEL(0);
+#undef DUST_WARP_KERNEL
         DUST_LAUNCH_OK("svmpc_instance_kernel");
         return DUST_OK;
       }

@@ -286,7 +286,8 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
 // S / P_hi ring of kSBufs = 3 (P_hi overwrites the S it came from), P_lo ring of 2: GEMM1 runs TWO tiles ahead of
 // GEMM2, so the softmax stage of a tile has two tile periods (not one) before the tensor pipe waits for it
 #ifndef DUST_TC_SBUFS
-#define DUST_TC_SBUFS 3          // 2 = the previous pipeline (GEMM1 one tile ahead), kept for A/B builds
+#define DUST_TC_SBUFS 2          // 3 = GEMM1 two tiles ahead of GEMM2 (S/P_hi ring of three): measured SLOWER on B200
+                                 // (5.43 vs 5.04 ms at N = 65536, profiles/r2_phi_sbufs_ab.md) -- kept as a build option
 #endif
 constexpr int kSBufs = DUST_TC_SBUFS;
 constexpr int kLag = kSBufs - 1;  // tiles GEMM2 runs behind GEMM1
