@@ -74,7 +74,7 @@ class GmmArgs(C.Structure):
 class MedianArgs(C.Structure):
     _fields_ = [
         ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("x", _p), ("hist", _p),
-        ("selected", _p), ("row_norms", _p),
+        ("selected", _p), ("row_norms", _p), ("sample_begin", _i), ("sample_end", _i),
     ]
 
 
@@ -129,6 +129,8 @@ SYMBOLS = {
     "dust_median_fast_supported": (C.c_int, [_i, _i]),
     "dust_median_fast_workspace_bytes": (_sz, [_i, _i]),
     "dust_median_fast_prepare": (C.c_int, [C.POINTER(MedianArgs), _p, _sz, _p]),
+    "dust_median_fast_sample_hist_offset": (_sz, [_i, _i]),
+    "dust_median_fast_window": (C.c_int, [C.POINTER(MedianArgs), _p, _sz, _p]),
     "dust_median_fast_count": (C.c_int, [C.POINTER(MedianArgs), _p, _sz, _p]),
     "dust_median_fast_select": (C.c_int, [C.POINTER(MedianArgs), _p, _p]),
     "dust_phi_workspace_bytes": (_sz, [C.POINTER(PhiArgs)]),
@@ -167,7 +169,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.dust_abi_version() != 1:
+    if lib.dust_abi_version() != 2:
         raise ImportError("libdust_b200.so ABI version mismatch: rebuild the library")
     _lib = lib
     return lib

@@ -315,6 +315,8 @@ namespace dust {
 bool median_tc_supported(int N, int D);
 size_t median_tc_workspace(int N, int D);
 int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t stream);
+int median_tc_window(const dust_median_args* a, void* workspace, cudaStream_t stream);
+size_t median_tc_sample_hist_offset(int N, int D);
 int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t stream);
 int median_tc_select(const dust_median_args* a, float* median_out, cudaStream_t stream);
 }  // namespace dust
@@ -330,6 +332,8 @@ static int check_fast(const dust_median_args* a, const void* workspace, size_t b
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   DUST_REQUIRE(r0 >= 0 && r1 <= a->N && r0 < r1 && r0 % 128 == 0 && r1 % 128 == 0, DUST_ERR_INVALID_ARG,
                "%s: row range must be 128-aligned", who);
+  DUST_REQUIRE(a->sample_begin >= 0 && a->sample_end >= a->sample_begin && a->sample_end <= (1 << 20), DUST_ERR_INVALID_ARG,
+               "%s: sample share [%d, %d) outside [0, 2^20)", who, a->sample_begin, a->sample_end);
   return DUST_OK;
 }
 
@@ -337,6 +341,12 @@ extern "C" int dust_median_fast_prepare(const dust_median_args* a, void* workspa
   const int rc = check_fast(a, workspace, bytes, "dust_median_fast_prepare");
   if (rc) return rc;
   return median_tc_prepare(a, workspace, (cudaStream_t)stream_);
+}
+extern "C" size_t dust_median_fast_sample_hist_offset(int32_t N, int32_t D) { return median_tc_sample_hist_offset(N, D); }
+extern "C" int dust_median_fast_window(const dust_median_args* a, void* workspace, size_t bytes, void* stream_) {
+  const int rc = check_fast(a, workspace, bytes, "dust_median_fast_window");
+  if (rc) return rc;
+  return median_tc_window(a, workspace, (cudaStream_t)stream_);
 }
 extern "C" int dust_median_fast_count(const dust_median_args* a, void* workspace, size_t bytes, void* stream_) {
   const int rc = check_fast(a, workspace, bytes, "dust_median_fast_count");

@@ -698,12 +698,13 @@ __device__ __forceinline__ void warp_find_rank(const T* arr, int per_lane, unsig
 // the global one at the end (the sample spreads over a few hundred bins: per-sample global atomics
 // queue up on them).
 __global__ void __launch_bounds__(kMedSampleThreads) med_sample_kernel(const float* __restrict__ x, const float* __restrict__ xn,
-                                                                       int N, int D, unsigned int* __restrict__ hist32) {
+                                                                       int N, int D, unsigned int* __restrict__ hist32,
+                                                                       int k_begin, int k_end) {
   extern __shared__ unsigned int hs[];   // [32768]
   for (int b = threadIdx.x; b < 32768; b += blockDim.x) hs[b] = 0u;
   __syncthreads();
   const bool vec = (D & 3) == 0 && ((((uintptr_t)x) & 15) == 0);   // rows are 16-byte aligned: independent 128-bit loads
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < kMedSample; k += gridDim.x * blockDim.x) {
+  for (int k = k_begin + blockIdx.x * blockDim.x + threadIdx.x; k < k_end; k += gridDim.x * blockDim.x) {
     const uint32_t i = hash32(2u * k + 1u) % (uint32_t)N, j = hash32(2u * k + 0x9e3779b9u) % (uint32_t)N;
     const float* __restrict__ xi = x + (long long)i * D;
     const float* __restrict__ xj = x + (long long)j * D;
@@ -986,7 +987,12 @@ size_t median_tc_workspace(int N, int D) {
   return sizeof(float) * ((size_t)N * (2 * Dp + 1) + 64) + sizeof(unsigned int) * 32768;
 }
 
-// sample + window (run by every rank on the same gathered X: no communication needed)
+size_t median_tc_sample_hist_offset(int N, int D) {
+  const size_t Dp = round_up(D, 8);
+  return sizeof(float) * ((size_t)(N + 63) / 64 * 64 + 2 * (size_t)N * Dp);
+}
+
+// operand images + this rank's share of the sample (sample_begin/end; every rank holds the same gathered X)
 int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t stream) {
   const int N = a->N, D = a->D, Dp = round_up(D, 8);
   float* ws = (float*)workspace;
@@ -1000,9 +1006,18 @@ int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t s
   DUST_CUDA_OK(cudaFuncSetAttribute(med_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned int) * 32768)));
   {
     DUST_TIMED("med_sample_kernel", stream);
-    med_sample_kernel<<<kMedSampleGrid, kMedSampleThreads, sizeof(unsigned int) * 32768, stream>>>(a->x, xn, N, D, hist32);
+    const int k0 = a->sample_end > a->sample_begin ? a->sample_begin : 0;
+    const int k1 = a->sample_end > a->sample_begin ? a->sample_end : kMedSample;
+    const int grid = min(kMedSampleGrid, max(1, ceil_div(k1 - k0, kMedSampleThreads)));
+    med_sample_kernel<<<grid, kMedSampleThreads, sizeof(unsigned int) * 32768, stream>>>(a->x, xn, N, D, hist32, k0, k1);
   }
   DUST_LAUNCH_OK("med_sample_kernel");
+  return DUST_OK;
+}
+
+// window from the (summed) sample histogram
+int median_tc_window(const dust_median_args* a, void* workspace, cudaStream_t stream) {
+  unsigned int* hist32 = (unsigned int*)((char*)workspace + median_tc_sample_hist_offset(a->N, a->D));
   {
     DUST_TIMED("med_sample_select_kernel", stream);
     med_sample_select_kernel<<<1, 1024, 0, stream>>>(hist32, a->selected + 4);

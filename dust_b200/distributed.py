@@ -103,7 +103,9 @@ class ShardedSVGD:
         if self._median_ws is None:
             self._median_ws = self.ops.MedianWorkspace(self.N, self.D, x_all.device)
         if defer_fallback:
-            return self.ops.median_sq_dist_deferred(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist)
+            # every rank draws 1/world of the 2^20 sampled pairs that place the window; the sample histogram (128 KB) is summed
+            return self.ops.median_sq_dist_deferred(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist,
+                                                    sample=row_block(1 << 20, self.rank, self.world))
         return self.ops.median_sq_dist(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist), None
 
     def phi(self, x_local, score_local, bw=None, bw_scale=1.0):

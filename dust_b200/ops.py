@@ -202,20 +202,28 @@ class MedianWorkspace:
         self.fast = bool(lib.dust_median_fast_supported(N, D))
         self.fast_bytes = lib.dust_median_fast_workspace_bytes(N, D) if self.fast else 0
         self.fast_ws = _ws(self.fast_bytes, device) if self.fast else None
+        self.sample_hist = None
+        if self.fast:      # the 32768-bin histogram of the sampled pairs inside the workspace (summed over ranks when sharded)
+            off = int(lib.dust_median_fast_sample_hist_offset(N, D))
+            self.sample_hist = self.fast_ws[off:off + 4 * 32768].view(torch.int32)
         self.flag_host, self.flag_event = None, None      # pinned success flag of the deferred (sharded) form
 
 
-def _median_args(x, ws, rows):
+def _median_args(x, ws, rows, sample=None):
     N, D = x.shape
     a = L.MedianArgs()
     a.N, a.D = N, D
     a.row_begin, a.row_end = (0, N) if rows is None else rows
+    a.sample_begin, a.sample_end = (0, 0) if sample is None else sample
     a.x, a.hist, a.selected, a.row_norms = L.ptr(x), ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
     return a
 
 
 def _median_fast(a, ws, all_reduce):
-    L.call("dust_median_fast_prepare", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream(), launches=4)
+    L.call("dust_median_fast_prepare", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream(), launches=2)
+    if all_reduce is not None and a.sample_end > a.sample_begin:
+        all_reduce(ws.sample_hist)         # every rank drew its own share of the sampled pairs
+    L.call("dust_median_fast_window", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream())
     L.call("dust_median_fast_count", C.byref(a), ws.fast_ws.data_ptr(), ws.fast_bytes, L.stream())
     if all_reduce is not None:
         all_reduce(ws.hist)
@@ -248,7 +256,7 @@ def median_sq_dist(x, ws=None, rows=None, all_reduce=None, allow_fast=True):
     return ws.median
 
 
-def median_sq_dist_deferred(x, ws=None, rows=None, all_reduce=None):
+def median_sq_dist_deferred(x, ws=None, rows=None, all_reduce=None, sample=None):
     """The sharded form of `median_sq_dist`: when the tensor-core window pass applies it runs ALONE -- the radix
     kernels behind it would drag two more histogram all-reduces along that do nothing in the common case -- and
     the success flag travels to pinned host memory behind an event.  -> (median, check): `check()` waits for that
@@ -258,7 +266,7 @@ def median_sq_dist_deferred(x, ws=None, rows=None, all_reduce=None):
     L.require_cuda()
     N, D = x.shape
     ws = ws or MedianWorkspace(N, D, x.device)
-    a = _median_args(x, ws, rows)
+    a = _median_args(x, ws, rows, sample if all_reduce is not None else None)
     ws.hist.zero_()
     ws.selected.zero_()
     if not (ws.fast and a.row_begin % 128 == 0 and a.row_end % 128 == 0):

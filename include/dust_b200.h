@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DUST_B200_ABI_VERSION 1
+#define DUST_B200_ABI_VERSION 2
 
 typedef enum dust_status {
   DUST_OK = 0,
@@ -265,6 +265,8 @@ typedef struct dust_median_args {
   uint32_t* selected;        /* [8] device, zeroed by the caller: {hi16, rank lo, rank hi, bits,
                                 window start, fast-path ok flag, -, bits (fast path)} */
   float* row_norms;          /* [N] device scratch: |x_i|^2, written by pass 0, read by pass 1 */
+  int32_t sample_begin, sample_end;  /* fast path: the share [begin, end) of the 2^20 sampled pairs this rank draws
+                                (0, 0: all of them); sum the sample histogram over the ranks before `window` */
 } dust_median_args;
 
 int dust_median_hist_pass(const dust_median_args* args, int32_t pass, void* stream);
@@ -282,6 +284,11 @@ int dust_median_select(const dust_median_args* args, int32_t pass, float* median
 int dust_median_fast_supported(int32_t N, int32_t D);
 size_t dust_median_fast_workspace_bytes(int32_t N, int32_t D);
 int dust_median_fast_prepare(const dust_median_args* args, void* workspace, size_t workspace_bytes, void* stream);
+/* `prepare` writes the operand images and histograms this rank's share of the sample into the workspace at byte offset
+ * dust_median_fast_sample_hist_offset (uint32[32768]; all-reduce it when the sample is sharded); `window` then
+ * interpolates the median's position in the sample and chooses the window (selected[4..6]). */
+size_t dust_median_fast_sample_hist_offset(int32_t N, int32_t D);
+int dust_median_fast_window(const dust_median_args* args, void* workspace, size_t workspace_bytes, void* stream);
 int dust_median_fast_count(const dust_median_args* args, void* workspace, size_t workspace_bytes, void* stream);
 int dust_median_fast_select(const dust_median_args* args, float* median_out, void* stream);
 

@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/dust_b200.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in dust_b200/_lib.py"
-    assert lib.dust_abi_version() == 1
+    assert lib.dust_abi_version() == 2
     assert b"sm_100a" in lib.dust_build_info()
 
 
