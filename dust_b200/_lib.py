@@ -109,7 +109,7 @@ class MpfArgs(C.Structure):
         ("model", C.POINTER(ModelDesc)), ("B", _i), ("Np", _i), ("n_steps", _i), ("log_space", _i),
         ("x", _p), ("obs0", _p), ("action", _p), ("obs1", _p), ("prior_inv_var", _p),
         ("obs_std", _f), ("bw", _f), ("lr", _f), ("grad_norms", _p),
-        ("workspace", _p), ("workspace_bytes", C.c_size_t),
+        ("workspace", _p), ("workspace_bytes", C.c_size_t), ("bw_dev", _p),
     ]
 
 
@@ -140,6 +140,7 @@ SYMBOLS = {
     "dust_disco_step": (C.c_int, [C.POINTER(DiscoStepArgs), _p]),
     "dust_mpf_workspace_bytes": (C.c_size_t, [C.POINTER(MpfArgs)]),
     "dust_mpf_optimize": (C.c_int, [C.POINTER(MpfArgs), _p]),
+    "dust_silverman_bandwidth": (C.c_int, [_p, _i, _f, _p, _p, _i, _p]),
     "dust_model_step": (C.c_int, [C.POINTER(ModelDesc), _i, _p, _p, _p, _p, _p]),
     "dust_model_cost": (C.c_int, [C.POINTER(ModelDesc), _i, _i, _p, _p, _p, _p]),
     "dust_noise_normal": (C.c_int, [_p, C.c_int64, C.c_uint64, C.c_uint64, _p]),

@@ -2,6 +2,7 @@
 with rollout, cost and soft-min weights computed by the K1 CUDA kernels."""
 import torch
 
+from ..inference.belief import Lazy, resolve
 from .. import _lib as L
 from .. import ops
 from ..utils.utf import MerweScaledUTF
@@ -86,7 +87,8 @@ class MultiDISCO(BaseController):
                 return p.reshape(1, 1, -1), L.PARAMS_BLOCKED, None
             return None, L.PARAMS_BLOCKED, None
         params = params_dist.sample(self._params_shape)
-        params_log_p = params_dist.log_prob(params)
+        drawn = params
+        params_log_p = Lazy(lambda: params_dist.log_prob(drawn))     # read by diagnostics only: formed on first use
         if self._params_log_space is True:
             params = params.exp()
         tiling = L.PARAMS_INTERLEAVED if params.ndim == 1 else L.PARAMS_BLOCKED
@@ -161,7 +163,7 @@ class MultiDISCO(BaseController):
         states = res.get("states")
         # _sigma_rollout hands the actions back as given, _rollout tiled over the parameter draws
         acts = actions if self._tf is not None else actions.unsqueeze(0).expand(self.n_params, -1, -1, -1, -1)
-        return res["costs"], states, acts, res["mppi_weights"], res["params_log_p"]
+        return res["costs"], states, acts, res["mppi_weights"], resolve(res["params_log_p"])
 
     def step(self, strategy="argmax", steps=1, ext_actions=None):
         """disco.py:396-417."""

@@ -22,6 +22,8 @@ struct MpfKParams {
   const float *obs0, *action, *obs1, *prior_inv_var;
   float inv_obs_var, bw, lr;
   float* grad_norms;
+  const float* bw_dev;   // device scalar overriding bw, or nullptr
+  int lanes;             // lanes per particle in mpf_kernel: 32, or 16 / 8 when all particles then fit one pass
 };
 
 // d log N(obs1; f(obs0, a; p), obs_std^2 I) / d x  for one particle (x = p or log p)
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
   float* xs = sm;                       // [Np][DP]
   float* sc = sm + k.Np * DP;           // [Np][DP] score
   float* ph = sc + k.Np * DP;           // [Np][DP] phi
-  __shared__ float red[kMpfMaxThreads / 32];
+  __shared__ float red[kMpfMaxThreads / 8];
   __shared__ float s_cell;
   const long long inst = blockIdx.x;
   float* xg = k.x + inst * (long long)k.Np * DP;
@@ -92,12 +94,21 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
   }
   __syncthreads();
   const float c_cell = s_cell;
-  const float inv_bw2 = 1.0f / (k.bw * k.bw);
+  const float bw = k.bw_dev ? __ldg(k.bw_dev) : k.bw;
+  const float inv_bw2 = 1.0f / (bw * bw);
   const float inv_np = 1.0f / (float)k.Np;
 
-  // One WARP per particle, lanes over the other particles (warp-shuffle sums): with a thread per
-  // particle the 512-particle stress shape was three serial passes of 512 exponentials per thread.
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // A group of LP lanes per particle (LP = 32: one warp), lanes over the other particles (shuffle sums): with a
+  // thread per particle the 512-particle stress shape was three serial passes of 512 exponentials per thread.
+  // Few particles (the demos: 50) take LP = 16 so that ALL of them are worked on in one pass of the CTA.
+  const int LP = k.lanes;
+  const int warp = threadIdx.x / LP, lane = threadIdx.x % LP, nwarps = blockDim.x / LP;
+  // the lanes of THIS group only: the groups of one hardware warp may run different trip counts
+  const unsigned gmask = LP == 32 ? 0xffffffffu : (((1u << LP) - 1u) << (((threadIdx.x & 31) / LP) * LP));
+  auto group_sum = [&](float v) {
+    for (int o = LP >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+    return v;
+  };
   for (int step = 0; step < k.n_steps; ++step) {
     // score_i = grad log-likelihood + grad log GMM(x_i; centres = current particles).  The centres
     // ARE the particles (mpf.py:32-38): the j = i term has exponent 0 and every other one is <= 0,
@@ -110,7 +121,7 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
       float z = 0.f, acc[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) acc[d] = 0.f;
-      for (int j = lane; j < k.Np; j += 32) {
+      for (int j = lane; j < k.Np; j += LP) {
         float q = 0.f;
 #pragma unroll
         for (int d = 0; d < DP; ++d) { const float df = xi[d] - xs[j * DP + d]; q += df * df * piv[d]; }
@@ -119,10 +130,10 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
 #pragma unroll
         for (int d = 0; d < DP; ++d) acc[d] += e * (xs[j * DP + d] - xi[d]);
       }
-      z = warp_sum(z);
+      z = group_sum(z);
 #pragma unroll
       for (int d = 0; d < DP; ++d) {
-        const float a_d = warp_sum(acc[d]);
+        const float a_d = group_sum(acc[d]);
         if (lane == 0) sc[i * DP + d] = g[d] + a_d / z * piv[d];
       }
     }
@@ -133,7 +144,7 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
       float xi[DP], acc[DP];
 #pragma unroll
       for (int d = 0; d < DP; ++d) { xi[d] = xs[i * DP + d]; acc[d] = 0.f; }
-      for (int j = lane; j < k.Np; j += 32) {
+      for (int j = lane; j < k.Np; j += LP) {
         float d2 = 0.f, df[DP];
 #pragma unroll
         for (int d = 0; d < DP; ++d) { df[d] = xi[d] - xs[j * DP + d]; d2 += df[d] * df[d]; }
@@ -143,7 +154,7 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
       }
 #pragma unroll
       for (int d = 0; d < DP; ++d) {
-        const float a_d = warp_sum(acc[d]);
+        const float a_d = group_sum(acc[d]);
         if (lane == 0) { ph[i * DP + d] = a_d; nrm += a_d * a_d; }
       }
     }
@@ -184,7 +195,8 @@ __global__ void __launch_bounds__(256) mpf_coop_kernel(const MpfKParams k, float
   for (int i = 0; i < DP; ++i) piv[i] = k.prior_inv_var[i];
   float c_cell = 0.f;
   if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits) c_cell = grid_lookup(k.m, k.m.grid_bits, o0[0], o0[1]);
-  const float inv_bw2 = 1.0f / (k.bw * k.bw);
+  const float bw = k.bw_dev ? __ldg(k.bw_dev) : k.bw;
+  const float inv_bw2 = 1.0f / (bw * bw);
   const float inv_np = 1.0f / (float)k.Np;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int gwarp = blockIdx.x * nwarps + warp, total_warps = gridDim.x * nwarps;
@@ -297,6 +309,87 @@ static int mpf_coop_grid(const dust_mpf_args* a) {
   return g < kNumSMs ? g : kNumSMs;
 }
 
+namespace dust {
+// KDEpy's silvermans_rule on n <= 4096 values: bitonic sort in shared memory, the two percentiles by linear
+// interpolation and the sample standard deviation in double (numpy works on the float64 copy of the particles)
+__global__ void __launch_bounds__(1024) silverman_kernel(const float* __restrict__ x, int n, int npad, float scale, float* bw_out,
+                                                         float* inv_var_out, int dp) {
+  extern __shared__ float sv[];   // [npad] sorted ascending, padded with +inf
+  __shared__ double red_s[32], red_q[32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < npad; i += blockDim.x) sv[i] = i < n ? x[i] : INFINITY;
+  __syncthreads();
+  for (int size = 2; size <= npad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < npad; i += blockDim.x) {
+        const int j = i ^ stride;
+        if (j > i) {
+          const bool up = (i & size) == 0;
+          const float a = sv[i], b = sv[j];
+          if ((a > b) == up) { sv[i] = b; sv[j] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // mean, then the sum of squared deviations (two passes, double)
+  double s = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) s += (double)sv[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((tid & 31) == 0) red_s[tid >> 5] = s;
+  __syncthreads();
+  double mean = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) mean += red_s[w];
+  mean /= (double)n;
+  double q = 0.0;
+  for (int i = tid; i < n; i += blockDim.x) { const double d = (double)sv[i] - mean; q += d * d; }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  if ((tid & 31) == 0) red_q[tid >> 5] = q;
+  __syncthreads();
+  if (tid == 0) {
+    double ss = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) ss += red_q[w];
+    auto pct = [&](double p) {      // numpy.percentile, linear interpolation
+      const double pos = p / 100.0 * (double)(n - 1);
+      const int lo = (int)floor(pos);
+      const int hi = lo + 1 < n ? lo + 1 : lo;
+      const double t = pos - (double)lo;
+      const double a = (double)sv[lo], b = (double)sv[hi];
+      return t >= 0.5 ? b - (b - a) * (1.0 - t) : a + (b - a) * t;
+    };
+    double bw = 1.0;
+    if (n > 1) {
+      const double sd = sqrt(ss / (double)(n - 1));
+      const double iqr = (pct(75.0) - pct(25.0)) / 1.349;
+      double sigma = iqr > 0.0 ? (sd < iqr ? sd : iqr) : sd;
+      const double fac = pow((double)n * 3.0 / 4.0, -0.2);
+      if (sigma > 0.0) {
+        bw = sigma * fac;
+      } else {
+        const double iqr2 = (pct(99.0) - pct(1.0)) / 4.6526957480816815;
+        bw = iqr2 > 0.0 ? iqr2 * fac : 1.0;
+      }
+    }
+    const float bwf = (float)(bw * (double)scale);
+    bw_out[0] = bwf;
+    if (inv_var_out)
+      for (int d = 0; d < dp; ++d) inv_var_out[d] = 1.0f / (bwf * bwf);
+  }
+}
+}  // namespace dust
+
+extern "C" int dust_silverman_bandwidth(const float* x, int32_t n, float scale, float* bw_out, float* inv_var_out, int32_t dp,
+                                        void* stream_) {
+  DUST_REQUIRE(x && bw_out && n > 0 && n <= 4096 && dp >= 0, DUST_ERR_INVALID_ARG,
+               "dust_silverman_bandwidth: x, bw_out and 1 <= n <= 4096 are required (got n=%d)", n);
+  int npad = 2;
+  while (npad < n) npad <<= 1;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  { DUST_TIMED("silverman_kernel", stream); silverman_kernel<<<1, npad < 1024 ? (npad < 32 ? 32 : npad) : 1024, sizeof(float) * npad, stream>>>(x, n, npad, scale, bw_out, inv_var_out, dp); }
+  DUST_LAUNCH_OK("silverman_kernel");
+  return DUST_OK;
+}
+
 extern "C" size_t dust_mpf_workspace_bytes(const dust_mpf_args* a) {
   if (a == nullptr || a->model == nullptr) return 0;
   const int g = mpf_coop_grid(a);
@@ -310,7 +403,7 @@ extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   DUST_REQUIRE(a->B > 0 && a->Np > 0 && a->n_steps >= 0, DUST_ERR_INVALID_ARG, "dust_mpf_optimize: sizes must be positive");
   DUST_REQUIRE(a->x && a->obs0 && a->action && a->obs1 && a->prior_inv_var, DUST_ERR_INVALID_ARG,
                "dust_mpf_optimize: x, obs0, action, obs1, prior_inv_var are required");
-  DUST_REQUIRE(a->obs_std > 0.f && a->bw > 0.f, DUST_ERR_INVALID_ARG, "dust_mpf_optimize: obs_std and bw must be positive");
+  DUST_REQUIRE(a->obs_std > 0.f && (a->bw > 0.f || a->bw_dev), DUST_ERR_INVALID_ARG, "dust_mpf_optimize: obs_std and bw must be positive");
   const int kind = a->model->kind, dp = model_dp(kind);
   const size_t smem = sizeof(float) * 3 * (size_t)a->Np * dp;
   DUST_REQUIRE(smem <= 200 * 1024, DUST_ERR_UNSUPPORTED, "dust_mpf_optimize: Np=%d too large for one CTA", a->Np);
@@ -319,6 +412,7 @@ extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   k.B = a->B; k.Np = a->Np; k.dp = dp; k.n_steps = a->n_steps; k.log_space = a->log_space;
   k.x = a->x; k.obs0 = a->obs0; k.action = a->action; k.obs1 = a->obs1; k.prior_inv_var = a->prior_inv_var;
   k.inv_obs_var = 1.0f / (a->obs_std * a->obs_std); k.bw = a->bw; k.lr = a->lr; k.grad_norms = a->grad_norms;
+  k.bw_dev = a->bw_dev; k.lanes = 32;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int coop = mpf_coop_grid(a);
   if (coop && a->workspace && a->workspace_bytes >= dust_mpf_workspace_bytes(a) && a->n_steps > 0) {
@@ -334,6 +428,9 @@ extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   int kMpfThreads = 32 * (a->Np < 32 ? a->Np : 32);
   if ((long long)a->B * kMpfThreads > (long long)kNumSMs * 2048) kMpfThreads = 256;
   if (kMpfThreads < 64) kMpfThreads = 64;
+  // 33..64 particles of few instances (the demos' 50): 16 lanes per particle cover them all in ONE pass of a
+  // 1024-thread CTA instead of two passes of 32 warps (each pass is latency bound: model step + Jacobian per particle)
+  if (a->Np > 32 && a->Np <= 64 && kMpfThreads == 1024) k.lanes = 16;
   if (kind == DUST_MODEL_PENDULUM) {
     if (smem > 48 * 1024) DUST_CUDA_OK(cudaFuncSetAttribute(mpf_kernel<DUST_MODEL_PENDULUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     { DUST_TIMED("mpf_kernel", stream); mpf_kernel<DUST_MODEL_PENDULUM><<<a->B, kMpfThreads, smem, stream>>>(k); }

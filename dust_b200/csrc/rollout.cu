@@ -6,6 +6,7 @@
 // Reference: dust/controllers/disco.py:139-209 (rollout), :294-346 (cost), :380-393 (soft-min),
 // dust/inference/likelihoods.py:81-135, dust/inference/svmpc.py:46-54.
 // Compiled with -fmad=false (see models.cuh).
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "models.cuh"
@@ -727,6 +728,155 @@ __global__ void __launch_bounds__(kFusedThreads / TPT, TPT == 2 ? 5 : DUST_FUSED
 }
 
 // ---------------------------------------------------------------------------------------
+// The rest of the SVGD step for ONE instance, by all threads of a CTA (blockDim.x a multiple of 32), on data the CTA
+// holds in shared memory: th_s [N][thst] the particles, gl_s [N][thst] the likelihood gradient, ll_s [N] the
+// log-likelihood.  (svmpc.py:38-95, 128-200: prior score, phi, SGD step, weights / argmax / shift.)  Work is spread
+// over (particle, centre) pairs and (particle, dimension) items -- any N <= 32 and any D = H*A that fits shared memory.
+// Scratch: sc_s, nw_s [N][thst]; Lg_s, Kx_s [N][N]; lmix_s, logw_s [N].
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void svmpc_tail(const RolloutKParams& k, const TailParams& t, long long inst, int A,
+                                           const float* th_s, int thst, const float* gl_s, const float* ll_s, float* sc_s,
+                                           float* nw_s, float* Lg_s, float* Kx_s, float* lmix_s, float* logw_s) {
+  const int N = k.N, HA = k.HA;
+  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const float* mu_g = t.mu ? t.mu + inst * (long long)N * HA : nullptr;
+  if (warp == 0) warp_log_mix(t.mix ? t.mix + inst * N : nullptr, N, lmix_s);
+  __syncthreads();
+  // (i, k): iv-weighted distance to centre k (GMM logits) and the kernel among the particles
+  for (int p = tid; p < N * N; p += nthr) {
+    const int i = p / N, kk = p - i * N;
+    const float* xi = th_s + i * thst;
+    const float* xk = th_s + kk * thst;
+    float q = 0.f, dxx = 0.f;
+    if (t.aliased) {
+      for (int d = 0; d < HA; ++d) {
+        const float df = xi[d] - xk[d];
+        const float d2 = df * df;
+        dxx += d2;
+        q = fmaf(d2, __ldg(t.inv_var + d), q);
+      }
+    } else {
+      const float* ck = mu_g + kk * HA;
+      for (int d = 0; d < HA; ++d) {
+        const float df = xi[d] - xk[d];
+        dxx = fmaf(df, df, dxx);
+        const float dc = xi[d] - __ldg(ck + d);
+        q = fmaf(dc * dc, __ldg(t.inv_var + d), q);
+      }
+    }
+    Lg_s[p] = lmix_s[kk] - 0.5f * q;
+    Kx_s[p] = expf(-t.gamma * dxx);
+  }
+  __syncthreads();
+  // responsibilities r_ik = softmax_k(logits): a warp per particle, lanes over the centres (N <= 32)
+  for (int i = warp; i < N; i += nwarps) {
+    const float l = lane < N ? Lg_s[i * N + lane] : -INFINITY;
+    const float mx = warp_max(l);
+    const float e = lane < N ? expf(l - mx) : 0.f;
+    const float z = warp_sum(e);
+    if (lane < N) Lg_s[i * N + lane] = e / z;
+  }
+  __syncthreads();
+  // (i, d): prior score, total score
+  for (int e = tid; e < N * HA; e += nthr) {
+    const int i = e / HA, d = e - i * HA;
+    const float xi = th_s[i * thst + d];
+    float a = 0.f;
+    if (t.aliased) {
+      for (int kk = 0; kk < N; ++kk) a = fmaf(Lg_s[i * N + kk], th_s[kk * thst + d] - xi, a);
+    } else {
+      for (int kk = 0; kk < N; ++kk) a = fmaf(Lg_s[i * N + kk], __ldg(mu_g + kk * HA + d) - xi, a);
+    }
+    sc_s[i * thst + d] = gl_s[i * thst + d] + a * __ldg(t.inv_var + d);
+  }
+  __syncthreads();
+  // (i, d): phi_i = sum_j K_ij (c1 score_j + c2 (x_i - x_j)); SGD step
+  for (int e = tid; e < N * HA; e += nthr) {
+    const int i = e / HA, d = e - i * HA;
+    const float xi = th_s[i * thst + d];
+    float accp = 0.f;
+    for (int j = 0; j < N; ++j) accp = fmaf(Kx_s[i * N + j], fmaf(t.c2, xi - th_s[j * thst + d], t.c1 * sc_s[j * thst + d]), accp);
+    const float nv = xi + t.lr * accp;
+    nw_s[i * thst + d] = nv;
+    const long long oidx = (inst * N + i) * (long long)HA + d;
+    if (t.phi) t.phi[oidx] = accp;
+    if (t.theta_out) t.theta_out[oidx] = nv;
+  }
+  if (!t.do_forward) return;
+  __syncthreads();
+  // weights from the PRE-update costs and the prior evaluated at the POST-update particles (quirk H19: an
+  // aliased prior's centres are the updated particles themselves)
+  for (int p = tid; p < N * N; p += nthr) {
+    const int i = p / N, kk = p - i * N;
+    const float* xi = nw_s + i * thst;
+    float q = 0.f;
+    if (t.aliased) {
+      const float* ck = nw_s + kk * thst;
+      for (int d = 0; d < HA; ++d) { const float dc = xi[d] - ck[d]; q = fmaf(dc * dc, __ldg(t.inv_var + d), q); }
+    } else {
+      const float* ck = mu_g + kk * HA;
+      for (int d = 0; d < HA; ++d) { const float dc = xi[d] - __ldg(ck + d); q = fmaf(dc * dc, __ldg(t.inv_var + d), q); }
+    }
+    Lg_s[p] = lmix_s[kk] - 0.5f * q;
+  }
+  __syncthreads();
+  for (int i = warp; i < N; i += nwarps) {
+    const float l = lane < N ? Lg_s[i * N + lane] : -INFINITY;
+    const float mx = warp_max(l);
+    const float z = warp_sum(lane < N ? expf(l - mx) : 0.f);
+    if (lane == 0) logw_s[i] = ll_s[i] + ((mx + logf(z)) + t.log_norm);
+  }
+  __syncthreads();
+  __shared__ int s_istar;
+  if (warp == 0) {
+    const float lw = lane < N ? logw_s[lane] : -INFINITY;
+    const float mx = warp_max(lw);
+    const float z = warp_sum(lane < N ? expf(lw - mx) : 0.f);
+    const float lse = mx + logf(z);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    if (lane < N) {
+      const float pw = expf(lw - lse);
+      t.p_weights[inst * N + lane] = pw;
+      if (t.mix_next) t.mix_next[inst * N + lane] = t.weighted ? pw : 1.0f;
+      best = pw; bi = lane;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) {
+      s_istar = bi;
+      if (t.i_star) t.i_star[inst] = bi;
+    }
+  }
+  __syncthreads();
+  const int is = s_istar;
+  if (t.a_seq)
+    for (int d = tid; d < HA; d += nthr) t.a_seq[inst * HA + d] = nw_s[is * thst + d];
+  if (t.theta_next) {
+    const int shift_lim = (k.H - 1) * A;
+    for (int e = tid; e < N * HA; e += nthr) {
+      const int n2 = e / HA, d = e - n2 * HA;
+      float v;
+      if (d < shift_lim) {
+        v = nw_s[n2 * thst + d + A];
+      } else if (t.roll == DUST_ROLL_REPEAT) {
+        v = nw_s[n2 * thst + d];
+      } else {
+        const int a = d - shift_lim;
+        float sm = 0.f;
+        for (int h = 0; h < k.H; ++h) sm += nw_s[n2 * thst + h * A + a];
+        v = sm / (float)k.H;
+      }
+      t.theta_next[inst * (long long)N * HA + e] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // Second generation of the fused per-instance kernel (packed pendulum path; H*A a multiple of 4, N <= 32).
 //
 // What limited the first one (ncu, profiles/r1_fused_instance_kernel_ncu.md): 96 registers -- 20 of them the
@@ -955,146 +1105,193 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
   }
   if (!o.tail.enabled) return;
 
-  // ------------------------------------------------------------------------------------
-  // tail (svmpc.py:38-95, 128-200): prior score, phi, SGD step, weights / argmax / shift, on pairs and items
-  // ------------------------------------------------------------------------------------
-  const TailParams& t = o.tail;
-  const float* mu_g = t.mu ? t.mu + inst * (long long)N * HA : nullptr;
-  if (warp == 0) warp_log_mix(t.mix ? t.mix + inst * N : nullptr, N, lmix_s);
-  __syncthreads();
-  // (i, k): iv-weighted distance to centre k (GMM logits) and the kernel among the particles
-  for (int p = tid; p < N * N; p += kWarpKernelThreads) {
-    const int i = p / N, kk = p - i * N;
-    const float* xi = th_s + i * thst;
-    const float* xk = th_s + kk * thst;
-    float q = 0.f, dxx = 0.f;
-    if (t.aliased) {
-      for (int d = 0; d < HA; ++d) {
-        const float df = xi[d] - xk[d];
-        const float d2 = df * df;
-        dxx += d2;
-        q = fmaf(d2, __ldg(t.inv_var + d), q);
-      }
-    } else {
-      const float* ck = mu_g + kk * HA;
-      for (int d = 0; d < HA; ++d) {
-        const float df = xi[d] - xk[d];
-        dxx = fmaf(df, df, dxx);
-        const float dc = xi[d] - __ldg(ck + d);
-        q = fmaf(dc * dc, __ldg(t.inv_var + d), q);
-      }
-    }
-    Lg_s[p] = lmix_s[kk] - 0.5f * q;
-    Kx_s[p] = expf(-t.gamma * dxx);
-  }
-  __syncthreads();
-  // responsibilities r_ik = softmax_k(logits): a warp per particle, lanes over the centres (N <= 32)
-  for (int i = warp; i < N; i += kWarpKernelWarps) {
-    const float l = lane < N ? Lg_s[i * N + lane] : -INFINITY;
-    const float mx = warp_max(l);
-    const float e = lane < N ? expf(l - mx) : 0.f;
-    const float z = warp_sum(e);
-    if (lane < N) Lg_s[i * N + lane] = e / z;
-  }
-  __syncthreads();
-  // (i, d): prior score, total score
-  for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
-    const int i = e / HA, d = e - i * HA;
-    const float xi = th_s[i * thst + d];
-    float a = 0.f;
-    if (t.aliased) {
-      for (int kk = 0; kk < N; ++kk) a = fmaf(Lg_s[i * N + kk], th_s[kk * thst + d] - xi, a);
-    } else {
-      for (int kk = 0; kk < N; ++kk) a = fmaf(Lg_s[i * N + kk], __ldg(mu_g + kk * HA + d) - xi, a);
-    }
-    sc_s[i * thst + d] = gl_s[i * thst + d] + a * __ldg(t.inv_var + d);
-  }
-  __syncthreads();
-  // (i, d): phi_i = sum_j K_ij (c1 score_j + c2 (x_i - x_j)); SGD step
-  for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
-    const int i = e / HA, d = e - i * HA;
-    const float xi = th_s[i * thst + d];
-    float accp = 0.f;
-    for (int j = 0; j < N; ++j) accp = fmaf(Kx_s[i * N + j], fmaf(t.c2, xi - th_s[j * thst + d], t.c1 * sc_s[j * thst + d]), accp);
-    const float nv = xi + t.lr * accp;
-    nw_s[i * thst + d] = nv;
-    const long long oidx = (inst * N + i) * (long long)HA + d;
-    if (t.phi) t.phi[oidx] = accp;
-    if (t.theta_out) t.theta_out[oidx] = nv;
-  }
-  if (!t.do_forward) return;
-  __syncthreads();
-  // weights from the PRE-update costs and the prior evaluated at the POST-update particles (quirk H19: an
-  // aliased prior's centres are the updated particles themselves)
-  for (int p = tid; p < N * N; p += kWarpKernelThreads) {
-    const int i = p / N, kk = p - i * N;
-    const float* xi = nw_s + i * thst;
-    float q = 0.f;
-    if (t.aliased) {
-      const float* ck = nw_s + kk * thst;
-      for (int d = 0; d < HA; ++d) { const float dc = xi[d] - ck[d]; q = fmaf(dc * dc, __ldg(t.inv_var + d), q); }
-    } else {
-      const float* ck = mu_g + kk * HA;
-      for (int d = 0; d < HA; ++d) { const float dc = xi[d] - __ldg(ck + d); q = fmaf(dc * dc, __ldg(t.inv_var + d), q); }
-    }
-    Lg_s[p] = lmix_s[kk] - 0.5f * q;
-  }
-  __syncthreads();
-  for (int i = warp; i < N; i += kWarpKernelWarps) {
-    const float l = lane < N ? Lg_s[i * N + lane] : -INFINITY;
-    const float mx = warp_max(l);
-    const float z = warp_sum(lane < N ? expf(l - mx) : 0.f);
-    if (lane == 0) logw_s[i] = ll_s[i] + ((mx + logf(z)) + t.log_norm);
-  }
-  __syncthreads();
-  __shared__ int s_istar;
-  if (warp == 0) {
-    const float lw = lane < N ? logw_s[lane] : -INFINITY;
-    const float mx = warp_max(lw);
-    const float z = warp_sum(lane < N ? expf(lw - mx) : 0.f);
-    const float lse = mx + logf(z);
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    if (lane < N) {
-      const float pw = expf(lw - lse);
-      t.p_weights[inst * N + lane] = pw;
-      if (t.mix_next) t.mix_next[inst * N + lane] = t.weighted ? pw : 1.0f;
-      best = pw; bi = lane;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ob = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-    }
-    if (lane == 0) {
-      s_istar = bi;
-      if (t.i_star) t.i_star[inst] = bi;
-    }
-  }
-  __syncthreads();
-  const int is = s_istar;
-  if (t.a_seq)
-    for (int d = tid; d < HA; d += kWarpKernelThreads) t.a_seq[inst * HA + d] = nw_s[is * thst + d];
-  if (t.theta_next) {
-    const int shift_lim = (k.H - 1);     // A = 1
-    for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
-      const int n2 = e / HA, d = e - n2 * HA;
-      float v;
-      if (d < shift_lim) {
-        v = nw_s[n2 * thst + d + 1];
-      } else if (t.roll == DUST_ROLL_REPEAT) {
-        v = nw_s[n2 * thst + d];
-      } else {
-        float sm = 0.f;
-        for (int h = 0; h < k.H; ++h) sm += nw_s[n2 * thst + h];
-        v = sm / (float)k.H;
-      }
-      t.theta_next[inst * (long long)N * HA + e] = v;
-    }
-  }
+  svmpc_tail(k, o.tail, inst, 1, th_s, thst, gl_s, ll_s, sc_s, nw_s, Lg_s, Kx_s, lmix_s, logw_s);
 }
 #endif
+
+// ---------------------------------------------------------------------------------------
+// Few instances (the demo shapes: ONE instance, 384 trajectories x 4-8 parameter draws): the whole control step in one
+// launch of a thread-block CLUSTER per instance.  The instance's trajectories are cut into C = 8 row blocks, one per
+// CTA; inside a CTA a thread rolls out one (row, parameter draw) pair, so the 3072 / 1536 rollouts of the two demo
+// configurations spread over 8 SMs instead of queueing in one CTA.  Two exchanges through distributed shared memory:
+//   1. every CTA writes the finished costs of its rows into the cost vector of ALL CTAs (cluster.sync), so each can
+//      form the per-policy soft-min statistics on its own;
+//   2. every CTA sends its partial weighted column sums (the analytic likelihood gradient, svmpc.py:46-54) to rank 0
+//      (cluster.sync), which adds them in rank order and runs the tail (svmpc_tail) for the instance.
+// Costs per (row, draw) come from trajectory_cost_sum and are averaged in draw order: bit-identical to the fused
+// per-instance kernels.  Reference: disco.py:139-209, 294-346, 380-393; likelihoods.py:81-135; svmpc.py:32-95, 128-200.
+// ---------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+constexpr int kClusterSize = 8;
+constexpr int kClusterMaxThreads = 512;
+
+struct ClusterLayout {
+  int rows, PT, threads, stride, thst;
+  int off_tile, off_th, off_grid, off_cpart, off_costs, off_w, off_stat, off_recv, off_tail, total_floats;
+};
+static ClusterLayout cluster_layout(int SN, int N, int HA, int P, int grid_words) {
+  ClusterLayout L;
+  L.rows = (SN + kClusterSize - 1) / kClusterSize;
+  L.PT = P < kClusterMaxThreads / L.rows ? P : kClusterMaxThreads / L.rows;
+  if (L.PT < 1) L.PT = 1;
+  L.threads = (L.rows * L.PT + 31) & ~31;
+  if (L.threads < 128) L.threads = 128;
+  L.stride = padded_stride(HA);
+  L.thst = (HA + 3) & ~3;
+  int off = 0;
+  auto take = [&](int n) { const int o = off; off += (n + 3) & ~3; return o; };
+  L.off_tile = take(L.rows * L.stride);
+  L.off_th = take(N * L.thst);
+  L.off_grid = take(grid_words);
+  L.off_cpart = take(P * L.rows);
+  L.off_costs = take(SN);
+  L.off_w = take(L.rows);
+  L.off_stat = take(4 * N);                       // cmin, za, csum, ll per policy
+  L.off_recv = take(kClusterSize * N * HA);       // rank 0: the partial column sums of every CTA
+  L.off_tail = take(3 * N * L.thst + 2 * N * N + 2 * N);
+  L.total_floats = off;
+  return L;
+}
+
+template <int MODEL>
+__global__ void __launch_bounds__(kClusterMaxThreads) svmpc_cluster_kernel(const RolloutKParams k, const FusedOut o, const ClusterLayout L) {
+  constexpr int A = (MODEL == DUST_MODEL_PENDULUM) ? 1 : 2;
+  extern __shared__ __align__(16) float smem[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const long long inst = blockIdx.x / kClusterSize;
+  const int N = k.N, HA = k.HA, SN = k.SN, P = k.P;
+  const int tid = threadIdx.x, nthr = blockDim.x, warp = tid >> 5, lane = tid & 31, nwarps = nthr >> 5;
+  const int stride = L.stride, thst = L.thst;
+  float* tile = smem + L.off_tile;
+  float* th_s = smem + L.off_th;
+  uint32_t* grid_s = reinterpret_cast<uint32_t*>(smem + L.off_grid);
+  float* cpart = smem + L.off_cpart;
+  float* costs_all = smem + L.off_costs;
+  float* w_s = smem + L.off_w;
+  float* cmin_s = smem + L.off_stat;
+  float* za_s = cmin_s + N;
+  float* ll_s = za_s + 2 * N;
+  float* recv = smem + L.off_recv;
+  const int r0 = rank * L.rows;
+  const int rows = max(0, min(L.rows, SN - r0));
+
+  // ---- stage this CTA's noise rows (padded), the policy means, the occupancy bits ----
+  const float* __restrict__ src = k.noise + (inst * SN + r0) * (long long)HA;
+  if ((HA & 3) == 0 && ((((uintptr_t)k.noise) & 15) == 0)) {
+    const int HA4 = HA >> 2;
+    for (int e = tid; e < rows * HA4; e += nthr) {
+      const int r = e / HA4, c4 = e - r * HA4;
+      *reinterpret_cast<float4*>(tile + r * stride + 4 * c4) = __ldg(reinterpret_cast<const float4*>(src) + e);
+    }
+  } else {
+    for (int e = tid; e < rows * HA; e += nthr) {
+      const int r = e / HA, c = e - r * HA;
+      tile[r * stride + c] = __ldg(src + e);
+    }
+  }
+  for (int e = tid; e < N * HA; e += nthr) {
+    const int nn = e / HA;
+    th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
+  }
+  if (MODEL == DUST_MODEL_PARTICLE && k.m.grid_bits != nullptr) {
+    const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
+    for (int w = tid; w < words; w += nthr) grid_s[w] = __ldg(k.m.grid_bits + w);
+  }
+  __syncthreads();
+
+  // ---- rollouts: thread <-> (row, draw group); one trajectory per (row, draw) ----
+  const float sg0 = k.sigma[0], sg1 = k.sigma[A - 1];
+  {
+    const int row = tid % L.rows, pg = tid / L.rows;
+    if (row < rows && pg < L.PT) {
+      const int j = r0 + row;
+      const float* __restrict__ erow = tile + row * stride;
+      const float* __restrict__ th_row = th_s + (j % N) * thst;
+      const bool small = small_angle_horizon<MODEL>(k, inst);
+      for (int p = pg; p < P; p += L.PT) {
+        cpart[p * L.rows + row] =
+            small ? trajectory_cost_sum<MODEL, true, false, true>(k, erow, grid_s, inst, j, p, p + 1, th_row, sg0, sg1)
+                  : trajectory_cost_sum<MODEL, false, false, true>(k, erow, grid_s, inst, j, p, p + 1, th_row, sg0, sg1);
+      }
+    }
+  }
+  __syncthreads();
+  // mean over the draws in draw order (disco.py:330), then into the cost vector of every CTA of the cluster
+  if (tid < rows) {
+    float cs = 0.f;
+    for (int p = 0; p < P; ++p) cs = cs + cpart[p * L.rows + tid];
+    const float cost = (P == 1) ? cs : cs / (float)P;
+    if (o.costs) o.costs[inst * SN + r0 + tid] = cost;
+    for (int c = 0; c < kClusterSize; ++c) cluster.map_shared_rank(costs_all, c)[r0 + tid] = cost;
+  }
+  cluster.sync();
+
+  // ---- per-policy soft-min statistics (every CTA, same arithmetic as policy_softmin_kernel) ----
+  for (int n = warp; n < N; n += nwarps) {
+    float cmin = INFINITY, csum = 0.f;
+    for (int s2 = lane; s2 < k.S; s2 += 32) {
+      const float c = costs_all[s2 * N + n];
+      cmin = fminf(cmin, c);
+      csum += c;
+    }
+    cmin = warp_min(cmin);
+    csum = warp_sum(csum);
+    float za = 0.f;
+    for (int s2 = lane; s2 < k.S; s2 += 32) za += expf(-o.alpha * (costs_all[s2 * N + n] - cmin));
+    za = warp_sum(za);
+    if (lane == 0) {
+      cmin_s[n] = cmin;
+      za_s[n] = za;
+      const float ll = (o.likelihood == DUST_LIK_EXP_UTILITY) ? (-o.alpha * cmin + logf(za)) - logf((float)k.S)   // likelihoods.py:133-135
+                                                              : -o.alpha * (csum / (float)k.S);                   // likelihoods.py:119
+      ll_s[n] = ll;
+      if (rank == 0 && o.log_lik) o.log_lik[inst * N + n] = ll;
+    }
+  }
+  __syncthreads();
+  if (o.grad_lik || o.tail.enabled) {
+    if (tid < rows) {
+      const int n = (r0 + tid) % N;
+      w_s[tid] = expf(-o.alpha * (costs_all[r0 + tid] - cmin_s[n])) / za_s[n];
+    }
+    __syncthreads();
+    // partial weighted column sums over this CTA's rows: (a - theta)/sigma^2 = eps/sigma
+    float* dst = cluster.map_shared_rank(recv, 0) + rank * N * HA;
+    const int first_n = r0 % N;
+    for (int col = tid; col < N * HA; col += nthr) {
+      const int n = col / HA, c = col - n * HA;
+      const float sg = (c % A) ? sg1 : sg0;
+      const float f = (1.0f / (sg * sg)) * sg;
+      float acc = 0.f;
+      int row = n - first_n;
+      if (row < 0) row += N;
+      for (; row < rows; row += N) acc = fmaf(w_s[row] * f, tile[row * stride + c], acc);
+      dst[col] = acc;
+    }
+  }
+  cluster.sync();
+  if (rank != 0) return;
+  float* tail_s = smem + L.off_tail;
+  float* gl_s = tail_s;
+  float* sc_s = gl_s + N * thst;
+  float* nw_s = sc_s + N * thst;
+  float* Lg_s = nw_s + N * thst;
+  float* Kx_s = Lg_s + N * N;
+  float* lmix_s = Kx_s + N * N;
+  float* logw_s = lmix_s + N;
+  if (o.grad_lik || o.tail.enabled) {
+    for (int col = tid; col < N * HA; col += nthr) {
+      float g = 0.f;
+      for (int c = 0; c < kClusterSize; ++c) g += recv[c * N * HA + col];
+      const int n = col / HA;
+      if (o.grad_lik) o.grad_lik[inst * (long long)N * HA + col] = g;
+      gl_s[n * thst + (col - n * HA)] = g;
+    }
+  }
+  if (!o.tail.enabled) return;
+  svmpc_tail(k, o.tail, inst, A, th_s, thst, gl_s, ll_s, sc_s, nw_s, Lg_s, Kx_s, lmix_s, logw_s);
+}
 
 // ---------------------------------------------------------------------------------------
 // per-policy statistics: combine parameter chunks, log-likelihood, soft-min weights, mixture
@@ -1339,6 +1536,22 @@ static bool fused_path_ok(const dust_rollout_args* a, const RolloutPlan& pl, boo
          HA <= 32 && a->N <= kFusedThreads && (long long)a->B * 2 >= kNumSMs && (a->log_lik || a->grad_lik || tail);
 }
 
+// few instances: the cluster kernel (one thread-block cluster per instance) produces the same outputs in one launch
+static bool cluster_path_ok(const dust_rollout_args* a, bool reduce_only, ClusterLayout* out) {
+  static const bool off = getenv("DUST_B200_NO_CLUSTER") != nullptr;
+  if (off || reduce_only || a->p_end > a->p_begin) return false;
+  if (a->lik_weights || a->mppi_weights || a->mppi_delta || a->mix || a->states || a->sigma_weights || a->ctrl_mat) return false;
+  if (!a->theta || (long long)a->B * 2 >= kNumSMs || a->N > 32) return false;
+  const int kind = a->model->kind, HA = a->H * model_da(kind), P = a->params ? a->P : 1;
+  const long long SN = (long long)a->S * a->N;
+  if (P > 64 || SN > (long long)kClusterSize * kClusterMaxThreads || HA > 256) return false;
+  const int words = (kind == DUST_MODEL_PARTICLE && a->model->grid_bits) ? (a->model->grid_nx * a->model->grid_ny + 31) / 32 : 0;
+  const ClusterLayout L = cluster_layout((int)SN, a->N, HA, P, words);
+  if ((size_t)L.total_floats * 4 > 200 * 1024) return false;
+  if (out) *out = L;
+  return true;
+}
+
 }  // namespace dust
 
 using namespace dust;
@@ -1348,7 +1561,7 @@ extern "C" int dust_rollout_plan(const dust_rollout_args* a, int32_t plan[5]) {
   int rc = validate_model(a->model);
   if (rc) return rc;
   const RolloutPlan pl = plan_rollout(a);
-  plan[0] = fused_path_ok(a, pl, false, false) ? 1 : 0;
+  plan[0] = cluster_path_ok(a, false, nullptr) && (a->log_lik || a->grad_lik) ? 2 : (fused_path_ok(a, pl, false, false) ? 1 : 0);
   plan[1] = pl.PC; plan[2] = pl.Pchunk; plan[3] = pl.NSUB; plan[4] = pl.parts;
   return DUST_OK;
 }
@@ -1414,10 +1627,39 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
   const int stride = padded_stride(k.HA);
   const size_t grid_bytes = (kind == DUST_MODEL_PARTICLE && a->model->grid_bits)
                                 ? sizeof(uint32_t) * ((a->model->grid_nx * a->model->grid_ny + 31) / 32) : 0;
+  // ---- few instances: one thread-block cluster per instance, the whole step in one launch ----
+  ClusterLayout CL;
+  if (cluster_path_ok(a, reduce_only, &CL) && (a->log_lik || a->grad_lik || tail)) {
+    FusedOut o{a->costs, a->log_lik, a->grad_lik, a->likelihood, a->alpha, TailParams{}};
+    if (tail) o.tail = *tail;
+    k.cost_out = nullptr;
+    const size_t csmem = (size_t)CL.total_floats * 4;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a->B * kClusterSize), 1, 1);
+    cfg.blockDim = dim3((unsigned)CL.threads, 1, 1);
+    cfg.dynamicSmemBytes = csmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kClusterSize; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+#define DUST_CLUSTER(MODEL)                                                                                               \
+  do {                                                                                                                    \
+    if (csmem > 48 * 1024)                                                                                                \
+      DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_cluster_kernel<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem)); \
+    { DUST_TIMED("svmpc_cluster_kernel", stream); DUST_CUDA_OK(cudaLaunchKernelEx(&cfg, svmpc_cluster_kernel<MODEL>, k, o, CL)); } \
+  } while (0)
+    if (kind == DUST_MODEL_PENDULUM) DUST_CLUSTER(DUST_MODEL_PENDULUM);
+    else DUST_CLUSTER(DUST_MODEL_PARTICLE);
+#undef DUST_CLUSTER
+    DUST_LAUNCH_OK("svmpc_cluster_kernel");
+    return DUST_OK;
+  }
   // ---- fused per-instance path: everything the SVGD step needs in one launch -----------------
   const bool fused_ok = fused_path_ok(a, pl, tail != nullptr, reduce_only);
   DUST_REQUIRE(fused_ok || !tail, DUST_ERR_UNSUPPORTED,
-               "dust_svmpc_step: the fused control step needs B >= 74, H*A <= 32, no parameter chunking");
+               "dust_svmpc_step: the one-launch control step needs N <= 32 and either few instances (B < 74: S*N <= 4096, "
+               "P <= 64) or many (B >= 74: H*A <= 32)");
   if (fused_ok) {
     const int thst_h = (k.HA + 3) & ~3;
     const size_t fsmem = sizeof(float) * ((size_t)2 * kFusedThreads * stride + (size_t)a->N * thst_h +

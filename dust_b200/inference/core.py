@@ -55,6 +55,7 @@ class SvmpcCore:
         self.sharded = sharded
         self._make_opt, self._opt = optimizer, None
         self.last = {}
+        self._pending = None      # forward results the one-launch step already produced (consumed by forward_step)
 
     @property
     def ops(self):
@@ -73,9 +74,38 @@ class SvmpcCore:
     def _flat(self, t):
         return t.reshape(self.B, self.N, self.D)
 
-    def optimize_step(self, state0, eps, params=None, tiling=L.PARAMS_BLOCKED, want_states=False):
+    def _one_launch(self, state0, eps, params, tiling, lean=False):
+        """The whole SVGD step AND the forward results in one launch (`dust_svmpc_step`: the warp kernel for many
+        instances, the cluster kernel for few), when the configuration allows it.  -> outputs or None."""
+        if not (self.kernel == "gpytorch" and self.grad == "analytic" and self.roll_strategy != L.ROLL_RESAMPLE
+                and self._make_opt is None and self.sharded is None and getattr(self, "_fused_ok", True)):
+            return None
+        ell2 = self.lengthscale ** 2
+        want = ("costs", "log_lik", "theta_out") + (() if lean else ("grad_lik", "phi"))
+        try:
+            return self.ops.svmpc_step(self.spec, state0, eps, self.theta, self.sigma, self.mu, self.mix, self.inv_var,
+                                       self.log_norm, 1.0 / (2.0 * ell2), 1.0 / self.N, -1.0 / ell2, self.lr, params=params,
+                                       param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
+                                       temperature=self.temperature, aliased=self.aliased, do_forward=True,
+                                       roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior, want=want)
+        except NotImplementedError:
+            self._fused_ok = False
+            return None
+
+    def optimize_step(self, state0, eps, params=None, tiling=L.PARAMS_BLOCKED, want_states=False, lean=False):
         """One SVGD step on the policy particles.  state0 [B,ds], eps [B,S,N,H,A] standard normal,
-        params [B,P,dp] | None.  Updates theta in place of the old tensor (new storage)."""
+        params [B,P,dp] | None.  Updates theta in place of the old tensor (new storage).  lean: the one-launch
+        step skips the diagnostic outputs (likelihood gradient, phi)."""
+        self._pending = None
+        if not want_states:
+            out = self._one_launch(state0, eps, params, tiling, lean)
+            if out is not None:
+                # the particles after the update (before the roll); what forward_step would compute rides along
+                self.theta = out["theta_out"]
+                self._pending = out
+                self.last = dict(costs=out["costs"], log_lik=out["log_lik"], grad_lik=out.get("grad_lik"), grad_pri=None,
+                                 phi=out.get("phi"), states=None, lik_weights=None, theta1=out["theta_out"])
+                return self.last
         mu = self.theta if self.aliased else self.mu
         _, grad_pri = self.ops.gmm(self._flat(self.theta), self._flat(mu), self.mix, self.inv_var, self.log_norm,
                               want_log_prob=False)
@@ -126,25 +156,7 @@ class SvmpcCore:
         """optimize_step + forward_step.  One kernel launch when the shape qualifies for the fused
         instance kernel (B >= 74, H*A <= 32, analytic gradient, fixed-lengthscale kernel), else the
         staged sequence.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])"""
-        if (self.kernel == "gpytorch" and self.grad == "analytic" and self.roll_strategy != L.ROLL_RESAMPLE
-                and self._make_opt is None and getattr(self, "_fused_ok", True)):
-            ell2 = self.lengthscale ** 2
-            want = ("costs", "log_lik", "theta_out") + (("phi",) if want_phi else ())
-            try:
-                out = self.ops.svmpc_step(self.spec, state0, eps, self.theta, self.sigma, self.mu, self.mix, self.inv_var,
-                                     self.log_norm, 1.0 / (2.0 * ell2), 1.0 / self.N, -1.0 / ell2, self.lr, params=params,
-                                     param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
-                                     temperature=self.temperature, aliased=self.aliased, do_forward=True,
-                                     roll_strategy=self.roll_strategy, weighted_prior=self.weighted_prior, want=want)
-            except NotImplementedError:
-                self._fused_ok = False
-            else:
-                self.last = dict(costs=out["costs"], log_lik=out["log_lik"], theta1=out["theta_out"], phi=out.get("phi"),
-                                 states=None, lik_weights=None)
-                self.theta = out["theta_next"]
-                self.mu, self.mix, self.aliased = self.theta, out["mix_next"], True
-                return out["a_seq"], out["p_weights"], out["i_star"]
-        self.optimize_step(state0, eps, params, tiling)
+        self.optimize_step(state0, eps, params, tiling, lean=not want_phi)
         return self.forward_step()
 
     def likelihood_at_particles(self, state0, eps, params=None, tiling=L.PARAMS_BLOCKED):
@@ -154,6 +166,7 @@ class SvmpcCore:
                                     param_tiling=tiling, likelihood=self.likelihood, alpha=self.alpha,
                                     temperature=self.temperature, want=("costs", "log_lik"))
         self.last = dict(self.last, costs=out["costs"], log_lik=out["log_lik"])
+        self._pending = None
         return out["log_lik"]
 
     def draw_resample_noise(self):
@@ -166,6 +179,12 @@ class SvmpcCore:
 
     def forward_step(self, log_lik=None):
         """Weights, best particle, shift, prior refresh.  -> (a_seq [B,H,A], p_weights [B,N], i_star [B])."""
+        if log_lik is None and self._pending is not None:
+            p, self._pending = self._pending, None        # the one-launch step already weighed, selected and shifted
+            self.theta = p["theta_next"]
+            self.mu, self.mix, self.aliased = self.theta, p["mix_next"], True
+            return p["a_seq"], p["p_weights"], p["i_star"]
+        self._pending = None
         log_lik = self.last["log_lik"] if log_lik is None else log_lik
         mu = self.theta if self.aliased else self.mu
         noise = None if self.roll_strategy != L.ROLL_RESAMPLE else self.draw_resample_noise()

@@ -5,6 +5,7 @@ import torch
 
 from .. import _lib as L
 from .. import ops
+from .belief import resolve
 
 
 class GaussianLikelihood:
@@ -48,12 +49,12 @@ class CostLikelihood:
 
     def __init__(self, n_samples, controller, model):
         self.n_samples = n_samples
-        self.last_states = None
+        self._last_states = None
         self.last_actions = None
         self.last_policies = None
         self.last_costs = None
         self.params = None
-        self.params_log_p = None
+        self._params_log_p = None
         self.controller = controller
         self.model = model
         self._last = {}
@@ -63,6 +64,28 @@ class CostLikelihood:
         self.noise_fn = None
         self._noise_seed = int(torch.initial_seed()) & (2 ** 63 - 1)
         self._noise_draws = 0
+
+    @property
+    def params_log_p(self):
+        """Log-density of the last parameter draws under the belief they came from (formed on first access)."""
+        self._params_log_p = resolve(self._params_log_p)
+        return self._params_log_p
+
+    @params_log_p.setter
+    def params_log_p(self, value):
+        self._params_log_p = value
+
+    @property
+    def last_states(self):
+        """Rollout states of the last evaluation [P,S,N,H+1,ds].  SVMPC stores a thunk: the states are rolled out
+        again from that step's inputs when (and only when) somebody reads them."""
+        if callable(self._last_states):
+            self._last_states = self._last_states()
+        return self._last_states
+
+    @last_states.setter
+    def last_states(self, value):
+        self._last_states = value
 
     def draw_noise(self, shape):
         """Standard-normal action noise [S,N,H,A] on the controller's device (the rsample draw of

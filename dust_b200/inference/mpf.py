@@ -5,6 +5,7 @@ import torch
 import torch.distributions as dist
 
 from .. import ops
+from .belief import ParticleBelief
 from .likelihoods import GaussianLikelihood
 from .svgd import SVGD
 
@@ -52,38 +53,45 @@ class MPF(SVGD):
 
     def update_prior(self, bw):
         """mpf.py:26-38: GMM with one component per particle, covariance bw^2 I.  Its centres
-        alias `self.x` (the kernel updates x in place, exactly like the reference's SGD)."""
+        alias `self.x` (the kernel updates x in place, exactly like the reference's SGD).  `bw` may be a python
+        number, a per-dimension tensor, or the 1-element DEVICE tensor of the Silverman kernel (no host copy)."""
         n, d = self.x.shape
         if bw is None:
             bw = bw_silverman(self.x.flatten(1, -1), self.bw_scale)
         bw_t = torch.as_tensor(bw, dtype=torch.float32).reshape(-1)
         self._prior_var = (bw_t ** 2).expand(d).clone() if bw_t.numel() == 1 else (bw_t ** 2).clone()
+        self._prior_inv_var = (1.0 / self._prior_var).to(self.device).contiguous()
         self._prior_obj = None
 
     @property
     def prior(self):
+        """The belief as the controller consumes it: a `ParticleBelief` (samples / log-density with a few device ops;
+        any other `torch.distributions` attribute is served by the real MixtureSameFamily, built on demand)."""
         if self._prior_obj is None:
-            n, d = self.x.shape
-            cov = torch.diag(self._prior_var).to(self.device)
-            comp = dist.Independent(dist.MultivariateNormal(loc=self.x, covariance_matrix=cov),
-                                    reinterpreted_batch_ndims=0)
-            self._prior_obj = dist.MixtureSameFamily(dist.Categorical(torch.ones(n, device=self.device)), comp)
+            self._prior_obj = ParticleBelief(self.x, self._prior_var)
         return self._prior_obj
 
     def optimize(self, action, new_obs, bw=None, n_steps=100, debug=False):
         lik = self.likelihood
         if new_obs is not None:
             lik.condition(action, new_obs)
-        if bw is None:
-            bw = silvermans_rule(self.x.detach().cpu().numpy()) * self.bw_scale
         assert lik.past_action is not None, \
             "Previous action is None. Need at least one observation to start sampling."
         if self._spec is None:
             self._spec = lik.model.device_spec(device=self.device)
         dev = self.device
+        inv_var = self._prior_inv_var
+        if bw is None:
+            # Silverman's rule on the flattened particles (mpf.py:72), on the device: the kernel reads the bandwidth
+            # from device memory, nothing travels to the host
+            bw, next_inv_var = ops.silverman_bandwidth(self.x, self.bw_scale, dp=self.x.shape[1])
+        else:
+            next_inv_var = None
         f = lambda t: torch.as_tensor(t, dtype=torch.float32).reshape(1, -1).to(dev).contiguous()  # noqa: E731
         gn = ops.mpf_optimize(self._spec, self.x.unsqueeze(0), f(lik.past_obs), f(lik.past_action), f(lik.loc),
-                              (1.0 / self._prior_var).to(dev).contiguous(), lik.sigma, float(bw),
-                              self.opt_args.get("lr", 1e-3), n_steps, lik.log_space)
-        self.update_prior(bw)
+                              inv_var, lik.sigma, bw, self.opt_args.get("lr", 1e-3), n_steps, lik.log_space)
+        if next_inv_var is not None:
+            self._prior_inv_var, self._prior_var, self._prior_obj = next_inv_var, 1.0 / next_inv_var, None
+        else:
+            self.update_prior(bw)
         return gn[0], bw

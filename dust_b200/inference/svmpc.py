@@ -3,6 +3,7 @@ dust/inference/svmpc.py:14-200), every stage on the GPU through `SvmpcCore` (B =
 import torch
 
 from .. import _lib as L
+from .. import ops
 from ..kernels.base_kernels import RBF
 from ..kernels.composite_kernels import iid_mp
 from .core import SvmpcCore
@@ -80,6 +81,7 @@ class SVMPC(SVGD):
     @theta.setter
     def theta(self, value):
         self._core.theta = torch.as_tensor(value, dtype=torch.float32).to(self.device).unsqueeze(0).contiguous()
+        self._core._pending = None       # forward results computed for the old particles no longer apply
 
     @property
     def prior(self):
@@ -108,10 +110,18 @@ class SVMPC(SVGD):
         is the controller's."""
         lik, c = self.likelihood, self._core
         state0, eps, params, tiling, params_log_p = self._evaluate(state, params_dist, eps)
-        out = c.optimize_step(state0, eps, params, tiling, want_states=lik.controller.return_states)
+        theta_before = c.theta
+        out = c.optimize_step(state0, eps, params, tiling)
         lik._last = {"log_lik": out["log_lik"][0]}
         lik.last_costs = out["costs"][0]
-        lik.last_states = None if out["states"] is None else out["states"][0]
+        if lik.controller.return_states:
+            # the rollouts are only read for rendering (particle_example.py:190): produced on first access, from the
+            # inputs of this step, instead of being written on every control step
+            spec, sigma = c.spec, c.sigma
+            lik.last_states = lambda: ops.rollout_cost(spec, state0, eps, theta=theta_before, sigma=sigma, params=params,
+                                                       param_tiling=tiling, want=("costs", "states"))["states"][0]
+        else:
+            lik.last_states = None
         lik.last_actions = None
         lik._last_eps, lik._last_theta = eps[0], None
         lik.params_log_p = params_log_p

@@ -71,6 +71,15 @@ class BaseModel:
                 out.append((name, tuple(t.reshape(-1).tolist())))
         return tuple(out)
 
+    def cached_spec(self, device):
+        """The cost-free DeviceModelSpec of this model on `device` (what `step` needs), rebuilt only when the model's
+        defaults changed."""
+        fp = (str(device), self.spec_fingerprint())
+        ent = self.__dict__.get("_step_spec")
+        if ent is None or ent[0] != fp:
+            ent = self.__dict__["_step_spec"] = (fp, self.device_spec(device=device))
+        return ent[1]
+
     # --- device side -------------------------------------------------------------------
     #: order of the parameter columns the kernels expect
     device_param_order = ()

@@ -100,7 +100,7 @@ class Particle(BaseModel):
         M = st.shape[0]
         ac = torch.as_tensor(actions, dtype=torch.float32).reshape(-1, 2).to(dev).expand(M, 2).contiguous()
         prm = self._dict_to_device_params(params_dict, M, dev)
-        return ops.model_step(self.device_spec(device=dev), st, ac, prm).reshape(shape)
+        return ops.model_step(self.cached_spec(dev), st, ac, prm).reshape(shape)
 
     def _cost(self, states, actions, terminal):
         L.require_cuda()
@@ -109,7 +109,7 @@ class Particle(BaseModel):
         ac = None
         if actions is not None and torch.is_tensor(actions):
             ac = actions.to(dev, torch.float32).reshape(-1, 2).expand(st.shape[0], 2).contiguous()
-        return ops.model_cost(self.device_spec(device=dev), st, ac, terminal)
+        return ops.model_cost(self.cached_spec(dev), st, ac, terminal)
 
     def default_inst_cost(self, states, actions=0, n_pol=0, debug=False):
         return self._cost(states, actions, False)

@@ -105,7 +105,7 @@ class PendulumModel(BaseModel):
         if params_dict is None and self.defaults_are_tensors():
             params_dict = {}
         prm = self._dict_to_device_params(params_dict, M, dev)
-        out = ops.model_step(self.device_spec(), st, ac, prm)
+        out = ops.model_step(self.cached_spec(dev), st, ac, prm)
         return out.reshape(torch.as_tensor(states).shape)
 
     @staticmethod

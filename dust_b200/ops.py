@@ -338,8 +338,23 @@ def disco_step(a_mat, a_mix, a_low, a_high, strategy=L.SELECT_ARGMAX, steps=1):
     return nxt, a_seq
 
 
+def silverman_bandwidth(x, scale=1.0, dp=0):
+    """KDEpy's Silverman rule on the flattened device tensor x (n <= 4096) -> (bw [1], inv_var [dp] = 1/bw^2), both
+    on the device (no host round trip: `mpf_optimize(bw=bw_tensor)` reads the bandwidth there)."""
+    L.require_cuda()
+    flat = x.reshape(-1)
+    if not flat.is_contiguous():
+        flat = flat.contiguous()
+    bw = torch.empty(1, dtype=torch.float32, device=x.device)
+    iv = torch.empty(max(int(dp), 1), dtype=torch.float32, device=x.device)
+    L.call("dust_silverman_bandwidth", L.ptr(flat), flat.numel(), float(scale), L.ptr(bw), L.ptr(iv) if dp else None, int(dp),
+           L.stream())
+    return bw, (iv if dp else None)
+
+
 def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space, cooperative=True):
-    """x [B,Np,dp] is updated IN PLACE.  -> grad_norms [B,n_steps]."""
+    """x [B,Np,dp] is updated IN PLACE.  bw: python float, or a 1-element device tensor (read by the kernel).
+    -> grad_norms [B,n_steps]."""
     L.require_cuda()
     B, Np, dp = x.shape
     assert dp == spec.dp, f"parameter dim {dp} != model's {spec.dp}"
@@ -349,7 +364,9 @@ def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_
     a.B, a.Np, a.n_steps, a.log_space = B, Np, int(n_steps), int(bool(log_space))
     a.x, a.obs0, a.action, a.obs1 = L.ptr(x), L.ptr(obs0), L.ptr(action), L.ptr(obs1)
     a.prior_inv_var = L.ptr(prior_inv_var)
-    a.obs_std, a.bw, a.lr = float(obs_std), float(bw), float(lr)
+    bw_dev = bw if torch.is_tensor(bw) else None
+    a.obs_std, a.bw, a.lr = float(obs_std), 0.0 if bw_dev is not None else float(bw), float(lr)
+    a.bw_dev = L.ptr(bw_dev)
     a.grad_norms = L.ptr(gn)
     # > 0: one large instance, cooperative multi-SM kernel (cooperative=False keeps the one-CTA kernel)
     nbytes = L.load().dust_mpf_workspace_bytes(C.byref(a)) if cooperative else 0

@@ -407,10 +407,18 @@ typedef struct dust_mpf_args {
                               * (B = 1, Np >= 128) is then spread over many SMs by a cooperative launch
                               * (two grid barriers per SVGD step, same per-particle arithmetic)            */
   size_t workspace_bytes;
+  const float* bw_dev;       /* optional device scalar: the kernel bandwidth is read from it (bw is then ignored), e.g.
+                              * the output of dust_silverman_bandwidth -- no host round trip between the two          */
 } dust_mpf_args;
 
 size_t dust_mpf_workspace_bytes(const dust_mpf_args* args);   /* 0: the one-CTA-per-instance kernel is used */
 int dust_mpf_optimize(const dust_mpf_args* args, void* stream);
+
+/* Silverman's rule as KDEpy 1.1.0 `bw_selection.silvermans_rule` applies it to the flattened particles
+ * (dust/inference/mpf.py:72, svmpc.py:105): sigma = min(std(ddof=1), IQR/1.349) [std if IQR = 0],
+ * bw = scale * sigma * (0.75 n)^(-1/5); percentiles by linear interpolation, arithmetic in double.
+ * x: n <= 4096 device floats.  bw_out[0] = bw; inv_var_out[0..dp) = 1/bw^2 (may be NULL). */
+int dust_silverman_bandwidth(const float* x, int32_t n, float scale, float* bw_out, float* inv_var_out, int32_t dp, void* stream);
 
 /* one model step for M (state, action, params) triples: BaseModel.step
  * dust/models/pendulum.py:61-100, dust/models/particle.py:117-166.  params may be NULL. */

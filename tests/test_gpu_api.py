@@ -332,6 +332,7 @@ def test_one_launch_control_step_matches_staged_path(kind, N, S, H, wp):
     mk = lambda: SvmpcCore(spec, theta.clone(), mu.clone(), mix.clone(), torch.full((A,), 4.0), torch.full((A,), 2.0),  # noqa: E731
                            alpha=1.0, lr=0.5, kernel="gpytorch", weighted_prior=wp)
     fused, staged = mk(), mk()
+    staged._fused_ok = False          # keep this one on the staged kernels (gmm -> rollout/cost -> phi -> forward)
     lib = L.load()
     for step in range(2):  # step 0: free-standing prior; step 1: aliased prior
         eps = torch.randn(B, S, N, H, A, device=dev)

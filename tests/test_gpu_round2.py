@@ -219,3 +219,154 @@ def test_stress_shape_variants_are_reached_and_match_the_oracle(particle_env, B,
         for key, v in (("costs", e_c), ("grad_lik_vs_own_costs", e_g), ("pathwise_grad", e_p)):
             worst[key] = max(worst.get(key, 0.0), v)
     record_parity(f"stress-shape particle H=50 P=296 NSUB={nsub}", **worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# few instances: the whole control step in one launch of a thread-block cluster per instance
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,B,N,S,H,P,wp", [("pendulum", 1, 3, 128, 30, 8, False),      # configs[0]
+                                               ("particle", 1, 6, 64, 40, 4, True),        # configs[1]
+                                               ("pendulum", 3, 8, 33, 20, 0, True),        # ragged row blocks, no draws
+                                               ("particle", 2, 5, 7, 9, 3, False),         # fewer rows than CTAs x warps
+                                               ("pendulum", 1, 32, 100, 12, 20, False)])   # draws looped inside a thread
+def test_cluster_kernel_control_step_matches_staged_path(particle_env, kind, B, N, S, H, P, wp):
+    """`dust_svmpc_step` for B < 74 (svmpc_cluster_kernel: 8 CTAs per instance, costs and partial gradients exchanged
+    through distributed shared memory) against the staged kernels: costs bit for bit, everything else to rounding;
+    first with a free-standing prior, then with the prior aliasing the particles; and against the float64 oracle."""
+    from dust_b200 import _lib as L
+    from dust_b200.inference.core import SvmpcCore
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    torch.manual_seed(N * 11 + S)
+    if kind == "pendulum":
+        spec = PendulumModel(uncertain_params=("length", "mass")).device_spec(inst_cost, term_cost, DEV)
+        ds, A, dp, model = 2, 1, 2, O.Model("pendulum")
+    else:
+        spec, ds, A, dp, model = particle_env["spec"], 4, 2, 1, O.Model("particle", particle_env["cfg"])
+    state = torch.randn(B, ds, device=DEV) * (torch.tensor([6.0, 6.0, 1.0, 1.0], device=DEV) if kind == "particle" else 1.5)
+    theta, mu = torch.randn(B, N, H, A, device=DEV) * 2, torch.randn(B, N, H, A, device=DEV)
+    mix = torch.rand(B, N, device=DEV) + 0.1
+    params = (torch.rand(B, P, dp, device=DEV) + 0.8) if P else None
+    alpha = 1.0 if kind == "pendulum" else 1e-3
+    mk = lambda: SvmpcCore(spec, theta.clone(), mu.clone(), mix.clone(), torch.full((A,), 4.0), torch.full((A,), 2.0),  # noqa: E731
+                           alpha=alpha, lr=0.5, kernel="gpytorch", weighted_prior=wp)
+    fused, staged = mk(), mk()
+    staged._fused_ok = False
+    lib = L.load()
+    worst = {}
+    for step in range(2):
+        eps = torch.randn(B, S, N, H, A, device=DEV)
+        theta_in, mu_in, mix_in, aliased = fused.theta.clone(), fused.mu.clone(), fused.mix.clone(), fused.aliased
+        lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
+        fused.optimize_step(state, eps, params)
+        prof = L.profiler_report(); lib.dust_profiler_enable(0)
+        assert list(prof) == ["svmpc_cluster_kernel"] and prof["svmpc_cluster_kernel"][0] == 1, prof
+        theta1 = fused.theta.clone()
+        a1, p1, i1 = fused.forward_step()
+        staged.optimize_step(state, eps, params)
+        theta1s = staged.theta.clone()
+        a2, p2, i2 = staged.forward_step()
+        assert torch.equal(fused.last["costs"], staged.last["costs"])
+        e = dict(log_lik=rel_max(fused.last["log_lik"].cpu(), staged.last["log_lik"].cpu()),
+                 grad_lik=rel_max(fused.last["grad_lik"].cpu(), staged.last["grad_lik"].cpu()),
+                 phi=rel_max(fused.last["phi"].cpu(), staged.last["phi"].cpu()), theta1=rel_max(theta1.cpu(), theta1s.cpu()),
+                 p_weights=float((p1 - p2).abs().max()), a_seq=rel_max(a1.cpu(), a2.cpu()),
+                 theta_next=rel_max(fused.theta.cpu(), staged.theta.cpu()), mix=rel_max(fused.mix.cpu(), staged.mix.cpu()))
+        assert torch.equal(i1, i2)
+        assert e["log_lik"] <= 1e-6 and e["grad_lik"] <= 1e-5 and e["phi"] <= 1e-4 and e["theta1"] <= 1e-5, e
+        assert e["p_weights"] <= 1e-4 and e["a_seq"] <= 1e-5 and e["theta_next"] <= 1e-5 and e["mix"] <= 1e-4, e
+        # float64 restatement of the first instance
+        st = O.SvmpcState(theta_in[0].cpu().double(), mu_in[0].cpu().double(), mix_in[0].cpu().double(), 4.0, aliased=aliased)
+        ref = O.svmpc_optimize(model, st, state[0].cpu().double(), eps[0].cpu().double(), torch.full((A,), 2.0).double(),
+                               None if params is None else params[0].cpu().double(), False, alpha, 0.5, kernel="rbf")
+        e["costs_vs_oracle"] = rel_elem(fused.last["costs"][0].cpu(), ref["costs"])
+        e["theta1_vs_oracle"] = rel_max(theta1[0].cpu(), ref["theta1"])
+        assert e["costs_vs_oracle"] <= RTOL_COST and e["theta1_vs_oracle"] <= RTOL_PHI, e
+        for k_, v in e.items():
+            worst[k_] = max(worst.get(k_, 0.0), v)
+        staged.theta = fused.theta.clone()
+        staged.mu, staged.mix = staged.theta, fused.mix.clone()
+    record_parity(f"cluster kernel {kind} B={B} N={N} S={S} H={H} P={P}", **worst)
+
+
+# ---------------------------------------------------------------------------------------------
+# the parameter filter without host round trips: device Silverman rule, the belief object
+# ---------------------------------------------------------------------------------------------
+def test_device_silverman_rule_matches_kdepy_restatement():
+    """`dust_silverman_bandwidth` against the host restatement of KDEpy's rule (checked against the reference's own
+    values in the CPU suite): recorded particle clouds, sizes that are not powers of two, degenerate data."""
+    from dust_b200 import ops
+    from dust_b200.inference.mpf import silvermans_rule
+
+    d = load("dual_pendulum_silverman")
+    clouds = [d[f"t{t}_in_mpf_x0"] for t in range(int(d["n_steps"]))]
+    g = torch.Generator().manual_seed(5)
+    clouds += [torch.randn(n, generator=g) * s for n, s in ((2, 1.0), (3, 0.1), (100, 2.0), (513, 1e-3), (4096, 30.0))]
+    clouds += [torch.cat([torch.zeros(90), torch.randn(10, generator=g)]),     # IQR = 0: falls back to the std
+               torch.full((64,), 0.7), torch.tensor([1.5])]                       # all equal -> 1.0; a single value -> 1.0
+    worst = 0.0
+    for x in clouds:
+        ref = silvermans_rule(x.numpy()) * 0.8
+        bw, iv = ops.silverman_bandwidth(cu(x), 0.8, dp=2)
+        got = float(bw[0])
+        worst = max(worst, abs(got - ref) / ref)
+        assert abs(got - ref) <= 2e-7 * ref, (x.shape, got, ref)
+        assert torch.allclose(iv.cpu(), torch.full((2,), 1.0 / got ** 2), rtol=1e-6)
+    record_parity("device Silverman rule vs host restatement", max_rel_err=worst)
+
+
+def test_mpf_class_with_device_bandwidth_matches_reference():
+    """MPF.optimize(bw=None): the pendulum configuration's setting (mpf_bandwidth: None) -- Silverman on the device,
+    the kernel reading the bandwidth from device memory, 16 lanes per particle (Np = 50) -- against the reference's
+    recording, teacher forced on the particles (the pendulum filter amplifies rounding)."""
+    from dust_b200.inference.likelihoods import GaussianLikelihood
+    from dust_b200.inference.mpf import MPF
+    from dust_b200.models.pendulum import PendulumModel
+    from tests.util import assert_close_to_reference
+
+    d = load("dual_pendulum_silverman")
+    model = PendulumModel(uncertain_params=("length", "mass"))
+    lik = GaussianLikelihood(initial_obs=d["t0_in_state"], obs_std=float(d["obs_std"]), model=model, log_space=False)
+    mpf = MPF(init_particles=d["t0_in_mpf_x0"].clone(), likelihood=lik, optimizer_class=torch.optim.SGD,
+              lr=float(d["mpf_lr"]), bw=float(d["mpf_prior_bw0"]), bw_scale=1.0)
+    worst = 0.0
+    prior_bw = float(d["mpf_prior_bw0"])
+    for t in range(int(d["n_steps"])):
+        x0 = d[f"t{t}_in_mpf_x0"]
+        mpf.x.copy_(cu(x0))
+        mpf.update_prior(prior_bw)
+        lik.condition(None, d[f"t{t}_in_state"])                  # past observation of this step
+        gn, bw = mpf.optimize(d[f"t{t}_out_a_seq"][0], d[f"t{t}_out_next_state"], bw=None, n_steps=20)
+        assert torch.is_tensor(bw) and bw.is_cuda, "the bandwidth must stay on the device"
+        bw_ref = float(d[f"t{t}_out_mpf_bw"])
+        worst = max(worst, abs(float(bw) - bw_ref) / bw_ref)
+        assert abs(float(bw) - bw_ref) <= 1e-6 * bw_ref
+        x64, _ = O.mpf_optimize(O.Model("pendulum"), x0.double(), d[f"t{t}_in_state"].double(), d[f"t{t}_out_a_seq"][0].double(),
+                                d[f"t{t}_out_next_state"].double(), float(d["obs_std"]), prior_bw ** 2, bw_ref, float(d["mpf_lr"]), 20, False)
+        assert_close_to_reference(mpf.x.cpu(), d[f"t{t}_out_mpf_x1"], x64, RTOL_PHI, f"MPF class device bandwidth t{t} x1")
+        assert gn.shape == (20,)
+        # the prior of the next step carries this step's bandwidth (mpf.py:84)
+        assert torch.allclose(mpf._prior_inv_var.cpu(), torch.full((2,), 1.0 / bw_ref ** 2), rtol=1e-5)
+        prior_bw = bw_ref
+    record_parity("MPF class, Silverman bandwidth on the device", bw_rel_err=worst)
+
+
+def test_particle_belief_samples_and_log_prob():
+    """`MPF.prior` (ParticleBelief): log-density equal to the torch MixtureSameFamily it stands for, samples with the
+    mixture's moments, centres aliasing the particles."""
+    from dust_b200.inference.belief import ParticleBelief
+
+    torch.manual_seed(3)
+    x = torch.randn(50, 2, device=DEV) * 0.2 + torch.tensor([0.9, 1.1], device=DEV)
+    b = ParticleBelief(x, torch.tensor([0.01, 0.04]))
+    ref = b.as_torch()
+    v = torch.randn(37, 2, device=DEV) * 0.3 + 1.0
+    assert rel_max(b.log_prob(v).cpu(), ref.log_prob(v).cpu()) <= 1e-5
+    s = b.sample([20000])
+    assert s.shape == (20000, 2) and s.is_cuda
+    assert float((s.mean(0) - ref.mean).abs().max()) <= 0.01
+    assert float((s.var(0) - ref.variance).abs().max()) <= 0.01
+    assert rel_max(b.mean.cpu(), ref.mean.cpu()) <= 1e-6 and rel_max(b.variance.cpu(), ref.variance.cpu()) <= 1e-5
+    x += 1.0                                   # in-place move of the particles: the belief follows (quirk H24)
+    assert float((b.sample([4000]).mean(0) - x.mean(0)).abs().max()) <= 0.03
+    assert b.sample([8]).shape == (8, 2) and b.event_shape == torch.Size([2])
