@@ -166,7 +166,14 @@ def time_class_path(name, dev, steps, warmup):
         class_dual_step(o)
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - w0) * 1e3 / steps
-    return {"wall_ms_per_dual_step": wall_ms, "dual_steps_per_sec": 1e3 / wall_ms,
+    ref = None
+    try:   # the UNMODIFIED reference timed on the build container's cores (profiles/reference_cpu_demo.py; it cannot travel)
+        r = json.load(open(os.path.join(ROOT, "profiles", "r2_reference_cpu_demo.json")))
+        ref = {"ms_per_dual_step": r["configs"][name]["ms_per_dual_step"], "threads": r["configs"][name]["threads"],
+               "host_cpus": r["cpus"], "where": r["where"], "ratio": r["configs"][name]["ms_per_dual_step"] / wall_ms}
+    except Exception:
+        pass
+    return {"wall_ms_per_dual_step": wall_ms, "dual_steps_per_sec": 1e3 / wall_ms, "reference_unmodified_cpu": ref,
             "library_launches_per_step": (lib.dust_launch_count() - n0) / steps,
             "api": "SVMPC.optimize + SVMPC.forward + model.step + MPF.optimize (drop-in classes, belief = mpf.prior)"}
 

@@ -83,7 +83,7 @@ class PhiArgs(C.Structure):
         ("B", _i), ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("per_dim", _i),
         ("x", _p), ("score", _p), ("gamma", _f), ("c1", _f), ("c2", _f), ("gamma_dev", _p),
         ("bw_scale", _f), ("lr", _f), ("phi", _p), ("x_out", _p), ("bandwidths", _p),
-        ("workspace", _p), ("workspace_bytes", _sz),
+        ("workspace", _p), ("workspace_bytes", _sz), ("x_prepared", _i),
     ]
 
 

@@ -160,10 +160,11 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
     }
     if (lane == 0) red[warp] = nrm;
     __syncthreads();
-    if (threadIdx.x == 0 && k.grad_norms) {
-      float t = 0.f;
-      for (int w = 0; w < nwarps; ++w) t += red[w];
-      k.grad_norms[inst * k.n_steps + step] = sqrtf(t);
+    if (threadIdx.x < 32 && k.grad_norms) {     // one warp adds the per-group partial norms (a serial loop in one
+      float t = 0.f;                            // thread held every other warp at the barrier below)
+      for (int w = threadIdx.x; w < nwarps; w += 32) t += red[w];
+      t = warp_sum(t);
+      if (threadIdx.x == 0) k.grad_norms[inst * k.n_steps + step] = sqrtf(t);
     }
     for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) xs[e] = xs[e] + k.lr * ph[e];  // SGD (mpf.py:59-62)
     __syncthreads();

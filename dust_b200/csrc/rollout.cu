@@ -1198,7 +1198,8 @@ __global__ void __launch_bounds__(kClusterMaxThreads) svmpc_cluster_kernel(const
     const int words = (k.m.grid_nx * k.m.grid_ny + 31) >> 5;
     for (int w = tid; w < words; w += nthr) grid_s[w] = __ldg(k.m.grid_bits + w);
   }
-  __syncthreads();
+  // every CTA of the cluster is running (its shared memory exists) before anyone writes into a peer; also the CTA barrier
+  cluster.sync();
 
   // ---- rollouts: thread <-> (row, draw group); one trajectory per (row, draw) ----
   const float sg0 = k.sigma[0], sg1 = k.sigma[A - 1];

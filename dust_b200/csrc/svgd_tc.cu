@@ -151,10 +151,12 @@ __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ 
 }
 
 static int tc_prep(const float* x, const float* score, int N, int D, int Dp, int NV, float* x_hi, float* x_lo, float* vb_hi,
-                   float* vb_lo, float* xn, cudaStream_t stream) {
-  const int nbx = ceil_div((long long)N * (Dp / 4), 256);
+                   float* vb_lo, float* xn, cudaStream_t stream, bool x_prepared = false) {
+  // x_prepared: the X images and the norms are already in place (median pass on the same workspace): V^T images only
+  const int nbx = x_prepared ? 0 : ceil_div((long long)N * (Dp / 4), 256);
   const int nbv = score ? ceil_div((long long)(N / 4) * NV, 256) : 0;
-  const int nbn = ceil_div(N, 256);
+  const int nbn = x_prepared ? 0 : ceil_div(N, 256);
+  if (nbx + nbv + nbn == 0) return DUST_OK;
   {
     DUST_TIMED("tc_prep_kernel", stream);
     tc_prep_kernel<<<nbx + nbv + nbn, 256, 0, stream>>>(x, score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, nbx, nbv);
@@ -1101,7 +1103,7 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   float* vb_hi = ws;           ws += (size_t)N * NV;
   float* vb_lo = ws;           ws += (size_t)N * NV;
   float* oacc = ws;
-  int rc = tc_prep(a->x, a->score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream);
+  int rc = tc_prep(a->x, a->score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream, a->x_prepared != 0);
   if (rc != DUST_OK) return rc;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
   const int row_tiles = (r1 - r0) / kTcBM;

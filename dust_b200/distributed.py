@@ -93,6 +93,16 @@ class ShardedSVGD:
         wait_s()
         return x_all, s_all
 
+    def _shared_bytes(self, device):
+        import ctypes as C
+
+        from . import _lib as L
+        a = L.PhiArgs()
+        a.B, a.N, a.D = 1, self.N, self.D
+        a.row_begin, a.row_end = self.rows
+        lib = L.load()
+        return int(max(lib.dust_phi_workspace_bytes(C.byref(a)), lib.dust_median_fast_workspace_bytes(self.N, self.D), 1))
+
     def median(self, x_all, defer_fallback=False):
         """Exact lower median of all N^2 squared distances: each rank histograms its row block.
         defer_fallback (library ops only): run the tensor-core window pass alone and return (median, check);
@@ -101,7 +111,9 @@ class ShardedSVGD:
         if getattr(self.ops, "MedianWorkspace", None) is None:     # stand-in ops (host-logic tests)
             return self.ops.median_sq_dist(x_all, rows=self.rows, all_reduce=self._all_reduce_hist), None
         if self._median_ws is None:
-            self._median_ws = self.ops.MedianWorkspace(self.N, self.D, x_all.device)
+            # ONE buffer for the median pass and for phi: both keep |x|^2 and the operand images of X at its head
+            self._shared_ws = torch.empty(self._shared_bytes(x_all.device), dtype=torch.uint8, device=x_all.device)
+            self._median_ws = self.ops.MedianWorkspace(self.N, self.D, x_all.device, fast_ws=self._shared_ws)
         if defer_fallback:
             # every rank draws 1/world of the 2^20 sampled pairs that place the window; the sample histogram (128 KB) is summed
             return self.ops.median_sq_dist_deferred(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist,
@@ -122,7 +134,10 @@ class ShardedSVGD:
         med, check = self.median(x_all, defer_fallback=True)
         coef = self.ops.bandwidth_from_median(med, self.N, bw_scale, 0)
         wait_s()
-        out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=self.rows)
+        shared = getattr(self, "_shared_ws", None)
+        kw = {} if shared is None else dict(workspace=shared, x_prepared=self._median_ws.fast and self.rows[0] % 128 == 0
+                                            and self.rows[1] % 128 == 0)
+        out = self.ops.svgd_phi(x_all.unsqueeze(0), s_all.unsqueeze(0), gamma_dev=coef, rows=self.rows, **kw)
         if check is not None and not check():
             # the rank fell outside the sampled window (ties, clusters): the two-pass radix select, then phi again
             med = self.ops.median_sq_dist(x_all, ws=self._median_ws, rows=self.rows, all_reduce=self._all_reduce_hist,

@@ -166,8 +166,10 @@ def gmm_log_norm(var_full):
 
 
 def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, gamma_dev=None, per_dim=False, bw_scale=1.0, lr=0.0,
-             want_phi=True, want_update=False, rows=None, want_bandwidths=False):
-    """K5.  x, score [B,N,D].  Returns dict(phi=, x_out=, bandwidths=)."""
+             want_phi=True, want_update=False, rows=None, want_bandwidths=False, workspace=None, x_prepared=False):
+    """K5.  x, score [B,N,D].  Returns dict(phi=, x_out=, bandwidths=).
+    workspace: a caller-owned uint8 buffer (at least dust_phi_workspace_bytes) instead of a fresh one; with
+    x_prepared its head already holds the operand images of x (the median pass ran on the same buffer)."""
     L.require_cuda()
     B, N, D = x.shape
     dev = x.device
@@ -183,8 +185,12 @@ def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, gamma_dev=None, per_dim=False,
     a.bw_scale, a.lr = float(bw_scale), float(lr)
     a.phi, a.x_out, a.bandwidths = L.ptr(phi), L.ptr(xo), L.ptr(bws)
     nbytes = L.load().dust_phi_workspace_bytes(C.byref(a))
-    ws = _ws(nbytes, dev)
-    a.workspace, a.workspace_bytes = ws.data_ptr(), nbytes
+    if workspace is not None and workspace.numel() >= nbytes:
+        ws = workspace
+        a.x_prepared = int(bool(x_prepared))
+    else:
+        ws = _ws(nbytes, dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), max(nbytes, ws.numel())
     L.call("dust_svgd_phi", C.byref(a), L.stream(), launches=2 if per_dim or N > 512 else 1)
     return dict(phi=phi, x_out=xo, bandwidths=bws)
 
@@ -193,7 +199,9 @@ class MedianWorkspace:
     """Device scratch for the median select: 3*65536+8 u64 bins, 8 u32 of state, N row norms, and
     (when the tensor-core pass applies) the tiled operand images."""
 
-    def __init__(self, N, D, device):
+    def __init__(self, N, D, device, fast_ws=None):
+        """fast_ws: a caller-owned uint8 buffer for the tensor-core pass (shared with `svgd_phi(workspace=...)`: both
+        keep |x|^2 and the hi/lo operand images of x at its head, so phi need not prepare them again)."""
         self.hist = torch.zeros(3 * 65536 + 8, dtype=torch.int64, device=device)
         self.selected = torch.zeros(8, dtype=torch.int32, device=device)
         self.row_norms = torch.empty(N, dtype=torch.float32, device=device)
@@ -201,7 +209,10 @@ class MedianWorkspace:
         lib = L.load()
         self.fast = bool(lib.dust_median_fast_supported(N, D))
         self.fast_bytes = lib.dust_median_fast_workspace_bytes(N, D) if self.fast else 0
-        self.fast_ws = _ws(self.fast_bytes, device) if self.fast else None
+        if self.fast and fast_ws is not None and fast_ws.numel() >= self.fast_bytes:
+            self.fast_ws = fast_ws
+        else:
+            self.fast_ws = _ws(self.fast_bytes, device) if self.fast else None
         self.sample_hist = None
         if self.fast:      # the 32768-bin histogram of the sampled pairs inside the workspace (summed over ranks when sharded)
             off = int(lib.dust_median_fast_sample_hist_offset(N, D))

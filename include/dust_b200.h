@@ -320,6 +320,9 @@ typedef struct dust_phi_args {
   float* bandwidths;         /* per_dim only, optional [B, D]                          */
   void* workspace;
   size_t workspace_bytes;
+  int32_t x_prepared;        /* tensor-core path: the head of `workspace` already holds |x|^2 and the hi/lo operand images
+                                of this x -- written there by dust_median_fast_prepare on the SAME buffer (its workspace
+                                has the same head layout) -- so only the [score | x] images are prepared               */
 } dust_phi_args;
 
 size_t dust_phi_workspace_bytes(const dust_phi_args* args);
