@@ -109,7 +109,7 @@ class MpfArgs(C.Structure):
         ("model", C.POINTER(ModelDesc)), ("B", _i), ("Np", _i), ("n_steps", _i), ("log_space", _i),
         ("x", _p), ("obs0", _p), ("action", _p), ("obs1", _p), ("prior_inv_var", _p),
         ("obs_std", _f), ("bw", _f), ("lr", _f), ("grad_norms", _p),
-        ("workspace", _p), ("workspace_bytes", C.c_size_t), ("bw_dev", _p),
+        ("workspace", _p), ("workspace_bytes", C.c_size_t), ("bw_dev", _p), ("phi_out", _p),
     ]
 
 
@@ -143,6 +143,7 @@ SYMBOLS = {
     "dust_silverman_bandwidth": (C.c_int, [_p, _i, _f, _p, _p, _i, _p]),
     "dust_model_step": (C.c_int, [C.POINTER(ModelDesc), _i, _p, _p, _p, _p, _p]),
     "dust_model_cost": (C.c_int, [C.POINTER(ModelDesc), _i, _i, _p, _p, _p, _p]),
+    "dust_aux_model_step": (C.c_int, [_i, _f, C.POINTER(_f * 8), _i, _p, _p, _p, _p, _p]),
     "dust_noise_normal": (C.c_int, [_p, C.c_int64, C.c_uint64, C.c_uint64, _p]),
     "dust_profiler_enable": (None, [C.c_int]),
     "dust_profiler_reset": (None, []),

@@ -23,6 +23,7 @@ struct MpfKParams {
   float inv_obs_var, bw, lr;
   float* grad_norms;
   const float* bw_dev;   // device scalar overriding bw, or nullptr
+  float* phi_out;        // [B,Np,dp] phi of the last step, or nullptr
   int lanes;             // lanes per particle in mpf_kernel: 32, or 16 / 8 when all particles then fit one pass
 };
 
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(kMpfMaxThreads) mpf_kernel(const MpfKParams k)
       t = warp_sum(t);
       if (threadIdx.x == 0) k.grad_norms[inst * k.n_steps + step] = sqrtf(t);
     }
+    if (k.phi_out && step == k.n_steps - 1)
+      for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) k.phi_out[inst * (long long)k.Np * DP + e] = ph[e];
     for (int e = threadIdx.x; e < k.Np * DP; e += blockDim.x) xs[e] = xs[e] + k.lr * ph[e];  // SGD (mpf.py:59-62)
     __syncthreads();
   }
@@ -413,10 +416,10 @@ extern "C" int dust_mpf_optimize(const dust_mpf_args* a, void* stream_) {
   k.B = a->B; k.Np = a->Np; k.dp = dp; k.n_steps = a->n_steps; k.log_space = a->log_space;
   k.x = a->x; k.obs0 = a->obs0; k.action = a->action; k.obs1 = a->obs1; k.prior_inv_var = a->prior_inv_var;
   k.inv_obs_var = 1.0f / (a->obs_std * a->obs_std); k.bw = a->bw; k.lr = a->lr; k.grad_norms = a->grad_norms;
-  k.bw_dev = a->bw_dev; k.lanes = 32;
+  k.bw_dev = a->bw_dev; k.lanes = 32; k.phi_out = a->phi_out;
   cudaStream_t stream = (cudaStream_t)stream_;
   const int coop = mpf_coop_grid(a);
-  if (coop && a->workspace && a->workspace_bytes >= dust_mpf_workspace_bytes(a) && a->n_steps > 0) {
+  if (coop && !a->phi_out && a->workspace && a->workspace_bytes >= dust_mpf_workspace_bytes(a) && a->n_steps > 0) {
     float* ws = (float*)a->workspace;
     void* kargs[] = {(void*)&k, (void*)&ws};
     const void* fn = kind == DUST_MODEL_PENDULUM ? (const void*)mpf_coop_kernel<DUST_MODEL_PENDULUM>

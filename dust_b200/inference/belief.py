@@ -17,6 +17,8 @@ class ParticleBelief:
         """centres [n, d] device tensor (kept by reference); var [d] tensor (host or device) of component variances."""
         self._x = centres
         self._var = torch.as_tensor(var, dtype=torch.float32).reshape(-1)
+        if self._var.numel() == 1:
+            self._var = self._var.expand(centres.shape[1])
         self._std_dev = None
         self._torch = None
 

@@ -45,9 +45,10 @@ class MPF(SVGD):
         self.likelihood = likelihood
         plain_sgd = self.optimizer_class is torch.optim.SGD and not any(
             self.opt_args.get(k) for k in ("momentum", "weight_decay", "nesterov", "dampening"))
-        if not plain_sgd:
-            raise NotImplementedError("MPF: only plain SGD (no momentum / weight decay / nesterov / dampening) is fused "
-                                      "into the update kernel; other optimisers are not implemented")
+        # plain SGD (the demos) is fused: all n_steps of an optimize() call run inside one launch.  Any other torch
+        # optimiser (mpf.py:23: built once, its state lives across calls; Adam is the SVGD default) takes phi from the
+        # kernel one step at a time and updates the particles in place on the device (mpf.py:59-62)
+        self.optimizer = None if plain_sgd else self.optimizer_class(params=[self.x], **self.opt_args)
         self._spec = None
         self.update_prior(bw)
 
@@ -58,9 +59,13 @@ class MPF(SVGD):
         n, d = self.x.shape
         if bw is None:
             bw = bw_silverman(self.x.flatten(1, -1), self.bw_scale)
-        bw_t = torch.as_tensor(bw, dtype=torch.float32).reshape(-1)
-        self._prior_var = (bw_t ** 2).expand(d).clone() if bw_t.numel() == 1 else (bw_t ** 2).clone()
-        self._prior_inv_var = (1.0 / self._prior_var).to(self.device).contiguous()
+        if not torch.is_tensor(bw) and getattr(self, "_prior_bw_key", None) == (float(bw), d):
+            self._prior_obj = None       # same scalar bandwidth as last time (the particle configuration): tensors stand
+            return
+        bw_t = torch.as_tensor(bw, dtype=torch.float32).reshape(-1).to(self.device)
+        self._prior_var = (bw_t ** 2).expand(d).clone() if bw_t.numel() == 1 else (bw_t ** 2).clone()   # on the device
+        self._prior_inv_var = (1.0 / self._prior_var).contiguous()
+        self._prior_bw_key = (float(bw), d) if not torch.is_tensor(bw) else None
         self._prior_obj = None
 
     @property
@@ -88,10 +93,24 @@ class MPF(SVGD):
         else:
             next_inv_var = None
         f = lambda t: torch.as_tensor(t, dtype=torch.float32).reshape(1, -1).to(dev).contiguous()  # noqa: E731
-        gn = ops.mpf_optimize(self._spec, self.x.unsqueeze(0), f(lik.past_obs), f(lik.past_action), f(lik.loc),
-                              inv_var, lik.sigma, bw, self.opt_args.get("lr", 1e-3), n_steps, lik.log_space)
+        if self.optimizer is None:
+            gn = ops.mpf_optimize(self._spec, self.x.unsqueeze(0), f(lik.past_obs), f(lik.past_action), f(lik.loc),
+                                  inv_var, lik.sigma, bw, self.opt_args.get("lr", 1e-3), n_steps, lik.log_space)
+        else:
+            obs0, act, obs1 = f(lik.past_obs), f(lik.past_action), f(lik.loc)
+            phi = torch.empty_like(self.x).unsqueeze(0)
+            norms = []
+            for _ in range(n_steps):
+                norms.append(ops.mpf_optimize(self._spec, self.x.unsqueeze(0), obs0, act, obs1, inv_var, lik.sigma, bw, 0.0, 1,
+                                              lik.log_space, phi_out=phi)[0])
+                self.optimizer.zero_grad()
+                self.x.grad = -phi[0]
+                self.optimizer.step()
+                self.x.grad = None
+            gn = torch.cat(norms).unsqueeze(0) if norms else torch.empty(1, 0, device=dev)
         if next_inv_var is not None:
             self._prior_inv_var, self._prior_var, self._prior_obj = next_inv_var, 1.0 / next_inv_var, None
+            self._prior_bw_key = None
         else:
             self.update_prior(bw)
         return gn[0], bw

@@ -363,8 +363,10 @@ def silverman_bandwidth(x, scale=1.0, dp=0):
     return bw, (iv if dp else None)
 
 
-def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space, cooperative=True):
+def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_steps, log_space, cooperative=True,
+                 phi_out=None):
     """x [B,Np,dp] is updated IN PLACE.  bw: python float, or a 1-element device tensor (read by the kernel).
+    phi_out [B,Np,dp]: receives phi of the last step (lr = 0, n_steps = 1: evaluate phi only).
     -> grad_norms [B,n_steps]."""
     L.require_cuda()
     B, Np, dp = x.shape
@@ -379,6 +381,9 @@ def mpf_optimize(spec, x, obs0, action, obs1, prior_inv_var, obs_std, bw, lr, n_
     a.obs_std, a.bw, a.lr = float(obs_std), 0.0 if bw_dev is not None else float(bw), float(lr)
     a.bw_dev = L.ptr(bw_dev)
     a.grad_norms = L.ptr(gn)
+    a.phi_out = L.ptr(phi_out)
+    if phi_out is not None:
+        cooperative = False
     # > 0: one large instance, cooperative multi-SM kernel (cooperative=False keeps the one-CTA kernel)
     nbytes = L.load().dust_mpf_workspace_bytes(C.byref(a)) if cooperative else 0
     ws = _ws(nbytes, x.device) if nbytes else None
@@ -393,6 +398,18 @@ def model_step(spec, states, actions, params=None):
     M = states.shape[0]
     nxt = torch.empty_like(states)
     L.call("dust_model_step", C.byref(spec.desc), M, L.ptr(states), L.ptr(actions), L.ptr(params), L.ptr(nxt),
+           L.stream())
+    return nxt
+
+
+def aux_model_step(kind, dt, cfg, states, actions, params=None):
+    """One transition of the skid-steer robot (kind 0) / cart-pole (kind 1).  cfg: up to 8 python floats (defaults and
+    action bounds); states [M,ds], actions [M,A], params [M,np] | None -> next states [M,ds]."""
+    L.require_cuda()
+    M = states.shape[0]
+    nxt = torch.empty_like(states)
+    c = (C.c_float * 8)(*([float(v) for v in cfg] + [0.0] * (8 - len(cfg))))
+    L.call("dust_aux_model_step", int(kind), float(dt), C.byref(c), M, L.ptr(states), L.ptr(actions), L.ptr(params), L.ptr(nxt),
            L.stream())
     return nxt
 

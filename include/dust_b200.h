@@ -412,6 +412,9 @@ typedef struct dust_mpf_args {
   size_t workspace_bytes;
   const float* bw_dev;       /* optional device scalar: the kernel bandwidth is read from it (bw is then ignored), e.g.
                               * the output of dust_silverman_bandwidth -- no host round trip between the two          */
+  float* phi_out;            /* optional [B, Np, dp]: phi of the LAST step.  With lr = 0 and n_steps = 1 the call only
+                              * evaluates phi at x -- the host then applies any optimiser (mpf.py:59-62: Adam is the
+                              * reference's default; plain SGD stays fused in the kernel)                                */
 } dust_mpf_args;
 
 size_t dust_mpf_workspace_bytes(const dust_mpf_args* args);   /* 0: the one-CTA-per-instance kernel is used */
@@ -430,6 +433,15 @@ int dust_model_step(const dust_model_desc* model, int32_t M, const float* states
 
 /* trajectory-free cost evaluation used by the drivers (inst_cost_fn on the plant state):
  * demo/pendulum_example.py:21-28, dust/models/particle.py:170-225.  actions may be NULL (0). */
+/* One transition of the reference's other two forward models (no cost function / demo ships for them, so only
+ * `model.step` exists): skid-steer robot dust/models/skid_steer_robot.py:73-122 (states [M,5], actions [M,2], params
+ * [M,3] = x_icr, wheel_radius, axial_distance or NULL; cfg = {x_icr, wheel_radius, axial_distance, min_right, max_right,
+ * min_left, max_left, -}) and cart-pole dust/models/cartpole.py:127-172 (states [M,4], actions [M,1], params [M,7] =
+ * g, mass_cart, mass_pole, length, mu_c, mu_p, f_mag or NULL; cfg = the same seven defaults).  cfg is HOST memory. */
+enum { DUST_AUX_SKID_STEER = 0, DUST_AUX_CARTPOLE = 1 };
+int dust_aux_model_step(int32_t kind, float dt, const float* cfg, int32_t M, const float* states, const float* actions,
+                        const float* params, float* next_states, void* stream);
+
 int dust_model_cost(const dust_model_desc* model, int32_t M, int32_t terminal, const float* states,
                     const float* actions, float* costs, void* stream);
 

@@ -738,3 +738,40 @@ def median_sq_dist_tiled(x, tile=2048, dtype=torch.float32):
     lo = int((cum2 > (k - below)).nonzero()[0])
     bits = (hi << 16) | lo
     return torch.tensor([bits], dtype=torch.int32).view(torch.float32)[0]
+
+
+# =====================================================================================
+# the reference's other two forward models: step only (no cost function / demo ships for them)
+# =====================================================================================
+
+
+def skid_steer_step(x, a, dt, x_icr=0.2, wheel_radius=0.0625, axial_distance=0.475, lo=(-0.5, -0.5), hi=(0.5, 0.5)):
+    """dust/models/skid_steer_robot.py:73-122.  x [M,5], a [M,2] -> [M,5]; parameters scalars or [M,1] tensors."""
+    px, py, th = x[:, 0:1], x[:, 1:2], x[:, 2:3]
+    r = a[:, 0:1].clamp(lo[0], hi[0])
+    l = a[:, 1:2].clamp(lo[1], hi[1])  # noqa: E741
+    lin = (r + l) * math.pi * wheel_radius
+    ang = (r - l) * 2 * math.pi * wheel_radius / axial_distance
+    fwd = lin * dt
+    lat = -ang * x_icr * dt
+    nx = px + fwd * torch.cos(th) - lat * torch.sin(th)
+    ny = py + fwd * torch.sin(th) + lat * torch.cos(th)
+    return torch.cat([nx, ny, th + ang * dt, lin.expand_as(px), ang.expand_as(px)], dim=1)
+
+
+def cartpole_step(x, a, dt=0.05, g=9.8, m_c=1.0, m_p=0.1, length=1.0, mu_c=0.5e-3, mu_p=2e-6, f_mag=10.0):
+    """dust/models/cartpole.py:147-172, the method body as written (`mass = m_c + m_c`, :160).  The reference's method
+    itself raises AttributeError before reaching it (name-mangled `self.__params_dict`, :150-155): PARITY UNPINNED for
+    this function -- there is no reference output to check it against, only the source text."""
+    px, x_d, th, th_d = x.chunk(4, dim=1)
+    acts = torch.clamp(a, min=-1, max=1) * f_mag
+    mass = m_c + m_c
+    pm = m_p * length
+    cart_friction = mu_c * x_d.sign()
+    pole_friction = (mu_p * th_d) / pm
+    factor = (acts + pm * th.sin() * th_d ** 2 - cart_friction) / mass
+    tdd_num = g * th.sin() - th.cos() * factor - pole_friction
+    tdd_den = length * (4.0 / 3 - (m_p * th.cos() ** 2) / mass)
+    theta_dd = tdd_num / tdd_den
+    x_dd = factor - pm * theta_dd * torch.cos(th) / mass
+    return x + torch.cat([x_d, x_dd, th_d, theta_dd], dim=1) * dt

@@ -747,7 +747,58 @@ def gen_optim():
     save("svmpc_pendulum_slow_pred", tags=["shim-dependent:gpytorch", "shim-dependent:KDEpy(dead value)"], **out)
 
 
-GENERATORS = dict(map=gen_map, forward=gen_forward_all, svmpc=gen_svmpc, dual=gen_dual, mpf=gen_mpf, phi=gen_phi,
+# ----------------------------------------------------------------------------------
+# G11: MPF with a non-SGD optimiser (mpf.py:23, 59-62: the optimiser is built once and keeps its state across
+# optimize() calls; Adam is the SVGD default, svgd.py:115)
+# ----------------------------------------------------------------------------------
+def gen_mpf_optim():
+    print("G11 MPF with Adam / momentum SGD")
+    for name, kw in (("mpf_particle_adam", dict(optimizer_class=torch.optim.Adam, lr=0.01)),
+                     ("mpf_particle_momentum", dict(optimizer_class=torch.optim.SGD, lr=0.01, momentum=0.9))):
+        w = make_particle(5)
+        model = w["model"]
+        torch.manual_seed(17)
+        x0 = dist.Normal(2.0, 0.1).sample([50, 1]).clamp(min=1e-6).log()
+        obs0 = torch.tensor([-8.0, -7.5, 1.0, 2.0])
+        lik = likelihoods.GaussianLikelihood(initial_obs=obs0, obs_std=0.1, model=model, log_space=True)
+        mpf = mpf_mod.MPF(init_particles=x0.clone(), likelihood=lik, bw=0.1, bw_scale=1.0, **kw)
+        out = dict(x0=x0, obs0=obs0, prior_bw=np.array(0.1), obs_std=np.array(0.1), lr=np.array(kw["lr"]), bw=np.array(0.5))
+        obs = obs0
+        for c, action in enumerate((torch.tensor([6.0, -3.0]), torch.tensor([-2.0, 5.0]))):   # two calls: the state carries over
+            nxt = model.step(obs.view(1, -1), action.view(1, -1), {"mass": torch.tensor([[3.0]])}).view(-1)
+            gn, bw = mpf.optimize(action, nxt, bw=0.5, n_steps=10)
+            out[f"c{c}_action"], out[f"c{c}_obs1"], out[f"c{c}_x1"], out[f"c{c}_grad_norms"] = action, nxt, mpf.x.detach().clone(), gn
+            obs = nxt
+        save(name, **out)
+
+
+# ----------------------------------------------------------------------------------
+# G12: the skid-steer robot's step (skid_steer_robot.py:73-122).  The cart-pole's step raises AttributeError in the
+# reference (cartpole.py:150-155), so no fixture can be recorded for it.
+# ----------------------------------------------------------------------------------
+def gen_aux_models():
+    print("G12 skid-steer step")
+    sk = ref_import("models.skid_steer_robot")
+    torch.manual_seed(23)
+    m = sk.SkidSteerRobot(delta_t=0.1)
+    M = 64
+    states = torch.randn(M, 5) * torch.tensor([3.0, 3.0, 2.0, 0.3, 0.3])
+    actions = torch.randn(M, 2) * 0.6            # some beyond the +-0.5 wheel-speed box
+    nxt_default = m.step(states, actions, None)
+    pd = {"x_icr": 0.1 + 0.2 * torch.rand(M, 1), "wheel_radius": 0.05 + 0.03 * torch.rand(M, 1),
+          "axial_distance": 0.4 + 0.2 * torch.rand(M, 1)}
+    nxt_sampled = m.step(states, actions, pd)
+    try:
+        ref_import("models.cartpole").CartPoleModel().step(torch.zeros(1, 4), torch.zeros(1, 1))
+        cart_err = ""
+    except Exception as e:  # noqa: BLE001
+        cart_err = type(e).__name__
+    save("skid_steer_step", states=states, actions=actions, next_default=nxt_default, next_sampled=nxt_sampled,
+         x_icr=pd["x_icr"], wheel_radius=pd["wheel_radius"], axial_distance=pd["axial_distance"], dt=np.array(0.1),
+         cartpole_reference_raises=np.array(int(cart_err == "AttributeError")))
+
+
+GENERATORS = dict(aux=gen_aux_models, mpf_optim=gen_mpf_optim, map=gen_map, forward=gen_forward_all, svmpc=gen_svmpc, dual=gen_dual, mpf=gen_mpf, phi=gen_phi,
                   pathwise=gen_pathwise, episode=gen_episode, widen=gen_widen, optim=gen_optim)
 
 if __name__ == "__main__":

@@ -372,3 +372,54 @@ def test_particle_belief_samples_and_log_prob():
     x += 1.0                                   # in-place move of the particles: the belief follows (quirk H24)
     assert float((b.sample([4000]).mean(0) - x.mean(0)).abs().max()) <= 0.03
     assert b.sample([8]).shape == (8, 2) and b.event_shape == torch.Size([2])
+
+
+@pytest.mark.parametrize("name,opt", [("mpf_particle_adam", dict(optimizer_class=torch.optim.Adam, lr=0.01)),
+                                      ("mpf_particle_momentum", dict(optimizer_class=torch.optim.SGD, lr=0.01, momentum=0.9))])
+def test_mpf_class_with_torch_optimizers_on_device(name, opt):
+    """MPF with Adam (the SVGD default, svgd.py:115) and momentum SGD: phi from the kernel one step at a time, the
+    optimiser -- built once, state kept across optimize() calls (mpf.py:23) -- on the device particles."""
+    from dust_b200.inference.likelihoods import GaussianLikelihood
+    from dust_b200.inference.mpf import MPF
+    from dust_b200.models.particle import Particle
+
+    d = load(name)
+    model = Particle(**ENV, uncertain_params=["mass"], mass=2.0)
+    lik = GaussianLikelihood(initial_obs=d["obs0"], obs_std=float(d["obs_std"]), model=model, log_space=True)
+    mpf = MPF(init_particles=d["x0"].clone(), likelihood=lik, bw=float(d["prior_bw"]), bw_scale=1.0, **opt)
+    assert mpf.optimizer is not None
+    worst = {}
+    for c in range(2):
+        gn, bw = mpf.optimize(d[f"c{c}_action"], d[f"c{c}_obs1"], bw=float(d["bw"]), n_steps=10)
+        e_x, e_g = rel_max(mpf.x.cpu(), d[f"c{c}_x1"]), rel_max(gn.cpu(), d[f"c{c}_grad_norms"])
+        worst[f"x_call{c}"], worst[f"grad_norms_call{c}"] = e_x, e_g
+        assert e_x <= RTOL_PHI and e_g <= 1e-3, (c, e_x, e_g)
+    record_parity(f"MPF class {name}", **worst)
+
+
+def test_skid_steer_and_cartpole_step_on_device():
+    """The reference's two other forward models (step only): the skid-steer robot against the reference's recording,
+    the cart-pole against the restatement of its method body (the reference's own step raises: parity unpinned)."""
+    from dust_b200.models.cartpole import CartPoleModel
+    from dust_b200.models.skid_steer_robot import SkidSteerRobot
+
+    d = load("skid_steer_step")
+    m = SkidSteerRobot(delta_t=float(d["dt"]))
+    nd = m.step(cu(d["states"]), cu(d["actions"]), None).cpu()
+    ns = m.step(cu(d["states"]), cu(d["actions"]), {k: cu(d[k]) for k in ("x_icr", "wheel_radius", "axial_distance")}).cpu()
+    e1, e2 = rel_elem(nd, d["next_default"], floor=1e-6), rel_elem(ns, d["next_sampled"], floor=1e-6)
+    assert e1 <= RTOL_COST and e2 <= RTOL_COST, (e1, e2)       # sinf / cosf differ from libm in the last bits
+    torch.manual_seed(31)
+    M = 200
+    x = torch.randn(M, 4) * torch.tensor([1.0, 2.0, 0.3, 1.5])
+    a = torch.randn(M, 1) * 0.8
+    cp = CartPoleModel()
+    got = cp.step(cu(x), cu(a)).cpu()
+    ref = O.cartpole_step(x.double(), a.double())
+    e3 = rel_elem(got, ref, floor=1e-6)
+    pd = {"mass_pole": 0.05 + 0.1 * torch.rand(M, 1), "length": 0.5 + torch.rand(M, 1)}
+    got_p = cp.step(cu(x), cu(a), {k: cu(v) for k, v in pd.items()}).cpu()
+    ref_p = O.cartpole_step(x.double(), a.double(), m_p=pd["mass_pole"].double(), length=pd["length"].double())
+    e4 = rel_elem(got_p, ref_p, floor=1e-6)
+    assert e3 <= RTOL_COST and e4 <= RTOL_COST, (e3, e4)
+    record_parity("skid-steer / cart-pole step", skid_default=e1, skid_sampled=e2, cartpole_default=e3, cartpole_sampled=e4)

@@ -375,5 +375,6 @@ def test_mpf_class_on_cpu(monkeypatch):
         assert rel_max(mpf.x, d[f"t{t}_out_mpf_x1"]) <= 5e-4 and gn.shape == (20,)
         assert rel_max(gn, d[f"t{t}_out_mpf_grad_norms"]) <= 5e-3
     assert torch.equal(prior0.component_distribution.base_dist.loc, mpf.x)
-    with pytest.raises(NotImplementedError):
-        mpf_module.MPF(init_particles=d["t0_in_mpf_x0"].clone(), likelihood=lik, optimizer_class=torch.optim.Adam, device="cpu")
+    # any other optimiser is built once over the particle tensor (mpf.py:23) and stepped on phi from the kernel
+    adam = mpf_module.MPF(init_particles=d["t0_in_mpf_x0"].clone(), likelihood=lik, optimizer_class=torch.optim.Adam, device="cpu")
+    assert isinstance(adam.optimizer, torch.optim.Adam) and adam.optimizer.param_groups[0]["params"][0] is adam.x

@@ -266,3 +266,37 @@ def test_particle_episode_against_reference_driver(cfg):
     assert errs[0] == 0.0 and errs[1] == 0.0, errs
     assert max(errs[:5]) <= 2e-6 and max(errs) <= 2e-3, errs
     assert abs(cum - float(d["cum_cost"])) <= 1e-3 * float(d["cum_cost"])
+
+
+@pytest.mark.parametrize("name,mk", [("mpf_particle_adam", lambda p: torch.optim.Adam(p, lr=0.01)),
+                                     ("mpf_particle_momentum", lambda p: torch.optim.SGD(p, lr=0.01, momentum=0.9))])
+def test_mpf_with_torch_optimizers_oracle(name, mk):
+    """MPF with a non-SGD optimiser (mpf.py:23, 59-62): the optimiser is built once and keeps its state across
+    optimize() calls; the prior of the second call carries the first call's bandwidth (mpf.py:84)."""
+    from tests.util import golden_grid
+
+    d = load(name)
+    model = O.Model("particle", O.ParticleCfg(golden_grid()))
+    x = d["x0"].clone().double()
+    opt = mk([x])
+    obs, pv = d["obs0"].double(), float(d["prior_bw"]) ** 2
+    for c in range(2):
+        act, nxt = d[f"c{c}_action"].double(), d[f"c{c}_obs1"].double()
+        for _ in range(10):
+            phi = O.mpf_phi(model, x.detach(), obs, act, nxt, float(d["obs_std"]), pv, float(d["bw"]), True)
+            opt.zero_grad()
+            x.grad = -phi
+            opt.step()
+        assert rel_max(x.detach(), d[f"c{c}_x1"]) <= 2e-5
+        obs, pv = nxt, float(d["bw"]) ** 2
+
+
+def test_skid_steer_step_oracle_equals_reference():
+    """skid_steer_robot.py:73-122 with default and with per-row sampled parameters, bit for bit; and the reason there is
+    no cart-pole fixture: the reference's own CartPoleModel.step raises (cartpole.py:150-155)."""
+    d = load("skid_steer_step")
+    a = O.skid_steer_step(d["states"], d["actions"], float(d["dt"]))
+    assert torch.equal(a, d["next_default"])
+    b = O.skid_steer_step(d["states"], d["actions"], float(d["dt"]), d["x_icr"], d["wheel_radius"], d["axial_distance"])
+    assert torch.equal(b, d["next_sampled"])
+    assert int(d["cartpole_reference_raises"]) == 1          # recorded: the AttributeError of the reference's CartPoleModel.step
