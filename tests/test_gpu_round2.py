@@ -416,10 +416,11 @@ def test_skid_steer_and_cartpole_step_on_device():
     cp = CartPoleModel()
     got = cp.step(cu(x), cu(a)).cpu()
     ref = O.cartpole_step(x.double(), a.double())
-    e3 = rel_elem(got, ref, floor=1e-6)
+    e3 = rel_max(got, ref)                       # norm-wise: theta_dd cancels to ~0 for some rows
     pd = {"mass_pole": 0.05 + 0.1 * torch.rand(M, 1), "length": 0.5 + torch.rand(M, 1)}
     got_p = cp.step(cu(x), cu(a), {k: cu(v) for k, v in pd.items()}).cpu()
     ref_p = O.cartpole_step(x.double(), a.double(), m_p=pd["mass_pole"].double(), length=pd["length"].double())
-    e4 = rel_elem(got_p, ref_p, floor=1e-6)
-    assert e3 <= RTOL_COST and e4 <= RTOL_COST, (e3, e4)
+    e4 = rel_max(got_p, ref_p)
+    assert e3 <= 2e-6 and e4 <= 2e-6, (e3, e4)
+    assert rel_elem(got, ref, floor=1e-2) <= RTOL_COST and rel_elem(got_p, ref_p, floor=1e-2) <= RTOL_COST
     record_parity("skid-steer / cart-pole step", skid_default=e1, skid_sampled=e2, cartpole_default=e3, cartpole_sampled=e4)
