@@ -35,7 +35,7 @@ def float64_rows(X, S, idx, gamma, c1, c2):
     return c1 * (K @ Sd) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xd)
 
 
-def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="separate", emulate_world=1, checks=True):
+def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="packed", emulate_world=1, checks=True):
     import torch.distributed as dist
 
     from dust_b200 import _lib as L
@@ -170,11 +170,13 @@ def main():
     ap.add_argument("--dim", type=int, default=40)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--gather", default="separate", choices=["packed", "separate"],
-                    help="sharded runs: X and score gathered into their own buffers (default) or one all-gather of [X | score]")
+    ap.add_argument("--gather", default="packed", choices=["packed", "separate"],
+                    help="sharded runs: one all-gather of [X | score], read in place through a row stride (default), or X and score "
+                         "gathered into their own buffers by two collectives")
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="single process only: time the row block ONE rank of a world of this size computes (all N "
                          "columns resident, no collective) -- the per-rank device work of the sharded run")
+    ap.add_argument("--no-checks", action="store_true", help="skip the float64 / radix-select checks (profiler captures)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -186,7 +188,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    out = phi_block(rank, world, dev, args.steps, args.warmup, args.particles, args.dim, args.gather, args.emulate_world)
+    out = phi_block(rank, world, dev, args.steps, args.warmup, args.particles, args.dim, args.gather, args.emulate_world,
+                    checks=not args.no_checks)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:

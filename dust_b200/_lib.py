@@ -74,7 +74,7 @@ class GmmArgs(C.Structure):
 class MedianArgs(C.Structure):
     _fields_ = [
         ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("x", _p), ("hist", _p),
-        ("selected", _p), ("row_norms", _p), ("sample_begin", _i), ("sample_end", _i),
+        ("selected", _p), ("row_norms", _p), ("sample_begin", _i), ("sample_end", _i), ("ld", _i),
     ]
 
 
@@ -83,7 +83,7 @@ class PhiArgs(C.Structure):
         ("B", _i), ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("per_dim", _i),
         ("x", _p), ("score", _p), ("gamma", _f), ("c1", _f), ("c2", _f), ("gamma_dev", _p),
         ("bw_scale", _f), ("lr", _f), ("phi", _p), ("x_out", _p), ("bandwidths", _p),
-        ("workspace", _p), ("workspace_bytes", _sz), ("x_prepared", _i),
+        ("workspace", _p), ("workspace_bytes", _sz), ("x_prepared", _i), ("ld", _i),
     ]
 
 
@@ -206,6 +206,16 @@ def ptr(t):
         raise ValueError(f"dust_b200: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()} "
                          "(kernels are enqueued on the current device's stream: wrap the call in torch.cuda.device(...))")
     return t.data_ptr()
+
+
+def ptr_rows(t):
+    """(device pointer, row stride in floats) of a 2-D float32 CUDA tensor whose rows are contiguous but may be spaced
+    (a column slice of a wider buffer, e.g. X = packed[:, :D])."""
+    if t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda or t.dtype != torch.float32:
+        raise ValueError("dust_b200: expected a 2-D float32 CUDA tensor with unit column stride")
+    if t.device.index != torch.cuda.current_device():
+        raise ValueError(f"dust_b200: tensor lives on {t.device} but the current device is cuda:{torch.cuda.current_device()}")
+    return t.data_ptr(), int(t.stride(0))
 
 
 def profiler_report():

@@ -14,20 +14,20 @@ constexpr int kLT = 64;        // tile edge (rows and columns)
 constexpr int kLThreads = 256; // 16 x 16 threads, 4 x 4 micro-tile each
 
 // squared row norms
-__global__ void row_norms_kernel(const float* __restrict__ x, int N, int D, float* __restrict__ xn) {
+__global__ void row_norms_kernel(const float* __restrict__ x, int N, int D, int ld, float* __restrict__ xn) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   float s = 0.f;
-  for (int d = 0; d < D; ++d) { const float v = x[(long long)i * D + d]; s += v * v; }
+  for (int d = 0; d < D; ++d) { const float v = x[(long long)i * ld + d]; s += v * v; }
   xn[i] = s;
 }
 
-// stage a [kLT, D] block of rows transposed into shared memory: dst[d][r]
-__device__ __forceinline__ void stage_rows_T(const float* __restrict__ x, int N, int D, int r0, float* dst) {
+// stage a [kLT, D] block of rows (row stride ld floats) transposed into shared memory: dst[d][r]
+__device__ __forceinline__ void stage_rows_T(const float* __restrict__ x, int N, int D, int ld, int r0, float* dst) {
   for (int e = threadIdx.x; e < kLT * D; e += kLThreads) {
     const int r = e / D, d = e - r * D;
     const int gi = r0 + r;
-    dst[d * kLT + r] = gi < N ? __ldg(x + (long long)gi * D + d) : 0.f;
+    dst[d * kLT + r] = gi < N ? __ldg(x + (long long)gi * ld + d) : 0.f;
   }
 }
 
@@ -62,7 +62,7 @@ __device__ __forceinline__ void tile_d2(const float* xi_t, const float* xj_t, co
 // median: histogram passes
 // ---------------------------------------------------------------------------------------
 struct HistKParams {
-  int N, D, row_begin, row_end, pass;
+  int N, D, ld, row_begin, row_end, pass;
   const float *x, *xn;
   unsigned long long* hist;
   const uint32_t* selected;
@@ -80,12 +80,12 @@ __global__ void __launch_bounds__(kLThreads) median_hist_kernel(const HistKParam
   const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   if (k.pass == 0)
     for (int e = threadIdx.x; e < 32768; e += kLThreads) lh[e] = 0u;
-  stage_rows_T(k.x, k.row_end, k.D, i0, xi_t);
+  stage_rows_T(k.x, k.row_end, k.D, k.ld, i0, xi_t);
   if (threadIdx.x < kLT) xn_i[threadIdx.x] = (i0 + threadIdx.x < k.row_end) ? k.xn[i0 + threadIdx.x] : 0.f;
   const uint32_t sel_hi = k.pass == 1 ? k.selected[0] : 0u;
   for (int j0 = 0; j0 < k.N; j0 += kLT) {
     __syncthreads();
-    stage_rows_T(k.x, k.N, k.D, j0, xj_t);
+    stage_rows_T(k.x, k.N, k.D, k.ld, j0, xj_t);
     if (threadIdx.x < kLT) xn_j[threadIdx.x] = (j0 + threadIdx.x < k.N) ? k.xn[j0 + threadIdx.x] : 0.f;
     __syncthreads();
     float d2[4][4];
@@ -189,11 +189,11 @@ __global__ void __launch_bounds__(kLThreads) phi_large_kernel(const PhiLKParams 
   float acc[MAXQ];
 #pragma unroll
   for (int q = 0; q < MAXQ; ++q) acc[q] = 0.f;
-  stage_rows_T(k.x, k.row_end, D, i0, xi_t);
+  stage_rows_T(k.x, k.row_end, D, D, i0, xi_t);
   if (threadIdx.x < kLT) xn_i[threadIdx.x] = (i0 + threadIdx.x < k.row_end) ? k.xn[i0 + threadIdx.x] : 0.f;
   for (int j0 = 0; j0 < k.N; j0 += kLT) {
     __syncthreads();
-    stage_rows_T(k.x, k.N, D, j0, xj_t);
+    stage_rows_T(k.x, k.N, D, D, j0, xj_t);
     if (threadIdx.x < kLT) xn_j[threadIdx.x] = (j0 + threadIdx.x < k.N) ? k.xn[j0 + threadIdx.x] : 0.f;
     for (int e = threadIdx.x; e < kLT * C; e += kLThreads) {
       const int r = e / C, c = e - r * C;
@@ -258,13 +258,14 @@ int phi_large(const dust_phi_args* a, cudaStream_t stream) {
   DUST_REQUIRE(a->workspace && a->workspace_bytes >= phi_large_workspace(a), DUST_ERR_WORKSPACE,
                "dust_svgd_phi: large-N path needs %zu bytes of workspace", phi_large_workspace(a));
   if (phi_tc_supported(a) && !getenv("DUST_B200_NO_TC")) return phi_tc(a, stream);
+  DUST_REQUIRE(a->ld == 0 || a->ld == a->D, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: a row stride (ld=%d) needs the tensor-core path", a->ld);
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   const size_t smem = sizeof(float) * ((size_t)2 * D * kLT + 2 * kLT + kLT * (kLT + 1) + (size_t)kLT * C);
   DUST_REQUIRE(smem <= 227 * 1024 && C <= 4 * 68, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: D=%d too large for the tiled kernel", D);
   for (int b = 0; b < a->B; ++b) {
     const float* x = a->x + (size_t)b * a->N * D;
     float* xn = (float*)a->workspace + (size_t)b * a->N;
-    { DUST_TIMED("row_norms_kernel", stream); row_norms_kernel<<<ceil_div(a->N, 256), 256, 0, stream>>>(x, a->N, D, xn); }
+    { DUST_TIMED("row_norms_kernel", stream); row_norms_kernel<<<ceil_div(a->N, 256), 256, 0, stream>>>(x, a->N, D, D, xn); }
     DUST_LAUNCH_OK("row_norms_kernel");
     PhiLKParams k{a->N, D, r0, r1, x, a->score + (size_t)b * a->N * D, xn, a->gamma, a->c1, a->c2, a->gamma_dev, a->lr,
                   a->phi ? a->phi + (size_t)b * a->N * D : nullptr, a->x_out ? a->x_out + (size_t)b * a->N * D : nullptr};
@@ -292,17 +293,19 @@ using namespace dust;
 extern "C" int dust_median_hist_pass(const dust_median_args* a, int32_t pass, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   DUST_REQUIRE(a != nullptr, DUST_ERR_INVALID_ARG, "dust_median_hist_pass: args is NULL");
+  DUST_REQUIRE(a->ld == 0 || a->ld >= a->D, DUST_ERR_INVALID_ARG, "dust_median_hist_pass: ld=%d < D=%d", a->ld, a->D);
   DUST_REQUIRE(a->N > 0 && a->D > 0 && a->x && a->hist && a->selected && a->row_norms, DUST_ERR_INVALID_ARG,
                "dust_median_hist_pass: N, D, x, hist, selected, row_norms are required");
   DUST_REQUIRE(pass == 0 || pass == 1, DUST_ERR_INVALID_ARG, "dust_median_hist_pass: pass must be 0 or 1");
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   DUST_REQUIRE(r0 >= 0 && r1 <= a->N && r0 < r1, DUST_ERR_INVALID_ARG, "dust_median_hist_pass: bad row range");
   float* xn = a->row_norms;
+  const int ld = a->ld > 0 ? a->ld : a->D;
   if (pass == 0) {
-    { DUST_TIMED("row_norms_kernel", stream); row_norms_kernel<<<ceil_div(a->N, 256), 256, 0, stream>>>(a->x, a->N, a->D, xn); }
+    { DUST_TIMED("row_norms_kernel", stream); row_norms_kernel<<<ceil_div(a->N, 256), 256, 0, stream>>>(a->x, a->N, a->D, ld, xn); }
     DUST_LAUNCH_OK("row_norms_kernel");
   }
-  HistKParams k{a->N, a->D, r0, r1, pass, a->x, xn, a->hist, a->selected};
+  HistKParams k{a->N, a->D, ld, r0, r1, pass, a->x, xn, a->hist, a->selected};
   size_t smem = sizeof(float) * ((size_t)2 * a->D * kLT + 2 * kLT) + (pass == 0 ? sizeof(uint32_t) * 32768 : 0);
   DUST_REQUIRE(smem <= 227 * 1024, DUST_ERR_UNSUPPORTED, "dust_median_hist_pass: D=%d too large", a->D);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -332,6 +335,7 @@ static int check_fast(const dust_median_args* a, const void* workspace, size_t b
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   DUST_REQUIRE(r0 >= 0 && r1 <= a->N && r0 < r1 && r0 % 128 == 0 && r1 % 128 == 0, DUST_ERR_INVALID_ARG,
                "%s: row range must be 128-aligned", who);
+  DUST_REQUIRE(a->ld == 0 || a->ld >= a->D, DUST_ERR_INVALID_ARG, "%s: ld=%d < D=%d", who, a->ld, a->D);
   DUST_REQUIRE(a->sample_begin >= 0 && a->sample_end >= a->sample_begin && a->sample_end <= (1 << 20), DUST_ERR_INVALID_ARG,
                "%s: sample share [%d, %d) outside [0, 2^20)", who, a->sample_begin, a->sample_end);
   return DUST_OK;

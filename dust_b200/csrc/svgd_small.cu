@@ -408,7 +408,9 @@ extern "C" int dust_svgd_phi(const dust_phi_args* a, void* stream_) {
   DUST_REQUIRE(r0 >= 0 && r1 <= a->N && r0 < r1, DUST_ERR_INVALID_ARG, "dust_svgd_phi: bad row range [%d,%d)", r0, r1);
   DUST_REQUIRE(a->x_out != a->x, DUST_ERR_INVALID_ARG,
                "dust_svgd_phi: x_out must not alias x (rows are read by other warps)");
+  DUST_REQUIRE(a->ld == 0 || a->ld >= a->D, DUST_ERR_INVALID_ARG, "dust_svgd_phi: ld=%d < D=%d", a->ld, a->D);
   if (!a->per_dim && (a->N > kSmallPhiMaxN || a->D > 32 * kMaxDPerLane)) return phi_large(a, stream);
+  DUST_REQUIRE(a->ld == 0 || a->ld == a->D, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: a row stride (ld=%d) needs the tensor-core path", a->ld);
   DUST_REQUIRE(a->D <= 32 * kMaxDPerLane, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: D=%d > %d in per_dim mode", a->D, 32 * kMaxDPerLane);
   DUST_REQUIRE(a->B <= 65535, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: B > 65535");
   PhiKParams k{a->B, a->N, a->D, r0, r1, a->x, a->score, a->gamma, a->c1, a->c2, a->gamma_dev, a->lr, a->phi, a->x_out, nullptr};

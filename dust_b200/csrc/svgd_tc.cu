@@ -39,6 +39,7 @@ constexpr int kXnStages = 16;     // |x_j|^2 ring of the median kernel
 
 struct TcParams {
   int N, D, Dp, NV, T, row_begin;
+  int ld;   // row stride of x (floats)
   // The (row tile, column tile) pairs of a call are numbered row-major, u = rt * T + j, and cut into equal
   // contiguous ranges: CTA c owns units [c * units_per_cta, (c + 1) * units_per_cta).  A range that crosses
   // a row-tile boundary is worked off as consecutive SEGMENTS (one per row tile), each with its own slot
@@ -70,7 +71,7 @@ __device__ __forceinline__ float tf32_lo(float v, float hi) { return __uint_as_f
 // which is core_index() inside a 128-row tile AND inside a 64-row tile (both are whole 8-row groups
 // laid out in row order).  Thread <-> one 16-byte core-matrix row, in image order: a warp writes 512
 // contiguous bytes per image and reads 64-byte pieces of 8 rows.
-__device__ __forceinline__ void tc_prep_x_block(int block, const float* __restrict__ x, int N, int D, int Dp,
+__device__ __forceinline__ void tc_prep_x_block(int block, const float* __restrict__ x, int N, int D, int ld, int Dp,
                                                 float* __restrict__ x_hi, float* __restrict__ x_lo) {
   const long long e = (long long)block * blockDim.x + threadIdx.x;   // index of the float4 in the image
   const int kq = Dp >> 2;
@@ -80,8 +81,8 @@ __device__ __forceinline__ void tc_prep_x_block(int block, const float* __restri
   const int kg = (int)(t % kq);
   const int row = (int)(t / kq) * 8 + r7, k = kg * 4;
   float v[4];
-  const float* xr = x + (long long)row * D;
-  if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0) && k + 3 < D) {
+  const float* xr = x + (long long)row * ld;
+  if ((D & 3) == 0 && (ld & 3) == 0 && ((((uintptr_t)x) & 15) == 0) && k + 3 < D) {
     const float4 q = __ldg(reinterpret_cast<const float4*>(xr + k));
     v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
   } else {
@@ -96,12 +97,12 @@ __device__ __forceinline__ void tc_prep_x_block(int block, const float* __restri
 }
 
 // |x_i|^2 as one fused-multiply-add chain over d = 0 .. D-1 per row (a warp reads 32 consecutive rows)
-__device__ __forceinline__ void tc_norms_block(int block, const float* __restrict__ x, int N, int D, float* __restrict__ xn) {
+__device__ __forceinline__ void tc_norms_block(int block, const float* __restrict__ x, int N, int D, int ld, float* __restrict__ xn) {
   const int row = block * blockDim.x + threadIdx.x;
   if (row >= N) return;
-  const float* xr = x + (long long)row * D;
+  const float* xr = x + (long long)row * ld;
   float s = 0.f;
-  if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0)) {
+  if ((D & 3) == 0 && (ld & 3) == 0 && ((((uintptr_t)x) & 15) == 0)) {
     for (int d = 0; d < D; d += 4) {
       const float4 q = __ldg(reinterpret_cast<const float4*>(xr + d));
       s = fmaf(q.x, q.x, s); s = fmaf(q.y, q.y, s); s = fmaf(q.z, q.z, s); s = fmaf(q.w, q.w, s);
@@ -117,7 +118,7 @@ __device__ __forceinline__ void tc_norms_block(int block, const float* __restric
 // Thread <-> one 16-byte core-matrix row = 4 consecutive particles of one dimension, in image order:
 // element (n2, jj) of tile jt sits at jt * NV * 64 + ((n2 >> 3) * 16 + (jj >> 2)) * 32 + (n2 & 7) * 4 + (jj & 3).
 __device__ __forceinline__ void tc_prep_v_block(int block, const float* __restrict__ x, const float* __restrict__ score, int N,
-                                                int D, int NV, float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
+                                                int D, int ld, int NV, float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
   const long long e = (long long)block * blockDim.x + threadIdx.x;   // index of the float4 in the image
   if (e >= (long long)(N >> 2) * NV) return;
   const int per_tile = NV * (kTcBN >> 2);
@@ -128,7 +129,7 @@ __device__ __forceinline__ void tc_prep_v_block(int block, const float* __restri
   if (n2 < 2 * D) {
     const float* src = n2 < D ? score + n2 : x + (n2 - D);
 #pragma unroll
-    for (int c = 0; c < 4; ++c) v[c] = __ldg(src + (long long)(j + c) * D);
+    for (int c = 0; c < 4; ++c) v[c] = __ldg(src + (long long)(j + c) * ld);
   }
   float4 hi, lo;
   hi.x = tf32_hi(v[0]); hi.y = tf32_hi(v[1]); hi.z = tf32_hi(v[2]); hi.w = tf32_hi(v[3]);
@@ -140,17 +141,17 @@ __device__ __forceinline__ void tc_prep_v_block(int block, const float* __restri
 // ONE launch prepares everything a pass needs: CTAs [0, nbx) write the X images, [nbx, nbx + nbv) the
 // V^T images (nbv = 0 for the median pass, which has no second GEMM), the rest the squared norms --
 // three small memory-bound jobs that overlap instead of queueing behind each other's launch
-__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D,
+__global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D, int ld,
                                                       int Dp, int NV, float* __restrict__ x_hi, float* __restrict__ x_lo,
                                                       float* __restrict__ vb_hi, float* __restrict__ vb_lo,
                                                       float* __restrict__ xn, int nbx, int nbv) {
   const int b = blockIdx.x;
-  if (b < nbx) tc_prep_x_block(b, x, N, D, Dp, x_hi, x_lo);
-  else if (b < nbx + nbv) tc_prep_v_block(b - nbx, x, score, N, D, NV, vb_hi, vb_lo);
-  else tc_norms_block(b - nbx - nbv, x, N, D, xn);
+  if (b < nbx) tc_prep_x_block(b, x, N, D, ld, Dp, x_hi, x_lo);
+  else if (b < nbx + nbv) tc_prep_v_block(b - nbx, x, score, N, D, ld, NV, vb_hi, vb_lo);
+  else tc_norms_block(b - nbx - nbv, x, N, D, ld, xn);
 }
 
-static int tc_prep(const float* x, const float* score, int N, int D, int Dp, int NV, float* x_hi, float* x_lo, float* vb_hi,
+static int tc_prep(const float* x, const float* score, int N, int D, int ld, int Dp, int NV, float* x_hi, float* x_lo, float* vb_hi,
                    float* vb_lo, float* xn, cudaStream_t stream, bool x_prepared = false) {
   // x_prepared: the X images and the norms are already in place (median pass on the same workspace): V^T images only
   const int nbx = x_prepared ? 0 : ceil_div((long long)N * (Dp / 4), 256);
@@ -159,7 +160,7 @@ static int tc_prep(const float* x, const float* score, int N, int D, int Dp, int
   if (nbx + nbv + nbn == 0) return DUST_OK;
   {
     DUST_TIMED("tc_prep_kernel", stream);
-    tc_prep_kernel<<<nbx + nbv + nbn, 256, 0, stream>>>(x, score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, nbx, nbv);
+    tc_prep_kernel<<<nbx + nbv + nbn, 256, 0, stream>>>(x, score, N, D, ld, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, nbx, nbv);
   }
   DUST_LAUNCH_OK("tc_prep_kernel");
   return DUST_OK;
@@ -598,7 +599,7 @@ __global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) 
       ks += og[(size_t)d * kTcBM];
       kx += og[(size_t)(p.D + d) * kTcBM];
     }
-    const float xv = p.x[(long long)gi * p.D + d];
+    const float xv = p.x[(long long)gi * p.ld + d];
     const float ph = c1 * ks + c2 * (ksum * xv - kx);
     if (p.phi) p.phi[(long long)gi * p.D + d] = ph;
     if (p.x_out) p.x_out[(long long)gi * p.D + d] = xv + p.lr * ph;
@@ -700,16 +701,16 @@ __device__ __forceinline__ void warp_find_rank(const T* arr, int per_lane, unsig
 // the global one at the end (the sample spreads over a few hundred bins: per-sample global atomics
 // queue up on them).
 __global__ void __launch_bounds__(kMedSampleThreads) med_sample_kernel(const float* __restrict__ x, const float* __restrict__ xn,
-                                                                       int N, int D, unsigned int* __restrict__ hist32,
+                                                                       int N, int D, int ld, unsigned int* __restrict__ hist32,
                                                                        int k_begin, int k_end) {
   extern __shared__ unsigned int hs[];   // [32768]
   for (int b = threadIdx.x; b < 32768; b += blockDim.x) hs[b] = 0u;
   __syncthreads();
-  const bool vec = (D & 3) == 0 && ((((uintptr_t)x) & 15) == 0);   // rows are 16-byte aligned: independent 128-bit loads
+  const bool vec = (D & 3) == 0 && (ld & 3) == 0 && ((((uintptr_t)x) & 15) == 0);   // rows are 16-byte aligned: independent 128-bit loads
   for (int k = k_begin + blockIdx.x * blockDim.x + threadIdx.x; k < k_end; k += gridDim.x * blockDim.x) {
     const uint32_t i = hash32(2u * k + 1u) % (uint32_t)N, j = hash32(2u * k + 0x9e3779b9u) % (uint32_t)N;
-    const float* __restrict__ xi = x + (long long)i * D;
-    const float* __restrict__ xj = x + (long long)j * D;
+    const float* __restrict__ xi = x + (long long)i * ld;
+    const float* __restrict__ xj = x + (long long)j * ld;
     float dot = 0.f;
     if (vec) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -771,8 +772,10 @@ __global__ void __launch_bounds__(1024) med_sample_select_kernel(unsigned int* h
   for (int b = t; b < 32768; b += 1024) hist32[b] = 0u;
 }
 
+constexpr int kMedConsumers = kTcThreads - 128;   // threads of the three consumer warpgroups (warps 4..15)
 struct MedTcParams {
   int N, Dp, T, row_begin, ksplit;
+  int xb_stages;                     // operand ring depth (<= kMedXbStages), as many as fit beside the hit queues
   int kcount, kchunk;                // circular half band: T/2 + 1 column tiles per row tile, kchunk of them per CTA
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *xn;
   const uint32_t* state;             // [0] window start
@@ -781,18 +784,28 @@ struct MedTcParams {
 
 enum { MB_A = 0, MB_XB_FULL = 1, MB_XB_EMPTY = 7, MB_XN_FULL = 13, MB_XN_EMPTY = 29, MB_S_FULL = 45, MB_S_EMPTY = 51, MB_COUNT = 57 };
 
-__host__ __device__ inline size_t med_smem_bytes(int Dp) {
-  return (size_t)2 * kTcBM * Dp * 4 + (size_t)kMedXbStages * 2 * kTcBN * Dp * 4 + (size_t)kXnStages * kTcBN * 4 + 64 * 8 + 64;
+// A operand (hi, lo), operand ring, |x_j|^2 ring, barriers + TMEM slot, then the consumers' hit queues: 32 window
+// hits per thread (one per element of a 32-column half), interleaved by thread
+__host__ __device__ inline size_t med_smem_bytes(int Dp, int stages) {
+  return (size_t)2 * kTcBM * Dp * 4 + (size_t)stages * 2 * kTcBN * Dp * 4 + (size_t)kXnStages * kTcBN * 4 + 64 * 8 + 64 +
+         (size_t)kMedConsumers * 32 * 4;
+}
+__host__ __device__ inline int med_xb_stages(int Dp) {
+  for (int s = kMedXbStages; s >= 3; --s)
+    if (med_smem_bytes(Dp, s) <= 227 * 1024) return s;
+  return 0;
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t a_bytes = kTcBM * p.Dp * 4, xb_half = kTcBN * p.Dp * 4, xb_stage = 2 * xb_half;
   const uint32_t off_a_hi = 0, off_a_lo = a_bytes, off_xb = 2 * a_bytes;
-  const uint32_t off_xn = off_xb + kMedXbStages * xb_stage;
+  const int nstage = p.xb_stages;
+  const uint32_t off_xn = off_xb + nstage * xb_stage;
   const uint32_t off_bars = (off_xn + kXnStages * kTcBN * 4 + 7) & ~7u;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + off_bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + off_bars + 64 * 8);
+  const uint32_t off_hitq = off_bars + 64 * 8 + 64;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i0 = p.row_begin + (blockIdx.x / p.ksplit) * kTcBM;
   // d2 is symmetric: in units of 128-point blocks (Tb = N/128 of them; a block is one row tile and
@@ -810,7 +823,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[MB_A], 1);
-    for (int s = 0; s < kMedXbStages; ++s) { mbar_init(&bars[MB_XB_FULL + s], 1); mbar_init(&bars[MB_XB_EMPTY + s], 1); }
+    for (int s = 0; s < kMedXbStages; ++s) { mbar_init(&bars[MB_XB_FULL + s], 1); mbar_init(&bars[MB_XB_EMPTY + s], 1); }   // nstage of them are used
     // the |x_j|^2 slices ride in their own deep ring, recycled by the 4 consumer warps of a tile, so an
     // operand stage is free as soon as its MMAs retire
     for (int s = 0; s < kXnStages; ++s) { mbar_init(&bars[MB_XN_FULL + s], 1); mbar_init(&bars[MB_XN_EMPTY + s], 4); }
@@ -834,8 +847,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       bulk_g2s(smem + off_a_hi, p.xa_hi + arow, a_bytes, &bars[MB_A]);
       bulk_g2s(smem + off_a_lo, p.xa_lo + arow, a_bytes, &bars[MB_A]);
       for (int j = 0; j < T; ++j) {
-        const int sx = j % kMedXbStages, sn = j % kXnStages;
-        mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / kMedXbStages) & 1) ^ 1);
+        const int sx = j % nstage, sn = j % kXnStages;
+        mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / nstage) & 1) ^ 1);
         unsigned char* xb = smem + off_xb + sx * xb_stage;
         mbar_expect_tx(&bars[MB_XB_FULL + sx], xb_stage);
         const long long jt = col_tile(j);
@@ -857,8 +870,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       const uint32_t xb_stage16 = xb_stage >> 4, xb_half16 = xb_half >> 4;
       if (T > 0) mbar_wait(&bars[MB_A], 0);
       for (int j = 0; j < T; ++j) {
-        const int b = j % kMedSBufs, sx = j % kMedXbStages;
-        mbar_wait(&bars[MB_XB_FULL + sx], (j / kMedXbStages) & 1);
+        const int b = j % kMedSBufs, sx = j % nstage;
+        mbar_wait(&bars[MB_XB_FULL + sx], (j / nstage) & 1);
         mbar_wait(&bars[MB_S_EMPTY + b], ((j / kMedSBufs) & 1) ^ 1);
         tc_fence_after();
         const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
@@ -889,6 +902,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
     const float xn_i = p.xn[i0 + row];
     const int jdiag = (i0 + row) / kTcBN;
     const uint32_t win_lo = p.state[0], win_n = p.state[2];
+    // this thread's hit queue: entry i at hitq[i * kMedConsumers + consumer index] (conflict-free across a warp)
+    const uint32_t q0 = smem_u32(smem + off_hitq) + (uint32_t)(threadIdx.x - 128) * 4u;
     unsigned int below = 0;
     for (int j = wg; j < T; j += 3) {
       const int b = j % kMedSBufs, sn = j % kXnStages;
@@ -900,6 +915,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       const int cdiag = (col_tile(j) == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
       const uint32_t wgt = (kb == 0 || 2 * kb == Tb) ? 1u : 2u;
       const unsigned long long wgt64 = wgt;
+      uint32_t nbelow = 0;                 // minus the number of values below the window in this tile
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
@@ -910,21 +926,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
           for (int c = 0; c < 32; ++c)
             if (half * 32 + c == cdiag) r[c] = __float_as_uint(0.5f * (xnj[half * 32 + c] + xn_i));  // => d2 = 0
         }
-        // branch-free per element: a divergent `if (in window) atomicAdd` costs ~10 extra
-        // instructions of reconvergence bookkeeping per distance
+        // Per distance: d2, its position relative to the window (the borrow of the subtraction counts the values
+        // below it), and -- for the ~3 % inside the window -- a predicated store of that position into the thread's
+        // queue.  The 64-bit histogram updates (address arithmetic, descriptor, reduction) run afterwards, for the
+        // hits only: per-element predicated `red.global` compiled to a branch + descriptor moves around EVERY element.
+        uint32_t qa = q0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
           const float s = __uint_as_float(r[c]);
-          const float d2 = fmaxf((xnj[half * 32 + c] - 2.0f * s) + xn_i, 0.f);
-          const uint32_t rel = __float_as_uint(d2) - win_lo;   // wraps (top bit set) iff below the window
-          below += (rel >> 31) * wgt;
+          const float d2 = fmaxf(fmaf(-2.0f, s, xnj[half * 32 + c]) + xn_i, 0.f);   // 2s is exact: same value as (x_j - 2s) + x_i
           asm volatile(
-              "{\n\t.reg .pred p;\n\t.reg .u64 a;\n\t"
-              "setp.lt.u32 p, %1, %2;\n\t"
-              "mad.wide.u32 a, %1, 8, %0;\n\t"
-              "@p red.global.add.u64 [a], %3;\n\t}" ::"l"(p.hist), "r"(rel), "r"(win_n), "l"(wgt64));
+              "{\n\t.reg .pred p;\n\t.reg .u32 rel;\n\t"
+              "sub.cc.u32 rel, %2, %3;\n\t"      // position in the window; borrow <=> below it
+              "subc.u32 %0, %0, 0;\n\t"
+              "setp.lt.u32 p, rel, %4;\n\t"
+              "@p st.shared.u32 [%1], rel;\n\t"
+              "@p add.u32 %1, %1, %5;\n\t}"
+              : "+r"(nbelow), "+r"(qa)
+              : "r"(__float_as_uint(d2)), "r"(win_lo), "r"(win_n), "n"(kMedConsumers * 4)
+              : "memory");
+        }
+        for (uint32_t a = q0; a < qa; a += kMedConsumers * 4) {
+          uint32_t rel;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(a) : "memory");
+          asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p.hist + rel), "l"(wgt64) : "memory");
         }
       }
+      below += (0u - nbelow) * wgt;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -982,7 +1010,7 @@ __global__ void __launch_bounds__(1024) med_window_select_kernel(const unsigned 
 bool median_tc_supported(int N, int D) {
   const int Dp = round_up(D, 8);
   if (N % kTcBM || N < 1024 || Dp > 64) return false;
-  return med_smem_bytes(Dp) <= 227 * 1024;
+  return med_xb_stages(Dp) > 0;
 }
 size_t median_tc_workspace(int N, int D) {
   const size_t Dp = round_up(D, 8);
@@ -1003,7 +1031,8 @@ int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t s
   float* x_lo = ws;  ws += (size_t)N * Dp;
   unsigned int* hist32 = (unsigned int*)ws;
   DUST_CUDA_OK(cudaMemsetAsync(hist32, 0, sizeof(unsigned int) * 32768, stream));
-  int rc = tc_prep(a->x, nullptr, N, D, Dp, 0, x_hi, x_lo, nullptr, nullptr, xn, stream);
+  const int ld = a->ld > 0 ? a->ld : D;
+  int rc = tc_prep(a->x, nullptr, N, D, ld, Dp, 0, x_hi, x_lo, nullptr, nullptr, xn, stream);
   if (rc != DUST_OK) return rc;
   DUST_CUDA_OK(cudaFuncSetAttribute(med_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(unsigned int) * 32768)));
   {
@@ -1011,7 +1040,7 @@ int median_tc_prepare(const dust_median_args* a, void* workspace, cudaStream_t s
     const int k0 = a->sample_end > a->sample_begin ? a->sample_begin : 0;
     const int k1 = a->sample_end > a->sample_begin ? a->sample_end : kMedSample;
     const int grid = min(kMedSampleGrid, max(1, ceil_div(k1 - k0, kMedSampleThreads)));
-    med_sample_kernel<<<grid, kMedSampleThreads, sizeof(unsigned int) * 32768, stream>>>(a->x, xn, N, D, hist32, k0, k1);
+    med_sample_kernel<<<grid, kMedSampleThreads, sizeof(unsigned int) * 32768, stream>>>(a->x, xn, N, D, ld, hist32, k0, k1);
   }
   DUST_LAUNCH_OK("med_sample_kernel");
   return DUST_OK;
@@ -1048,8 +1077,9 @@ int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t str
     const double cost = (double)ceil_div((long long)row_tiles * ks, kNumSMs) * (chunk + 3.0);  // + per-CTA prologue
     if (cost < best_cost - 1e-9) { best_cost = cost; ksplit = ks; kchunk = chunk; }
   }
-  MedTcParams p{N, Dp, T, r0, ksplit, kcount, kchunk, x_hi, x_lo, x_hi, x_lo, xn, a->selected + 4, a->hist};
-  const size_t smem = med_smem_bytes(Dp);
+  const int stages = med_xb_stages(Dp);
+  MedTcParams p{N, Dp, T, r0, ksplit, stages, kcount, kchunk, x_hi, x_lo, x_hi, x_lo, xn, a->selected + 4, a->hist};
+  const size_t smem = med_smem_bytes(Dp, stages);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {
     DUST_TIMED("median_tc_kernel", stream);
@@ -1103,13 +1133,14 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   float* vb_hi = ws;           ws += (size_t)N * NV;
   float* vb_lo = ws;           ws += (size_t)N * NV;
   float* oacc = ws;
-  int rc = tc_prep(a->x, a->score, N, D, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream, a->x_prepared != 0);
+  const int ld = a->ld > 0 ? a->ld : D;
+  int rc = tc_prep(a->x, a->score, N, D, ld, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream, a->x_prepared != 0);
   if (rc != DUST_OK) return rc;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
   const int row_tiles = (r1 - r0) / kTcBM;
   if (row_tiles == 0) return DUST_OK;
   TcParams p;
-  p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0;
+  p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0; p.ld = ld;
   // a 128-row tile and a 64-row tile of the core-matrix image are both whole 8-row groups in row order:
   // ONE image serves as the A operand (row tiles) and as the B operand (column tiles)
   p.xa_hi = x_hi; p.xa_lo = x_lo; p.xb_hi = x_hi; p.xb_lo = x_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;

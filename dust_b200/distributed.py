@@ -37,9 +37,10 @@ class ShardedSVGD:
     `group` (dust/inference/svgd.py:127-135 with the bw_median bandwidth, svgd.py:42-52)."""
 
     def __init__(self, n_total, dim, group=None, ops=_ops, device=None, gather="packed"):
-        """gather: "packed" = one all-gather of [X | score] (concatenate before, slice after: the measured default);
-        "separate" = X and score gathered straight into their own contiguous [N, D] buffers (two collectives, no
-        staging copies; not yet measured on 8 GPUs)."""
+        """gather: "packed" = ONE all-gather of [X | score] into an [N, 2D] buffer that the kernels read in place through
+        a row stride (X = buffer[:, :D], score = buffer[:, D:]: no slicing copies); "separate" = X and score gathered
+        into their own [N, D] buffers by two collectives (the score gather then overlaps the bandwidth pass).
+        Measured on 8 B200 (profiles/r2_scale8.md): a collective costs ~35-40 us, more than the overlap wins."""
         if gather not in ("packed", "separate"):
             raise ValueError(gather)
         self.gather_mode = gather
@@ -84,8 +85,11 @@ class ShardedSVGD:
                 out.append(buf)
                 waits.append(work.wait)
             return out[0], out[1], waits[0], waits[1]
-        xs = self._all_gather(torch.cat([x_local, score_local], dim=1))
-        return xs[:, : self.D].contiguous(), xs[:, self.D:].contiguous(), nothing, nothing
+        local = torch.cat([x_local, score_local], dim=1)
+        if self._gathered is None or self._gathered.shape[1] != 2 * self.D or self._gathered.device != local.device:
+            self._gathered = torch.empty((self.N, 2 * self.D), dtype=local.dtype, device=local.device)
+        work = dist.all_gather_into_tensor(self._gathered, local, group=self.group, async_op=True)
+        return self._gathered[:, : self.D], self._gathered[:, self.D:], work.wait, nothing
 
     def gather(self, x_local, score_local):
         x_all, s_all, wait_x, wait_s = self.gather_async(x_local, score_local)

@@ -173,14 +173,21 @@ def svgd_phi(x, score, gamma=0.0, c1=0.0, c2=0.0, gamma_dev=None, per_dim=False,
     L.require_cuda()
     B, N, D = x.shape
     dev = x.device
-    phi = torch.empty_like(x) if want_phi else None
-    xo = torch.empty_like(x) if want_update else None
+    phi = torch.empty(x.shape, dtype=torch.float32, device=dev) if want_phi else None
+    xo = torch.empty(x.shape, dtype=torch.float32, device=dev) if want_update else None
     bws = torch.empty((B, D), dtype=torch.float32, device=dev) if (per_dim and want_bandwidths) else None
     a = L.PhiArgs()
     a.B, a.N, a.D = B, N, D
     a.row_begin, a.row_end = (0, N) if rows is None else rows
     a.per_dim = int(per_dim)
-    a.x, a.score = L.ptr(x), L.ptr(score)
+    if B == 1 and not x.is_contiguous():
+        # X and score as column slices of ONE [N, ld] buffer (the all-gathered [X | score]): no slicing copies
+        (px, ldx), (ps, lds) = L.ptr_rows(x[0]), L.ptr_rows(score[0])
+        if ldx != lds:
+            raise ValueError("dust_b200: x and score must share their row stride")
+        a.x, a.score, a.ld = px, ps, ldx
+    else:
+        a.x, a.score = L.ptr(x), L.ptr(score)
     a.gamma, a.c1, a.c2, a.gamma_dev = float(gamma), float(c1), float(c2), L.ptr(gamma_dev)
     a.bw_scale, a.lr = float(bw_scale), float(lr)
     a.phi, a.x_out, a.bandwidths = L.ptr(phi), L.ptr(xo), L.ptr(bws)
@@ -226,7 +233,11 @@ def _median_args(x, ws, rows, sample=None):
     a.N, a.D = N, D
     a.row_begin, a.row_end = (0, N) if rows is None else rows
     a.sample_begin, a.sample_end = (0, 0) if sample is None else sample
-    a.x, a.hist, a.selected, a.row_norms = L.ptr(x), ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
+    if x.is_contiguous():
+        px = L.ptr(x)
+    else:
+        px, a.ld = L.ptr_rows(x)           # a column slice of a wider buffer
+    a.x, a.hist, a.selected, a.row_norms = px, ws.hist.data_ptr(), ws.selected.data_ptr(), L.ptr(ws.row_norms)
     return a
 
 

@@ -267,6 +267,7 @@ typedef struct dust_median_args {
   float* row_norms;          /* [N] device scratch: |x_i|^2, written by pass 0, read by pass 1 */
   int32_t sample_begin, sample_end;  /* fast path: the share [begin, end) of the 2^20 sampled pairs this rank draws
                                 (0, 0: all of them); sum the sample histogram over the ranks before `window` */
+  int32_t ld;                /* row stride of x in floats (0 = D: contiguous rows) */
 } dust_median_args;
 
 int dust_median_hist_pass(const dust_median_args* args, int32_t pass, void* stream);
@@ -323,6 +324,9 @@ typedef struct dust_phi_args {
   int32_t x_prepared;        /* tensor-core path: the head of `workspace` already holds |x|^2 and the hi/lo operand images
                                 of this x -- written there by dust_median_fast_prepare on the SAME buffer (its workspace
                                 has the same head layout) -- so only the [score | x] images are prepared               */
+  int32_t ld;                /* row stride of x AND score in floats (0 = D: contiguous rows).  ld > D lets both live in
+                                one [N, ld] buffer -- e.g. the all-gathered [X | score] with score = x + D -- without
+                                slicing copies.  Tensor-core path only (other paths require ld = 0 or D)               */
 } dust_phi_args;
 
 size_t dust_phi_workspace_bytes(const dust_phi_args* args);

@@ -91,6 +91,36 @@ def test_phi_and_median_at_65536(cloud):
     assert e_blk <= 2e-6
 
 
+def test_phi_and_median_read_a_packed_buffer_in_place():
+    """X and score as column slices of ONE [N, 2D] buffer (the all-gathered [X | score] of ShardedSVGD, `ld` in the
+    ABI): the median, the bandwidth and the phi rows are bit-identical to the contiguous call (same launches, same
+    partition -- only the addresses the prepare kernels read differ).  svgd.py:42-52, 127-135."""
+    from dust_b200 import ops
+
+    N, D = 4096, 40
+    g = torch.Generator().manual_seed(5)
+    X, S = torch.randn(N, D, generator=g), torch.randn(N, D, generator=g)
+    packed = cu(torch.cat([X, S], dim=1))
+    xs, ss = packed[:, :D], packed[:, D:]
+    assert not xs.is_contiguous()
+    x, s = cu(X), cu(S)
+    ws_a, ws_b = ops.MedianWorkspace(N, D, x.device), ops.MedianWorkspace(N, D, x.device)
+    med_a, med_b = ops.median_sq_dist(x, ws=ws_a), ops.median_sq_dist(xs, ws=ws_b)
+    assert int(ws_a.selected[5]) == 1 and int(ws_b.selected[5]) == 1
+    assert torch.equal(med_a, med_b)
+    coef = ops.bandwidth_from_median(med_a, N, 1.0, 0)
+    for rows in (None, (1024, 1536)):
+        a = ops.svgd_phi(x.unsqueeze(0), s.unsqueeze(0), gamma_dev=coef, rows=rows, want_update=True, lr=0.5)
+        b = ops.svgd_phi(xs.unsqueeze(0), ss.unsqueeze(0), gamma_dev=coef, rows=rows, want_update=True, lr=0.5)
+        r0, r1 = rows or (0, N)
+        assert torch.equal(a["phi"][0, r0:r1], b["phi"][0, r0:r1])
+        assert torch.equal(a["x_out"][0, r0:r1], b["x_out"][0, r0:r1])
+        assert b["phi"].is_contiguous() and b["x_out"].is_contiguous()
+    # the paths without a row stride say so instead of reading the wrong rows
+    with pytest.raises(Exception):
+        ops.svgd_phi(xs[:256].unsqueeze(0), ss[:256].unsqueeze(0), gamma=0.5, c1=1.0, c2=1.0)
+
+
 # ---------------------------------------------------------------------------------------------
 # non-SGD optimisers and fast_pred=False through the SVMPC class, on the device
 # ---------------------------------------------------------------------------------------------
