@@ -119,6 +119,7 @@ SYMBOLS = {
     "dust_rollout_cost": (C.c_int, [C.POINTER(RolloutArgs), _p]),
     "dust_rollout_plan": (C.c_int, [C.POINTER(RolloutArgs), C.POINTER(_i * 5)]),
     "dust_cost_reduce": (C.c_int, [C.POINTER(RolloutArgs), _p]),
+    "dust_phi_tc_plan": (C.c_int, [_i, _i, C.POINTER(_i * 22)]),
     "dust_svmpc_step": (C.c_int, [C.POINTER(SvmpcStepArgs), _p]),
     "dust_adjoint_workspace_bytes": (_sz, [C.POINTER(AdjointArgs)]),
     "dust_rollout_adjoint": (C.c_int, [C.POINTER(AdjointArgs), _p]),

@@ -9,8 +9,8 @@
 // At most one CTA per SM, resident for the whole launch; it works off an equal contiguous range of
 // (128-row tile, 64-column tile) pairs, segment by segment when the range crosses row tiles.  16 warps:
 //   warp 0      producer   cp.async.bulk (1-D TMA) of pre-tiled hi/lo operand images into smem rings
-//   warp 1      MMA issuer one thread: GEMM1(j) -> S[j%3]; GEMM2(j-2): O += P(j-2) V_{j-2}  (two tiles behind)
-//   warp 2      TMEM allocation
+//   warp 1      GEMM1 issuer (one elected thread): S[j % 2] = X_i X_j^T as soon as GEMM2(j-2) has consumed that buffer
+//   warp 2      TMEM allocation, then GEMM2 issuer: O += P(j) V_j as soon as the softmax warps have written P(j)
 //   warp 3      producer of the V^T tiles
 //   warps 4-7   "softmax" warpgroup A: columns 0..31 of every tile  (tcgen05.ld S, exp, split, tcgen05.st P)
 //   warps 8-11  "softmax" warpgroup B: columns 32..63 of every tile
@@ -19,11 +19,15 @@
 //               measured bias ~2e-8 per accumulation step, i.e. 5e-4 over the 24576 steps of
 //               N = 65536 if left in TMEM) and added to the segment's slot of a global scratch;
 //               phi_tc_finish_kernel sums the slots of a row tile and forms the phi rows.
-// TMEM columns (512 allocated): S/P_hi[3] 0..191 (P_hi overwrites the S it was computed from),
-// P_lo[2] 192..319, O[2] 320..320+2*NV (NV <= 96).
+// TMEM columns (512 allocated): S/P_hi ring (P_hi overwrites the S it was computed from), P_lo[2], O[2] (2*NV columns)
+// and -- when 2*NV + 2*Dp <= 256 (d <= 40) -- the row tile itself, A_hi | A_lo (2*Dp columns): every MMA then reads
+// only its B operand from shared memory.  An SS-form 128x64x8 TF32 MMA fetches 6 KB of operands in its 32 cycles,
+// more than the 128 B/cycle the shared-memory port delivers (profiles/r2_phi_a_in_tmem.md).
 // Operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8x16B core
 // matrices); the prep kernel writes global memory already in that order, so every tile is one
 // contiguous bulk copy.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace dust {
@@ -40,10 +44,17 @@ constexpr int kXnStages = 16;     // |x_j|^2 ring of the median kernel
 struct TcParams {
   int N, D, Dp, NV, T, row_begin;
   int ld;   // row stride of x (floats)
-  // The (row tile, column tile) pairs of a call are numbered row-major, u = rt * T + j, and cut into equal
-  // contiguous ranges: CTA c owns units [c * units_per_cta, (c + 1) * units_per_cta).  A range that crosses
-  // a row-tile boundary is worked off as consecutive SEGMENTS (one per row tile), each with its own slot
-  // of the scratch; every SM carries the same number of tile pairs whatever row block a rank owns.
+  int a_tmem;  // 1: the row tile (A operand of GEMM1, hi and lo) lives in TMEM, written by the flush warps (TS form)
+  // Partition of the (row tile, column tile) pairs of a launch over its CTAs (at most one per SM):
+  //  * the first n_chunks * R CTAs (R = row tiles of the launch) each own ONE segment: CTA c = k * R + rt takes row
+  //    tile rt and the column chunk [k * chunk_w, min((k + 1) * chunk_w, T)).  All CTAs of a chunk start at the same
+  //    column tile and sweep the operand images together (a tile fetched by one is an L2 hit for the others);
+  //  * the columns [rem0, T) that the chunks leave over (rem_w of them per row tile) are numbered row-major,
+  //    u = rt * rem_w + (j - rem0), and cut into equal contiguous ranges of units_per_cta: CTA n_chunks * R + c' owns
+  //    [c' * units_per_cta, (c' + 1) * units_per_cta).  A range that crosses a row-tile boundary is worked off as
+  //    consecutive SEGMENTS (one per row tile), each with its own slot of the scratch.
+  // n_chunks = 0, rem0 = 0: plain row-major ranges (whole row tiles per CTA when units_per_cta = k * T).
+  int R, n_chunks, chunk_w, rem0, rem_w;
   int units_per_cta, total_units, max_seg;
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *vb_hi, *vb_lo, *xn, *x;
   float gamma, c1, c2;
@@ -251,6 +262,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -280,7 +296,7 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
   s.vb_stage_bytes = 2 * s.vb_half + kTcBN * 4;  // hi, lo, |x_j|^2
   s.vb = off; off += kVbStages * s.vb_stage_bytes;
   off = (off + 7) & ~7u;
-  s.bars = off; off += 32 * 8;
+  s.bars = off; off += 40 * 8;
   s.tmem_slot = off; off += 16;
   s.total = off;
   return s;
@@ -293,26 +309,38 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
                                  // (5.43 vs 5.04 ms at N = 65536, profiles/r2_phi_sbufs_ab.md) -- kept as a build option
 #endif
 constexpr int kSBufs = DUST_TC_SBUFS;
-constexpr int kLag = kSBufs - 1;  // tiles GEMM2 runs behind GEMM1
 enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 13, BAR_S_FULL = 17, BAR_P_FULL = 20,
-       BAR_P_EMPTY = 23, BAR_O_FULL = 25, BAR_O_EMPTY = 27, BAR_A_EMPTY = 29 };
+       BAR_P_EMPTY = 23, BAR_O_FULL = 25, BAR_O_EMPTY = 27, BAR_A_EMPTY = 29, BAR_S_EMPTY = 30, BAR_COUNT = 33 };
 
 // the segments of a CTA's unit range: `for (TcSegIter s(p); s.valid(); s.next())` gives row tile s.rt,
 // first column tile s.j0 and tile count s.len of segment s.seg
 struct TcSegIter {
-  int u, u1, T, seg, rt, j0, len;
-  __device__ __forceinline__ explicit TcSegIter(const TcParams& p) : T(p.T), seg(0) {
-    u = blockIdx.x * p.units_per_cta;
-    u1 = min(u + p.units_per_cta, p.total_units);
-    split();
+  int u, u1, W, j_off, seg, rt, j0, len;
+  __device__ __forceinline__ explicit TcSegIter(const TcParams& p) : seg(0) {
+    const int c = blockIdx.x - p.n_chunks * p.R;
+    if (c < 0) {                       // one (row tile, column chunk) segment
+      const int k = blockIdx.x / p.R;
+      rt = blockIdx.x - k * p.R;
+      j0 = k * p.chunk_w;
+      len = min(p.chunk_w, p.T - j0);
+      u = 0; u1 = len; W = 0; j_off = 0;
+    } else {                           // a contiguous range of the row-major numbered remainder columns
+      W = p.rem_w; j_off = p.rem0;
+      u = c * p.units_per_cta;
+      u1 = min(u + p.units_per_cta, p.total_units);
+      split();
+    }
   }
   __device__ __forceinline__ void split() {
-    rt = u / T;
-    j0 = u - rt * T;
-    len = min(T - j0, u1 - u);
+    rt = u / W;
+    j0 = j_off + (u - rt * W);
+    len = min(W - (j0 - j_off), u1 - u);
   }
   __device__ __forceinline__ bool valid() const { return u < u1; }
-  __device__ __forceinline__ void next() { u += len; ++seg; split(); }
+  __device__ __forceinline__ void next() {
+    u += len; ++seg;
+    if (W > 0 && u < u1) split();
+  }
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p) {
@@ -320,17 +348,20 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   const TcSmem L = tc_smem_layout(p.Dp, p.NV);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // the warp index as a value the compiler knows to be warp-uniform: the role branches below become uniform
+  // branches and the MMA issuer's loop state (ring indices, descriptors, TMEM addresses) stays in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const size_t slot_stride = (size_t)(p.NV + 2) * kTcBM;
   float* const oacc_cta = p.oacc + (size_t)blockIdx.x * p.max_seg * slot_stride;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[BAR_A], 1);
+    mbar_init(&bars[BAR_A], p.a_tmem ? 4 : 1);   // TMEM: one arrival per flush warp; shared memory: the TMA transaction
     mbar_init(&bars[BAR_A_EMPTY], 1);
     for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[BAR_XB_FULL + s], 1); mbar_init(&bars[BAR_XB_EMPTY + s], 1); }
     for (int s = 0; s < kVbStages; ++s) { mbar_init(&bars[BAR_VB_FULL + s], 1); mbar_init(&bars[BAR_VB_EMPTY + s], 1); }
     for (int b = 0; b < kSBufs; ++b) {
       mbar_init(&bars[BAR_S_FULL + b], 1);
+      mbar_init(&bars[BAR_S_EMPTY + b], 1);
       mbar_init(&bars[BAR_P_FULL + b], 8);   // one arrival per softmax warp (both groups work on every tile)
     }
     for (int b = 0; b < 2; ++b) mbar_init(&bars[BAR_P_EMPTY + b], 1);   // P_lo ring
@@ -348,8 +379,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + kSBufs * kTcBN, tO = tPlo + 2 * kTcBN;   // 192 + 128 + 2 NV <= 512
+  const uint32_t tAhi = tO + 2 * p.NV, tAlo = tAhi + p.Dp;                                       // a_tmem only
   // Ring stages, S/P buffers and O buffers are indexed by counters that run on ACROSS segments
   // (g: tiles, cg: flushed chunks), so the pipelines never drain at a row-tile boundary; only the
   // A operand (the row tile itself) is exchanged there.
@@ -360,12 +392,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       const uint32_t a_bytes = kTcBM * p.Dp * 4;
       int g = 0;
       for (TcSegIter s(p); s.valid(); s.next()) {
-        // the GEMM1s of the previous segment must have retired before their A operand is overwritten
-        if (s.seg > 0) mbar_wait(&bars[BAR_A_EMPTY], (s.seg - 1) & 1);
-        const long long arow = (long long)(p.row_begin / kTcBM + s.rt) * kTcBM * p.Dp;
-        mbar_expect_tx(&bars[BAR_A], 2 * a_bytes);
-        bulk_g2s(smem + L.a_hi, p.xa_hi + arow, a_bytes, &bars[BAR_A]);
-        bulk_g2s(smem + L.a_lo, p.xa_lo + arow, a_bytes, &bars[BAR_A]);
+        if (!p.a_tmem) {
+          // the GEMM1s of the previous segment must have retired before their A operand is overwritten
+          if (s.seg > 0) mbar_wait(&bars[BAR_A_EMPTY], (s.seg - 1) & 1);
+          const long long arow = (long long)(p.row_begin / kTcBM + s.rt) * kTcBM * p.Dp;
+          mbar_expect_tx(&bars[BAR_A], 2 * a_bytes);
+          bulk_g2s(smem + L.a_hi, p.xa_hi + arow, a_bytes, &bars[BAR_A]);
+          bulk_g2s(smem + L.a_lo, p.xa_lo + arow, a_bytes, &bars[BAR_A]);
+        }
         for (int j = 0; j < s.len; ++j, ++g) {
           const int sx = g % kXbStages;
           mbar_wait(&bars[BAR_XB_EMPTY + sx], ((g / kXbStages) & 1) ^ 1);
@@ -393,35 +427,80 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer ----------------------------------------
-    // the whole warp runs the loop converged (waits included); one elected lane issues
-    {
-      const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
-      const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV);
-      const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;     // 8-row group stride of the X tiles
-      const uint32_t sbo2 = (uint32_t)(kTcBN / 4) * 128u;    // ... of the V^T tiles
-      const int ks1 = p.Dp / 8;
-      constexpr int ks2 = kTcBN / 8;
-      // The issuing thread is a single warp: every integer op on the way to an MMA costs ~5 cycles.
-      // Descriptors are therefore built once; per MMA only the low word (start address >> 4) moves.
-      const uint64_t dA = make_desc(smem_u32(smem + L.a_hi), 128, sbo1), dX = make_desc(smem_u32(smem + L.xb), 128, sbo1);
-      const uint64_t dV = make_desc(smem_u32(smem + L.vb), 128, sbo2);
-      const uint32_t hiA = (uint32_t)(dA >> 32), hiV = (uint32_t)(dV >> 32);
-      const uint32_t loA_hi = (uint32_t)dA, loA_lo = loA_hi + ((kTcBM * p.Dp * 4) >> 4);
-      const uint32_t loX0 = (uint32_t)dX, loV0 = (uint32_t)dV;
-      const uint32_t xb_stage16 = L.xb_stage_bytes >> 4, xb_half16 = L.xb_half >> 4;
-      const uint32_t vb_stage16 = L.vb_stage_bytes >> 4, vb_half16 = L.vb_half >> 4;
-      // GEMM2 of running tile g: O[ch & 1] (+)= P[g & 1] V_g; first / last tile of flush chunk ch
-      auto gemm2 = [&](int g, int ch, bool first, bool last) {
-        const int b = g & 1, b3 = g % kSBufs, sv = g % kVbStages;
+    // ------------------------------ GEMM1 issuer --------------------------------------
+    // Two issuing warps, one per GEMM: a single warp spent ~2500 cycles per tile on its ~290 instructions (descriptor
+    // moves, waits, commits; ncu: the issuer never waited for P, the softmax warps waited for S) against 1440 cycles of
+    // tensor-pipe work.  Every dependency between the two GEMMs is an mbarrier (S_EMPTY, P_FULL, P_EMPTY), none relies
+    // on issue order.  The whole warp runs the loop converged (waits included); one elected lane issues.
+    const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
+    const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;     // 8-row group stride of the X tiles
+    const int ks1 = p.Dp / 8;
+    // Every integer op on the way to an MMA costs the issuing warp ~5 cycles: descriptors are built once, per MMA
+    // only the low word (start address >> 4) moves.
+    const uint64_t dA = make_desc(smem_u32(smem + L.a_hi), 128, sbo1), dX = make_desc(smem_u32(smem + L.xb), 128, sbo1);
+    const uint32_t hiA = (uint32_t)(dA >> 32);
+    const uint32_t loA_hi = (uint32_t)dA, loA_lo = loA_hi + ((kTcBM * p.Dp * 4) >> 4);
+    const uint32_t loX0 = (uint32_t)dX;
+    const uint32_t xb_stage16 = L.xb_stage_bytes >> 4, xb_half16 = L.xb_half >> 4;
+    int g = 0;                               // running tile counter
+    for (TcSegIter s(p); s.valid(); s.next()) {
+      mbar_wait(&bars[BAR_A], s.seg & 1);
+      for (int j = 0; j < s.len; ++j, ++g) {
+        const int b = g % kSBufs, sx = g % kXbStages;
+        mbar_wait(&bars[BAR_XB_FULL + sx], (g / kXbStages) & 1);
+        mbar_wait(&bars[BAR_S_EMPTY + b], ((g / kSBufs) & 1) ^ 1);   // GEMM2(g - kSBufs) has consumed the P_hi in this buffer
+        tc_fence_after();
+        const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
+        const uint32_t tSb = tS + b * kTcBN;
+        if (elect_one_sync()) {
+          if (p.a_tmem) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              if (kk < ks1) {
+                const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+                mma_ts(tSb, tAhi + kk * 8, bh, idesc1, kk > 0 ? 1u : 0u);
+                mma_ts(tSb, tAhi + kk * 8, bl, idesc1, 1u);
+                mma_ts(tSb, tAlo + kk * 8, bh, idesc1, 1u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              if (kk < ks1) {
+                const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
+                const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
+                mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
+                mma_ss(tSb, ah, bl, idesc1, 1u);
+                mma_ss(tSb, al, bh, idesc1, 1u);
+              }
+            }
+          }
+          tc_commit(&bars[BAR_S_FULL + b]);
+          tc_commit(&bars[BAR_XB_EMPTY + sx]);
+          if (j == s.len - 1) tc_commit(&bars[BAR_A_EMPTY]);   // last reader of this segment's A operand
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 2) {
+    // ------------------------------ GEMM2 issuer (after the TMEM allocation above) ------
+    // O[chunk & 1] (+)= P[g] V_g, tile by tile; first / last tile of a flush chunk open / close an O buffer
+    const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV);
+    const uint32_t sbo2 = (uint32_t)(kTcBN / 4) * 128u;    // 8-row group stride of the V^T tiles
+    constexpr int ks2 = kTcBN / 8;
+    const uint64_t dV = make_desc(smem_u32(smem + L.vb), 128, sbo2);
+    const uint32_t hiV = (uint32_t)(dV >> 32), loV0 = (uint32_t)dV;
+    const uint32_t vb_stage16 = L.vb_stage_bytes >> 4, vb_half16 = L.vb_half >> 4;
+    int g = 0, cg = 0;                       // running tile / chunk counters
+    for (TcSegIter s(p); s.valid(); s.next()) {
+      for (int j = 0; j < s.len; ++j, ++g) {
+        const bool first = (j % kTcChunk) == 0;
+        const bool last = (j % kTcChunk) == kTcChunk - 1 || j == s.len - 1;
+        const int b = g & 1, b3 = g % kSBufs, sv = g % kVbStages, ob = cg & 1;
         mbar_wait(&bars[BAR_VB_FULL + sv], (g / kVbStages) & 1);
+        if (first) mbar_wait(&bars[BAR_O_EMPTY + ob], ((cg >> 1) & 1) ^ 1);   // the flush warps drained this O buffer (two chunks ago)
         mbar_wait(&bars[BAR_P_FULL + b3], (g / kSBufs) & 1);
         tc_fence_after();
-        const int ob = ch & 1;
-        if (first) {  // the flush warps must have drained this O buffer (two chunks ago)
-          mbar_wait(&bars[BAR_O_EMPTY + ob], ((ch >> 1) & 1) ^ 1);
-          tc_fence_after();
-        }
         const uint32_t tOb = tO + ob * p.NV;
         const uint32_t vh = loV0 + sv * vb_stage16, vl = vh + vb_half16;
         const uint32_t ph = tPhi + b3 * kTcBN, pl = tPlo + b * kTcBN;
@@ -433,51 +512,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
             mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
             mma_ts(tOb, pl + kk * 8, bh, idesc2, 1u);
           }
+          tc_commit(&bars[BAR_S_EMPTY + b3]);
           tc_commit(&bars[BAR_P_EMPTY + b]);
           tc_commit(&bars[BAR_VB_EMPTY + sv]);
           if (last) tc_commit(&bars[BAR_O_FULL + ob]);
         }
         __syncwarp();
-      };
-      int g = 0, cg = 0;                       // running tile / chunk counters
-      // GEMM2 runs kLag tiles behind GEMM1: flush-chunk info of the tiles in between (slot = tile % kLag)
-      int pch[2] = {0, 0};
-      bool pfirst[2] = {false, false}, plast[2] = {false, false};
-      for (TcSegIter s(p); s.valid(); s.next()) {
-        mbar_wait(&bars[BAR_A], s.seg & 1);
-        for (int j = 0; j < s.len; ++j, ++g) {
-          const int b = g % kSBufs, sx = g % kXbStages;
-          mbar_wait(&bars[BAR_XB_FULL + sx], (g / kXbStages) & 1);
-          tc_fence_after();
-          const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
-          const uint32_t tSb = tS + b * kTcBN;
-          if (elect_one_sync()) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              if (kk < ks1) {
-                const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
-                const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
-                mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
-                mma_ss(tSb, ah, bl, idesc1, 1u);
-                mma_ss(tSb, al, bh, idesc1, 1u);
-              }
-            }
-            tc_commit(&bars[BAR_S_FULL + b]);
-            tc_commit(&bars[BAR_XB_EMPTY + sx]);
-            if (j == s.len - 1) tc_commit(&bars[BAR_A_EMPTY]);   // last reader of this segment's A operand
-          }
-          __syncwarp();
-          const int q = g % kLag;
-          if (g >= kLag) gemm2(g - kLag, pch[q], pfirst[q], plast[q]);
-          pch[q] = cg;
-          pfirst[q] = (j % kTcChunk) == 0;
-          plast[q] = (j % kTcChunk) == kTcChunk - 1 || j == s.len - 1;
-          if (plast[q]) ++cg;
-        }
+        if (last) ++cg;
       }
-#pragma unroll
-      for (int l = kLag; l >= 1; --l)
-        if (g >= l) gemm2(g - l, pch[(g - l) % kLag], pfirst[(g - l) % kLag], plast[(g - l) % kLag]);
     }
   } else if (warp >= 4 && warp < 12) {
     // ------------------------------ softmax warpgroups ---------------------------------
@@ -543,10 +585,53 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
     // running sums live in a per-segment global scratch, column-major ([NV][128]: a warp touches 128
     // contiguous bytes per column); only 16 columns are in registers at any time
     int cg = 0;
+    // a_tmem: this warpgroup also stages the row tile of a segment in TMEM (thread <-> row: hi / lo split of its Dp
+    // values, the same bits tc_prep_kernel writes into the images).  seg > 0: once the previous segment's last GEMM1
+    // has retired (BAR_A_EMPTY) -- which does not depend on the chunk drained below, so it goes first
+    auto stage_a = [&](int seg, int rt) {
+      const float* __restrict__ xr = p.x + (long long)(p.row_begin + rt * kTcBM + row) * p.ld;
+      const bool vec = (p.D & 3) == 0 && (p.ld & 3) == 0 && ((((uintptr_t)p.x) & 15) == 0);
+      if (seg > 0) {
+        mbar_wait(&bars[BAR_A_EMPTY], (seg - 1) & 1);
+        tc_fence_after();
+      }
+      for (int k0 = 0; k0 < p.Dp; k0 += 8) {
+        float v[8];
+        if (vec && k0 + 8 <= p.D) {
+          const float4 q0 = __ldg(reinterpret_cast<const float4*>(xr + k0)), q1 = __ldg(reinterpret_cast<const float4*>(xr + k0 + 4));
+          v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w; v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = (k0 + c < p.D) ? __ldg(xr + k0 + c) : 0.f;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float h = tf32_hi(v[c]);
+          hi[c] = __float_as_uint(h);
+          lo[c] = __float_as_uint(tf32_lo(v[c], h));
+        }
+        tmem_st8(tAhi + lane_base + k0, hi);
+        tmem_st8(tAlo + lane_base + k0, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[BAR_A]);
+    };
+    if (p.a_tmem) {
+      TcSegIter s0(p);
+      if (s0.valid()) stage_a(0, s0.rt);
+    }
     for (TcSegIter s(p); s.valid(); s.next()) {
       float* og = oacc_cta + (size_t)s.seg * slot_stride + row;
       const int n_chunks = (s.len + kTcChunk - 1) / kTcChunk;
       for (int ch = 0; ch < n_chunks; ++ch, ++cg) {
+        if (p.a_tmem && ch == n_chunks - 1) {
+          TcSegIter nx = s;
+          nx.next();
+          if (nx.valid()) stage_a(nx.seg, nx.rt);
+        }
         const int ob = cg & 1;
         mbar_wait(&bars[BAR_O_FULL + ob], (cg >> 1) & 1);
         tc_fence_after();
@@ -582,20 +667,28 @@ __global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) 
   float c1 = p.c1, c2 = p.c2;
   if (p.gamma_dev) { c1 = p.gamma_dev[1]; c2 = p.gamma_dev[2]; }
   const size_t slot_stride = (size_t)(p.NV + 2) * kTcBM;
-  const long long W = p.units_per_cta, T = p.T;
-  const int c_first = (int)((rt * T) / W), c_last = (int)(((rt + 1) * T - 1) / W);
-  // slot of CTA c's segment on row tile rt: its segments start at row tile (c * W) / T
-  auto slot = [&](int c) { return p.oacc + ((size_t)c * p.max_seg + (size_t)(rt - (c * W) / T)) * slot_stride + row; };
+  // the segments that worked on row tile rt, in a fixed order: the chunk CTAs k * R + rt (slot 0 each), then the
+  // remainder CTAs c' whose range meets [rt * rem_w, (rt + 1) * rem_w) (slot = rt - first row tile of c')
+  const long long W = p.units_per_cta, Tw = p.rem_w;
+  const int nc = p.n_chunks, cbase = p.n_chunks * p.R;
+  int c_first = 0, c_last = -1;
+  if (Tw > 0) { c_first = (int)((rt * Tw) / W); c_last = (int)(((rt + 1) * Tw - 1) / W); }
+  const int n_src = nc + (c_last - c_first + 1);
+  auto slot = [&](int i) {
+    if (i < nc) return p.oacc + (size_t)(i * p.R + rt) * p.max_seg * slot_stride + row;
+    const int c = c_first + (i - nc);
+    return p.oacc + ((size_t)(cbase + c) * p.max_seg + (size_t)(rt - (c * W) / Tw)) * slot_stride + row;
+  };
   float ksum = 0.f;
-  for (int c = c_first; c <= c_last; ++c) {
-    const float* og = slot(c);
+  for (int i = 0; i < n_src; ++i) {
+    const float* og = slot(i);
     ksum += og[(size_t)p.NV * kTcBM] + og[(size_t)(p.NV + 1) * kTcBM];
   }
   const int d0 = blockIdx.y * 8, d1 = min(d0 + 8, p.D);
   for (int d = d0; d < d1; ++d) {
     float ks = 0.f, kx = 0.f;  // sum_j K s_j, sum_j K x_j
-    for (int c = c_first; c <= c_last; ++c) {
-      const float* og = slot(c);
+    for (int i = 0; i < n_src; ++i) {
+      const float* og = slot(i);
       ks += og[(size_t)d * kTcBM];
       kx += og[(size_t)(p.D + d) * kTcBM];
     }
@@ -606,32 +699,57 @@ __global__ void __launch_bounds__(kTcBM) phi_tc_finish_kernel(const TcParams p) 
   }
 }
 
-// equal contiguous unit ranges over at most one CTA per SM; a floor on the range length keeps the
-// per-CTA prologue (TMEM allocation, A operand, pipeline fill, O drain: ~5 tile times) amortised
-struct TcPlan { int grid, units_per_cta, total_units, max_seg, row_tile0, row_tiles; };
-static TcPlan tc_plan(int row_tiles, int T) {
-  TcPlan pl;
-  pl.row_tile0 = 0; pl.row_tiles = row_tiles;
-  pl.total_units = row_tiles * T;
-  const int floor_units = T < 16 ? T : 16;
-  int W = ceil_div(pl.total_units, kNumSMs);
-  if (W < floor_units) W = floor_units;
-  pl.units_per_cta = W;
-  pl.grid = ceil_div(pl.total_units, W);
-  pl.max_seg = (W + T - 2) / T + 1;
+// Partition of one launch (see TcParams).  A floor on the range length keeps the per-CTA prologue (TMEM allocation,
+// A operand, pipeline fill, O drain: ~5 tile times) amortised.
+struct TcPlan { int grid, R, n_chunks, chunk_w, rem0, rem_w, units_per_cta, total_units, max_seg, row_tile0, row_tiles; };
+constexpr int kSegOverhead = 3;   // tile times a further segment costs its CTA (A exchange, O drain, scratch slot)
+
+// fewer row tiles than SMs: R * T units over up to 148 CTAs
+static TcPlan tc_plan(int R, int T) {
+  TcPlan pl{};
+  pl.row_tile0 = 0; pl.row_tiles = R; pl.R = R;
+  const long long units = (long long)R * T;
+  int W = (int)ceil_div(units, (long long)kNumSMs);
+  if (W < 16) {                       // little work: plain row-major ranges of at least 16 units
+    W = T < 16 ? T : 16;
+    pl.n_chunks = 0; pl.chunk_w = 0; pl.rem0 = 0; pl.rem_w = T;
+    pl.units_per_cta = W; pl.total_units = (int)units;
+    pl.grid = ceil_div(pl.total_units, W);
+    pl.max_seg = (W + T - 2) / T + 1;
+    return pl;
+  }
+  // (A) chunks of exactly W columns + the left-over columns as row-major ranges of W units;  (B) floor(148 / R) chunks
+  // that cover all T columns, some SMs idle.  The cheaper one by the longest CTA (+ segment overheads) is taken.
+  const int nfA = T / W, remA = T - nfA * W;
+  const int segA = remA > 0 ? (W + remA - 2) / remA + 1 : 1;
+  const long long costA = W + (long long)kSegOverhead * (segA - 1);
+  const int nfB = kNumSMs / R, wB = ceil_div(T, nfB);
+  if (costA <= wB) {
+    pl.n_chunks = nfA; pl.chunk_w = W; pl.rem0 = nfA * W; pl.rem_w = remA;
+    pl.units_per_cta = W; pl.total_units = R * remA;
+    pl.grid = nfA * R + ceil_div(pl.total_units, W);
+    pl.max_seg = segA;
+  } else {
+    pl.n_chunks = ceil_div(T, wB); pl.chunk_w = wB; pl.rem0 = T; pl.rem_w = 0;
+    pl.units_per_cta = wB; pl.total_units = 0;
+    pl.grid = pl.n_chunks * R;
+    pl.max_seg = 1;
+  }
   return pl;
 }
 // A call is cut into at most two launches.  First k = row_tiles / 148 WHOLE row tiles per SM: every CTA
 // starts at column tile 0 and they sweep the column images together, so a tile fetched from HBM by one
 // CTA is an L2 hit for the other 147 (with ranges that start at scattered column phases the 63 MB of
 // operand images are streamed by every CTA on its own schedule and no longer stay resident: 2.1 GB of
-// DRAM reads per launch instead of ~0.4).  Then the remaining row tiles, as equal unit ranges.
+// DRAM reads per launch instead of ~0.4).  Then the remaining row tiles, in column chunks (tc_plan).
 static int tc_launch_plans(int row_tiles, int T, TcPlan out[2]) {
   int n = 0;
   const int k = row_tiles / kNumSMs;
   if (k >= 1) {
     TcPlan& a = out[n++];
-    a.row_tile0 = 0; a.row_tiles = k * kNumSMs;
+    a = TcPlan{};
+    a.row_tile0 = 0; a.row_tiles = k * kNumSMs; a.R = a.row_tiles;
+    a.n_chunks = 0; a.chunk_w = 0; a.rem0 = 0; a.rem_w = T;
     a.total_units = a.row_tiles * T; a.units_per_cta = k * T; a.grid = kNumSMs; a.max_seg = k;
   }
   const int rest = row_tiles - k * kNumSMs;
@@ -915,7 +1033,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       const int cdiag = (col_tile(j) == jdiag) ? ((i0 + row) & (kTcBN - 1)) : -1;
       const uint32_t wgt = (kb == 0 || 2 * kb == Tb) ? 1u : 2u;
       const unsigned long long wgt64 = wgt;
-      uint32_t nbelow = 0;                 // minus the number of values below the window in this tile
+      uint32_t nbelow = 0;                 // number of values below the window in this tile
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
         uint32_t r[32];
@@ -926,33 +1044,46 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
           for (int c = 0; c < 32; ++c)
             if (half * 32 + c == cdiag) r[c] = __float_as_uint(0.5f * (xnj[half * 32 + c] + xn_i));  // => d2 = 0
         }
-        // Per distance: d2, its position relative to the window (the borrow of the subtraction counts the values
-        // below it), and -- for the ~3 % inside the window -- a predicated store of that position into the thread's
-        // queue.  The 64-bit histogram updates (address arithmetic, descriptor, reduction) run afterwards, for the
-        // hits only: per-element predicated `red.global` compiled to a branch + descriptor moves around EVERY element.
+        // Per distance: d2 (two at a time on the packed FP32 pipe, each lane rounded like the scalar fmaf / add), its
+        // position relative to the window (rel; bit 31 <=> below it, both bit patterns being < 2^31: one IMAD.HI adds
+        // it to one of four independent counters), and -- for the ~3 % inside the window -- a predicated store of rel
+        // into the thread's queue.  The 64-bit histogram updates (address arithmetic, descriptor, reduction) run
+        // afterwards, for the hits only: per-element predicated `red.global` compiled to a branch + descriptor moves
+        // around EVERY element, and the earlier carry-chain form (sub.cc / subc) serialised the 32 elements.
         uint32_t qa = q0;
+        uint32_t nb[4] = {0u, 0u, 0u, 0u};
+        const float4* __restrict__ xq = reinterpret_cast<const float4*>(xnj + half * 32);
+        const float2 m2 = make_float2(-2.0f, -2.0f), xi2 = make_float2(xn_i, xn_i);
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float s = __uint_as_float(r[c]);
-          const float d2 = fmaxf(fmaf(-2.0f, s, xnj[half * 32 + c]) + xn_i, 0.f);   // 2s is exact: same value as (x_j - 2s) + x_i
-          asm volatile(
-              "{\n\t.reg .pred p;\n\t.reg .u32 rel;\n\t"
-              "sub.cc.u32 rel, %2, %3;\n\t"      // position in the window; borrow <=> below it
-              "subc.u32 %0, %0, 0;\n\t"
-              "setp.lt.u32 p, rel, %4;\n\t"
-              "@p st.shared.u32 [%1], rel;\n\t"
-              "@p add.u32 %1, %1, %5;\n\t}"
-              : "+r"(nbelow), "+r"(qa)
-              : "r"(__float_as_uint(d2)), "r"(win_lo), "r"(win_n), "n"(kMedConsumers * 4)
-              : "memory");
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 xv = xq[c4];
+          const float2 s01 = make_float2(__uint_as_float(r[4 * c4]), __uint_as_float(r[4 * c4 + 1]));
+          const float2 s23 = make_float2(__uint_as_float(r[4 * c4 + 2]), __uint_as_float(r[4 * c4 + 3]));
+          const float2 e01 = __fadd2_rn(__ffma2_rn(m2, s01, make_float2(xv.x, xv.y)), xi2);   // (x_j - 2s) + x_i, 2s exact
+          const float2 e23 = __fadd2_rn(__ffma2_rn(m2, s23, make_float2(xv.z, xv.w)), xi2);
+          const float d2v[4] = {fmaxf(e01.x, 0.f), fmaxf(e01.y, 0.f), fmaxf(e23.x, 0.f), fmaxf(e23.y, 0.f)};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t rel = __float_as_uint(d2v[k]) - win_lo;
+            nb[k] = __umulhi(rel, 2u) + nb[k];
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.lt.u32 p, %1, %2;\n\t"
+                "@p st.shared.u32 [%0], %1;\n\t"
+                "@p add.u32 %0, %0, %3;\n\t}"
+                : "+r"(qa)
+                : "r"(rel), "r"(win_n), "n"(kMedConsumers * 4)
+                : "memory");
+          }
         }
+        nbelow += (nb[0] + nb[1]) + (nb[2] + nb[3]);
         for (uint32_t a = q0; a < qa; a += kMedConsumers * 4) {
           uint32_t rel;
           asm volatile("ld.shared.u32 %0, [%1];" : "=r"(rel) : "r"(a) : "memory");
           asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p.hist + rel), "l"(wgt64) : "memory");
         }
       }
-      below += (0u - nbelow) * wgt;
+      below += nbelow * wgt;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -1141,6 +1272,7 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   if (row_tiles == 0) return DUST_OK;
   TcParams p;
   p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0; p.ld = ld;
+  p.a_tmem = ((kSBufs + 2) * kTcBN + 2 * NV + 2 * Dp <= 512 && !getenv("DUST_B200_TC_A_SMEM")) ? 1 : 0;
   // a 128-row tile and a 64-row tile of the core-matrix image are both whole 8-row groups in row order:
   // ONE image serves as the A operand (row tiles) and as the B operand (column tiles)
   p.xa_hi = x_hi; p.xa_lo = x_lo; p.xb_hi = x_hi; p.xb_lo = x_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
@@ -1153,6 +1285,7 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
     const TcPlan& pl = plans[i];
     p.row_begin = r0 + pl.row_tile0 * kTcBM;
     p.units_per_cta = pl.units_per_cta; p.total_units = pl.total_units; p.max_seg = pl.max_seg;
+    p.R = pl.R; p.n_chunks = pl.n_chunks; p.chunk_w = pl.chunk_w; p.rem0 = pl.rem0; p.rem_w = pl.rem_w;
     {
       DUST_TIMED("phi_tc_kernel", stream);
       phi_tc_kernel<<<pl.grid, kTcThreads, L.total, stream>>>(p);
@@ -1169,3 +1302,20 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
 }
 
 }  // namespace dust
+
+// How dust_svgd_phi's tensor-core path partitions `row_tiles` x `col_tiles` tile pairs over its launches (no launch,
+// no device needed): plan[i] = {grid, R, n_chunks, chunk_w, rem0, rem_w, units_per_cta, total_units, max_seg,
+// row_tile0, row_tiles} of launch i; returns the number of launches.  Tests emulate the kernel's segment iterator on
+// it to prove every tile pair is visited exactly once and the finish kernel finds every scratch slot.
+extern "C" int dust_phi_tc_plan(int32_t row_tiles, int32_t col_tiles, int32_t plan[2][11]) {
+  if (row_tiles <= 0 || col_tiles < 16 || plan == nullptr) return 0;
+  dust::TcPlan pl[2];
+  const int n = dust::tc_launch_plans(row_tiles, col_tiles, pl);
+  for (int i = 0; i < n; ++i) {
+    const dust::TcPlan& q = pl[i];
+    const int v[11] = {q.grid, q.R, q.n_chunks, q.chunk_w, q.rem0, q.rem_w, q.units_per_cta, q.total_units, q.max_seg,
+                       q.row_tile0, q.row_tiles};
+    for (int c = 0; c < 11; ++c) plan[i][c] = v[c];
+  }
+  return n;
+}

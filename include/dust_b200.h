@@ -330,6 +330,12 @@ typedef struct dust_phi_args {
 } dust_phi_args;
 
 size_t dust_phi_workspace_bytes(const dust_phi_args* args);
+/* How the tensor-core path of dust_svgd_phi cuts `row_tiles` (128 rows each) x `col_tiles` (64 columns each) tile
+ * pairs into launches and CTAs (no launch, no device needed).  plan[i] = {grid, R, n_chunks, chunk_w, rem0, rem_w,
+ * units_per_cta, total_units, max_seg, row_tile0, row_tiles} of launch i: CTA c < n_chunks * R owns row tile c % R and
+ * the column chunk [(c / R) * chunk_w, +chunk_w); the others own equal contiguous ranges of the row-major numbered
+ * left-over columns [rem0, rem0 + rem_w).  Returns the number of launches (<= 2).  Tests use it to prove coverage. */
+int dust_phi_tc_plan(int32_t row_tiles, int32_t col_tiles, int32_t plan[2][11]);
 int dust_svgd_phi(const dust_phi_args* args, void* stream);
 
 /* bandwidth -> (gamma,c1,c2) on the device, from the median written by dust_median_select:

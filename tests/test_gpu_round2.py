@@ -91,6 +91,50 @@ def test_phi_and_median_at_65536(cloud):
     assert e_blk <= 2e-6
 
 
+@pytest.mark.parametrize("N,D,rows", [(8192, 40, None), (8192, 40, (1024, 2048)), (8192, 40, (0, 128)),
+                                      (8192, 24, (384, 8192)), (24576, 40, None), (20480, 32, None),
+                                      (9344 * 2, 16, (0, 9344))])
+def test_phi_partitions_and_operand_modes(N, D, rows):
+    """The tensor-core phi over every class of partition dust_phi_tc_plan produces (plain ranges for little work, column
+    chunks with and without left-over columns, whole row tiles per SM plus a chunked rest) and both homes of the row
+    tile (TMEM for d <= 40, shared memory above / with DUST_B200_TC_A_SMEM): sampled rows against float64, and the two
+    operand modes against each other bit for bit (the same MMAs on the same operand bits).  svgd.py:127-135."""
+    import os
+
+    from dust_b200 import _lib as L
+    from dust_b200 import ops
+
+    g = torch.Generator().manual_seed(N + D)
+    X = torch.randn(N, D, generator=g) * 0.7
+    S = torch.randn(N, D, generator=g)
+    x, s = cu(X).unsqueeze(0), cu(S).unsqueeze(0)
+    gam, c1, c2 = 1.0 / (2.0 * D), 1.0 / N, 1.0 / (N * D)
+    r0, r1 = rows or (0, N)
+    lib = L.load()
+    lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
+    out = ops.svgd_phi(x, s, gamma=gam, c1=c1, c2=c2, rows=rows)["phi"][0, r0:r1]
+    prof = L.profiler_report()
+    lib.dust_profiler_enable(0)
+    assert "phi_tc_kernel" in prof and "phi_large_kernel" not in prof
+    idx = torch.cat([torch.arange(r0, r1, max(1, (r1 - r0) // 96))[:96], torch.randint(r0, r1, (96,), generator=g)])
+    Xd, Sd = X.double(), S.double()
+    xi = Xd[idx]
+    d2 = ((xi * xi).sum(-1, keepdim=True) + (Xd * Xd).sum(-1)[None, :] - 2 * xi @ Xd.t()).clamp(min=0)
+    d2[torch.arange(len(idx)), idx] = 0.0
+    K = (-gam * d2).exp()
+    ref = c1 * (K @ Sd) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xd)
+    got = out.cpu()[idx - r0].double()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    record_parity(f"phi partitions N={N} D={D} rows={rows}", err_vs_float64_max=err, rtol=RTOL_PHI)
+    assert err <= 0.25 * RTOL_PHI, err     # wide kernel (gamma d2 ~ 0.5): ksum * x_i - K X cancels to a few percent
+    os.environ["DUST_B200_TC_A_SMEM"] = "1"
+    try:
+        other = ops.svgd_phi(x, s, gamma=gam, c1=c1, c2=c2, rows=rows)["phi"][0, r0:r1]
+    finally:
+        del os.environ["DUST_B200_TC_A_SMEM"]
+    assert torch.equal(out, other)
+
+
 def test_phi_and_median_read_a_packed_buffer_in_place():
     """X and score as column slices of ONE [N, 2D] buffer (the all-gathered [X | score] of ShardedSVGD, `ld` in the
     ABI): the median, the bandwidth and the phi rows are bit-identical to the contiguous call (same launches, same

@@ -153,6 +153,70 @@ def test_silverman_and_box():
         Box(dim=0)
 
 
+def _phi_segments(pl, cta):
+    """The kernel's TcSegIter (svgd_tc.cu) restated: the (row tile, first column tile, length) segments of CTA `cta`."""
+    grid, R, n_chunks, chunk_w, rem0, rem_w, W, total, max_seg, _, _ = pl
+    T = rem0 + rem_w
+    c = cta - n_chunks * R
+    if c < 0:
+        k, rt = divmod(cta, R)
+        return [(rt, k * chunk_w, min(chunk_w, T - k * chunk_w))]
+    out, u, u1 = [], c * W, min((c + 1) * W, total)
+    while u < u1:
+        rt = u // rem_w
+        jj = u - rt * rem_w
+        ln = min(rem_w - jj, u1 - u)
+        out.append((rt, rem0 + jj, ln))
+        u += ln
+    return out
+
+
+@pytest.mark.parametrize("col_tiles", [16, 64, 128, 1024])
+def test_phi_tensor_core_partition_covers_every_tile_pair_once(col_tiles):
+    """dust_phi_tc_plan (the partition phi_tc_kernel works off, dust/inference/svgd.py:127-135 by row blocks): for row
+    blocks of every size class -- fewer row tiles than SMs, an exact multiple, a multiple plus a rest -- each (row tile,
+    column tile) pair belongs to exactly one segment, no CTA exceeds its scratch slots, and the finish kernel's slot
+    lookup (chunk CTAs k * R + rt, then the remainder CTAs that meet the row tile) names exactly the segments that
+    worked on a row tile."""
+    import ctypes as C
+
+    from dust_b200 import _lib as L
+    lib = L.load()
+    T = col_tiles
+    for row_tiles in [1, 2, 3, 7, 8, 16, 31, 64, 68, 73, 74, 75, 100, 147, 148, 149, 200, 296, 300, 512]:
+        if row_tiles * 128 > T * 64 * 4 and T < 1024:      # keep the emulation small
+            continue
+        buf = (C.c_int32 * 22)()
+        n = lib.dust_phi_tc_plan(row_tiles, T, C.byref(buf))
+        assert 1 <= n <= 2
+        plans = [list(buf[i * 11:(i + 1) * 11]) for i in range(n)]
+        assert sum(pl[10] for pl in plans) == row_tiles and plans[0][9] == 0
+        for pl in plans:
+            grid, R, n_chunks, chunk_w, rem0, rem_w, W, total, max_seg, rt0, rts = pl
+            assert 1 <= grid <= 148 and R == rts and rem0 + rem_w == T
+            seen = np.zeros((R, T), dtype=np.int32)
+            by_rt = {}
+            longest = 0
+            for cta in range(grid):
+                segs = _phi_segments(pl, cta)
+                assert 1 <= len(segs) <= max_seg, (row_tiles, T, cta, segs, pl)
+                longest = max(longest, sum(s[2] for s in segs))
+                for slot, (rt, j0, ln) in enumerate(segs):
+                    assert ln >= 1 and 0 <= rt < R and j0 + ln <= T
+                    seen[rt, j0:j0 + ln] += 1
+                    by_rt.setdefault(rt, []).append((cta, slot))
+            assert (seen == 1).all(), (row_tiles, T, pl)
+            # balance: the longest CTA is within a few percent (+ the 16-unit floor) of an even split
+            assert longest <= max(16, int(np.ceil(R * T / 148) * 1.16) + 1), (row_tiles, T, longest, pl)
+            # the finish kernel's view of row tile rt
+            for rt in range(R):
+                srcs = [(k * R + rt, 0) for k in range(n_chunks)]
+                if rem_w > 0:
+                    for c in range((rt * rem_w) // W, ((rt + 1) * rem_w - 1) // W + 1):
+                        srcs.append((n_chunks * R + c, rt - (c * W) // rem_w))
+                assert sorted(srcs) == sorted(by_rt[rt]), (row_tiles, T, rt, pl)
+
+
 def test_row_blocks_partition():
     from dust_b200.distributed import row_block
 
