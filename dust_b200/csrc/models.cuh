@@ -218,6 +218,26 @@ __device__ __forceinline__ void pendulum_step_pair(const ModelParams& m, const P
                    fminf(fmaxf(pre.y, -m.max_speed_pend), m.max_speed_pend));
   th = fma2(om, bc2(m.dt), th);
 }
+// terminal cost of both trajectories: pendulum_cost<false> lane by lane (the reduction of th itself, the same two
+// polynomials, cos selected by the quadrant, weights applied as unfused products): bit-identical to the scalar call
+__device__ __forceinline__ float2 pendulum_cost_pair(const ModelParams& m, float2 th, float2 om) {
+  const float2 t = fma2(th, bc2(0.636619772f), bc2(12582912.0f));
+  const float2 kf = add2(t, bc2(-12582912.0f));
+  float2 r = fma2(kf, bc2(-1.57079637050628662109375f), th);
+  r = fma2(kf, bc2(4.37113900018624283e-8f), r);
+  const float2 r2 = mul2(r, r);
+  float2 ps = fma2(fma2(bc2(-1.9515295891e-4f), r2, bc2(8.3321608736e-3f)), r2, bc2(-1.6666654611e-1f));
+  ps = fma2(ps, mul2(r2, r), r);
+  float2 pc = fma2(fma2(bc2(2.443315711809948e-5f), r2, bc2(-1.388731625493765e-3f)), r2, bc2(4.166664568298827e-2f));
+  pc = fma2(fma2(pc, r2, bc2(-0.5f)), r2, bc2(1.0f));
+  const uint32_t qa = __float_as_uint(t.x), qb = __float_as_uint(t.y);
+  float2 c;   // cos: the sine polynomial in odd quadrants, negative in quadrants 1 and 2
+  c.x = flip_sign((qa & 1u) ? ps.x : pc.x, (qa << 30) + 0x40000000u);
+  c.y = flip_sign((qb & 1u) ? ps.y : pc.y, (qb << 30) + 0x40000000u);
+  float2 tt = add2(c, bc2(-1.0f));
+  tt = mul2(tt, tt);
+  return add2(mul2_unfused(bc2(m.w_angle), tt), mul2_unfused(bc2(m.w_speed), mul2(om, om)));
+}
 #else
 #define DUST_PEND_PAIR 0
 #endif

@@ -240,7 +240,7 @@ __device__ __forceinline__ float2 pendulum_pair_cost_sum(const RolloutKParams& k
     }
     for (; t < k.H; ++t)
       pendulum_step_pair(k.m, cf, th, om, add2(bc2(th_row[t]), mul2_unfused(sg, make_float2(rowA[t], rowB[t]))), run);
-    const float2 term = make_float2(pendulum_cost<false>(k.m, th.x, om.x), pendulum_cost<false>(k.m, th.y, om.y));
+    const float2 term = pendulum_cost_pair(k.m, th, om);
     csum = add2(csum, add2(run, term));
   }
   return csum;
@@ -919,15 +919,20 @@ __host__ __device__ inline WarpKernelSmem warp_kernel_smem(int N, int HA) {
 }
 
 #if DUST_PEND_PAIR
+__device__ __forceinline__ float exp2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // acc <- acc * scale + eA * rowA + eB * rowB over one score row, both trajectories of the lane at once (packed pipe)
 template <int HA4>
 __device__ __forceinline__ void fold_score_rows(float* __restrict__ acc_row, const float* __restrict__ rowA,
-                                                const float* __restrict__ rowB, bool hasB, float scale, float eA, float eB, int HA) {
+                                                const float* __restrict__ rowB, float scale, float eA, float eB, int HA) {
   const float2 sc2 = bc2(scale), ea2 = bc2(eA), eb2 = bc2(eB);
   auto chunk = [&](int c) {
     const float4 a4 = *reinterpret_cast<const float4*>(acc_row + c);
     const float4 va = *reinterpret_cast<const float4*>(rowA + c);
-    const float4 vb = hasB ? *reinterpret_cast<const float4*>(rowB + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 vb = *reinterpret_cast<const float4*>(rowB + c);   // a missing row: the caller passes rowA and eB = 0
     const float2 lo = fma2(make_float2(a4.x, a4.y), sc2, fma2(ea2, make_float2(va.x, va.y), mul2(eb2, make_float2(vb.x, vb.y))));
     const float2 hi = fma2(make_float2(a4.z, a4.w), sc2, fma2(ea2, make_float2(va.z, va.w), mul2(eb2, make_float2(vb.z, vb.w))));
     *reinterpret_cast<float4*>(acc_row + c) = make_float4(lo.x, lo.y, hi.x, hi.y);
@@ -956,39 +961,43 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
   const int slot = warp * La + lane;             // dense index of an active lane; slot % N == lane % N
   const int n = lane % N;
   float* acc_row = smem + L.off_acc + (active ? slot : 0) * stride;
-  const float* __restrict__ noise = k.noise + inst * (long long)k.SN * HA;
   const int ntiles = (k.SN + WT - 1) / WT;
   const bool bulk = stride == HA;                // unpadded rows: a tile is one contiguous block
   // this warp's tile buffer and "tile landed" barrier: tile t of the instance goes to warp t % 4, which requests its
   // next tile itself as soon as it has folded the current one -- no CTA barrier, no index arithmetic in the loop
   float* const my_tile = smem + L.off_tile + warp * L.tile_floats;
   uint64_t* const my_bar = &full_bar[warp];
+  const uint32_t bar_a = smem_u32(my_bar), tile_a = smem_u32(my_tile);   // shared-window addresses, converted once
   const float* __restrict__ rowA = my_tile + lane * stride;
   const float* __restrict__ rowB = my_tile + (lane + La) * stride;
   const uint32_t tile_bytes = (uint32_t)WT * (uint32_t)HA * 4u;
+  // the warp's next tile in global memory: tiles warp, warp + 4, ... of the instance, one pointer bump per request
+  const float* __restrict__ next_src = k.noise + (inst * (long long)k.SN + (long long)warp * WT) * HA;
+  int next_j0 = warp * WT;
 
-  auto request = [&](int t) {                    // rows [t*WT, ..) into this warp's buffer; called by the whole warp
-    const int j0 = t * WT;
+  auto request = [&]() {                         // the warp's next tile into its buffer; called by the whole warp
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // this warp's reads of the buffer are done
     if (bulk) {
       if (lane == 0) {
-        const uint32_t bytes = (j0 + WT <= k.SN) ? tile_bytes : (uint32_t)(k.SN - j0) * (uint32_t)HA * 4u;
-        mbar_expect_tx(my_bar, bytes);
-        bulk_g2s(my_tile, noise + (long long)j0 * HA, bytes, my_bar);
+        const uint32_t bytes = (next_j0 + WT <= k.SN) ? tile_bytes : (uint32_t)(k.SN - next_j0) * (uint32_t)HA * 4u;
+        mbar_expect_tx_a(bar_a, bytes);
+        bulk_g2s_a(tile_a, next_src, bytes, bar_a);
       }
     } else {
-      const int rows = min(WT, k.SN - j0);
-      if (lane == 0) mbar_expect_tx(my_bar, (uint32_t)rows * (uint32_t)HA * 4u);
+      const int rows = min(WT, k.SN - next_j0);
+      if (lane == 0) mbar_expect_tx_a(bar_a, (uint32_t)rows * (uint32_t)HA * 4u);
       __syncwarp();
-      for (int r = lane; r < rows; r += 32) bulk_g2s(my_tile + r * stride, noise + (long long)(j0 + r) * HA, (uint32_t)HA * 4u, my_bar);
+      for (int r = lane; r < rows; r += 32) bulk_g2s_a(tile_a + (uint32_t)(r * stride) * 4u, next_src + (long long)r * HA, (uint32_t)HA * 4u, bar_a);
     }
+    next_src += (long long)kWarpKernelWarps * WT * HA;
+    next_j0 += kWarpKernelWarps * WT;
   };
   if (lane == 0) {
     mbar_init(my_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  if (warp < ntiles) request(warp);
+  if (warp < ntiles) request();
   for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
     const int nn = e / HA;
     th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
@@ -999,15 +1008,17 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
   const float th0 = __ldg(k.state0 + inst * 2), om0 = __ldg(k.state0 + inst * 2 + 1);
   const bool small = small_angle_horizon<DUST_MODEL_PENDULUM>(k, inst);
   const float* __restrict__ th_row = th_s + n * thst;
-  float* cost_ptr = o.costs ? o.costs + inst * k.SN + warp * WT + lane : nullptr;
+  const bool want_costs = o.costs != nullptr;     // uniform: the pointer below is only dereferenced when set
+  uintptr_t cost_ptr = reinterpret_cast<uintptr_t>(o.costs) + sizeof(float) * (size_t)(inst * k.SN + warp * WT + lane);
   __syncthreads();                               // policy means visible to every warp
 
   float m_run = INFINITY, z_run = 0.f, c_run = 0.f;
   uint32_t parity = 0;
+  const float nal2 = -o.alpha * 1.4426950408889634f;
   for (int t = warp; t < ntiles; t += kWarpKernelWarps) {
     const int j0 = t * WT;
     const int rows = min(WT, k.SN - j0);
-    mbar_wait(my_bar, parity);
+    mbar_wait_a(bar_a, parity);
     parity ^= 1u;
     if (active && lane < rows) {
       const bool hasB = lane + La < rows;
@@ -1030,25 +1041,28 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
       }
       const float costA = (k.P == 1) ? csA : csA / (float)k.P;
       const float costB = hasB ? ((k.P == 1) ? csB : csB / (float)k.P) : INFINITY;
-      if (cost_ptr) {
-        cost_ptr[0] = costA;
-        if (hasB) cost_ptr[La] = costB;
+      if (want_costs) {
+        float* cp = reinterpret_cast<float*>(cost_ptr);
+        cp[0] = costA;
+        if (hasB) cp[La] = costB;
       }
       c_run += costA;
       if (hasB) c_run += costB;
       // online soft-min of this lane's rows relative to its running minimum: both new rows are folded at once
       const float m_new = fminf(m_run, fminf(costA, costB));
-      const float scale = expf(-o.alpha * (m_run - m_new));          // 0 on the first tile (m_run = inf), 1 if the minimum stands
-      const float eA = expf(-o.alpha * (costA - m_new));
-      const float eB = expf(-o.alpha * (costB - m_new));             // 0 for a missing row (cost = inf)
+      // exp(-alpha d) = 2^(-alpha log2(e) d) on the MUFU unit (2 ulp; the argument's rounding adds |d| 6e-8 relative to a
+      // weight of e^-|d|): two instructions per weight instead of libm's nine
+      const float scale = exp2_fast(nal2 * (m_run - m_new));         // 0 on the first tile (m_run = inf), 1 if the minimum stands
+      const float eA = exp2_fast(nal2 * (costA - m_new));
+      const float eB = exp2_fast(nal2 * (costB - m_new));            // 0 for a missing row (cost = inf)
       m_run = m_new;
       z_run = z_run * scale + (eA + eB);
       if (scale != 1.f || eA > 1e-30f || eB > 1e-30f)                // else: invisible in float32
-        fold_score_rows<HA4>(acc_row, rowA, rowB, hasB, scale, eA, eB, HA);
+        fold_score_rows<HA4>(acc_row, rowA, hasB ? rowB : rowA, scale, eA, eB, HA);
     }
-    if (cost_ptr) cost_ptr += kWarpKernelWarps * WT;
+    cost_ptr += sizeof(float) * (size_t)(kWarpKernelWarps * WT);
     __syncwarp();
-    if (t + kWarpKernelWarps < ntiles) request(t + kWarpKernelWarps);
+    if (t + kWarpKernelWarps < ntiles) request();
   }
 
   // ---- combine the G = 4*La/N lanes that share a policy -----------------------------------------------
