@@ -21,7 +21,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from bench_common import ClockSampler, cublas_tf32_tflops, measured_peaks, timed_ms  # noqa: E402
+from bench_common import ClockSampler, committed_traffic, cublas_tf32_tflops, measured_peaks, timed_ms  # noqa: E402
+
+PHI_SOURCES = ["dust_b200/csrc/svgd_tc.cu", "dust_b200/csrc/common.cuh"]
 
 
 def float64_rows(X, S, idx, gamma, c1, c2):
@@ -35,7 +37,7 @@ def float64_rows(X, S, idx, gamma, c1, c2):
     return c1 * (K @ Sd) + c2 * (K.sum(1, keepdim=True) * xi - K @ Xd)
 
 
-def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="packed", emulate_world=1, checks=True):
+def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="peer", emulate_world=1, checks=True):
     import torch.distributed as dist
 
     from dust_b200 import _lib as L
@@ -48,7 +50,24 @@ def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="packed
     S = -X                                               # uses only its row block as its local input
     emu = emulate_world if world == 1 else 1
     b, e = row_block(N, rank, world) if emu == 1 else row_block(N, emu // 2, emu)
+    gather_note = None
+    if world > 1 and gather == "peer":
+        # the NVLink peer-memory exchange needs CUDA IPC between the ranks' processes: if the box refuses it, every rank
+        # learns so here (the decision is all-reduced) and the job takes the NCCL all-gather instead -- and says so
+        ok = torch.ones(1, device=dev)
+        try:
+            from dust_b200.distributed import PeerExchange
+            probe = PeerExchange(N // world, 2 * D, device=dev)
+        except Exception as exc:  # noqa: BLE001
+            ok.zero_()
+            gather_note = f"peer exchange unavailable ({type(exc).__name__}: {exc}); NCCL all-gather used"
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            gather = "packed"
+            gather_note = gather_note or "peer exchange unavailable on another rank; NCCL all-gather used"
     sh = ShardedSVGD(N, D, device=dev, gather=gather)
+    if world > 1 and gather == "peer":
+        sh._peer = probe
     xl, sl = X[b:e].contiguous(), S[b:e].contiguous()
     if emu > 1:   # this process plays rank emu // 2: its row block against the resident columns
         sh.rows = (b, e)
@@ -120,7 +139,7 @@ def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="packed
     peak = peaks["bf16_tflops"] / 2.0
     fl_phi, fl_med = 6.0 * N * N * D, 4.0 * N * N * D
     out = {"workload": "large-N SVGD phi (BASELINE.json configs[3])", "N": N, "d": D, "n_gpus": world, "emulated_world": emu,
-           "rows_of_rank0": [b, e], "gather": gather if world > 1 else None, "steps": steps, "warmup": warmup,
+           "rows_of_rank0": [b, e], "gather": gather if world > 1 else None, "gather_note": gather_note, "steps": steps, "warmup": warmup,
            "ms_phi": ms_phi, "ms_phi_with_median": ms_full if emu == 1 else None,
            "algorithmic_tflops_phi": fl_phi / emu / (ms_phi * 1e-3) / 1e12,    # whole job (all ranks) over its time
            "algorithmic_tflops_with_median": (fl_phi + fl_med) / (ms_full * 1e-3) / 1e12 if emu == 1 else None,
@@ -128,10 +147,12 @@ def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="packed
            "l2_policy": "operands (31 MB) are L2-resident by design: tensor-pipe bound, HBM traffic negligible"}
     if n_phi:
         ach = issued / (t_phi_kernel * 1e-3) / 1e12
+        traffic, traffic_note = committed_traffic("phi_tc_kernel", PHI_SOURCES) if world * emu == 1 else (None, "captured for the single-GPU call only")
         out["roofline"] = {"kernel": "phi_tc_kernel", "bound": "tensor", "unit": "TFLOP/s", "achieved": ach, "peak": peak,
                            "frac": ach / peak, "peak_source": f"{peaks['source']} bf16_tflops / 2 (nominal TF32:BF16 = 1:2)",
                            "peak_inrun_cublas_tf32": tf32_inrun, "frac_vs_inrun_cublas_tf32": ach / tf32_inrun,
-                           "ms_per_launch_sum": t_phi_kernel, "launches": n_phi, "traffic": None,
+                           "ms_per_launch_sum": t_phi_kernel, "launches": n_phi, "traffic": traffic, "traffic_note": traffic_note,
+                           "algorithmic_operand_bytes": 4.0 * N * (2 * Dp + 2 * NV + 1),
                            "note": "achieved counts the TF32 MMA FLOPs issued (3 per algorithmic product, K padded to 8 / NV to 16); "
                                    "algorithmic FLOPs are a third of it"}
     if n_med:
@@ -170,9 +191,9 @@ def main():
     ap.add_argument("--dim", type=int, default=40)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--gather", default="packed", choices=["packed", "separate"],
-                    help="sharded runs: one all-gather of [X | score], read in place through a row stride (default), or X and score "
-                         "gathered into their own buffers by two collectives")
+    ap.add_argument("--gather", default="peer", choices=["peer", "packed", "separate"],
+                    help="sharded runs: rows pulled over NVLink peer memory (default; csrc/peer.cu), one NCCL all-gather of "
+                         "[X | score] read in place through a row stride, or X and score gathered by two collectives")
     ap.add_argument("--emulate-world", type=int, default=1,
                     help="single process only: time the row block ONE rank of a world of this size computes (all N "
                          "columns resident, no collective) -- the per-rank device work of the sharded run")

@@ -78,6 +78,14 @@ class MedianArgs(C.Structure):
     ]
 
 
+class PeerArgs(C.Structure):
+    _fields_ = [
+        ("world", _i), ("rank", _i), ("epoch", _i), ("rows_per_rank", _i), ("row_floats", _i),
+        ("slabs", C.POINTER(_p)), ("flags", C.POINTER(_p)), ("gathered", _p),
+        ("gathered_peers", C.POINTER(_p)), ("counters", _p), ("n_parts", _i), ("part_floats", _i * 4), ("parts", _p * 4),
+    ]
+
+
 class PhiArgs(C.Structure):
     _fields_ = [
         ("B", _i), ("N", _i), ("D", _i), ("row_begin", _i), ("row_end", _i), ("per_dim", _i),
@@ -120,6 +128,15 @@ SYMBOLS = {
     "dust_rollout_plan": (C.c_int, [C.POINTER(RolloutArgs), C.POINTER(_i * 5)]),
     "dust_cost_reduce": (C.c_int, [C.POINTER(RolloutArgs), _p]),
     "dust_phi_tc_plan": (C.c_int, [_i, _i, C.POINTER(_i * 22)]),
+    "dust_peer_alloc": (C.c_int, [_sz, C.POINTER(_p)]),
+    "dust_peer_free": (C.c_int, [_p]),
+    "dust_peer_export": (C.c_int, [_p, C.POINTER(C.c_ubyte * 64)]),
+    "dust_peer_open": (C.c_int, [C.POINTER(C.c_ubyte * 64), C.POINTER(_p)]),
+    "dust_peer_close": (C.c_int, [_p]),
+    "dust_peer_signal": (C.c_int, [C.POINTER(PeerArgs), _p]),
+    "dust_peer_gather": (C.c_int, [C.POINTER(PeerArgs), _p]),
+    "dust_peer_push": (C.c_int, [C.POINTER(PeerArgs), _p]),
+    "dust_peer_wait": (C.c_int, [C.POINTER(PeerArgs), _p]),
     "dust_svmpc_step": (C.c_int, [C.POINTER(SvmpcStepArgs), _p]),
     "dust_adjoint_workspace_bytes": (_sz, [C.POINTER(AdjointArgs)]),
     "dust_rollout_adjoint": (C.c_int, [C.POINTER(AdjointArgs), _p]),
@@ -172,7 +189,7 @@ def load():
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args
-    if lib.dust_abi_version() != 2:
+    if lib.dust_abi_version() != 3:
         raise ImportError("libdust_b200.so ABI version mismatch: rebuild the library")
     _lib = lib
     return lib

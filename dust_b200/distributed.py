@@ -32,6 +32,105 @@ def shard_instances(n_instances, rank=None, world=None):
     return row_block(n_instances, rank, world)
 
 
+class PeerExchange:
+    """All-gather of equal row blocks over NVLink peer memory (csrc/peer.cu, push form): every rank owns two gathered
+    buffers [world * rows_per_rank, row_floats] that the other ranks map through CUDA IPC.  `gather(x, score)` stores
+    the local rows into block `rank` of the current-parity buffer of EVERY rank (posted 16-byte stores), raises this
+    rank's flag there, and makes the current stream wait for all flags of the exchange -- two small launches, no host
+    synchronisation, no library collective.  One process per GPU on one NVSwitch box; the 64-byte handles travel
+    once, through `group`.  Buffers alternate by parity: the tensor `gather` returns stays valid until the exchange
+    after next."""
+
+    def __init__(self, rows_per_rank, row_floats, group=None, device=None):
+        import ctypes as C
+
+        from . import _lib as L
+        self.L, self.C = L, C
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.rows, self.width = int(rows_per_rank), int(row_floats)
+        if self.width % 4:
+            raise ValueError("PeerExchange: rows must be whole 16-byte vectors")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        lib = L.load()
+        self.buf_stride = (4 * self.world * self.rows * self.width + 255) // 256 * 256
+        total = 2 * self.buf_stride + 512                       # two gathered buffers, flags [<= 16], counters [<= 16]
+        base = C.c_void_p()
+        with torch.cuda.device(self.device):
+            L.check(lib.dust_peer_alloc(total, C.byref(base)))
+            handle = (C.c_ubyte * 64)()
+            L.check(lib.dust_peer_export(base, C.byref(handle)))
+            mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.device)
+            every = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            every = every.cpu().reshape(self.world, 64)
+            self.bases = []
+            for r in range(self.world):
+                if r == self.rank:
+                    self.bases.append(base.value)
+                    continue
+                h = (C.c_ubyte * 64)(*[int(v) for v in every[r]])
+                p = C.c_void_p()
+                L.check(lib.dust_peer_open(C.byref(h), C.byref(p)))
+                self.bases.append(p.value)
+        self._own = base.value
+        self.epoch = 0
+        self._buf_arrays = [(C.c_void_p * self.world)(*[b + par * self.buf_stride for b in self.bases]) for par in (0, 1)]
+        self._flag_array = (C.c_void_p * self.world)(*[b + 2 * self.buf_stride for b in self.bases])
+        self._counters = self._own + 2 * self.buf_stride + 256
+        self._local = [_as_tensor(self._own + par * self.buf_stride, (self.world * self.rows, self.width), self.device, self)
+                       for par in (0, 1)]
+        dist.barrier(group=group)                                # every mapping exists before the first store
+
+    def gather(self, *parts):
+        """parts: contiguous float32 tensors [rows_per_rank, w_i], w_i % 4 == 0, sum(w_i) = row_floats (X and score)
+        -> [N, row_floats] (rank-major rows)."""
+        L, C = self.L, self.C
+        if not 1 <= len(parts) <= 4:
+            raise ValueError("PeerExchange.gather: 1..4 row pieces")
+        self.epoch += 1
+        par = self.epoch & 1
+        a = L.PeerArgs()
+        a.world, a.rank, a.epoch, a.rows_per_rank, a.row_floats = self.world, self.rank, self.epoch, self.rows, self.width
+        a.gathered_peers = C.cast(self._buf_arrays[par], C.POINTER(C.c_void_p))
+        a.flags = C.cast(self._flag_array, C.POINTER(C.c_void_p))
+        a.counters = self._counters
+        a.n_parts = len(parts)
+        for k, t in enumerate(parts):
+            if t.shape[0] != self.rows or not t.is_contiguous():
+                raise ValueError("PeerExchange.gather: pieces must be contiguous [rows_per_rank, w]")
+            a.parts[k] = L.ptr(t)
+            a.part_floats[k] = int(t.shape[1])
+        L.call("dust_peer_push", C.byref(a), L.stream())
+        L.call("dust_peer_wait", C.byref(a), L.stream())
+        return self._local[par]
+
+    def close(self):
+        if getattr(self, "_own", None) is None:
+            return
+        lib = self.L.load()
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)                           # nobody still writes into this rank's buffers
+        for r, b in enumerate(self.bases):
+            if r != self.rank:
+                lib.dust_peer_close(b)
+        lib.dust_peer_free(self._own)
+        self._own = None
+
+
+class _DevMem:
+    """__cuda_array_interface__ view of library-owned device memory (kept alive by `owner`)."""
+
+    def __init__(self, ptr, shape, owner):
+        self.owner = owner
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<f4", "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
+def _as_tensor(ptr, shape, device, owner):
+    return torch.as_tensor(_DevMem(ptr, shape, owner), device=device)
+
+
 class ShardedSVGD:
     """phi = (K grad log p + sum grad k)/N for N particles split by row blocks over the ranks of
     `group` (dust/inference/svgd.py:127-135 with the bw_median bandwidth, svgd.py:42-52)."""
@@ -39,9 +138,11 @@ class ShardedSVGD:
     def __init__(self, n_total, dim, group=None, ops=_ops, device=None, gather="packed"):
         """gather: "packed" = ONE all-gather of [X | score] into an [N, 2D] buffer that the kernels read in place through
         a row stride (X = buffer[:, :D], score = buffer[:, D:]: no slicing copies); "separate" = X and score gathered
-        into their own [N, D] buffers by two collectives (the score gather then overlaps the bandwidth pass).
-        Measured on 8 B200 (profiles/r2_scale8.md): a collective costs ~35-40 us, more than the overlap wins."""
-        if gather not in ("packed", "separate"):
+        into their own [N, D] buffers by two collectives (the score gather then overlaps the bandwidth pass);
+        "peer" = no library collective: every rank stores its rows over NVLink peer memory into the packed buffer of
+        every rank (`PeerExchange`, csrc/peer.cu; CUDA devices of one box only).
+        Measured on 8 B200 (profiles/r2_scale8.md): the NCCL all-gather of 21 MB costs ~90 us of a 0.6 ms step."""
+        if gather not in ("packed", "separate", "peer"):
             raise ValueError(gather)
         self.gather_mode = gather
         self._gathered2 = {}
@@ -54,6 +155,7 @@ class ShardedSVGD:
         self.device = device
         self._gathered = None
         self._median_ws = None
+        self._peer = None
 
     def _all_gather(self, local):
         """[n_loc, C] -> [N, C] (rank-major row order)."""
@@ -85,6 +187,11 @@ class ShardedSVGD:
                 out.append(buf)
                 waits.append(work.wait)
             return out[0], out[1], waits[0], waits[1]
+        if self.gather_mode == "peer":
+            if self._peer is None:
+                self._peer = PeerExchange(self.N // self.world, 2 * self.D, group=self.group, device=x_local.device)
+            both = self._peer.gather(x_local.contiguous(), score_local.contiguous())
+            return both[:, : self.D], both[:, self.D:], nothing, nothing
         local = torch.cat([x_local, score_local], dim=1)
         if self._gathered is None or self._gathered.shape[1] != 2 * self.D or self._gathered.device != local.device:
             self._gathered = torch.empty((self.N, 2 * self.D), dtype=local.dtype, device=local.device)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define DUST_B200_ABI_VERSION 2
+#define DUST_B200_ABI_VERSION 3
 
 typedef enum dust_status {
   DUST_OK = 0,
@@ -460,6 +460,44 @@ int dust_model_cost(const dust_model_desc* model, int32_t M, int32_t terminal, c
  * values depends only on (seed, offset, i), so a fill is reproducible, and ranks / successive steps
  * draw independent streams by using distinct offsets.  out: n floats, 16-byte aligned. */
 int dust_noise_normal(float* out, int64_t n, uint64_t seed, uint64_t offset, void* stream);
+
+/* Exchange of row-block sharded SVGD over NVLink peer memory, replacing the all-gather of particles and scores
+ * that row-block sharding of dust/inference/svgd.py:127-135 needs (the reference has one process and no exchange).
+ * One process per GPU on one NVSwitch box.  Every rank allocates a slab with dust_peer_alloc (plain cudaMalloc: CUDA
+ * IPC cannot export pool memory), exports it (64-byte handle, exchanged by the host over any channel) and opens the
+ * other ranks' handles.  Per exchange `epoch` (1, 2, ...): write the local rows into the slab of parity epoch & 1,
+ * dust_peer_signal (stores `epoch` into entry `rank` of the flag array ON EVERY RANK, after a system fence), then
+ * dust_peer_gather: every CTA waits for the flag of the rank whose rows it copies and pulls them with 16-byte loads
+ * into `gathered` [world * rows_per_rank, row_floats].  Two slabs alternating by parity make a second barrier
+ * unnecessary (csrc/peer.cu).  A peer that never signals traps the kernel after ~2 s (launch failure, no hang). */
+typedef struct dust_peer_args {
+  int32_t world, rank;       /* ranks on the box (<= 16), this rank */
+  int32_t epoch;             /* > 0, the same on every rank, increasing by one per exchange */
+  int32_t rows_per_rank;     /* rows every rank contributes */
+  int32_t row_floats;        /* floats per row (2D for [X | score]); rows_per_rank * row_floats % 4 == 0 */
+  const float* const* slabs; /* HOST array [world]: this epoch's slab of every rank as mapped in this process */
+  int32_t* const* flags;     /* HOST array [world]: the int32 flag array [world] of every rank as mapped here */
+  float* gathered;           /* [world * rows_per_rank, row_floats] local output of dust_peer_gather */
+  /* push form (dust_peer_push / dust_peer_wait): no slabs; the gathered buffers themselves are peer-mapped */
+  float* const* gathered_peers; /* HOST array [world]: this epoch's gathered buffer of every rank as mapped here */
+  int32_t* counters;         /* LOCAL device int32 [world], zero-filled once (arrival counters of the push CTAs) */
+  int32_t n_parts;           /* 1..4 pieces a local row is made of, e.g. X and score */
+  int32_t part_floats[4];    /* floats per row of each piece (multiples of 4; their sum = row_floats) */
+  const float* parts[4];     /* local [rows_per_rank, part_floats[k]] contiguous, 16-byte aligned */
+} dust_peer_args;
+
+int dust_peer_alloc(size_t bytes, void** ptr);                      /* zero-filled, 256-byte aligned */
+int dust_peer_free(void* ptr);
+int dust_peer_export(const void* ptr, unsigned char handle[64]);     /* ptr from dust_peer_alloc */
+int dust_peer_open(const unsigned char handle[64], void** ptr);      /* maps a peer's allocation, enables peer access */
+int dust_peer_close(void* ptr);
+int dust_peer_signal(const dust_peer_args* args, void* stream);
+int dust_peer_gather(const dust_peer_args* args, void* stream);
+/* Push form: every rank stores its rows (pieces concatenated per row) into block `rank` of gathered_peers[q] for every
+ * q and raises flags_on_q[rank] = epoch once all of them have landed; dust_peer_wait holds the stream until all flags
+ * of `epoch` are up in the local flag array.  Buffers of two parities alternate, as the slabs do. */
+int dust_peer_push(const dust_peer_args* args, void* stream);
+int dust_peer_wait(const dust_peer_args* args, void* stream);
 
 /* Optional per-kernel timing for benchmarks: when enabled every kernel launch of the library is
  * bracketed by CUDA events on its stream.  dust_profiler_report synchronises the device and

@@ -4,7 +4,9 @@ import csv, subprocess
 
 REPS = [("round 1: `svmpc_instance_kernel<pendulum,20,2>` (CTA tiles, accumulators in registers)", "gpurun_out/fused_r8.ncu-rep"),
         ("round 2a: `svmpc_warp_kernel` (per-warp TMA tiles, accumulators in shared memory, pair/item tail)", "gpurun_out/fused_r2a.ncu-rep"),
-        ("round 2b: + host-side coefficients (no FP64), one buffer per warp, templated fold", "gpurun_out/fused_r2b.ncu-rep")]
+        ("round 2b: + host-side coefficients (no FP64), one buffer per warp, templated fold", "gpurun_out/fused_r2b.ncu-rep"),
+        ("round 2c: + packed terminal cost, MUFU soft-min weights, running tile pointer (fewer instructions, same duration: "
+         "the FMA-heavy pipe -- every packed FFMA2/FADD2/FMUL2 holds it two cycles -- and the issue slots bind)", "gpurun_out/fused_r2c.ncu-rep")]
 KEYS = [("gpu__time_duration.sum", "duration (us, under ncu)"), ("smsp__inst_executed.sum", "warp instructions"),
         ("launch__registers_per_thread", "registers / thread"), ("launch__occupancy_limit_registers", "CTAs/SM (register limit)"),
         ("launch__occupancy_limit_shared_mem", "CTAs/SM (shared-memory limit)"), ("launch__shared_mem_per_block_dynamic", "dynamic smem / CTA (KB)"),
@@ -12,6 +14,7 @@ KEYS = [("gpu__time_duration.sum", "duration (us, under ncu)"), ("smsp__inst_exe
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active (%)"),
         ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps / cycle"),
         ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "FMA pipe cycles active (%)"),
+        ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_elapsed", "FMA-heavy pipe cycles active (% of elapsed)"),
         ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe cycles active (%)"),
         ("dram__bytes_read.sum", "DRAM read (MB)"), ("dram__bytes_write.sum", "DRAM written (MB)"),
         ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput (% of peak)")]

@@ -2,8 +2,9 @@
 hash of the sources the capture was taken on.  bench.py emits `roofline.traffic` only while that hash still matches
 the tree (a stale figure is dropped, not repeated).
 
-usage: python profiles/update_traffic.py <report.ncu-rep> <kernel key> <source files ...>
-   e.g. python profiles/update_traffic.py gpurun_out/fused_r2a.ncu-rep svmpc_instance_kernel \
+usage: python profiles/update_traffic.py [--sum] <report.ncu-rep> <kernel key> <source files ...>
+   --sum: the kernel runs as several launches per call (phi_tc_kernel: whole row tiles, then the rest): add them up
+   e.g. python profiles/update_traffic.py gpurun_out/fused_r2c.ncu-rep svmpc_instance_kernel=svmpc_warp_kernel \
             dust_b200/csrc/rollout.cu dust_b200/csrc/models.cuh dust_b200/csrc/common.cuh"""
 import csv
 import json
@@ -17,26 +18,31 @@ from bench_common import source_sha  # noqa: E402
 
 
 def main():
-    rep, key, files = sys.argv[1], sys.argv[2], sys.argv[3:]
+    argv = [a for a in sys.argv[1:] if a != "--sum"]
+    total = "--sum" in sys.argv[1:]
+    rep, key, files = argv[0], argv[1], argv[2:]
+    key, _, match = key.partition("=")      # "<json key>=<substring of the kernel name>" when the two differ
+    match = match or key
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
     rows = list(csv.reader(out.splitlines()))
     hdr, units = rows[0], rows[1]
-    cand = [r for r in rows[2:] if key in r[hdr.index("Kernel Name")]]
+    cand = [r for r in rows[2:] if match in r[hdr.index("Kernel Name")]]
     assert cand, f"no launch of {key} in {rep}"
     r = cand[-1]
 
     def get(name):
         i = hdr.index(name)
-        v = float(r[i].replace(",", ""))
         u = units[i].lower()
-        return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        return sum(float(q[i].replace(",", "")) * scale for q in (cand if total else [r]))
 
     rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
     path = os.path.join(ROOT, "profiles", "traffic.json")
     db = json.load(open(path)) if os.path.isfile(path) else {}
     db[key] = {"kernel": r[hdr.index("Kernel Name")], "report": os.path.basename(rep), "dram_bytes_read": rd, "dram_bytes_write": wr,
                "dram_bytes_per_launch": rd + wr, "source_files": files, "source_sha": source_sha(files),
-               "note": "ncu --set full, one launch of the bench workload, --clock-control none"}
+               "launches": len(cand) if total else 1,
+               "note": "ncu --set full, one call of the bench workload, --clock-control none"}
     json.dump(db, open(path, "w"), indent=1)
     print(key, db[key])
 

@@ -135,6 +135,106 @@ def test_phi_partitions_and_operand_modes(N, D, rows):
     assert torch.equal(out, other)
 
 
+def test_peer_gather_kernels_two_ranks_on_one_device():
+    """dust_peer_signal / dust_peer_gather and dust_peer_push / dust_peer_wait (csrc/peer.cu; the exchange that row-block sharding of svgd.py:127-135 needs)
+    with both ranks played by one process on one device -- the IPC mapping aside, the same launches a two-rank job
+    makes: slabs alternate by epoch parity, a gather waits for the flags of its epoch, the result is the rank-major
+    concatenation.  (The mapping itself runs under torchrun in bench.py, which compares with the single-GPU rows.)"""
+    import ctypes as C
+
+    from dust_b200 import _lib as L
+
+    lib = L.load()
+    world, rows, width = 2, 384, 80
+    stride = (4 * rows * width + 255) // 256 * 256
+    bases = []
+    for _ in range(world):
+        p = C.c_void_p()
+        L.check(lib.dust_peer_alloc(2 * stride + 256, C.byref(p)))
+        bases.append(p.value)
+    handle = (C.c_ubyte * 64)()
+    L.check(lib.dust_peer_export(bases[0], C.byref(handle)))
+    assert any(handle)
+    try:
+        g = torch.Generator().manual_seed(3)
+        outs = [torch.zeros(world * rows, width, device=DEV) for _ in range(world)]
+        for epoch in (1, 2, 3):
+            par = epoch & 1
+            blocks = [torch.randn(rows, width, generator=g) for _ in range(world)]
+            slabs = (C.c_void_p * world)(*[b + par * stride for b in bases])
+            flags = (C.c_void_p * world)(*[b + 2 * stride for b in bases])
+
+            def args(rank):
+                a = L.PeerArgs()
+                a.world, a.rank, a.epoch, a.rows_per_rank, a.row_floats = world, rank, epoch, rows, width
+                a.slabs, a.flags = C.cast(slabs, C.POINTER(C.c_void_p)), C.cast(flags, C.POINTER(C.c_void_p))
+                a.gathered = outs[rank].data_ptr()
+                return a
+
+            for r in range(world):      # every rank: rows into its slab, then its flag on every rank
+                dst = torch.as_tensor(_Dev(bases[r] + par * stride, (rows, width)), device=DEV)
+                dst.copy_(blocks[r].to(DEV))
+                L.call("dust_peer_signal", C.byref(args(r)), L.stream())
+            for r in range(world):
+                L.call("dust_peer_gather", C.byref(args(r)), L.stream())
+            torch.cuda.synchronize()
+            want = torch.cat(blocks, 0)
+            for r in range(world):
+                assert torch.equal(outs[r].cpu(), want), (epoch, r)
+            fl = torch.as_tensor(_Dev(bases[0] + 2 * stride, (world,), "<i4"), device=DEV)
+            assert fl.cpu().tolist() == [epoch] * world
+        a = args(0)
+        a.epoch = 0
+        with pytest.raises(ValueError):
+            L.call("dust_peer_gather", C.byref(a), L.stream())
+        # push form: the gathered buffers are the shared allocations (parity p at bases[r] + p * gstride), the rows come
+        # straight from X and score; flags and arrival counters sit behind the two buffers
+        gstride = (4 * world * rows * width + 255) // 256 * 256
+        pbases = []
+        for _ in range(world):
+            p = C.c_void_p()
+            L.check(lib.dust_peer_alloc(2 * gstride + 512, C.byref(p)))
+            pbases.append(p.value)
+        bases += pbases
+        for epoch in (1, 2, 3):
+            par = epoch & 1
+            xs = [torch.randn(rows, width // 2, generator=g).to(DEV) for _ in range(world)]
+            ss = [torch.randn(rows, width // 2, generator=g).to(DEV) for _ in range(world)]
+            bufs = (C.c_void_p * world)(*[b + par * gstride for b in pbases])
+            flags = (C.c_void_p * world)(*[b + 2 * gstride for b in pbases])
+            for r in range(world):
+                a = L.PeerArgs()
+                a.world, a.rank, a.epoch, a.rows_per_rank, a.row_floats = world, r, epoch, rows, width
+                a.gathered_peers, a.flags = C.cast(bufs, C.POINTER(C.c_void_p)), C.cast(flags, C.POINTER(C.c_void_p))
+                a.counters = pbases[r] + 2 * gstride + 256
+                a.n_parts = 2
+                a.parts[0], a.parts[1] = xs[r].data_ptr(), ss[r].data_ptr()
+                a.part_floats[0] = a.part_floats[1] = width // 2
+                L.call("dust_peer_push", C.byref(a), L.stream())
+            for r in range(world):
+                a = L.PeerArgs()
+                a.world, a.rank, a.epoch = world, r, epoch
+                a.flags = C.cast(flags, C.POINTER(C.c_void_p))
+                L.call("dust_peer_wait", C.byref(a), L.stream())
+            torch.cuda.synchronize()
+            want = torch.cat([torch.cat([xs[r], ss[r]], 1) for r in range(world)], 0)
+            for r in range(world):
+                got = torch.as_tensor(_Dev(pbases[r] + par * gstride, (world * rows, width)), device=DEV)
+                assert torch.equal(got, want), (epoch, r)
+            cnt = torch.as_tensor(_Dev(pbases[0] + 2 * gstride + 256, (world,), "<i4"), device=DEV)
+            assert cnt.cpu().tolist() == [0] * world          # the last CTA per destination re-arms the counter
+    finally:
+        torch.cuda.synchronize()
+        for b in bases:
+            lib.dust_peer_free(b)
+
+
+class _Dev:
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 2,
+                                         "strides": None}
+
+
 def test_phi_and_median_read_a_packed_buffer_in_place():
     """X and score as column slices of ONE [N, 2D] buffer (the all-gathered [X | score] of ShardedSVGD, `ld` in the
     ABI): the median, the bandwidth and the phi rows are bit-identical to the contiguous call (same launches, same

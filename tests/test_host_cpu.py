@@ -26,7 +26,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/dust_b200.h but not exported"
         assert name in _lib.SYMBOLS, f"{name} has no ctypes prototype in dust_b200/_lib.py"
-    assert lib.dust_abi_version() == 2
+    assert lib.dust_abi_version() == 3
     assert b"sm_100a" in lib.dust_build_info()
 
 
@@ -39,7 +39,7 @@ def test_struct_layouts_match_the_header():
     names = {"dust_model_desc": _lib.ModelDesc, "dust_rollout_args": _lib.RolloutArgs, "dust_svmpc_step_args": _lib.SvmpcStepArgs, "dust_adjoint_args": _lib.AdjointArgs,
              "dust_gmm_args": _lib.GmmArgs, "dust_median_args": _lib.MedianArgs, "dust_phi_args": _lib.PhiArgs,
              "dust_svmpc_forward_args": _lib.SvmpcForwardArgs, "dust_disco_step_args": _lib.DiscoStepArgs,
-             "dust_mpf_args": _lib.MpfArgs}
+             "dust_mpf_args": _lib.MpfArgs, "dust_peer_args": _lib.PeerArgs}
     src = '#include <stdio.h>\n#include "dust_b200.h"\nint main(){' + "".join(
         f'printf("{n} %zu\\n", sizeof({n}));' for n in names) + "return 0;}"
     exe = "/tmp/dust_sizeof"
