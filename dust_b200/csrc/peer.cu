@@ -87,12 +87,12 @@ struct PushParams {
 __global__ void __launch_bounds__(kPeerThreads) peer_push_kernel(PushParams p) {
   const int q = blockIdx.y;
   float4* __restrict__ out = p.dst[q] + (long long)p.rank * p.rows * p.vec_per_row;
-  const long long total = (long long)p.rows * p.vec_per_row;
-  const long long per_cta = (total + gridDim.x - 1) / gridDim.x;
-  const long long i0 = (long long)blockIdx.x * per_cta, i1 = min(i0 + per_cta, total);
-  for (long long i = i0 + threadIdx.x; i < i1; i += kPeerThreads) {
-    const int row = (int)(i / p.vec_per_row);
-    int v = (int)(i - (long long)row * p.vec_per_row);
+  const int total = p.rows * p.vec_per_row;            // < 2^31 (checked on the host)
+  const int per_cta = (total + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per_cta, i1 = min(i0 + per_cta, total);
+  auto fetch = [&](int i) {
+    const int row = i / p.vec_per_row;
+    int v = i - row * p.vec_per_row;
     float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -101,8 +101,15 @@ __global__ void __launch_bounds__(kPeerThreads) peer_push_kernel(PushParams p) {
         v -= p.part_vec[k];
       }
     }
-    out[i] = val;
+    return val;
+  };
+  // four independent loads in flight per thread, then four posted stores
+  int i = i0 + threadIdx.x;
+  for (; i + 3 * kPeerThreads < i1; i += 4 * kPeerThreads) {
+    const float4 a = fetch(i), b = fetch(i + kPeerThreads), c = fetch(i + 2 * kPeerThreads), d = fetch(i + 3 * kPeerThreads);
+    out[i] = a; out[i + kPeerThreads] = b; out[i + 2 * kPeerThreads] = c; out[i + 3 * kPeerThreads] = d;
   }
+  for (; i < i1; i += kPeerThreads) out[i] = fetch(i);
   __threadfence_system();             // this thread's remote stores, visible at the destination before anything later
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -245,6 +252,7 @@ extern "C" int dust_peer_push(const dust_peer_args* a, void* stream_) {
   p.n_parts = a->n_parts; p.world = a->world; p.rank = a->rank; p.epoch = a->epoch; p.rows = a->rows_per_rank;
   p.vec_per_row = a->row_floats / 4; p.counters = a->counters;
   const long long total = (long long)p.rows * p.vec_per_row;
+  DUST_REQUIRE(total < (1ll << 31), DUST_ERR_UNSUPPORTED, "dust_peer_push: a rank's block has %lld 16-byte vectors (limit 2^31)", total);
   int chunks = (int)((total + 4 * kPeerThreads - 1) / (4 * kPeerThreads));
   const int want = (4 * kNumSMs + a->world - 1) / a->world;
   if (chunks > want) chunks = want;
