@@ -133,7 +133,11 @@ def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="peer",
     peaks = measured_peaks()
     tf32_inrun = cublas_tf32_tflops(dev)
     Dp, NV = (D + 7) // 8 * 8, (2 * D + 15) // 16 * 16
-    issued = 3 * 2.0 * N * N * (Dp + NV) / (world * emu)       # 3xTF32: hi*hi + hi*lo + lo*hi, per GPU
+    mode = int(lib.dust_phi_tc_mode(D))
+    bf16lo = mode >= 0 and bool(mode & 2)
+    # tensor work issued per GPU in TF32-equivalent FLOPs: GEMM1 3 TF32 MMAs per product (hi*hi + hi*lo + lo*hi); GEMM2
+    # P_hi V_hi + P_hi V_lo in TF32 and the P_lo V correction either in TF32 or -- bf16lo -- as kind::f16 at twice the rate
+    issued = 2.0 * N * N * (3 * Dp + (2.5 if bf16lo else 3.0) * NV) / (world * emu)
     n_phi, t_phi_kernel = prof.get("phi_tc_kernel", (0, 0.0))
     n_med, t_med_kernel = prof.get("median_tc_kernel", (0, 0.0))
     peak = peaks["bf16_tflops"] / 2.0
@@ -153,8 +157,10 @@ def phi_block(rank, world, dev, steps=5, warmup=3, N=65536, D=40, gather="peer",
                            "peak_inrun_cublas_tf32": tf32_inrun, "frac_vs_inrun_cublas_tf32": ach / tf32_inrun,
                            "ms_per_launch_sum": t_phi_kernel, "launches": n_phi, "traffic": traffic, "traffic_note": traffic_note,
                            "algorithmic_operand_bytes": 4.0 * N * (2 * Dp + 2 * NV + 1),
-                           "note": "achieved counts the TF32 MMA FLOPs issued (3 per algorithmic product, K padded to 8 / NV to 16); "
-                                   "algorithmic FLOPs are a third of it"}
+                           "kernel_form": {"row_tile_in_tmem": bool(mode & 1), "p_lo_term_bf16": bf16lo} if mode >= 0 else None,
+                           "note": "achieved counts the tensor work issued in TF32-equivalent FLOPs (3 MMAs per Gram product, 2 TF32 + 1 "
+                                   "bf16-at-half-cost or 3 TF32 per K V product; K padded to 8 / NV to 16); algorithmic FLOPs are "
+                                   "6 N^2 d, about a third of it"}
     if n_med:
         issued_med = 3 * 2.0 * N * N * Dp / 2 / (world * emu)   # symmetric half band of tile pairs
         out["median_kernel"] = {"kernel": "median_tc_kernel", "ms": t_med_kernel,

@@ -128,6 +128,7 @@ SYMBOLS = {
     "dust_rollout_plan": (C.c_int, [C.POINTER(RolloutArgs), C.POINTER(_i * 5)]),
     "dust_cost_reduce": (C.c_int, [C.POINTER(RolloutArgs), _p]),
     "dust_phi_tc_plan": (C.c_int, [_i, _i, C.POINTER(_i * 22)]),
+    "dust_phi_tc_mode": (C.c_int, [_i]),
     "dust_peer_alloc": (C.c_int, [_sz, C.POINTER(_p)]),
     "dust_peer_free": (C.c_int, [_p]),
     "dust_peer_export": (C.c_int, [_p, C.POINTER(C.c_ubyte * 64)]),

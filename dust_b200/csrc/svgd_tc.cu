@@ -45,6 +45,8 @@ struct TcParams {
   int N, D, Dp, NV, T, row_begin;
   int ld;   // row stride of x (floats)
   int a_tmem;  // 1: the row tile (A operand of GEMM1, hi and lo) lives in TMEM, written by the flush warps (TS form)
+  int bf16lo;  // 1: GEMM2's P_lo V term as kind::f16 on bf16 copies (P_lo: 32 TMEM columns per buffer; needs a_tmem)
+  const void* vb_bf;   // bf16 V^T images (bf16lo)
   // Partition of the (row tile, column tile) pairs of a launch over its CTAs (at most one per SM):
   //  * the first n_chunks * R CTAs (R = row tiles of the launch) each own ONE segment: CTA c = k * R + rt takes row
   //    tile rt and the column chunk [k * chunk_w, min((k + 1) * chunk_w, T)).  All CTAs of a chunk start at the same
@@ -73,6 +75,20 @@ __host__ __device__ inline int core_index(int r, int k, int K) {
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_lo(float v, float hi) { return __uint_as_float(__float_as_uint(v - hi) & 0xffffe000u); }
+
+// GEMM2's correction term P_lo V carries 2^-11 of the result: it runs as kind::f16 on bf16 copies (P_lo = bf16(K - K_hi),
+// V as bf16), 16 instead of 8 elements of K per instruction and two values per TMEM column -- P_lo takes 32 columns
+// instead of 64, which is what lets a third S buffer fit beside the row tile (192 + 64 + 160 + 80 = 496 columns).
+// Precision of the term: 8 + 8 mantissa bits on 2^-11 of the sum (~2^-19 relative, unbiased) instead of 2^-21.
+#ifndef DUST_TC_BF16LO
+#define DUST_TC_BF16LO 1
+#endif
+// two floats -> one 32-bit word of two bf16, element `even` in the low half (round to nearest even)
+__device__ __forceinline__ uint32_t pack_bf16x2(float even, float odd) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(odd), "f"(even));
+  return d;
+}
 
 // ---------------------------------------------------------------------------------------
 // prep: squared norms and the tiled hi / lo operand images
@@ -128,8 +144,11 @@ __device__ __forceinline__ void tc_norms_block(int block, const float* __restric
 // (the row sums of K are accumulated exactly in the softmax warps' registers instead of a ones column).
 // Thread <-> one 16-byte core-matrix row = 4 consecutive particles of one dimension, in image order:
 // element (n2, jj) of tile jt sits at jt * NV * 64 + ((n2 >> 3) * 16 + (jj >> 2)) * 32 + (n2 & 7) * 4 + (jj & 3).
+// The bf16 copy (GEMM2's P_lo V term) uses the same K-major core-matrix order with 8 elements per 16-byte row:
+// element (n2, jj) of tile jt at bf16 index jt * NV * 64 + ((n2 >> 3) * 8 + (jj >> 3)) * 64 + (n2 & 7) * 8 + (jj & 7).
 __device__ __forceinline__ void tc_prep_v_block(int block, const float* __restrict__ x, const float* __restrict__ score, int N,
-                                                int D, int ld, int NV, float* __restrict__ vb_hi, float* __restrict__ vb_lo) {
+                                                int D, int ld, int NV, float* __restrict__ vb_hi, float* __restrict__ vb_lo,
+                                                uint2* __restrict__ vb_bf) {
   const long long e = (long long)block * blockDim.x + threadIdx.x;   // index of the float4 in the image
   if (e >= (long long)(N >> 2) * NV) return;
   const int per_tile = NV * (kTcBN >> 2);
@@ -147,6 +166,9 @@ __device__ __forceinline__ void tc_prep_v_block(int block, const float* __restri
   lo.x = tf32_lo(v[0], hi.x); lo.y = tf32_lo(v[1], hi.y); lo.z = tf32_lo(v[2], hi.z); lo.w = tf32_lo(v[3], hi.w);
   reinterpret_cast<float4*>(vb_hi)[e] = hi;
   reinterpret_cast<float4*>(vb_lo)[e] = lo;
+  if (vb_bf)
+    vb_bf[(long long)jt * NV * 16 + (ng * 8 + (jq >> 1)) * 16 + n7 * 2 + (jq & 1)] =
+        make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
 
 // ONE launch prepares everything a pass needs: CTAs [0, nbx) write the X images, [nbx, nbx + nbv) the
@@ -154,16 +176,16 @@ __device__ __forceinline__ void tc_prep_v_block(int block, const float* __restri
 // three small memory-bound jobs that overlap instead of queueing behind each other's launch
 __global__ void __launch_bounds__(256) tc_prep_kernel(const float* __restrict__ x, const float* __restrict__ score, int N, int D, int ld,
                                                       int Dp, int NV, float* __restrict__ x_hi, float* __restrict__ x_lo,
-                                                      float* __restrict__ vb_hi, float* __restrict__ vb_lo,
+                                                      float* __restrict__ vb_hi, float* __restrict__ vb_lo, uint2* __restrict__ vb_bf,
                                                       float* __restrict__ xn, int nbx, int nbv) {
   const int b = blockIdx.x;
   if (b < nbx) tc_prep_x_block(b, x, N, D, ld, Dp, x_hi, x_lo);
-  else if (b < nbx + nbv) tc_prep_v_block(b - nbx, x, score, N, D, ld, NV, vb_hi, vb_lo);
+  else if (b < nbx + nbv) tc_prep_v_block(b - nbx, x, score, N, D, ld, NV, vb_hi, vb_lo, vb_bf);
   else tc_norms_block(b - nbx - nbv, x, N, D, ld, xn);
 }
 
 static int tc_prep(const float* x, const float* score, int N, int D, int ld, int Dp, int NV, float* x_hi, float* x_lo, float* vb_hi,
-                   float* vb_lo, float* xn, cudaStream_t stream, bool x_prepared = false) {
+                   float* vb_lo, float* xn, cudaStream_t stream, bool x_prepared = false, void* vb_bf = nullptr) {
   // x_prepared: the X images and the norms are already in place (median pass on the same workspace): V^T images only
   const int nbx = x_prepared ? 0 : ceil_div((long long)N * (Dp / 4), 256);
   const int nbv = score ? ceil_div((long long)(N / 4) * NV, 256) : 0;
@@ -171,7 +193,7 @@ static int tc_prep(const float* x, const float* score, int N, int D, int ld, int
   if (nbx + nbv + nbn == 0) return DUST_OK;
   {
     DUST_TIMED("tc_prep_kernel", stream);
-    tc_prep_kernel<<<nbx + nbv + nbn, 256, 0, stream>>>(x, score, N, D, ld, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, nbx, nbv);
+    tc_prep_kernel<<<nbx + nbv + nbn, 256, 0, stream>>>(x, score, N, D, ld, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, (uint2*)vb_bf, xn, nbx, nbv);
   }
   DUST_LAUNCH_OK("tc_prep_kernel");
   return DUST_OK;
@@ -225,6 +247,18 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
       : "memory");
 }
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4)                    // D format F32
+         | (1u << 7) | (1u << 10)     // A, B format BF16
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_ts_f16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -262,6 +296,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
@@ -281,19 +323,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
 struct TcSmem {
   // byte offsets into dynamic shared memory
   uint32_t a_hi, a_lo, xb, vb, bars, tmem_slot, total;
-  uint32_t xb_stage_bytes, vb_stage_bytes, xb_half, vb_half;
+  uint32_t xb_stage_bytes, vb_stage_bytes, xb_half, vb_half, vb_bf_bytes;
 };
 
-__host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
+// a_tmem: the row tile lives in TMEM, no shared memory for it; bf16lo: a V stage also carries the bf16 copy
+__host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV, bool a_tmem = false, bool bf16lo = false) {
   TcSmem s;
   uint32_t off = 0;
-  s.a_hi = off; off += kTcBM * Dp * 4;
-  s.a_lo = off; off += kTcBM * Dp * 4;
+  s.a_hi = off; off += a_tmem ? 0 : kTcBM * Dp * 4;
+  s.a_lo = off; off += a_tmem ? 0 : kTcBM * Dp * 4;
   s.xb_half = kTcBN * Dp * 4;
   s.xb_stage_bytes = 2 * s.xb_half;
   s.xb = off; off += kXbStages * s.xb_stage_bytes;
   s.vb_half = NV * kTcBN * 4;
-  s.vb_stage_bytes = 2 * s.vb_half + kTcBN * 4;  // hi, lo, |x_j|^2
+  s.vb_bf_bytes = bf16lo ? NV * kTcBN * 2 : 0;
+  s.vb_stage_bytes = 2 * s.vb_half + kTcBN * 4 + s.vb_bf_bytes;  // hi, lo, |x_j|^2, bf16 copy
   s.vb = off; off += kVbStages * s.vb_stage_bytes;
   off = (off + 7) & ~7u;
   s.bars = off; off += 40 * 8;
@@ -305,8 +349,9 @@ __host__ __device__ inline TcSmem tc_smem_layout(int Dp, int NV) {
 // S / P_hi ring of kSBufs = 3 (P_hi overwrites the S it came from), P_lo ring of 2: GEMM1 runs TWO tiles ahead of
 // GEMM2, so the softmax stage of a tile has two tile periods (not one) before the tensor pipe waits for it
 #ifndef DUST_TC_SBUFS
-#define DUST_TC_SBUFS 2          // 3 = GEMM1 two tiles ahead of GEMM2 (S/P_hi ring of three): measured SLOWER on B200
-                                 // (5.43 vs 5.04 ms at N = 65536, profiles/r2_phi_sbufs_ab.md) -- kept as a build option
+#define DUST_TC_SBUFS 3          // S/P_hi ring: GEMM1 may run three tiles ahead of GEMM2.  With ONE issuing warp a ring of
+                                 // three measured slower (5.43 vs 5.04 ms at N = 65536); with two issuers the S -> exp -> P ->
+                                 // GEMM2 chain through two buffers is what binds (profiles/r2_phi_a_in_tmem.md)
 #endif
 constexpr int kSBufs = DUST_TC_SBUFS;
 enum { BAR_A = 0, BAR_XB_FULL = 1, BAR_XB_EMPTY = 5, BAR_VB_FULL = 9, BAR_VB_EMPTY = 13, BAR_S_FULL = 17, BAR_P_FULL = 20,
@@ -343,9 +388,11 @@ struct TcSegIter {
   }
 };
 
+// FAST: the row tile of GEMM1 in TMEM (TS form) and GEMM2's P_lo V term as kind::f16 on bf16 copies (tc_mode)
+template <bool FAST>
 __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const TcSmem L = tc_smem_layout(p.Dp, p.NV);
+  const TcSmem L = tc_smem_layout(p.Dp, p.NV, FAST, FAST);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.bars);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.tmem_slot);
   // the warp index as a value the compiler knows to be warp-uniform: the role branches below become uniform
@@ -355,7 +402,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   float* const oacc_cta = p.oacc + (size_t)blockIdx.x * p.max_seg * slot_stride;
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[BAR_A], p.a_tmem ? 4 : 1);   // TMEM: one arrival per flush warp; shared memory: the TMA transaction
+    mbar_init(&bars[BAR_A], FAST ? 4 : 1);   // TMEM: one arrival per flush warp; shared memory: the TMA transaction
     mbar_init(&bars[BAR_A_EMPTY], 1);
     for (int s = 0; s < kXbStages; ++s) { mbar_init(&bars[BAR_XB_FULL + s], 1); mbar_init(&bars[BAR_XB_EMPTY + s], 1); }
     for (int s = 0; s < kVbStages; ++s) { mbar_init(&bars[BAR_VB_FULL + s], 1); mbar_init(&bars[BAR_VB_EMPTY + s], 1); }
@@ -380,7 +427,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
-  const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + kSBufs * kTcBN, tO = tPlo + 2 * kTcBN;   // 192 + 128 + 2 NV <= 512
+  constexpr uint32_t plo_w = FAST ? kTcBN / 2 : kTcBN;      // TMEM columns of one P_lo buffer (two bf16 per column)
+  const uint32_t tS = tmem, tPhi = tmem, tPlo = tmem + kSBufs * kTcBN, tO = tPlo + 2 * plo_w;
   const uint32_t tAhi = tO + 2 * p.NV, tAlo = tAhi + p.Dp;                                       // a_tmem only
   // Ring stages, S/P buffers and O buffers are indexed by counters that run on ACROSS segments
   // (g: tiles, cg: flushed chunks), so the pipelines never drain at a row-tile boundary; only the
@@ -392,7 +440,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       const uint32_t a_bytes = kTcBM * p.Dp * 4;
       int g = 0;
       for (TcSegIter s(p); s.valid(); s.next()) {
-        if (!p.a_tmem) {
+        if (!FAST) {
           // the GEMM1s of the previous segment must have retired before their A operand is overwritten
           if (s.seg > 0) mbar_wait(&bars[BAR_A_EMPTY], (s.seg - 1) & 1);
           const long long arow = (long long)(p.row_begin / kTcBM + s.rt) * kTcBM * p.Dp;
@@ -423,6 +471,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
           bulk_g2s(vb, p.vb_hi + (long long)(s.j0 + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
           bulk_g2s(vb + L.vb_half, p.vb_lo + (long long)(s.j0 + j) * p.NV * kTcBN, L.vb_half, &bars[BAR_VB_FULL + sv]);
           bulk_g2s(vb + 2 * L.vb_half, p.xn + (long long)(s.j0 + j) * kTcBN, kTcBN * 4, &bars[BAR_VB_FULL + sv]);
+          if (FAST)
+            bulk_g2s(vb + 2 * L.vb_half + kTcBN * 4, reinterpret_cast<const unsigned char*>(p.vb_bf) + (long long)(s.j0 + j) * L.vb_bf_bytes,
+                     L.vb_bf_bytes, &bars[BAR_VB_FULL + sv]);
         }
       }
     }
@@ -453,7 +504,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         const uint32_t xh = loX0 + sx * xb_stage16, xl = xh + xb_half16;
         const uint32_t tSb = tS + b * kTcBN;
         if (elect_one_sync()) {
-          if (p.a_tmem) {
+          if (FAST) {
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk) {
               if (kk < ks1) {
@@ -485,8 +536,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
   } else if (warp == 2) {
     // ------------------------------ GEMM2 issuer (after the TMEM allocation above) ------
     // O[chunk & 1] (+)= P[g] V_g, tile by tile; first / last tile of a flush chunk open / close an O buffer
-    const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV);
+    const uint32_t idesc2 = make_idesc_tf32(kTcBM, p.NV), idesc2b = make_idesc_bf16(kTcBM, p.NV);
     const uint32_t sbo2 = (uint32_t)(kTcBN / 4) * 128u;    // 8-row group stride of the V^T tiles
+    const uint32_t sbo2b = (uint32_t)(kTcBN / 8) * 128u;   // ... of their bf16 copies (8 elements per core-matrix row)
+    const uint32_t hiVb = (uint32_t)(make_desc(0, 128, sbo2b) >> 32);
+    const uint32_t vb_bf16 = (2 * L.vb_half + kTcBN * 4) >> 4;   // the bf16 copy inside a V stage, in 16-byte units
     constexpr int ks2 = kTcBN / 8;
     const uint64_t dV = make_desc(smem_u32(smem + L.vb), 128, sbo2);
     const uint32_t hiV = (uint32_t)(dV >> 32), loV0 = (uint32_t)dV;
@@ -503,14 +557,27 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
         tc_fence_after();
         const uint32_t tOb = tO + ob * p.NV;
         const uint32_t vh = loV0 + sv * vb_stage16, vl = vh + vb_half16;
-        const uint32_t ph = tPhi + b3 * kTcBN, pl = tPlo + b * kTcBN;
+        const uint32_t ph = tPhi + b3 * kTcBN, pl = tPlo + b * plo_w;
         if (elect_one_sync()) {
+          if (FAST) {
 #pragma unroll
-          for (int kk = 0; kk < ks2; ++kk) {
-            const uint64_t bh = desc_lo_hi(vh + kk * 16, hiV), bl = desc_lo_hi(vl + kk * 16, hiV);
-            mma_ts(tOb, ph + kk * 8, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
-            mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
-            mma_ts(tOb, pl + kk * 8, bh, idesc2, 1u);
+            for (int kk = 0; kk < ks2; ++kk) {
+              const uint64_t bh = desc_lo_hi(vh + kk * 16, hiV), bl = desc_lo_hi(vl + kk * 16, hiV);
+              mma_ts(tOb, ph + kk * 8, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
+              mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
+            }
+            const uint32_t vbf = vh + vb_bf16;
+#pragma unroll
+            for (int kk = 0; kk < ks2 / 2; ++kk)     // 16 bf16 of K per instruction = two core matrices = 8 TMEM columns
+              mma_ts_f16(tOb, pl + kk * 8, desc_lo_hi(vbf + kk * 16, hiVb), idesc2b, 1u);
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < ks2; ++kk) {
+              const uint64_t bh = desc_lo_hi(vh + kk * 16, hiV), bl = desc_lo_hi(vl + kk * 16, hiV);
+              mma_ts(tOb, ph + kk * 8, bh, idesc2, (!first || kk > 0) ? 1u : 0u);
+              mma_ts(tOb, ph + kk * 8, bl, idesc2, 1u);
+              mma_ts(tOb, pl + kk * 8, bh, idesc2, 1u);
+            }
           }
           tc_commit(&bars[BAR_S_EMPTY + b3]);
           tc_commit(&bars[BAR_P_EMPTY + b]);
@@ -555,21 +622,33 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
           for (int c = 0; c < 32; ++c)
             if (c == (cdiag_all & 31)) r[c] = __float_as_uint(0.5f * (xnj[c] + xn_i));  // => d2 = 0
         }
+        // d2 = max((x_j - 2s) + x_i, 0) with 2s exact inside the fma; K = 2^(-g2 d2); hi = its TF32 part, lo = K - hi.
+        // Scalar on purpose: the same loop on the packed FP32 pipe (FFMA2 / FADD2 / FMUL2, 23 % fewer instructions)
+        // measured 13 % SLOWER -- 128 registers, loads of |x_j|^2 no longer hoisted, the softmax warps latency-bound
+        // (profiles/r2_phi_a_in_tmem.md, column 5).
+        uint32_t lo2[16];
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float sv_ = __uint_as_float(r[c]);
-          const float d2 = fmaxf((xnj[c] - 2.0f * sv_) + xn_i, 0.f);
+          const float d2 = fmaxf(fmaf(-2.0f, __uint_as_float(r[c]), xnj[c]) + xn_i, 0.f);
           const float kv = ex2_approx(-g2 * d2);
           ksum += kv;
           const float hi = tf32_hi(kv);
           r[c] = __float_as_uint(hi);
-          lo[c] = __float_as_uint(tf32_lo(kv, hi));
+          lo[c] = FAST ? __float_as_uint(kv - hi) : __float_as_uint(tf32_lo(kv, hi));
         }
         // P_hi overwrites the S columns it came from (this tile's own buffer); GEMM2(g-2) must be done with P_lo[b]
         mbar_wait(&bars[BAR_P_EMPTY + b], (it & 1) ^ 1);
         tc_fence_after();
         tmem_st32(tPhi + lane_base + b3 * kTcBN + half * 32, r);
-        tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
+        if (FAST) {
+          // two bf16 per TMEM column, the even element of a pair in the low half (the other order is 1.7e-4 off float64
+          // instead of 4e-6: measured, profiles/r2_run18.sh)
+#pragma unroll
+          for (int c = 0; c < 16; ++c) lo2[c] = pack_bf16x2(__uint_as_float(lo[2 * c]), __uint_as_float(lo[2 * c + 1]));
+          tmem_st16(tPlo + lane_base + b * plo_w + half * 16, lo2);
+        } else {
+          tmem_st32(tPlo + lane_base + b * kTcBN + half * 32, lo);
+        }
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -619,7 +698,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[BAR_A]);
     };
-    if (p.a_tmem) {
+    if (FAST) {
       TcSegIter s0(p);
       if (s0.valid()) stage_a(0, s0.rt);
     }
@@ -627,7 +706,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
       float* og = oacc_cta + (size_t)s.seg * slot_stride + row;
       const int n_chunks = (s.len + kTcChunk - 1) / kTcChunk;
       for (int ch = 0; ch < n_chunks; ++ch, ++cg) {
-        if (p.a_tmem && ch == n_chunks - 1) {
+        if (FAST && ch == n_chunks - 1) {
           TcSegIter nx = s;
           nx.next();
           if (nx.valid()) stage_a(nx.seg, nx.rt);
@@ -1234,15 +1313,29 @@ int median_tc_select(const dust_median_args* a, float* median_out, cudaStream_t 
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
+// Which form the kernel takes for a shape: (row tile in TMEM + bf16 P_lo term) when the TMEM columns
+// (S/P_hi ring, two P_lo buffers of 32, two O buffers, A_hi | A_lo) and the shared memory (no A, a bf16 V copy per
+// stage) allow it, else (row tile in shared memory + TF32 P_lo term).  mode < 0: neither fits.
+struct TcMode { int a_tmem, bf16lo; bool ok; };
+static TcMode tc_mode(int Dp, int NV) {
+  const size_t cap = 227 * 1024;
+  const bool fast_ok = DUST_TC_BF16LO && kSBufs * kTcBN + 2 * (kTcBN / 2) + 2 * NV + 2 * Dp <= 512 &&
+                       tc_smem_layout(Dp, NV, true, true).total <= cap;
+  if (fast_ok && !getenv("DUST_B200_TC_A_SMEM")) return TcMode{1, 1, true};
+  const bool plain_ok = (kSBufs + 2) * kTcBN + 2 * NV <= 512 && tc_smem_layout(Dp, NV, false, false).total <= cap;
+  return TcMode{0, 0, plain_ok};
+}
+
 bool phi_tc_supported(const dust_phi_args* a) {
   if (a->B != 1 || a->per_dim) return false;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : a->N;
   if (a->N % kTcBM || r0 % kTcBM || r1 % kTcBM || a->N < 1024) return false;
   const int Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
-  if ((kSBufs + 2) * kTcBN + 2 * NV > 512 || Dp > 64) return false;   // TMEM columns: S/P_hi ring, P_lo ring, two O buffers
-  return tc_smem_layout(Dp, NV).total <= 227 * 1024;
+  if (Dp > 64) return false;
+  return tc_mode(Dp, NV).ok;
 }
 
+// head (shared with the median pass): |x|^2, X images hi / lo; then V^T images hi / lo, their bf16 copy, the scratch
 size_t phi_tc_workspace(const dust_phi_args* a) {
   const size_t N = a->N, Dp = round_up(a->D, 8), NV = round_up(2 * a->D, 16);
   const int rows = (a->row_end > 0 ? a->row_end : a->N) - a->row_begin;
@@ -1250,7 +1343,7 @@ size_t phi_tc_workspace(const dust_phi_args* a) {
   const int n = tc_launch_plans(rows / kTcBM, a->N / kTcBN, pl);
   size_t slots = 0;
   for (int i = 0; i < n; ++i) slots += (size_t)pl[i].grid * pl[i].max_seg;
-  return sizeof(float) * (N * (2 * Dp + 2 * NV + 1) + 64 + slots * (NV + 2) * kTcBM);
+  return sizeof(float) * (N * (2 * Dp + 2 * NV + 1) + N * NV / 2 + 64 + slots * (NV + 2) * kTcBM);
 }
 
 int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
@@ -1263,22 +1356,26 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
   float* x_lo = ws;            ws += (size_t)N * Dp;
   float* vb_hi = ws;           ws += (size_t)N * NV;
   float* vb_lo = ws;           ws += (size_t)N * NV;
+  float* vb_bf = ws;           ws += (size_t)N * NV / 2;
   float* oacc = ws;
+  const TcMode mode = tc_mode(Dp, NV);
+  DUST_REQUIRE(mode.ok, DUST_ERR_UNSUPPORTED, "dust_svgd_phi: D=%d does not fit the tensor-core kernel", D);
   const int ld = a->ld > 0 ? a->ld : D;
-  int rc = tc_prep(a->x, a->score, N, D, ld, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream, a->x_prepared != 0);
+  int rc = tc_prep(a->x, a->score, N, D, ld, Dp, NV, x_hi, x_lo, vb_hi, vb_lo, xn, stream, a->x_prepared != 0, mode.bf16lo ? vb_bf : nullptr);
   if (rc != DUST_OK) return rc;
   const int r0 = a->row_begin, r1 = a->row_end > 0 ? a->row_end : N;
   const int row_tiles = (r1 - r0) / kTcBM;
   if (row_tiles == 0) return DUST_OK;
   TcParams p;
   p.N = N; p.D = D; p.Dp = Dp; p.NV = NV; p.T = N / kTcBN; p.row_begin = r0; p.ld = ld;
-  p.a_tmem = ((kSBufs + 2) * kTcBN + 2 * NV + 2 * Dp <= 512 && !getenv("DUST_B200_TC_A_SMEM")) ? 1 : 0;
+  p.a_tmem = mode.a_tmem; p.bf16lo = mode.bf16lo; p.vb_bf = vb_bf;
   // a 128-row tile and a 64-row tile of the core-matrix image are both whole 8-row groups in row order:
   // ONE image serves as the A operand (row tiles) and as the B operand (column tiles)
   p.xa_hi = x_hi; p.xa_lo = x_lo; p.xb_hi = x_hi; p.xb_lo = x_lo; p.vb_hi = vb_hi; p.vb_lo = vb_lo; p.xn = xn; p.x = a->x;
   p.gamma = a->gamma; p.c1 = a->c1; p.c2 = a->c2; p.gamma_dev = a->gamma_dev; p.lr = a->lr; p.phi = a->phi; p.x_out = a->x_out; p.oacc = oacc;
-  const TcSmem L = tc_smem_layout(Dp, NV);
-  DUST_CUDA_OK(cudaFuncSetAttribute(phi_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
+  const TcSmem L = tc_smem_layout(Dp, NV, mode.a_tmem != 0, mode.bf16lo != 0);
+  const bool fast = mode.a_tmem != 0;
+  DUST_CUDA_OK(cudaFuncSetAttribute(fast ? phi_tc_kernel<true> : phi_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total));
   TcPlan plans[2];
   const int n_plans = tc_launch_plans(row_tiles, p.T, plans);
   for (int i = 0; i < n_plans; ++i) {
@@ -1288,7 +1385,8 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
     p.R = pl.R; p.n_chunks = pl.n_chunks; p.chunk_w = pl.chunk_w; p.rem0 = pl.rem0; p.rem_w = pl.rem_w;
     {
       DUST_TIMED("phi_tc_kernel", stream);
-      phi_tc_kernel<<<pl.grid, kTcThreads, L.total, stream>>>(p);
+      if (fast) phi_tc_kernel<true><<<pl.grid, kTcThreads, L.total, stream>>>(p);
+      else phi_tc_kernel<false><<<pl.grid, kTcThreads, L.total, stream>>>(p);
     }
     DUST_LAUNCH_OK("phi_tc_kernel");
     {
@@ -1302,6 +1400,16 @@ int phi_tc(const dust_phi_args* a, cudaStream_t stream) {
 }
 
 }  // namespace dust
+
+// Which form of phi_tc_kernel a dimension D takes (no device needed): bit 0 = the row tile of GEMM1 lives in TMEM,
+// bit 1 = GEMM2's P_lo V correction term runs as kind::f16 on bf16 copies; -1 = D does not fit the tensor-core kernel.
+extern "C" int dust_phi_tc_mode(int32_t D) {
+  if (D <= 0) return -1;
+  const int Dp = dust::round_up(D, 8), NV = dust::round_up(2 * D, 16);
+  if (Dp > 64) return -1;
+  const dust::TcMode m = dust::tc_mode(Dp, NV);
+  return m.ok ? (m.a_tmem | (m.bf16lo << 1)) : -1;
+}
 
 // How dust_svgd_phi's tensor-core path partitions `row_tiles` x `col_tiles` tile pairs over its launches (no launch,
 // no device needed): plan[i] = {grid, R, n_chunks, chunk_w, rem0, rem_w, units_per_cta, total_units, max_seg,

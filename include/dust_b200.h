@@ -336,6 +336,11 @@ size_t dust_phi_workspace_bytes(const dust_phi_args* args);
  * the column chunk [(c / R) * chunk_w, +chunk_w); the others own equal contiguous ranges of the row-major numbered
  * left-over columns [rem0, rem0 + rem_w).  Returns the number of launches (<= 2).  Tests use it to prove coverage. */
 int dust_phi_tc_plan(int32_t row_tiles, int32_t col_tiles, int32_t plan[2][11]);
+/* Which form of the tensor-core kernel dimension D takes (no device needed): bit 0 = the row tile of the Gram GEMM
+ * lives in TMEM (TS form), bit 1 = the P_lo V correction term of the second GEMM runs as kind::f16 on bf16 copies
+ * (2^-11 of the sum carried with 16 mantissa bits); -1 = D does not fit (the SIMT kernel takes it).  bench_phi.py
+ * uses it to count the tensor work actually issued. */
+int dust_phi_tc_mode(int32_t D);
 int dust_svgd_phi(const dust_phi_args* args, void* stream);
 
 /* bandwidth -> (gamma,c1,c2) on the device, from the median written by dust_median_select:
