@@ -41,7 +41,7 @@ def parse():
     ap.add_argument("--no-phi", action="store_true", help="skip the large-N SVGD phi block (configs[3])")
     ap.add_argument("--no-configs", action="store_true", help="skip the demo / dual-stress block (configs[0], [1], [4])")
     ap.add_argument("--phi-steps", type=int, default=20)
-    ap.add_argument("--config-steps", type=int, default=10)
+    ap.add_argument("--config-steps", type=int, default=40)
     return ap.parse_args()
 
 
