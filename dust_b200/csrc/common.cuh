@@ -160,6 +160,24 @@ __device__ __forceinline__ void bulk_g2s_a(uint32_t dst, const void* src, uint32
                "r"(bytes), "r"(bar)
                : "memory");
 }
+// a wait that is allowed to be late (a warp that drains a buffer every few dozen tile times): sleeps between polls so
+// that its try_wait / branch pairs do not take issue slots from the warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t ns = 256) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t ok = 0;
+  for (uint32_t spin = 0; spin < kSpinCap; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(ns);
+  }
+  __trap();
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))

@@ -110,7 +110,8 @@ __global__ void __launch_bounds__(kPeerThreads) peer_push_kernel(PushParams p) {
     out[i] = a; out[i + kPeerThreads] = b; out[i + 2 * kPeerThreads] = c; out[i + 3 * kPeerThreads] = d;
   }
   for (; i < i1; i += kPeerThreads) out[i] = fetch(i);
-  __threadfence_system();             // this thread's remote stores, visible at the destination before anything later
+  // CTA barrier, then ONE system-scope fence by the thread that counts the CTA in: the barrier orders every thread's
+  // stores before it, the fence is cumulative (a fence per thread -- 150 000 of them -- held the kernel at 0.064 ms)
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence_system();

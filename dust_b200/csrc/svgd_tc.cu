@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) phi_tc_kernel(const TcParams p)
           if (nx.valid()) stage_a(nx.seg, nx.rt);
         }
         const int ob = cg & 1;
-        mbar_wait(&bars[BAR_O_FULL + ob], (cg >> 1) & 1);
+        mbar_wait_relaxed(&bars[BAR_O_FULL + ob], (cg >> 1) & 1);   // 32 tile times apart: do not spin on the softmax warps' scheduler
         tc_fence_after();
         for (int c0 = 0; c0 < p.NV; c0 += 16) {
           uint32_t r[16];

@@ -6,7 +6,7 @@ REPS = [("round 1: `svmpc_instance_kernel<pendulum,20,2>` (CTA tiles, accumulato
         ("round 2a: `svmpc_warp_kernel` (per-warp TMA tiles, accumulators in shared memory, pair/item tail)", "gpurun_out/fused_r2a.ncu-rep"),
         ("round 2b: + host-side coefficients (no FP64), one buffer per warp, templated fold", "gpurun_out/fused_r2b.ncu-rep"),
         ("round 2c: + packed terminal cost, MUFU soft-min weights, running tile pointer (fewer instructions, same duration: "
-         "the FMA-heavy pipe -- every packed FFMA2/FADD2/FMUL2 holds it two cycles -- and the issue slots bind)", "gpurun_out/fused_r2c.ncu-rep")]
+         "the FMA-heavy pipe -- every packed FFMA2/FADD2/FMUL2 holds it two cycles -- and the issue slots bind)", "gpurun_out/fused_r2c.ncu-rep")]  # fused_r2d.ncu-rep: the same kernel recaptured after common.cuh changed (traffic.json)
 KEYS = [("gpu__time_duration.sum", "duration (us, under ncu)"), ("smsp__inst_executed.sum", "warp instructions"),
         ("launch__registers_per_thread", "registers / thread"), ("launch__occupancy_limit_registers", "CTAs/SM (register limit)"),
         ("launch__occupancy_limit_shared_mem", "CTAs/SM (shared-memory limit)"), ("launch__shared_mem_per_block_dynamic", "dynamic smem / CTA (KB)"),

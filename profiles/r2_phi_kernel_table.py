@@ -8,9 +8,11 @@ REPS = [("round 2c: single issuing warp, row tile (A of GEMM1) in shared memory 
         ("round 2e: + two issuing warps (GEMM1 / GEMM2), S_EMPTY barrier", "gpurun_out/phi_r2e.ncu-rep"),
         ("round 2f: + GEMM2's P_lo V term as kind::f16 on bf16 copies (P_lo: 32 TMEM columns per buffer), S/P_hi ring of three", "gpurun_out/phi_r2f.ncu-rep"),
         ("round 2g (withdrawn): softmax loop on the packed FP32 pipe -- fewer instructions, 128 registers, latency-bound, slower", "gpurun_out/phi_r2g.ncu-rep"),
-        ("round 2h: scalar softmax loop with an explicit fma, kernel templated on its form (no runtime mode branches, no predicated-off duplicates)", "gpurun_out/phi_r2h.ncu-rep")]
+        ("round 2h: scalar softmax loop with an explicit fma, kernel templated on its form (no runtime mode branches, no predicated-off duplicates)", "gpurun_out/phi_r2h.ncu-rep"),
+        ("round 2i: + the flush warps sleep between polls of O_FULL (final)", "gpurun_out/phi_r2i.ncu-rep")]
 KEYS = [("gpu__time_duration.sum", "duration (ms, under ncu)"),
-        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe cycles active (%)"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "`sm__pipe_tensor_cycles_active` (% of elapsed)"),
+        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "the `TriageCompute ... realtime` variant of it (%; sampled, unstable)"),
         ("smsp__inst_executed.sum", "warp instructions"), ("launch__registers_per_thread", "registers / thread"),
         ("launch__shared_mem_per_block_dynamic", "dynamic smem / CTA (KB)"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active (%)"),
@@ -58,8 +60,10 @@ lines += ["",
           "GEMM2 warp back to waiting for P 37 % of its time.  (6) keeps the scalar loop, writes the fma explicitly (ptxas had emitted "
           "s + s, two adds), and templates the kernel on its form so that neither the TF32 split nor the other form's MMAs are issued "
           "predicated-off: 96 registers.",
-          "The `tensor pipe cycles active` counter is not a pure work counter: (4) does the same job in fewer tensor cycles AND less time, "
-          "and reads lower than (3); read it together with the duration row.",
+          "Two counters: `sm__pipe_tensor_cycles_active` (the one BASELINE names) is stable from capture to capture (86.1 / 86.4 % for the "
+          "identical kernels of (6) and (7)); the `TriageCompute ... realtime` variant that round 1 quoted (54 %) is sampled and is not "
+          "(80.4 vs 53.4 % for the same two captures): it is listed for continuity only.  Neither is a pure work counter -- (4) does the "
+          "same job in fewer tensor cycles AND less time -- so read them together with the duration row.",
           "Timed in `bench_phi.py` (steady state, power-capped clocks): 5.09 -> 4.70 -> 4.17 -> 3.85 -> (4.10) -> 3.53 ms of kernel per "
           "call, phi 5.05 -> 3.33 ms (`profiles/r2_bench_phi_run8.json`, `r2_bench_phi_run9_a_tmem_w1.json`, `r2_bench_phi_run10_w1.json`, "
           "`r2_bench_phi_run18_w1.json`, `r2_bench_phi_run19_w1.json`, `r2_bench_phi_run20_w1.json`); one rank's row block of 8: "
