@@ -92,6 +92,51 @@ def dual_step(cfg, p):
     return nxt
 
 
+def dual_step_inplace(cfg, p):
+    """`dual_step` with the controller's state held in PERSISTENT buffers (what a CUDA graph needs: `SvmpcCore` rebinds
+    theta / mix to fresh tensors every step, a captured graph would keep reading the old ones): the particles and the
+    mixture weights are pointed at the buffers before the step and copied back into them after it.  Steady state only
+    (the prior already aliases the particles)."""
+    core = p["core"]
+    if "theta_p" not in p:
+        p["theta_p"], p["mix_p"] = core.theta.clone(), core.mix.clone()
+    core.theta = core.mu = p["theta_p"]
+    core.mix = p["mix_p"]
+    nxt = dual_step(cfg, p)
+    p["theta_p"].copy_(core.theta)
+    p["mix_p"].copy_(core.mix)
+    core.theta = core.mu = p["theta_p"]
+    core.mix = p["mix_p"]
+    return nxt
+
+
+def graph_dual_step(cfg, p, steps, warmup):
+    """The same dual step captured ONCE into a CUDA graph and replayed (the C ABI allocates nothing and only enqueues on
+    the stream it is given, so its launches are capturable; torch's few helper kernels are captured with them).
+    -> {"device_ms_per_dual_step", "wall_ms_per_dual_step", "nodes"} or {"unavailable": why}."""
+    try:
+        from dust_b200.utils.graphs import CapturedStep
+
+        g = CapturedStep(lambda: dual_step_inplace(cfg, p)).graph
+        for _ in range(warmup):
+            g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return {"device_ms_per_dual_step": e0.elapsed_time(e1) / steps, "wall_ms_per_dual_step": (time.perf_counter() - w0) * 1e3 / steps,
+                "note": "one torch.cuda.CUDAGraph holding the control step, the plant step, the 20 MPF steps and the two copies that "
+                        "keep the controller state in persistent buffers; replayed (state evolves across replays: "
+                        "tests/test_gpu_round2.py::test_captured_control_step_replays_the_eager_sequence)"}
+    except Exception as exc:  # noqa: BLE001
+        torch.cuda.synchronize()
+        return {"unavailable": f"{type(exc).__name__}: {exc}"[:300]}
+
+
 def class_objects(name, dev, seed=0):
     """The reference-shaped objects of a demo configuration (demo/*_example.py), on the device."""
     import torch.distributions as dist
@@ -274,6 +319,7 @@ def configs_block(rank, world, dev, names=("pendulum_demo", "particle_demo", "du
             sync()
         if class_path and world == 1 and emulate_world == 1 and name != "dual_stress":
             line["drop_in_classes"] = time_class_path(name, dev, steps, warmup)
+            line["cuda_graph"] = graph_dual_step(cfg, p, steps, warmup)      # last: a failed capture must not disturb the rest
         out[name] = line
     if sampler:
         out["clocks"] = sampler.stop()

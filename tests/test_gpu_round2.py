@@ -603,3 +603,31 @@ def test_skid_steer_and_cartpole_step_on_device():
     assert e3 <= 2e-6 and e4 <= 2e-6, (e3, e4)
     assert rel_elem(got, ref, floor=1e-2) <= RTOL_COST and rel_elem(got_p, ref_p, floor=1e-2) <= RTOL_COST
     record_parity("skid-steer / cart-pole step", skid_default=e1, skid_sampled=e2, cartpole_default=e3, cartpole_sampled=e4)
+
+
+def test_captured_control_step_replays_the_eager_sequence():
+    """dust_b200.utils.graphs.CapturedStep: one dual control step of the pendulum demo shape (the cluster-kernel
+    control step, the plant step, 20 MPF steps; particle_example.py:177-207) captured into a CUDA graph with the
+    controller state in persistent buffers; k replays leave the policy particles, the mixture weights and the
+    parameter particles exactly where k eager steps leave them."""
+    from bench_configs import CONFIGS, build, dual_step, dual_step_inplace
+    from dust_b200.utils.graphs import CapturedStep
+
+    cfg = CONFIGS["pendulum_demo"]
+    dev = torch.device(DEV)
+    eager, graphed = build(cfg, dev, seed=4), build(cfg, dev, seed=4)
+    for q in (eager, graphed):
+        dual_step(cfg, q)                      # reach the steady state: the prior aliases the particles from here on
+    assert torch.equal(eager["core"].theta, graphed["core"].theta)
+    step = CapturedStep(lambda: dual_step_inplace(cfg, graphed), warmup=3)   # 3 eager steps; the capture pass runs nothing
+    for _ in range(3):
+        dual_step(cfg, eager)
+    assert torch.equal(eager["core"].theta, graphed["theta_p"])
+    for _ in range(4):
+        dual_step(cfg, eager)
+        step()
+    torch.cuda.synchronize()
+    assert torch.equal(eager["core"].theta, graphed["theta_p"])
+    assert torch.equal(eager["core"].mix, graphed["mix_p"])
+    assert torch.equal(eager["mpf_x"], graphed["mpf_x"])
+    assert not torch.equal(graphed["theta_p"], build(cfg, dev, seed=4)["core"].theta)
