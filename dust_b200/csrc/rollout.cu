@@ -247,6 +247,74 @@ __device__ __forceinline__ float2 pendulum_pair_cost_sum(const RolloutKParams& k
 }
 #endif
 
+#if DUST_PEND_PAIR
+// Two pairs per thread (rows A, B and C, D; all four of the same policy): the two packed chains are independent, so
+// the compiler interleaves them -- one chain's quadrant logic (ALU pipe) under the other's polynomials (FMA pipe).
+// Per trajectory the same instructions as pendulum_pair_cost_sum: bit-identical costs.
+__device__ __forceinline__ void pendulum_quad_cost_sum(const RolloutKParams& k, const float* __restrict__ const (&row)[4], long long inst,
+                                                       const int (&j)[4], const float* __restrict__ th_row, float sg0, float th0,
+                                                       float om0, float2 (&out)[2]) {
+  float2 csum[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+  const float2 sg = bc2(sg0);
+  for (int p = 0; p < k.P; ++p) {
+    PendulumCoef2 cf[2];
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      PendulumCoef ca, cb;
+      if (k.params) {
+        const int pa = k.interleaved ? (int)(((long long)p * k.SN + j[2 * q]) % k.P) : p;
+        const int pb = k.interleaved ? (int)(((long long)p * k.SN + j[2 * q + 1]) % k.P) : p;
+        const float* qa = k.params + (inst * k.P + pa) * 2;
+        const float* qb = k.params + (inst * k.P + pb) * 2;
+        ca = pendulum_coef_sampled(k.m, __ldg(qa), __ldg(qa + 1));
+        cb = (pb == pa) ? ca : pendulum_coef_sampled(k.m, __ldg(qb), __ldg(qb + 1));
+      } else {
+        ca = cb = pendulum_coef_default(k.m);
+      }
+      cf[q] = PendulumCoef2{make_float2(ca.c1, cb.c1), make_float2(ca.c2, cb.c2)};
+    }
+    float2 th[2] = {bc2(th0), bc2(th0)}, om[2] = {bc2(om0), bc2(om0)}, run[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    int t = 0;
+    for (; t + 4 <= k.H; t += 4) {
+      const float4 t4 = *reinterpret_cast<const float4*>(th_row + t);
+      float4 e[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e[r] = *reinterpret_cast<const float4*>(row[r] + t);
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 ea = e[2 * q], eb = e[2 * q + 1];
+        pendulum_step_pair(k.m, cf[q], th[q], om[q], add2(bc2(t4.x), mul2_unfused(sg, make_float2(ea.x, eb.x))), run[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 ea = e[2 * q], eb = e[2 * q + 1];
+        pendulum_step_pair(k.m, cf[q], th[q], om[q], add2(bc2(t4.y), mul2_unfused(sg, make_float2(ea.y, eb.y))), run[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 ea = e[2 * q], eb = e[2 * q + 1];
+        pendulum_step_pair(k.m, cf[q], th[q], om[q], add2(bc2(t4.z), mul2_unfused(sg, make_float2(ea.z, eb.z))), run[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const float4 ea = e[2 * q], eb = e[2 * q + 1];
+        pendulum_step_pair(k.m, cf[q], th[q], om[q], add2(bc2(t4.w), mul2_unfused(sg, make_float2(ea.w, eb.w))), run[q]);
+      }
+    }
+    for (; t < k.H; ++t) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+        pendulum_step_pair(k.m, cf[q], th[q], om[q],
+                           add2(bc2(th_row[t]), mul2_unfused(sg, make_float2(row[2 * q][t], row[2 * q + 1][t]))), run[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) csum[q] = add2(csum[q], add2(run[q], pendulum_cost_pair(k.m, th[q], om[q])));
+  }
+  out[0] = csum[0];
+  out[1] = csum[1];
+}
+#endif
+
 // |theta_t + pi| <= |theta_0| + t dt max_speed + pi: decided once per instance (uniform in the CTA)
 template <int MODEL>
 __device__ __forceinline__ bool small_angle_horizon(const RolloutKParams& k, long long inst) {
@@ -899,12 +967,13 @@ constexpr int kWarpKernelWarps = kWarpKernelThreads / 32;
 struct WarpKernelSmem {
   int stride, thst, tile_floats, off_tile, off_acc, off_th, off_tail, off_bar, total_bytes;
 };
-__host__ __device__ inline WarpKernelSmem warp_kernel_smem(int N, int HA) {
+// NP = pairs of trajectories per lane and tile (1: svmpc_warp_kernel, 2: svmpc_quad_kernel)
+__host__ __device__ inline WarpKernelSmem warp_kernel_smem(int N, int HA, int NP = 1) {
   WarpKernelSmem L;
   L.stride = padded_stride(HA);
   L.thst = (HA + 3) & ~3;
   const int La = (32 / N) * N;
-  L.tile_floats = 2 * La * L.stride;
+  L.tile_floats = 2 * NP * La * L.stride;
   // tail scratch (gl, sc, nw [N][thst]; Lg, Kx [N][N]; ll, lmix, logw, lse [N]; reductions 3 x [threads]) lives in
   // the tile buffers, which are dead once every warp has left the rollout loop
   const int tail = 3 * N * L.thst + 2 * N * N + 4 * N + 3 * kWarpKernelThreads;
@@ -943,6 +1012,69 @@ __device__ __forceinline__ void fold_score_rows(float* __restrict__ acc_row, con
   } else {
     for (int c = 0; c < HA; c += 4) chunk(c);
   }
+}
+
+// What follows the rollout loop of the warp kernels: the G = 4*La/N lanes that share a policy are combined (soft-min
+// statistics through shared memory, weighted score rows summed per policy), then -- dust_svmpc_step -- the tail.
+__device__ __forceinline__ void warp_kernel_finish(const RolloutKParams& k, const FusedOut& o, const WarpKernelSmem& L, float* smem,
+                                                   long long inst, int HA, int La, bool active, int slot, int n, float* acc_row,
+                                                   float* th_s, float m_run, float z_run, float c_run, float sg0) {
+  const int N = k.N, stride = L.stride, thst = L.thst, tid = threadIdx.x;
+  // ---- combine the G = 4*La/N lanes that share a policy -----------------------------------------------
+  float* tail_s = smem + L.off_tail;
+  float* gl_s = tail_s;                    // [N][thst] likelihood gradient
+  float* sc_s = gl_s + N * thst;           // [N][thst] score = grad_lik + grad_prior
+  float* nw_s = sc_s + N * thst;           // [N][thst] updated particles
+  float* Lg_s = nw_s + N * thst;           // [N][N] mixture logits / responsibilities
+  float* Kx_s = Lg_s + N * N;              // [N][N] kernel matrix among the particles
+  float* ll_s = Kx_s + N * N;              // [N] log-likelihood
+  float* lmix_s = ll_s + N;                // [N] log mixture weights
+  float* logw_s = lmix_s + N;              // [N]
+  float* lse_s = logw_s + N;               // [N]
+  float* red_m = lse_s + N;                // [threads]
+  float* red_z = red_m + kWarpKernelThreads;
+  float* red_c = red_z + kWarpKernelThreads;
+  const int TNT = kWarpKernelWarps * La;   // lanes that own trajectories
+  __syncthreads();                         // every warp is done with the tile ring: the scratch above may overwrite it
+  if (active) { red_m[slot] = m_run; red_c[slot] = c_run; }
+  __syncthreads();
+  const int G = TNT / N;
+  float m_n = INFINITY;
+  for (int g = 0; g < G; ++g) m_n = fminf(m_n, red_m[g * N + n]);
+  const float own = (active && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) : 0.f;
+  if (active) red_z[slot] = z_run * own;
+  __syncthreads();
+  float z_n = 0.f, c_n = 0.f;
+  for (int g = 0; g < G; ++g) z_n += red_z[g * N + n];
+  if (tid < N) {
+    for (int g = 0; g < G; ++g) c_n += red_c[g * N + n];
+    const float ll = (o.likelihood == DUST_LIK_EXP_UTILITY) ? (-o.alpha * m_n + logf(z_n)) - logf((float)k.S)   // likelihoods.py:133-135
+                                                            : -o.alpha * (c_n / (float)k.S);                    // likelihoods.py:119
+    if (o.log_lik) o.log_lik[inst * N + tid] = ll;
+    ll_s[tid] = ll;
+  }
+  if (o.grad_lik || o.tail.enabled) {
+    // (a - theta)/sigma^2 = eps/sigma: the factor 1/sigma is applied once per row here
+    const float f = (own / z_n) * ((1.0f / (sg0 * sg0)) * sg0);
+    if (active)
+      for (int c = 0; c < HA; c += 4) {
+        float4 v = *reinterpret_cast<float4*>(acc_row + c);
+        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
+        *reinterpret_cast<float4*>(acc_row + c) = v;
+      }
+    __syncthreads();
+    const float* accs = smem + L.off_acc;
+    for (int col = tid; col < N * HA; col += kWarpKernelThreads) {
+      const int n2 = col / HA, c = col - n2 * HA;
+      float sacc = 0.f;
+      for (int g = 0; g < G; ++g) sacc += accs[(g * N + n2) * stride + c];
+      if (o.grad_lik) o.grad_lik[inst * (long long)N * HA + col] = sacc;
+      gl_s[n2 * thst + c] = sacc;
+    }
+  }
+  if (!o.tail.enabled) return;
+
+  svmpc_tail(k, o.tail, inst, 1, th_s, thst, gl_s, ll_s, sc_s, nw_s, Lg_s, Kx_s, lmix_s, logw_s);
 }
 
 // HA4 = H*A/4 when it is a compile-time constant (the bench shape: 5), 0 = any multiple of 4 up to 32
@@ -1065,61 +1197,149 @@ __global__ void __launch_bounds__(kWarpKernelThreads, 7) svmpc_warp_kernel(const
     if (t + kWarpKernelWarps < ntiles) request();
   }
 
-  // ---- combine the G = 4*La/N lanes that share a policy -----------------------------------------------
-  float* tail_s = smem + L.off_tail;
-  float* gl_s = tail_s;                    // [N][thst] likelihood gradient
-  float* sc_s = gl_s + N * thst;           // [N][thst] score = grad_lik + grad_prior
-  float* nw_s = sc_s + N * thst;           // [N][thst] updated particles
-  float* Lg_s = nw_s + N * thst;           // [N][N] mixture logits / responsibilities
-  float* Kx_s = Lg_s + N * N;              // [N][N] kernel matrix among the particles
-  float* ll_s = Kx_s + N * N;              // [N] log-likelihood
-  float* lmix_s = ll_s + N;                // [N] log mixture weights
-  float* logw_s = lmix_s + N;              // [N]
-  float* lse_s = logw_s + N;               // [N]
-  float* red_m = lse_s + N;                // [threads]
-  float* red_z = red_m + kWarpKernelThreads;
-  float* red_c = red_z + kWarpKernelThreads;
-  const int TNT = kWarpKernelWarps * La;   // lanes that own trajectories
-  __syncthreads();                         // every warp is done with the tile ring: the scratch above may overwrite it
-  if (active) { red_m[slot] = m_run; red_c[slot] = c_run; }
-  __syncthreads();
-  const int G = TNT / N;
-  float m_n = INFINITY;
-  for (int g = 0; g < G; ++g) m_n = fminf(m_n, red_m[g * N + n]);
-  const float own = (active && m_run != INFINITY) ? expf(-o.alpha * (m_run - m_n)) : 0.f;
-  if (active) red_z[slot] = z_run * own;
-  __syncthreads();
-  float z_n = 0.f, c_n = 0.f;
-  for (int g = 0; g < G; ++g) z_n += red_z[g * N + n];
-  if (tid < N) {
-    for (int g = 0; g < G; ++g) c_n += red_c[g * N + n];
-    const float ll = (o.likelihood == DUST_LIK_EXP_UTILITY) ? (-o.alpha * m_n + logf(z_n)) - logf((float)k.S)   // likelihoods.py:133-135
-                                                            : -o.alpha * (c_n / (float)k.S);                    // likelihoods.py:119
-    if (o.log_lik) o.log_lik[inst * N + tid] = ll;
-    ll_s[tid] = ll;
-  }
-  if (o.grad_lik || o.tail.enabled) {
-    // (a - theta)/sigma^2 = eps/sigma: the factor 1/sigma is applied once per row here
-    const float f = (own / z_n) * ((1.0f / (sg0 * sg0)) * sg0);
-    if (active)
-      for (int c = 0; c < HA; c += 4) {
-        float4 v = *reinterpret_cast<float4*>(acc_row + c);
-        v.x *= f; v.y *= f; v.z *= f; v.w *= f;
-        *reinterpret_cast<float4*>(acc_row + c) = v;
-      }
-    __syncthreads();
-    const float* accs = smem + L.off_acc;
-    for (int col = tid; col < N * HA; col += kWarpKernelThreads) {
-      const int n2 = col / HA, c = col - n2 * HA;
-      float sacc = 0.f;
-      for (int g = 0; g < G; ++g) sacc += accs[(g * N + n2) * stride + c];
-      if (o.grad_lik) o.grad_lik[inst * (long long)N * HA + col] = sacc;
-      gl_s[n2 * thst + c] = sacc;
-    }
-  }
-  if (!o.tail.enabled) return;
+  warp_kernel_finish(k, o, L, smem, inst, HA, La, active, slot, n, acc_row, th_s, m_run, z_run, c_run, sg0);
+}
 
-  svmpc_tail(k, o.tail, inst, 1, th_s, thst, gl_s, ll_s, sc_s, nw_s, Lg_s, Kx_s, lmix_s, logw_s);
+// acc <- acc * scale + sum_r e[r] * row[r] over one score row: the four trajectories of a lane at once (packed pipe)
+template <int HA4>
+__device__ __forceinline__ void fold_score_rows4(float* __restrict__ acc_row, const float* __restrict__ const (&row)[4], float scale,
+                                                 const float (&e)[4], int HA) {
+  const float2 sc2 = bc2(scale), e0 = bc2(e[0]), e1 = bc2(e[1]), e2 = bc2(e[2]), e3 = bc2(e[3]);
+  auto chunk = [&](int c) {
+    const float4 a4 = *reinterpret_cast<const float4*>(acc_row + c);
+    const float4 v0 = *reinterpret_cast<const float4*>(row[0] + c), v1 = *reinterpret_cast<const float4*>(row[1] + c);
+    const float4 v2 = *reinterpret_cast<const float4*>(row[2] + c), v3 = *reinterpret_cast<const float4*>(row[3] + c);
+    float2 lo = fma2(e0, make_float2(v0.x, v0.y), mul2(e1, make_float2(v1.x, v1.y)));
+    float2 hi = fma2(e0, make_float2(v0.z, v0.w), mul2(e1, make_float2(v1.z, v1.w)));
+    lo = fma2(e2, make_float2(v2.x, v2.y), lo);
+    hi = fma2(e2, make_float2(v2.z, v2.w), hi);
+    lo = fma2(e3, make_float2(v3.x, v3.y), lo);
+    hi = fma2(e3, make_float2(v3.z, v3.w), hi);
+    lo = fma2(make_float2(a4.x, a4.y), sc2, lo);
+    hi = fma2(make_float2(a4.z, a4.w), sc2, hi);
+    *reinterpret_cast<float4*>(acc_row + c) = make_float4(lo.x, lo.y, hi.x, hi.y);
+  };
+  if (HA4 > 0) {
+#pragma unroll
+    for (int c4 = 0; c4 < HA4; ++c4) chunk(4 * c4);
+  } else {
+    for (int c = 0; c < HA; c += 4) chunk(c);
+  }
+}
+
+// Two pairs per lane: tiles of 4 * La rows, 16 warps per SM with two independent packed chains each (the per-tile
+// overhead -- barrier wait, request, exponentials, fold -- is shared by four trajectories).  Host guarantees
+// S*N % (4 * La) == 0 (no ragged tile).  An experiment that lost (see the launch site); opt-in with DUST_B200_QUAD=1.
+template <int HA4>
+__global__ void __launch_bounds__(kWarpKernelThreads, 4) svmpc_quad_kernel(const RolloutKParams k, const FusedOut o) {
+  extern __shared__ __align__(16) float smem[];
+  const int HA = HA4 > 0 ? 4 * HA4 : k.HA, N = k.N;
+  const WarpKernelSmem L = warp_kernel_smem(N, HA, 2);
+  const int stride = L.stride, thst = L.thst;
+  const int La = (32 / N) * N, WT = 4 * La;
+  float* th_s = smem + L.off_th;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+  const long long inst = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool active = lane < La;
+  const int slot = warp * La + lane;
+  const int n = lane % N;
+  float* acc_row = smem + L.off_acc + (active ? slot : 0) * stride;
+  const int ntiles = k.SN / WT;
+  float* const my_tile = smem + L.off_tile + warp * L.tile_floats;
+  uint64_t* const my_bar = &full_bar[warp];
+  const uint32_t bar_a = smem_u32(my_bar), tile_a = smem_u32(my_tile);
+  const float* row[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) row[r] = my_tile + (lane + r * La) * stride;
+  const uint32_t tile_bytes = (uint32_t)WT * (uint32_t)HA * 4u;
+  const bool bulk = stride == HA;
+  const float* __restrict__ next_src = k.noise + (inst * (long long)k.SN + (long long)warp * WT) * HA;
+
+  auto request = [&]() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (bulk) {
+      if (lane == 0) {
+        mbar_expect_tx_a(bar_a, tile_bytes);
+        bulk_g2s_a(tile_a, next_src, tile_bytes, bar_a);
+      }
+    } else {
+      if (lane == 0) mbar_expect_tx_a(bar_a, tile_bytes);
+      __syncwarp();
+      for (int r = lane; r < WT; r += 32) bulk_g2s_a(tile_a + (uint32_t)(r * stride) * 4u, next_src + (long long)r * HA, (uint32_t)HA * 4u, bar_a);
+    }
+    next_src += (long long)kWarpKernelWarps * WT * HA;
+  };
+  if (lane == 0) {
+    mbar_init(my_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  if (warp < ntiles) request();
+  for (int e = tid; e < N * HA; e += kWarpKernelThreads) {
+    const int nn = e / HA;
+    th_s[nn * thst + (e - nn * HA)] = k.theta[inst * (long long)N * HA + e];
+  }
+  if (active)
+    for (int c = 0; c < stride; c += 4) *reinterpret_cast<float4*>(acc_row + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float sg0 = k.sigma[0];
+  const float th0 = __ldg(k.state0 + inst * 2), om0 = __ldg(k.state0 + inst * 2 + 1);
+  const bool small = small_angle_horizon<DUST_MODEL_PENDULUM>(k, inst);
+  const float* __restrict__ th_row = th_s + n * thst;
+  const bool want_costs = o.costs != nullptr;
+  uintptr_t cost_ptr = reinterpret_cast<uintptr_t>(o.costs) + sizeof(float) * (size_t)(inst * k.SN + warp * WT + lane);
+  __syncthreads();
+
+  float m_run = INFINITY, z_run = 0.f, c_run = 0.f;
+  uint32_t parity = 0;
+  const float nal2 = -o.alpha * 1.4426950408889634f;
+  for (int t = warp; t < ntiles; t += kWarpKernelWarps) {
+    const int j0 = t * WT;
+    mbar_wait_a(bar_a, parity);
+    parity ^= 1u;
+    if (active) {
+      float cost[4];
+      if (small) {
+        const int j[4] = {j0 + lane, j0 + lane + La, j0 + lane + 2 * La, j0 + lane + 3 * La};
+        float2 cs[2];
+        pendulum_quad_cost_sum(k, row, inst, j, th_row, sg0, th0, om0, cs);
+        cost[0] = cs[0].x; cost[1] = cs[0].y; cost[2] = cs[1].x; cost[3] = cs[1].y;
+      } else {
+        // an angle beyond the fast range: the scalar step, one copy of the code (no dynamic indexing of row[] / cost[]:
+        // the arrays must stay in registers)
+        cost[0] = cost[1] = cost[2] = cost[3] = 0.f;
+#pragma unroll 1
+        for (int r = 0; r < 4; ++r) {
+          const float v = trajectory_cost_sum<DUST_MODEL_PENDULUM, false, false, true>(k, my_tile + (lane + r * La) * stride, nullptr, inst,
+                                                                                      j0 + lane + r * La, 0, k.P, th_row, sg0, sg0);
+          if (r == 0) cost[0] = v; else if (r == 1) cost[1] = v; else if (r == 2) cost[2] = v; else cost[3] = v;
+        }
+      }
+      if (k.P != 1) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cost[r] = cost[r] / (float)k.P;
+      }
+      if (want_costs) {
+        float* cp = reinterpret_cast<float*>(cost_ptr);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) cp[r * La] = cost[r];
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r) c_run += cost[r];
+      const float m_new = fminf(fminf(m_run, fminf(cost[0], cost[1])), fminf(cost[2], cost[3]));
+      const float scale = exp2_fast(nal2 * (m_run - m_new));
+      float e[4];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) e[r] = exp2_fast(nal2 * (cost[r] - m_new));
+      m_run = m_new;
+      z_run = z_run * scale + ((e[0] + e[1]) + (e[2] + e[3]));
+      if (scale != 1.f || fmaxf(fmaxf(e[0], e[1]), fmaxf(e[2], e[3])) > 1e-30f) fold_score_rows4<HA4>(acc_row, row, scale, e, HA);
+    }
+    cost_ptr += sizeof(float) * (size_t)(kWarpKernelWarps * WT);
+    __syncwarp();
+    if (t + kWarpKernelWarps < ntiles) request();
+  }
+  warp_kernel_finish(k, o, L, smem, inst, HA, La, active, slot, n, acc_row, th_s, m_run, z_run, c_run, sg0);
 }
 #endif
 
@@ -1693,6 +1913,25 @@ static int rollout_cost_impl(const dust_rollout_args* a, const TailParams* tail,
     // forces the first one (A/B measurements)
     static const bool force_v1 = getenv("DUST_B200_FUSED_V1") != nullptr || getenv("DUST_B200_NO_PAIR") != nullptr;
     if (kind == DUST_MODEL_PENDULUM && !force_v1 && (k.HA & 3) == 0 && a->N <= 32 && ((((uintptr_t)a->noise) & 15) == 0)) {
+      // DUST_B200_QUAD=1: two pairs per lane (svmpc_quad_kernel; needs tiles without a ragged end).  Measured 3 % SLOWER
+      // than one pair per lane at the bench shape (0.320 vs 0.309 ms: 16 warps/SM with two chains each lose to 28 with
+      // one, profiles/r2_instance_kernel_ncu.md) -- kept as an A/B build of the same arithmetic, off by default.
+      const bool use_quad = getenv("DUST_B200_QUAD") != nullptr;   // read per call: the tests toggle it
+      const int La_h = (32 / a->N) * a->N;
+      const WarpKernelSmem Lq = warp_kernel_smem(a->N, k.HA, 2);
+      if (use_quad && k.SN % (4 * La_h) == 0 && Lq.total_bytes <= 227 * 1024) {
+#define DUST_QUAD_KERNEL(HA4)                                                                                              \
+  do {                                                                                                                     \
+    if (Lq.total_bytes > 48 * 1024)                                                                                        \
+      DUST_CUDA_OK(cudaFuncSetAttribute(svmpc_quad_kernel<HA4>, cudaFuncAttributeMaxDynamicSharedMemorySize, Lq.total_bytes)); \
+    { DUST_TIMED("svmpc_instance_kernel", stream); svmpc_quad_kernel<HA4><<<a->B, kWarpKernelThreads, Lq.total_bytes, stream>>>(k, o); } \
+  } while (0)
+        if (k.HA == 20) DUST_QUAD_KERNEL(5);
+        else DUST_QUAD_KERNEL(0);
+#undef DUST_QUAD_KERNEL
+        DUST_LAUNCH_OK("svmpc_instance_kernel");
+        return DUST_OK;
+      }
       const WarpKernelSmem Lw = warp_kernel_smem(a->N, k.HA);
       if (Lw.total_bytes <= 227 * 1024) {
 #define DUST_WARP_KERNEL(HA4)                                                                                              \

@@ -6,7 +6,9 @@ REPS = [("round 1: `svmpc_instance_kernel<pendulum,20,2>` (CTA tiles, accumulato
         ("round 2a: `svmpc_warp_kernel` (per-warp TMA tiles, accumulators in shared memory, pair/item tail)", "gpurun_out/fused_r2a.ncu-rep"),
         ("round 2b: + host-side coefficients (no FP64), one buffer per warp, templated fold", "gpurun_out/fused_r2b.ncu-rep"),
         ("round 2c: + packed terminal cost, MUFU soft-min weights, running tile pointer (fewer instructions, same duration: "
-         "the FMA-heavy pipe -- every packed FFMA2/FADD2/FMUL2 holds it two cycles -- and the issue slots bind)", "gpurun_out/fused_r2c.ncu-rep")]  # fused_r2d.ncu-rep: the same kernel recaptured after common.cuh changed (traffic.json)
+         "the FMA-heavy pipe -- every packed FFMA2/FADD2/FMUL2 holds it two cycles -- and the issue slots bind)", "gpurun_out/fused_r2c.ncu-rep"),
+        ("round 2e (off by default, DUST_B200_QUAD=1): `svmpc_quad_kernel`, two pairs per lane, 4 CTAs/SM -- fewer instructions, two "
+         "independent chains per warp, and slower: 0.320 vs 0.309 ms in the same bench run (`r2_bench_run25_quad/pair.json`)", "gpurun_out/fused_r2e.ncu-rep")]  # fused_r2d.ncu-rep: the same kernel recaptured after common.cuh changed (traffic.json)
 KEYS = [("gpu__time_duration.sum", "duration (us, under ncu)"), ("smsp__inst_executed.sum", "warp instructions"),
         ("launch__registers_per_thread", "registers / thread"), ("launch__occupancy_limit_registers", "CTAs/SM (register limit)"),
         ("launch__occupancy_limit_shared_mem", "CTAs/SM (shared-memory limit)"), ("launch__shared_mem_per_block_dynamic", "dynamic smem / CTA (KB)"),

@@ -631,3 +631,43 @@ def test_captured_control_step_replays_the_eager_sequence():
     assert torch.equal(eager["core"].mix, graphed["mix_p"])
     assert torch.equal(eager["mpf_x"], graphed["mpf_x"])
     assert not torch.equal(graphed["theta_p"], build(cfg, dev, seed=4)["core"].theta)
+
+
+def test_two_pairs_per_lane_kernel_equals_the_default():
+    """svmpc_quad_kernel (DUST_B200_QUAD=1; an A/B build of the batched pendulum step with two trajectory pairs per
+    lane, disco.py:139-209 + svmpc.py:46-54 in one launch): costs bit-equal to the default kernel, likelihood and its
+    gradient to summation order."""
+    import os
+
+    from dust_b200 import _lib as L
+    from dust_b200 import ops
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    dev = torch.device(DEV)
+    spec = PendulumModel().device_spec(inst_cost, term_cost, dev)
+    B, N, S, H = 80, 8, 64, 20                   # S*N = 512 rows = 4 tiles of 128: no ragged tile
+    g = torch.Generator().manual_seed(7)
+    theta = cu(torch.randn(B, N, H, 1, generator=g) * 2)
+    eps = cu(torch.randn(B, S, N, H, 1, generator=g))
+    state = cu((torch.rand(B, 2, generator=g) * 2 - 1) * torch.tensor([3.0, 1.0]))
+    sigma = cu(torch.tensor([2.0]))
+    kw = dict(theta=theta, sigma=sigma, alpha=1.0, want=("costs", "log_lik", "grad_lik"))
+    lib = L.load()
+
+    def run():
+        lib.dust_profiler_reset(); lib.dust_profiler_enable(1)
+        out = ops.rollout_cost(spec, state, eps, **kw)
+        prof = L.profiler_report()
+        lib.dust_profiler_enable(0)
+        assert list(prof) == ["svmpc_instance_kernel"], prof
+        return {k: v.clone() for k, v in out.items() if v is not None}
+
+    ref = run()
+    os.environ["DUST_B200_QUAD"] = "1"
+    try:
+        quad = run()
+    finally:
+        del os.environ["DUST_B200_QUAD"]
+    assert torch.equal(quad["costs"], ref["costs"])
+    assert rel_max(quad["log_lik"].cpu(), ref["log_lik"].cpu()) <= 1e-6
+    assert rel_max(quad["grad_lik"].cpu(), ref["grad_lik"].cpu()) <= 1e-5
