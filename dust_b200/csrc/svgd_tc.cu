@@ -975,17 +975,19 @@ struct MedTcParams {
   int xb_stages;                     // operand ring depth (<= kMedXbStages), as many as fit beside the hit queues
   int kcount, kchunk;                // circular half band: T/2 + 1 column tiles per row tile, kchunk of them per CTA
   const float *xa_hi, *xa_lo, *xb_hi, *xb_lo, *xn;
+  const float* x;                    // the particles themselves (row stride ld): the row tile is staged in TMEM from them
+  int D, ld;
   const uint32_t* state;             // [0] window start
   unsigned long long* hist;          // [kMedWindowBins] window histogram, then [kMedWindowBins] = count below
 };
 
 enum { MB_A = 0, MB_XB_FULL = 1, MB_XB_EMPTY = 7, MB_XN_FULL = 13, MB_XN_EMPTY = 29, MB_S_FULL = 45, MB_S_EMPTY = 51, MB_COUNT = 57 };
 
-// A operand (hi, lo), operand ring, |x_j|^2 ring, barriers + TMEM slot, then the consumers' hit queues: 32 window
-// hits per thread (one per element of a 32-column half), interleaved by thread
+// operand ring, |x_j|^2 ring, barriers + TMEM slot, then the consumers' hit queues: 32 window hits per thread (one per
+// element of a 32-column half), interleaved by thread.  The row tile (A operand) lives in TMEM behind the S ring
+// (6 x 64 + 2 Dp <= 512 columns): as in phi_tc_kernel, an SS-form MMA would fetch 6 KB per 32 cycles from shared memory.
 __host__ __device__ inline size_t med_smem_bytes(int Dp, int stages) {
-  return (size_t)2 * kTcBM * Dp * 4 + (size_t)stages * 2 * kTcBN * Dp * 4 + (size_t)kXnStages * kTcBN * 4 + 64 * 8 + 64 +
-         (size_t)kMedConsumers * 32 * 4;
+  return (size_t)stages * 2 * kTcBN * Dp * 4 + (size_t)kXnStages * kTcBN * 4 + 64 * 8 + 64 + (size_t)kMedConsumers * 32 * 4;
 }
 __host__ __device__ inline int med_xb_stages(int Dp) {
   for (int s = kMedXbStages; s >= 3; --s)
@@ -995,8 +997,8 @@ __host__ __device__ inline int med_xb_stages(int Dp) {
 
 __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t a_bytes = kTcBM * p.Dp * 4, xb_half = kTcBN * p.Dp * 4, xb_stage = 2 * xb_half;
-  const uint32_t off_a_hi = 0, off_a_lo = a_bytes, off_xb = 2 * a_bytes;
+  const uint32_t xb_half = kTcBN * p.Dp * 4, xb_stage = 2 * xb_half;
+  const uint32_t off_xb = 0;
   const int nstage = p.xb_stages;
   const uint32_t off_xn = off_xb + nstage * xb_stage;
   const uint32_t off_bars = (off_xn + kXnStages * kTcBN * 4 + 7) & ~7u;
@@ -1019,7 +1021,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
   auto col_tile = [&](int j) { return (kBlk * itile + kbase + j) % p.T; };
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[MB_A], 1);
+    mbar_init(&bars[MB_A], 4);       // the four warps of consumer group 0 stage the row tile in TMEM
     for (int s = 0; s < kMedXbStages; ++s) { mbar_init(&bars[MB_XB_FULL + s], 1); mbar_init(&bars[MB_XB_EMPTY + s], 1); }   // nstage of them are used
     // the |x_j|^2 slices ride in their own deep ring, recycled by the 4 consumer warps of a tile, so an
     // operand stage is free as soon as its MMAs retire
@@ -1036,13 +1038,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const uint32_t tAhi = tmem + kMedSBufs * kTcBN, tAlo = tAhi + p.Dp;
 
   if (warp == 0) {
     if (lane == 0 && T > 0) {
-      const long long arow = (long long)(i0 / kTcBM) * kTcBM * p.Dp;
-      mbar_expect_tx(&bars[MB_A], 2 * a_bytes);
-      bulk_g2s(smem + off_a_hi, p.xa_hi + arow, a_bytes, &bars[MB_A]);
-      bulk_g2s(smem + off_a_lo, p.xa_lo + arow, a_bytes, &bars[MB_A]);
       for (int j = 0; j < T; ++j) {
         const int sx = j % nstage, sn = j % kXnStages;
         mbar_wait(&bars[MB_XB_EMPTY + sx], ((j / nstage) & 1) ^ 1);
@@ -1061,9 +1060,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
       const uint32_t idesc1 = make_idesc_tf32(kTcBM, kTcBN);
       const uint32_t sbo1 = (uint32_t)(p.Dp / 4) * 128u;
       const int ks1 = p.Dp / 8;
-      const uint64_t dA = make_desc(smem_u32(smem + off_a_hi), 128, sbo1), dX = make_desc(smem_u32(smem + off_xb), 128, sbo1);
-      const uint32_t hiA = (uint32_t)(dA >> 32);
-      const uint32_t loA_hi = (uint32_t)dA, loA_lo = loA_hi + (a_bytes >> 4), loX0 = (uint32_t)dX;
+      const uint64_t dX = make_desc(smem_u32(smem + off_xb), 128, sbo1);
+      const uint32_t hiA = (uint32_t)(dX >> 32), loX0 = (uint32_t)dX;
       const uint32_t xb_stage16 = xb_stage >> 4, xb_half16 = xb_half >> 4;
       if (T > 0) mbar_wait(&bars[MB_A], 0);
       for (int j = 0; j < T; ++j) {
@@ -1077,11 +1075,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk) {
             if (kk < ks1) {
-              const uint64_t ah = desc_lo_hi(loA_hi + kk * 16, hiA), al = desc_lo_hi(loA_lo + kk * 16, hiA);
               const uint64_t bh = desc_lo_hi(xh + kk * 16, hiA), bl = desc_lo_hi(xl + kk * 16, hiA);
-              mma_ss(tSb, ah, bh, idesc1, kk > 0 ? 1u : 0u);
-              mma_ss(tSb, ah, bl, idesc1, 1u);
-              mma_ss(tSb, al, bh, idesc1, 1u);
+              mma_ts(tSb, tAhi + kk * 8, bh, idesc1, kk > 0 ? 1u : 0u);
+              mma_ts(tSb, tAhi + kk * 8, bl, idesc1, 1u);
+              mma_ts(tSb, tAlo + kk * 8, bh, idesc1, 1u);
             }
           }
           tc_commit(&bars[MB_S_FULL + b]);
@@ -1101,6 +1098,34 @@ __global__ void __launch_bounds__(kTcThreads, 1) median_tc_kernel(const MedTcPar
     const uint32_t win_lo = p.state[0], win_n = p.state[2];
     // this thread's hit queue: entry i at hitq[i * kMedConsumers + consumer index] (conflict-free across a warp)
     const uint32_t q0 = smem_u32(smem + off_hitq) + (uint32_t)(threadIdx.x - 128) * 4u;
+    if (wg == 0 && T > 0) {
+      // stage the row tile: thread <-> row, the hi / lo TF32 split of its Dp values (the bits tc_prep_kernel writes)
+      const float* __restrict__ xr = p.x + (long long)(i0 + row) * p.ld;
+      const bool vec = (p.D & 3) == 0 && (p.ld & 3) == 0 && ((((uintptr_t)p.x) & 15) == 0);
+      for (int k0 = 0; k0 < p.Dp; k0 += 8) {
+        float v[8];
+        if (vec && k0 + 8 <= p.D) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(xr + k0)), a1 = __ldg(reinterpret_cast<const float4*>(xr + k0 + 4));
+          v[0] = a0.x; v[1] = a0.y; v[2] = a0.z; v[3] = a0.w; v[4] = a1.x; v[5] = a1.y; v[6] = a1.z; v[7] = a1.w;
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) v[c] = (k0 + c < p.D) ? __ldg(xr + k0 + c) : 0.f;
+        }
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float h = tf32_hi(v[c]);
+          hi[c] = __float_as_uint(h);
+          lo[c] = __float_as_uint(tf32_lo(v[c], h));
+        }
+        tmem_st8(tAhi + lane_base + k0, hi);
+        tmem_st8(tAlo + lane_base + k0, lo);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[MB_A]);
+    }
     unsigned int below = 0;
     for (int j = wg; j < T; j += 3) {
       const int b = j % kMedSBufs, sn = j % kXnStages;
@@ -1288,7 +1313,8 @@ int median_tc_count(const dust_median_args* a, void* workspace, cudaStream_t str
     if (cost < best_cost - 1e-9) { best_cost = cost; ksplit = ks; kchunk = chunk; }
   }
   const int stages = med_xb_stages(Dp);
-  MedTcParams p{N, Dp, T, r0, ksplit, stages, kcount, kchunk, x_hi, x_lo, x_hi, x_lo, xn, a->selected + 4, a->hist};
+  MedTcParams p{N, Dp, T, r0, ksplit, stages, kcount, kchunk, x_hi, x_lo, x_hi, x_lo, xn, a->x, a->D, a->ld > 0 ? a->ld : a->D,
+                a->selected + 4, a->hist};
   const size_t smem = med_smem_bytes(Dp, stages);
   DUST_CUDA_OK(cudaFuncSetAttribute(median_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   {

@@ -5,9 +5,10 @@ import subprocess
 
 REPS = [("round 1: per-element `setp` + predicated `red.global.u64`", "gpurun_out/tc_r4.ncu-rep"),
         ("round 2c: window hits queued per thread in shared memory, 64-bit reductions for the hits only (carry-chain below counter)", "gpurun_out/median_r2c.ncu-rep"),
-        ("round 2d: distances two at a time (FFMA2 / FADD2), four IMAD.HI below counters, |x_j|^2 as float4", "gpurun_out/median_r2d.ncu-rep")]
+        ("round 2d: distances two at a time (FFMA2 / FADD2), four IMAD.HI below counters, |x_j|^2 as float4", "gpurun_out/median_r2d.ncu-rep"),
+        ("round 2e: the row tile staged in TMEM by the first consumer warpgroup, TS-form GEMM1 (as in phi_tc_kernel)", "gpurun_out/median_r2e.ncu-rep")]
 KEYS = [("gpu__time_duration.sum", "duration (ms, under ncu)"),
-        ("TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed", "tensor pipe cycles active (%)"),
+        ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "`sm__pipe_tensor_cycles_active` (% of elapsed)"),
         ("smsp__inst_executed.sum", "warp instructions"), ("launch__registers_per_thread", "registers / thread"),
         ("launch__shared_mem_per_block_dynamic", "dynamic smem / CTA (KB)"),
         ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue active (%)"),
@@ -30,9 +31,12 @@ lines.append("| thread instructions per distance (all warps) | " + " | ".join(f"
 lines.append("| SM cycles per 128 x 64 tile (1965 MHz; GEMM1 floor 15 x 32 = 480, 720 with A and B from shared memory) | " + " | ".join(
     f"{float(d['gpu__time_duration.sum']) * 1e-3 * 1.965e9 / (512 * 1026 / 148):.0f}" for _, d, _ in cols) + " |")
 lines += [""] + [f"({i + 1}) {t}  [`{r}`]" for i, (t, _, r) in enumerate(cols)]
-lines += ["", "The consumer loop of (3) is 270 instructions per 32 distances (`--page source`): IMAD 54, ISETP 35, FMNMX 32, predicated STS 32, "
+lines += ["", "In (3) the consumers waited for S 23 % of their time while the issuing warp never waited for a free S buffer: the SS-form GEMM1 "
+          "(720 cycles per tile: 6 KB of operands per MMA through the 128 B/cycle shared-memory port) was the limit.  (4) reads the row tile "
+          "from TMEM: 1.44 -> 1.31 ms; what binds now is the consumers' issue rate.", "",
+          "The consumer loop of (3) is 270 instructions per 32 distances (`--page source`): IMAD 54, ISETP 35, FMNMX 32, predicated STS 32, "
           "LEA + VIADD + IADD3 62 (window position, queue pointer), FFMA2 16, FADD2 16, LDS.128 8.  At ~800 cycles per tile the three consumer "
-          "warpgroups (one warp-tile of ~600 instructions per scheduler) and the SS-form GEMM1 (720 cycles) are in balance: going further needs "
-          "both the row tile in TMEM, as in `phi_tc_kernel`, and fewer integer instructions per distance."]
+          "warpgroups (one warp-tile of ~600 instructions per scheduler) and the SS-form GEMM1 (720 cycles) were in balance; with the row tile "
+          "in TMEM the next step is fewer integer instructions per distance."]
 open("profiles/r2_median_kernel_ncu.md", "w").write("\n".join(lines) + "\n")
 print("\n".join(lines))

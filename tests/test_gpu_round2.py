@@ -92,7 +92,7 @@ def test_phi_and_median_at_65536(cloud):
 
 
 @pytest.mark.parametrize("N,D,rows", [(8192, 40, None), (8192, 40, (1024, 2048)), (8192, 40, (0, 128)),
-                                      (8192, 24, (384, 8192)), (24576, 40, None), (20480, 32, None),
+                                      (8192, 24, (384, 8192)), (24576, 40, None), (20480, 32, None), (4096, 37, None),
                                       (9344 * 2, 16, (0, 9344))])
 def test_phi_partitions_and_operand_modes(N, D, rows):
     """The tensor-core phi over every class of partition dust_phi_tc_plan produces (plain ranges for little work, column
