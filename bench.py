@@ -199,7 +199,7 @@ def run_ours(args, rank, world, local_rank):
     B = args.instances
     ctl = BatchedSVMPC(PendulumModel(), B, c["N"], c["S"], c["H"], c["ctrl_sigma"], c["prior_sigma"], alpha=c["alpha"],
                        learning_rate=c["lr"], kernel="gpytorch", inst_cost_fn=inst_cost, term_cost_fn=term_cost,
-                       device=dev, seed=1234 + rank)
+                       device=dev, seed=1234 + rank, prefetch_noise=not os.environ.get("DUST_BENCH_NO_PREFETCH"))
     g = ctl.gen
     state = (torch.rand(B, 2, device=dev, generator=g) * 2 - 1) * torch.tensor([3.14159, 1.0], device=dev)
     eps = ctl.draw_noise()  # resident in HBM for the `value` measurement
@@ -313,7 +313,8 @@ def run_ours(args, rank, world, local_rank):
         "data": "synthetic", "config": cfg, "rollouts_per_sec": value * c["N"] * c["S"] * c["P"],
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms_total / K,
                 "h2d_bytes_per_step": B * c["ds"] * 4, "d2h_bytes_per_step": B * c["A"] * 4,
-                "note": "state in (pinned host) -> action out (pinned host); noise drawn on the device inside the call"},
+                "note": "state in (pinned host) -> action out (pinned host); noise drawn on the device inside the call"
+                        + ("" if os.environ.get("DUST_BENCH_NO_PREFETCH") else "; the draw of step k + 1 is enqueued on a side stream while step k runs (BatchedSVMPC(prefetch_noise=True))")},
         "gpu_launches": launches, "kernel_ms_per_step": step_kernel_ms, "roofline": roof, "cpu_baseline": cpu,
         "clocks": clocks, "phi": phi, "configs": cfgs,
     }

@@ -12,7 +12,7 @@ class BatchedSVMPC:
     def __init__(self, model, n_instances, n_policies, action_samples, horizon, ctrl_sigma, prior_sigma,
                  alpha=1.0, learning_rate=1.0, kernel="gpytorch", inst_cost_fn=None, term_cost_fn=None,
                  weighted_prior=False, roll_strategy="repeat", grad="analytic", params_samples=0,
-                 device="cuda", seed=0, noise_stream=0):
+                 device="cuda", seed=0, noise_stream=0, prefetch_noise=False):
         L.require_cuda()
         self.device = torch.device(device)
         self.model = model
@@ -35,6 +35,14 @@ class BatchedSVMPC:
         self.eps = torch.empty(B, self.S, N, H, A, device=self.device)
         # action noise: the library's counter-based generator, one Philox stream per (rank, draw)
         self.seed, self.noise_stream, self.draws = int(seed), int(noise_stream), 0
+        # prefetch (control_step): the draw of the NEXT step is enqueued on a side stream while this step's kernel runs --
+        # it depends on nothing but the draw counter.  Two buffers alternate; events order fill -> use -> refill.
+        self.prefetch = bool(prefetch_noise)
+        self._side = torch.cuda.Stream(device=self.device) if self.prefetch else None   # a higher stream priority changes nothing (measured)
+        self._eps2 = [self.eps, torch.empty_like(self.eps)] if self.prefetch else None
+        self._filled = [None, None]        # event: buffer i holds the draw for the step that will use it
+        self._used = [None, None]          # event: the step that read buffer i has been enqueued and finished
+        self._next = 0
 
     @property
     def theta(self):
@@ -54,8 +62,35 @@ class BatchedSVMPC:
         """-> (a_seq [B,H,A], p_weights [B,N], i_star [B])"""
         return self.core.forward_step()
 
+    def _enqueue_fill(self, i):
+        """fill buffer i with the next draw on the side stream, after the step that last read it"""
+        with torch.cuda.stream(self._side):
+            if self._used[i] is not None:
+                self._side.wait_event(self._used[i])
+            ops.noise_normal(self._eps2[i], self.seed, (self.noise_stream << 40) + self.draws)
+            self.draws += 1
+            ev = torch.cuda.Event()
+            ev.record(self._side)
+            self._filled[i] = ev
+
     def control_step(self, state, eps=None, params=None):
-        """optimize + forward for every instance; returns the actions to apply [B,A]."""
+        """optimize + forward for every instance; returns the actions to apply [B,A].
+        With `prefetch_noise=True` (and no `eps` given) the same draws are made in the same order, one step ahead, on a
+        side stream: the fill of step k + 1 shares the GPU with the kernel of step k instead of preceding it."""
+        if eps is None and self.prefetch:
+            cur = torch.cuda.current_stream(self.device)
+            i = self._next
+            if self._filled[i] is None:
+                self._enqueue_fill(i)                      # first call: nothing was prefetched yet
+            cur.wait_event(self._filled[i])
+            self._filled[i] = None
+            self._enqueue_fill(1 - i)                      # the next step's draw, concurrent with this step's kernel
+            a_seq, _, _ = self.core.control_step(state, self._eps2[i], params)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._used[i] = ev
+            self._next = 1 - i
+            return a_seq[:, 0]
         eps = self.draw_noise() if eps is None else eps
         a_seq, _, _ = self.core.control_step(state, eps, params)
         return a_seq[:, 0]

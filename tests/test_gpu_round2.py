@@ -671,3 +671,23 @@ def test_two_pairs_per_lane_kernel_equals_the_default():
     assert torch.equal(quad["costs"], ref["costs"])
     assert rel_max(quad["log_lik"].cpu(), ref["log_lik"].cpu()) <= 1e-6
     assert rel_max(quad["grad_lik"].cpu(), ref["grad_lik"].cpu()) <= 1e-5
+
+
+def test_batched_controller_noise_prefetch_is_the_same_sequence():
+    """BatchedSVMPC(prefetch_noise=True): the action noise of step k + 1 is drawn on a side stream while step k runs
+    (likelihoods.py:97-103 draws it inside every call); same draws in the same order, hence the same actions."""
+    from dust_b200.batched import BatchedSVMPC
+    from dust_b200.models.pendulum import PendulumModel, inst_cost, term_cost
+
+    dev = torch.device(DEV)
+    mk = lambda pf: BatchedSVMPC(PendulumModel(), 96, 8, 64, 20, 2.0, 2.0, alpha=1.0, learning_rate=2.0, kernel="gpytorch",  # noqa: E731
+                                 inst_cost_fn=inst_cost, term_cost_fn=term_cost, device=dev, seed=11, prefetch_noise=pf)
+    a, b = mk(False), mk(True)
+    g = torch.Generator().manual_seed(2)
+    for step in range(5):
+        state = cu((torch.rand(96, 2, generator=g) * 2 - 1) * torch.tensor([3.0, 1.0]))
+        ua, ub = a.control_step(state).clone(), b.control_step(state).clone()
+        torch.cuda.synchronize()
+        assert torch.equal(ua, ub), step
+    assert torch.equal(a.theta, b.theta)
+    assert a.draws == 5 and b.draws == 6          # one draw ahead
