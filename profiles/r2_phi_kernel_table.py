@@ -60,6 +60,9 @@ lines += ["",
           "GEMM2 warp back to waiting for P 37 % of its time.  (6) keeps the scalar loop, writes the fma explicitly (ptxas had emitted "
           "s + s, two adds), and templates the kernel on its form so that neither the TF32 split nor the other form's MMAs are issued "
           "predicated-off: 96 registers.",
+          "Tried after (7) and withdrawn: the |x_j|^2 slices in a ring of their own (eight stages, filled by the X producer, recycled by the "
+          "softmax warps) so that the softmax warps do not wait for the V stage that carried them: 2.74 -> 2.85 ms on the main launch "
+          "(`gpurun_out/phi_r2k.ncu-rep`, scratch) -- the single producer thread now paces the X tiles.",
           "Two counters: `sm__pipe_tensor_cycles_active` (the one BASELINE names) is stable from capture to capture (86.1 / 86.4 % for the "
           "identical kernels of (6) and (7)); the `TriageCompute ... realtime` variant that round 1 quoted (54 %) is sampled and is not "
           "(80.4 vs 53.4 % for the same two captures): it is listed for continuity only.  Neither is a pure work counter -- (4) does the "
