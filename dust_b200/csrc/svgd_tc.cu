@@ -1,7 +1,8 @@
 // Large-N SVGD phi on the 5th-generation tensor cores (tcgen05 / TMEM), flash style: the Gram
-// tile S = X_i X_j^T and the products K [score | X | 1] run as 3xTF32 MMAs (hi*hi + hi*lo + lo*hi,
-// fp32 accumulation in TMEM) so float32 accuracy holds; exp and the hi/lo split of K happen in
-// registers between the two GEMMs and K is never materialised outside TMEM.
+// tile S = X_i X_j^T and the products K [score | X] run as 3xTF32 MMAs (hi*hi + hi*lo + lo*hi, fp32
+// accumulation in TMEM; the third term of the second GEMM, 2^-11 of the sum, on bf16 copies) so float32
+// accuracy holds; exp and the hi/lo split of K happen in registers between the two GEMMs and K is never
+// materialised outside TMEM.
 //
 //   phi_i = c1 * sum_j K_ij s_j + c2 * (x_i sum_j K_ij - sum_j K_ij x_j),  K_ij = exp(-gamma d2_ij),
 //   d2_ij = max(|x_i|^2 + |x_j|^2 - 2 x_i.x_j, 0)          (dust/inference/svgd.py:28-39, 92-99, 127-135)
@@ -9,19 +10,19 @@
 // At most one CTA per SM, resident for the whole launch; it works off an equal contiguous range of
 // (128-row tile, 64-column tile) pairs, segment by segment when the range crosses row tiles.  16 warps:
 //   warp 0      producer   cp.async.bulk (1-D TMA) of pre-tiled hi/lo operand images into smem rings
-//   warp 1      GEMM1 issuer (one elected thread): S[j % 2] = X_i X_j^T as soon as GEMM2(j-2) has consumed that buffer
+//   warp 1      GEMM1 issuer (one elected thread): S[j % 3] = X_i X_j^T as soon as GEMM2(j-3) has consumed that buffer
 //   warp 2      TMEM allocation, then GEMM2 issuer: O += P(j) V_j as soon as the softmax warps have written P(j)
 //   warp 3      producer of the V^T tiles
 //   warps 4-7   "softmax" warpgroup A: columns 0..31 of every tile  (tcgen05.ld S, exp, split, tcgen05.st P)
 //   warps 8-11  "softmax" warpgroup B: columns 32..63 of every tile
-//   warps 12-15 flush warpgroup: every kTcChunk column tiles the O accumulator is drained into
+//   warps 12-15 flush warpgroup: stages the row tile of a segment in TMEM; every kTcChunk column tiles the O accumulator is drained into
 //               round-to-nearest fp32 registers (the tensor core's own fp32 accumulation truncates:
 //               measured bias ~2e-8 per accumulation step, i.e. 5e-4 over the 24576 steps of
 //               N = 65536 if left in TMEM) and added to the segment's slot of a global scratch;
 //               phi_tc_finish_kernel sums the slots of a row tile and forms the phi rows.
-// TMEM columns (512 allocated): S/P_hi ring (P_hi overwrites the S it was computed from), P_lo[2], O[2] (2*NV columns)
-// and -- when 2*NV + 2*Dp <= 256 (d <= 40) -- the row tile itself, A_hi | A_lo (2*Dp columns): every MMA then reads
-// only its B operand from shared memory.  An SS-form 128x64x8 TF32 MMA fetches 6 KB of operands in its 32 cycles,
+// TMEM columns (512 allocated): S/P_hi ring of three (P_hi overwrites the S it was computed from), P_lo[2] (32 columns
+// each: two bf16 per column), O[2] (2*NV columns) and the row tile itself, A_hi | A_lo (2*Dp columns): every MMA reads
+// only its B operand from shared memory.  (phi_tc_kernel<false>: row tile in shared memory, P_lo in TF32, 64 columns.)  An SS-form 128x64x8 TF32 MMA fetches 6 KB of operands in its 32 cycles,
 // more than the 128 B/cycle the shared-memory port delivers (profiles/r2_phi_a_in_tmem.md).
 // Operands live in shared memory in the canonical K-major no-swizzle UMMA layout (8x16B core
 // matrices); the prep kernel writes global memory already in that order, so every tile is one
